@@ -1,0 +1,116 @@
+/* mitty_b200 -- C ABI of the B200-native read-generation engine (libmitty_b200.so).
+ *
+ * Drop-in boundary for Mitty's data-parallel hot path.  The reference (alenzhao/Mitty, pure
+ * Python) has no FFI; each entry point below names the reference call it replaces
+ * (paths relative to the reference repo) and INTEGRATION.md shows the ctypes binding a
+ * maintainer would add to mitty/simulation/{readgenerate,readcorrupt,illumina,rpc}.py.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * MG_E* code, with a message available from mg_last_error(); the caller owns all host buffers
+ * (pinned memory makes the copies asynchronous, pageable memory works); one mg_ctx per GPU and
+ * one host thread per mg_ctx; there is no global state and NO CPU fallback -- without a CUDA
+ * device mg_ctx_create fails.
+ */
+#ifndef MITTY_B200_H
+#define MITTY_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mg_ctx mg_ctx;
+
+#define MG_OK 0
+#define MG_ECUDA (-1)      /* CUDA runtime error                                   */
+#define MG_EINVAL (-2)     /* bad argument / unknown handle                        */
+#define MG_ECAP (-3)       /* caller buffer too small; needed size reported        */
+#define MG_EVALUE (-4)     /* input the reference would reject or cannot represent */
+#define MG_EINDEX (-5)     /* read longer than the model (IndexError, illumina.py:156) */
+
+#define MG_MODE_PHILOX_C 0 /* production: counter-based Philox4x32-10 draws on the device       */
+#define MG_MODE_DET_C 1    /* deterministic: the reference's numpy RandomState draws, from host  */
+#define MG_MODE_EXPLICIT_C 2 /* test hook: explicit template starts and lengths                 */
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* stream: a cudaStream_t to launch on (e.g. torch's current stream) or NULL for an own stream. */
+int mg_ctx_create(int device, void *stream, mg_ctx **out);
+void mg_ctx_destroy(mg_ctx *ctx);
+const char *mg_last_error(mg_ctx *ctx);
+int mg_synchronize(mg_ctx *ctx);
+
+/* ---- read model: illumina.read_model_params hand-off (mitty/simulation/illumina.py:12-40) ---
+ * cum_tlen f64[n_tlen]; cum_bq_mat f64[n_mates][n_cycles][n_bq]; phred_p f64[100] =
+ * 10**(-arange(100)/10) (illumina.py:137); rlen = model['mean_rlen'].                          */
+int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double *cum_bq_mat, int n_mates,
+                  int n_cycles, int n_bq, const double *phred_p, int rlen);
+
+/* ---- region: replaces fasta.fetch(chrom, start, end) + the str the worker keeps
+ * (mitty/simulation/readgenerate.py:186).  ref_bytes = the region's bases as in the FASTA
+ * (ASCII); bed_start = 0-based start.  The sequence is 2-bit packed on the device; runs of
+ * non-ACGT bytes (N, IUPAC, lower case) are kept as an exception list.                          */
+int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t bed_start, int64_t *region_id);
+int mg_region_free(mg_ctx *ctx, int64_t region_id);
+
+/* ---- chromosome copy: replaces rpc.create_node_list (mitty/simulation/rpc.py:38-116) and the
+ * p_min/p_max computation (readgenerate.py:192).  Variants of ONE copy in VCF order (output of
+ * vcfio.parse, mitty/lib/vcfio.py:105-126): pos 1-based, op 'X'/'I'/'D', oplen, ALT strings
+ * pooled as alt_pool[alt_off[i] .. alt_off[i+1]).  Builds the node table, the packed haplotype
+ * and the block lookup table in HBM.                                                           */
+int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *pos, const uint8_t *op,
+                  const int64_t *oplen, const uint8_t *alt_pool, const int64_t *alt_off, int64_t *copy_id,
+                  int64_t *p_min, int64_t *p_max, int64_t *n_nodes);
+int mg_copy_free(mg_ctx *ctx, int64_t copy_id);
+/* node table as the reference's Node tuples (rpc.py:5-35): arrays of n_nodes entries            */
+int mg_copy_nodes(mg_ctx *ctx, int64_t copy_id, int64_t *ps, int64_t *pr, uint8_t *op, int64_t *oplen);
+/* the copy's haplotype as ASCII (p_max - p_min bytes), read back from the packed device copy    */
+int mg_copy_haplotype(mg_ctx *ctx, int64_t copy_id, uint8_t *out, int64_t cap);
+
+/* ---- one work unit ------------------------------------------------------------------------- */
+typedef struct {
+  int64_t copy_id;
+  int64_t n_candidates;     /* int((p_max - p_min) * p * 1.2), illumina.py:69                    */
+  double p;                 /* per-base template probability (PHILOX mode gaps)                  */
+  int32_t mode;             /* MG_MODE_*_C                                                       */
+  uint32_t unit_seed;       /* rng_seed of the unit (readgenerate.py:150); Philox key            */
+  const int64_t *ts;        /* DET/EXPLICIT [n]: geometric(p).cumsum()+p_min+1, shuffled (illumina.py:70-71) */
+  const double *u_tlen;     /* DET [n]: tlen_rng.rand(n) (illumina.py:72)                        */
+  const int64_t *tl;        /* EXPLICIT [n]: template lengths                                    */
+  const int8_t *fo;         /* DET/EXPLICIT [n]: file_order_rng.randint(2, ...) (illumina.py:93), consumed in kept order */
+  const char *qname_prefix; /* "@<sample>:<worker_id>:<ps>:"  (readgenerate.py:195,210)          */
+  const char *qname_mid;    /* "|<chrom>|<cpy>"               (readgenerate.py:223)              */
+  int32_t corrupt;          /* 1: fuse Illumina corruption (PHILOX draws) into the emit kernel    */
+  uint32_t corrupt_seed;
+  int64_t p_min, p_max;     /* only read by mg_sample_templates when copy_id == 0 (plugin call
+                               generate_reads(model, p_min, p_max, seed) without a haplotype)      */
+} mg_unit_desc;
+
+/* replaces read_module.generate_reads (illumina.py:43-110): per candidate j the template start
+ * ts_out[j], end te_out[j] (-1 if te >= p_max) and, in PHILOX mode, the file-order bit.          */
+int mg_sample_templates(mg_ctx *ctx, const mg_unit_desc *d, int64_t *ts_out, int64_t *te_out, int8_t *fo_out);
+
+/* replaces the per-unit body of read_generating_worker + fastq_lines + writer
+ * (readgenerate.py:183-253).  Writes the unit's FASTQ records of file 1 / file 2 into out1 / out2
+ * (host buffers of `cap` bytes each; NULL,NULL keeps the result on the device only).
+ * n_bytes = bytes per file (both files always have the same size), n_templates = templates
+ * written, n_te_kept = templates that passed te < p_max.  MG_ECAP if cap < n_bytes.             */
+int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap,
+                     int64_t *n_bytes, int64_t *n_templates, int64_t *n_te_kept);
+
+/* ---- corrupt-reads: replaces readcorrupt.multi_process / illumina.corrupt_template
+ * (mitty/simulation/readcorrupt.py:18-118, illumina.py:113-162) over whole FASTQ buffers.
+ * in2/out2 may be NULL (single-end).  DET mode consumes the reference's draws: for read k (file-1
+ * read then file-2 read of each template) bq_rnd/call_rnd/base_rnd[draw_off[k] + cycle].          */
+int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_t *in2, int64_t len2, int32_t mode,
+                     uint32_t seed, const double *bq_rnd, const double *call_rnd, const uint8_t *base_rnd,
+                     const int64_t *draw_off, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *out_len1,
+                     int64_t *out_len2, int64_t *n_templates);
+
+/* ---- profiling: device time (CUDA events on the launch stream) of the emit / corrupt kernels -- */
+int mg_prof_reset(mg_ctx *ctx);
+int mg_prof_get(mg_ctx *ctx, double *emit_ms, int64_t *emit_launches, int64_t *emit_bytes, int64_t *total_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+"""Command line with the reference's ``generate-reads`` / ``corrupt-reads`` / ``qname`` commands
+(mitty/cli.py:106-157): same positional arguments and options, plus ``--deterministic`` (consume
+the reference's numpy draws; byte-exact against ``mitty ... --threads 1``) and, for
+generate-reads, ``--corrupt`` (fuse the corruption model into the emit kernel)."""
+import logging
+import os
+
+import click
+
+from mitty_b200.readmodels import builtin_models, get_read_model, load_model
+
+
+@click.group()
+@click.version_option()
+@click.option('-v', '--verbose', type=int, default=0)
+def cli(verbose):
+  """B200-native engine for Mitty's read generation and corruption"""
+  logging.basicConfig(level=[logging.ERROR, logging.WARNING, logging.INFO, logging.DEBUG][min(verbose, 3)])
+
+
+@cli.command('list-read-models')
+@click.option('-d', type=click.Path(exists=True), help='List models in this directory')
+def list_read_models(d):
+  """List read models"""
+  import glob
+  names = builtin_models() if d is None else glob.glob(os.path.join(d, '*'))
+  for name in names:
+    try:
+      mod_data = load_model(name)
+      click.echo('\n----------\n{}:\n{}\n=========='.format(os.path.basename(name), mod_data['model_description']))
+    except Exception:
+      logging.debug('Skipping {}. Not a read model file'.format(name))
+
+
+@cli.command()
+def qname():
+  """Display qname format"""
+  import mitty_b200.simulation.readgenerate as reads
+  click.echo(reads.__qname_format_details__)
+
+
+def print_qname(ctx, param, value):
+  import mitty_b200.simulation.readgenerate as reads
+  if not value or ctx.resilient_parsing:
+    return
+  click.echo(reads.__qname_format_details__)
+  ctx.exit()
+
+
+@cli.command('generate-reads', short_help='Generate simulated reads.')
+@click.argument('fasta')
+@click.argument('vcf')
+@click.argument('sample_name')
+@click.argument('bed')
+@click.argument('modelfile')
+@click.argument('coverage', type=float)
+@click.argument('seed', type=int)
+@click.argument('fastq1', type=click.Path())
+@click.option('--fastq2', type=click.Path())
+@click.option('--threads', default=2)
+@click.option('--qname', is_flag=True, callback=print_qname, expose_value=False, is_eager=True, help='Print documentation for information encoded in qname')
+@click.option('--deterministic', is_flag=True, help="Consume the reference's numpy draws: byte-exact vs `mitty generate-reads --threads 1`")
+@click.option('--corrupt', is_flag=True, help='Fuse the Illumina corruption model into read generation (Philox draws)')
+@click.option('--device', default=0, help='CUDA device')
+def generate_reads(fasta, vcf, sample_name, bed, modelfile, coverage, seed, fastq1, fastq2, threads, deterministic, corrupt, device):
+  """Generate simulated reads"""
+  import mitty_b200.simulation.readgenerate as reads
+  read_module, model = get_read_model(modelfile)
+  reads.process_multi_threaded(
+    fasta, vcf, sample_name, bed, read_module, model, coverage,
+    fastq1, fastq2, threads=threads, seed=seed,
+    mode='deterministic' if deterministic else 'philox', corrupt=corrupt, device=device)
+
+
+@cli.command('corrupt-reads', short_help='Apply corruption model to FASTQ file of reads')
+@click.argument('modelfile')
+@click.argument('fastq1_in', type=click.Path(exists=True))
+@click.argument('fastq1_out', type=click.Path())
+@click.argument('seed', type=int)
+@click.option('--fastq2-in', type=click.Path(exists=True))
+@click.option('--fastq2-out', type=click.Path())
+@click.option('--threads', default=2)
+@click.option('--deterministic', is_flag=True, help="Consume the reference's numpy draws: byte-exact vs `mitty corrupt-reads --threads 1`")
+@click.option('--device', default=0, help='CUDA device')
+def read_corruption(modelfile, fastq1_in, fastq1_out, seed, fastq2_in, fastq2_out, threads, deterministic, device):
+  """Apply corruption model to FASTQ file of reads"""
+  import mitty_b200.simulation.readcorrupt as rc
+  read_module, read_model = get_read_model(modelfile)
+  rc.multi_process(read_module, read_model, fastq1_in, fastq1_out, fastq2_in, fastq2_out, processes=threads, seed=seed,
+                   mode='deterministic' if deterministic else 'philox', device=device)
+
+
+if __name__ == '__main__':
+  cli()

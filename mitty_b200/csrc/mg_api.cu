@@ -1,0 +1,639 @@
+// C-ABI of the engine (include/mitty_b200.h): context, device-memory management, the host half
+// of the haplotype builder (the inherently sequential greedy variant walk of rpc.py:48-61) and
+// the launch sequences of the kernels in mg_kernels.cu.  No CPU fallback lives here.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mitty_b200.h"
+#include "mg_internal.h"
+
+namespace {
+
+struct DevBuf {  // grow-only device buffer
+  void *p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t need(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct ExcRun { int64_t start, len; uint8_t byte; };
+
+struct Region {
+  int64_t len = 0, bed_start = 0;
+  uint32_t *d_ref = nullptr;      // packed, with MG_HAP_PAD words of padding on both sides
+  std::vector<ExcRun> exc;        // non-ACGT runs, region-relative
+  ~Region() { if (d_ref) cudaFree(d_ref); }
+};
+
+struct HostNode { int64_t ps, pr, oplen; uint8_t op; };
+
+struct Copy {
+  int64_t region_id = 0;
+  int64_t p_min = 0, p_max = 0;
+  std::vector<HostNode> nodes;
+  std::vector<MgExc> exc;
+  MgNode *d_nodes = nullptr; uint32_t *d_hap = nullptr; uint32_t *d_blk = nullptr; MgExc *d_exc = nullptr;
+  int n_blk = 0; int64_t hap_words = 0;
+  ~Copy() { cudaFree(d_nodes); cudaFree(d_hap); cudaFree(d_blk); cudaFree(d_exc); }
+};
+
+const int BLK_SHIFT = 8;
+
+}  // namespace
+
+struct mg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  // model
+  DevBuf m_tlen, m_bq, m_phred;
+  int n_tlen = 0, n_mates = 0, n_cycles = 0, n_bq = 0, rlen = 0;
+  // handles
+  std::map<int64_t, std::unique_ptr<Region>> regions;
+  std::map<int64_t, std::unique_ptr<Copy>> copies;
+  int64_t next_id = 1;
+  // scratch
+  DevBuf s_raw, s_exc, s_ts, s_u, s_fo, s_tsorted, s_partial, s_state, s_out[2], s_str, s_qn, s_sample[3];
+  DevBuf c_in[2], c_out[2], c_nl[2], c_cnt, c_sz[2], c_off[2], c_tmp, c_draw[4];
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double emit_ms = 0; int64_t emit_launches = 0, emit_bytes = 0, total_launches = 0;
+};
+
+namespace {
+
+int fail(mg_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, MG_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int mg_ctx_create(int device, void *stream, mg_ctx **out) {
+  if (!out) return MG_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    fprintf(stderr, "mitty_b200: no usable CUDA device %d (%s); this engine has no CPU fallback\n", device,
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count");
+    return MG_ECUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return MG_ECUDA;
+  mg_ctx *ctx = new mg_ctx();
+  ctx->device = device;
+  if (stream) ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+  else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MG_ECUDA; } ctx->own_stream = true; }
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  *out = ctx;
+  return MG_OK;
+}
+
+void mg_ctx_destroy(mg_ctx *ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->regions.clear(); ctx->copies.clear();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *mg_last_error(mg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mg_synchronize(mg_ctx *ctx) {
+  if (!ctx) return MG_EINVAL;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MG_OK;
+}
+
+int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double *cum_bq_mat, int n_mates, int n_cycles,
+                  int n_bq, const double *phred_p, int rlen) {
+  if (!ctx || !cum_tlen || !cum_bq_mat || !phred_p || n_tlen <= 0 || n_mates < 1 || n_cycles <= 0 || n_bq <= 0 || rlen <= 0)
+    return fail(ctx, MG_EINVAL, "mg_model_load: bad arguments");
+  DeviceGuard g(ctx->device);
+  CU(ctx->m_tlen.need(sizeof(double) * n_tlen));
+  CU(ctx->m_bq.need(sizeof(double) * (size_t)n_mates * n_cycles * n_bq));
+  CU(ctx->m_phred.need(sizeof(double) * 100));
+  CU(cudaMemcpyAsync(ctx->m_tlen.p, cum_tlen, sizeof(double) * n_tlen, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->m_bq.p, cum_bq_mat, sizeof(double) * (size_t)n_mates * n_cycles * n_bq, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->m_phred.p, phred_p, sizeof(double) * 100, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->n_tlen = n_tlen; ctx->n_mates = n_mates; ctx->n_cycles = n_cycles; ctx->n_bq = n_bq; ctx->rlen = rlen;
+  return MG_OK;
+}
+
+// ---- region ---------------------------------------------------------------------------------
+
+int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t bed_start, int64_t *region_id) {
+  if (!ctx || !region_id || len < 0 || (len > 0 && !ref_bytes)) return fail(ctx, MG_EINVAL, "mg_region_load: bad arguments");
+  if (len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "region of %lld bases exceeds the 2^32 addressing of one region", (long long)len);
+  DeviceGuard g(ctx->device);
+  const uint32_t EXC_CAP = 1u << 20;
+  std::unique_ptr<Region> R(new Region());
+  R->len = len; R->bed_start = bed_start;
+  int64_t words = (len + 15) / 16;
+  CU(cudaMalloc(&R->d_ref, sizeof(uint32_t) * (words + 2 * MG_HAP_PAD)));
+  CU(cudaMemsetAsync(R->d_ref, 0, sizeof(uint32_t) * (words + 2 * MG_HAP_PAD), ctx->stream));
+  if (len > 0) {
+    CU(ctx->s_raw.need((size_t)len + 32));
+    // exception scratch: [cnt u32 x2 (padded to 16 B)][start i64 x cap][end i64 x cap][byte u8 x cap]
+    size_t exc_bytes = 16 + (size_t)EXC_CAP * 17;
+    CU(ctx->s_exc.need(exc_bytes));
+    uint8_t *eb = ctx->s_exc.as<uint8_t>();
+    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(eb);
+    int64_t *d_start = reinterpret_cast<int64_t *>(eb + 16);
+    int64_t *d_end = d_start + EXC_CAP;
+    uint8_t *d_byte = reinterpret_cast<uint8_t *>(d_end + EXC_CAP);
+    CU(cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_raw.p, ref_bytes, (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    mg_launch_pack_ref(ctx->s_raw.as<uint8_t>(), len, R->d_ref + MG_HAP_PAD, d_cnt, d_start, d_byte, d_end, EXC_CAP, ctx->stream);
+    ctx->total_launches++;
+    CU(cudaGetLastError());
+    uint32_t cnt[2];
+    CU(cudaMemcpyAsync(cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (cnt[0] != cnt[1]) return fail(ctx, MG_ECUDA, "internal: exception run starts (%u) != ends (%u)", cnt[0], cnt[1]);
+    if (cnt[0] > EXC_CAP)
+      return fail(ctx, MG_EVALUE, "reference has %u runs of non-ACGT bytes (limit %u): soft-masked (lower-case) references are not supported yet", cnt[0], EXC_CAP);
+    if (cnt[0]) {
+      std::vector<int64_t> st(cnt[0]), en(cnt[0]);
+      std::vector<uint8_t> by(cnt[0]);
+      CU(cudaMemcpy(st.data(), d_start, 8 * (size_t)cnt[0], cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(en.data(), d_end, 8 * (size_t)cnt[0], cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(by.data(), d_byte, (size_t)cnt[0], cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> order(cnt[0]);
+      for (uint32_t i = 0; i < cnt[0]; i++) order[i] = i;
+      std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return st[a] < st[b]; });
+      std::sort(en.begin(), en.end());
+      R->exc.resize(cnt[0]);
+      for (uint32_t i = 0; i < cnt[0]; i++) R->exc[i] = ExcRun{st[order[i]], en[i] - st[order[i]] + 1, by[order[i]]};
+    }
+  }
+  int64_t id = ctx->next_id++;
+  ctx->regions[id] = std::move(R);
+  *region_id = id;
+  return MG_OK;
+}
+
+int mg_region_free(mg_ctx *ctx, int64_t region_id) {
+  if (!ctx) return MG_EINVAL;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  return ctx->regions.erase(region_id) ? MG_OK : fail(ctx, MG_EINVAL, "unknown region %lld", (long long)region_id);
+}
+
+// ---- chromosome copy --------------------------------------------------------------------------
+
+int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *pos, const uint8_t *op, const int64_t *oplen,
+                  const uint8_t *alt_pool, const int64_t *alt_off, int64_t *copy_id, int64_t *p_min, int64_t *p_max,
+                  int64_t *n_nodes) {
+  if (!ctx || !copy_id || n_var < 0 || (n_var > 0 && (!pos || !op || !oplen || !alt_pool || !alt_off)))
+    return fail(ctx, MG_EINVAL, "mg_copy_build: bad arguments");
+  auto it = ctx->regions.find(region_id);
+  if (it == ctx->regions.end()) return fail(ctx, MG_EINVAL, "unknown region %lld", (long long)region_id);
+  DeviceGuard g(ctx->device);
+  Region &R = *it->second;
+  std::unique_ptr<Copy> C(new Copy());
+  C->region_id = region_id;
+
+  // -- the greedy walk (rpc.py:48-61).  src: bit 63 set -> byte offset in the alt pool, else base
+  //    offset in the region's reference.
+  const int64_t start1 = R.bed_start + 1;            // ref_start_pos, readgenerate.py:190
+  int64_t samp = start1, refp = start1;
+  std::vector<uint64_t> src;                          // per node
+  auto push = [&](int64_t ps, int64_t pr, uint8_t o, int64_t ol, uint64_t s) {
+    C->nodes.push_back(HostNode{ps, pr, ol, o}); src.push_back(s);
+  };
+  const uint64_t ALT = 1ull << 63;
+  for (int64_t i = 0; i < n_var; i++) {
+    const int64_t vp = pos[i];
+    if (vp < refp) continue;                          // rpc.py:55
+    if (op[i] == 'X') {                               // rpc.py:75-87
+      int64_t delta = vp - refp;
+      if (delta > 0) { push(samp, refp, '=', delta, (uint64_t)(refp - start1)); refp = vp; samp += delta; }
+      if (alt_off[i + 1] - alt_off[i] != 1) return fail(ctx, MG_EVALUE, "SNP at %lld has an ALT of length %lld", (long long)vp, (long long)(alt_off[i + 1] - alt_off[i]));
+      push(samp, refp, 'X', 1, ALT | (uint64_t)alt_off[i]);
+      refp += 1; samp += 1;
+    } else if (op[i] == 'I') {                        // rpc.py:90-102
+      int64_t delta = vp + 1 - refp;
+      if (delta > 0) { push(samp, refp, '=', delta, (uint64_t)(refp - start1)); samp += delta; }
+      refp = vp + 1;
+      if (alt_off[i + 1] - alt_off[i] - 1 != oplen[i]) return fail(ctx, MG_EVALUE, "insertion at %lld: oplen %lld does not match its ALT", (long long)vp, (long long)oplen[i]);
+      push(samp, refp, 'I', oplen[i], ALT | (uint64_t)(alt_off[i] + 1));
+      samp += oplen[i];
+    } else if (op[i] == 'D') {                        // rpc.py:105-116
+      int64_t delta = vp + 1 - refp;
+      if (delta > 0) { push(samp, refp, '=', delta, (uint64_t)(refp - start1)); samp += delta; }
+      refp = vp + 1 + oplen[i];
+      push(samp - 1, refp, 'D', oplen[i], 0);
+    } else {
+      return fail(ctx, MG_EVALUE, "variant %lld has op %d (expected X, I or D)", (long long)i, (int)op[i]);
+    }
+  }
+  const int64_t offset = refp - start1;               // rpc.py:58-61
+  if (offset <= R.len) push(samp, refp, '=', R.len - offset, (uint64_t)offset);
+  if (C->nodes.empty() || C->nodes.back().op == 'D')
+    return fail(ctx, MG_EVALUE, "a deletion crosses the end of the region: the reference's node list would end in 'D' "
+                "(readgenerate.py:192 assumes it never does); trim the BED region or the VCF");
+  for (size_t k = 0; k < C->nodes.size(); k++) {
+    const HostNode &nd = C->nodes[k];
+    if (nd.op == '=' && (int64_t)src[k] + nd.oplen > R.len)
+      return fail(ctx, MG_EVALUE, "variant beyond the end of the region at reference position %lld", (long long)nd.pr);
+  }
+  C->p_min = C->nodes.front().ps;                     // readgenerate.py:192
+  C->p_max = C->nodes.back().ps + C->nodes.back().oplen;
+  const int64_t hap_len = C->p_max - C->p_min;
+  if (hap_len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "haplotype of %lld bases exceeds 2^32", (long long)hap_len);
+  if (C->nodes.back().pr + C->nodes.back().oplen >= (1ll << 31)) return fail(ctx, MG_EVALUE, "reference positions beyond 2^31 are not supported");
+
+  // -- device node table, segments for the haplotype kernel, exception runs in sample space
+  const size_t nn = C->nodes.size();
+  std::vector<MgNode> dn(nn);
+  std::vector<uint32_t> seg_start; std::vector<uint64_t> seg_src;
+  size_t rx = 0;                                      // cursor into the region's exception runs
+  auto add_exc = [&](int64_t s, int64_t l, uint8_t b) {
+    if (!C->exc.empty()) { MgExc &e = C->exc.back(); if ((int64_t)e.start + e.len == s && e.byte == b) { e.len += (uint32_t)l; return; } }
+    C->exc.push_back(MgExc{(uint32_t)s, (uint32_t)l, b, 0});
+  };
+  for (size_t k = 0; k < nn; k++) {
+    const HostNode &nd = C->nodes[k];
+    const int64_t rel = nd.ps - C->p_min;
+    dn[k].key = (uint32_t)(rel + (nd.op == 'D' ? 1 : 0));   // rpc.py:127
+    dn[k].pr = (int32_t)nd.pr; dn[k].oplen = (int32_t)nd.oplen; dn[k].op = nd.op;
+    if (nd.oplen > INT32_MAX) return fail(ctx, MG_EVALUE, "node longer than 2^31");
+    if (nd.op == 'D' || nd.oplen == 0) continue;
+    seg_start.push_back((uint32_t)rel); seg_src.push_back(src[k]);
+    if (nd.op == '=') {
+      const int64_t a = (int64_t)src[k], b = a + nd.oplen;
+      while (rx < R.exc.size() && R.exc[rx].start + R.exc[rx].len <= a) rx++;
+      for (size_t q = rx; q < R.exc.size() && R.exc[q].start < b; q++) {
+        int64_t s = std::max(a, R.exc[q].start), e = std::min(b, R.exc[q].start + R.exc[q].len);
+        if (e > s) add_exc(rel + (s - a), e - s, R.exc[q].byte);
+      }
+    } else {
+      const uint8_t *alt = alt_pool + (src[k] & ~ALT);
+      for (int64_t q = 0; q < nd.oplen; q++)
+        if (mg_base_code(alt[q]) > 3) add_exc(rel + q, 1, alt[q]);
+    }
+  }
+
+  // -- upload + device builds
+  const int64_t alt_bytes = n_var ? alt_off[n_var] : 0;
+  C->hap_words = (hap_len + 15) / 16;
+  C->n_blk = (int)((hap_len >> BLK_SHIFT) + 1);
+  CU(cudaMalloc(&C->d_nodes, sizeof(MgNode) * nn));
+  CU(cudaMalloc(&C->d_hap, sizeof(uint32_t) * (C->hap_words + 2 * MG_HAP_PAD)));
+  CU(cudaMalloc(&C->d_blk, sizeof(uint32_t) * C->n_blk));
+  CU(cudaMalloc(&C->d_exc, sizeof(MgExc) * std::max<size_t>(1, C->exc.size())));
+  CU(cudaMemcpyAsync(C->d_nodes, dn.data(), sizeof(MgNode) * nn, cudaMemcpyHostToDevice, ctx->stream));
+  if (!C->exc.empty()) CU(cudaMemcpyAsync(C->d_exc, C->exc.data(), sizeof(MgExc) * C->exc.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(C->d_hap, 0, sizeof(uint32_t) * (C->hap_words + 2 * MG_HAP_PAD), ctx->stream));
+  const size_t ns = seg_start.size();
+  if (ns && hap_len > 0) {
+    // scratch layout: [seg_src u64 x ns][seg_start u32 x ns][alt bytes]
+    size_t o_start = 8 * ns, o_alt = o_start + ((4 * ns + 15) & ~(size_t)15);
+    CU(ctx->s_str.need(o_alt + (size_t)alt_bytes + 16));
+    uint8_t *sb = ctx->s_str.as<uint8_t>();
+    CU(cudaMemcpyAsync(sb, seg_src.data(), 8 * ns, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(sb + o_start, seg_start.data(), 4 * ns, cudaMemcpyHostToDevice, ctx->stream));
+    if (alt_bytes) CU(cudaMemcpyAsync(sb + o_alt, alt_pool, (size_t)alt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    mg_launch_hap_build(R.d_ref + MG_HAP_PAD, sb + o_alt, reinterpret_cast<uint32_t *>(sb + o_start),
+                        reinterpret_cast<uint64_t *>(sb), (int)ns, (uint32_t)hap_len, C->d_hap + MG_HAP_PAD, C->hap_words, ctx->stream);
+    ctx->total_launches++;
+  }
+  mg_launch_blk_table(C->d_nodes, (int)nn, C->d_blk, C->n_blk, BLK_SHIFT, ctx->stream);
+  ctx->total_launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));   // host vectors above go out of scope
+
+  int64_t id = ctx->next_id++;
+  if (p_min) *p_min = C->p_min;
+  if (p_max) *p_max = C->p_max;
+  if (n_nodes) *n_nodes = (int64_t)nn;
+  ctx->copies[id] = std::move(C);
+  *copy_id = id;
+  return MG_OK;
+}
+
+int mg_copy_free(mg_ctx *ctx, int64_t copy_id) {
+  if (!ctx) return MG_EINVAL;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  return ctx->copies.erase(copy_id) ? MG_OK : fail(ctx, MG_EINVAL, "unknown copy %lld", (long long)copy_id);
+}
+
+int mg_copy_nodes(mg_ctx *ctx, int64_t copy_id, int64_t *ps, int64_t *pr, uint8_t *op, int64_t *oplen) {
+  if (!ctx) return MG_EINVAL;
+  auto it = ctx->copies.find(copy_id);
+  if (it == ctx->copies.end()) return fail(ctx, MG_EINVAL, "unknown copy %lld", (long long)copy_id);
+  const Copy &C = *it->second;
+  for (size_t k = 0; k < C.nodes.size(); k++) { ps[k] = C.nodes[k].ps; pr[k] = C.nodes[k].pr; op[k] = C.nodes[k].op; oplen[k] = C.nodes[k].oplen; }
+  return MG_OK;
+}
+
+int mg_copy_haplotype(mg_ctx *ctx, int64_t copy_id, uint8_t *out, int64_t cap) {
+  if (!ctx || !out) return MG_EINVAL;
+  auto it = ctx->copies.find(copy_id);
+  if (it == ctx->copies.end()) return fail(ctx, MG_EINVAL, "unknown copy %lld", (long long)copy_id);
+  DeviceGuard g(ctx->device);
+  const Copy &C = *it->second;
+  const int64_t n = C.p_max - C.p_min;
+  if (cap < n) return fail(ctx, MG_ECAP, "haplotype needs %lld bytes", (long long)n);
+  std::vector<uint32_t> w((size_t)C.hap_words);
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (C.hap_words) CU(cudaMemcpy(w.data(), C.d_hap + MG_HAP_PAD, 4 * (size_t)C.hap_words, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; i++) out[i] = (uint8_t)("ACGT"[(w[i >> 4] >> (2 * (i & 15))) & 3]);
+  for (const MgExc &e : C.exc) for (uint32_t q = 0; q < e.len; q++) out[e.start + q] = (uint8_t)e.byte;
+  return MG_OK;
+}
+
+// ---- work units -----------------------------------------------------------------------------------
+
+static int fill_unit_params(mg_ctx *ctx, const mg_unit_desc *d, MgUnitParams &P, const Copy **copy_out, bool sample_only) {
+  if (!d) return fail(ctx, MG_EINVAL, "null unit descriptor");
+  if (ctx->rlen == 0) return fail(ctx, MG_EINVAL, "no read model loaded (mg_model_load)");
+  if (d->n_candidates < 0 || d->n_candidates >= (1ll << 31)) return fail(ctx, MG_EVALUE, "n_candidates %lld out of range", (long long)d->n_candidates);
+  memset(&P, 0, sizeof P);
+  *copy_out = nullptr;
+  if (sample_only && d->copy_id == 0) {
+    if (d->p_max < d->p_min || d->p_max - d->p_min >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "p_min/p_max span out of range");
+    P.hap_len = (uint32_t)(d->p_max - d->p_min); P.p_min = d->p_min;
+  } else {
+    auto it = ctx->copies.find(d->copy_id);
+    if (it == ctx->copies.end()) return fail(ctx, MG_EINVAL, "unknown copy %lld", (long long)d->copy_id);
+    const Copy &C = *it->second;
+    *copy_out = &C;
+    P.hap = C.d_hap + MG_HAP_PAD; P.hap_len = (uint32_t)(C.p_max - C.p_min); P.p_min = C.p_min;
+    P.nodes = C.d_nodes; P.n_nodes = (int)C.nodes.size();
+    P.blk = C.d_blk; P.blk_shift = BLK_SHIFT; P.n_blk = C.n_blk;
+    P.exc = C.d_exc; P.n_exc = (int)C.exc.size();
+  }
+  P.cum_tlen = ctx->m_tlen.as<double>(); P.n_tlen = ctx->n_tlen; P.rlen = ctx->rlen;
+  P.mode = d->mode; P.n_cand = (uint32_t)d->n_candidates;
+  const size_t n = (size_t)d->n_candidates;
+  if (d->mode == MG_MODE_PHILOX) {
+    if (!(d->p > 0.0 && d->p < 1.0)) return fail(ctx, MG_EINVAL, "PHILOX mode needs 0 < p < 1");
+    if (n) {
+      CU(ctx->s_tsorted.need(4 * n + 64));
+      CU(ctx->s_partial.need(8 * (n / 2048 + 2)));
+      mg_launch_gap_scan((uint32_t)n, d->p, d->unit_seed, 0x67617031u, ctx->s_tsorted.as<uint32_t>(),
+                         ctx->s_partial.as<unsigned long long>(), ctx->stream);
+      ctx->total_launches += 3;
+    }
+    P.ts_sorted = ctx->s_tsorted.as<uint32_t>();
+    P.key_tlen0 = d->unit_seed; P.key_tlen1 = 0x746c6531u;
+    P.key_perm0 = d->unit_seed ^ 0x7368756bu; P.key_perm1 = d->unit_seed * 0x9E3779B1u + 0x66656973u;
+    uint32_t bits = 2;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)std::max<size_t>(n, 2)) bits++;
+    if (bits & 1) bits++;
+    P.half_bits = bits / 2;
+  } else if (d->mode == MG_MODE_DET || d->mode == MG_MODE_EXPLICIT) {
+    if (n && (!d->ts || (!d->fo && !sample_only) || (d->mode == MG_MODE_DET ? !d->u_tlen : !d->tl))) return fail(ctx, MG_EINVAL, "deterministic mode needs ts, fo and u_tlen/tl arrays");
+    if (n) {
+      CU(ctx->s_ts.need(8 * n)); CU(ctx->s_u.need(8 * n)); CU(ctx->s_fo.need(n));
+      CU(cudaMemcpyAsync(ctx->s_ts.p, d->ts, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->s_u.p, d->mode == MG_MODE_DET ? (const void *)d->u_tlen : (const void *)d->tl, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+      if (d->fo) CU(cudaMemcpyAsync(ctx->s_fo.p, d->fo, n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    P.ts_in = ctx->s_ts.as<int64_t>();
+    if (d->mode == MG_MODE_DET) P.u_tlen = ctx->s_u.as<double>(); else P.tl_in = ctx->s_u.as<int64_t>();
+    P.fo_in = ctx->s_fo.as<int8_t>();
+  } else {
+    return fail(ctx, MG_EINVAL, "unknown mode %d", d->mode);
+  }
+  return MG_OK;
+}
+
+int mg_sample_templates(mg_ctx *ctx, const mg_unit_desc *d, int64_t *ts_out, int64_t *te_out, int8_t *fo_out) {
+  if (!ctx || !ts_out || !te_out || !fo_out) return fail(ctx, MG_EINVAL, "mg_sample_templates: bad arguments");
+  DeviceGuard g(ctx->device);
+  MgSampleParams S; const Copy *C;
+  int rc = fill_unit_params(ctx, d, S.u, &C, true);
+  if (rc) return rc;
+  const size_t n = (size_t)d->n_candidates;
+  if (!n) return MG_OK;
+  CU(ctx->s_sample[0].need(8 * n)); CU(ctx->s_sample[1].need(8 * n)); CU(ctx->s_sample[2].need(n));
+  S.ts_out = ctx->s_sample[0].as<int64_t>(); S.te_out = ctx->s_sample[1].as<int64_t>(); S.fo_out = ctx->s_sample[2].as<int8_t>();
+  mg_launch_sample(S, ctx->stream);
+  ctx->total_launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ts_out, S.ts_out, 8 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(te_out, S.te_out, 8 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(fo_out, S.fo_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MG_OK;
+}
+
+int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *n_bytes,
+                     int64_t *n_templates, int64_t *n_te_kept) {
+  if (!ctx) return MG_EINVAL;
+  DeviceGuard g(ctx->device);
+  MgUnitParams P; const Copy *C;
+  int rc = fill_unit_params(ctx, d, P, &C, false);
+  if (rc) return rc;
+  if (!d->qname_prefix || !d->qname_mid) return fail(ctx, MG_EINVAL, "qname_prefix / qname_mid missing");
+  if (d->corrupt && d->mode != MG_MODE_PHILOX) return fail(ctx, MG_EINVAL, "fused corruption draws from Philox: use mg_corrupt_fastq for deterministic mode");
+  if (d->corrupt && ctx->rlen > ctx->n_cycles) return fail(ctx, MG_EINDEX, "read length %d exceeds the model's %d cycles", ctx->rlen, ctx->n_cycles);
+  if (d->corrupt && ctx->n_mates < 2) return fail(ctx, MG_EINVAL, "paired corruption needs a 2-mate model");
+  const size_t n = (size_t)d->n_candidates;
+  const int pl = (int)strlen(d->qname_prefix), ml = (int)strlen(d->qname_mid);
+  const int L = ctx->rlen;
+
+  // qname constants
+  DevBuf &strb = ctx->s_qn;
+  CU(strb.need((size_t)pl + ml + 32));
+  CU(cudaMemcpyAsync(strb.p, d->qname_prefix, pl, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(strb.as<uint8_t>() + pl, d->qname_mid, ml, cudaMemcpyHostToDevice, ctx->stream));
+  P.prefix = strb.as<uint8_t>(); P.prefix_len = pl; P.mid = strb.as<uint8_t>() + pl; P.mid_len = ml;
+
+  P.corrupt = d->corrupt; P.cum_bq = ctx->m_bq.as<double>(); P.n_cycles = ctx->n_cycles; P.n_bq = ctx->n_bq;
+  P.phred = ctx->m_phred.as<double>(); P.key_cor0 = d->corrupt_seed; P.key_cor1 = d->unit_seed ^ 0x636f7231u;
+
+  P.n_tiles = (int)((n + MG_TILE - 1) / MG_TILE);
+  int stage = MG_TILE * (2 * L + 80);
+  if (stage > 160 * 1024) stage = 160 * 1024;
+  P.stage_cap = stage & ~15;
+  int smem = 0;
+  const int grid = mg_unit_grid(P.stage_cap, P.n_tlen, &smem);
+
+  // scan state: [totals 4 x u64][tile counter (16 B)][descA][descB]
+  const size_t state_bytes = 48 + 16 * (size_t)std::max(P.n_tiles, 1);
+  CU(ctx->s_state.need(state_bytes));
+  uint8_t *sb = ctx->s_state.as<uint8_t>();
+  P.totals = reinterpret_cast<unsigned long long *>(sb);
+  P.tile_counter = reinterpret_cast<uint32_t *>(sb + 32);
+  P.descA = reinterpret_cast<unsigned long long *>(sb + 48);
+  P.descB = P.descA + std::max(P.n_tiles, 1);
+
+  // device output buffers: sized from an estimate, regrown to the exact size on overflow
+  size_t est = n * (size_t)(2 * L + 5 + pl + ml + 12 + 2 * 36) + 4096;
+  const bool want_out = (out1 != nullptr) || (out2 != nullptr);
+  unsigned long long tot[4] = {0, 0, 0, 0};
+  for (int attempt = 0; attempt < 2; attempt++) {
+    CU(ctx->s_out[0].need(est)); CU(ctx->s_out[1].need(est));
+    P.out[0] = ctx->s_out[0].as<uint8_t>(); P.out[1] = ctx->s_out[1].as<uint8_t>();
+    P.cap = std::min(ctx->s_out[0].cap, ctx->s_out[1].cap);
+    CU(cudaMemsetAsync(sb, 0, state_bytes, ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    mg_launch_unit(P, grid, smem, ctx->stream);
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(tot, P.totals, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (P.n_tiles) {
+      float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      ctx->emit_ms += ms; ctx->emit_launches++; ctx->total_launches++;
+      ctx->emit_bytes += 2 * (int64_t)tot[2];
+    }
+    if (!tot[3]) break;
+    if (attempt == 1) return fail(ctx, MG_ECUDA, "internal: output overflow after regrow");
+    est = (size_t)tot[2] + 4096;
+  }
+  if (n_bytes) *n_bytes = (int64_t)tot[2];
+  if (n_templates) *n_templates = (int64_t)tot[1];
+  if (n_te_kept) *n_te_kept = (int64_t)tot[0];
+  if (want_out) {
+    if ((int64_t)tot[2] > cap) return fail(ctx, MG_ECAP, "output needs %lld bytes per file, caller gave %lld", (long long)tot[2], (long long)cap);
+    if (out1 && tot[2]) CU(cudaMemcpyAsync(out1, P.out[0], (size_t)tot[2], cudaMemcpyDeviceToHost, ctx->stream));
+    if (out2 && tot[2]) CU(cudaMemcpyAsync(out2, P.out[1], (size_t)tot[2], cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return MG_OK;
+}
+
+// ---- corrupt-reads ---------------------------------------------------------------------------------
+
+int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_t *in2, int64_t len2, int32_t mode,
+                     uint32_t seed, const double *bq_rnd, const double *call_rnd, const uint8_t *base_rnd,
+                     const int64_t *draw_off, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *out_len1,
+                     int64_t *out_len2, int64_t *n_templates) {
+  if (!ctx || !in1 || len1 < 0 || (in2 && len2 < 0)) return fail(ctx, MG_EINVAL, "mg_corrupt_fastq: bad arguments");
+  if (ctx->rlen == 0) return fail(ctx, MG_EINVAL, "no read model loaded (mg_model_load)");
+  if (mode != MG_MODE_PHILOX && mode != MG_MODE_DET) return fail(ctx, MG_EINVAL, "unknown mode %d", mode);
+  DeviceGuard g(ctx->device);
+  const int nf = in2 ? 2 : 1;
+  if (nf > ctx->n_mates) return fail(ctx, MG_EINVAL, "paired corruption needs a 2-mate model");
+  const uint8_t *in[2] = {in1, in2}; const int64_t len[2] = {len1, len2};
+  MgCorruptParams P; memset(&P, 0, sizeof P);
+  int64_t n_lines[2] = {0, 0};
+  for (int f = 0; f < nf; f++) {
+    CU(ctx->c_in[f].need((size_t)len[f] + 16));
+    if (len[f]) CU(cudaMemcpyAsync(ctx->c_in[f].p, in[f], (size_t)len[f], cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t chunks = mg_nl_chunks(len[f]);
+    CU(ctx->c_cnt.need(8 * (size_t)(2 * chunks + 4)));
+    CU(ctx->c_tmp.need(8 * (size_t)mg_scan_tmp_elems(std::max<int64_t>(chunks, 1))));
+    int64_t *cnt = ctx->c_cnt.as<int64_t>(), *off = cnt + chunks + 1;
+    mg_launch_nl_count(ctx->c_in[f].as<uint8_t>(), len[f], cnt, ctx->stream);
+    mg_launch_scan_i64(cnt, off, chunks, ctx->c_tmp.as<int64_t>(), ctx->stream);
+    CU(cudaMemcpyAsync(&n_lines[f], off + chunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(ctx->c_nl[f].need(8 * (size_t)(n_lines[f] + 1)));
+    mg_launch_nl_write(ctx->c_in[f].as<uint8_t>(), len[f], off, ctx->c_nl[f].as<int64_t>(), ctx->stream);
+    ctx->total_launches += 5;
+    CU(cudaGetLastError());
+    P.in[f] = ctx->c_in[f].as<uint8_t>(); P.nl[f] = ctx->c_nl[f].as<int64_t>();
+  }
+  int64_t n_rec = n_lines[0] / 4;                                   // zip() of the two readers, readcorrupt.py:53
+  if (nf == 2) n_rec = std::min(n_rec, n_lines[1] / 4);
+  P.n_rec = n_rec; P.n_files = nf;
+  P.cum_bq = ctx->m_bq.as<double>(); P.n_cycles = ctx->n_cycles; P.n_bq = ctx->n_bq; P.phred = ctx->m_phred.as<double>();
+  P.mode = mode; P.key0 = seed; P.key1 = 0x636f7232u;
+  if (out_len1) *out_len1 = 0;
+  if (out_len2) *out_len2 = 0;
+  if (n_templates) *n_templates = n_rec;
+  if (n_rec == 0) return MG_OK;
+
+  CU(ctx->s_state.need(64));
+  P.err = ctx->s_state.as<unsigned long long>();
+  CU(cudaMemsetAsync(P.err, 0, 8, ctx->stream));
+  CU(ctx->c_tmp.need(8 * (size_t)mg_scan_tmp_elems(n_rec)));
+  for (int f = 0; f < nf; f++) { CU(ctx->c_sz[f].need(8 * (size_t)n_rec)); CU(ctx->c_off[f].need(8 * (size_t)(n_rec + 1))); }
+  mg_launch_corrupt_sizes(P, ctx->c_sz[0].as<int64_t>(), nf > 1 ? ctx->c_sz[1].as<int64_t>() : nullptr, ctx->stream);
+  int64_t total[2] = {0, 0};
+  for (int f = 0; f < nf; f++) {
+    mg_launch_scan_i64(ctx->c_sz[f].as<int64_t>(), ctx->c_off[f].as<int64_t>(), n_rec, ctx->c_tmp.as<int64_t>(), ctx->stream);
+    CU(cudaMemcpyAsync(&total[f], ctx->c_off[f].as<int64_t>() + n_rec, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    P.out_off[f] = ctx->c_off[f].as<int64_t>();
+    ctx->total_launches += 3;
+  }
+  unsigned long long err = 0;
+  CU(cudaMemcpyAsync(&err, P.err, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (err) return fail(ctx, MG_EINDEX, "a read is longer than the model's %d cycles (IndexError in the reference, illumina.py:156)", ctx->n_cycles);
+  if (out_len1) *out_len1 = total[0];
+  if (out_len2) *out_len2 = total[1];
+  if (std::max(total[0], total[1]) > cap) return fail(ctx, MG_ECAP, "output needs %lld bytes, caller gave %lld", (long long)std::max(total[0], total[1]), (long long)cap);
+  for (int f = 0; f < nf; f++) { CU(ctx->c_out[f].need((size_t)total[f] + 16)); P.out[f] = ctx->c_out[f].as<uint8_t>(); }
+
+  if (mode == MG_MODE_DET) {
+    if (!bq_rnd || !call_rnd || !base_rnd || !draw_off) return fail(ctx, MG_EINVAL, "deterministic mode needs the draw arrays");
+    const int64_t n_reads = n_rec * nf;
+    const int64_t n_draws = draw_off[n_reads];
+    CU(ctx->c_draw[0].need(8 * (size_t)n_draws + 8)); CU(ctx->c_draw[1].need(8 * (size_t)n_draws + 8));
+    CU(ctx->c_draw[2].need((size_t)n_draws + 8)); CU(ctx->c_draw[3].need(8 * (size_t)(n_reads + 1)));
+    CU(cudaMemcpyAsync(ctx->c_draw[0].p, bq_rnd, 8 * (size_t)n_draws, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->c_draw[1].p, call_rnd, 8 * (size_t)n_draws, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->c_draw[2].p, base_rnd, (size_t)n_draws, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->c_draw[3].p, draw_off, 8 * (size_t)(n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
+    P.bq_rnd = ctx->c_draw[0].as<double>(); P.call_rnd = ctx->c_draw[1].as<double>();
+    P.base_rnd = ctx->c_draw[2].as<uint8_t>(); P.draw_off = ctx->c_draw[3].as<int64_t>();
+  }
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  mg_launch_corrupt(P, ctx->stream);
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(cudaGetLastError());
+  if (out1) CU(cudaMemcpyAsync(out1, P.out[0], (size_t)total[0], cudaMemcpyDeviceToHost, ctx->stream));
+  if (nf > 1 && out2) CU(cudaMemcpyAsync(out2, P.out[1], (size_t)total[1], cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->emit_ms += ms; ctx->emit_launches++; ctx->total_launches++;
+  ctx->emit_bytes += 2 * (total[0] + total[1]);
+  return MG_OK;
+}
+
+int mg_prof_reset(mg_ctx *ctx) {
+  if (!ctx) return MG_EINVAL;
+  ctx->emit_ms = 0; ctx->emit_launches = 0; ctx->emit_bytes = 0; ctx->total_launches = 0;
+  return MG_OK;
+}
+
+int mg_prof_get(mg_ctx *ctx, double *emit_ms, int64_t *emit_launches, int64_t *emit_bytes, int64_t *total_launches) {
+  if (!ctx) return MG_EINVAL;
+  if (emit_ms) *emit_ms = ctx->emit_ms;
+  if (emit_launches) *emit_launches = ctx->emit_launches;
+  if (emit_bytes) *emit_bytes = ctx->emit_bytes;
+  if (total_launches) *total_launches = ctx->total_launches;
+  return MG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,470 @@
+// Per-thread logic of the read-generation engine, shared by every kernel.
+//
+// Everything here is __host__ __device__ and free of CUDA-only constructs so that
+// tests/emul/ can compile the very same code with g++ and check it against the oracle on
+// the build box (which has no GPU).  The product never runs these on the CPU: the only
+// product callers are the kernels in mg_kernels.cu.
+//
+// Reference semantics restated (paths under /root/reference):
+//   node lookup      rpc.get_begin_end_nodes   mitty/simulation/rpc.py:119-130
+//   pos/cigar/v_list rpc.generate_read         mitty/simulation/rpc.py:133-160
+//   qname / record   readgenerate.fastq_lines  mitty/simulation/readgenerate.py:222-230
+//   N filter/revcomp read_generating_worker    mitty/simulation/readgenerate.py:198-210
+//   corruption       illumina.corrupt_single_read  mitty/simulation/illumina.py:131-162
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MG_HD __host__ __device__ __forceinline__
+#else
+#define MG_HD inline
+#endif
+
+// ------------------------------------------------------------------------------------------
+// Data layout in HBM
+
+// One node of a chromosome copy (rpc.Node, rpc.py:5-35) in 16 bytes -> one 128-bit load.
+//   key   = ps - p_min (+1 for 'D' nodes: the searchsorted key of rpc.py:127)
+//   pr    = 1-based reference position
+//   op    = '=', 'X', 'I' or 'D' (ASCII)
+struct alignas(16) MgNode {
+  uint32_t key;
+  int32_t pr;
+  int32_t oplen;
+  uint32_t op;
+};
+
+// Maximal run of one non-ACGT byte on the haplotype, in sample-relative coordinates.
+struct alignas(16) MgExc {
+  uint32_t start;
+  uint32_t len;
+  uint32_t byte;
+  uint32_t pad;
+};
+
+// ------------------------------------------------------------------------------------------
+// Bit tricks with portable fall-backs (the device versions map to single instructions)
+
+MG_HD uint32_t mg_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // ((hi:lo) >> sh) low word, sh in [0,31]
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+#endif
+}
+
+MG_HD uint32_t mg_brev(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+  x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+  return (x >> 16) | (x << 16);
+#endif
+}
+
+MG_HD uint32_t mg_prmt(uint32_t a, uint32_t sel) {  // byte i of result = byte (nibble i of sel & 3) of a
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, 0u, sel);
+#else
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= ((a >> (8 * ((sel >> (4 * i)) & 3))) & 0xFFu) << (8 * i);
+  return r;
+#endif
+}
+
+// 16 consecutive 2-bit codes starting at base index s (s >= 0) of a packed sequence
+// (16 bases per 32-bit word, base i in bits [2i, 2i+1] of word i/16).
+template <class P>
+MG_HD uint32_t mg_codes16(P seq, int64_t s) {
+  int64_t w = s >> 4;
+  uint32_t sh = (uint32_t)(s & 15) * 2u;
+  uint32_t lo = seq[w];
+  uint32_t hi = sh ? seq[w + 1] : 0u;
+  return mg_funnel_r(lo, hi, sh);
+}
+
+// reverse the order of the 16 codes in a word and complement them (A<->T, C<->G is code ^ 3)
+MG_HD uint32_t mg_revcomp16(uint32_t x) {
+  uint32_t y = mg_brev(x);
+  y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+  return ~y;
+}
+
+// four 2-bit codes (low byte of b) -> four ASCII bases
+MG_HD uint32_t mg_chars4(uint32_t b) {
+  uint32_t y = (b | (b << 4)) & 0x0F0Fu;
+  uint32_t z = (y | (y << 2)) & 0x3333u;
+  return mg_prmt(0x54474341u /* 'A','C','G','T' little-endian */, z);
+}
+
+MG_HD uint32_t mg_base_code(uint8_t c) {  // ACGT -> 0..3, anything else -> 4
+  return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), the counter-based generator of the production mode
+
+struct MgPhilox { uint32_t v[4]; };
+
+MG_HD void mg_mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
+}
+
+MG_HD MgPhilox mg_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0, l0, h1, l1;
+    mg_mulhilo(0xD2511F53u, c0, h0, l0);
+    mg_mulhilo(0xCD9E8D57u, c2, h1, l1);
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  MgPhilox o; o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+
+// 53-bit uniform in [0,1) from two words, the same construction numpy's random_sample uses
+MG_HD double mg_u53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+// Philox stream tags (counter word 3)
+#define MG_STREAM_GAP 0x67617073u
+#define MG_STREAM_TLEN 0x746c656eu
+#define MG_STREAM_CORRUPT 0x636f7272u
+
+// Keyed pseudo-random permutation of [0, n): balanced Feistel network on the next even power of
+// two with cycle walking.  Replaces RandomState.shuffle (illumina.py:71) in production mode.
+MG_HD uint32_t mg_feistel_round(uint32_t r, uint32_t k) {
+  uint32_t x = r * 0x9E3779B1u + k;
+  x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+  return x;
+}
+
+MG_HD uint32_t mg_permute(uint32_t i, uint32_t n, uint32_t half_bits, uint32_t k0, uint32_t k1) {
+  const uint32_t hm = (1u << half_bits) - 1u;
+  do {
+    uint32_t l = i >> half_bits, r = i & hm;
+    for (int t = 0; t < 6; t++) {
+      uint32_t f = mg_feistel_round(r, (t & 1) ? k1 + (uint32_t)t : k0 + (uint32_t)t) & hm;
+      uint32_t nl = r; r = l ^ f; l = nl;
+    }
+    i = (l << half_bits) | r;
+  } while (i >= n);
+  return i;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decimal helpers
+
+MG_HD int mg_ndigits(uint64_t v) {
+  int d = 1;
+  while (v >= 10) { v /= 10; d++; }
+  return d;
+}
+
+// sum of the decimal lengths of 1..m  (closed form; used to place records whose qname carries a
+// serial number that is only known after the block/grid scan)
+MG_HD uint64_t mg_digit_sum(uint64_t m) {
+  if (m == 0) return 0;
+  int d = mg_ndigits(m);
+  uint64_t ones = 0, p = 1;
+  for (int k = 0; k < d; k++) { ones += p; p *= 10; }
+  return (uint64_t)d * (m + 1) - ones;
+}
+
+// ------------------------------------------------------------------------------------------
+// Writers.  CountWriter sizes a record, WordStream writes it (any byte alignment) with aligned
+// 32-bit stores in the interior and byte stores only for the first / last partial word.
+
+struct MgCountWriter {
+  uint32_t n;
+  MG_HD void put(uint8_t) { n++; }
+  MG_HD void put_word(uint32_t) { n += 4; }
+};
+
+struct MgWordStream {
+  uint32_t *wp;     // next aligned word
+  uint32_t carry;   // pending bytes, low nb bytes valid
+  uint32_t nb;      // pending byte count 0..3
+  uint32_t skip;    // leading bytes of the first word that belong to someone else
+
+  MG_HD void begin(uint8_t *dst) {
+    uintptr_t a = (uintptr_t)dst & 3;
+    wp = (uint32_t *)(dst - a);
+    carry = 0; nb = (uint32_t)a; skip = (uint32_t)a;
+  }
+  MG_HD void flush_word(uint32_t w) {
+    if (skip) {
+      uint8_t *b = (uint8_t *)wp;
+      for (uint32_t i = skip; i < 4; i++) b[i] = (uint8_t)(w >> (8 * i));
+      skip = 0;
+    } else {
+      *wp = w;
+    }
+    wp++;
+  }
+  MG_HD void put(uint8_t c) {
+    carry |= (uint32_t)c << (8 * nb);
+    if (++nb == 4) { flush_word(carry); carry = 0; nb = 0; }
+  }
+  MG_HD void put_word(uint32_t w) {  // four bytes, little-endian order
+    if (nb == 0) { flush_word(w); return; }
+    uint32_t sh = 8 * nb;
+    flush_word(carry | (w << sh));
+    carry = w >> (32 - sh);
+  }
+  MG_HD void end() {
+    uint8_t *b = (uint8_t *)wp;
+    for (uint32_t i = skip; i < nb; i++) b[i] = (uint8_t)(carry >> (8 * i));
+    nb = 0; skip = 0;
+  }
+};
+
+template <class W>
+MG_HD void mg_put_uint(W &w, uint64_t v) {
+  // digits are stacked as nibbles in a register (no local-memory array): v < 10^16
+  uint64_t acc = 0;
+  int n = 0;
+  do { acc = (acc << 4) | (v % 10); v /= 10; n++; } while (v);
+  for (; n; n--) { w.put((uint8_t)('0' + (acc & 15))); acc >>= 4; }
+}
+
+template <class W>
+MG_HD void mg_put_int(W &w, int64_t v) {
+  if (v < 0) { w.put('-'); mg_put_uint(w, (uint64_t)(-v)); } else mg_put_uint(w, (uint64_t)v);
+}
+
+template <class W>
+MG_HD void mg_put_bytes(W &w, const uint8_t *s, int n) {
+  for (int i = 0; i < n; i++) w.put(s[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Node lookup: searchsorted(keys, x, 'right') - 1 (rpc.py:127-130), accelerated by a block table
+// blk[b] = last node whose key <= (b << blk_shift).
+
+template <class NP, class BP>
+MG_HD int mg_find_node(NP nodes, BP blk, int blk_shift, int n_blk, int n_nodes, uint32_t x) {
+  uint32_t b = x >> blk_shift;
+  if ((int)b >= n_blk) b = (uint32_t)(n_blk - 1);
+  int lo = (int)blk[b];
+  int hi = ((int)b + 1 < n_blk) ? (int)blk[b + 1] : n_nodes - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (nodes[mid].key <= x) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// '|strand|pos|rlen|cigar|vlist' for one read (fastq_lines, readgenerate.py:224-225, over
+// generate_read, rpc.py:144-158).  x = read start relative to p_min, L = read length.
+template <class W, class NP>
+MG_HD void mg_fmt_read(W &w, NP nodes, int n0, int n1, uint32_t x, int L, int strand) {
+  MgNode f = nodes[n0];
+  int64_t ps0 = (int64_t)f.key - (f.op == 'D' ? 1 : 0);
+  int64_t pos;
+  bool inside_ins = (f.op == 'I') && (n0 == n1);
+  if (f.op == 'I') pos = inside_ins ? (int64_t)f.pr - 1 : (int64_t)f.pr;      // rpc.py:148-156
+  else pos = (int64_t)x - ps0 + (int64_t)f.pr;                               // rpc.py:158
+  w.put('|'); w.put((uint8_t)('0' + strand));
+  w.put('|'); mg_put_int(w, pos);
+  w.put('|'); mg_put_uint(w, (uint64_t)L);
+  w.put('|');
+  if (inside_ins) {                                                          // rpc.py:154
+    w.put('>'); mg_put_int(w, (int64_t)x - ps0); w.put(':'); mg_put_uint(w, (uint64_t)L); w.put('I');
+  } else {
+    for (int k = n0; k <= n1; k++) {                                         // rpc.py:145
+      MgNode n = nodes[k];
+      int64_t len;
+      if (n.op != 'D') {
+        int64_t ps = (int64_t)n.key;
+        int64_t a = (int64_t)x - ps; if (a < 0) a = 0;
+        int64_t b = (int64_t)x + L - ps; if ((int64_t)n.oplen < b) b = n.oplen;
+        len = b - a;
+      } else len = n.oplen;
+      mg_put_int(w, len); w.put((uint8_t)n.op);
+    }
+  }
+  w.put('|');
+  bool first = true;
+  for (int k = n0; k <= n1; k++) {                                           // rpc.py:144
+    MgNode n = nodes[k];
+    if (n.op == '=') continue;
+    if (!first) w.put(',');
+    first = false;
+    if (n.op == 'X') w.put('0');
+    else if (n.op == 'I') mg_put_int(w, (int64_t)n.oplen);
+    else mg_put_int(w, -(int64_t)n.oplen);
+  }
+}
+
+// Whole qname line without the trailing newline:
+//   '@' stub ':' cnt '|' chrom '|' cpy  + per read in FILE order '|strand|pos|rlen|cigar|vlist'
+// prefix = "@<sample>:<worker>:<ps>:"   mid = "|<chrom>|<cpy>"
+struct MgReadRef { uint32_t x; int n0, n1, strand; };
+
+template <class W, class NP>
+MG_HD void mg_fmt_qname(W &w, const uint8_t *prefix, int prefix_len, uint64_t cnt, bool with_cnt,
+                        const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
+  mg_put_bytes(w, prefix, prefix_len);
+  if (with_cnt) mg_put_uint(w, cnt);
+  mg_put_bytes(w, mid, mid_len);
+  mg_fmt_read(w, nodes, first.n0, first.n1, first.x, L, first.strand);
+  mg_fmt_read(w, nodes, second.n0, second.n1, second.x, L, second.strand);
+}
+
+// L bases of the haplotype starting at relative offset x, forward (strand 0) or reverse
+// complemented (strand 1, readgenerate.py:205-206), as ASCII through the writer.
+template <class W, class HP>
+MG_HD void mg_emit_seq(W &w, HP hap, uint32_t x, int L, int strand) {
+  int nfull = L >> 4;
+  for (int c = 0; c <= nfull; c++) {
+    int nb = (c < nfull) ? 16 : (L & 15);
+    if (nb == 0) break;
+    uint32_t codes;
+    if (strand == 0) {
+      codes = mg_codes16(hap, (int64_t)x + 16 * c);
+    } else {
+      // output bases [16c, 16c+16) are the complement of forward bases [L-16c-16, L-16c) reversed
+      int64_t s = (int64_t)x + L - 16 * (int64_t)c - 16;   // may dip up to 15 below x: hap is front-padded
+      codes = mg_revcomp16(mg_codes16(hap, s));
+    }
+    int k = 0;
+    for (; k + 4 <= nb; k += 4) w.put_word(mg_chars4((codes >> (2 * k)) & 0xFFu));
+    if (k < nb) {
+      uint32_t ch = mg_chars4((codes >> (2 * k)) & 0xFFu);
+      for (; k < nb; k++) { w.put((uint8_t)ch); ch >>= 8; }
+    }
+  }
+}
+
+template <class W>
+MG_HD void mg_emit_fill(W &w, uint8_t c, int n) {
+  uint32_t cw = 0x01010101u * c;
+  int k = 0;
+  for (; k + 4 <= n; k += 4) w.put_word(cw);
+  for (; k < n; k++) w.put(c);
+}
+
+// Exception runs (non-ACGT bytes) overlapping [x, x+L): first run with start+len > x.
+template <class EP>
+MG_HD int mg_exc_first(EP exc, int n_exc, uint32_t x) {
+  int lo = 0, hi = n_exc;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((uint64_t)exc[mid].start + exc[mid].len <= (uint64_t)x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// number of 'N' in the read (seq.count('N'), readgenerate.py:204)
+template <class EP>
+MG_HD int mg_count_N(EP exc, int n_exc, uint32_t x, int L) {
+  int cnt = 0;
+  for (int k = mg_exc_first(exc, n_exc, x); k < n_exc; k++) {
+    MgExc e = exc[k];
+    if ((uint64_t)e.start >= (uint64_t)x + L) break;
+    if (e.byte != 'N') continue;
+    uint64_t a = e.start > x ? e.start : x;
+    uint64_t b = (uint64_t)e.start + e.len < (uint64_t)x + L ? (uint64_t)e.start + e.len : (uint64_t)x + L;
+    cnt += (int)(b - a);
+  }
+  return cnt;
+}
+
+// overwrite the bases of a written read (seq points at its first byte) that fall in exception
+// runs.  The reference's translate table only maps ATCGN (readgenerate.py:56), so an exception
+// byte is copied unchanged on either strand; only its position is mirrored on strand 1.
+template <class EP>
+MG_HD void mg_patch_exc(uint8_t *seq, EP exc, int n_exc, uint32_t x, int L, int strand) {
+  for (int k = mg_exc_first(exc, n_exc, x); k < n_exc; k++) {
+    MgExc e = exc[k];
+    if ((uint64_t)e.start >= (uint64_t)x + L) break;
+    uint64_t a = e.start > x ? e.start : x;
+    uint64_t b = (uint64_t)e.start + e.len < (uint64_t)x + L ? (uint64_t)e.start + e.len : (uint64_t)x + L;
+    for (uint64_t i = a; i < b; i++) {
+      int idx = (int)(i - x);
+      seq[strand ? (L - 1 - idx) : idx] = (uint8_t)e.byte;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Corruption of one base call (illumina.py:155-160)
+
+MG_HD uint8_t mg_base_rot(uint8_t c, int r) {  // illumina.py:131-136: A->CTG C->ATG T->ACG G->ACT else N
+  uint32_t t;
+  switch (c) {
+    case 'A': t = 'C' | ('T' << 8) | ('G' << 16); break;
+    case 'C': t = 'A' | ('T' << 8) | ('G' << 16); break;
+    case 'T': t = 'A' | ('C' << 8) | ('G' << 16); break;
+    case 'G': t = 'A' | ('C' << 8) | ('T' << 16); break;
+    default: t = 'N' | ('N' << 8) | ('N' << 16); break;
+  }
+  return (uint8_t)(t >> (8 * r));
+}
+
+// searchsorted(row, u) side='left' over n doubles
+template <class DP>
+MG_HD int mg_lower_bound_f64(DP row, int n, double u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (row[mid] < u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// One FASTQ record (fastq_lines, readgenerate.py:227-230):  qname \n SEQ \n+\n ~~~~ \n
+// `mine` is the read that goes into this file; first/second give the qname's file order.
+// qlen = length of the qname line without its newline (known from the sizing pass).
+template <class NP, class HP, class EP>
+MG_HD void mg_emit_record(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
+                          const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second,
+                          MgReadRef mine, int L, HP hap, EP exc, int n_exc) {
+  MgWordStream ws;
+  ws.begin(dst);
+  mg_fmt_qname(ws, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
+  ws.put('\n');
+  mg_emit_seq(ws, hap, mine.x, L, mine.strand);
+  ws.put('\n'); ws.put('+'); ws.put('\n');
+  mg_emit_fill(ws, '~', L);
+  ws.put('\n');
+  ws.end();
+  if (n_exc) mg_patch_exc(dst + qlen + 1, exc, n_exc, mine.x, L, mine.strand);
+}
+
+// One base call with explicit draws (deterministic mode: the reference's own numpy draws)
+template <class DP>
+MG_HD void mg_corrupt_call(uint8_t *seq, uint8_t *qual, int n, DP cum_row, int n_bq, DP phred,
+                           double u_bq, double u_call, int rot) {
+  int bq = mg_lower_bound_f64(cum_row, n_bq, u_bq);                // illumina.py:156
+  if (bq > 93) bq = 93;
+  if (u_call < phred[bq]) seq[n] = mg_base_rot(seq[n], rot);       // illumina.py:159-160
+  qual[n] = (uint8_t)(bq + 33);
+}
+
+// Production mode: both uniforms come from one Philox half-block; the substitution choice reuses
+// the conditional uniformity of u_call given u_call < p (no third draw).
+template <class DP>
+MG_HD void mg_corrupt_call_philox(uint8_t *seq, uint8_t *qual, int n, DP cum_row, int n_bq, DP phred,
+                                  uint32_t w_bq, uint32_t w_call) {
+  double u_bq = (double)w_bq * (1.0 / 4294967296.0), u_call = (double)w_call * (1.0 / 4294967296.0);
+  int bq = mg_lower_bound_f64(cum_row, n_bq, u_bq);
+  if (bq > 93) bq = 93;
+  double p = phred[bq];
+  if (u_call < p) {
+    int rot = (int)(3.0 * (u_call / p));
+    seq[n] = mg_base_rot(seq[n], rot > 2 ? 2 : rot);
+  }
+  qual[n] = (uint8_t)(bq + 33);
+}

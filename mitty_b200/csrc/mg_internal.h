@@ -1,0 +1,77 @@
+// Internal interface between the C-ABI host code (mg_api.cu) and the kernels (mg_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mg_core.cuh"
+
+#define MG_TILE 128          // candidates (and threads) per emit tile
+#define MG_HAP_PAD 8         // 32-bit words of padding on both sides of a packed sequence
+
+enum { MG_MODE_PHILOX = 0, MG_MODE_DET = 1, MG_MODE_EXPLICIT = 2 };
+
+struct MgUnitParams {
+  // haplotype of one chromosome copy, resident in HBM
+  const uint32_t *hap;       // 2-bit packed, 16 bases / word, pointer already biased past the front pad
+  uint32_t hap_len;          // p_max - p_min
+  int64_t p_min;             // 1-based sample coordinate of hap base 0
+  const MgNode *nodes; int n_nodes;
+  const uint32_t *blk; int blk_shift; int n_blk;
+  const MgExc *exc; int n_exc;
+  // read model
+  const double *cum_tlen; int n_tlen; int rlen;
+  // template sampling
+  int mode; uint32_t n_cand;
+  const int64_t *ts_in;      // DET / EXPLICIT: shuffled template starts (1-based sample coords)
+  const double *u_tlen;      // DET: uniforms for the template-length inverse CDF
+  const int64_t *tl_in;      // EXPLICIT: template lengths
+  const int8_t *fo_in;       // DET / EXPLICIT: file-order bits, consumed in te<p_max survivor order
+  const uint32_t *ts_sorted; // PHILOX: cumulative geometric gaps (+1), relative to p_min
+  uint32_t key_tlen0, key_tlen1, key_perm0, key_perm1, half_bits;
+  // qname constants: prefix = "@sample:worker:ps:", mid = "|chrom|cpy"
+  const uint8_t *prefix; int prefix_len; const uint8_t *mid; int mid_len;
+  // outputs
+  uint8_t *out[2]; uint64_t cap;
+  uint64_t *rec_off;         // optional: byte offset of every record (+ total at [n])
+  // fused corruption (PHILOX draws)
+  int corrupt; const double *cum_bq; int n_cycles, n_bq; const double *phred; uint32_t key_cor0, key_cor1;
+  // grid-wide scan state
+  unsigned long long *descA, *descB; uint32_t *tile_counter;
+  unsigned long long *totals;  // [0] te<p_max survivors, [1] templates written, [2] bytes per file, [3] overflow
+  int n_tiles; int stage_cap;
+};
+
+struct MgSampleParams {      // template sampling only (the read-module plugin's generate_reads)
+  MgUnitParams u;
+  int64_t *ts_out; int64_t *te_out; int8_t *fo_out;  // per candidate (uncompacted); te = -1 when dropped
+};
+
+struct MgCorruptParams {     // standalone corrupt-reads over FASTQ resident in HBM
+  const uint8_t *in[2]; uint8_t *out[2];
+  const int64_t *nl[2];      // newline positions of each input file
+  const int64_t *out_off[2]; // output record offsets [n_rec + 1]
+  int64_t n_rec; int n_files;
+  const double *cum_bq; int n_cycles, n_bq; const double *phred;
+  int mode;                  // MG_MODE_PHILOX / MG_MODE_DET
+  uint32_t key0, key1;
+  const double *bq_rnd, *call_rnd; const uint8_t *base_rnd; const int64_t *draw_off;  // DET: per read [2*n_rec+1]
+  unsigned long long *err;   // [0] != 0 -> a read is longer than the model
+};
+
+// launchers (all asynchronous on `st`)
+void mg_launch_pack_ref(const uint8_t *raw, int64_t len, uint32_t *packed, uint32_t *exc_cnt, int64_t *exc_start,
+                        uint8_t *exc_byte, int64_t *exc_end, uint32_t exc_cap, cudaStream_t st);
+void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const uint32_t *seg_start, const uint64_t *seg_src,
+                         int n_seg, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st);
+void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st);
+void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
+                        cudaStream_t st);
+int mg_unit_grid(int stage_cap, int n_tlen, int *smem_bytes);
+void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st);
+void mg_launch_sample(const MgSampleParams &P, cudaStream_t st);
+void mg_launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st);  // exclusive, out[n] = total
+int64_t mg_scan_tmp_elems(int64_t n);
+void mg_launch_nl_count(const uint8_t *buf, int64_t len, int64_t *cnt, cudaStream_t st);
+void mg_launch_nl_write(const uint8_t *buf, int64_t len, const int64_t *off, int64_t *nl, cudaStream_t st);
+int64_t mg_nl_chunks(int64_t len);
+void mg_launch_corrupt_sizes(const MgCorruptParams &P, int64_t *sz0, int64_t *sz1, cudaStream_t st);
+void mg_launch_corrupt(const MgCorruptParams &P, cudaStream_t st);

@@ -1,0 +1,740 @@
+// Hand-written sm_100a kernels of the read-generation engine.  No tensor cores: every kernel
+// here is HBM / L2-bound byte and integer work (scan, gather, format, table lookup).
+//
+//   k_pack_ref        ASCII reference -> 2-bit packed words + non-ACGT run boundaries
+//   k_hap_build       packed reference + variant segments -> packed haplotype of one copy
+//   k_blk_table       node keys -> block lookup table
+//   k_gap_*           Philox geometric gaps -> grid-wide inclusive scan (template starts)
+//   k_unit_emit       THE hot kernel: template sampling + filters + node lookup + qname/CIGAR
+//                     formatting + sequence extraction/revcomp (+ fused Philox corruption),
+//                     decoupled look-back scan for record placement, smem-staged coalesced
+//                     FASTQ writes
+//   k_sample          template sampling only (read-module plugin generate_reads)
+//   k_scan_*          generic exclusive scan (int64)
+//   k_nl_*            FASTQ newline index
+//   k_corrupt_*       standalone corrupt-reads over FASTQ in HBM
+#include "mg_internal.h"
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t n = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v += n;
+  }
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long ld_vol64(const unsigned long long *p) {
+  return *(const volatile unsigned long long *)p;
+}
+__device__ __forceinline__ void st_vol64(unsigned long long *p, unsigned long long v) {
+  *(volatile unsigned long long *)p = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pack_ref: 16 bases per thread
+
+__global__ void __launch_bounds__(256) k_pack_ref(const uint8_t *__restrict__ raw, int64_t len, uint32_t *__restrict__ packed,
+                                                  uint32_t *exc_cnt, int64_t *exc_start, uint8_t *exc_byte,
+                                                  int64_t *exc_end, uint32_t exc_cap) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t base = w * 16;
+  if (base >= len) return;
+  uint8_t c[18];  // c[0] = byte before, c[1..16] = mine, c[17] = byte after
+  c[0] = base > 0 ? raw[base - 1] : 0;
+  if (base + 16 <= len) {
+    uint4 v = *reinterpret_cast<const uint4 *>(raw + base);
+    uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[1 + i] = (uint8_t)(q[i >> 2] >> (8 * (i & 3)));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[1 + i] = (base + i < len) ? raw[base + i] : (uint8_t)'A';
+  }
+  c[17] = (base + 16 < len) ? raw[base + 16] : 0;
+  uint32_t word = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    int64_t pos = base + i;
+    if (pos >= len) break;
+    uint32_t code = mg_base_code(c[1 + i]);
+    if (code > 3) {
+      bool is_start = (pos == 0) || (c[i] != c[1 + i]);
+      bool is_end = (pos == len - 1) || (c[2 + i] != c[1 + i]);
+      if (is_start) {
+        uint32_t k = atomicAdd(&exc_cnt[0], 1u);
+        if (k < exc_cap) { exc_start[k] = pos; exc_byte[k] = c[1 + i]; }
+      }
+      if (is_end) {
+        uint32_t k = atomicAdd(&exc_cnt[1], 1u);
+        if (k < exc_cap) exc_end[k] = pos;
+      }
+      code = 0;
+    }
+    word |= code << (2 * i);
+  }
+  packed[w] = word;
+}
+
+void mg_launch_pack_ref(const uint8_t *raw, int64_t len, uint32_t *packed, uint32_t *exc_cnt, int64_t *exc_start,
+                        uint8_t *exc_byte, int64_t *exc_end, uint32_t exc_cap, cudaStream_t st) {
+  int64_t words = (len + 15) / 16;
+  if (words == 0) return;
+  k_pack_ref<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(raw, len, packed, exc_cnt, exc_start, exc_byte, exc_end, exc_cap);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_hap_build: one thread per 16-base haplotype word.  Segments (the non-'D' nodes) tile the
+// haplotype: seg_start[k] .. seg_start[k+1].  seg_src bit 63 = 1 -> alt pool byte offset,
+// else base offset into the packed reference.
+
+__global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ ref, const uint8_t *__restrict__ alt_pool,
+                                                   const uint32_t *__restrict__ seg_start, const uint64_t *__restrict__ seg_src,
+                                                   int n_seg, uint32_t hap_len, uint32_t *__restrict__ hap, int64_t hap_words) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= hap_words) return;
+  uint64_t s0 = (uint64_t)w * 16;
+  if (s0 >= hap_len) { hap[w] = 0; return; }
+  // last segment with seg_start <= s0
+  int lo = 0, hi = n_seg - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if ((uint64_t)seg_start[mid] <= s0) lo = mid; else hi = mid - 1;
+  }
+  int k = lo;
+  uint64_t seg_end = (k + 1 < n_seg) ? seg_start[k + 1] : hap_len;
+  uint64_t src = seg_src[k];
+  uint32_t word;
+  if (!(src >> 63) && s0 + 16 <= seg_end) {
+    word = mg_codes16(ref, (int64_t)(src + (s0 - seg_start[k])));        // whole word from the reference
+  } else {
+    word = 0;
+    for (int i = 0; i < 16; i++) {
+      uint64_t s = s0 + i;
+      if (s >= hap_len) break;
+      while (s >= seg_end) { k++; seg_end = (k + 1 < n_seg) ? seg_start[k + 1] : hap_len; src = seg_src[k]; }
+      uint64_t off = s - seg_start[k];
+      uint32_t code;
+      if (src >> 63) {
+        code = mg_base_code(alt_pool[(src & ~(1ull << 63)) + off]);
+        if (code > 3) code = 0;
+      } else {
+        uint64_t r = src + off;
+        code = (ref[r >> 4] >> (2 * (r & 15))) & 3u;
+      }
+      word |= code << (2 * i);
+    }
+  }
+  hap[w] = word;
+}
+
+void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const uint32_t *seg_start, const uint64_t *seg_src,
+                         int n_seg, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st) {
+  if (hap_words == 0) return;
+  k_hap_build<<<(unsigned)((hap_words + 255) / 256), 256, 0, st>>>(ref, alt_pool, seg_start, seg_src, n_seg, hap_len, hap, hap_words);
+}
+
+__global__ void __launch_bounds__(256) k_blk_table(const MgNode *__restrict__ nodes, int n_nodes, uint32_t *__restrict__ blk,
+                                                   int n_blk, int blk_shift) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blk) return;
+  uint64_t x = (uint64_t)b << blk_shift;
+  int lo = 0, hi = n_nodes - 1;                 // nodes[0].key == 0 always
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if ((uint64_t)nodes[mid].key <= x) lo = mid; else hi = mid - 1;
+  }
+  blk[b] = (uint32_t)lo;
+}
+
+void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st) {
+  k_blk_table<<<(n_blk + 255) / 256, 256, 0, st>>>(nodes, n_nodes, blk, n_blk, blk_shift);
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox geometric gaps + grid-wide inclusive scan (illumina.py:70 in production mode)
+
+#define GAP_PER_THREAD 8
+#define GAP_THREADS 256
+#define GAP_PER_BLOCK (GAP_PER_THREAD * GAP_THREADS)
+
+__device__ __forceinline__ void gaps8(uint32_t i0, uint32_t n, double inv_log1mp, uint32_t k0, uint32_t k1, uint32_t g[8]) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint32_t i = i0 + 2 * q;
+    MgPhilox r = mg_philox(i >> 1, 0u, 0u, MG_STREAM_GAP, k0, k1);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      double u = mg_u53(r.v[2 * h], r.v[2 * h + 1]);
+      double gd = ceil(log(1.0 - u) * inv_log1mp);
+      uint32_t gv = gd < 1.0 ? 1u : (gd > 4.0e9 ? 4000000000u : (uint32_t)gd);
+      g[2 * q + h] = (i + h < n) ? gv : 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GAP_THREADS) k_gap_partial(uint32_t n, double inv_log1mp, uint32_t k0, uint32_t k1,
+                                                             unsigned long long *partial) {
+  __shared__ unsigned long long s_w[GAP_THREADS / 32];
+  uint32_t i0 = blockIdx.x * GAP_PER_BLOCK + threadIdx.x * GAP_PER_THREAD;
+  uint32_t g[8];
+  unsigned long long sum = 0;
+  if (i0 < n) { gaps8(i0, n, inv_log1mp, k0, k1, g); for (int q = 0; q < 8; q++) sum += g[q]; }
+  sum = warp_sum_u64(sum);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < GAP_THREADS / 32; w++) t += s_w[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of up to a few 10^5 partials by one block
+__global__ void __launch_bounds__(1024) k_scan_partials_u64(unsigned long long *partial, int n) {
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_carry;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    unsigned long long v = (i < n) ? partial[i] : 0, x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(FULL, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long t = s_w[lane], xx = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(FULL, xx, d); if (lane >= d) xx += y; }
+      s_w[lane] = xx - t;  // exclusive warp offsets
+    }
+    __syncthreads();
+    unsigned long long carry = s_carry;
+    unsigned long long incl = carry + s_w[wid] + x;
+    if (i < n) partial[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(GAP_THREADS) k_gap_final(uint32_t n, double inv_log1mp, uint32_t k0, uint32_t k1,
+                                                           const unsigned long long *__restrict__ partial, uint32_t *__restrict__ ts_sorted) {
+  __shared__ unsigned long long s_w[GAP_THREADS / 32];
+  uint32_t i0 = blockIdx.x * GAP_PER_BLOCK + threadIdx.x * GAP_PER_THREAD;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t g[8];
+  unsigned long long sum = 0;
+  if (i0 < n) { gaps8(i0, n, inv_log1mp, k0, k1, g); for (int q = 0; q < 8; q++) sum += g[q]; }
+  else { for (int q = 0; q < 8; q++) g[q] = 0; }
+  unsigned long long x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(FULL, x, d); if (lane >= d) x += y; }
+  if (lane == 31) s_w[wid] = x;
+  __syncthreads();
+  unsigned long long off = partial[blockIdx.x];
+  for (int w = 0; w < wid; w++) off += s_w[w];
+  unsigned long long run = off + x - sum;  // exclusive prefix of this thread
+  if (i0 < n) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      run += g[q];
+      if (i0 + q < n) {
+        unsigned long long v = run + 1;      // ts = cumsum + p_min + 1, stored relative to p_min
+        ts_sorted[i0 + q] = v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
+      }
+    }
+  }
+}
+
+void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
+                        cudaStream_t st) {
+  if (n == 0) return;
+  double inv = 1.0 / log(1.0 - p);
+  int nb = (int)((n + GAP_PER_BLOCK - 1) / GAP_PER_BLOCK);
+  k_gap_partial<<<nb, GAP_THREADS, 0, st>>>(n, inv, k0, k1, partial);
+  k_scan_partials_u64<<<1, 1024, 0, st>>>(partial, nb);
+  k_gap_final<<<nb, GAP_THREADS, 0, st>>>(n, inv, k0, k1, partial, ts_sorted);
+}
+
+// ------------------------------------------------------------------------------------------
+// Template sampling for one candidate (illumina.py:66-76, 93-96)
+
+struct Cand { int64_t ts_rel; int64_t te_rel; uint32_t fo; bool k1; };
+
+__device__ __forceinline__ Cand sample_candidate(const MgUnitParams &P, const double *cum_tlen, uint32_t j) {
+  Cand c;
+  int64_t tl;
+  c.fo = 0;
+  if (P.mode == MG_MODE_PHILOX) {
+    uint32_t i = mg_permute(j, P.n_cand, P.half_bits, P.key_perm0, P.key_perm1);
+    c.ts_rel = (int64_t)P.ts_sorted[i];
+    MgPhilox r = mg_philox(j, 0u, 0u, MG_STREAM_TLEN, P.key_tlen0, P.key_tlen1);
+    tl = mg_lower_bound_f64(cum_tlen, P.n_tlen, mg_u53(r.v[0], r.v[1]));      // illumina.py:72
+    c.fo = r.v[2] & 1u;
+  } else {
+    c.ts_rel = P.ts_in[j] - P.p_min;
+    tl = (P.mode == MG_MODE_DET) ? (int64_t)mg_lower_bound_f64(cum_tlen, P.n_tlen, P.u_tlen[j]) : P.tl_in[j];
+  }
+  if (tl < P.rlen) tl = P.rlen;                                                // illumina.py:73
+  c.te_rel = c.ts_rel + tl;
+  c.k1 = (c.te_rel < (int64_t)P.hap_len) && (c.ts_rel >= 0);                   // illumina.py:75
+  return c;
+}
+
+__global__ void __launch_bounds__(256) k_sample(MgSampleParams S) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  double *s_tlen = reinterpret_cast<double *>(smem);
+  for (int i = threadIdx.x; i < S.u.n_tlen; i += blockDim.x) s_tlen[i] = S.u.cum_tlen[i];
+  __syncthreads();
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < S.u.n_cand; j += gridDim.x * blockDim.x) {
+    Cand c = sample_candidate(S.u, s_tlen, j);
+    S.ts_out[j] = c.ts_rel + S.u.p_min;
+    S.te_out[j] = c.k1 ? c.te_rel + S.u.p_min : -1;
+    S.fo_out[j] = (int8_t)c.fo;
+  }
+}
+
+void mg_launch_sample(const MgSampleParams &P, cudaStream_t st) {
+  if (P.u.n_cand == 0) return;
+  int grid = (int)((P.u.n_cand + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  k_sample<<<grid, 256, P.u.n_tlen * sizeof(double), st>>>(P);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_unit_emit
+
+struct Slot {
+  uint32_t xa, xb;        // read starts (relative to p_min) of mate 0 / mate 1
+  int32_t n0a, n0b;       // first node of each read
+  uint16_t dna, dnb;      // n1 - n0 of each read
+  uint32_t aux;           // PHILOX: file-order bit; DET/EXPLICIT: local rank among te<p_max survivors
+  uint32_t sz;            // record bytes without the serial digits
+  uint32_t esz;           // exclusive scan of sz inside the tile
+  uint32_t loff;          // byte offset of the record inside the tile (phase 2)
+  uint32_t qlen;          // qname length (phase 2)
+};
+
+struct Agg { unsigned long long c1, c2, by; };
+
+#define DESC_FLAG(x) ((uint32_t)((x) >> 62))
+#define DESC_MASK62 ((1ull << 62) - 1ull)
+
+// warp 0: exclusive prefix of (c1, c2, bytes) over all tiles before `tile` (decoupled look-back)
+__device__ Agg tile_lookback(const MgUnitParams &P, int tile, int lane) {
+  Agg ex = {0, 0, 0};
+  int idx = tile - 1;
+  while (true) {
+    int t = idx - lane;
+    unsigned long long a = 0, b = 0;
+    uint32_t fl = 2;  // tiles before 0 behave like an all-zero inclusive prefix
+    if (t >= 0) {
+      do {
+        a = ld_vol64(P.descA + t);
+        b = ld_vol64(P.descB + t);
+      } while (DESC_FLAG(a) == 0 || DESC_FLAG(a) != DESC_FLAG(b));
+      fl = DESC_FLAG(a);
+    }
+    __syncwarp();
+    uint32_t pm = __ballot_sync(FULL, fl == 2);
+    int first = __ffs(pm) - 1;
+    bool take = (t >= 0) && (first < 0 || lane <= first);
+    unsigned long long c1 = take ? ((a >> 31) & 0x7FFFFFFFull) : 0;
+    unsigned long long c2 = take ? (a & 0x7FFFFFFFull) : 0;
+    unsigned long long by = take ? (b & DESC_MASK62) : 0;
+    ex.c1 += warp_sum_u64(c1); ex.c2 += warp_sum_u64(c2); ex.by += warp_sum_u64(by);
+    if (first >= 0) break;
+    idx -= 32;
+  }
+  return ex;
+}
+
+__device__ __forceinline__ void corrupt_pair_philox(const MgUnitParams &P, uint8_t *seq, uint8_t *qual, int L, uint32_t serial,
+                                                    int f, int pr) {
+  MgPhilox r = mg_philox(serial, (uint32_t)f, (uint32_t)pr, MG_STREAM_CORRUPT, P.key_cor0, P.key_cor1);
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    int n = 2 * pr + h;
+    if (n < L) {
+      const double *row = P.cum_bq + ((size_t)f * P.n_cycles + n) * P.n_bq;     // mate row = file index, illumina.py:125-128
+      mg_corrupt_call_philox(seq, qual, n, row, P.n_bq, P.phred, r.v[2 * h], r.v[2 * h + 1]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ MgUnitParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  double *s_tlen = reinterpret_cast<double *>(smem);
+  uint8_t *stage = smem + ((P.n_tlen * sizeof(double) + 15) & ~(size_t)15);
+
+  __shared__ Slot slots[MG_TILE];
+  __shared__ uint32_t s_wc[MG_TILE / 32], s_ws[MG_TILE / 32];
+  __shared__ unsigned long long s_base[3];
+  __shared__ uint32_t s_tile, s_tot_c, s_tot_sz;
+
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int L = P.rlen;
+  for (int i = t; i < P.n_tlen; i += MG_TILE) s_tlen[i] = P.cum_tlen[i];
+
+  while (true) {
+    __syncthreads();
+    if (t == 0) s_tile = atomicAdd(P.tile_counter, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    if (tile >= P.n_tiles) break;
+
+    // ---- phase 1: one candidate per thread -------------------------------------------------
+    const uint32_t j = (uint32_t)tile * MG_TILE + t;
+    bool k1 = false, k2 = false;
+    uint32_t xa = 0, xb = 0, fo = 0, sz = 0;
+    int n0a = 0, n1a = 0, n0b = 0, n1b = 0;
+    if (j < P.n_cand) {
+      Cand c = sample_candidate(P, s_tlen, j);
+      k1 = c.k1; fo = c.fo;
+      if (k1) {
+        xa = (uint32_t)c.ts_rel; xb = (uint32_t)(c.te_rel - L);                 // illumina.py:95-96
+        k2 = true;
+        if (P.n_exc) k2 = (mg_count_N(P.exc, P.n_exc, xa, L) <= 2) && (mg_count_N(P.exc, P.n_exc, xb, L) <= 2);  // readgenerate.py:204
+        if (k2) {
+          n0a = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xa);
+          n1a = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xa + L - 1);
+          n0b = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xb);
+          n1b = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xb + L - 1);
+          MgCountWriter cw; cw.n = 0;
+          mg_fmt_read(cw, P.nodes, n0a, n1a, xa, L, 0);
+          mg_fmt_read(cw, P.nodes, n0b, n1b, xb, L, 1);
+          sz = (uint32_t)(P.prefix_len + P.mid_len) + cw.n + 2u * (uint32_t)L + 5u;
+        }
+      }
+    }
+    // block scan of (k1 | k2 << 16, sz)
+    uint32_t cpk = (k1 ? 1u : 0u) | (k2 ? 0x10000u : 0u);
+    uint32_t ic = warp_incl_scan_u32(cpk, lane), is = warp_incl_scan_u32(sz, lane);
+    if (lane == 31) { s_wc[wid] = ic; s_ws[wid] = is; }
+    __syncthreads();
+    uint32_t oc = 0, os = 0, tc = 0, ts_ = 0;
+#pragma unroll
+    for (int w = 0; w < MG_TILE / 32; w++) {
+      if (w < wid) { oc += s_wc[w]; os += s_ws[w]; }
+      tc += s_wc[w]; ts_ += s_ws[w];
+    }
+    const uint32_t ec = oc + ic - cpk, es = os + is - sz;   // exclusive
+    if (k2) {
+      Slot &s = slots[ec >> 16];
+      s.xa = xa; s.xb = xb; s.n0a = n0a; s.n0b = n0b;
+      s.dna = (uint16_t)(n1a - n0a); s.dnb = (uint16_t)(n1b - n0b);
+      s.aux = (P.mode == MG_MODE_PHILOX) ? fo : (ec & 0xFFFFu);
+      s.sz = sz; s.esz = es;
+    }
+    const uint32_t tile_c1 = tc & 0xFFFFu, tile_c2 = tc >> 16, tile_sz = ts_;
+
+    // ---- grid-wide placement: decoupled look-back over tile descriptors ----------------------
+    if (wid == 0) {
+      Agg ex = {0, 0, 0};
+      if (tile > 0) {
+        if (lane == 0) {
+          st_vol64(P.descA + tile, (1ull << 62) | ((unsigned long long)tile_c1 << 31) | tile_c2);
+          st_vol64(P.descB + tile, (1ull << 62) | tile_sz);
+        }
+        ex = tile_lookback(P, tile, lane);
+      }
+      if (lane == 0) {
+        unsigned long long i1 = ex.c1 + tile_c1, i2 = ex.c2 + tile_c2, ib = ex.by + tile_sz;
+        st_vol64(P.descA + tile, (2ull << 62) | (i1 << 31) | i2);
+        st_vol64(P.descB + tile, (2ull << 62) | ib);
+        s_base[0] = ex.c1; s_base[1] = ex.c2; s_base[2] = ex.by;
+        if (tile == P.n_tiles - 1) {
+          P.totals[0] = i1; P.totals[1] = i2; P.totals[2] = ib + mg_digit_sum(i2);
+          if (P.rec_off) P.rec_off[i2] = ib + mg_digit_sum(i2);
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned long long base1 = s_base[0], base2 = s_base[1];
+    const unsigned long long dsum0 = mg_digit_sum(base2);
+    const unsigned long long goff = s_base[2] + dsum0;                          // byte offset of the tile in each file
+    const uint32_t nk = tile_c2;
+    const uint32_t tile_bytes = tile_sz + (uint32_t)(mg_digit_sum(base2 + nk) - dsum0);
+    const bool overflow = goff + tile_bytes > P.cap;
+    if (overflow && t == 0) atomicExch(&P.totals[3], 1ull);
+    const uint32_t pad = (uint32_t)(goff & 15);
+    const bool staged = (pad + tile_bytes) <= (uint32_t)P.stage_cap;
+
+    // ---- phase 2: one kept template per thread -----------------------------------------------
+    MgReadRef ra = {0, 0, 0, 0}, rb = {0, 0, 0, 1};
+    uint32_t loff = 0, qlen = 0, my_fo = 0;
+    unsigned long long cnt = 0;
+    if ((uint32_t)t < nk) {
+      Slot &s = slots[t];
+      ra.x = s.xa; ra.n0 = s.n0a; ra.n1 = s.n0a + s.dna; ra.strand = 0;
+      rb.x = s.xb; rb.n0 = s.n0b; rb.n1 = s.n0b + s.dnb; rb.strand = 1;
+      cnt = base2 + t + 1;                                                      // readgenerate.py:209
+      loff = s.esz + (uint32_t)(mg_digit_sum(base2 + t) - dsum0);
+      qlen = s.sz + (uint32_t)mg_ndigits(cnt) - (2u * (uint32_t)L + 5u);
+      my_fo = (P.mode == MG_MODE_PHILOX) ? s.aux : (uint32_t)(P.fo_in[base1 + s.aux] & 1);   // illumina.py:93
+      s.loff = loff; s.qlen = qlen;
+      if (P.rec_off && !overflow) P.rec_off[base2 + t] = goff + loff;
+    }
+    if (!overflow) {
+      for (int f = 0; f < 2; f++) {
+        if (P.out[f] == nullptr) continue;
+        if ((uint32_t)t < nk) {
+          // reads[fo] = mate (readgenerate.py:207): file f holds mate 0 iff fo == f
+          MgReadRef first = my_fo ? rb : ra, second = my_fo ? ra : rb;
+          MgReadRef mine = f ? second : first;
+          uint8_t *dst = staged ? (stage + pad + loff) : (P.out[f] + goff + loff);
+          mg_emit_record(dst, qlen, P.prefix, P.prefix_len, cnt, P.mid, P.mid_len, P.nodes, first, second, mine, L,
+                         P.hap, P.exc, P.n_exc);
+          if (P.corrupt && !staged) {
+            uint8_t *seq = dst + qlen + 1;
+            for (int pr = 0; 2 * pr < L; pr++) corrupt_pair_philox(P, seq, seq + L + 3, L, (uint32_t)(cnt - 1), f, pr);
+          }
+        }
+        if (staged) {
+          __syncthreads();
+          if (P.corrupt) {
+            for (uint32_t k = wid; k < nk; k += MG_TILE / 32) {
+              uint8_t *seq = stage + pad + slots[k].loff + slots[k].qlen + 1;
+              for (int pr = lane; 2 * pr < L; pr += 32)
+                corrupt_pair_philox(P, seq, seq + L + 3, L, (uint32_t)(base2 + k), f, pr);
+            }
+            __syncthreads();
+          }
+          // coalesced copy-out: smem and global share the same 16-byte phase (pad)
+          uint8_t *gdst = P.out[f] + goff;
+          const uint8_t *ssrc = stage + pad;
+          uint32_t head = (16u - pad) & 15u;
+          if (head > tile_bytes) head = tile_bytes;
+          if ((uint32_t)t < head) gdst[t] = ssrc[t];
+          uint32_t nvec = (tile_bytes - head) >> 4;
+          const uint4 *sv = reinterpret_cast<const uint4 *>(ssrc + head);
+          uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
+          for (uint32_t v = t; v < nvec; v += MG_TILE) gv[v] = sv[v];
+          uint32_t done = head + (nvec << 4);
+          if (done + t < tile_bytes) gdst[done + t] = ssrc[done + t];
+          __syncthreads();
+        }
+      }
+    }
+  }
+}
+
+int mg_unit_grid(int stage_cap, int n_tlen, int *smem_bytes) {
+  int smem = (int)(((size_t)n_tlen * sizeof(double) + 15) & ~(size_t)15) + stage_cap + 16;
+  *smem_bytes = smem;
+  cudaFuncSetAttribute(k_unit_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int per_sm = 0, dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unit_emit, MG_TILE, smem);
+  if (per_sm < 1) per_sm = 1;
+  return sms * per_sm;
+}
+
+void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st) {
+  if (P.n_tiles == 0) return;
+  if (grid > P.n_tiles) grid = P.n_tiles;
+  k_unit_emit<<<grid, MG_TILE, smem_bytes, st>>>(P);
+}
+
+// ------------------------------------------------------------------------------------------
+// generic exclusive scan of int64 (out[n] = total)
+
+#define SCAN_THREADS 256
+#define SCAN_PER_THREAD 4
+#define SCAN_PER_BLOCK (SCAN_THREADS * SCAN_PER_THREAD)
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int64_t *__restrict__ in, int64_t n, unsigned long long *partial) {
+  __shared__ unsigned long long s_w[SCAN_THREADS / 32];
+  int64_t i0 = (int64_t)blockIdx.x * SCAN_PER_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+  unsigned long long sum = 0;
+  for (int q = 0; q < SCAN_PER_THREAD; q++) if (i0 + q < n) sum += (unsigned long long)in[i0 + q];
+  sum = warp_sum_u64(sum);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tt = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; w++) tt += s_w[w];
+    partial[blockIdx.x] = tt;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const int64_t *__restrict__ in, int64_t *__restrict__ out, int64_t n,
+                                                             const unsigned long long *__restrict__ partial) {
+  __shared__ unsigned long long s_w[SCAN_THREADS / 32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t i0 = (int64_t)blockIdx.x * SCAN_PER_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+  unsigned long long v[SCAN_PER_THREAD], sum = 0;
+  for (int q = 0; q < SCAN_PER_THREAD; q++) { v[q] = (i0 + q < n) ? (unsigned long long)in[i0 + q] : 0; sum += v[q]; }
+  unsigned long long x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(FULL, x, d); if (lane >= d) x += y; }
+  if (lane == 31) s_w[wid] = x;
+  __syncthreads();
+  unsigned long long run = partial[blockIdx.x] + x - sum;
+  for (int w = 0; w < wid; w++) run += s_w[w];
+  for (int q = 0; q < SCAN_PER_THREAD; q++) {
+    if (i0 + q < n) out[i0 + q] = (int64_t)run;
+    run += v[q];
+    if (i0 + q == n - 1) out[n] = (int64_t)run;
+  }
+}
+
+int64_t mg_scan_tmp_elems(int64_t n) { return (n + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK + 1; }
+
+void mg_launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st) {
+  if (n == 0) { cudaMemsetAsync(out, 0, sizeof(int64_t), st); return; }
+  int nb = (int)((n + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
+  k_scan_reduce<<<nb, SCAN_THREADS, 0, st>>>(in, n, reinterpret_cast<unsigned long long *>(tmp));
+  k_scan_partials_u64<<<1, 1024, 0, st>>>(reinterpret_cast<unsigned long long *>(tmp), nb);
+  k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, reinterpret_cast<const unsigned long long *>(tmp));
+}
+
+// ------------------------------------------------------------------------------------------
+// FASTQ newline index
+
+#define NL_CHUNK 4096
+#define NL_THREADS 256
+
+int64_t mg_nl_chunks(int64_t len) { return (len + NL_CHUNK - 1) / NL_CHUNK; }
+
+__global__ void __launch_bounds__(NL_THREADS) k_nl_count(const uint8_t *__restrict__ buf, int64_t len, int64_t *__restrict__ cnt) {
+  __shared__ uint32_t s_w[NL_THREADS / 32];
+  int64_t base = (int64_t)blockIdx.x * NL_CHUNK + threadIdx.x * 16;
+  uint32_t c = 0;
+  for (int i = 0; i < 16; i++) if (base + i < len && buf[base + i] == '\n') c++;
+  for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t tt = 0; for (int w = 0; w < NL_THREADS / 32; w++) tt += s_w[w]; cnt[blockIdx.x] = tt; }
+}
+
+__global__ void __launch_bounds__(NL_THREADS) k_nl_write(const uint8_t *__restrict__ buf, int64_t len, const int64_t *__restrict__ off,
+                                                         int64_t *__restrict__ nl) {
+  __shared__ uint32_t s_w[NL_THREADS / 32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t base = (int64_t)blockIdx.x * NL_CHUNK + threadIdx.x * 16;
+  uint32_t m = 0;
+  for (int i = 0; i < 16; i++) if (base + i < len && buf[base + i] == '\n') m |= 1u << i;
+  uint32_t c = __popc(m);
+  uint32_t ic = warp_incl_scan_u32(c, lane);
+  if (lane == 31) s_w[wid] = ic;
+  __syncthreads();
+  uint32_t o = ic - c;
+  for (int w = 0; w < wid; w++) o += s_w[w];
+  int64_t dst = off[blockIdx.x] + o;
+  while (m) { int i = __ffs(m) - 1; m &= m - 1; nl[dst++] = base + i; }
+}
+
+void mg_launch_nl_count(const uint8_t *buf, int64_t len, int64_t *cnt, cudaStream_t st) {
+  if (len == 0) return;
+  k_nl_count<<<(unsigned)mg_nl_chunks(len), NL_THREADS, 0, st>>>(buf, len, cnt);
+}
+void mg_launch_nl_write(const uint8_t *buf, int64_t len, const int64_t *off, int64_t *nl, cudaStream_t st) {
+  if (len == 0) return;
+  k_nl_write<<<(unsigned)mg_nl_chunks(len), NL_THREADS, 0, st>>>(buf, len, off, nl);
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone corrupt-reads (readcorrupt.py:18-118 over illumina.py:113-162)
+
+__device__ __forceinline__ void fq_lines(const int64_t *nl, int64_t r, int64_t &h0, int64_t &h1, int64_t &s0, int64_t &s1) {
+  h0 = (r == 0) ? 0 : nl[4 * r - 1] + 1;   // header line [h0, h1)
+  h1 = nl[4 * r];
+  s0 = h1 + 1;                             // sequence line [s0, s1)
+  s1 = nl[4 * r + 1];
+}
+
+// sizes of the output records; sz[f][r] = 1 + name + 1 + L + 3 + L + 1 (readcorrupt.py:113)
+__global__ void __launch_bounds__(256) k_corrupt_sizes(MgCorruptParams P, int64_t *sz0, int64_t *sz1) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.n_rec) return;
+  int64_t h0, h1, s0, s1;
+  fq_lines(P.nl[0], r, h0, h1, s0, s1);
+  int64_t ne = h0 + 1;                     // FastxFile .name: up to the first whitespace
+  while (ne < h1) { uint8_t c = P.in[0][ne]; if (c == ' ' || c == '\t' || c == '\r') break; ne++; }
+  int64_t name_len = ne - (h0 + 1);
+  if (name_len < 0) name_len = 0;
+  int64_t L0 = s1 - s0;
+  if (L0 > P.n_cycles) atomicExch(P.err, 1ull);
+  sz0[r] = 2 * L0 + name_len + 6;
+  if (P.n_files > 1) {
+    fq_lines(P.nl[1], r, h0, h1, s0, s1);
+    int64_t L1 = s1 - s0;
+    if (L1 > P.n_cycles) atomicExch(P.err, 1ull);
+    sz1[r] = 2 * L1 + name_len + 6;
+  }
+}
+
+void mg_launch_corrupt_sizes(const MgCorruptParams &P, int64_t *sz0, int64_t *sz1, cudaStream_t st) {
+  if (P.n_rec == 0) return;
+  k_corrupt_sizes<<<(unsigned)((P.n_rec + 255) / 256), 256, 0, st>>>(P, sz0, sz1);
+}
+
+// one warp per template; lanes stride over name bytes and base-call pairs
+__global__ void __launch_bounds__(256) k_corrupt(MgCorruptParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < P.n_rec; r += warps) {
+    int64_t nh0, nh1, s0, s1;
+    fq_lines(P.nl[0], r, nh0, nh1, s0, s1);
+    for (int f = 0; f < P.n_files; f++) {
+      int64_t h0, h1;
+      if (f) fq_lines(P.nl[f], r, h0, h1, s0, s1);
+      const int64_t o = P.out_off[f][r];
+      const int L = (int)(s1 - s0);
+      const int name_len = (int)(P.out_off[f][r + 1] - o - 2 * (int64_t)L - 6);
+      uint8_t *out = P.out[f] + o;
+      const uint8_t *name = P.in[0] + nh0 + 1;                                 // read 1's name on both files
+      if (lane == 0) { out[0] = '@'; out[1 + name_len] = '\n'; }
+      for (int i = lane; i < name_len; i += 32) out[1 + i] = name[i];
+      uint8_t *seq = out + 2 + name_len, *qual = seq + L + 3;
+      const uint8_t *src = P.in[f] + s0;
+      for (int i = lane; i < L; i += 32) seq[i] = src[i];
+      if (lane == 0) { seq[L] = '\n'; seq[L + 1] = '+'; seq[L + 2] = '\n'; qual[L] = '\n'; }
+      __syncwarp();
+      if (L > P.n_cycles) continue;
+      if (P.mode == MG_MODE_DET) {
+        const int64_t d0 = P.draw_off[r * P.n_files + f];
+        for (int n = lane; n < L; n += 32) {
+          const double *row = P.cum_bq + ((size_t)f * P.n_cycles + n) * P.n_bq;
+          mg_corrupt_call(seq, qual, n, row, P.n_bq, P.phred, P.bq_rnd[d0 + n], P.call_rnd[d0 + n], (int)P.base_rnd[d0 + n]);
+        }
+      } else {
+        for (int pr = lane; 2 * pr < L; pr += 32) {
+          MgPhilox rr = mg_philox((uint32_t)r, (uint32_t)(r >> 32) * 2u + (uint32_t)f, (uint32_t)pr, MG_STREAM_CORRUPT, P.key0, P.key1);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            int n = 2 * pr + h;
+            if (n < L) {
+              const double *row = P.cum_bq + ((size_t)f * P.n_cycles + n) * P.n_bq;
+              mg_corrupt_call_philox(seq, qual, n, row, P.n_bq, P.phred, rr.v[2 * h], rr.v[2 * h + 1]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+void mg_launch_corrupt(const MgCorruptParams &P, cudaStream_t st) {
+  if (P.n_rec == 0) return;
+  int64_t blocks = (P.n_rec + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_corrupt<<<(unsigned)blocks, 256, 0, st>>>(P);
+}

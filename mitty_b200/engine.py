@@ -1,0 +1,206 @@
+"""Host-side handle on one GPU: a thin, typed layer over the C ABI (include/mitty_b200.h).
+
+One ``Engine`` = one ``mg_ctx`` = one GPU + one CUDA stream.  Everything numeric happens in the
+CUDA library; this module only moves numpy buffers across the boundary and turns status codes into
+the exceptions the reference raises (ValueError / IndexError).
+"""
+import ctypes as C
+
+import numpy as np
+
+from mitty_b200 import _lib
+from mitty_b200._lib import MODE_DET, MODE_EXPLICIT, MODE_PHILOX, UnitDesc
+
+SEED_MAX = (1 << 32) - 1  # illumina.py:9
+PHRED_P = 10 ** (-np.arange(100) / 10)  # illumina.py:137
+
+
+def _ptr(a):
+  return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class CopyHandle(object):
+  __slots__ = ('id', 'p_min', 'p_max', 'n_nodes', 'region')
+
+  def __init__(self, id_, p_min, p_max, n_nodes, region):
+    self.id, self.p_min, self.p_max, self.n_nodes, self.region = id_, p_min, p_max, n_nodes, region
+
+
+class Engine(object):
+  def __init__(self, device=0, stream=None):
+    self._L = _lib.lib()
+    h = C.c_void_p()
+    rc = self._L.mg_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+    if rc != 0:
+      raise RuntimeError('mitty_b200: cannot create a context on CUDA device {} (rc={}); the engine has no CPU fallback'.format(device, rc))
+    self._h = h
+    self.device = device
+    self.rlen = None
+    self._keep = []
+
+  def close(self):
+    if getattr(self, '_h', None):
+      self._L.mg_ctx_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  def _check(self, rc):
+    if rc == 0:
+      return
+    msg = self._L.mg_last_error(self._h).decode()
+    if rc == _lib.MG_EVALUE:
+      raise ValueError(msg)
+    if rc == _lib.MG_EINDEX:
+      raise IndexError(msg)
+    if rc == _lib.MG_ECAP:
+      raise BufferError(msg)
+    raise RuntimeError('mitty_b200 rc={}: {}'.format(rc, msg))
+
+  def synchronize(self):
+    self._check(self._L.mg_synchronize(self._h))
+
+  # -- model -------------------------------------------------------------------------------------
+  def load_model(self, model, rlen=None):
+    """model: dict with cum_tlen, cum_bq_mat (raw .pkl model or read_model_params output)."""
+    cum_tlen = np.ascontiguousarray(model['cum_tlen'], dtype=np.float64)
+    cum_bq = np.ascontiguousarray(model['cum_bq_mat'], dtype=np.float64)
+    if rlen is None:
+      rlen = model['rlen'] if 'rlen' in model else model['mean_rlen']
+    self.rlen = int(rlen)
+    self._check(self._L.mg_model_load(self._h, _ptr(cum_tlen), cum_tlen.size, _ptr(cum_bq), cum_bq.shape[0],
+                                      cum_bq.shape[1], cum_bq.shape[2], _ptr(PHRED_P), self.rlen))
+
+  # -- haplotypes --------------------------------------------------------------------------------
+  def load_region(self, ref_bytes, bed_start):
+    ref = np.ascontiguousarray(ref_bytes, dtype=np.uint8)
+    rid = C.c_int64(0)
+    self._check(self._L.mg_region_load(self._h, _ptr(ref) if ref.size else None, ref.size, int(bed_start), C.byref(rid)))
+    return rid.value
+
+  def free_region(self, rid):
+    self._check(self._L.mg_region_free(self._h, rid))
+
+  def build_copy(self, rid, vl):
+    """vl: mitty_b200.lib.vcfio.VariantList of the variants on this chromosome copy."""
+    cid, p_min, p_max, nn = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    n = len(vl)
+    alt_pool = vl.alt_pool if vl.alt_pool.size else np.zeros(1, dtype=np.uint8)
+    self._check(self._L.mg_copy_build(self._h, rid, n, _ptr(vl.pos), _ptr(vl.op), _ptr(vl.oplen), _ptr(alt_pool),
+                                      _ptr(vl.alt_off), C.byref(cid), C.byref(p_min), C.byref(p_max), C.byref(nn)))
+    return CopyHandle(cid.value, p_min.value, p_max.value, nn.value, rid)
+
+  def free_copy(self, cp):
+    self._check(self._L.mg_copy_free(self._h, cp.id))
+
+  def copy_nodes(self, cp):
+    """-> (ps, pr, op, oplen) arrays: the reference's Node fields (rpc.py:5-35)."""
+    n = cp.n_nodes
+    ps, pr, oplen = (np.empty(n, dtype=np.int64) for _ in range(3))
+    op = np.empty(n, dtype=np.uint8)
+    self._check(self._L.mg_copy_nodes(self._h, cp.id, _ptr(ps), _ptr(pr), _ptr(op), _ptr(oplen)))
+    return ps, pr, op, oplen
+
+  def copy_haplotype(self, cp):
+    out = np.empty(max(1, cp.p_max - cp.p_min), dtype=np.uint8)
+    self._check(self._L.mg_copy_haplotype(self._h, cp.id, _ptr(out), out.size))
+    return out[:cp.p_max - cp.p_min]
+
+  # -- units -------------------------------------------------------------------------------------
+  def _desc(self, cp, n, p, mode, seed, ts, u_tlen, tl, fo, prefix, mid, corrupt, corrupt_seed, p_min=0, p_max=0):
+    d = UnitDesc()
+    d.copy_id = cp.id if cp is not None else 0
+    d.n_candidates = int(n); d.p = float(p); d.mode = int(mode); d.unit_seed = int(seed) & 0xFFFFFFFF
+    keep = []
+    for name, a, dt in (('ts', ts, np.int64), ('u_tlen', u_tlen, np.float64), ('tl', tl, np.int64), ('fo', fo, np.int8)):
+      if a is not None:
+        a = np.ascontiguousarray(a, dtype=dt)
+        if a.size < n:
+          raise ValueError('{} has {} entries, {} candidates'.format(name, a.size, n))
+        keep.append(a)
+        setattr(d, name, a.ctypes.data)
+    d.qname_prefix = prefix.encode() if prefix is not None else None
+    d.qname_mid = mid.encode() if mid is not None else None
+    d.corrupt = int(bool(corrupt)); d.corrupt_seed = int(corrupt_seed) & 0xFFFFFFFF
+    d.p_min, d.p_max = int(p_min), int(p_max)
+    return d, keep
+
+  def sample_templates(self, n, p, mode, seed, cp=None, p_min=0, p_max=0, ts=None, u_tlen=None, tl=None):
+    """-> per-candidate (ts, te, fo); te == -1 where te >= p_max (illumina.py:66-76)."""
+    d, keep = self._desc(cp, n, p, mode, seed, ts, u_tlen, tl, None, None, None, 0, 0, p_min, p_max)
+    ts_o, te_o = np.empty(max(1, n), dtype=np.int64), np.empty(max(1, n), dtype=np.int64)
+    fo_o = np.empty(max(1, n), dtype=np.int8)
+    self._check(self._L.mg_sample_templates(self._h, C.byref(d), _ptr(ts_o), _ptr(te_o), _ptr(fo_o)))
+    return ts_o[:n], te_o[:n], fo_o[:n]
+
+  def generate_unit(self, cp, n, p, mode, seed, prefix, mid, ts=None, u_tlen=None, tl=None, fo=None,
+                    corrupt=False, corrupt_seed=0, out=None, fetch=True):
+    """One work unit -> (fastq1, fastq2, n_templates, n_te_kept).
+
+    out: optional pair of preallocated uint8 arrays (e.g. pinned) to receive the bytes; the
+    returned arrays are views of them.  fetch=False leaves the result on the device.
+    """
+    d, keep = self._desc(cp, n, p, mode, seed, ts, u_tlen, tl, fo, prefix, mid, corrupt, corrupt_seed)
+    nb, nt, nk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    if not fetch:
+      self._check(self._L.mg_unit_generate(self._h, C.byref(d), None, None, 0, C.byref(nb), C.byref(nt), C.byref(nk)))
+      return None, None, nt.value, nk.value, nb.value
+    if out is None:
+      est = int(n) * (2 * self.rlen + 120 + len(prefix) + len(mid)) // 1 + 4096
+      out = (np.empty(est, dtype=np.uint8), np.empty(est, dtype=np.uint8))
+    o1, o2 = out
+    rc = self._L.mg_unit_generate(self._h, C.byref(d), _ptr(o1), _ptr(o2), min(o1.size, o2.size), C.byref(nb), C.byref(nt), C.byref(nk))
+    if rc == _lib.MG_ECAP:
+      o1, o2 = np.empty(nb.value, dtype=np.uint8), np.empty(nb.value, dtype=np.uint8)
+      rc = self._L.mg_unit_generate(self._h, C.byref(d), _ptr(o1), _ptr(o2), nb.value, C.byref(nb), C.byref(nt), C.byref(nk))
+    self._check(rc)
+    return o1[:nb.value], o2[:nb.value], nt.value, nk.value, nb.value
+
+  # -- corruption --------------------------------------------------------------------------------
+  def corrupt_fastq(self, fq1, fq2=None, mode=MODE_PHILOX, seed=0, draws=None):
+    """Whole-buffer corrupt-reads.  fq1/fq2: bytes or uint8 arrays of 4-line FASTQ records.
+    draws (deterministic mode): (bq_rnd f64, call_rnd f64, base_rnd u8, draw_off i64[n_reads+1])."""
+    a1 = np.frombuffer(fq1, dtype=np.uint8) if not isinstance(fq1, np.ndarray) else fq1
+    a2 = None if fq2 is None else (np.frombuffer(fq2, dtype=np.uint8) if not isinstance(fq2, np.ndarray) else fq2)
+    if a1.size and a1[-1] != 10:
+      a1 = np.concatenate([a1, np.array([10], dtype=np.uint8)])
+    if a2 is not None and a2.size and a2[-1] != 10:
+      a2 = np.concatenate([a2, np.array([10], dtype=np.uint8)])
+    cap = int(a1.size + (a2.size if a2 is not None else 0)) + 64
+    o1 = np.empty(cap, dtype=np.uint8)
+    o2 = np.empty(cap, dtype=np.uint8) if a2 is not None else None
+    l1, l2, nt = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    bq = call = base = off = None
+    if mode == MODE_DET:
+      bq, call, base, off = draws
+      bq = np.ascontiguousarray(bq, dtype=np.float64); call = np.ascontiguousarray(call, dtype=np.float64)
+      base = np.ascontiguousarray(base, dtype=np.uint8); off = np.ascontiguousarray(off, dtype=np.int64)
+    self._check(self._L.mg_corrupt_fastq(self._h, _ptr(a1) if a1.size else _ptr(np.zeros(1, np.uint8)), a1.size,
+                                         _ptr(a2) if a2 is not None else None, a2.size if a2 is not None else 0,
+                                         int(mode), int(seed) & 0xFFFFFFFF, _ptr(bq), _ptr(call), _ptr(base), _ptr(off),
+                                         _ptr(o1), _ptr(o2), cap, C.byref(l1), C.byref(l2), C.byref(nt)))
+    return o1[:l1.value], (o2[:l2.value] if o2 is not None else None), nt.value
+
+  # -- profiling ---------------------------------------------------------------------------------
+  def prof_reset(self):
+    self._L.mg_prof_reset(self._h)
+
+  def prof(self):
+    ms, n, b, tl = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    self._L.mg_prof_get(self._h, C.byref(ms), C.byref(n), C.byref(b), C.byref(tl))
+    return {'emit_ms': ms.value, 'emit_launches': n.value, 'emit_bytes': b.value, 'total_launches': tl.value}
+
+
+_default = None
+
+
+def default_engine():
+  """Process-wide engine on cuda:0 for the plugin-style module functions."""
+  global _default
+  if _default is None:
+    _default = Engine(0)
+  return _default

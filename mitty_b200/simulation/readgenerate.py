@@ -1,0 +1,167 @@
+"""generate-reads: the orchestration of ``mitty/simulation/readgenerate.py`` on GPUs.
+
+Same entry point and arguments as the reference (``process_multi_threaded``,
+readgenerate.py:76-78); same work-unit schedule (``get_data_for_workers``, 129-159); same FASTQ /
+qname bytes (``fastq_lines``, 222-230).  What differs is where the work happens: every unit's
+template sampling, node lookup, sequence extraction, reverse complement and record formatting is
+one kernel launch (``k_unit_emit``); the host only walks the schedule and appends each unit's byte
+ranges to the two output files in schedule order.
+
+Modes
+  philox         production: all draws come from Philox4x32-10 on the device
+  deterministic  the reference's own numpy RandomState draws are made on the host and consumed on
+                 the device; the output equals the reference's ``--threads 1`` FASTQ byte for byte
+
+Multi-GPU: units are independent (each carries its own seed), so they are dealt to the GPUs by
+longest-processing-time-first; there is no collective, only the ordered concatenation done here.
+"""
+import logging
+import time
+
+import numpy as np
+
+import mitty_b200.lib.vcfio as vio
+from mitty_b200.engine import MODE_DET, MODE_PHILOX, SEED_MAX, Engine
+
+logger = logging.getLogger(__name__)
+
+__qname_format__ = '@read_serial|chrom|copy|strand|pos|rlen|cigar|vs1,vs2,...|strand|pos|rlen|cigar|vs1,vs2,...'
+__qname_format_details__ = """
+@read_serial|chrom|copy|strand|pos|rlen|cigar|vs1,vs2,...|strand|pos|rlen|cigar|vs1,vs2,...
+
+  read_serial  unique code for the template: sample:worker:unit:count
+  chrom        chromosome the read was taken from (as in the BED file)
+  copy         copy of the chromosome the read was taken from (0, 1, ...)
+  strand       forward strand (0) or reverse strand (1)
+  pos          position of the read, one based
+  rlen         read length
+  cigar        CIGAR of the read against the reference (ops: = X I D)
+  vs1,vs2,...  comma separated sizes of the variants the read covers (0 SNP, +n INS, -n DEL)
+
+The five per-read fields are repeated for the other read of the template (in file order).
+chrom and pos are one based to make comparing qname info in a genome browser easier.
+
+For reads from inside a long insertion the CIGAR has the format '>p:nI' where '>' marks a read
+inside a long insertion, p is how many bases into the insertion the read starts and n is the read
+length.
+"""
+
+
+def get_data_for_workers(model, vcf, seed):
+  """The reference's work-unit schedule (readgenerate.py:129-159): one unit per (region, copy,
+  pass), each with its own seed, then shuffled.  Yields dicts in consumption order."""
+  seed_rng = np.random.RandomState(seed)
+  shuffle_seed = seed_rng.randint(SEED_MAX)
+  region_list = [
+    {'region_idx': idx, 'region_cpy': cpy, 'rng_seed': seed_rng.randint(SEED_MAX)}
+    for idx, v in enumerate(vcf)
+    for cpy in range(len(v['v']))
+    for _ in range(model['passes'])
+  ]
+  logger.debug('{} passes will be made'.format(len(region_list)))
+  np.random.RandomState(shuffle_seed).shuffle(region_list)
+  for region in region_list:
+    yield region
+
+
+class RegionCache(object):
+  """Regions and chromosome copies resident in HBM, built on first use."""
+
+  def __init__(self, engine, vcf_df, fetch_ref):
+    self.engine, self.vcf_df, self.fetch_ref = engine, vcf_df, fetch_ref
+    self.regions, self.copies = {}, {}
+
+  def copy(self, r_idx, cpy):
+    key = (r_idx, cpy)
+    if key not in self.copies:
+      if r_idx not in self.regions:
+        region = self.vcf_df[r_idx]['region']
+        self.regions[r_idx] = self.engine.load_region(self.fetch_ref(region), region[1])
+      self.copies[key] = self.engine.build_copy(self.regions[r_idx], self.vcf_df[r_idx]['v'][cpy])
+    return self.copies[key]
+
+
+def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sample_name, worker_id, ps,
+                  mode='philox', corrupt=False, corrupt_seed=0, out=None, fetch=True):
+  """One work unit (the body of read_generating_worker's loop, readgenerate.py:183-214)
+  -> (fastq1 bytes, fastq2 bytes, template count)."""
+  n = int((cp.p_max - cp.p_min) * read_model['p'] * 1.2)          # illumina.py:69
+  prefix = '@{}:{}:{}:'.format(sample_name, worker_id, ps)         # readgenerate.py:195, 210
+  mid = '|{}|{}'.format(chrom, cpy)                                # readgenerate.py:223
+  if mode == 'deterministic':
+    ts, u, fo = read_module.unit_draws(read_model, cp.p_min, cp.p_max, rng_seed)
+    return engine.generate_unit(cp, n, read_model['p'], MODE_DET, rng_seed, prefix, mid, ts=ts, u_tlen=u, fo=fo,
+                                out=out, fetch=fetch)
+  if not (0 <= rng_seed <= SEED_MAX):
+    raise ValueError('Seed value {} is out of range 0 - {}'.format(rng_seed, SEED_MAX))
+  return engine.generate_unit(cp, n, read_model['p'], MODE_PHILOX, rng_seed, prefix, mid,
+                              corrupt=corrupt, corrupt_seed=corrupt_seed, out=out, fetch=fetch)
+
+
+def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_module, model, coverage,
+                           fastq1_fname, fastq2_fname, threads=2, seed=7, mode='philox', corrupt=False,
+                           corrupt_seed=None, device=0):
+  """Same signature as the reference (readgenerate.py:76-78) plus keyword-only extras.
+
+  threads is accepted for command-line compatibility; one GPU runs every unit of this process
+  (one process per GPU: see mitty_b200.multigpu for the sharded driver).  Output order and qname
+  serials are those of the reference's ``--threads 1`` run (worker id 0, unit index = schedule
+  index), whatever the GPU count.
+  """
+  read_model = read_module.read_model_params(model, coverage)
+  vcf_df = vio.load_variant_file(vcf_fname, sample_name, bed_fname)
+  fasta = vio.FastaFile(fasta_fname)
+  engine = Engine(device)
+  engine.load_model(read_model)
+  cache = RegionCache(engine, vcf_df, lambda region: fasta.fetch(reference=region[0], start=region[1], end=region[2]))
+
+  t0 = time.time()
+  total = 0
+  fastq_l = [open(fastq1_fname, 'wb')]
+  if fastq2_fname is not None:
+    fastq_l += [open(fastq2_fname, 'wb')]
+  try:
+    for ps, wd in enumerate(get_data_for_workers(read_model, vcf_df, seed)):
+      r_idx, cpy, rng_seed = wd['region_idx'], wd['region_cpy'], int(wd['rng_seed'])
+      region = vcf_df[r_idx]['region']
+      cp = cache.copy(r_idx, cpy)
+      f1, f2, cnt, _, _ = generate_unit(engine, read_module, read_model, cp, region[0], cpy, rng_seed, sample_name, 0, ps,
+                                        mode=mode, corrupt=corrupt,
+                                        corrupt_seed=seed if corrupt_seed is None else corrupt_seed)
+      for fp, r in zip(fastq_l, (f1, f2)):                          # writer, readgenerate.py:246-248
+        fp.write(memoryview(r))
+      total += cnt
+      logger.debug('Unit {} ({}, copy {}): {} templates'.format(ps, region, cpy, cnt))
+  finally:
+    for fp in fastq_l:
+      fp.close()
+    engine.close()
+  t1 = time.time()
+  logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s)'.format(total, t1 - t0, total / max(t1 - t0, 1e-9)))
+
+
+# ---- the qname contract's inverse (readgenerate.py:256-291) --------------------------------------
+
+from collections import namedtuple  # noqa: E402
+
+ri = namedtuple('ReadInfo', ['sample', 'rid', 'chrom', 'cpy', 'strand', 'pos', 'rlen', 'cigar', 'special_cigar', 'v_list'])
+
+
+def parse_qname(qname):
+  """qname (without the leading '@') -> one ReadInfo per read, in file order."""
+  def _parse_(_cigar, _v_list):
+    if _cigar[0] == '>':  # read from inside a long insertion
+      _special_cigar = _cigar
+      _cigar = _cigar.split(':')[-1]
+    else:
+      _special_cigar = None
+    return _cigar, _special_cigar, [int(v) for v in _v_list.split(',') if v != '']
+
+  d = qname.split('|')
+  rid, chrom, cpy = d[:3]
+  sample, _ = rid.split(':', 1)
+  cpy = int(cpy)
+  return [
+    ri(sample, rid, chrom, cpy, int(strand), int(pos), int(rlen), *_parse_(cigar, v_list))
+    for strand, pos, rlen, cigar, v_list in zip(d[3::5], d[4::5], d[5::5], d[6::5], d[7::5])
+  ]

@@ -104,3 +104,88 @@ def oracle_regions(regions):
 
 def model(name):
   return load_model(name)
+
+
+# ---- god-aligner style round trip -------------------------------------------------------------------
+
+class HaplotypeIndex(object):
+  """Independent re-derivation of reads from their qname, the way Mitty's god-aligner trusts it
+  (mitty/benchmarking/god_aligner.py:141-183 over readgenerate.parse_qname): POS is a REFERENCE
+  coordinate, so the read is located through a reference->haplotype map built from the oracle's
+  node list, then the CIGAR is walked over reference and haplotype together."""
+
+  def __init__(self, ref, ref_start_pos, cv):
+    self.nodes = oracle.create_node_list(ref, ref_start_pos, cv)
+    self.p_min = self.nodes[0][0]
+    self.hap = ''.join(n[4] for n in self.nodes)
+    self.ref = ref.tobytes().decode() if isinstance(ref, np.ndarray) else ref
+    self.ref_start = ref_start_pos
+    # reference position -> sample position for '=' and 'X' nodes
+    self.eq_pr = np.array([n[1] for n in self.nodes if n[2] in '=X'], dtype=np.int64)
+    self.eq_ps = np.array([n[0] for n in self.nodes if n[2] in '=X'], dtype=np.int64)
+    self.ins = {n[1]: n for n in self.nodes if n[2] == 'I'}   # keyed by pr
+
+  def ref_to_samp(self, pos):
+    k = np.searchsorted(self.eq_pr, pos, side='right') - 1
+    return int(self.eq_ps[k] + (pos - self.eq_pr[k]))
+
+  def check(self, info, seq):
+    """info: ReadInfo from parse_qname; seq: the FASTQ sequence as written. Returns None or an error string."""
+    import re
+    comp = str.maketrans('ATCGN', 'TAGCN')
+    fwd = seq.translate(comp)[::-1] if info.strand else seq    # god_aligner.py:163-166
+    if info.special_cigar is not None:
+      m = re.match(r'>(\d+):(\d+)I', info.special_cigar)
+      node = self.ins.get(info.pos + 1)
+      if node is None:
+        return 'no insertion after pos {}'.format(info.pos)
+      off, n = int(m.group(1)), int(m.group(2))
+      return None if node[4][off:off + n] == fwd else 'inside-insertion read mismatch'
+    ops = re.findall(r'(\d+)(\D)', info.cigar)
+    if sum(int(c) for c, o in ops if o != 'D') != info.rlen or len(fwd) != info.rlen:
+      return 'cigar length != rlen'
+    rp, i = info.pos, 0
+    first = True
+    for c, o in ops:
+      c = int(c)
+      if o == '=':
+        if self.ref[rp - self.ref_start:rp - self.ref_start + c] != fwd[i:i + c]:
+          return '= segment differs from the reference at {}'.format(rp)
+        rp += c; i += c
+      elif o == 'X':
+        s = self.ref_to_samp(rp) - self.p_min
+        if self.hap[s:s + c] != fwd[i:i + c]:
+          return 'X base differs from the haplotype at {}'.format(rp)
+        rp += c; i += c
+      elif o == 'I':
+        node = self.ins.get(rp)
+        if node is None:
+          return 'no insertion at {}'.format(rp)
+        ins = node[4]
+        if (ins[len(ins) - c:] if first else ins[:c]) != fwd[i:i + c]:
+          return 'inserted bases differ at {}'.format(rp)
+        i += c
+      elif o == 'D':
+        rp += c
+      else:
+        return 'unexpected op ' + o
+      first = False
+    return None
+
+
+def roundtrip_fastq(f1, f2, index_for):
+  """Every read of a FASTQ pair re-derived from its qname. index_for(chrom, cpy) -> HaplotypeIndex.
+  Returns (reads checked, list of errors)."""
+  from mitty_b200.simulation.readgenerate import parse_qname
+  errs, n = [], 0
+  for buf in (f1, f2):
+    lines = buf.decode().split('\n')
+    which = 0 if buf is f1 else 1
+    for k in range(0, len(lines) - 1, 4):
+      infos = parse_qname(lines[k][1:])
+      info = infos[which]
+      e = index_for(info.chrom, info.cpy).check(info, lines[k + 1])
+      n += 1
+      if e:
+        errs.append((lines[k], e))
+  return n, errs

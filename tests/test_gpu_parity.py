@@ -1,0 +1,226 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI
+(libmitty_b200.so) and is compared with the oracle / the golden vectors of the reference:
+bit-exact for every byte and index."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from mitty_b200 import synth
+from mitty_b200.lib import vcfio
+from tests import helpers as H
+from tests.test_oracle_golden import RPC_KAT_CPY0, RPC_KAT_CPY1
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+  from mitty_b200.engine import Engine
+  e = Engine(0)
+  yield e
+  e.close()
+
+
+def gpu_generate(eng, wl, model, coverage, seed, mode, corrupt=False, regions=None):
+  """In-memory generate-reads: the loop of readgenerate.process_multi_threaded without files."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  regions = regions or H.workload_regions(wl)
+  rm = il.read_model_params(model, coverage)
+  eng.load_model(rm)
+  cache = rg.RegionCache(eng, regions, None)
+  cache.fetch_ref = lambda region: next(r['ref'] for r in regions if r['region'] == region)
+  o1, o2, total = [], [], 0
+  for ps, wd in enumerate(rg.get_data_for_workers(rm, regions, seed)):
+    r_idx, cpy = wd['region_idx'], wd['region_cpy']
+    cp = cache.copy(r_idx, cpy)
+    f1, f2, cnt, _, _ = rg.generate_unit(eng, il, rm, cp, regions[r_idx]['region'][0], cpy, int(wd['rng_seed']), wl['sample'], 0, ps,
+                                         mode=mode, corrupt=corrupt, corrupt_seed=seed)
+    o1.append(f1.tobytes()); o2.append(f2.tobytes()); total += cnt
+  for cp in cache.copies.values():
+    eng.free_copy(cp)
+  for rid in cache.regions.values():
+    eng.free_region(rid)
+  return b''.join(o1), b''.join(o2), total
+
+
+# ---- the reference's own KATs through the device ---------------------------------------------------
+
+def test_tiny_node_list_and_reads(eng, tmp_path):
+  """test_rpc.py:111-180 through mg_copy_build / k_hap_build / k_unit_emit."""
+  import mitty_b200.simulation.rpc as rpc
+  p = H.write_tiny(tmp_path)
+  vcf = vcfio.load_variant_file(p['vcf'], 'g0_s0', p['whole_bed'])
+  nl = rpc.create_node_list(H.TINY_SEQ, 1, vcf[0]['v'][1], engine=eng)
+  assert nl.tuples() == [
+    (1, 1, '=', 4, 'ATGA', None), (5, 5, 'X', 1, 'T', 0), (6, 6, '=', 3, 'GTA', None),
+    (9, 9, 'I', 3, 'TTT', 3), (12, 9, '=', 3, 'TCC', None), (14, 14, 'D', 2, '', -2),
+    (15, 14, '=', 7, 'GGAGGCG', None), (21, 25, 'D', 4, '', -4), (22, 25, '=', 1, 'C', None)]
+  for pp, l, n0, n1, want in RPC_KAT_CPY1:
+    got = rpc.generate_read(pp, l, nl)
+    if got is not None:   # None: template end on/after p_max, never sampled by the reference
+      assert got == want
+  assert rpc.generate_read(9, 2, nl) == (8, '>0:2I', [3], 'TT')
+  assert rpc.generate_read(1, 10, nl) == (1, '4=1X3=2I', [0, 3], 'ATGATGTATT')
+  nl.free()
+  nl = rpc.create_node_list(H.TINY_SEQ, 1, vcf[0]['v'][0], engine=eng)
+  for pp, l, n0, n1, want in RPC_KAT_CPY0:
+    assert rpc.generate_read(pp, l, nl) == want
+  nl.free()
+
+
+def test_edge_nodes_and_haplotypes(eng):
+  """Node tables and packed haplotypes of every (region, copy) of the edge workload == oracle."""
+  import mitty_b200.simulation.rpc as rpc
+  for r in H.workload_regions(synth.edge_workload()):
+    for vl in r['v']:
+      nl = rpc.create_node_list(r['ref'], r['region'][1] + 1, vl, engine=eng)
+      assert nl.tuples() == oracle.create_node_list(r['ref'], r['region'][1] + 1, H.oracle_cv(vl))
+      nl.free()
+
+
+def test_deletion_across_region_end_is_rejected(eng):
+  import mitty_b200.simulation.rpc as rpc
+  vl = vcfio.VariantList.from_variants([vcfio.Variant(20, 'GTTAC', 'G', 'D', 4)])
+  with pytest.raises(ValueError):
+    rpc.create_node_list(H.TINY_SEQ[:23], 1, vl, engine=eng)
+
+
+# ---- template sampling (plugin generate_reads) -----------------------------------------------------
+
+def test_generate_reads_plugin_golden(eng):
+  """illumina.generate_reads (deterministic draws, device searchsorted/filter) == the reference."""
+  import mitty_b200.simulation.illumina as il
+  z = np.load(os.path.join(H.GOLDEN, 'templates.npz'))
+  for key in sorted({k.rsplit('_', 1)[0] for k in z.files}):
+    name, p_min, p_max, seed = key.rsplit('_', 3)
+    rm = il.read_model_params(H.model(name + '.pkl'), 30.0)
+    r = il.generate_reads(rm, int(p_min), int(p_max), int(seed), engine=eng)
+    np.testing.assert_array_equal(r[0]['pos'], z[key + '_pos0'])
+    np.testing.assert_array_equal(r[1]['pos'], z[key + '_pos1'])
+    np.testing.assert_array_equal(r[0]['file_order'], z[key + '_fo0'])
+    np.testing.assert_array_equal(r[1]['file_order'], z[key + '_fo1'])
+    assert r[0]['len'].dtype == np.uint32 and (r[0]['len'] == rm['rlen']).all()
+  with pytest.raises(ValueError):
+    il.generate_reads(il.read_model_params(H.model('1kg-pcr-free.pkl'), 30.0), 1, 1000, 1 << 32, engine=eng)
+
+
+# ---- explicit templates: every corner of the emit kernel -------------------------------------------
+
+@pytest.mark.parametrize('L', [150, 37, 16, 1, 250])
+def test_edge_units_explicit(eng, L):
+  from mitty_b200.engine import MODE_EXPLICIT
+  regs = H.workload_regions(synth.edge_workload())
+  rs = np.random.RandomState(L)
+  eng.load_model({'cum_tlen': np.array([1.0]), 'cum_bq_mat': np.ones((2, 300, 94)), 'rlen': L})
+  total = 0
+  for ri, r in enumerate(regs):
+    rid = eng.load_region(r['ref'], r['region'][1])
+    for cpy, vl in enumerate(r['v']):
+      cp = eng.build_copy(rid, vl)
+      n = 3000
+      ts = rs.randint(cp.p_min - 2, cp.p_max, size=n).astype(np.int64)
+      ts[:5] = cp.p_min + np.arange(5)
+      tl = rs.randint(0, 3 * L + 40, size=n).astype(np.int64)
+      tl[5:10] = L
+      ts[5:10] = cp.p_max - L - 1 - np.arange(5)
+      fo = rs.randint(0, 2, size=n).astype(np.int8)
+      f1, f2, cnt, nk, nb = eng.generate_unit(cp, n, 0.5, MODE_EXPLICIT, 0, '@EDGE:0:{}:'.format(ri), '|{}|{}'.format(r['region'][0], cpy),
+                                              ts=ts, tl=tl, fo=fo)
+      te = ts + np.maximum(tl, L)
+      keep = (te < cp.p_max) & (ts >= cp.p_min)
+      assert nk == keep.sum()
+      o1, o2, ocnt = oracle.generate_unit(r['ref'], r['region'][1] + 1, H.oracle_cv(vl), L, ts[keep], te[keep], fo[:keep.sum()],
+                                          'EDGE:0:{}'.format(ri), r['region'][0], cpy)
+      assert cnt == ocnt
+      assert f1.tobytes() == o1 and f2.tobytes() == o2
+      total += cnt
+      eng.free_copy(cp)
+    eng.free_region(rid)
+  assert total > 5000
+
+
+def test_empty_and_tiny_units(eng):
+  from mitty_b200.engine import MODE_EXPLICIT
+  eng.load_model({'cum_tlen': np.array([1.0]), 'cum_bq_mat': np.ones((2, 300, 94)), 'rlen': 10})
+  rid = eng.load_region(np.frombuffer(H.TINY_SEQ.encode(), dtype=np.uint8), 0)
+  cp = eng.build_copy(rid, vcfio.VariantList.from_variants([]))
+  assert (cp.p_min, cp.p_max, cp.n_nodes) == (1, 26, 1)
+  f1, f2, cnt, nk, nb = eng.generate_unit(cp, 0, 0.5, MODE_EXPLICIT, 0, '@s:0:0:', '|1|0',
+                                          ts=np.zeros(1, np.int64), tl=np.zeros(1, np.int64), fo=np.zeros(1, np.int8))
+  assert (cnt, nk, nb, f1.size, f2.size) == (0, 0, 0, 0, 0)
+  f1, f2, cnt, nk, nb = eng.generate_unit(cp, 1, 0.5, MODE_EXPLICIT, 0, '@s:0:0:', '|1|0',
+                                          ts=np.array([3], np.int64), tl=np.array([12], np.int64), fo=np.ones(1, np.int8))
+  assert f1.tobytes() == b'@s:0:0:1|1|0|1|5|10|10=||0|3|10|10=|\nCTTGGATACG\n+\n~~~~~~~~~~\n'
+  assert f2.tobytes() == b'@s:0:0:1|1|0|1|5|10|10=||0|3|10|10=|\nGACGTATCCA\n+\n~~~~~~~~~~\n'
+  eng.free_copy(cp); eng.free_region(rid)
+
+
+# ---- deterministic mode: byte-exact against the reference -------------------------------------------
+
+@pytest.mark.parametrize('name,wl_fn', [('edge', synth.edge_workload), ('edge250', synth.edge_workload),
+                                        ('mid', lambda: synth.config1(contig_len=100000)),
+                                        ('config1', synth.config1)])
+def test_deterministic_fastq_golden(eng, name, wl_fn):
+  """generate-reads (+ corrupt-reads) in deterministic mode == the unmodified reference with
+  --threads 1 (golden sha256 from tests/golden/make_golden.py; edge also byte-compared)."""
+  import mitty_b200.simulation.illumina as il
+  from mitty_b200.engine import MODE_DET
+  import mitty_b200.simulation.readcorrupt as rc
+  info = H.golden()['fastq'][name]
+  m = H.model(info['model'])
+  wl = wl_fn()
+  f1, f2, n = gpu_generate(eng, wl, m, info['coverage'], info['seed'], 'deterministic')
+  assert n == info['pairs']
+  if name == 'edge':
+    assert f1 == H.golden_fastq('edge.r1.fq.gz') and f2 == H.golden_fastq('edge.r2.fq.gz')
+  assert (len(f1), H.sha256(f1)) == (info['r1']['bytes'], info['r1']['sha256'])
+  assert (len(f2), H.sha256(f2)) == (info['r2']['bytes'], info['r2']['sha256'])
+  if 'c1' not in info:
+    return
+  a1, a2 = np.frombuffer(f1, dtype=np.uint8), np.frombuffer(f2, dtype=np.uint8)
+  ws = int(np.random.RandomState(info['seed']).randint(il.SEED_MAX))
+  l1, l2 = rc.seq_lengths(a1), rc.seq_lengths(a2)
+  lens = np.empty(2 * l1.size, dtype=np.int64); lens[0::2] = l1; lens[1::2] = l2
+  eng.load_model(m)
+  c1, c2, cn = eng.corrupt_fastq(a1, a2, mode=MODE_DET, draws=il.corrupt_draws(lens.tolist(), np.random.RandomState(ws)))
+  assert cn == info['pairs']
+  if name == 'edge':
+    assert c1.tobytes() == H.golden_fastq('edge.c1.fq.gz') and c2.tobytes() == H.golden_fastq('edge.c2.fq.gz')
+  assert H.sha256(c1.tobytes()) == info['c1']['sha256'] and H.sha256(c2.tobytes()) == info['c2']['sha256']
+
+
+def test_corrupt_template_plugin_golden(eng):
+  import mitty_b200.simulation.illumina as il
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  for case in H.golden()['corrupt_template']:
+    out = il.corrupt_template(m, tuple(case['in']), np.random.RandomState(case['seed']), engine=eng)
+    assert [list(o) for o in out] == case['out']
+
+
+def test_corrupt_read_longer_than_model(eng):
+  m = dict(H.model('hiseq-X-v2.5-Garvan.pkl'))
+  eng.load_model(m)
+  s = 'A' * 301
+  with pytest.raises(IndexError):
+    eng.corrupt_fastq('@q\n{}\n+\n{}\n'.format(s, s).encode())
+
+
+def test_cli_files_deterministic(tmp_path):
+  """The command line end to end on files (FASTA / VCF.gz / BED in, two FASTQ out)."""
+  from click.testing import CliRunner
+  from mitty_b200.cli import cli
+  info = H.golden()['fastq']['edge']
+  wl = synth.edge_workload()
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'), gz=True)
+  r1, r2, c1, c2 = (str(tmp_path / x) for x in ('r1.fq', 'r2.fq', 'c1.fq', 'c2.fq'))
+  res = CliRunner().invoke(cli, ['generate-reads', fa, vcf, wl['sample'], bed, info['model'], str(info['coverage']), str(info['seed']),
+                                 r1, '--fastq2', r2, '--threads', '1', '--deterministic'], catch_exceptions=False)
+  assert res.exit_code == 0, res.output
+  assert open(r1, 'rb').read() == H.golden_fastq('edge.r1.fq.gz') and open(r2, 'rb').read() == H.golden_fastq('edge.r2.fq.gz')
+  res = CliRunner().invoke(cli, ['corrupt-reads', info['model'], r1, c1, str(info['seed']), '--fastq2-in', r2, '--fastq2-out', c2,
+                                 '--threads', '1', '--deterministic'], catch_exceptions=False)
+  assert res.exit_code == 0, res.output
+  assert open(c1, 'rb').read() == H.golden_fastq('edge.c1.fq.gz') and open(c2, 'rb').read() == H.golden_fastq('edge.c2.fq.gz')

@@ -1,0 +1,341 @@
+"""bench.py -- read pairs/s of the read-generation hot path (generate-reads + Illumina corruption).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[2] -- one chr1-shaped synthetic contig
+(249,250,621 bp, ~10 % N in long runs, ~330 k SNP/indel records, diploid), 30x, 2x150
+(hiseq-X-v2.5-Garvan model, the shipped 150-bp model), production (Philox) mode with
+the corruption model fused into the emit kernel.  One STEP = the whole contig at 30x: both
+chromosome copies built from the resident packed reference, then all 4 work units
+(2 copies x 2 passes, ~25 M read pairs, ~18 GB of FASTQ).  With N GPUs every rank runs its own
+chr1-shaped contig (different seed): units are independent, there is no collective on the data
+path ("weak" scaling); torch.distributed is used only for the barrier and the max/sum of timings.
+
+value   pairs/s with inputs resident in HBM (packed reference, variant arrays on the host side of
+        mg_copy_build), outputs left in HBM; timed with CUDA events on the launch stream.
+e2e     the same step through the C ABI with HOST buffers: raw reference bytes H2D + packing,
+        copy builds, units, and every FASTQ byte D2H into pinned memory, inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = 'hiseq-X-v2.5-Garvan.pkl'
+COVERAGE = 30.0
+SLICE = 10000000  # CPU-baseline sample: one 10 Mb slice of the same contig
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--contig-len', type=int, default=249250621)
+  ap.add_argument('--seed', type=int, default=7)
+  ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--perfect', action='store_true', help='perfect reads only (no fused corruption)')
+  return ap.parse_args()
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+  Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+  def __init__(self, index):
+    self.index, self.rows, self.p = index, [], None
+
+  def start(self):
+    try:
+      self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+    except Exception:
+      self.p = None
+
+  def _read(self):
+    for line in self.p.stdout:
+      self.rows.append([x.strip() for x in line.split(',')])
+
+  def stop(self):
+    if self.p is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    self.p.terminate()
+    try:
+      self.p.wait(timeout=5)
+    except Exception:
+      self.p.kill()
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2]))
+        for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+          if v.lower().startswith('active'):
+            reasons.add(name)
+      except Exception:
+        pass
+    return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    try:
+      return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)'
+    except Exception:
+      pass
+  return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def make_workload(args, rank):
+  from mitty_b200 import synth
+  from mitty_b200.lib import vcfio
+  length = args.contig_len
+  scale = length / 249250621.0
+  wl = synth.chr1_shaped(seed=args.seed + 101 * rank, length=length, n_runs=max(3, int(39 * scale)))
+  region = wl['regions'][0]
+  r = vcfio.from_variant_table(wl['tables'][0], region)
+  return wl, region, r
+
+
+# ---- CPU baseline (the oracle: plain-C port of the reference algorithm) ------------------------------
+
+def _cpu_unit(job):
+  """One oracle work unit on a slice: generate-reads + corrupt-reads (single thread)."""
+  import oracle
+  ref, start, vl_arrays, rm_small, seed, cum_bq = job
+  cv = oracle.CopyVariants(*vl_arrays)
+  p_min, p_max, _ = oracle.node_span(ref, start + 1, cv)
+  t0 = time.perf_counter()
+  ts, te, fo = oracle.templates(rm_small['p'], rm_small['rlen'], rm_small['cum_tlen'], p_min, p_max, seed)
+  f1, f2, n = oracle.generate_unit(ref, start + 1, cv, rm_small['rlen'], ts, te, fo, 'S:0:0', '1', 0)
+  c1, c2, _ = oracle.corrupt_fastq(cum_bq, seed, f1, f2)
+  return n, time.perf_counter() - t0
+
+
+def cpu_jobs(args, wl, n_jobs):
+  import mitty_b200.simulation.illumina as il
+  from mitty_b200.lib import vcfio
+  from mitty_b200.readmodels import load_model
+  model = load_model(MODEL)
+  rm = il.read_model_params(model, COVERAGE)
+  rm_small = {'p': rm['p'], 'rlen': int(rm['rlen']), 'cum_tlen': np.asarray(rm['cum_tlen'])}
+  seq = wl['contigs'][0][1]
+  length = seq.shape[0]
+  sl = min(SLICE, length)
+  jobs = []
+  for k in range(n_jobs):
+    # slices are taken from the non-N part of the contig, round robin
+    start = int((length // 3 + k * sl) % max(1, length - sl))
+    region = ('1', start, start + sl)
+    r = vcfio.from_variant_table(wl['tables'][0], region)
+    vl = r['v'][k % 2]
+    # keep variants fully inside the slice (no deletion across the slice end)
+    keep = (vl.pos > start + 1000) & (vl.pos < start + sl - 1000)
+    idx = np.flatnonzero(keep)
+    alts = [vl.alt_pool[vl.alt_off[i]:vl.alt_off[i + 1]].tobytes().decode() for i in idx]
+    jobs.append((np.ascontiguousarray(seq[start:start + sl]), start, (vl.pos[idx], vl.op[idx], vl.oplen[idx], alts), rm_small,
+                 1000 + k, np.asarray(model['cum_bq_mat'])))
+  return jobs, sl
+
+
+def cpu_baseline(args, wl, procs):
+  import multiprocessing as mp
+  jobs, sl = cpu_jobs(args, wl, procs)
+  t0 = time.perf_counter()
+  if procs == 1:
+    res = [_cpu_unit(jobs[0])]
+  else:
+    with mp.get_context('fork').Pool(procs) as pool:
+      res = pool.map(_cpu_unit, jobs)
+  wall = time.perf_counter() - t0
+  pairs = sum(r[0] for r in res)
+  return pairs, wall, sl
+
+
+def run_reference(args):
+  """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure
+  Python and cannot travel to the GPU box) on all host cores, on bounded samples of the workload."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  import oracle
+  oracle.build()
+  cores = os.cpu_count() or 1
+  procs = max(1, min(cores, 64))
+  wl, region, r = make_workload(args, 0)
+  times, pairs = [], 0
+  for s in range(args.warmup + args.steps):
+    n, wall, sl = cpu_baseline(args, wl, procs)
+    if s >= args.warmup:
+      times.append(wall); pairs += n
+  value = pairs / sum(times)
+  sample = '{} processes x one {} Mb-slice work unit (generate + corrupt, ~{} pairs) per step'.format(procs, sl // 1000000, pairs // max(1, args.steps))
+  line = {'impl': 'reference', 'metric': 'read pairs/sec (2x150, FASTQ-formatted, corrupted)', 'value': value, 'unit': 'pairs/s',
+          'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
+          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+          'config': config_dict(args),
+          'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': procs, 'kind': 'port', 'sample': sample},
+          'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+  print(json.dumps(line))
+
+
+def config_dict(args):
+  return {'workload': 'configs[2]: chr1-shaped synthetic contig ({} bp, ~10% N, GIAB-density diploid VCF), 30x paired 2x150, '
+                      'Philox mode{}'.format(args.contig_len, '' if args.perfect else ' + fused Illumina corruption'),
+          'read_model': MODEL + ' (mean_rlen 150)', 'coverage': COVERAGE, 'units_per_step': 4, 'seed': args.seed,
+          'parallelism': 'one contig per GPU, units independent, no collective',
+          'l2': 'each unit streams ~4.6 GB of FASTQ through L2 (>> 126 MB), so nothing is re-read warm between timed units'}
+
+
+# ---- the engine --------------------------------------------------------------------------------------
+
+def main():
+  args = parse()
+  if args.impl == 'reference':
+    return run_reference(args)
+
+  import torch
+  import torch.distributed as dist
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  from mitty_b200.engine import Engine
+  from mitty_b200.readmodels import load_model
+
+  model = load_model(MODEL)
+  rm = il.read_model_params(model, COVERAGE)
+  L = int(rm['rlen'])
+  wl, region, r = make_workload(args, rank)
+  stream = torch.cuda.Stream()
+  eng = Engine(local, stream=stream.cuda_stream)
+  eng.load_model(rm)
+  ref_host = torch.from_numpy(np.ascontiguousarray(wl['contigs'][0][1])).pin_memory()
+  ref_np = ref_host.numpy()
+  corrupt = not args.perfect
+
+  units = [(cpy, ps) for cpy in range(len(r['v'])) for ps in range(rm['passes'])]
+
+  def step(seed, rid, out=None, fetch=False):
+    """Both copies built from the region, then the 4 units. Returns (pairs, fastq bytes)."""
+    pairs = nbytes = 0
+    copies = [eng.build_copy(rid, vl) for vl in r['v']]
+    for k, (cpy, ps) in enumerate(units):
+      _, _, cnt, _, nb = rg.generate_unit(eng, il, rm, copies[cpy], region[0], cpy, (seed * 7919 + k * 104729) & 0xFFFFFFFF,
+                                          wl['sample'], 0, k, mode='philox', corrupt=corrupt, corrupt_seed=seed, out=out, fetch=fetch)
+      pairs += cnt; nbytes += 2 * nb
+    for cp in copies:
+      eng.free_copy(cp)
+    return pairs, nbytes
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  # ---- value: inputs resident in HBM, outputs stay in HBM
+  rid = eng.load_region(ref_np, region[1])
+  for w in range(args.warmup):
+    step(1000 + w, rid)
+  barrier()
+  eng.prof_reset()
+  clocks = ClockSampler(local); clocks.start()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  pairs = nbytes = 0
+  with torch.cuda.stream(stream):
+    ev0.record(stream)
+    for s in range(args.steps):
+      p_, b_ = step(2000 + s, rid)
+      pairs += p_; nbytes += b_
+    ev1.record(stream)
+  barrier()
+  ms = ev0.elapsed_time(ev1)
+  clk = clocks.stop()
+  prof = eng.prof()
+  eng.free_region(rid)
+
+  # ---- e2e: host buffers in, host buffers out
+  e2e = None
+  if not args.no_e2e:
+    est = int((args.contig_len * rm['p'] * 1.2) * (2 * L + 110)) + (1 << 20)
+    out = (torch.empty(est, dtype=torch.uint8).pin_memory().numpy(), torch.empty(est, dtype=torch.uint8).pin_memory().numpy())
+    def e2e_step(seed):
+      rid_ = eng.load_region(ref_np, region[1])
+      p_, b_ = step(seed, rid_, out=out, fetch=True)
+      eng.free_region(rid_)
+      return p_, b_
+    for w in range(min(args.warmup, 3)):
+      e2e_step(3000 + w)
+    barrier()
+    t0 = time.perf_counter()
+    ep = eb = 0
+    for s in range(args.steps):
+      p_, b_ = e2e_step(4000 + s)
+      ep += p_; eb += b_
+    torch.cuda.synchronize()
+    e_wall = time.perf_counter() - t0
+    h2d = ref_np.nbytes + sum(v.pos.nbytes + v.op.nbytes + v.oplen.nbytes + v.alt_pool.nbytes + v.alt_off.nbytes for v in r['v'])
+    e2e = [ep, e_wall, h2d, eb / max(1, args.steps)]
+
+  # ---- aggregate over ranks: max time, summed work
+  if world > 1:
+    t = torch.tensor([ms, e2e[1] if e2e else 0.0], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    w_ = torch.tensor([pairs, e2e[0] if e2e else 0, nbytes], dtype=torch.float64, device='cuda')
+    dist.all_reduce(w_, op=dist.ReduceOp.SUM)
+    ms, e_wall_max = float(t[0]), float(t[1])
+    pairs_all, e_pairs_all = float(w_[0]), float(w_[1])
+  else:
+    pairs_all, e_pairs_all, e_wall_max = float(pairs), float(e2e[0]) if e2e else 0.0, e2e[1] if e2e else 0.0
+
+  if rank == 0:
+    peak, peak_src = measured_peak()
+    # dominant kernel: k_unit_emit.  Algorithmic bytes per launch = FASTQ bytes written (both files)
+    # + 2 * ceil(L/4) haplotype bytes read per pair, over the CUDA-event time of the
+    # emit launches (events recorded around each launch on the launch stream inside the library).
+    alg = nbytes + pairs * 2 * ((L + 3) // 4)
+    ach = alg / (prof['emit_ms'] * 1e-3) / 1e9 if prof['emit_ms'] > 0 else 0.0
+    line = {'metric': 'read pairs/sec (2x150, FASTQ-formatted, corrupted)' if corrupt else 'read pairs/sec (2x150, FASTQ-formatted, perfect reads)',
+            'value': pairs_all / (ms * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
+            'data': 'synthetic', 'config': config_dict(args), 'clocks': clk,
+            'gpu_launches': prof['total_launches'],
+            'roofline': {'bound': 'hbm', 'kernel': 'k_unit_emit', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                         'traffic': None, 'peak_source': peak_src, 'launches': prof['emit_launches'],
+                         'avg_launch_ms': prof['emit_ms'] / max(1, prof['emit_launches']),
+                         'algorithmic_bytes_per_pair': alg / max(1, pairs)}}
+    if e2e:
+      line['e2e'] = {'value': e_pairs_all / e_wall_max, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(e2e[2]), 'd2h_bytes_per_step': int(e2e[3]),
+                     'sink': 'pinned host memory'}
+    if not args.no_cpu_baseline and world == 1:
+      import oracle
+      oracle.build()
+      n, wall, sl = cpu_baseline(args, wl, 1)
+      line['cpu_baseline'] = {'value': n / wall, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port',
+                              'sample': 'one {} Mb-slice work unit of the same contig (generate + corrupt, {} pairs), C oracle, 1 thread'.format(sl // 1000000, n)}
+    print(json.dumps(line))
+  eng.close()
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -49,7 +49,8 @@ struct Copy {
   std::vector<MgExc> exc;
   MgNode *d_nodes = nullptr; uint32_t *d_hap = nullptr; uint32_t *d_blk = nullptr; MgExc *d_exc = nullptr;
   int n_blk = 0; int64_t hap_words = 0;
-  ~Copy() { cudaFree(d_nodes); cudaFree(d_hap); cudaFree(d_blk); cudaFree(d_exc); }
+  mg_ctx *owner = nullptr;
+  ~Copy();
 };
 
 const int BLK_SHIFT = 8;
@@ -62,8 +63,12 @@ struct mg_ctx {
   bool own_stream = false;
   std::string err;
   // model
-  DevBuf m_tlen, m_bq, m_phred;
+  DevBuf m_tlen, m_bq, m_phred, m_alias[2], m_err;   // alias[0]: 64-entry rows, alias[1]: 128-entry rows
   int n_tlen = 0, n_mates = 0, n_cycles = 0, n_bq = 0, rlen = 0;
+  int n64 = 0;   // leading cycles whose rows (all mates) put no mass on BQ >= 64: 64-entry alias rows are exact there
+  std::vector<uint32_t> h_alias[2]; std::vector<MgErr> h_err;
+  std::vector<std::pair<void *, size_t>> pool;   // device blocks of freed copies, reused by the next build
+  std::map<void *, size_t> block_size;
   // handles
   std::map<int64_t, std::unique_ptr<Region>> regions;
   std::map<int64_t, std::unique_ptr<Copy>> copies;
@@ -86,11 +91,70 @@ int fail(mg_ctx *c, int code, const char *fmt, ...) {
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, MG_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+// Vose alias table for one (mate, cycle) row of the quality model.  Outcome b = number of CDF
+// entries < u (searchsorted side='left', illumina.py:156) clipped to 93; entry = prob24 << 7 | alias.
+void build_alias_row(const double *cum, int n_bq, int K, uint32_t *out) {
+  std::vector<double> q(K, 0.0);
+  double prev = 0.0;
+  for (int b = 0; b < n_bq; b++) {
+    double c = cum[b]; if (c > 1.0) c = 1.0; if (c < prev) c = prev;
+    if (std::min(b, 93) < K) q[std::min(b, 93)] += c - prev;   // 64-entry rows are only used where this mass is zero
+    prev = c;
+  }
+  if (std::min(n_bq, 93) < K) q[std::min(n_bq, 93)] += 1.0 - prev;
+  std::vector<int> small, large;
+  for (int i = 0; i < K; i++) { q[i] *= K; (q[i] < 1.0 ? small : large).push_back(i); }
+  std::vector<double> prob(K, 1.0); std::vector<int> alias(K);
+  for (int i = 0; i < K; i++) alias[i] = i;
+  while (!small.empty() && !large.empty()) {
+    int s = small.back(); small.pop_back();
+    int l = large.back(); large.pop_back();
+    prob[s] = q[s]; alias[s] = l;
+    q[l] = (q[l] + q[s]) - 1.0;
+    (q[l] < 1.0 ? small : large).push_back(l);
+  }
+  for (int i = 0; i < K; i++) {
+    double pr = prob[i] < 0.0 ? 0.0 : (prob[i] > 1.0 ? 1.0 : prob[i]);
+    uint32_t pq = (uint32_t)std::floor(pr * 16777216.0 + 0.5);
+    if (pq > (1u << 24)) pq = 1u << 24;
+    out[i] = (pq << 7) | (uint32_t)alias[i];
+  }
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+}  // namespace
+
+namespace {
+
+// Device blocks of freed chromosome copies are kept and handed to the next build: cudaMalloc /
+// cudaFree synchronise the device and cost milliseconds for haplotype-sized blocks.
+cudaError_t pool_get(mg_ctx *ctx, void **p, size_t bytes) {
+  int best = -1;
+  for (size_t i = 0; i < ctx->pool.size(); i++)
+    if (ctx->pool[i].second >= bytes && ctx->pool[i].second <= 2 * bytes + (1u << 20) &&
+        (best < 0 || ctx->pool[i].second < ctx->pool[best].second)) best = (int)i;
+  if (best >= 0) { *p = ctx->pool[best].first; ctx->pool.erase(ctx->pool.begin() + best); return cudaSuccess; }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaSuccess) ctx->block_size[*p] = bytes;
+  return e;
+}
+
+void pool_free(mg_ctx *ctx, void *p) {
+  if (!p) return;
+  if (ctx) {
+    auto it = ctx->block_size.find(p);
+    if (it != ctx->block_size.end() && ctx->pool.size() < 64) { ctx->pool.push_back({p, it->second}); return; }
+    if (it != ctx->block_size.end()) ctx->block_size.erase(it);
+  }
+  cudaFree(p);
+}
+
+Copy::~Copy() { pool_free(owner, d_nodes); pool_free(owner, d_hap); pool_free(owner, d_blk); pool_free(owner, d_exc); }
 
 }  // namespace
 
@@ -121,6 +185,8 @@ void mg_ctx_destroy(mg_ctx *ctx) {
   DeviceGuard g(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->regions.clear(); ctx->copies.clear();
+  for (auto &b : ctx->pool) cudaFree(b.first);
+  ctx->pool.clear(); ctx->block_size.clear();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -147,8 +213,47 @@ int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double 
   CU(cudaMemcpyAsync(ctx->m_tlen.p, cum_tlen, sizeof(double) * n_tlen, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->m_bq.p, cum_bq_mat, sizeof(double) * (size_t)n_mates * n_cycles * n_bq, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->m_phred.p, phred_p, sizeof(double) * 100, cudaMemcpyHostToDevice, ctx->stream));
+  // production-mode tables: alias rows per (mate, cycle) and integer error thresholds per BQ.
+  // Rows are built twice: 64 entries (one 256-byte line pair per warp-wide lookup; exact while all
+  // mass sits on BQ < 64, true for every cycle < max_rlen of the shipped models) and 128 entries.
+  int n64 = n_cycles;
+  for (int m = 0; m < n_mates; m++)
+    for (int c = 0; c < n_cycles; c++) {
+      const double *row = cum_bq_mat + ((size_t)m * n_cycles + c) * n_bq;
+      const double at63 = n_bq > 63 ? row[63] : (n_bq ? row[n_bq - 1] : 0.0);   // mass on outcomes <= 63
+      if (n_bq == 0 || at63 < 1.0) { if (c < n64) n64 = c; break; }
+    }
+  for (int t = 0; t < 2; t++) {
+    const int K = 64 << t;
+    ctx->h_alias[t].assign((size_t)n_mates * n_cycles * K, 0u);
+    for (size_t r = 0; r < (size_t)n_mates * n_cycles; r++)
+      if (t == 1 || (int)(r % n_cycles) < n64) build_alias_row(cum_bq_mat + r * n_bq, n_bq, K, ctx->h_alias[t].data() + r * K);
+    CU(ctx->m_alias[t].need(4 * ctx->h_alias[t].size()));
+    CU(cudaMemcpyAsync(ctx->m_alias[t].p, ctx->h_alias[t].data(), 4 * ctx->h_alias[t].size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->h_err.assign(128, MgErr{0, 0, 0, 0});
+  for (int b = 0; b < 100; b++) {
+    double pe = phred_p[b];
+    uint32_t thr = pe >= 1.0 ? 0xFFFFFFFFu : (pe <= 0.0 ? 0u : (uint32_t)std::floor(pe * 4294967296.0));
+    ctx->h_err[b] = MgErr{thr, thr / 3u, (uint32_t)((2ull * thr) / 3ull), 0};
+  }
+  CU(ctx->m_err.need(sizeof(MgErr) * 128));
+  CU(cudaMemcpyAsync(ctx->m_err.p, ctx->h_err.data(), sizeof(MgErr) * 128, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  ctx->n_tlen = n_tlen; ctx->n_mates = n_mates; ctx->n_cycles = n_cycles; ctx->n_bq = n_bq; ctx->rlen = rlen;
+  ctx->n_tlen = n_tlen; ctx->n_mates = n_mates; ctx->n_cycles = n_cycles; ctx->n_bq = n_bq; ctx->rlen = rlen; ctx->n64 = n64;
+  return MG_OK;
+}
+
+int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t alias_cap, int32_t *n64, uint32_t *err_out) {
+  if (!ctx || ctx->rlen == 0) return fail(ctx, MG_EINVAL, "no read model loaded");
+  if (kshift != 6 && kshift != 7) return fail(ctx, MG_EINVAL, "kshift must be 6 or 7");
+  const std::vector<uint32_t> &h = ctx->h_alias[kshift - 6];
+  if (n64) *n64 = ctx->n64;
+  if (alias_out) {
+    if (alias_cap < (int64_t)h.size()) return fail(ctx, MG_ECAP, "alias table needs %lld entries", (long long)h.size());
+    memcpy(alias_out, h.data(), 4 * h.size());
+  }
+  if (err_out) memcpy(err_out, ctx->h_err.data(), sizeof(MgErr) * 128);
   return MG_OK;
 }
 
@@ -311,10 +416,11 @@ int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *
   const int64_t alt_bytes = n_var ? alt_off[n_var] : 0;
   C->hap_words = (hap_len + 15) / 16;
   C->n_blk = (int)((hap_len >> BLK_SHIFT) + 1);
-  CU(cudaMalloc(&C->d_nodes, sizeof(MgNode) * nn));
-  CU(cudaMalloc(&C->d_hap, sizeof(uint32_t) * (C->hap_words + 2 * MG_HAP_PAD)));
-  CU(cudaMalloc(&C->d_blk, sizeof(uint32_t) * C->n_blk));
-  CU(cudaMalloc(&C->d_exc, sizeof(MgExc) * std::max<size_t>(1, C->exc.size())));
+  C->owner = ctx;
+  CU(pool_get(ctx, (void **)&C->d_nodes, sizeof(MgNode) * nn));
+  CU(pool_get(ctx, (void **)&C->d_hap, sizeof(uint32_t) * (C->hap_words + 2 * MG_HAP_PAD)));
+  CU(pool_get(ctx, (void **)&C->d_blk, sizeof(uint32_t) * C->n_blk));
+  CU(pool_get(ctx, (void **)&C->d_exc, sizeof(MgExc) * std::max<size_t>(1, C->exc.size())));
   CU(cudaMemcpyAsync(C->d_nodes, dn.data(), sizeof(MgNode) * nn, cudaMemcpyHostToDevice, ctx->stream));
   if (!C->exc.empty()) CU(cudaMemcpyAsync(C->d_exc, C->exc.data(), sizeof(MgExc) * C->exc.size(), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(C->d_hap, 0, sizeof(uint32_t) * (C->hap_words + 2 * MG_HAP_PAD), ctx->stream));
@@ -476,8 +582,12 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
   CU(cudaMemcpyAsync(strb.as<uint8_t>() + pl, d->qname_mid, ml, cudaMemcpyHostToDevice, ctx->stream));
   P.prefix = strb.as<uint8_t>(); P.prefix_len = pl; P.mid = strb.as<uint8_t>() + pl; P.mid_len = ml;
 
-  P.corrupt = d->corrupt; P.cum_bq = ctx->m_bq.as<double>(); P.n_cycles = ctx->n_cycles; P.n_bq = ctx->n_bq;
-  P.phred = ctx->m_phred.as<double>(); P.key_cor0 = d->corrupt_seed; P.key_cor1 = d->unit_seed ^ 0x636f7231u;
+  if (pl > MG_QN_MAX || ml > MG_QN_MAX) return fail(ctx, MG_EVALUE, "sample / chromosome name too long for the qname buffers (%d)", MG_QN_MAX);
+  P.corrupt = d->corrupt;
+  P.cor.kshift = (L <= ctx->n64) ? 6 : 7;
+  P.cor.alias = ctx->m_alias[P.cor.kshift - 6].as<uint32_t>(); P.cor.err = ctx->m_err.as<MgErr>(); P.cor.n_cycles = ctx->n_cycles;
+  P.cor.k0 = d->corrupt_seed; P.cor.k1 = d->unit_seed ^ 0x636f7231u;
+  P.L_nd = mg_ndigits32((uint32_t)L);
 
   P.n_tiles = (int)((n + MG_TILE - 1) / MG_TILE);
   int stage = MG_TILE * (2 * L + 80);
@@ -567,7 +677,10 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
   if (nf == 2) n_rec = std::min(n_rec, n_lines[1] / 4);
   P.n_rec = n_rec; P.n_files = nf;
   P.cum_bq = ctx->m_bq.as<double>(); P.n_cycles = ctx->n_cycles; P.n_bq = ctx->n_bq; P.phred = ctx->m_phred.as<double>();
-  P.mode = mode; P.key0 = seed; P.key1 = 0x636f7232u;
+  P.mode = mode;
+  P.cor.kshift = 7;   // any read length up to n_cycles
+  P.cor.alias = ctx->m_alias[1].as<uint32_t>(); P.cor.err = ctx->m_err.as<MgErr>(); P.cor.n_cycles = ctx->n_cycles;
+  P.cor.k0 = seed; P.cor.k1 = 0x636f7232u;
   if (out_len1) *out_len1 = 0;
   if (out_len2) *out_len2 = 0;
   if (n_templates) *n_templates = n_rec;

@@ -19,6 +19,11 @@
 #else
 #define MG_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define MG_UNROLL _Pragma("unroll")
+#else
+#define MG_UNROLL
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Data layout in HBM
@@ -164,19 +169,33 @@ MG_HD uint32_t mg_permute(uint32_t i, uint32_t n, uint32_t half_bits, uint32_t k
 // ------------------------------------------------------------------------------------------
 // Decimal helpers
 
+MG_HD int mg_ndigits32(uint32_t v) {   // branch-free: no division
+  return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+         (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
+
 MG_HD int mg_ndigits(uint64_t v) {
+  if (v <= 0xFFFFFFFFull) return mg_ndigits32((uint32_t)v);
   int d = 1;
   while (v >= 10) { v /= 10; d++; }
   return d;
 }
 
+MG_HD int mg_nchars_int(int64_t v) { return v < 0 ? 1 + mg_ndigits((uint64_t)(-v)) : mg_ndigits((uint64_t)v); }
+
 // sum of the decimal lengths of 1..m  (closed form; used to place records whose qname carries a
-// serial number that is only known after the block/grid scan)
+// serial number that is only known after the block/grid scan):  d*(m+1) - 11..1 (d ones)
 MG_HD uint64_t mg_digit_sum(uint64_t m) {
   if (m == 0) return 0;
   int d = mg_ndigits(m);
   uint64_t ones = 0, p = 1;
-  for (int k = 0; k < d; k++) { ones += p; p *= 10; }
+  if (d <= 10) {
+    const uint32_t t = (uint32_t)d;
+    ones = t == 1 ? 1ull : t == 2 ? 11ull : t == 3 ? 111ull : t == 4 ? 1111ull : t == 5 ? 11111ull : t == 6 ? 111111ull :
+           t == 7 ? 1111111ull : t == 8 ? 11111111ull : t == 9 ? 111111111ull : 1111111111ull;
+  } else {
+    for (int k = 0; k < d; k++) { ones += p; p *= 10; }
+  }
   return (uint64_t)d * (m + 1) - ones;
 }
 
@@ -229,8 +248,17 @@ struct MgWordStream {
 };
 
 template <class W>
-MG_HD void mg_put_uint(W &w, uint64_t v) {
-  // digits are stacked as nibbles in a register (no local-memory array): v < 10^16
+MG_HD void mg_put_u32(W &w, uint32_t v) {
+  // digits are stacked as nibbles in a register pair (no local-memory array); /10 is a multiply
+  uint64_t acc = 0;
+  int n = 0;
+  do { uint32_t q = v / 10u; acc = (acc << 4) | (v - q * 10u); v = q; n++; } while (v);
+  for (; n; n--) { w.put((uint8_t)('0' + ((uint32_t)acc & 15u))); acc >>= 4; }
+}
+
+template <class W>
+MG_HD void mg_put_uint(W &w, uint64_t v) {   // v < 10^16
+  if (v <= 0xFFFFFFFFull) { mg_put_u32(w, (uint32_t)v); return; }
   uint64_t acc = 0;
   int n = 0;
   do { acc = (acc << 4) | (v % 10); v /= 10; n++; } while (v);
@@ -264,45 +292,89 @@ MG_HD int mg_find_node(NP nodes, BP blk, int blk_shift, int n_blk, int n_nodes, 
   return lo;
 }
 
+// Per-read geometry shared by the sizing pass and the formatting pass.
+//   pos (rpc.py:148-158), whether the read lies inside one insertion (rpc.py:149-154) and the
+//   last node n1 = searchsorted(keys, x+L-1, 'right') - 1, found by walking forward from n0.
+template <class NP>
+MG_HD int mg_last_node(NP nodes, int n0, int n_nodes, uint32_t x, int L) {
+  const uint32_t last = x + (uint32_t)L - 1u;
+  int n1 = n0;
+  while (n1 + 1 < n_nodes && nodes[n1 + 1].key <= last) n1++;
+  return n1;
+}
+
+MG_HD int32_t mg_read_pos(const MgNode &f, bool single, uint32_t x) {
+  if (f.op == 'I') return single ? f.pr - 1 : f.pr;                         // rpc.py:148-156
+  const int64_t ps0 = (int64_t)f.key - (f.op == 'D' ? 1 : 0);
+  return (int32_t)((int64_t)x - ps0 + (int64_t)f.pr);                        // rpc.py:158
+}
+
+MG_HD int32_t mg_cigar_len(const MgNode &n, uint32_t x, int L) {             // rpc.py:145
+  if (n.op == 'D') return n.oplen;
+  int64_t a = (int64_t)x - (int64_t)n.key; if (a < 0) a = 0;
+  int64_t b = (int64_t)x + L - (int64_t)n.key; if ((int64_t)n.oplen < b) b = n.oplen;
+  return (int32_t)(b - a);
+}
+
+template <class W>
+MG_HD void mg_put_i32(W &w, int32_t v) {
+  if (v < 0) { w.put('-'); mg_put_u32(w, (uint32_t)(-(int64_t)v)); } else mg_put_u32(w, (uint32_t)v);
+}
+
+MG_HD int mg_nchars_i32(int32_t v) { return v < 0 ? 1 + mg_ndigits32((uint32_t)(-(int64_t)v)) : mg_ndigits32((uint32_t)v); }
+
+// length of '|strand|pos|rlen|cigar|vlist' for one read; L_nd = decimal digits of L
+template <class NP>
+MG_HD uint32_t mg_read_fields_len(NP nodes, int n0, int n1, uint32_t x, int L, int L_nd) {
+  const MgNode f = nodes[n0];
+  const bool single = (n0 == n1);
+  uint32_t n = 2u + 1u + (uint32_t)mg_nchars_i32(mg_read_pos(f, single, x)) + 1u + (uint32_t)L_nd + 1u + 1u;
+  if (single && f.op == '=') return n + (uint32_t)L_nd + 1u;                 // "<L>=" and an empty v_list
+  if (single && f.op == 'I')                                                 // ">p:<L>I" and "<oplen>"
+    return n + 1u + (uint32_t)mg_nchars_i32((int32_t)((int64_t)x - (int64_t)f.key)) + 1u + (uint32_t)L_nd + 1u + (uint32_t)mg_nchars_i32(f.oplen);
+  uint32_t nv = 0;
+  for (int k = n0; k <= n1; k++) {
+    const MgNode nd = nodes[k];
+    n += (uint32_t)mg_nchars_i32(mg_cigar_len(nd, x, L)) + 1u;
+    if (nd.op != '=') {
+      n += (nv ? 1u : 0u) + (nd.op == 'X' ? 1u : nd.op == 'I' ? (uint32_t)mg_nchars_i32(nd.oplen) : (uint32_t)mg_nchars_i32(-nd.oplen));
+      nv++;
+    }
+  }
+  return n;
+}
+
 // '|strand|pos|rlen|cigar|vlist' for one read (fastq_lines, readgenerate.py:224-225, over
 // generate_read, rpc.py:144-158).  x = read start relative to p_min, L = read length.
 template <class W, class NP>
 MG_HD void mg_fmt_read(W &w, NP nodes, int n0, int n1, uint32_t x, int L, int strand) {
-  MgNode f = nodes[n0];
-  int64_t ps0 = (int64_t)f.key - (f.op == 'D' ? 1 : 0);
-  int64_t pos;
-  bool inside_ins = (f.op == 'I') && (n0 == n1);
-  if (f.op == 'I') pos = inside_ins ? (int64_t)f.pr - 1 : (int64_t)f.pr;      // rpc.py:148-156
-  else pos = (int64_t)x - ps0 + (int64_t)f.pr;                               // rpc.py:158
+  const MgNode f = nodes[n0];
+  const bool single = (n0 == n1);
   w.put('|'); w.put((uint8_t)('0' + strand));
-  w.put('|'); mg_put_int(w, pos);
-  w.put('|'); mg_put_uint(w, (uint64_t)L);
+  w.put('|'); mg_put_i32(w, mg_read_pos(f, single, x));
+  w.put('|'); mg_put_u32(w, (uint32_t)L);
   w.put('|');
-  if (inside_ins) {                                                          // rpc.py:154
-    w.put('>'); mg_put_int(w, (int64_t)x - ps0); w.put(':'); mg_put_uint(w, (uint64_t)L); w.put('I');
+  if (single && f.op == '=') {                                               // the common case: "<L>=" + empty v_list
+    mg_put_u32(w, (uint32_t)L); w.put('='); w.put('|');
+    return;
+  }
+  if (single && f.op == 'I') {                                               // rpc.py:154
+    w.put('>'); mg_put_i32(w, (int32_t)((int64_t)x - (int64_t)f.key)); w.put(':'); mg_put_u32(w, (uint32_t)L); w.put('I');
   } else {
     for (int k = n0; k <= n1; k++) {                                         // rpc.py:145
-      MgNode n = nodes[k];
-      int64_t len;
-      if (n.op != 'D') {
-        int64_t ps = (int64_t)n.key;
-        int64_t a = (int64_t)x - ps; if (a < 0) a = 0;
-        int64_t b = (int64_t)x + L - ps; if ((int64_t)n.oplen < b) b = n.oplen;
-        len = b - a;
-      } else len = n.oplen;
-      mg_put_int(w, len); w.put((uint8_t)n.op);
+      const MgNode n = nodes[k];
+      mg_put_i32(w, mg_cigar_len(n, x, L)); w.put((uint8_t)n.op);
     }
   }
   w.put('|');
   bool first = true;
   for (int k = n0; k <= n1; k++) {                                           // rpc.py:144
-    MgNode n = nodes[k];
+    const MgNode n = nodes[k];
     if (n.op == '=') continue;
     if (!first) w.put(',');
     first = false;
     if (n.op == 'X') w.put('0');
-    else if (n.op == 'I') mg_put_int(w, (int64_t)n.oplen);
-    else mg_put_int(w, -(int64_t)n.oplen);
+    else mg_put_i32(w, n.op == 'I' ? n.oplen : -n.oplen);
   }
 }
 
@@ -441,6 +513,120 @@ MG_HD void mg_emit_record(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, in
   ws.put('\n');
   ws.end();
   if (n_exc) mg_patch_exc(dst + qlen + 1, exc, n_exc, mine.x, L, mine.strand);
+}
+
+// The other file's record has the same qname, the same offsets and (for perfect reads) the same
+// quality line: only the L sequence bytes are rewritten in place.
+template <class HP, class EP>
+MG_HD void mg_rewrite_seq(uint8_t *seq_dst, MgReadRef mine, int L, HP hap, EP exc, int n_exc) {
+  MgWordStream ws;
+  ws.begin(seq_dst);
+  mg_emit_seq(ws, hap, mine.x, L, mine.strand);
+  ws.end();
+  if (n_exc) mg_patch_exc(seq_dst, exc, n_exc, mine.x, L, mine.strand);
+}
+
+// qname line + the three separator newlines of a record whose SEQ / QUAL lines are written by
+// mg_emit_seq_corrupt (fused corruption).
+template <class NP>
+MG_HD void mg_emit_frame(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
+                         const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
+  MgWordStream ws;
+  ws.begin(dst);
+  mg_fmt_qname(ws, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
+  ws.put('\n');
+  ws.end();
+  uint8_t *p = dst + qlen + 1 + L;
+  p[0] = '\n'; p[1] = '+'; p[2] = '\n'; p[3 + L] = '\n';
+}
+
+// ------------------------------------------------------------------------------------------
+// Production-mode corruption (Philox draws, alias-method quality sampling).
+//
+// Draw layout (the specification tests/philox_ref.py restates in numpy): for template serial s
+// (0-based count within the unit), file f and cycle pair q = n / 2,
+//     r = Philox4x32-10(counter = (s, f, q, MG_STREAM_CORRUPT), key = (k0, k1))
+// cycle 2q uses (r[0], r[1]), cycle 2q+1 uses (r[2], r[3]) as (w_bq, w_call):
+//     idx = w_bq >> (32 - kshift); frac = (w_bq << kshift) >> 8        (24 bits)
+//     e = alias[(f * n_cycles + n) << kshift | idx]; bq = frac < (e >> 7) ? idx : (e & 127)
+//     error iff w_call < thr[bq], thr = min(2^32-1, floor(phred_p[bq] * 2^32))   (illumina.py:137,159)
+//     substituted base = base_rot[base][(w_call >= thr/3) + (w_call >= 2*thr/3)]  (illumina.py:131-136,160;
+//     given an error, w_call is uniform on [0, thr), so no third draw is needed)
+struct alignas(16) MgErr { uint32_t thr, t1, t2, pad; };
+
+struct MgCorruptCtx {
+  const uint32_t *alias;   // [n_mates][n_cycles][1 << kshift]
+  const MgErr *err;        // [128]
+  int kshift, n_cycles;
+  uint32_t k0, k1;
+};
+
+MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &base, uint32_t &qual) {
+  const uint32_t idx = w_bq >> (32 - C.kshift);
+  const uint32_t frac = (w_bq << C.kshift) >> 8;
+  const uint32_t e = C.alias[(((size_t)f * C.n_cycles + (size_t)n) << C.kshift) | idx];
+  const uint32_t bq = frac < (e >> 7) ? idx : (e & 127u);
+  const MgErr t = C.err[bq];
+  if (w_call < t.thr) base = mg_base_rot((uint8_t)base, (int)(w_call >= t.t1) + (int)(w_call >= t.t2));
+  qual = bq + 33u;
+}
+
+// SEQ and QUAL lines of one read, corrupted on the fly: every thread of a warp is at the same
+// cycle of its own record, so the alias row (one 256-byte line pair) is shared by the warp.
+template <class HP, class EP>
+MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgReadRef mine, int L, HP hap, EP exc, int n_exc,
+                               const MgCorruptCtx &C, uint32_t serial, uint32_t f) {
+  MgWordStream ws, wq;
+  ws.begin(seq_dst); wq.begin(qual_dst);
+  const int nchunk = (L + 15) >> 4;
+  for (int c = 0; c < nchunk; c++) {
+    uint32_t codes;
+    if (mine.strand == 0) codes = mg_codes16(hap, (int64_t)mine.x + 16 * c);
+    else codes = mg_revcomp16(mg_codes16(hap, (int64_t)mine.x + L - 16 * (int64_t)c - 16));
+    MG_UNROLL
+    for (int q = 0; q < 4; q++) {
+      const int n0 = 16 * c + 4 * q;
+      if (n0 < L) {
+        uint32_t ch = mg_chars4((codes >> (8 * q)) & 0xFFu), qw = 0;
+        MG_UNROLL
+        for (int h = 0; h < 2; h++) {
+          if (n0 + 2 * h < L) {
+            const MgPhilox r = mg_philox(serial, f, (uint32_t)((n0 >> 1) + h), MG_STREAM_CORRUPT, C.k0, C.k1);
+            MG_UNROLL
+            for (int e = 0; e < 2; e++) {
+              const int j = 2 * h + e, n = n0 + j;
+              if (n < L) {
+                uint32_t base = (ch >> (8 * j)) & 0xFFu, qual;
+                mg_corrupt_one(C, f, n, e ? r.v[2] : r.v[0], e ? r.v[3] : r.v[1], base, qual);
+                ch = (ch & ~(0xFFu << (8 * j))) | (base << (8 * j));
+                qw |= qual << (8 * j);
+              }
+            }
+          }
+        }
+        if (n0 + 4 <= L) { ws.put_word(ch); wq.put_word(qw); }
+        else for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
+      }
+    }
+  }
+  ws.end(); wq.end();
+  if (n_exc) {
+    // bases in exception runs: the reference substitutes 'N' for any non-ACGT base on an error
+    // (base_rot.get(base, 'NNN'), illumina.py:160) and leaves it alone otherwise
+    for (int k = mg_exc_first(exc, n_exc, mine.x); k < n_exc; k++) {
+      const MgExc e = exc[k];
+      if ((uint64_t)e.start >= (uint64_t)mine.x + L) break;
+      uint64_t a = e.start > mine.x ? e.start : mine.x;
+      uint64_t b = (uint64_t)e.start + e.len < (uint64_t)mine.x + L ? (uint64_t)e.start + e.len : (uint64_t)mine.x + L;
+      for (uint64_t i = a; i < b; i++) {
+        const int idx = (int)(i - mine.x), n = mine.strand ? (L - 1 - idx) : idx;
+        const MgPhilox r = mg_philox(serial, f, (uint32_t)(n >> 1), MG_STREAM_CORRUPT, C.k0, C.k1);
+        uint32_t base = e.byte, qual;
+        mg_corrupt_one(C, f, n, (n & 1) ? r.v[2] : r.v[0], (n & 1) ? r.v[3] : r.v[1], base, qual);
+        seq_dst[n] = (uint8_t)base;
+      }
+    }
+  }
 }
 
 // One base call with explicit draws (deterministic mode: the reference's own numpy draws)

@@ -5,6 +5,7 @@
 #include "mg_core.cuh"
 
 #define MG_TILE 128          // candidates (and threads) per emit tile
+#define MG_QN_MAX 192        // max length of the qname prefix / mid strings
 #define MG_HAP_PAD 8         // 32-bit words of padding on both sides of a packed sequence
 
 enum { MG_MODE_PHILOX = 0, MG_MODE_DET = 1, MG_MODE_EXPLICIT = 2 };
@@ -32,8 +33,9 @@ struct MgUnitParams {
   // outputs
   uint8_t *out[2]; uint64_t cap;
   uint64_t *rec_off;         // optional: byte offset of every record (+ total at [n])
-  // fused corruption (PHILOX draws)
-  int corrupt; const double *cum_bq; int n_cycles, n_bq; const double *phred; uint32_t key_cor0, key_cor1;
+  // fused corruption (PHILOX draws, alias tables)
+  int corrupt; MgCorruptCtx cor;
+  int L_nd;                  // decimal digits of rlen
   // grid-wide scan state
   unsigned long long *descA, *descB; uint32_t *tile_counter;
   unsigned long long *totals;  // [0] te<p_max survivors, [1] templates written, [2] bytes per file, [3] overflow
@@ -52,7 +54,7 @@ struct MgCorruptParams {     // standalone corrupt-reads over FASTQ resident in 
   int64_t n_rec; int n_files;
   const double *cum_bq; int n_cycles, n_bq; const double *phred;
   int mode;                  // MG_MODE_PHILOX / MG_MODE_DET
-  uint32_t key0, key1;
+  MgCorruptCtx cor;          // PHILOX: alias tables + keys
   const double *bq_rnd, *call_rnd; const uint8_t *base_rnd; const int64_t *draw_off;  // DET: per read [2*n_rec+1]
   unsigned long long *err;   // [0] != 0 -> a read is longer than the model
 };

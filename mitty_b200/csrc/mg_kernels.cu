@@ -363,19 +363,6 @@ __device__ Agg tile_lookback(const MgUnitParams &P, int tile, int lane) {
   return ex;
 }
 
-__device__ __forceinline__ void corrupt_pair_philox(const MgUnitParams &P, uint8_t *seq, uint8_t *qual, int L, uint32_t serial,
-                                                    int f, int pr) {
-  MgPhilox r = mg_philox(serial, (uint32_t)f, (uint32_t)pr, MG_STREAM_CORRUPT, P.key_cor0, P.key_cor1);
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    int n = 2 * pr + h;
-    if (n < L) {
-      const double *row = P.cum_bq + ((size_t)f * P.n_cycles + n) * P.n_bq;     // mate row = file index, illumina.py:125-128
-      mg_corrupt_call_philox(seq, qual, n, row, P.n_bq, P.phred, r.v[2 * h], r.v[2 * h + 1]);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   double *s_tlen = reinterpret_cast<double *>(smem);
@@ -384,11 +371,14 @@ __global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ M
   __shared__ Slot slots[MG_TILE];
   __shared__ uint32_t s_wc[MG_TILE / 32], s_ws[MG_TILE / 32];
   __shared__ unsigned long long s_base[3];
-  __shared__ uint32_t s_tile, s_tot_c, s_tot_sz;
+  __shared__ uint32_t s_tile;
+  __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
 
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int L = P.rlen;
   for (int i = t; i < P.n_tlen; i += MG_TILE) s_tlen[i] = P.cum_tlen[i];
+  for (int i = t; i < P.prefix_len; i += MG_TILE) s_prefix[i] = P.prefix[i];
+  for (int i = t; i < P.mid_len; i += MG_TILE) s_mid[i] = P.mid[i];
 
   while (true) {
     __syncthreads();
@@ -411,13 +401,11 @@ __global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ M
         if (P.n_exc) k2 = (mg_count_N(P.exc, P.n_exc, xa, L) <= 2) && (mg_count_N(P.exc, P.n_exc, xb, L) <= 2);  // readgenerate.py:204
         if (k2) {
           n0a = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xa);
-          n1a = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xa + L - 1);
+          n1a = mg_last_node(P.nodes, n0a, P.n_nodes, xa, L);
           n0b = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xb);
-          n1b = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xb + L - 1);
-          MgCountWriter cw; cw.n = 0;
-          mg_fmt_read(cw, P.nodes, n0a, n1a, xa, L, 0);
-          mg_fmt_read(cw, P.nodes, n0b, n1b, xb, L, 1);
-          sz = (uint32_t)(P.prefix_len + P.mid_len) + cw.n + 2u * (uint32_t)L + 5u;
+          n1b = mg_last_node(P.nodes, n0b, P.n_nodes, xb, L);
+          sz = (uint32_t)(P.prefix_len + P.mid_len) + mg_read_fields_len(P.nodes, n0a, n1a, xa, L, P.L_nd) +
+               mg_read_fields_len(P.nodes, n0b, n1b, xb, L, P.L_nd) + 2u * (uint32_t)L + 5u;
         }
       }
     }
@@ -494,26 +482,23 @@ __global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ M
         if (P.out[f] == nullptr) continue;
         if ((uint32_t)t < nk) {
           // reads[fo] = mate (readgenerate.py:207): file f holds mate 0 iff fo == f
-          MgReadRef first = my_fo ? rb : ra, second = my_fo ? ra : rb;
-          MgReadRef mine = f ? second : first;
+          const MgReadRef first = my_fo ? rb : ra, second = my_fo ? ra : rb;
+          const MgReadRef mine = f ? second : first;
           uint8_t *dst = staged ? (stage + pad + loff) : (P.out[f] + goff + loff);
-          mg_emit_record(dst, qlen, P.prefix, P.prefix_len, cnt, P.mid, P.mid_len, P.nodes, first, second, mine, L,
-                         P.hap, P.exc, P.n_exc);
-          if (P.corrupt && !staged) {
-            uint8_t *seq = dst + qlen + 1;
-            for (int pr = 0; 2 * pr < L; pr++) corrupt_pair_philox(P, seq, seq + L + 3, L, (uint32_t)(cnt - 1), f, pr);
+          // staged tiles keep the qname (and, for perfect reads, the quality line) of file 0 in
+          // place: the other file only rewrites its L sequence bytes
+          const bool full = (f == 0) || !staged || (P.out[0] == nullptr);
+          if (P.corrupt) {
+            if (full) mg_emit_frame(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
+            mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, mine, L, P.hap, P.exc, P.n_exc, P.cor, (uint32_t)(cnt - 1), (uint32_t)f);
+          } else if (full) {
+            mg_emit_record(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, mine, L, P.hap, P.exc, P.n_exc);
+          } else {
+            mg_rewrite_seq(dst + qlen + 1, mine, L, P.hap, P.exc, P.n_exc);
           }
         }
         if (staged) {
           __syncthreads();
-          if (P.corrupt) {
-            for (uint32_t k = wid; k < nk; k += MG_TILE / 32) {
-              uint8_t *seq = stage + pad + slots[k].loff + slots[k].qlen + 1;
-              for (int pr = lane; 2 * pr < L; pr += 32)
-                corrupt_pair_philox(P, seq, seq + L + 3, L, (uint32_t)(base2 + k), f, pr);
-            }
-            __syncthreads();
-          }
           // coalesced copy-out: smem and global share the same 16-byte phase (pad)
           uint8_t *gdst = P.out[f] + goff;
           const uint8_t *ssrc = stage + pad;
@@ -716,13 +701,14 @@ __global__ void __launch_bounds__(256) k_corrupt(MgCorruptParams P) {
         }
       } else {
         for (int pr = lane; 2 * pr < L; pr += 32) {
-          MgPhilox rr = mg_philox((uint32_t)r, (uint32_t)(r >> 32) * 2u + (uint32_t)f, (uint32_t)pr, MG_STREAM_CORRUPT, P.key0, P.key1);
+          const MgPhilox rr = mg_philox((uint32_t)r, (uint32_t)(r >> 32) * 2u + (uint32_t)f, (uint32_t)pr, MG_STREAM_CORRUPT, P.cor.k0, P.cor.k1);
 #pragma unroll
           for (int h = 0; h < 2; h++) {
-            int n = 2 * pr + h;
+            const int n = 2 * pr + h;
             if (n < L) {
-              const double *row = P.cum_bq + ((size_t)f * P.n_cycles + n) * P.n_bq;
-              mg_corrupt_call_philox(seq, qual, n, row, P.n_bq, P.phred, rr.v[2 * h], rr.v[2 * h + 1]);
+              uint32_t base = seq[n], q;
+              mg_corrupt_one(P.cor, (uint32_t)f, n, h ? rr.v[2] : rr.v[0], h ? rr.v[3] : rr.v[1], base, q);
+              seq[n] = (uint8_t)base; qual[n] = (uint8_t)q;
             }
           }
         }

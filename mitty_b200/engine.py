@@ -72,8 +72,18 @@ class Engine(object):
     if rlen is None:
       rlen = model['rlen'] if 'rlen' in model else model['mean_rlen']
     self.rlen = int(rlen)
+    self._model_shape = cum_bq.shape
     self._check(self._L.mg_model_load(self._h, _ptr(cum_tlen), cum_tlen.size, _ptr(cum_bq), cum_bq.shape[0],
                                       cum_bq.shape[1], cum_bq.shape[2], _ptr(PHRED_P), self.rlen))
+
+  def model_tables(self, kshift):
+    """-> (alias u32[n_mates, n_cycles, 1 << kshift], n64, err u32[128, 4]) as built at load time."""
+    n64 = C.c_int32(0)
+    self._check(self._L.mg_model_tables(self._h, kshift, None, 0, C.byref(n64), None))
+    alias = np.zeros(self._model_shape[0] * self._model_shape[1] << kshift, dtype=np.uint32)
+    err = np.zeros((128, 4), dtype=np.uint32)
+    self._check(self._L.mg_model_tables(self._h, kshift, _ptr(alias), alias.size, C.byref(n64), _ptr(err)))
+    return alias.reshape(self._model_shape[0], self._model_shape[1], 1 << kshift), n64.value, err
 
   # -- haplotypes --------------------------------------------------------------------------------
   def load_region(self, ref_bytes, bed_start):

@@ -7,13 +7,19 @@
 
 extern "C" {
 
-// mirrors k_unit_emit phase 1 + phase 2 for explicit templates (ts_rel, tl), one template at a time
+// mirrors k_unit_emit phase 1 + phase 2 for explicit templates (ts_rel, tl), one template at a time.
+// Like a staged tile of the kernel: the file-0 record is written into a stage buffer and copied
+// out, then only the sequence (and, when corrupting, the quality) bytes are rewritten for file 1.
 int64_t emul_unit(const uint32_t *hap, uint32_t hap_len, const MgNode *nodes, int n_nodes, const uint32_t *blk,
                   int blk_shift, int n_blk, const MgExc *exc, int n_exc, int L, int64_t n, const int64_t *ts_rel,
                   const int64_t *tl_in, const int8_t *fo_in, const char *prefix, const char *mid, uint8_t *out1,
-                  uint8_t *out2, int64_t cap, int64_t *n_bytes) {
+                  uint8_t *out2, int64_t cap, int64_t *n_bytes,
+                  int corrupt, const uint32_t *alias, int kshift, int n_cycles, const uint32_t *err, uint32_t k0, uint32_t k1) {
   const int pl = (int)strlen(prefix), ml = (int)strlen(mid);
+  const int L_nd = mg_ndigits32((uint32_t)L);
+  MgCorruptCtx cor; cor.alias = alias; cor.err = (const MgErr *)err; cor.kshift = kshift; cor.n_cycles = n_cycles; cor.k0 = k0; cor.k1 = k1;
   uint64_t sz_sum = 0, cnt1 = 0, cnt2 = 0;
+  static uint8_t stage_raw[1 << 16];
   for (int64_t j = 0; j < n; j++) {
     int64_t tl = tl_in[j] < L ? L : tl_in[j];
     int64_t te = ts_rel[j] + tl;
@@ -22,20 +28,36 @@ int64_t emul_unit(const uint32_t *hap, uint32_t hap_len, const MgNode *nodes, in
     cnt1++;
     uint32_t xa = (uint32_t)ts_rel[j], xb = (uint32_t)(te - L);
     if (n_exc && !(mg_count_N(exc, n_exc, xa, L) <= 2 && mg_count_N(exc, n_exc, xb, L) <= 2)) continue;
-    MgReadRef ra = {xa, mg_find_node(nodes, blk, blk_shift, n_blk, n_nodes, xa), mg_find_node(nodes, blk, blk_shift, n_blk, n_nodes, xa + L - 1), 0};
-    MgReadRef rb = {xb, mg_find_node(nodes, blk, blk_shift, n_blk, n_nodes, xb), mg_find_node(nodes, blk, blk_shift, n_blk, n_nodes, xb + L - 1), 1};
+    MgReadRef ra = {xa, mg_find_node(nodes, blk, blk_shift, n_blk, n_nodes, xa), 0, 0};
+    MgReadRef rb = {xb, mg_find_node(nodes, blk, blk_shift, n_blk, n_nodes, xb), 0, 1};
+    ra.n1 = mg_last_node(nodes, ra.n0, n_nodes, xa, L);
+    rb.n1 = mg_last_node(nodes, rb.n0, n_nodes, xb, L);
+    if (ra.n1 != mg_find_node(nodes, blk, blk_shift, n_blk, n_nodes, xa + L - 1)) return -2;
+    if (rb.n1 != mg_find_node(nodes, blk, blk_shift, n_blk, n_nodes, xb + L - 1)) return -2;
     MgCountWriter cw; cw.n = 0;
     mg_fmt_read(cw, nodes, ra.n0, ra.n1, ra.x, L, 0);
     mg_fmt_read(cw, nodes, rb.n0, rb.n1, rb.x, L, 1);
+    if (cw.n != mg_read_fields_len(nodes, ra.n0, ra.n1, xa, L, L_nd) + mg_read_fields_len(nodes, rb.n0, rb.n1, xb, L, L_nd)) return -3;
     uint32_t sz = (uint32_t)(pl + ml) + cw.n + 2u * (uint32_t)L + 5u;
     uint64_t cnt = cnt2 + 1;
     uint64_t off = sz_sum + mg_digit_sum(cnt2);         // the kernel's placement formula
     uint32_t qlen = sz + (uint32_t)mg_ndigits(cnt) - (2u * (uint32_t)L + 5u);
     uint64_t rec = sz + (uint64_t)mg_ndigits(cnt);
-    if ((int64_t)(off + rec) > cap) return -1;
+    if ((int64_t)(off + rec) > cap || rec + 8 > sizeof stage_raw) return -1;
     MgReadRef first = fo ? rb : ra, second = fo ? ra : rb;
-    mg_emit_record(out1 + off, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, first, L, hap, exc, n_exc);
-    mg_emit_record(out2 + off, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, second, L, hap, exc, n_exc);
+    uint8_t *dst = stage_raw + (off & 3);                // same word phase as the final destination
+    if (corrupt) {
+      mg_emit_frame(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, L);
+      mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, first, L, hap, exc, n_exc, cor, (uint32_t)(cnt - 1), 0u);
+      memcpy(out1 + off, dst, rec);
+      mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, second, L, hap, exc, n_exc, cor, (uint32_t)(cnt - 1), 1u);
+      memcpy(out2 + off, dst, rec);
+    } else {
+      mg_emit_record(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, first, L, hap, exc, n_exc);
+      memcpy(out1 + off, dst, rec);
+      mg_rewrite_seq(dst + qlen + 1, second, L, hap, exc, n_exc);
+      memcpy(out2 + off, dst, rec);
+    }
     sz_sum += sz; cnt2++;
   }
   *n_bytes = (int64_t)(sz_sum + mg_digit_sum(cnt2));

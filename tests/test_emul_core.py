@@ -61,7 +61,7 @@ def device_layout(ref, ref_start_pos, cv, blk_shift=8):
               p_min=p_min, p_max=p_max, hap=hap)
 
 
-def run_emul(lib, lay, L, ts, tl, fo, prefix, mid):
+def run_emul(lib, lay, L, ts, tl, fo, prefix, mid, corrupt=None):
   cap = int(len(ts)) * (2 * L + 400) + 4096
   o1, o2 = np.zeros(cap, dtype=np.uint8), np.zeros(cap, dtype=np.uint8)
   nb = C.c_int64(0)
@@ -72,8 +72,11 @@ def run_emul(lib, lay, L, ts, tl, fo, prefix, mid):
                     C.c_int(lay['nodes'].size), C.c_void_p(lay['blk'].ctypes.data), C.c_int(lay['blk_shift']), C.c_int(lay['n_blk']),
                     C.c_void_p(lay['exc'].ctypes.data), C.c_int(lay['n_exc']), C.c_int(L), C.c_int64(len(ts)),
                     C.c_void_p(ts_rel.ctypes.data), C.c_void_p(tl.ctypes.data), C.c_void_p(fo.ctypes.data),
-                    prefix.encode(), mid.encode(), C.c_void_p(o1.ctypes.data), C.c_void_p(o2.ctypes.data), C.c_int64(cap), C.byref(nb))
-  assert n >= 0
+                    prefix.encode(), mid.encode(), C.c_void_p(o1.ctypes.data), C.c_void_p(o2.ctypes.data), C.c_int64(cap), C.byref(nb),
+                    *((C.c_int(0), None, C.c_int(6), C.c_int(0), None, C.c_uint32(0), C.c_uint32(0)) if corrupt is None else
+                      (C.c_int(1), C.c_void_p(corrupt['alias'].ctypes.data), C.c_int(corrupt['kshift']), C.c_int(corrupt['alias'].shape[1]),
+                       C.c_void_p(corrupt['err'].ctypes.data), C.c_uint32(corrupt['k0']), C.c_uint32(corrupt['k1']))))
+  assert n >= 0, n
   return o1[:nb.value].tobytes(), o2[:nb.value].tobytes(), n
 
 
@@ -178,3 +181,35 @@ def test_corrupt_call_matches_oracle(emul):
       want_q.append(chr(bq + 33))
     assert s.tobytes().decode() == ''.join(want_s) and q.tobytes().decode() == ''.join(want_q)
     assert s.tobytes().decode() != seq
+
+
+@pytest.mark.parametrize('L,kshift', [(150, 6), (150, 7), (37, 6), (5, 7)])
+def test_fused_philox_corruption_matches_numpy_spec(emul, L, kshift):
+  """Fused production-mode corruption (inline in the emit path, alias rows + Philox) == the numpy
+  restatement of its draw layout applied to the perfect reads, incl. N / exception bases."""
+  from tests import philox_ref as PR
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  assert PR.exact64_cycles(m['cum_bq_mat']) == 150
+  alias = PR.alias_tables(m['cum_bq_mat'], kshift, n_rows=150)
+  err = PR.err_table(oracle.PHRED_P)
+  # the alias rows encode the model's per-cycle distribution (searchsorted-left outcomes)
+  for mate in (0, 1):
+    pm = np.diff(np.concatenate([np.zeros((150, 1)), m['cum_bq_mat'][mate, :150, :]], axis=1), axis=1)
+    for cyc in (0, 1, 75, 149):
+      assert np.abs(PR.alias_distribution(alias[mate, cyc], kshift)[:94] - pm[cyc]).max() < 1e-8
+  regs = H.workload_regions(synth.edge_workload())
+  r = regs[0]
+  cv = H.oracle_cv(r['v'][1])
+  lay = device_layout(r['ref'], r['region'][1] + 1, cv)
+  rs = np.random.RandomState(4)
+  n = 1200
+  ts = rs.randint(lay['p_min'], lay['p_max'] - 3 * L, size=n).astype(np.int64)
+  tl = rs.randint(L, 3 * L, size=n).astype(np.int64)
+  fo = rs.randint(0, 2, size=n).astype(np.int8)
+  p1, p2, cnt = run_emul(emul, lay, L, ts, tl, fo, '@E:0:0:', '|e|1')
+  cor = dict(alias=alias, kshift=kshift, err=err, k0=12345, k1=0xdeadbeef)
+  c1, c2, ccnt = run_emul(emul, lay, L, ts, tl, fo, '@E:0:0:', '|e|1', corrupt=cor)
+  assert ccnt == cnt and cnt > 800
+  assert c1 == PR.corrupt_file(p1, 0, alias, kshift, err, cor['k0'], cor['k1'])
+  assert c2 == PR.corrupt_file(p2, 1, alias, kshift, err, cor['k0'], cor['k1'])
+  assert c1 != p1 and b'N' in c1

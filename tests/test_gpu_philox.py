@@ -163,3 +163,42 @@ def test_philox_large_unit_exact(eng):
   assert cnt == ocnt and cnt < nk      # some templates were dropped for N content
   assert H.sha256(f1.tobytes()) == H.sha256(o1) and H.sha256(f2.tobytes()) == H.sha256(o2)
   eng.free_copy(cp); eng.free_region(rid)
+
+
+def test_philox_corruption_exact_vs_numpy_spec(eng):
+  """Production-mode corruption is fully specified (Philox counters, alias rows, integer error
+  thresholds): the fused emit kernel and the standalone corrupt kernel must reproduce the numpy
+  restatement of that specification byte for byte."""
+  import mitty_b200.simulation.illumina as il
+  from mitty_b200.engine import MODE_PHILOX
+  from tests import philox_ref as PR
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  rm = il.read_model_params(m, 30.0)
+  eng.load_model(rm)
+  # the tables the library built at load time == the Python restatement of Vose's method
+  err = PR.err_table(oracle.PHRED_P)
+  for kshift in (6, 7):
+    alias, n64, lerr = eng.model_tables(kshift)
+    assert n64 == PR.exact64_cycles(m['cum_bq_mat']) == 150
+    want = PR.alias_tables(m['cum_bq_mat'], kshift, n_rows=n64 if kshift == 6 else None)
+    np.testing.assert_array_equal(alias, want)
+    np.testing.assert_array_equal(lerr, err)
+  alias6, alias7 = PR.alias_tables(m['cum_bq_mat'], 6, n_rows=150), PR.alias_tables(m['cum_bq_mat'], 7)
+  r = H.workload_regions(synth.edge_workload())[0]
+  rid = eng.load_region(r['ref'], r['region'][1])
+  cp = eng.build_copy(rid, r['v'][1])
+  n = int((cp.p_max - cp.p_min) * 0.1)
+  unit_seed, cseed = 4242, 77
+  p1, p2, cnt, _, _ = eng.generate_unit(cp, n, 0.1, MODE_PHILOX, unit_seed, '@E:0:0:', '|e|1')
+  c1, c2, ccnt, _, _ = eng.generate_unit(cp, n, 0.1, MODE_PHILOX, unit_seed, '@E:0:0:', '|e|1', corrupt=True, corrupt_seed=cseed)
+  assert cnt == ccnt and cnt > 500
+  k1 = unit_seed ^ 0x636f7231
+  assert c1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, alias6, 6, err, cseed, k1)
+  assert c2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, alias6, 6, err, cseed, k1)
+  # standalone corrupt-reads over the same perfect reads
+  eng.load_model(m)
+  s1, s2, scnt = eng.corrupt_fastq(p1, p2, mode=MODE_PHILOX, seed=cseed)
+  assert scnt == cnt
+  assert s1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, alias7, 7, err, cseed, 0x636f7232)
+  assert s2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, alias7, 7, err, cseed, 0x636f7232)
+  eng.free_copy(cp); eng.free_region(rid)

@@ -63,7 +63,8 @@ struct mg_ctx {
   bool own_stream = false;
   std::string err;
   // model
-  DevBuf m_tlen, m_bq, m_phred, m_alias[2], m_err;   // alias[0]: 64-entry rows, alias[1]: 128-entry rows
+  DevBuf m_tlen, m_bq, m_phred, m_alias[2], m_err, m_tlen_alias;
+  bool has_tlen_alias = false;   // n_tlen + 1 <= 1024 outcomes: 1024-entry alias table of the template-length model   // alias[0]: 64-entry rows, alias[1]: 128-entry rows
   int n_tlen = 0, n_mates = 0, n_cycles = 0, n_bq = 0, rlen = 0;
   int n64 = 0;   // leading cycles whose rows (all mates) put no mass on BQ >= 64: 64-entry alias rows are exact there
   std::vector<uint32_t> h_alias[2]; std::vector<MgErr> h_err;
@@ -91,17 +92,10 @@ int fail(mg_ctx *c, int code, const char *fmt, ...) {
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, MG_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-// Vose alias table for one (mate, cycle) row of the quality model.  Outcome b = number of CDF
-// entries < u (searchsorted side='left', illumina.py:156) clipped to 93; entry = prob24 << 7 | alias.
-void build_alias_row(const double *cum, int n_bq, int K, uint32_t *out) {
-  std::vector<double> q(K, 0.0);
-  double prev = 0.0;
-  for (int b = 0; b < n_bq; b++) {
-    double c = cum[b]; if (c > 1.0) c = 1.0; if (c < prev) c = prev;
-    if (std::min(b, 93) < K) q[std::min(b, 93)] += c - prev;   // 64-entry rows are only used where this mass is zero
-    prev = c;
-  }
-  if (std::min(n_bq, 93) < K) q[std::min(n_bq, 93)] += 1.0 - prev;
+// Vose's alias method over K outcomes with probabilities q (sum 1): entry i = prob << alias_bits | alias,
+// prob quantised to prob_bits.  A draw takes idx uniform in [0, K) and frac uniform in [0, 2^prob_bits):
+// outcome = frac < prob ? idx : alias.
+void vose(std::vector<double> q, int K, int prob_bits, int alias_bits, uint32_t *out) {
   std::vector<int> small, large;
   for (int i = 0; i < K; i++) { q[i] *= K; (q[i] < 1.0 ? small : large).push_back(i); }
   std::vector<double> prob(K, 1.0); std::vector<int> alias(K);
@@ -113,12 +107,33 @@ void build_alias_row(const double *cum, int n_bq, int K, uint32_t *out) {
     q[l] = (q[l] + q[s]) - 1.0;
     (q[l] < 1.0 ? small : large).push_back(l);
   }
+  const double scale = (double)(1u << prob_bits);
   for (int i = 0; i < K; i++) {
     double pr = prob[i] < 0.0 ? 0.0 : (prob[i] > 1.0 ? 1.0 : prob[i]);
-    uint32_t pq = (uint32_t)std::floor(pr * 16777216.0 + 0.5);
-    if (pq > (1u << 24)) pq = 1u << 24;
-    out[i] = (pq << 7) | (uint32_t)alias[i];
+    uint32_t pq = (uint32_t)std::floor(pr * scale + 0.5);
+    if (pq > (1u << prob_bits)) pq = 1u << prob_bits;
+    if (prob_bits + alias_bits == 32 && pq == (1u << prob_bits)) pq -= 1;   // no room for the 2^bits value
+    out[i] = (pq << alias_bits) | (uint32_t)alias[i];
   }
+}
+
+// Outcome probabilities of searchsorted(cum, u, side='left') for u uniform in [0,1): outcome b =
+// number of entries < u, b in [0, n]; outcomes above `clip` are folded into `clip`.
+std::vector<double> ss_left_probs(const double *cum, int n, int K, int clip) {
+  std::vector<double> q(K, 0.0);
+  double prev = 0.0;
+  for (int b = 0; b < n; b++) {
+    double c = cum[b]; if (c > 1.0) c = 1.0; if (c < prev) c = prev;
+    if (std::min(b, clip) < K) q[std::min(b, clip)] += c - prev;   // narrow tables are only used where this mass is zero
+    prev = c;
+  }
+  if (std::min(n, clip) < K) q[std::min(n, clip)] += 1.0 - prev;
+  return q;
+}
+
+// alias row of one (mate, cycle) of the quality model: outcome clipped to 93 (illumina.py:156)
+void build_alias_row(const double *cum, int n_bq, int K, uint32_t *out) {
+  vose(ss_left_probs(cum, n_bq, K, 93), K, 24, 7, out);
 }
 
 struct DeviceGuard {
@@ -230,6 +245,13 @@ int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double 
       if (t == 1 || (int)(r % n_cycles) < n64) build_alias_row(cum_bq_mat + r * n_bq, n_bq, K, ctx->h_alias[t].data() + r * K);
     CU(ctx->m_alias[t].need(4 * ctx->h_alias[t].size()));
     CU(cudaMemcpyAsync(ctx->m_alias[t].p, ctx->h_alias[t].data(), 4 * ctx->h_alias[t].size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->has_tlen_alias = (n_tlen + 1 <= MG_TLEN_K);
+  if (ctx->has_tlen_alias) {
+    std::vector<uint32_t> ta(MG_TLEN_K);
+    vose(ss_left_probs(cum_tlen, n_tlen, MG_TLEN_K, n_tlen), MG_TLEN_K, 22, 10, ta.data());
+    CU(ctx->m_tlen_alias.need(4 * MG_TLEN_K));
+    CU(cudaMemcpy(ctx->m_tlen_alias.p, ta.data(), 4 * MG_TLEN_K, cudaMemcpyHostToDevice));
   }
   ctx->h_err.assign(128, MgErr{0, 0, 0, 0});
   for (int b = 0; b < 100; b++) {
@@ -505,6 +527,7 @@ static int fill_unit_params(mg_ctx *ctx, const mg_unit_desc *d, MgUnitParams &P,
     P.exc = C.d_exc; P.n_exc = (int)C.exc.size();
   }
   P.cum_tlen = ctx->m_tlen.as<double>(); P.n_tlen = ctx->n_tlen; P.rlen = ctx->rlen;
+  P.tlen_alias = ctx->has_tlen_alias ? ctx->m_tlen_alias.as<uint32_t>() : nullptr;
   P.mode = d->mode; P.n_cand = (uint32_t)d->n_candidates;
   const size_t n = (size_t)d->n_candidates;
   if (d->mode == MG_MODE_PHILOX) {
@@ -590,11 +613,13 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
   P.L_nd = mg_ndigits32((uint32_t)L);
 
   P.n_tiles = (int)((n + MG_TILE - 1) / MG_TILE);
-  int stage = MG_TILE * (2 * L + 80);
+  // stage sized for the expected ~5/6 of the candidates that survive (1.2x over-draw) with >3 sigma
+  // of slack; a tile that does not fit takes the direct-to-global path
+  int stage = MG_TILE * (2 * L + 44);
   if (stage > 160 * 1024) stage = 160 * 1024;
   P.stage_cap = stage & ~15;
   int smem = 0;
-  const int grid = mg_unit_grid(P.stage_cap, P.n_tlen, &smem);
+  const int grid = mg_unit_grid(P.stage_cap, &smem);
 
   // scan state: [totals 4 x u64][tile counter (16 B)][descA][descB]
   const size_t state_bytes = 48 + 16 * (size_t)std::max(P.n_tiles, 1);

@@ -209,6 +209,13 @@ struct MgCountWriter {
   MG_HD void put_word(uint32_t) { n += 4; }
 };
 
+// plain byte stores: used for the qname, whose per-lane byte counts differ (a shared word
+// stream would flush on a different iteration in every lane and serialise the warp)
+struct MgByteWriter {
+  uint8_t *p;
+  MG_HD void put(uint8_t c) { *p++ = c; }
+};
+
 struct MgWordStream {
   uint32_t *wp;     // next aligned word
   uint32_t carry;   // pending bytes, low nb bytes valid
@@ -503,10 +510,11 @@ template <class NP, class HP, class EP>
 MG_HD void mg_emit_record(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
                           const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second,
                           MgReadRef mine, int L, HP hap, EP exc, int n_exc) {
+  MgByteWriter bw; bw.p = dst;
+  mg_fmt_qname(bw, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
+  bw.put('\n');
   MgWordStream ws;
-  ws.begin(dst);
-  mg_fmt_qname(ws, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
-  ws.put('\n');
+  ws.begin(bw.p);
   mg_emit_seq(ws, hap, mine.x, L, mine.strand);
   ws.put('\n'); ws.put('+'); ws.put('\n');
   mg_emit_fill(ws, '~', L);
@@ -531,11 +539,9 @@ MG_HD void mg_rewrite_seq(uint8_t *seq_dst, MgReadRef mine, int L, HP hap, EP ex
 template <class NP>
 MG_HD void mg_emit_frame(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
                          const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
-  MgWordStream ws;
-  ws.begin(dst);
-  mg_fmt_qname(ws, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
-  ws.put('\n');
-  ws.end();
+  MgByteWriter bw; bw.p = dst;
+  mg_fmt_qname(bw, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
+  bw.put('\n');
   uint8_t *p = dst + qlen + 1 + L;
   p[0] = '\n'; p[1] = '+'; p[2] = '\n'; p[3 + L] = '\n';
 }
@@ -561,15 +567,24 @@ struct MgCorruptCtx {
   uint32_t k0, k1;
 };
 
-MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &base, uint32_t &qual) {
+// -> bit 2 = substitution happened, bits 0-1 = which of the three alternatives; qual = ASCII quality
+MG_HD uint32_t mg_corrupt_draw(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &qual) {
   const uint32_t idx = w_bq >> (32 - C.kshift);
   const uint32_t frac = (w_bq << C.kshift) >> 8;
   const uint32_t e = C.alias[(((size_t)f * C.n_cycles + (size_t)n) << C.kshift) | idx];
   const uint32_t bq = frac < (e >> 7) ? idx : (e & 127u);
   const MgErr t = C.err[bq];
-  if (w_call < t.thr) base = mg_base_rot((uint8_t)base, (int)(w_call >= t.t1) + (int)(w_call >= t.t2));
   qual = bq + 33u;
+  return w_call < t.thr ? (4u | ((uint32_t)(w_call >= t.t1) + (uint32_t)(w_call >= t.t2))) : 0u;
 }
+
+MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &base, uint32_t &qual) {
+  const uint32_t d = mg_corrupt_draw(C, f, n, w_bq, w_call, qual);
+  if (d) base = mg_base_rot((uint8_t)base, (int)(d & 3u));
+}
+
+// base_rot on 2-bit codes (A=0 C=1 G=2 T=3): A->CTG, C->ATG, G->ACT, T->ACG as 2-bit triples
+#define MG_ROT_TBL (45u | (44u << 6) | (52u << 12) | (36u << 18))
 
 // SEQ and QUAL lines of one read, corrupted on the fly: every thread of a warp is at the same
 // cycle of its own record, so the alias row (one 256-byte line pair) is shared by the warp.
@@ -587,7 +602,7 @@ MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgReadRef mi
     for (int q = 0; q < 4; q++) {
       const int n0 = 16 * c + 4 * q;
       if (n0 < L) {
-        uint32_t ch = mg_chars4((codes >> (8 * q)) & 0xFFu), qw = 0;
+        uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw = 0;
         MG_UNROLL
         for (int h = 0; h < 2; h++) {
           if (n0 + 2 * h < L) {
@@ -596,14 +611,19 @@ MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgReadRef mi
             for (int e = 0; e < 2; e++) {
               const int j = 2 * h + e, n = n0 + j;
               if (n < L) {
-                uint32_t base = (ch >> (8 * j)) & 0xFFu, qual;
-                mg_corrupt_one(C, f, n, e ? r.v[2] : r.v[0], e ? r.v[3] : r.v[1], base, qual);
-                ch = (ch & ~(0xFFu << (8 * j))) | (base << (8 * j));
+                uint32_t qual;
+                const uint32_t d = mg_corrupt_draw(C, f, n, e ? r.v[2] : r.v[0], e ? r.v[3] : r.v[1], qual);
+                if (d) {
+                  const uint32_t code = (b4 >> (2 * j)) & 3u;
+                  const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * (d & 3u))) & 3u;
+                  b4 ^= (code ^ nc) << (2 * j);
+                }
                 qw |= qual << (8 * j);
               }
             }
           }
         }
+        const uint32_t ch = mg_chars4(b4);
         if (n0 + 4 <= L) { ws.put_word(ch); wq.put_word(qw); }
         else for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
       }

@@ -5,6 +5,7 @@
 #include "mg_core.cuh"
 
 #define MG_TILE 128          // candidates (and threads) per emit tile
+#define MG_TLEN_K 1024       // entries of the template-length alias table (outcomes 0..n_tlen)
 #define MG_QN_MAX 192        // max length of the qname prefix / mid strings
 #define MG_HAP_PAD 8         // 32-bit words of padding on both sides of a packed sequence
 
@@ -20,6 +21,7 @@ struct MgUnitParams {
   const MgExc *exc; int n_exc;
   // read model
   const double *cum_tlen; int n_tlen; int rlen;
+  const uint32_t *tlen_alias; // PHILOX: MG_TLEN_K-entry alias table (prob22 << 10 | alias) or null
   // template sampling
   int mode; uint32_t n_cand;
   const int64_t *ts_in;      // DET / EXPLICIT: shuffled template starts (1-based sample coords)
@@ -67,7 +69,7 @@ void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const uin
 void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st);
 void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
                         cudaStream_t st);
-int mg_unit_grid(int stage_cap, int n_tlen, int *smem_bytes);
+int mg_unit_grid(int stage_cap, int *smem_bytes);
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st);
 void mg_launch_sample(const MgSampleParams &P, cudaStream_t st);
 void mg_launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st);  // exclusive, out[n] = total

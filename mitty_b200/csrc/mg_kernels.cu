@@ -275,7 +275,8 @@ void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t
 
 struct Cand { int64_t ts_rel; int64_t te_rel; uint32_t fo; bool k1; };
 
-__device__ __forceinline__ Cand sample_candidate(const MgUnitParams &P, const double *cum_tlen, uint32_t j) {
+// s_alias: the template-length alias table staged in shared memory (PHILOX mode, when the model has one)
+__device__ __forceinline__ Cand sample_candidate(const MgUnitParams &P, const uint32_t *s_alias, uint32_t j) {
   Cand c;
   int64_t tl;
   c.fo = 0;
@@ -283,11 +284,16 @@ __device__ __forceinline__ Cand sample_candidate(const MgUnitParams &P, const do
     uint32_t i = mg_permute(j, P.n_cand, P.half_bits, P.key_perm0, P.key_perm1);
     c.ts_rel = (int64_t)P.ts_sorted[i];
     MgPhilox r = mg_philox(j, 0u, 0u, MG_STREAM_TLEN, P.key_tlen0, P.key_tlen1);
-    tl = mg_lower_bound_f64(cum_tlen, P.n_tlen, mg_u53(r.v[0], r.v[1]));      // illumina.py:72
+    if (P.tlen_alias) {                                                        // illumina.py:72 by the alias method
+      const uint32_t idx = r.v[0] >> 22, e = s_alias[idx];
+      tl = (r.v[0] & 0x3FFFFFu) < (e >> 10) ? idx : (e & 1023u);
+    } else {
+      tl = mg_lower_bound_f64(P.cum_tlen, P.n_tlen, mg_u53(r.v[0], r.v[1]));
+    }
     c.fo = r.v[2] & 1u;
   } else {
     c.ts_rel = P.ts_in[j] - P.p_min;
-    tl = (P.mode == MG_MODE_DET) ? (int64_t)mg_lower_bound_f64(cum_tlen, P.n_tlen, P.u_tlen[j]) : P.tl_in[j];
+    tl = (P.mode == MG_MODE_DET) ? (int64_t)mg_lower_bound_f64(P.cum_tlen, P.n_tlen, P.u_tlen[j]) : P.tl_in[j];
   }
   if (tl < P.rlen) tl = P.rlen;                                                // illumina.py:73
   c.te_rel = c.ts_rel + tl;
@@ -296,9 +302,9 @@ __device__ __forceinline__ Cand sample_candidate(const MgUnitParams &P, const do
 }
 
 __global__ void __launch_bounds__(256) k_sample(MgSampleParams S) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  double *s_tlen = reinterpret_cast<double *>(smem);
-  for (int i = threadIdx.x; i < S.u.n_tlen; i += blockDim.x) s_tlen[i] = S.u.cum_tlen[i];
+  __shared__ uint32_t s_tlen[MG_TLEN_K];
+  if (S.u.mode == MG_MODE_PHILOX && S.u.tlen_alias)
+    for (int i = threadIdx.x; i < MG_TLEN_K; i += blockDim.x) s_tlen[i] = S.u.tlen_alias[i];
   __syncthreads();
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < S.u.n_cand; j += gridDim.x * blockDim.x) {
     Cand c = sample_candidate(S.u, s_tlen, j);
@@ -312,7 +318,7 @@ void mg_launch_sample(const MgSampleParams &P, cudaStream_t st) {
   if (P.u.n_cand == 0) return;
   int grid = (int)((P.u.n_cand + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  k_sample<<<grid, 256, P.u.n_tlen * sizeof(double), st>>>(P);
+  k_sample<<<grid, 256, 0, st>>>(P);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -365,8 +371,8 @@ __device__ Agg tile_lookback(const MgUnitParams &P, int tile, int lane) {
 
 __global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
-  double *s_tlen = reinterpret_cast<double *>(smem);
-  uint8_t *stage = smem + ((P.n_tlen * sizeof(double) + 15) & ~(size_t)15);
+  uint32_t *s_tlen = reinterpret_cast<uint32_t *>(smem);
+  uint8_t *stage = smem + MG_TLEN_K * sizeof(uint32_t);
 
   __shared__ Slot slots[MG_TILE];
   __shared__ uint32_t s_wc[MG_TILE / 32], s_ws[MG_TILE / 32];
@@ -376,7 +382,8 @@ __global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ M
 
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int L = P.rlen;
-  for (int i = t; i < P.n_tlen; i += MG_TILE) s_tlen[i] = P.cum_tlen[i];
+  if (P.mode == MG_MODE_PHILOX && P.tlen_alias)
+    for (int i = t; i < MG_TLEN_K; i += MG_TILE) s_tlen[i] = P.tlen_alias[i];
   for (int i = t; i < P.prefix_len; i += MG_TILE) s_prefix[i] = P.prefix[i];
   for (int i = t; i < P.mid_len; i += MG_TILE) s_mid[i] = P.mid[i];
 
@@ -518,8 +525,8 @@ __global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ M
   }
 }
 
-int mg_unit_grid(int stage_cap, int n_tlen, int *smem_bytes) {
-  int smem = (int)(((size_t)n_tlen * sizeof(double) + 15) & ~(size_t)15) + stage_cap + 16;
+int mg_unit_grid(int stage_cap, int *smem_bytes) {
+  int smem = MG_TLEN_K * (int)sizeof(uint32_t) + stage_cap + 16;
   *smem_bytes = smem;
   cudaFuncSetAttribute(k_unit_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int per_sm = 0, dev = 0, sms = 0;

@@ -615,11 +615,13 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
   P.n_tiles = (int)((n + MG_TILE - 1) / MG_TILE);
   // stage sized for the expected ~5/6 of the candidates that survive (1.2x over-draw) with >3 sigma
   // of slack; a tile that does not fit takes the direct-to-global path
-  int stage = MG_TILE * (2 * L + 44);
-  if (stage > 160 * 1024) stage = 160 * 1024;
+  // per-warp stage: room for all 32 candidates of a tile with an average qname (~5/6 survive the
+  // 1.2x over-draw); a tile that does not fit takes the direct-to-global path
+  int stage = MG_TILE * (2 * L + 5 + 80);
+  if (stage > 48 * 1024) stage = 48 * 1024;
   P.stage_cap = stage & ~15;
   int smem = 0;
-  const int grid = mg_unit_grid(P.stage_cap, &smem);
+  const int grid = mg_unit_grid(L, d->corrupt, P.stage_cap, &smem);
 
   // scan state: [totals 4 x u64][tile counter (16 B)][descA][descB]
   const size_t state_bytes = 48 + 16 * (size_t)std::max(P.n_tiles, 1);

@@ -19,10 +19,19 @@
 #else
 #define MG_HD inline
 #endif
+// MG_NI: deliberately NOT inlined.  The emit kernel is instruction-cache bound when every helper
+// is inlined at every call site (13 k SASS instructions); the formatting helpers are shared.
+#if defined(__CUDACC__)
+#define MG_NI static __host__ __device__ __noinline__ __attribute__((unused))
+#else
+#define MG_NI static __attribute__((noinline, unused))
+#endif
 #if defined(__CUDA_ARCH__)
 #define MG_UNROLL _Pragma("unroll")
+#define MG_NOUNROLL _Pragma("unroll 1")
 #else
 #define MG_UNROLL
+#define MG_NOUNROLL
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -55,6 +64,14 @@ MG_HD uint32_t mg_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // ((hi:lo)
   return __funnelshift_r(lo, hi, sh);
 #else
   return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+#endif
+}
+
+MG_HD uint32_t mg_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) {  // ((hi:lo) << sh) high word, sh in [0,31]
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, sh);
+#else
+  return sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;
 #endif
 }
 
@@ -185,7 +202,7 @@ MG_HD int mg_nchars_int(int64_t v) { return v < 0 ? 1 + mg_ndigits((uint64_t)(-v
 
 // sum of the decimal lengths of 1..m  (closed form; used to place records whose qname carries a
 // serial number that is only known after the block/grid scan):  d*(m+1) - 11..1 (d ones)
-MG_HD uint64_t mg_digit_sum(uint64_t m) {
+MG_NI uint64_t mg_digit_sum(uint64_t m) {
   if (m == 0) return 0;
   int d = mg_ndigits(m);
   uint64_t ones = 0, p = 1;
@@ -204,6 +221,7 @@ MG_HD uint64_t mg_digit_sum(uint64_t m) {
 // 32-bit stores in the interior and byte stores only for the first / last partial word.
 
 struct MgCountWriter {
+  static constexpr bool is_bytes = false;
   uint32_t n;
   MG_HD void put(uint8_t) { n++; }
   MG_HD void put_word(uint32_t) { n += 4; }
@@ -212,50 +230,55 @@ struct MgCountWriter {
 // plain byte stores: used for the qname, whose per-lane byte counts differ (a shared word
 // stream would flush on a different iteration in every lane and serialise the warp)
 struct MgByteWriter {
+  static constexpr bool is_bytes = true;
   uint8_t *p;
   MG_HD void put(uint8_t c) { *p++ = c; }
 };
 
 struct MgWordStream {
+  static constexpr bool is_bytes = false;
   uint32_t *wp;     // next aligned word
   uint32_t carry;   // pending bytes, low nb bytes valid
   uint32_t nb;      // pending byte count 0..3
-  uint32_t skip;    // leading bytes of the first word that belong to someone else
 
-  MG_HD void begin(uint8_t *dst) {
+  // The bytes before dst inside its word were written earlier BY THIS THREAD (the tail of its own
+  // qname / separator): they are read back and carried, so every flush is a plain word store.
+  MG_HD void begin_rmw(uint8_t *dst) {
     uintptr_t a = (uintptr_t)dst & 3;
     wp = (uint32_t *)(dst - a);
-    carry = 0; nb = (uint32_t)a; skip = (uint32_t)a;
+    nb = (uint32_t)a;
+    carry = a ? (*wp & (0xFFFFFFFFu >> (32 - 8 * (uint32_t)a))) : 0u;
   }
-  MG_HD void flush_word(uint32_t w) {
-    if (skip) {
-      uint8_t *b = (uint8_t *)wp;
-      for (uint32_t i = skip; i < 4; i++) b[i] = (uint8_t)(w >> (8 * i));
-      skip = 0;
-    } else {
-      *wp = w;
-    }
-    wp++;
-  }
+  MG_HD void flush_word(uint32_t w) { *wp++ = w; }
   MG_HD void put(uint8_t c) {
     carry |= (uint32_t)c << (8 * nb);
     if (++nb == 4) { flush_word(carry); carry = 0; nb = 0; }
   }
-  MG_HD void put_word(uint32_t w) {  // four bytes, little-endian order
-    if (nb == 0) { flush_word(w); return; }
-    uint32_t sh = 8 * nb;
-    flush_word(carry | (w << sh));
-    carry = w >> (32 - sh);
+  MG_HD void put_word(uint32_t w) {  // four bytes, little-endian order; branch-free in nb
+    const uint32_t sh = 8 * nb;
+    flush_word(carry | (w << sh));           // nb == 0: carry is 0 and sh is 0
+    carry = mg_funnel_l(w, 0u, sh);          // the top nb bytes of w (0 when nb == 0)
   }
+  // the last partial word is shared with the NEXT record (another thread): byte stores
   MG_HD void end() {
     uint8_t *b = (uint8_t *)wp;
-    for (uint32_t i = skip; i < nb; i++) b[i] = (uint8_t)(carry >> (8 * i));
-    nb = 0; skip = 0;
+    for (uint32_t i = 0; i < nb; i++) b[i] = (uint8_t)(carry >> (8 * i));
+    nb = 0;
   }
 };
 
+// decimal digits of v at p (byte stores), returns the advanced pointer
+MG_NI uint8_t *mg_put_u32_p(uint8_t *p, uint32_t v) {
+  uint64_t acc = 0;
+  int n = 0;
+  do { uint32_t q = v / 10u; acc = (acc << 4) | (v - q * 10u); v = q; n++; } while (v);
+  for (; n; n--) { *p++ = (uint8_t)('0' + ((uint32_t)acc & 15u)); acc >>= 4; }
+  return p;
+}
+
 template <class W>
 MG_HD void mg_put_u32(W &w, uint32_t v) {
+  if constexpr (W::is_bytes) { w.p = mg_put_u32_p(w.p, v); return; }
   // digits are stacked as nibbles in a register pair (no local-memory array); /10 is a multiply
   uint64_t acc = 0;
   int n = 0;
@@ -287,7 +310,7 @@ MG_HD void mg_put_bytes(W &w, const uint8_t *s, int n) {
 // blk[b] = last node whose key <= (b << blk_shift).
 
 template <class NP, class BP>
-MG_HD int mg_find_node(NP nodes, BP blk, int blk_shift, int n_blk, int n_nodes, uint32_t x) {
+MG_NI int mg_find_node(NP nodes, BP blk, int blk_shift, int n_blk, int n_nodes, uint32_t x) {
   uint32_t b = x >> blk_shift;
   if ((int)b >= n_blk) b = (uint32_t)(n_blk - 1);
   int lo = (int)blk[b];
@@ -332,7 +355,7 @@ MG_HD int mg_nchars_i32(int32_t v) { return v < 0 ? 1 + mg_ndigits32((uint32_t)(
 
 // length of '|strand|pos|rlen|cigar|vlist' for one read; L_nd = decimal digits of L
 template <class NP>
-MG_HD uint32_t mg_read_fields_len(NP nodes, int n0, int n1, uint32_t x, int L, int L_nd) {
+MG_NI uint32_t mg_read_fields_len(NP nodes, int n0, int n1, uint32_t x, int L, int L_nd) {
   const MgNode f = nodes[n0];
   const bool single = (n0 == n1);
   uint32_t n = 2u + 1u + (uint32_t)mg_nchars_i32(mg_read_pos(f, single, x)) + 1u + (uint32_t)L_nd + 1u + 1u;
@@ -396,8 +419,21 @@ MG_HD void mg_fmt_qname(W &w, const uint8_t *prefix, int prefix_len, uint64_t cn
   mg_put_bytes(w, prefix, prefix_len);
   if (with_cnt) mg_put_uint(w, cnt);
   mg_put_bytes(w, mid, mid_len);
-  mg_fmt_read(w, nodes, first.n0, first.n1, first.x, L, first.strand);
-  mg_fmt_read(w, nodes, second.n0, second.n1, second.x, L, second.strand);
+  MG_NOUNROLL
+  for (int r = 0; r < 2; r++) {
+    const MgReadRef R = r ? second : first;
+    mg_fmt_read(w, nodes, R.n0, R.n1, R.x, L, R.strand);
+  }
+}
+
+// qname + newline as bytes at dst (one shared copy per kernel), returns the advanced pointer
+template <class NP>
+MG_NI uint8_t *mg_qname_bytes(uint8_t *dst, const uint8_t *prefix, int prefix_len, uint64_t cnt,
+                              const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
+  MgByteWriter bw; bw.p = dst;
+  mg_fmt_qname(bw, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
+  bw.put('\n');
+  return bw.p;
 }
 
 // L bases of the haplotype starting at relative offset x, forward (strand 0) or reverse
@@ -425,6 +461,61 @@ MG_HD void mg_emit_seq(W &w, HP hap, uint32_t x, int L, int strand) {
   }
 }
 
+// Register window over a read: the 2-bit words covering it are fetched up front (independent
+// loads, all in flight at once) and, for the reverse strand, reversed and complemented word by
+// word in descending order, so that BOTH strands become a forward extraction
+//   codes(c) = funnel(w[c], w[c+1], 2 * off)
+// with compile-time word indices.  MAXW - 1 >= ceil((15 + L) / 16).
+template <int MAXW>
+struct MgWin { uint32_t w[MAXW]; uint32_t off; };
+
+template <int MAXW, class HP>
+MG_HD void mg_win_load(MgWin<MAXW> &W, HP hap, uint32_t x, int L, int strand) {
+  const uint32_t last = x + (uint32_t)L - 1u;
+  const int64_t w_first = (int64_t)(x >> 4), w_last = (int64_t)(last >> 4);
+  W.off = strand ? 15u - (last & 15u) : (x & 15u);
+  const int nw = (int)((W.off + (uint32_t)L + 15u) >> 4);
+  MG_UNROLL
+  for (int i = 0; i < MAXW; i++) {
+    uint32_t v = 0;
+    if (i < nw) v = hap[strand ? w_last - i : w_first + i];
+    W.w[i] = strand ? mg_revcomp16(v) : v;
+  }
+}
+
+template <int MAXW>
+MG_HD uint32_t mg_win_codes(const MgWin<MAXW> &W, int c) {  // c must be a compile-time constant after unrolling
+  return mg_funnel_r(W.w[c], W.w[c + 1], 2u * W.off);
+}
+
+// The emission loops run over chunk PAIRS with a rolled loop (a fully unrolled read is ~1000
+// instructions per site and thrashes the instruction cache): chunks (w[0],w[1]) and (w[1],w[2]) are
+// consumed, then the window slides down by two registers.
+template <int MAXW>
+MG_HD void mg_win_slide2(MgWin<MAXW> &W) {
+  MG_UNROLL
+  for (int i = 0; i < MAXW; i++) W.w[i] = (i + 2 < MAXW) ? W.w[i + 2] : 0u;
+}
+
+template <class WR, int MAXW>
+MG_HD void mg_emit_seq_win(WR &w, const MgWin<MAXW> &W, int L) {
+  MG_UNROLL
+  for (int c = 0; c < MAXW - 1; c++) {
+    if (16 * c < L) {
+      const uint32_t codes = mg_win_codes(W, c);
+      MG_UNROLL
+      for (int q = 0; q < 4; q++) {
+        const int n0 = 16 * c + 4 * q;
+        if (n0 + 4 <= L) w.put_word(mg_chars4((codes >> (8 * q)) & 0xFFu));
+        else if (n0 < L) {
+          uint32_t ch = mg_chars4((codes >> (8 * q)) & 0xFFu);
+          for (int j = 0; n0 + j < L; j++) { w.put((uint8_t)ch); ch >>= 8; }
+        }
+      }
+    }
+  }
+}
+
 template <class W>
 MG_HD void mg_emit_fill(W &w, uint8_t c, int n) {
   uint32_t cw = 0x01010101u * c;
@@ -446,7 +537,7 @@ MG_HD int mg_exc_first(EP exc, int n_exc, uint32_t x) {
 
 // number of 'N' in the read (seq.count('N'), readgenerate.py:204)
 template <class EP>
-MG_HD int mg_count_N(EP exc, int n_exc, uint32_t x, int L) {
+MG_NI int mg_count_N(EP exc, int n_exc, uint32_t x, int L) {
   int cnt = 0;
   for (int k = mg_exc_first(exc, n_exc, x); k < n_exc; k++) {
     MgExc e = exc[k];
@@ -463,7 +554,7 @@ MG_HD int mg_count_N(EP exc, int n_exc, uint32_t x, int L) {
 // runs.  The reference's translate table only maps ATCGN (readgenerate.py:56), so an exception
 // byte is copied unchanged on either strand; only its position is mirrored on strand 1.
 template <class EP>
-MG_HD void mg_patch_exc(uint8_t *seq, EP exc, int n_exc, uint32_t x, int L, int strand) {
+MG_NI void mg_patch_exc(uint8_t *seq, EP exc, int n_exc, uint32_t x, int L, int strand) {
   for (int k = mg_exc_first(exc, n_exc, x); k < n_exc; k++) {
     MgExc e = exc[k];
     if ((uint64_t)e.start >= (uint64_t)x + L) break;
@@ -503,35 +594,85 @@ MG_HD int mg_lower_bound_f64(DP row, int n, double u) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Source of a read's 2-bit codes, 16 bases per chunk.  MAXW > 0: register window (MgWin, loads
+// issued up front, both strands a forward extraction); MAXW == 0: streamed from memory (any L).
+template <int MAXW, class HP>
+struct MgSeqSrc {
+  MgWin<(MAXW > 0 ? MAXW : 2)> W;
+  HP hap; uint32_t x; int L, strand;
+  MG_HD void load(HP hap_, uint32_t x_, int L_, int strand_) {
+    hap = hap_; x = x_; L = L_; strand = strand_;
+    if constexpr (MAXW > 0) mg_win_load(W, hap, x, L, strand);
+  }
+  // streaming source only (MAXW == 0)
+  MG_HD uint32_t codes(int c) const {
+    if (strand == 0) return mg_codes16(hap, (int64_t)x + 16 * c);
+    // output bases [16c, 16c+16) are the complement of forward bases [L-16c-16, L-16c) reversed
+    return mg_revcomp16(mg_codes16(hap, (int64_t)x + L - 16 * (int64_t)c - 16));   // may dip 15 below x: front pad
+  }
+};
+
+// for_each_chunk(S, fn): fn(codes, c) for every 16-base chunk of the read, in order.  Consumes the
+// register window of S.
+template <int MAXW, class HP, class FN>
+MG_HD void mg_for_each_chunk(MgSeqSrc<MAXW, HP> &S, FN fn) {
+  const int L = S.L;
+  if constexpr (MAXW > 0) {
+    MG_NOUNROLL
+    for (int c = 0; 16 * c < L; c += 2) {
+      fn(mg_win_codes(S.W, 0), c);
+      if (16 * (c + 1) < L) fn(mg_win_codes(S.W, 1), c + 1);
+      mg_win_slide2(S.W);
+    }
+  } else {
+    for (int c = 0; 16 * c < L; c++) fn(S.codes(c), c);
+  }
+}
+
+// four output bases of chunk word q (n0 = first base index) through a writer
+template <class WR>
+MG_HD void mg_put_bases4(WR &w, uint32_t b4, int n0, int L) {
+  const uint32_t ch = mg_chars4(b4);
+  if (n0 + 4 <= L) w.put_word(ch);
+  else for (int j = 0; n0 + j < L; j++) w.put((uint8_t)(ch >> (8 * j)));
+}
+
+template <class WR, int MAXW, class HP>
+MG_HD void mg_emit_seq_src(WR &w, MgSeqSrc<MAXW, HP> &S) {
+  const int L = S.L;
+  mg_for_each_chunk(S, [&](uint32_t codes, int c) {
+    MG_NOUNROLL
+    for (int q = 0; q < 4; q++) if (16 * c + 4 * q < L) mg_put_bases4(w, (codes >> (8 * q)) & 0xFFu, 16 * c + 4 * q, L);
+  });
+}
+
 // One FASTQ record (fastq_lines, readgenerate.py:227-230):  qname \n SEQ \n+\n ~~~~ \n
-// `mine` is the read that goes into this file; first/second give the qname's file order.
+// S = the read that goes into this file (already loaded); first/second give the qname's file order.
 // qlen = length of the qname line without its newline (known from the sizing pass).
-template <class NP, class HP, class EP>
+template <int MAXW, class NP, class HP, class EP>
 MG_HD void mg_emit_record(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
                           const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second,
-                          MgReadRef mine, int L, HP hap, EP exc, int n_exc) {
-  MgByteWriter bw; bw.p = dst;
-  mg_fmt_qname(bw, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
-  bw.put('\n');
+                          MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc) {
+  const int L = S.L;
   MgWordStream ws;
-  ws.begin(bw.p);
-  mg_emit_seq(ws, hap, mine.x, L, mine.strand);
+  ws.begin_rmw(mg_qname_bytes(dst, prefix, prefix_len, cnt, mid, mid_len, nodes, first, second, L));
+  mg_emit_seq_src(ws, S);
   ws.put('\n'); ws.put('+'); ws.put('\n');
   mg_emit_fill(ws, '~', L);
   ws.put('\n');
   ws.end();
-  if (n_exc) mg_patch_exc(dst + qlen + 1, exc, n_exc, mine.x, L, mine.strand);
+  if (n_exc) mg_patch_exc(dst + qlen + 1, exc, n_exc, S.x, L, S.strand);
 }
 
 // The other file's record has the same qname, the same offsets and (for perfect reads) the same
 // quality line: only the L sequence bytes are rewritten in place.
-template <class HP, class EP>
-MG_HD void mg_rewrite_seq(uint8_t *seq_dst, MgReadRef mine, int L, HP hap, EP exc, int n_exc) {
+template <int MAXW, class HP, class EP>
+MG_HD void mg_rewrite_seq(uint8_t *seq_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc) {
   MgWordStream ws;
-  ws.begin(seq_dst);
-  mg_emit_seq(ws, hap, mine.x, L, mine.strand);
+  ws.begin_rmw(seq_dst);
+  mg_emit_seq_src(ws, S);
   ws.end();
-  if (n_exc) mg_patch_exc(seq_dst, exc, n_exc, mine.x, L, mine.strand);
+  if (n_exc) mg_patch_exc(seq_dst, exc, n_exc, S.x, S.L, S.strand);
 }
 
 // qname line + the three separator newlines of a record whose SEQ / QUAL lines are written by
@@ -539,9 +680,7 @@ MG_HD void mg_rewrite_seq(uint8_t *seq_dst, MgReadRef mine, int L, HP hap, EP ex
 template <class NP>
 MG_HD void mg_emit_frame(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
                          const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
-  MgByteWriter bw; bw.p = dst;
-  mg_fmt_qname(bw, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
-  bw.put('\n');
+  mg_qname_bytes(dst, prefix, prefix_len, cnt, mid, mid_len, nodes, first, second, L);
   uint8_t *p = dst + qlen + 1 + L;
   p[0] = '\n'; p[1] = '+'; p[2] = '\n'; p[3 + L] = '\n';
 }
@@ -586,49 +725,53 @@ MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_b
 // base_rot on 2-bit codes (A=0 C=1 G=2 T=3): A->CTG, C->ATG, G->ACT, T->ACG as 2-bit triples
 #define MG_ROT_TBL (45u | (44u << 6) | (52u << 12) | (36u << 18))
 
+// four bases (chunk word q, first base index n0) corrupted on the 2-bit codes -> ASCII bases + qualities
+MG_HD void mg_corrupt4(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, uint32_t &b4, uint32_t &qw) {
+  qw = 0;
+  MG_NOUNROLL
+  for (int h = 0; h < 2; h++) {
+    if (n0 + 2 * h < L) {
+      const MgPhilox r = mg_philox(serial, f, (uint32_t)((n0 >> 1) + h), MG_STREAM_CORRUPT, C.k0, C.k1);
+      MG_UNROLL
+      for (int e = 0; e < 2; e++) {
+        const int j = 2 * h + e, n = n0 + j;
+        if (n < L) {
+          uint32_t qual;
+          const uint32_t d = mg_corrupt_draw(C, f, n, e ? r.v[2] : r.v[0], e ? r.v[3] : r.v[1], qual);
+          if (d) {
+            const uint32_t code = (b4 >> (2 * j)) & 3u;
+            const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * (d & 3u))) & 3u;
+            b4 ^= (code ^ nc) << (2 * j);
+          }
+          qw |= qual << (8 * j);
+        }
+      }
+    }
+  }
+}
+
 // SEQ and QUAL lines of one read, corrupted on the fly: every thread of a warp is at the same
 // cycle of its own record, so the alias row (one 256-byte line pair) is shared by the warp.
-template <class HP, class EP>
-MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgReadRef mine, int L, HP hap, EP exc, int n_exc,
+template <int MAXW, class HP, class EP>
+MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc,
                                const MgCorruptCtx &C, uint32_t serial, uint32_t f) {
+  const int L = S.L;
+  const struct { uint32_t x; int strand; } mine = {S.x, S.strand};
   MgWordStream ws, wq;
-  ws.begin(seq_dst); wq.begin(qual_dst);
-  const int nchunk = (L + 15) >> 4;
-  for (int c = 0; c < nchunk; c++) {
-    uint32_t codes;
-    if (mine.strand == 0) codes = mg_codes16(hap, (int64_t)mine.x + 16 * c);
-    else codes = mg_revcomp16(mg_codes16(hap, (int64_t)mine.x + L - 16 * (int64_t)c - 16));
-    MG_UNROLL
+  ws.begin_rmw(seq_dst); wq.begin_rmw(qual_dst);
+  mg_for_each_chunk(S, [&](uint32_t codes, int c) {
+    MG_NOUNROLL
     for (int q = 0; q < 4; q++) {
       const int n0 = 16 * c + 4 * q;
       if (n0 < L) {
-        uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw = 0;
-        MG_UNROLL
-        for (int h = 0; h < 2; h++) {
-          if (n0 + 2 * h < L) {
-            const MgPhilox r = mg_philox(serial, f, (uint32_t)((n0 >> 1) + h), MG_STREAM_CORRUPT, C.k0, C.k1);
-            MG_UNROLL
-            for (int e = 0; e < 2; e++) {
-              const int j = 2 * h + e, n = n0 + j;
-              if (n < L) {
-                uint32_t qual;
-                const uint32_t d = mg_corrupt_draw(C, f, n, e ? r.v[2] : r.v[0], e ? r.v[3] : r.v[1], qual);
-                if (d) {
-                  const uint32_t code = (b4 >> (2 * j)) & 3u;
-                  const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * (d & 3u))) & 3u;
-                  b4 ^= (code ^ nc) << (2 * j);
-                }
-                qw |= qual << (8 * j);
-              }
-            }
-          }
-        }
+        uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw;
+        mg_corrupt4(C, serial, f, n0, L, b4, qw);
         const uint32_t ch = mg_chars4(b4);
         if (n0 + 4 <= L) { ws.put_word(ch); wq.put_word(qw); }
         else for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
       }
     }
-  }
+  });
   ws.end(); wq.end();
   if (n_exc) {
     // bases in exception runs: the reference substitutes 'N' for any non-ACGT base on an error

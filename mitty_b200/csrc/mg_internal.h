@@ -4,7 +4,8 @@
 #include <stdint.h>
 #include "mg_core.cuh"
 
-#define MG_TILE 128          // candidates (and threads) per emit tile
+#define MG_TILE 32           // candidates per emit tile: one warp owns one tile
+#define MG_CTA 128           // threads per CTA of the emit kernel (4 independent warps)
 #define MG_TLEN_K 1024       // entries of the template-length alias table (outcomes 0..n_tlen)
 #define MG_QN_MAX 192        // max length of the qname prefix / mid strings
 #define MG_HAP_PAD 8         // 32-bit words of padding on both sides of a packed sequence
@@ -69,7 +70,7 @@ void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const uin
 void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st);
 void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
                         cudaStream_t st);
-int mg_unit_grid(int stage_cap, int *smem_bytes);
+int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes);
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st);
 void mg_launch_sample(const MgSampleParams &P, cudaStream_t st);
 void mg_launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st);  // exclusive, out[n] = total

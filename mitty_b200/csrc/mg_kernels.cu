@@ -324,23 +324,13 @@ void mg_launch_sample(const MgSampleParams &P, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // k_unit_emit
 
-struct Slot {
-  uint32_t xa, xb;        // read starts (relative to p_min) of mate 0 / mate 1
-  int32_t n0a, n0b;       // first node of each read
-  uint16_t dna, dnb;      // n1 - n0 of each read
-  uint32_t aux;           // PHILOX: file-order bit; DET/EXPLICIT: local rank among te<p_max survivors
-  uint32_t sz;            // record bytes without the serial digits
-  uint32_t esz;           // exclusive scan of sz inside the tile
-  uint32_t loff;          // byte offset of the record inside the tile (phase 2)
-  uint32_t qlen;          // qname length (phase 2)
-};
-
 struct Agg { unsigned long long c1, c2, by; };
 
 #define DESC_FLAG(x) ((uint32_t)((x) >> 62))
 #define DESC_MASK62 ((1ull << 62) - 1ull)
 
-// warp 0: exclusive prefix of (c1, c2, bytes) over all tiles before `tile` (decoupled look-back)
+// Exclusive prefix of (c1, c2, bytes) over all tiles before `tile` (decoupled look-back), computed
+// by one whole warp; every lane returns the same sums.
 __device__ Agg tile_lookback(const MgUnitParams &P, int tile, int lane) {
   Agg ex = {0, 0, 0};
   int idx = tile - 1;
@@ -369,33 +359,38 @@ __device__ Agg tile_lookback(const MgUnitParams &P, int tile, int lane) {
   return ex;
 }
 
-__global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ MgUnitParams P) {
+// One WARP owns one tile of 32 candidates end to end: sampling, filters, sizing, warp scan,
+// look-back, formatting into its own shared-memory stage, coalesced copy-out.  Warps never wait
+// for each other (no block barrier inside the loop), so they drift apart and hide each other's
+// latencies; tiles are claimed from an atomic counter, which also keeps the look-back deadlock-free.
+template <int MAXW, bool CORRUPT>
+__global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t *s_tlen = reinterpret_cast<uint32_t *>(smem);
-  uint8_t *stage = smem + MG_TLEN_K * sizeof(uint32_t);
-
-  __shared__ Slot slots[MG_TILE];
-  __shared__ uint32_t s_wc[MG_TILE / 32], s_ws[MG_TILE / 32];
-  __shared__ unsigned long long s_base[3];
-  __shared__ uint32_t s_tile;
   __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
 
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  uint8_t *stage = smem + MG_TLEN_K * sizeof(uint32_t) + (size_t)wid * (P.stage_cap + 16);
   const int L = P.rlen;
-  if (P.mode == MG_MODE_PHILOX && P.tlen_alias)
-    for (int i = t; i < MG_TLEN_K; i += MG_TILE) s_tlen[i] = P.tlen_alias[i];
-  for (int i = t; i < P.prefix_len; i += MG_TILE) s_prefix[i] = P.prefix[i];
-  for (int i = t; i < P.mid_len; i += MG_TILE) s_mid[i] = P.mid[i];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  if (P.mode == MG_MODE_PHILOX && P.tlen_alias) {
+#pragma unroll 1
+    for (int i = t; i < MG_TLEN_K; i += MG_CTA) s_tlen[i] = P.tlen_alias[i];
+  }
+#pragma unroll 1
+  for (int i = t; i < P.prefix_len; i += MG_CTA) s_prefix[i] = P.prefix[i];
+#pragma unroll 1
+  for (int i = t; i < P.mid_len; i += MG_CTA) s_mid[i] = P.mid[i];
+  __syncthreads();
 
   while (true) {
-    __syncthreads();
-    if (t == 0) s_tile = atomicAdd(P.tile_counter, 1u);
-    __syncthreads();
-    const int tile = (int)s_tile;
+    uint32_t tile_u = 0;
+    if (lane == 0) tile_u = atomicAdd(P.tile_counter, 1u);
+    const int tile = (int)__shfl_sync(FULL, tile_u, 0);
     if (tile >= P.n_tiles) break;
 
-    // ---- phase 1: one candidate per thread -------------------------------------------------
-    const uint32_t j = (uint32_t)tile * MG_TILE + t;
+    // ---- phase 1: one candidate per lane ----------------------------------------------------
+    const uint32_t j = (uint32_t)tile * MG_TILE + lane;
     bool k1 = false, k2 = false;
     uint32_t xa = 0, xb = 0, fo = 0, sz = 0;
     int n0a = 0, n1a = 0, n0b = 0, n1b = 0;
@@ -416,131 +411,129 @@ __global__ void __launch_bounds__(MG_TILE) k_unit_emit(const __grid_constant__ M
         }
       }
     }
-    // block scan of (k1 | k2 << 16, sz)
-    uint32_t cpk = (k1 ? 1u : 0u) | (k2 ? 0x10000u : 0u);
-    uint32_t ic = warp_incl_scan_u32(cpk, lane), is = warp_incl_scan_u32(sz, lane);
-    if (lane == 31) { s_wc[wid] = ic; s_ws[wid] = is; }
-    __syncthreads();
-    uint32_t oc = 0, os = 0, tc = 0, ts_ = 0;
-#pragma unroll
-    for (int w = 0; w < MG_TILE / 32; w++) {
-      if (w < wid) { oc += s_wc[w]; os += s_ws[w]; }
-      tc += s_wc[w]; ts_ += s_ws[w];
-    }
-    const uint32_t ec = oc + ic - cpk, es = os + is - sz;   // exclusive
-    if (k2) {
-      Slot &s = slots[ec >> 16];
-      s.xa = xa; s.xb = xb; s.n0a = n0a; s.n0b = n0b;
-      s.dna = (uint16_t)(n1a - n0a); s.dnb = (uint16_t)(n1b - n0b);
-      s.aux = (P.mode == MG_MODE_PHILOX) ? fo : (ec & 0xFFFFu);
-      s.sz = sz; s.esz = es;
-    }
-    const uint32_t tile_c1 = tc & 0xFFFFu, tile_c2 = tc >> 16, tile_sz = ts_;
+    const uint32_t m1 = __ballot_sync(FULL, k1), m2 = __ballot_sync(FULL, k2);
+    const uint32_t tile_c1 = __popc(m1), tile_c2 = __popc(m2);
+    const uint32_t isz = warp_incl_scan_u32(sz, lane);
+    const uint32_t tile_sz = __shfl_sync(FULL, isz, 31);
+    const uint32_t rank1 = __popc(m1 & lt_mask);          // among te<p_max survivors (file-order draw index)
 
     // ---- grid-wide placement: decoupled look-back over tile descriptors ----------------------
-    if (wid == 0) {
-      Agg ex = {0, 0, 0};
-      if (tile > 0) {
-        if (lane == 0) {
-          st_vol64(P.descA + tile, (1ull << 62) | ((unsigned long long)tile_c1 << 31) | tile_c2);
-          st_vol64(P.descB + tile, (1ull << 62) | tile_sz);
-        }
-        ex = tile_lookback(P, tile, lane);
-      }
+    Agg ex = {0, 0, 0};
+    if (tile > 0) {
       if (lane == 0) {
-        unsigned long long i1 = ex.c1 + tile_c1, i2 = ex.c2 + tile_c2, ib = ex.by + tile_sz;
-        st_vol64(P.descA + tile, (2ull << 62) | (i1 << 31) | i2);
-        st_vol64(P.descB + tile, (2ull << 62) | ib);
-        s_base[0] = ex.c1; s_base[1] = ex.c2; s_base[2] = ex.by;
-        if (tile == P.n_tiles - 1) {
-          P.totals[0] = i1; P.totals[1] = i2; P.totals[2] = ib + mg_digit_sum(i2);
-          if (P.rec_off) P.rec_off[i2] = ib + mg_digit_sum(i2);
-        }
+        st_vol64(P.descA + tile, (1ull << 62) | ((unsigned long long)tile_c1 << 31) | tile_c2);
+        st_vol64(P.descB + tile, (1ull << 62) | tile_sz);
+      }
+      ex = tile_lookback(P, tile, lane);
+    }
+    if (lane == 0) {
+      const unsigned long long i1 = ex.c1 + tile_c1, i2 = ex.c2 + tile_c2, ib = ex.by + tile_sz;
+      st_vol64(P.descA + tile, (2ull << 62) | (i1 << 31) | i2);
+      st_vol64(P.descB + tile, (2ull << 62) | ib);
+      if (tile == P.n_tiles - 1) {
+        P.totals[0] = i1; P.totals[1] = i2; P.totals[2] = ib + mg_digit_sum(i2);
+        if (P.rec_off) P.rec_off[i2] = ib + mg_digit_sum(i2);
       }
     }
-    __syncthreads();
-    const unsigned long long base1 = s_base[0], base2 = s_base[1];
+    const unsigned long long base1 = ex.c1, base2 = ex.c2;
     const unsigned long long dsum0 = mg_digit_sum(base2);
-    const unsigned long long goff = s_base[2] + dsum0;                          // byte offset of the tile in each file
+    const unsigned long long goff = ex.by + dsum0;                              // byte offset of the tile in each file
     const uint32_t nk = tile_c2;
     const uint32_t tile_bytes = tile_sz + (uint32_t)(mg_digit_sum(base2 + nk) - dsum0);
     const bool overflow = goff + tile_bytes > P.cap;
-    if (overflow && t == 0) atomicExch(&P.totals[3], 1ull);
+    if (overflow && lane == 0) atomicExch(&P.totals[3], 1ull);
     const uint32_t pad = (uint32_t)(goff & 15);
     const bool staged = (pad + tile_bytes) <= (uint32_t)P.stage_cap;
 
-    // ---- phase 2: one kept template per thread -----------------------------------------------
-    MgReadRef ra = {0, 0, 0, 0}, rb = {0, 0, 0, 1};
+    // ---- compaction: lane k takes the k-th kept template (register shuffles, no shared memory) -
+    const int src = (int)__fns(m2, 0, lane + 1) & 31;
+    MgReadRef ra, rb;
+    ra.x = __shfl_sync(FULL, xa, src); ra.n0 = __shfl_sync(FULL, n0a, src); ra.n1 = __shfl_sync(FULL, n1a, src); ra.strand = 0;
+    rb.x = __shfl_sync(FULL, xb, src); rb.n0 = __shfl_sync(FULL, n0b, src); rb.n1 = __shfl_sync(FULL, n1b, src); rb.strand = 1;
+    const uint32_t k_sz = __shfl_sync(FULL, sz, src), k_esz = __shfl_sync(FULL, isz - sz, src);
+    const uint32_t k_fo = __shfl_sync(FULL, fo, src), k_rank1 = __shfl_sync(FULL, rank1, src);
+    const bool active = (uint32_t)lane < nk;
+
+    // ---- phase 2: one kept template per lane --------------------------------------------------
     uint32_t loff = 0, qlen = 0, my_fo = 0;
     unsigned long long cnt = 0;
-    if ((uint32_t)t < nk) {
-      Slot &s = slots[t];
-      ra.x = s.xa; ra.n0 = s.n0a; ra.n1 = s.n0a + s.dna; ra.strand = 0;
-      rb.x = s.xb; rb.n0 = s.n0b; rb.n1 = s.n0b + s.dnb; rb.strand = 1;
-      cnt = base2 + t + 1;                                                      // readgenerate.py:209
-      loff = s.esz + (uint32_t)(mg_digit_sum(base2 + t) - dsum0);
-      qlen = s.sz + (uint32_t)mg_ndigits(cnt) - (2u * (uint32_t)L + 5u);
-      my_fo = (P.mode == MG_MODE_PHILOX) ? s.aux : (uint32_t)(P.fo_in[base1 + s.aux] & 1);   // illumina.py:93
-      s.loff = loff; s.qlen = qlen;
-      if (P.rec_off && !overflow) P.rec_off[base2 + t] = goff + loff;
+    if (active) {
+      cnt = base2 + lane + 1;                                                   // readgenerate.py:209
+      loff = k_esz + (uint32_t)(mg_digit_sum(base2 + lane) - dsum0);
+      qlen = k_sz + (uint32_t)mg_ndigits(cnt) - (2u * (uint32_t)L + 5u);
+      my_fo = (P.mode == MG_MODE_PHILOX) ? k_fo : (uint32_t)(P.fo_in[base1 + k_rank1] & 1);   // illumina.py:93
+      if (P.rec_off && !overflow) P.rec_off[base2 + lane] = goff + loff;
     }
     if (!overflow) {
+      // reads[fo] = mate (readgenerate.py:207): file f holds mate 0 iff fo == f
+      const MgReadRef first = my_fo ? rb : ra, second = my_fo ? ra : rb;
+      MgSeqSrc<MAXW, const uint32_t *> S;
+      if (active) S.load(P.hap, first.x, L, first.strand);    // loads in flight while the qname is formatted
       for (int f = 0; f < 2; f++) {
         if (P.out[f] == nullptr) continue;
-        if ((uint32_t)t < nk) {
-          // reads[fo] = mate (readgenerate.py:207): file f holds mate 0 iff fo == f
-          const MgReadRef first = my_fo ? rb : ra, second = my_fo ? ra : rb;
-          const MgReadRef mine = f ? second : first;
+        if (active) {
           uint8_t *dst = staged ? (stage + pad + loff) : (P.out[f] + goff + loff);
           // staged tiles keep the qname (and, for perfect reads, the quality line) of file 0 in
           // place: the other file only rewrites its L sequence bytes
           const bool full = (f == 0) || !staged || (P.out[0] == nullptr);
-          if (P.corrupt) {
+          if (f == 1 && P.out[0] == nullptr) S.load(P.hap, second.x, L, second.strand);
+          if constexpr (CORRUPT) {
             if (full) mg_emit_frame(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
-            mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, mine, L, P.hap, P.exc, P.n_exc, P.cor, (uint32_t)(cnt - 1), (uint32_t)f);
-          } else if (full) {
-            mg_emit_record(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, mine, L, P.hap, P.exc, P.n_exc);
+            mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, P.cor, (uint32_t)(cnt - 1), (uint32_t)f);
           } else {
-            mg_rewrite_seq(dst + qlen + 1, mine, L, P.hap, P.exc, P.n_exc);
+            if (full) mg_emit_record(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
+            else mg_rewrite_seq(dst + qlen + 1, S, P.exc, P.n_exc);
           }
+          if (f == 0) S.load(P.hap, second.x, L, second.strand);          // overlaps with the copy-out below
         }
         if (staged) {
-          __syncthreads();
+          __syncwarp();
           // coalesced copy-out: smem and global share the same 16-byte phase (pad)
           uint8_t *gdst = P.out[f] + goff;
           const uint8_t *ssrc = stage + pad;
           uint32_t head = (16u - pad) & 15u;
           if (head > tile_bytes) head = tile_bytes;
-          if ((uint32_t)t < head) gdst[t] = ssrc[t];
-          uint32_t nvec = (tile_bytes - head) >> 4;
+          if ((uint32_t)lane < head) gdst[lane] = ssrc[lane];
+          const uint32_t nvec = (tile_bytes - head) >> 4;
           const uint4 *sv = reinterpret_cast<const uint4 *>(ssrc + head);
           uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
-          for (uint32_t v = t; v < nvec; v += MG_TILE) gv[v] = sv[v];
-          uint32_t done = head + (nvec << 4);
-          if (done + t < tile_bytes) gdst[done + t] = ssrc[done + t];
-          __syncthreads();
+          for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
+          const uint32_t done = head + (nvec << 4);
+          if (done + lane < tile_bytes) gdst[done + lane] = ssrc[done + lane];
+          __syncwarp();
         }
       }
     }
   }
 }
 
-int mg_unit_grid(int stage_cap, int *smem_bytes) {
-  int smem = MG_TLEN_K * (int)sizeof(uint32_t) + stage_cap + 16;
+typedef void (*unit_kernel_t)(const MgUnitParams);
+
+static unit_kernel_t unit_kernel(int L, int corrupt) {
+  // register window: MAXW - 1 >= ceil((15 + L) / 16)
+  if (L <= 161) return corrupt ? k_unit_emit<12, true> : k_unit_emit<12, false>;
+  if (L <= 305) return corrupt ? k_unit_emit<21, true> : k_unit_emit<21, false>;
+  return corrupt ? k_unit_emit<0, true> : k_unit_emit<0, false>;
+}
+
+int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
+  int smem = MG_TLEN_K * (int)sizeof(uint32_t) + (MG_CTA / 32) * (stage_cap + 16);
   *smem_bytes = smem;
-  cudaFuncSetAttribute(k_unit_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  unit_kernel_t k = unit_kernel(L, corrupt);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int per_sm = 0, dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unit_emit, MG_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, MG_CTA, smem);
   if (per_sm < 1) per_sm = 1;
   return sms * per_sm;
 }
 
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st) {
   if (P.n_tiles == 0) return;
-  if (grid > P.n_tiles) grid = P.n_tiles;
-  k_unit_emit<<<grid, MG_TILE, smem_bytes, st>>>(P);
+  const int need = (P.n_tiles + MG_CTA / 32 - 1) / (MG_CTA / 32);
+  if (grid > need) grid = need;
+  unit_kernel(P.rlen, P.corrupt)<<<grid, MG_CTA, smem_bytes, st>>>(P);
 }
 
 // ------------------------------------------------------------------------------------------

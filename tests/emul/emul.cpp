@@ -5,12 +5,11 @@
 #include <cstring>
 #include "../../mitty_b200/csrc/mg_core.cuh"
 
-extern "C" {
-
 // mirrors k_unit_emit phase 1 + phase 2 for explicit templates (ts_rel, tl), one template at a time.
 // Like a staged tile of the kernel: the file-0 record is written into a stage buffer and copied
 // out, then only the sequence (and, when corrupting, the quality) bytes are rewritten for file 1.
-int64_t emul_unit(const uint32_t *hap, uint32_t hap_len, const MgNode *nodes, int n_nodes, const uint32_t *blk,
+template <int MAXW>
+static int64_t emul_unit_t(const uint32_t *hap, uint32_t hap_len, const MgNode *nodes, int n_nodes, const uint32_t *blk,
                   int blk_shift, int n_blk, const MgExc *exc, int n_exc, int L, int64_t n, const int64_t *ts_rel,
                   const int64_t *tl_in, const int8_t *fo_in, const char *prefix, const char *mid, uint8_t *out1,
                   uint8_t *out2, int64_t cap, int64_t *n_bytes,
@@ -46,22 +45,41 @@ int64_t emul_unit(const uint32_t *hap, uint32_t hap_len, const MgNode *nodes, in
     if ((int64_t)(off + rec) > cap || rec + 8 > sizeof stage_raw) return -1;
     MgReadRef first = fo ? rb : ra, second = fo ? ra : rb;
     uint8_t *dst = stage_raw + (off & 3);                // same word phase as the final destination
+    MgSeqSrc<MAXW, const uint32_t *> S;
+    S.load(hap, first.x, L, first.strand);
     if (corrupt) {
       mg_emit_frame(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, L);
-      mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, first, L, hap, exc, n_exc, cor, (uint32_t)(cnt - 1), 0u);
+      mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, exc, n_exc, cor, (uint32_t)(cnt - 1), 0u);
       memcpy(out1 + off, dst, rec);
-      mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, second, L, hap, exc, n_exc, cor, (uint32_t)(cnt - 1), 1u);
+      S.load(hap, second.x, L, second.strand);
+      mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, exc, n_exc, cor, (uint32_t)(cnt - 1), 1u);
       memcpy(out2 + off, dst, rec);
     } else {
-      mg_emit_record(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, first, L, hap, exc, n_exc);
+      mg_emit_record(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, S, exc, n_exc);
       memcpy(out1 + off, dst, rec);
-      mg_rewrite_seq(dst + qlen + 1, second, L, hap, exc, n_exc);
+      S.load(hap, second.x, L, second.strand);
+      mg_rewrite_seq(dst + qlen + 1, S, exc, n_exc);
       memcpy(out2 + off, dst, rec);
     }
     sz_sum += sz; cnt2++;
   }
   *n_bytes = (int64_t)(sz_sum + mg_digit_sum(cnt2));
   return (int64_t)cnt2;
+}
+
+extern "C" {
+
+// maxw selects the code-source variant the kernel would use: 12 / 21 register windows, 0 streaming
+int64_t emul_unit(const uint32_t *hap, uint32_t hap_len, const MgNode *nodes, int n_nodes, const uint32_t *blk,
+                  int blk_shift, int n_blk, const MgExc *exc, int n_exc, int L, int64_t n, const int64_t *ts_rel,
+                  const int64_t *tl_in, const int8_t *fo_in, const char *prefix, const char *mid, uint8_t *out1,
+                  uint8_t *out2, int64_t cap, int64_t *n_bytes,
+                  int corrupt, const uint32_t *alias, int kshift, int n_cycles, const uint32_t *err, uint32_t k0, uint32_t k1, int maxw) {
+#define EMUL_ARGS hap, hap_len, nodes, n_nodes, blk, blk_shift, n_blk, exc, n_exc, L, n, ts_rel, tl_in, fo_in, prefix, mid, out1, out2, cap, n_bytes, corrupt, alias, kshift, n_cycles, err, k0, k1
+  if (maxw == 12 && L <= 161) return emul_unit_t<12>(EMUL_ARGS);
+  if (maxw == 21 && L <= 305) return emul_unit_t<21>(EMUL_ARGS);
+  if (maxw == 0) return emul_unit_t<0>(EMUL_ARGS);
+  return -9;
 }
 
 void emul_permute(uint32_t n, uint32_t half_bits, uint32_t k0, uint32_t k1, uint32_t *out) {

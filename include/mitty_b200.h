@@ -113,9 +113,12 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
                      const int64_t *draw_off, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *out_len1,
                      int64_t *out_len2, int64_t *n_templates);
 
-/* ---- profiling: device time (CUDA events on the launch stream) of the emit / corrupt kernels -- */
+/* ---- profiling: device time (CUDA events on the launch stream) of the emit / corrupt kernel
+ * (emit_ms over emit_launches launches, emit_bytes written) and of the planning kernel (plan_ms);
+ * total_launches counts every kernel this context launched since the last reset.               */
 int mg_prof_reset(mg_ctx *ctx);
-int mg_prof_get(mg_ctx *ctx, double *emit_ms, int64_t *emit_launches, int64_t *emit_bytes, int64_t *total_launches);
+int mg_prof_get(mg_ctx *ctx, double *emit_ms, int64_t *emit_launches, int64_t *emit_bytes, int64_t *total_launches,
+                double *plan_ms);
 
 #ifdef __cplusplus
 }

@@ -75,9 +75,10 @@ struct mg_ctx {
   std::map<int64_t, std::unique_ptr<Copy>> copies;
   int64_t next_id = 1;
   // scratch
-  DevBuf s_raw, s_exc, s_ts, s_u, s_fo, s_tsorted, s_partial, s_state, s_out[2], s_str, s_qn, s_sample[3];
+  DevBuf s_raw, s_exc, s_ts, s_u, s_fo, s_tsorted, s_partial, s_state, s_out[2], s_str, s_qn, s_plan, s_sample[3];
   DevBuf c_in[2], c_out[2], c_nl[2], c_cnt, c_sz[2], c_off[2], c_tmp, c_draw[4];
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  double plan_ms = 0;
   double emit_ms = 0; int64_t emit_launches = 0, emit_bytes = 0, total_launches = 0;
 };
 
@@ -190,7 +191,7 @@ int mg_ctx_create(int device, void *stream, mg_ctx **out) {
   ctx->device = device;
   if (stream) ctx->stream = reinterpret_cast<cudaStream_t>(stream);
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MG_ECUDA; } ctx->own_stream = true; }
-  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2);
   *out = ctx;
   return MG_OK;
 }
@@ -204,6 +205,7 @@ void mg_ctx_destroy(mg_ctx *ctx) {
   ctx->pool.clear(); ctx->block_size.clear();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -612,12 +614,9 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
   P.cor.k0 = d->corrupt_seed; P.cor.k1 = d->unit_seed ^ 0x636f7231u;
   P.L_nd = mg_ndigits32((uint32_t)L);
 
-  P.n_tiles = (int)((n + MG_TILE - 1) / MG_TILE);
-  // stage sized for the expected ~5/6 of the candidates that survive (1.2x over-draw) with >3 sigma
-  // of slack; a tile that does not fit takes the direct-to-global path
-  // per-warp stage: room for all 32 candidates of a tile with an average qname (~5/6 survive the
-  // 1.2x over-draw); a tile that does not fit takes the direct-to-global path
-  int stage = MG_TILE * (2 * L + 5 + 80);
+  P.n_tiles = (int)((n + MG_PLAN_TILE - 1) / MG_PLAN_TILE);
+  // per-warp stage of the emit kernel: 32 records with an average qname; larger batches are split
+  int stage = 32 * (2 * L + 5 + 100);
   if (stage > 48 * 1024) stage = 48 * 1024;
   P.stage_cap = stage & ~15;
   int smem = 0;
@@ -631,16 +630,22 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
   P.tile_counter = reinterpret_cast<uint32_t *>(sb + 32);
   P.descA = reinterpret_cast<unsigned long long *>(sb + 48);
   P.descB = P.descA + std::max(P.n_tiles, 1);
+  CU(ctx->s_plan.need(sizeof(MgPlan) * std::max<size_t>(n, 1)));
+  P.plan = ctx->s_plan.as<MgPlan>();
 
-  // device output buffers: sized from an estimate, regrown to the exact size on overflow
-  size_t est = n * (size_t)(2 * L + 5 + pl + ml + 12 + 2 * 36) + 4096;
+  // device output buffers: sized from an estimate, regrown to the exact size on overflow (the plan
+  // stays valid: only the emit kernel is launched again)
+  size_t est = n * (size_t)(2 * L + 5 + pl + ml + 12 + 2 * 36) / 6 * 5 + 4096;   // ~5/6 of the candidates survive
   const bool want_out = (out1 != nullptr) || (out2 != nullptr);
   unsigned long long tot[4] = {0, 0, 0, 0};
+  CU(cudaMemsetAsync(sb, 0, state_bytes, ctx->stream));
+  CU(cudaEventRecord(ctx->ev2, ctx->stream));
+  mg_launch_plan(P, ctx->stream);
+  CU(cudaGetLastError());
   for (int attempt = 0; attempt < 2; attempt++) {
     CU(ctx->s_out[0].need(est)); CU(ctx->s_out[1].need(est));
     P.out[0] = ctx->s_out[0].as<uint8_t>(); P.out[1] = ctx->s_out[1].as<uint8_t>();
     P.cap = std::min(ctx->s_out[0].cap, ctx->s_out[1].cap);
-    CU(cudaMemsetAsync(sb, 0, state_bytes, ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     mg_launch_unit(P, grid, smem, ctx->stream);
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -648,13 +653,16 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
     CU(cudaMemcpyAsync(tot, P.totals, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (P.n_tiles) {
-      float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      float ms = 0, ms_plan = 0;
+      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      if (attempt == 0) { cudaEventElapsedTime(&ms_plan, ctx->ev2, ctx->ev0); ctx->plan_ms += ms_plan; ctx->total_launches++; }
       ctx->emit_ms += ms; ctx->emit_launches++; ctx->total_launches++;
       ctx->emit_bytes += 2 * (int64_t)tot[2];
     }
     if (!tot[3]) break;
     if (attempt == 1) return fail(ctx, MG_ECUDA, "internal: output overflow after regrow");
     est = (size_t)tot[2] + 4096;
+    CU(cudaMemsetAsync(P.totals + 3, 0, 8, ctx->stream));
   }
   if (n_bytes) *n_bytes = (int64_t)tot[2];
   if (n_templates) *n_templates = (int64_t)tot[1];
@@ -763,13 +771,14 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
 
 int mg_prof_reset(mg_ctx *ctx) {
   if (!ctx) return MG_EINVAL;
-  ctx->emit_ms = 0; ctx->emit_launches = 0; ctx->emit_bytes = 0; ctx->total_launches = 0;
+  ctx->emit_ms = 0; ctx->plan_ms = 0; ctx->emit_launches = 0; ctx->emit_bytes = 0; ctx->total_launches = 0;
   return MG_OK;
 }
 
-int mg_prof_get(mg_ctx *ctx, double *emit_ms, int64_t *emit_launches, int64_t *emit_bytes, int64_t *total_launches) {
+int mg_prof_get(mg_ctx *ctx, double *emit_ms, int64_t *emit_launches, int64_t *emit_bytes, int64_t *total_launches, double *plan_ms) {
   if (!ctx) return MG_EINVAL;
   if (emit_ms) *emit_ms = ctx->emit_ms;
+  if (plan_ms) *plan_ms = ctx->plan_ms;
   if (emit_launches) *emit_launches = ctx->emit_launches;
   if (emit_bytes) *emit_bytes = ctx->emit_bytes;
   if (total_launches) *total_launches = ctx->total_launches;

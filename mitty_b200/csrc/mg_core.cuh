@@ -186,9 +186,22 @@ MG_HD uint32_t mg_permute(uint32_t i, uint32_t n, uint32_t half_bits, uint32_t k
 // ------------------------------------------------------------------------------------------
 // Decimal helpers
 
-MG_HD int mg_ndigits32(uint32_t v) {   // branch-free: no division
-  return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
-         (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+MG_HD uint32_t mg_pow10(int d) {   // 10^d for d in 0..9
+  switch (d) {
+    case 0: return 1u; case 1: return 10u; case 2: return 100u; case 3: return 1000u; case 4: return 10000u;
+    case 5: return 100000u; case 6: return 1000000u; case 7: return 10000000u; case 8: return 100000000u;
+    default: return 1000000000u;
+  }
+}
+
+MG_NI int mg_ndigits32(uint32_t v) {   // no division: bit length -> digit estimate -> one correction
+#if defined(__CUDA_ARCH__)
+  const int bits = 32 - __clz((int)(v | 1u));
+#else
+  const int bits = 32 - __builtin_clz(v | 1u);
+#endif
+  const int g = (bits * 1233) >> 12;          // floor(bits * log10(2)), g in 0..9
+  return g + ((v >= mg_pow10(g)) || v == 0u ? 1 : 0);
 }
 
 MG_HD int mg_ndigits(uint64_t v) {
@@ -204,15 +217,14 @@ MG_HD int mg_nchars_int(int64_t v) { return v < 0 ? 1 + mg_ndigits((uint64_t)(-v
 // serial number that is only known after the block/grid scan):  d*(m+1) - 11..1 (d ones)
 MG_NI uint64_t mg_digit_sum(uint64_t m) {
   if (m == 0) return 0;
-  int d = mg_ndigits(m);
-  uint64_t ones = 0, p = 1;
-  if (d <= 10) {
-    const uint32_t t = (uint32_t)d;
-    ones = t == 1 ? 1ull : t == 2 ? 11ull : t == 3 ? 111ull : t == 4 ? 1111ull : t == 5 ? 11111ull : t == 6 ? 111111ull :
-           t == 7 ? 1111111ull : t == 8 ? 11111111ull : t == 9 ? 111111111ull : 1111111111ull;
-  } else {
-    for (int k = 0; k < d; k++) { ones += p; p *= 10; }
+  if (m <= 0xFFFFFFFFull) {
+    const int d = mg_ndigits32((uint32_t)m);
+    const uint64_t ones = d < 10 ? (uint64_t)((mg_pow10(d) - 1u) / 9u) : 1111111111ull;
+    return (uint64_t)d * (m + 1) - ones;
   }
+  const int d = mg_ndigits(m);
+  uint64_t ones = 0, p = 1;
+  for (int k = 0; k < d; k++) { ones += p; p *= 10; }
   return (uint64_t)d * (m + 1) - ones;
 }
 
@@ -260,12 +272,13 @@ struct MgWordStream {
     carry = mg_funnel_l(w, 0u, sh);          // the top nb bytes of w (0 when nb == 0)
   }
   // the last partial word is shared with the NEXT record (another thread): byte stores
-  MG_HD void end() {
-    uint8_t *b = (uint8_t *)wp;
-    for (uint32_t i = 0; i < nb; i++) b[i] = (uint8_t)(carry >> (8 * i));
-    nb = 0;
-  }
+  MG_HD void end();
 };
+
+MG_NI void mg_store_tail(uint8_t *b, uint32_t carry, uint32_t nb) {
+  for (uint32_t i = 0; i < nb; i++) b[i] = (uint8_t)(carry >> (8 * i));
+}
+MG_HD void MgWordStream::end() { mg_store_tail((uint8_t *)wp, carry, nb); nb = 0; }
 
 // decimal digits of v at p (byte stores), returns the advanced pointer
 MG_NI uint8_t *mg_put_u32_p(uint8_t *p, uint32_t v) {
@@ -417,7 +430,7 @@ template <class W, class NP>
 MG_HD void mg_fmt_qname(W &w, const uint8_t *prefix, int prefix_len, uint64_t cnt, bool with_cnt,
                         const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
   mg_put_bytes(w, prefix, prefix_len);
-  if (with_cnt) mg_put_uint(w, cnt);
+  if (with_cnt) { if (cnt <= 0xFFFFFFFFull) mg_put_u32(w, (uint32_t)cnt); else mg_put_uint(w, cnt); }
   mg_put_bytes(w, mid, mid_len);
   MG_NOUNROLL
   for (int r = 0; r < 2; r++) {

@@ -4,13 +4,22 @@
 #include <stdint.h>
 #include "mg_core.cuh"
 
-#define MG_TILE 32           // candidates per emit tile: one warp owns one tile
-#define MG_CTA 128           // threads per CTA of the emit kernel (4 independent warps)
+#define MG_PLAN_TILE 256     // candidates per CTA tile of k_unit_plan
+#define MG_CTA 128           // threads per CTA of k_unit_emit (4 independent warps, 32 kept templates each)
 #define MG_TLEN_K 1024       // entries of the template-length alias table (outcomes 0..n_tlen)
 #define MG_QN_MAX 192        // max length of the qname prefix / mid strings
 #define MG_HAP_PAD 8         // 32-bit words of padding on both sides of a packed sequence
 
 enum { MG_MODE_PHILOX = 0, MG_MODE_DET = 1, MG_MODE_EXPLICIT = 2 };
+
+// One kept template as planned by k_unit_plan, stored at its final rank (serial - 1).
+struct alignas(16) MgPlan {
+  uint32_t xa, xb;     // read starts relative to p_min (mate 0 forward, mate 1 reverse)
+  int32_t n0a, n0b;    // first node of each read
+  uint32_t dn;         // (n1 - n0) of mate 0 | mate 1 << 16
+  uint32_t fo_sz;      // file-order bit << 31 | record bytes (with the serial's digits)
+  uint64_t off;        // byte offset of the record in each file
+};
 
 struct MgUnitParams {
   // haplotype of one chromosome copy, resident in HBM
@@ -35,7 +44,7 @@ struct MgUnitParams {
   const uint8_t *prefix; int prefix_len; const uint8_t *mid; int mid_len;
   // outputs
   uint8_t *out[2]; uint64_t cap;
-  uint64_t *rec_off;         // optional: byte offset of every record (+ total at [n])
+  MgPlan *plan;              // [n_cand] written by k_unit_plan, read by k_unit_emit
   // fused corruption (PHILOX draws, alias tables)
   int corrupt; MgCorruptCtx cor;
   int L_nd;                  // decimal digits of rlen
@@ -71,6 +80,7 @@ void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_
 void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
                         cudaStream_t st);
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes);
+void mg_launch_plan(const MgUnitParams &P, cudaStream_t st);
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st);
 void mg_launch_sample(const MgSampleParams &P, cudaStream_t st);
 void mg_launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st);  // exclusive, out[n] = total

@@ -359,38 +359,31 @@ __device__ Agg tile_lookback(const MgUnitParams &P, int tile, int lane) {
   return ex;
 }
 
-// One WARP owns one tile of 32 candidates end to end: sampling, filters, sizing, warp scan,
-// look-back, formatting into its own shared-memory stage, coalesced copy-out.  Warps never wait
-// for each other (no block barrier inside the loop), so they drift apart and hide each other's
-// latencies; tiles are claimed from an atomic counter, which also keeps the look-back deadlock-free.
-template <int MAXW, bool CORRUPT>
-__global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint32_t *s_tlen = reinterpret_cast<uint32_t *>(smem);
-  __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
+// ---- k_unit_plan ---------------------------------------------------------------------------
+// Phase 1 of a unit: one candidate per thread (sampling, te < p_max, N filter, node lookup, record
+// size), block scan, decoupled look-back, and one 32-byte MgPlan per KEPT template at its final
+// rank.  Small per-thread state, no staging memory: runs at high occupancy, which hides the
+// dependent L2 loads of the node / template-start gathers.
+#define PLAN_THREADS 256
 
+__global__ void __launch_bounds__(PLAN_THREADS) k_unit_plan(const __grid_constant__ MgUnitParams P) {
+  __shared__ uint32_t s_tlen[MG_TLEN_K];
+  __shared__ uint32_t s_wc[PLAN_THREADS / 32], s_ws[PLAN_THREADS / 32];
+  __shared__ unsigned long long s_base[3];
+  __shared__ uint32_t s_tile;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  uint8_t *stage = smem + MG_TLEN_K * sizeof(uint32_t) + (size_t)wid * (P.stage_cap + 16);
   const int L = P.rlen;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   if (P.mode == MG_MODE_PHILOX && P.tlen_alias) {
 #pragma unroll 1
-    for (int i = t; i < MG_TLEN_K; i += MG_CTA) s_tlen[i] = P.tlen_alias[i];
+    for (int i = t; i < MG_TLEN_K; i += PLAN_THREADS) s_tlen[i] = P.tlen_alias[i];
   }
-#pragma unroll 1
-  for (int i = t; i < P.prefix_len; i += MG_CTA) s_prefix[i] = P.prefix[i];
-#pragma unroll 1
-  for (int i = t; i < P.mid_len; i += MG_CTA) s_mid[i] = P.mid[i];
-  __syncthreads();
-
   while (true) {
-    uint32_t tile_u = 0;
-    if (lane == 0) tile_u = atomicAdd(P.tile_counter, 1u);
-    const int tile = (int)__shfl_sync(FULL, tile_u, 0);
+    __syncthreads();
+    if (t == 0) s_tile = atomicAdd(P.tile_counter, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
     if (tile >= P.n_tiles) break;
-
-    // ---- phase 1: one candidate per lane ----------------------------------------------------
-    const uint32_t j = (uint32_t)tile * MG_TILE + lane;
+    const uint32_t j = (uint32_t)tile * PLAN_THREADS + t;
     bool k1 = false, k2 = false;
     uint32_t xa = 0, xb = 0, fo = 0, sz = 0;
     int n0a = 0, n1a = 0, n0b = 0, n1b = 0;
@@ -411,98 +404,145 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
         }
       }
     }
-    const uint32_t m1 = __ballot_sync(FULL, k1), m2 = __ballot_sync(FULL, k2);
-    const uint32_t tile_c1 = __popc(m1), tile_c2 = __popc(m2);
-    const uint32_t isz = warp_incl_scan_u32(sz, lane);
-    const uint32_t tile_sz = __shfl_sync(FULL, isz, 31);
-    const uint32_t rank1 = __popc(m1 & lt_mask);          // among te<p_max survivors (file-order draw index)
-
-    // ---- grid-wide placement: decoupled look-back over tile descriptors ----------------------
-    Agg ex = {0, 0, 0};
-    if (tile > 0) {
+    // block scan of (k1 | k2 << 16, sz)
+    const uint32_t cpk = (k1 ? 1u : 0u) | (k2 ? 0x10000u : 0u);
+    const uint32_t ic = warp_incl_scan_u32(cpk, lane), is = warp_incl_scan_u32(sz, lane);
+    if (lane == 31) { s_wc[wid] = ic; s_ws[wid] = is; }
+    __syncthreads();
+    uint32_t oc = 0, os = 0, tc = 0, ts_ = 0;
+#pragma unroll
+    for (int w = 0; w < PLAN_THREADS / 32; w++) {
+      if (w < wid) { oc += s_wc[w]; os += s_ws[w]; }
+      tc += s_wc[w]; ts_ += s_ws[w];
+    }
+    const uint32_t ec = oc + ic - cpk, es = os + is - sz;   // exclusive
+    const uint32_t tile_c1 = tc & 0xFFFFu, tile_c2 = tc >> 16, tile_sz = ts_;
+    if (wid == 0) {
+      Agg ex = {0, 0, 0};
+      if (tile > 0) {
+        if (lane == 0) {
+          st_vol64(P.descA + tile, (1ull << 62) | ((unsigned long long)tile_c1 << 31) | tile_c2);
+          st_vol64(P.descB + tile, (1ull << 62) | tile_sz);
+        }
+        ex = tile_lookback(P, tile, lane);
+      }
       if (lane == 0) {
-        st_vol64(P.descA + tile, (1ull << 62) | ((unsigned long long)tile_c1 << 31) | tile_c2);
-        st_vol64(P.descB + tile, (1ull << 62) | tile_sz);
-      }
-      ex = tile_lookback(P, tile, lane);
-    }
-    if (lane == 0) {
-      const unsigned long long i1 = ex.c1 + tile_c1, i2 = ex.c2 + tile_c2, ib = ex.by + tile_sz;
-      st_vol64(P.descA + tile, (2ull << 62) | (i1 << 31) | i2);
-      st_vol64(P.descB + tile, (2ull << 62) | ib);
-      if (tile == P.n_tiles - 1) {
-        P.totals[0] = i1; P.totals[1] = i2; P.totals[2] = ib + mg_digit_sum(i2);
-        if (P.rec_off) P.rec_off[i2] = ib + mg_digit_sum(i2);
+        const unsigned long long i1 = ex.c1 + tile_c1, i2 = ex.c2 + tile_c2, ib = ex.by + tile_sz;
+        st_vol64(P.descA + tile, (2ull << 62) | (i1 << 31) | i2);
+        st_vol64(P.descB + tile, (2ull << 62) | ib);
+        s_base[0] = ex.c1; s_base[1] = ex.c2; s_base[2] = ex.by;
+        if (tile == P.n_tiles - 1) { P.totals[0] = i1; P.totals[1] = i2; P.totals[2] = ib + mg_digit_sum(i2); }
       }
     }
-    const unsigned long long base1 = ex.c1, base2 = ex.c2;
-    const unsigned long long dsum0 = mg_digit_sum(base2);
-    const unsigned long long goff = ex.by + dsum0;                              // byte offset of the tile in each file
-    const uint32_t nk = tile_c2;
-    const uint32_t tile_bytes = tile_sz + (uint32_t)(mg_digit_sum(base2 + nk) - dsum0);
-    const bool overflow = goff + tile_bytes > P.cap;
-    if (overflow && lane == 0) atomicExch(&P.totals[3], 1ull);
-    const uint32_t pad = (uint32_t)(goff & 15);
-    const bool staged = (pad + tile_bytes) <= (uint32_t)P.stage_cap;
+    __syncthreads();
+    if (k2) {
+      const unsigned long long base1 = s_base[0], base2 = s_base[1];
+      const unsigned long long rank = base2 + (ec >> 16);                        // cnt - 1, readgenerate.py:209
+      // the serial's digits change the record size: offset = scanned bytes + sum of digits of 1..rank
+      const unsigned long long off = s_base[2] + es + mg_digit_sum(rank);
+      const uint32_t my_fo = (P.mode == MG_MODE_PHILOX) ? fo : (uint32_t)(P.fo_in[base1 + (ec & 0xFFFFu)] & 1);   // illumina.py:93
+      MgPlan pl;
+      pl.xa = xa; pl.xb = xb; pl.n0a = n0a; pl.n0b = n0b;
+      pl.dn = (uint32_t)(n1a - n0a) | ((uint32_t)(n1b - n0b) << 16);
+      pl.fo_sz = (my_fo << 31) | (sz + (uint32_t)mg_ndigits32((uint32_t)(rank + 1)));
+      pl.off = off;
+      P.plan[rank] = pl;
+    }
+  }
+}
 
-    // ---- compaction: lane k takes the k-th kept template (register shuffles, no shared memory) -
-    const int src = (int)__fns(m2, 0, lane + 1) & 31;
+void mg_launch_plan(const MgUnitParams &P, cudaStream_t st) {
+  if (P.n_tiles == 0) return;
+  int grid = P.n_tiles < 148 * 8 ? P.n_tiles : 148 * 8;
+  k_unit_plan<<<grid, PLAN_THREADS, 0, st>>>(P);
+}
+
+// ---- k_unit_emit ---------------------------------------------------------------------------
+// Phase 2: one WARP owns 32 consecutive kept templates (every lane busy), formats their records
+// into its own shared-memory stage and copies the byte range out with coalesced 128-bit stores.
+// No block barrier and no scan: placement was decided by k_unit_plan.
+template <int MAXW, bool CORRUPT>
+__global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  uint8_t *stage = smem + (size_t)wid * (P.stage_cap + 16);
+  const int L = P.rlen;
+#pragma unroll 1
+  for (int i = t; i < P.prefix_len; i += MG_CTA) s_prefix[i] = P.prefix[i];
+#pragma unroll 1
+  for (int i = t; i < P.mid_len; i += MG_CTA) s_mid[i] = P.mid[i];
+  __syncthreads();
+  const unsigned long long n_kept = P.totals[1], n_bytes = P.totals[2];
+  if (n_bytes > P.cap) { if (t == 0 && blockIdx.x == 0) P.totals[3] = 1ull; return; }   // host regrows and relaunches
+  const unsigned long long n_wt = (n_kept + 31) / 32;
+  for (unsigned long long wt = (unsigned long long)blockIdx.x * (MG_CTA / 32) + wid; wt < n_wt; wt += (unsigned long long)gridDim.x * (MG_CTA / 32)) {
+    const unsigned long long rank = wt * 32 + lane;
+    const bool active = rank < n_kept;
+    MgPlan pl = P.plan[active ? rank : n_kept - 1];
+    const uint32_t rec = pl.fo_sz & 0x7FFFFFFFu, my_fo = pl.fo_sz >> 31;
+    const uint32_t qlen = rec - (2u * (uint32_t)L + 5u);
+    const unsigned long long cnt = rank + 1;
     MgReadRef ra, rb;
-    ra.x = __shfl_sync(FULL, xa, src); ra.n0 = __shfl_sync(FULL, n0a, src); ra.n1 = __shfl_sync(FULL, n1a, src); ra.strand = 0;
-    rb.x = __shfl_sync(FULL, xb, src); rb.n0 = __shfl_sync(FULL, n0b, src); rb.n1 = __shfl_sync(FULL, n1b, src); rb.strand = 1;
-    const uint32_t k_sz = __shfl_sync(FULL, sz, src), k_esz = __shfl_sync(FULL, isz - sz, src);
-    const uint32_t k_fo = __shfl_sync(FULL, fo, src), k_rank1 = __shfl_sync(FULL, rank1, src);
-    const bool active = (uint32_t)lane < nk;
-
-    // ---- phase 2: one kept template per lane --------------------------------------------------
-    uint32_t loff = 0, qlen = 0, my_fo = 0;
-    unsigned long long cnt = 0;
-    if (active) {
-      cnt = base2 + lane + 1;                                                   // readgenerate.py:209
-      loff = k_esz + (uint32_t)(mg_digit_sum(base2 + lane) - dsum0);
-      qlen = k_sz + (uint32_t)mg_ndigits(cnt) - (2u * (uint32_t)L + 5u);
-      my_fo = (P.mode == MG_MODE_PHILOX) ? k_fo : (uint32_t)(P.fo_in[base1 + k_rank1] & 1);   // illumina.py:93
-      if (P.rec_off && !overflow) P.rec_off[base2 + lane] = goff + loff;
-    }
-    if (!overflow) {
-      // reads[fo] = mate (readgenerate.py:207): file f holds mate 0 iff fo == f
-      const MgReadRef first = my_fo ? rb : ra, second = my_fo ? ra : rb;
+    ra.x = pl.xa; ra.n0 = pl.n0a; ra.n1 = pl.n0a + (int)(pl.dn & 0xFFFFu); ra.strand = 0;
+    rb.x = pl.xb; rb.n0 = pl.n0b; rb.n1 = pl.n0b + (int)(pl.dn >> 16); rb.strand = 1;
+    // reads[fo] = mate (readgenerate.py:207): file f holds mate 0 iff fo == f
+    const MgReadRef first = my_fo ? rb : ra, second = my_fo ? ra : rb;
+    const unsigned long long my_end = active ? pl.off + rec : 0ull;
+    // records are emitted in batches that fit the stage (normally the whole warp tile at once)
+    int lo = 0;
+    const int n_act = (int)((n_kept - wt * 32 < 32ull) ? (n_kept - wt * 32) : 32ull);
+    while (lo < n_act) {
+      const unsigned long long goff = __shfl_sync(FULL, pl.off, lo);            // byte offset of the batch in each file
+      const uint32_t pad = (uint32_t)(goff & 15);
+      const bool fits = active && lane >= lo && (my_end - goff + pad) <= (unsigned long long)P.stage_cap;
+      int hi = lo + __popc(__ballot_sync(FULL, fits));                           // fits is monotone in the lane index
+      if (hi == lo) hi = lo + 1;                                                 // a single oversize record: see below
+      const unsigned long long gend = __shfl_sync(FULL, my_end, hi - 1);
+      const uint32_t batch_bytes = (uint32_t)(gend - goff);
+      const bool oversize = (pad + batch_bytes) > (uint32_t)P.stage_cap;         // only a record larger than the stage
+      const bool mine = active && lane >= lo && lane < hi;
       MgSeqSrc<MAXW, const uint32_t *> S;
-      if (active) S.load(P.hap, first.x, L, first.strand);    // loads in flight while the qname is formatted
-      for (int f = 0; f < 2; f++) {
-        if (P.out[f] == nullptr) continue;
-        if (active) {
-          uint8_t *dst = staged ? (stage + pad + loff) : (P.out[f] + goff + loff);
-          // staged tiles keep the qname (and, for perfect reads, the quality line) of file 0 in
-          // place: the other file only rewrites its L sequence bytes
-          const bool full = (f == 0) || !staged || (P.out[0] == nullptr);
-          if (f == 1 && P.out[0] == nullptr) S.load(P.hap, second.x, L, second.strand);
-          if constexpr (CORRUPT) {
-            if (full) mg_emit_frame(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
-            mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, P.cor, (uint32_t)(cnt - 1), (uint32_t)f);
-          } else {
-            if (full) mg_emit_record(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
-            else mg_rewrite_seq(dst + qlen + 1, S, P.exc, P.n_exc);
+      // software pipeline with ONE load site: iteration f emits file f from the window loaded in
+      // iteration f-1 and then starts the loads of file f+1 (they overlap with the copy-out)
+      for (int f = -1; f < 2; f++) {
+        if (f >= 0 && P.out[f] == nullptr) continue;
+        if (mine) {
+          if (f >= 0) {
+            uint8_t *dst = oversize ? (P.out[f] + pl.off) : (stage + pad + (uint32_t)(pl.off - goff));
+            // the stage keeps the qname (and, for perfect reads, the quality line) of file 0 in
+            // place: the other file only rewrites its L sequence bytes
+            const bool full = (f == 0) || oversize || (P.out[0] == nullptr);
+            if constexpr (CORRUPT) {
+              if (full) mg_emit_frame(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
+              mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, P.cor, (uint32_t)rank, (uint32_t)f);
+            } else {
+              if (full) mg_emit_record(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
+              else mg_rewrite_seq(dst + qlen + 1, S, P.exc, P.n_exc);
+            }
           }
-          if (f == 0) S.load(P.hap, second.x, L, second.strand);          // overlaps with the copy-out below
+          if (f < 1) {
+            const MgReadRef nxt = (f < 0 && P.out[0] != nullptr) ? first : second;
+            S.load(P.hap, nxt.x, L, nxt.strand);
+          }
         }
-        if (staged) {
-          __syncwarp();
-          // coalesced copy-out: smem and global share the same 16-byte phase (pad)
-          uint8_t *gdst = P.out[f] + goff;
-          const uint8_t *ssrc = stage + pad;
-          uint32_t head = (16u - pad) & 15u;
-          if (head > tile_bytes) head = tile_bytes;
-          if ((uint32_t)lane < head) gdst[lane] = ssrc[lane];
-          const uint32_t nvec = (tile_bytes - head) >> 4;
-          const uint4 *sv = reinterpret_cast<const uint4 *>(ssrc + head);
-          uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
-          for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
-          const uint32_t done = head + (nvec << 4);
-          if (done + lane < tile_bytes) gdst[done + lane] = ssrc[done + lane];
-          __syncwarp();
-        }
+        if (f < 0 || oversize) continue;
+        __syncwarp();
+        // coalesced copy-out: smem and global share the same 16-byte phase (pad)
+        uint8_t *gdst = P.out[f] + goff;
+        const uint8_t *ssrc = stage + pad;
+        uint32_t head = (16u - pad) & 15u;
+        if (head > batch_bytes) head = batch_bytes;
+        if ((uint32_t)lane < head) gdst[lane] = ssrc[lane];
+        const uint32_t nvec = (batch_bytes - head) >> 4;
+        const uint4 *sv = reinterpret_cast<const uint4 *>(ssrc + head);
+        uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
+        for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
+        const uint32_t done = head + (nvec << 4);
+        if (done + lane < batch_bytes) gdst[done + lane] = ssrc[done + lane];
+        __syncwarp();
       }
+      lo = hi;
     }
   }
 }
@@ -517,7 +557,7 @@ static unit_kernel_t unit_kernel(int L, int corrupt) {
 }
 
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
-  int smem = MG_TLEN_K * (int)sizeof(uint32_t) + (MG_CTA / 32) * (stage_cap + 16);
+  int smem = (MG_CTA / 32) * (stage_cap + 16);
   *smem_bytes = smem;
   unit_kernel_t k = unit_kernel(L, corrupt);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -531,8 +571,6 @@ int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
 
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st) {
   if (P.n_tiles == 0) return;
-  const int need = (P.n_tiles + MG_CTA / 32 - 1) / (MG_CTA / 32);
-  if (grid > need) grid = need;
   unit_kernel(P.rlen, P.corrupt)<<<grid, MG_CTA, smem_bytes, st>>>(P);
 }
 

@@ -200,9 +200,9 @@ class Engine(object):
     self._L.mg_prof_reset(self._h)
 
   def prof(self):
-    ms, n, b, tl = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
-    self._L.mg_prof_get(self._h, C.byref(ms), C.byref(n), C.byref(b), C.byref(tl))
-    return {'emit_ms': ms.value, 'emit_launches': n.value, 'emit_bytes': b.value, 'total_launches': tl.value}
+    ms, n, b, tl, pms = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
+    self._L.mg_prof_get(self._h, C.byref(ms), C.byref(n), C.byref(b), C.byref(tl), C.byref(pms))
+    return {'emit_ms': ms.value, 'emit_launches': n.value, 'emit_bytes': b.value, 'total_launches': tl.value, 'plan_ms': pms.value}
 
 
 _default = None

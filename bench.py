@@ -313,15 +313,24 @@ def main():
     # emit launches (events recorded around each launch on the launch stream inside the library).
     alg = nbytes + pairs * 2 * ((L + 3) // 4)
     ach = alg / (prof['emit_ms'] * 1e-3) / 1e9 if prof['emit_ms'] > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')   # dram bytes per launch of k_unit_emit from the committed ncu --set full capture
+    if os.path.exists(tp):
+      try:
+        traffic = json.load(open(tp)).get('corrupt' if corrupt else 'perfect', {}).get(str(args.contig_len))
+      except Exception:
+        traffic = None
     line = {'metric': 'read pairs/sec (2x150, FASTQ-formatted, corrupted)' if corrupt else 'read pairs/sec (2x150, FASTQ-formatted, perfect reads)',
             'value': pairs_all / (ms * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
             'data': 'synthetic', 'config': config_dict(args), 'clocks': clk,
             'gpu_launches': prof['total_launches'],
             'roofline': {'bound': 'hbm', 'kernel': 'k_unit_emit', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                         'traffic': None, 'peak_source': peak_src, 'launches': prof['emit_launches'],
+                         'traffic': traffic, 'peak_source': peak_src, 'launches': prof['emit_launches'],
                          'avg_launch_ms': prof['emit_ms'] / max(1, prof['emit_launches']),
-                         'algorithmic_bytes_per_pair': alg / max(1, pairs)}}
+                         'algorithmic_bytes_per_launch': alg / max(1, prof['emit_launches']),
+                         'algorithmic_bytes_per_pair': alg / max(1, pairs),
+                         'other_kernels': {'k_unit_plan_avg_ms': prof['plan_ms'] / max(1, prof['emit_launches'])}}}
     if e2e:
       line['e2e'] = {'value': e_pairs_all / e_wall_max, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(e2e[2]), 'd2h_bytes_per_step': int(e2e[3]),
                      'sink': 'pinned host memory'}

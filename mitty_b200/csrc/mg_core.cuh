@@ -136,11 +136,10 @@ MG_HD void mg_mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
   hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
 }
 
-MG_HD MgPhilox mg_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int r = 0; r < 10; r++) {
+template <int ROUNDS>
+MG_HD MgPhilox mg_philox_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  MG_UNROLL
+  for (int r = 0; r < ROUNDS; r++) {
     uint32_t h0, l0, h1, l1;
     mg_mulhilo(0xD2511F53u, c0, h0, l0);
     mg_mulhilo(0xCD9E8D57u, c2, h1, l1);
@@ -150,6 +149,18 @@ MG_HD MgPhilox mg_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
   }
   MgPhilox o; o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
   return o;
+}
+
+// Philox4x32-10: template sampling (gaps, template length, file order)
+MG_HD MgPhilox mg_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  return mg_philox_r<10>(c0, c1, c2, c3, k0, k1);
+}
+
+// Philox4x32-7 (the fewest rounds Salmon et al. report as passing BigCrush): the per-base
+// corruption stream, where the generator is ~60 % of the instruction count
+#define MG_CORRUPT_ROUNDS 7
+MG_HD MgPhilox mg_philox_corrupt(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
+  return mg_philox_r<MG_CORRUPT_ROUNDS>(c0, c1, c2, 0x636f7272u /* MG_STREAM_CORRUPT */, k0, k1);
 }
 
 // 53-bit uniform in [0,1) from two words, the same construction numpy's random_sample uses
@@ -703,7 +714,7 @@ MG_HD void mg_emit_frame(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int
 //
 // Draw layout (the specification tests/philox_ref.py restates in numpy): for template serial s
 // (0-based count within the unit), file f and cycle pair q = n / 2,
-//     r = Philox4x32-10(counter = (s, f, q, MG_STREAM_CORRUPT), key = (k0, k1))
+//     r = Philox4x32-7(counter = (s, f, q, MG_STREAM_CORRUPT), key = (k0, k1))
 // cycle 2q uses (r[0], r[1]), cycle 2q+1 uses (r[2], r[3]) as (w_bq, w_call):
 //     idx = w_bq >> (32 - kshift); frac = (w_bq << kshift) >> 8        (24 bits)
 //     e = alias[(f * n_cycles + n) << kshift | idx]; bq = frac < (e >> 7) ? idx : (e & 127)
@@ -720,14 +731,18 @@ struct MgCorruptCtx {
 };
 
 // -> bit 2 = substitution happened, bits 0-1 = which of the three alternatives; qual = ASCII quality
-MG_HD uint32_t mg_corrupt_draw(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &qual) {
+MG_HD uint32_t mg_corrupt_finish(const MgCorruptCtx &C, uint32_t w_bq, uint32_t e, uint32_t w_call, uint32_t &qual) {
   const uint32_t idx = w_bq >> (32 - C.kshift);
   const uint32_t frac = (w_bq << C.kshift) >> 8;
-  const uint32_t e = C.alias[(((size_t)f * C.n_cycles + (size_t)n) << C.kshift) | idx];
   const uint32_t bq = frac < (e >> 7) ? idx : (e & 127u);
   const MgErr t = C.err[bq];
   qual = bq + 33u;
   return w_call < t.thr ? (4u | ((uint32_t)(w_call >= t.t1) + (uint32_t)(w_call >= t.t2))) : 0u;
+}
+
+MG_HD uint32_t mg_corrupt_draw(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &qual) {
+  const uint32_t e = C.alias[((f * (uint32_t)C.n_cycles + (uint32_t)n) << C.kshift) | (w_bq >> (32 - C.kshift))];
+  return mg_corrupt_finish(C, w_bq, e, w_call, qual);
 }
 
 MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &base, uint32_t &qual) {
@@ -738,27 +753,33 @@ MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_b
 // base_rot on 2-bit codes (A=0 C=1 G=2 T=3): A->CTG, C->ATG, G->ACT, T->ACG as 2-bit triples
 #define MG_ROT_TBL (45u | (44u << 6) | (52u << 12) | (36u << 18))
 
-// four bases (chunk word q, first base index n0) corrupted on the 2-bit codes -> ASCII bases + qualities
+// four bases (chunk word q, first base index n0) corrupted on the 2-bit codes -> new codes + ASCII
+// qualities.  Both Philox blocks are generated first and the four alias loads are issued
+// together, so their (L2) latencies overlap; cycles >= L read a valid row and are masked out.
 MG_HD void mg_corrupt4(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, uint32_t &b4, uint32_t &qw) {
+  const MgPhilox r0 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1), C.k0, C.k1);
+  const MgPhilox r1 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1) + 1u, C.k0, C.k1);
+  const uint32_t wb[4] = {r0.v[0], r0.v[2], r1.v[0], r1.v[2]};
+  const uint32_t wc[4] = {r0.v[1], r0.v[3], r1.v[1], r1.v[3]};
+  const uint32_t *row = C.alias + ((f * (uint32_t)C.n_cycles + (uint32_t)n0) << C.kshift);
+  uint32_t e[4];
+  MG_UNROLL
+  for (int j = 0; j < 4; j++) {
+    const uint32_t nj = (n0 + j < L) ? (uint32_t)j : 0u;                    // stay inside the table at the read's end
+    e[j] = row[(nj << C.kshift) | (wb[j] >> (32 - C.kshift))];
+  }
   qw = 0;
-  MG_NOUNROLL
-  for (int h = 0; h < 2; h++) {
-    if (n0 + 2 * h < L) {
-      const MgPhilox r = mg_philox(serial, f, (uint32_t)((n0 >> 1) + h), MG_STREAM_CORRUPT, C.k0, C.k1);
-      MG_UNROLL
-      for (int e = 0; e < 2; e++) {
-        const int j = 2 * h + e, n = n0 + j;
-        if (n < L) {
-          uint32_t qual;
-          const uint32_t d = mg_corrupt_draw(C, f, n, e ? r.v[2] : r.v[0], e ? r.v[3] : r.v[1], qual);
-          if (d) {
-            const uint32_t code = (b4 >> (2 * j)) & 3u;
-            const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * (d & 3u))) & 3u;
-            b4 ^= (code ^ nc) << (2 * j);
-          }
-          qw |= qual << (8 * j);
-        }
+  MG_UNROLL
+  for (int j = 0; j < 4; j++) {
+    uint32_t qual;
+    const uint32_t d = mg_corrupt_finish(C, wb[j], e[j], wc[j], qual);
+    if (n0 + j < L) {
+      if (d) {
+        const uint32_t code = (b4 >> (2 * j)) & 3u;
+        const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * (d & 3u))) & 3u;
+        b4 ^= (code ^ nc) << (2 * j);
       }
+      qw |= qual << (8 * j);
     }
   }
 }
@@ -796,7 +817,7 @@ MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgSeqSrc<MAX
       uint64_t b = (uint64_t)e.start + e.len < (uint64_t)mine.x + L ? (uint64_t)e.start + e.len : (uint64_t)mine.x + L;
       for (uint64_t i = a; i < b; i++) {
         const int idx = (int)(i - mine.x), n = mine.strand ? (L - 1 - idx) : idx;
-        const MgPhilox r = mg_philox(serial, f, (uint32_t)(n >> 1), MG_STREAM_CORRUPT, C.k0, C.k1);
+        const MgPhilox r = mg_philox_corrupt(serial, f, (uint32_t)(n >> 1), C.k0, C.k1);
         uint32_t base = e.byte, qual;
         mg_corrupt_one(C, f, n, (n & 1) ? r.v[2] : r.v[0], (n & 1) ? r.v[3] : r.v[1], base, qual);
         seq_dst[n] = (uint8_t)base;

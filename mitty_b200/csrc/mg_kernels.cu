@@ -465,9 +465,12 @@ template <int MAXW, bool CORRUPT>
 __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
+  __shared__ MgErr s_err[CORRUPT ? 128 : 1];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   uint8_t *stage = smem + (size_t)wid * (P.stage_cap + 16);
   const int L = P.rlen;
+  MgCorruptCtx cor = P.cor;
+  if constexpr (CORRUPT) { s_err[t & 127] = P.cor.err[t & 127]; cor.err = s_err; }   // error thresholds: 2 KB, shared memory
 #pragma unroll 1
   for (int i = t; i < P.prefix_len; i += MG_CTA) s_prefix[i] = P.prefix[i];
 #pragma unroll 1
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
             const bool full = (f == 0) || oversize || (P.out[0] == nullptr);
             if constexpr (CORRUPT) {
               if (full) mg_emit_frame(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
-              mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, P.cor, (uint32_t)rank, (uint32_t)f);
+              mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)rank, (uint32_t)f);
             } else {
               if (full) mg_emit_record(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
               else mg_rewrite_seq(dst + qlen + 1, S, P.exc, P.n_exc);
@@ -739,7 +742,7 @@ __global__ void __launch_bounds__(256) k_corrupt(MgCorruptParams P) {
         }
       } else {
         for (int pr = lane; 2 * pr < L; pr += 32) {
-          const MgPhilox rr = mg_philox((uint32_t)r, (uint32_t)(r >> 32) * 2u + (uint32_t)f, (uint32_t)pr, MG_STREAM_CORRUPT, P.cor.k0, P.cor.k1);
+          const MgPhilox rr = mg_philox_corrupt((uint32_t)r, (uint32_t)(r >> 32) * 2u + (uint32_t)f, (uint32_t)pr, P.cor.k0, P.cor.k1);
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             const int n = 2 * pr + h;

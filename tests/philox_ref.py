@@ -1,5 +1,5 @@
 """Numpy restatement of the engine's PRODUCTION-mode corruption (the draw layout documented at
-MgCorruptCtx in mitty_b200/csrc/mg_core.cuh): Philox4x32-10 counters, Vose alias rows, integer
+MgCorruptCtx in mitty_b200/csrc/mg_core.cuh): Philox4x32 counters, Vose alias rows, integer
 error thresholds.  Test infrastructure: lets the fused GPU path be checked byte for byte, not only
 statistically."""
 import numpy as np
@@ -7,13 +7,18 @@ import numpy as np
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = 0x9E3779B9, 0xBB67AE85
 STREAM_CORRUPT = 0x636f7272
+CORRUPT_ROUNDS = 7   # MG_CORRUPT_ROUNDS: the per-base corruption stream is Philox4x32-7
 MASK = np.uint64(0xFFFFFFFF)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
+  return philox4x32(c0, c1, c2, c3, k0, k1, 10)
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=10):
   c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
   k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
-  for _ in range(10):
+  for _ in range(rounds):
     p0, p1 = M0 * c0, M1 * c2
     h0, l0, h1, l1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
     c0, c1, c2, c3 = h1 ^ c1 ^ np.uint64(k0), l1, h0 ^ c3 ^ np.uint64(k1), l0
@@ -109,7 +114,7 @@ def corrupt_file(fq, f, alias, kshift, err, k0, k1, serials=None):
   nq = (L + 1) // 2
   s_grid = np.repeat(np.asarray(serials, dtype=np.uint64), nq)
   q_grid = np.tile(np.arange(nq, dtype=np.uint64), n_rec)
-  r = philox4x32_10(s_grid & MASK, (s_grid >> np.uint64(32)) * np.uint64(2) + np.uint64(f), q_grid, STREAM_CORRUPT, k0, k1)
+  r = philox4x32(s_grid & MASK, (s_grid >> np.uint64(32)) * np.uint64(2) + np.uint64(f), q_grid, STREAM_CORRUPT, k0, k1, CORRUPT_ROUNDS)
   w = np.stack(r, axis=1).reshape(n_rec, nq, 4)
   for rec in range(n_rec):
     seq = bytearray(lines[4 * rec + 1])

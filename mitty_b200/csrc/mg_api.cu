@@ -6,6 +6,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -40,12 +42,11 @@ struct Region {
   ~Region() { if (d_ref) cudaFree(d_ref); }
 };
 
-struct HostNode { int64_t ps, pr, oplen; uint8_t op; };
 
 struct Copy {
   int64_t region_id = 0;
   int64_t p_min = 0, p_max = 0;
-  std::vector<HostNode> nodes;
+  int64_t n_nodes = 0;
   std::vector<MgExc> exc;
   MgNode *d_nodes = nullptr; uint32_t *d_hap = nullptr; uint32_t *d_blk = nullptr; MgExc *d_exc = nullptr;
   int n_blk = 0; int64_t hap_words = 0;
@@ -68,6 +69,7 @@ struct mg_ctx {
   int n_tlen = 0, n_mates = 0, n_cycles = 0, n_bq = 0, rlen = 0;
   int n64 = 0;   // leading cycles whose rows (all mates) put no mass on BQ >= 64: 64-entry alias rows are exact there
   std::vector<uint32_t> h_alias[2]; std::vector<MgErr> h_err;
+  std::vector<MgNode> h_dn; std::vector<uint32_t> h_seg_start; std::vector<uint64_t> h_seg_src;   // copy-build scratch
   std::vector<std::pair<void *, size_t>> pool;   // device blocks of freed copies, reused by the next build
   std::map<void *, size_t> block_size;
   // handles
@@ -136,6 +138,13 @@ std::vector<double> ss_left_probs(const double *cum, int n, int K, int clip) {
 void build_alias_row(const double *cum, int n_bq, int K, uint32_t *out) {
   vose(ss_left_probs(cum, n_bq, K, 93), K, 24, 7, out);
 }
+
+struct Timer {   // MG_TIMING=1: host-side section timings on stderr
+  const char *name; double t0; bool on;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit Timer(const char *n) : name(n), t0(now()), on(getenv("MG_TIMING") != nullptr) {}
+  void lap(const char *what) { if (on) { double t = now(); fprintf(stderr, "[mg] %s/%s %.2f ms\n", name, what, t - t0); t0 = t; } }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -354,16 +363,45 @@ int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *
   Region &R = *it->second;
   std::unique_ptr<Copy> C(new Copy());
   C->region_id = region_id;
+  Timer tm("copy_build");
 
-  // -- the greedy walk (rpc.py:48-61).  src: bit 63 set -> byte offset in the alt pool, else base
-  //    offset in the region's reference.
-  const int64_t start1 = R.bed_start + 1;            // ref_start_pos, readgenerate.py:190
+  // -- the greedy walk (rpc.py:48-61), one pass: device node table, haplotype segments (the
+  //    non-'D' nodes) and exception runs in sample space.  src: bit 63 set -> byte offset in the alt
+  //    pool, else base offset in the region's reference.  Scratch vectors live in the context.
+  const int64_t start1 = R.bed_start + 1;            // ref_start_pos, readgenerate.py:190; also p_min
   int64_t samp = start1, refp = start1;
-  std::vector<uint64_t> src;                          // per node
-  auto push = [&](int64_t ps, int64_t pr, uint8_t o, int64_t ol, uint64_t s) {
-    C->nodes.push_back(HostNode{ps, pr, ol, o}); src.push_back(s);
-  };
+  std::vector<MgNode> &dn = ctx->h_dn;
+  std::vector<uint32_t> &seg_start = ctx->h_seg_start;
+  std::vector<uint64_t> &seg_src = ctx->h_seg_src;
+  dn.clear(); seg_start.clear(); seg_src.clear();
+  dn.reserve(2 * (size_t)n_var + 2); seg_start.reserve(2 * (size_t)n_var + 2); seg_src.reserve(2 * (size_t)n_var + 2);
   const uint64_t ALT = 1ull << 63;
+  size_t rx = 0;                                      // cursor into the region's exception runs
+  bool bad = false;
+  auto add_exc = [&](int64_t s, int64_t l, uint8_t b) {
+    if (!C->exc.empty()) { MgExc &e = C->exc.back(); if ((int64_t)e.start + e.len == s && e.byte == b) { e.len += (uint32_t)l; return; } }
+    C->exc.push_back(MgExc{(uint32_t)s, (uint32_t)l, b, 0});
+  };
+  auto push = [&](int64_t ps, int64_t pr, uint8_t o, int64_t ol, uint64_t sr) {
+    const int64_t rel = ps - start1;
+    if (ol > INT32_MAX || pr >= (1ll << 31) || rel >= (int64_t)0xFFF00000ll) { bad = true; return; }
+    dn.push_back(MgNode{(uint32_t)(rel + (o == 'D' ? 1 : 0)), (int32_t)pr, (int32_t)ol, o});   // key: rpc.py:127
+    if (o == 'D' || ol == 0) return;
+    seg_start.push_back((uint32_t)rel); seg_src.push_back(sr);
+    if (o == '=') {
+      const int64_t a = (int64_t)sr, b = a + ol;
+      if (b > R.len) { bad = true; return; }
+      while (rx < R.exc.size() && R.exc[rx].start + R.exc[rx].len <= a) rx++;
+      for (size_t q = rx; q < R.exc.size() && R.exc[q].start < b; q++) {
+        int64_t s0 = std::max(a, R.exc[q].start), e0 = std::min(b, R.exc[q].start + R.exc[q].len);
+        if (e0 > s0) add_exc(rel + (s0 - a), e0 - s0, R.exc[q].byte);
+      }
+    } else {
+      const uint8_t *alt = alt_pool + (sr & ~ALT);
+      for (int64_t q = 0; q < ol; q++)
+        if (mg_base_code(alt[q]) > 3) add_exc(rel + q, 1, alt[q]);
+    }
+  };
   for (int64_t i = 0; i < n_var; i++) {
     const int64_t vp = pos[i];
     if (vp < refp) continue;                          // rpc.py:55
@@ -391,50 +429,17 @@ int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *
   }
   const int64_t offset = refp - start1;               // rpc.py:58-61
   if (offset <= R.len) push(samp, refp, '=', R.len - offset, (uint64_t)offset);
-  if (C->nodes.empty() || C->nodes.back().op == 'D')
+  if (dn.empty() || dn.back().op == 'D')
     return fail(ctx, MG_EVALUE, "a deletion crosses the end of the region: the reference's node list would end in 'D' "
                 "(readgenerate.py:192 assumes it never does); trim the BED region or the VCF");
-  for (size_t k = 0; k < C->nodes.size(); k++) {
-    const HostNode &nd = C->nodes[k];
-    if (nd.op == '=' && (int64_t)src[k] + nd.oplen > R.len)
-      return fail(ctx, MG_EVALUE, "variant beyond the end of the region at reference position %lld", (long long)nd.pr);
-  }
-  C->p_min = C->nodes.front().ps;                     // readgenerate.py:192
-  C->p_max = C->nodes.back().ps + C->nodes.back().oplen;
+  if (bad) return fail(ctx, MG_EVALUE, "a variant reaches beyond the region, or positions / node lengths exceed 2^31 (haplotypes 2^32)");
+  const size_t nn = dn.size();
+  C->n_nodes = (int64_t)nn;
+  C->p_min = start1;                                  // readgenerate.py:192: nodes[0].ps
+  C->p_max = start1 + ((int64_t)dn.back().key) + dn.back().oplen;   // nodes[-1].ps + nodes[-1].oplen (last node is not 'D')
   const int64_t hap_len = C->p_max - C->p_min;
   if (hap_len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "haplotype of %lld bases exceeds 2^32", (long long)hap_len);
-  if (C->nodes.back().pr + C->nodes.back().oplen >= (1ll << 31)) return fail(ctx, MG_EVALUE, "reference positions beyond 2^31 are not supported");
-
-  // -- device node table, segments for the haplotype kernel, exception runs in sample space
-  const size_t nn = C->nodes.size();
-  std::vector<MgNode> dn(nn);
-  std::vector<uint32_t> seg_start; std::vector<uint64_t> seg_src;
-  size_t rx = 0;                                      // cursor into the region's exception runs
-  auto add_exc = [&](int64_t s, int64_t l, uint8_t b) {
-    if (!C->exc.empty()) { MgExc &e = C->exc.back(); if ((int64_t)e.start + e.len == s && e.byte == b) { e.len += (uint32_t)l; return; } }
-    C->exc.push_back(MgExc{(uint32_t)s, (uint32_t)l, b, 0});
-  };
-  for (size_t k = 0; k < nn; k++) {
-    const HostNode &nd = C->nodes[k];
-    const int64_t rel = nd.ps - C->p_min;
-    dn[k].key = (uint32_t)(rel + (nd.op == 'D' ? 1 : 0));   // rpc.py:127
-    dn[k].pr = (int32_t)nd.pr; dn[k].oplen = (int32_t)nd.oplen; dn[k].op = nd.op;
-    if (nd.oplen > INT32_MAX) return fail(ctx, MG_EVALUE, "node longer than 2^31");
-    if (nd.op == 'D' || nd.oplen == 0) continue;
-    seg_start.push_back((uint32_t)rel); seg_src.push_back(src[k]);
-    if (nd.op == '=') {
-      const int64_t a = (int64_t)src[k], b = a + nd.oplen;
-      while (rx < R.exc.size() && R.exc[rx].start + R.exc[rx].len <= a) rx++;
-      for (size_t q = rx; q < R.exc.size() && R.exc[q].start < b; q++) {
-        int64_t s = std::max(a, R.exc[q].start), e = std::min(b, R.exc[q].start + R.exc[q].len);
-        if (e > s) add_exc(rel + (s - a), e - s, R.exc[q].byte);
-      }
-    } else {
-      const uint8_t *alt = alt_pool + (src[k] & ~ALT);
-      for (int64_t q = 0; q < nd.oplen; q++)
-        if (mg_base_code(alt[q]) > 3) add_exc(rel + q, 1, alt[q]);
-    }
-  }
+  tm.lap("walk");
 
   // -- upload + device builds
   const int64_t alt_bytes = n_var ? alt_off[n_var] : 0;
@@ -464,7 +469,9 @@ int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *
   mg_launch_blk_table(C->d_nodes, (int)nn, C->d_blk, C->n_blk, BLK_SHIFT, ctx->stream);
   ctx->total_launches++;
   CU(cudaGetLastError());
+  tm.lap("enqueue");
   CU(cudaStreamSynchronize(ctx->stream));   // host vectors above go out of scope
+  tm.lap("sync");
 
   int64_t id = ctx->next_id++;
   if (p_min) *p_min = C->p_min;
@@ -486,8 +493,15 @@ int mg_copy_nodes(mg_ctx *ctx, int64_t copy_id, int64_t *ps, int64_t *pr, uint8_
   if (!ctx) return MG_EINVAL;
   auto it = ctx->copies.find(copy_id);
   if (it == ctx->copies.end()) return fail(ctx, MG_EINVAL, "unknown copy %lld", (long long)copy_id);
+  DeviceGuard g(ctx->device);
   const Copy &C = *it->second;
-  for (size_t k = 0; k < C.nodes.size(); k++) { ps[k] = C.nodes[k].ps; pr[k] = C.nodes[k].pr; op[k] = C.nodes[k].op; oplen[k] = C.nodes[k].oplen; }
+  std::vector<MgNode> dn((size_t)C.n_nodes);
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(dn.data(), C.d_nodes, sizeof(MgNode) * dn.size(), cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < dn.size(); k++) {   // the device table back in the reference's terms (rpc.py:5-35)
+    ps[k] = C.p_min + (int64_t)dn[k].key - (dn[k].op == 'D' ? 1 : 0);
+    pr[k] = dn[k].pr; op[k] = (uint8_t)dn[k].op; oplen[k] = dn[k].oplen;
+  }
   return MG_OK;
 }
 
@@ -524,7 +538,7 @@ static int fill_unit_params(mg_ctx *ctx, const mg_unit_desc *d, MgUnitParams &P,
     const Copy &C = *it->second;
     *copy_out = &C;
     P.hap = C.d_hap + MG_HAP_PAD; P.hap_len = (uint32_t)(C.p_max - C.p_min); P.p_min = C.p_min;
-    P.nodes = C.d_nodes; P.n_nodes = (int)C.nodes.size();
+    P.nodes = C.d_nodes; P.n_nodes = (int)C.n_nodes;
     P.blk = C.d_blk; P.blk_shift = BLK_SHIFT; P.n_blk = C.n_blk;
     P.exc = C.d_exc; P.n_exc = (int)C.exc.size();
   }

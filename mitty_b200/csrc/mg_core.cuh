@@ -735,9 +735,10 @@ MG_HD uint32_t mg_corrupt_finish(const MgCorruptCtx &C, uint32_t w_bq, uint32_t 
   const uint32_t idx = w_bq >> (32 - C.kshift);
   const uint32_t frac = (w_bq << C.kshift) >> 8;
   const uint32_t bq = frac < (e >> 7) ? idx : (e & 127u);
-  const MgErr t = C.err[bq];
   qual = bq + 33u;
-  return w_call < t.thr ? (4u | ((uint32_t)(w_call >= t.t1) + (uint32_t)(w_call >= t.t2))) : 0u;
+  if (w_call >= C.err[bq].thr) return 0u;                     // the common case: one load, one compare
+  const MgErr t = C.err[bq];
+  return 4u | ((uint32_t)(w_call >= t.t1) + (uint32_t)(w_call >= t.t2));
 }
 
 MG_HD uint32_t mg_corrupt_draw(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &qual) {
@@ -756,6 +757,7 @@ MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_b
 // four bases (chunk word q, first base index n0) corrupted on the 2-bit codes -> new codes + ASCII
 // qualities.  Both Philox blocks are generated first and the four alias loads are issued
 // together, so their (L2) latencies overlap; cycles >= L read a valid row and are masked out.
+template <bool FULL>   // FULL: all four cycles are inside the read (n0 + 4 <= L), no per-base bounds logic
 MG_HD void mg_corrupt4(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, uint32_t &b4, uint32_t &qw) {
   const MgPhilox r0 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1), C.k0, C.k1);
   const MgPhilox r1 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1) + 1u, C.k0, C.k1);
@@ -765,7 +767,7 @@ MG_HD void mg_corrupt4(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n
   uint32_t e[4];
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
-    const uint32_t nj = (n0 + j < L) ? (uint32_t)j : 0u;                    // stay inside the table at the read's end
+    const uint32_t nj = (FULL || n0 + j < L) ? (uint32_t)j : 0u;            // stay inside the table at the read's end
     e[j] = row[(nj << C.kshift) | (wb[j] >> (32 - C.kshift))];
   }
   qw = 0;
@@ -773,7 +775,7 @@ MG_HD void mg_corrupt4(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n
   for (int j = 0; j < 4; j++) {
     uint32_t qual;
     const uint32_t d = mg_corrupt_finish(C, wb[j], e[j], wc[j], qual);
-    if (n0 + j < L) {
+    if (FULL || n0 + j < L) {
       if (d) {
         const uint32_t code = (b4 >> (2 * j)) & 3u;
         const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * (d & 3u))) & 3u;
@@ -799,10 +801,14 @@ MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgSeqSrc<MAX
       const int n0 = 16 * c + 4 * q;
       if (n0 < L) {
         uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw;
-        mg_corrupt4(C, serial, f, n0, L, b4, qw);
-        const uint32_t ch = mg_chars4(b4);
-        if (n0 + 4 <= L) { ws.put_word(ch); wq.put_word(qw); }
-        else for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
+        if (n0 + 4 <= L) {
+          mg_corrupt4<true>(C, serial, f, n0, L, b4, qw);
+          ws.put_word(mg_chars4(b4)); wq.put_word(qw);
+        } else {
+          mg_corrupt4<false>(C, serial, f, n0, L, b4, qw);
+          const uint32_t ch = mg_chars4(b4);
+          for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
+        }
       }
     }
   });

@@ -211,3 +211,62 @@ def test_philox_corruption_exact_vs_numpy_spec(eng):
   assert s1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, alias7, 7, err, cseed, 0x636f7232)
   assert s2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, alias7, 7, err, cseed, 0x636f7232)
   eng.free_copy(cp); eng.free_region(rid)
+
+
+def test_philox_full_size_properties(eng):
+  """BASELINE-scale unit (a 60 Mb contig with N runs, ~1.5 M templates, fused corruption), checked
+  through size-independent properties: run-to-run determinism, record structure, consecutive
+  serials, the N filter, and god-aligner round trips of a random sample of the PERFECT twin run
+  (same seeds, so the same templates)."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  from mitty_b200.engine import MODE_PHILOX
+  wl = synth.chr1_shaped(seed=3, length=60000000, n_runs=12)
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  rm = il.read_model_params(m, 30.0)
+  eng.load_model(rm)
+  r = H.workload_regions(wl)[0]
+  rid = eng.load_region(r['ref'], 0)
+  cp = eng.build_copy(rid, r['v'][0])
+  n = int((cp.p_max - cp.p_min) * rm['p'] * 1.2)
+  args = (cp, n, rm['p'], MODE_PHILOX, 4242, '@BIG:0:0:', '|1|0')
+  c1, c2, cnt, nk, nb = eng.generate_unit(*args, corrupt=True, corrupt_seed=9)
+  assert cnt > 1200000 and cnt < nk
+  sha = (H.sha256(c1.tobytes()), H.sha256(c2.tobytes()))
+  d1, d2, cnt2, _, _ = eng.generate_unit(*args, corrupt=True, corrupt_seed=9)
+  assert cnt2 == cnt and (H.sha256(d1.tobytes()), H.sha256(d2.tobytes())) == sha      # deterministic
+  p1, p2, cntp, _, _ = eng.generate_unit(*args)                                         # perfect twin
+  assert cntp == cnt and p1.size == c1.size
+  for a, b in ((c1, p1), (c2, p2)):
+    nl = np.flatnonzero(a == 10)
+    assert nl.size == 4 * cnt and np.array_equal(nl, np.flatnonzero(b == 10))            # same layout
+    starts = np.concatenate([[0], nl[3:-1:4] + 1])
+    assert (a[starts] == ord('@')).all() and (a[nl[1::4] + 1] == ord('+')).all()
+    assert ((nl[1::4] - nl[0::4] - 1) == 150).all() and ((nl[3::4] - nl[2::4] - 1) == 150).all()
+    # qname lines are identical in the corrupted and the perfect file; qualities are in range
+    k = np.random.RandomState(1).randint(0, cnt, size=2000)
+    for i in k[:200]:
+      assert a[starts[i]:nl[4 * i]].tobytes() == b[starts[i]:nl[4 * i]].tobytes()
+    q = np.concatenate([a[nl[4 * i + 2] + 1:nl[4 * i + 3]] for i in k])
+    assert q.min() >= 33 + 1 and q.max() <= 33 + 41
+  # serials are 1..cnt in file order
+  nl = np.flatnonzero(p1 == 10)
+  starts = np.concatenate([[0], nl[3:-1:4] + 1])
+  for i in (0, 1, 9, 10, 99999, 100000, cnt - 1):
+    assert p1[starts[i]:nl[4 * i]].tobytes().split(b'|')[0] == '@BIG:0:0:{}'.format(i + 1).encode()
+  # no read with more than two N; sampled round trips through the qname
+  idx = H.HaplotypeIndex(r['ref'], 1, H.oracle_cv(r['v'][0]))
+  rs = np.random.RandomState(2)
+  errs = []
+  for which, buf in ((0, p1), (1, p2)):
+    nlb = np.flatnonzero(buf == 10)
+    st = np.concatenate([[0], nlb[3:-1:4] + 1])
+    for i in rs.randint(0, cnt, size=4000):
+      qn = buf[st[i] + 1:nlb[4 * i]].tobytes().decode()
+      seq = buf[nlb[4 * i] + 1:nlb[4 * i + 1]].tobytes().decode()
+      assert seq.count('N') <= 2
+      e = idx.check(rg.parse_qname(qn)[which], seq)
+      if e:
+        errs.append((qn, e))
+  assert not errs, errs[:3]
+  eng.free_copy(cp); eng.free_region(rid)

@@ -34,10 +34,16 @@ typedef struct mg_ctx mg_ctx;
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* stream: a cudaStream_t to launch on (e.g. torch's current stream) or NULL for an own stream. */
+int mg_device_count(void);   /* number of CUDA devices (0 if none / no driver) */
 int mg_ctx_create(int device, void *stream, mg_ctx **out);
 void mg_ctx_destroy(mg_ctx *ctx);
 const char *mg_last_error(mg_ctx *ctx);
 int mg_synchronize(mg_ctx *ctx);
+
+/* page-locked host memory for the caller's FASTQ buffers (makes the D2H copies of
+ * mg_unit_generate / mg_corrupt_fastq run at full PCIe speed and asynchronously)                 */
+int mg_host_alloc(mg_ctx *ctx, int64_t bytes, void **out);
+int mg_host_free(mg_ctx *ctx, void *p);
 
 /* ---- read model: illumina.read_model_params hand-off (mitty/simulation/illumina.py:12-40) ---
  * cum_tlen f64[n_tlen]; cum_bq_mat f64[n_mates][n_cycles][n_bq]; phred_p f64[100] =

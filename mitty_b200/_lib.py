@@ -20,7 +20,7 @@ MG_OK, MG_ECUDA, MG_EINVAL, MG_ECAP, MG_EVALUE, MG_EINDEX = 0, -1, -2, -3, -4, -
 MODE_PHILOX, MODE_DET, MODE_EXPLICIT = 0, 1, 2
 
 # every symbol include/mitty_b200.h declares
-SYMBOLS = ['mg_ctx_create', 'mg_ctx_destroy', 'mg_last_error', 'mg_synchronize', 'mg_model_load', 'mg_model_tables',
+SYMBOLS = ['mg_device_count', 'mg_ctx_create', 'mg_ctx_destroy', 'mg_last_error', 'mg_synchronize', 'mg_host_alloc', 'mg_host_free', 'mg_model_load', 'mg_model_tables',
            'mg_region_load', 'mg_region_free', 'mg_copy_build', 'mg_copy_free', 'mg_copy_nodes',
            'mg_copy_haplotype', 'mg_sample_templates', 'mg_unit_generate', 'mg_corrupt_fastq',
            'mg_prof_reset', 'mg_prof_get']
@@ -67,6 +67,8 @@ def lib():
     L.mg_ctx_destroy.argtypes = [C.c_void_p]
     L.mg_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
     L.mg_synchronize.argtypes = [C.c_void_p]
+    L.mg_host_alloc.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    L.mg_host_free.argtypes = [C.c_void_p, C.c_void_p]
     L.mg_model_load.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.mg_model_tables.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_void_p]
     L.mg_region_load.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]

@@ -61,15 +61,16 @@ def print_qname(ctx, param, value):
 @click.option('--qname', is_flag=True, callback=print_qname, expose_value=False, is_eager=True, help='Print documentation for information encoded in qname')
 @click.option('--deterministic', is_flag=True, help="Consume the reference's numpy draws: byte-exact vs `mitty generate-reads --threads 1`")
 @click.option('--corrupt', is_flag=True, help='Fuse the Illumina corruption model into read generation (Philox draws)')
-@click.option('--device', default=0, help='CUDA device')
-def generate_reads(fasta, vcf, sample_name, bed, modelfile, coverage, seed, fastq1, fastq2, threads, deterministic, corrupt, device):
-  """Generate simulated reads"""
+@click.option('--devices', default=None, help='comma separated CUDA devices (default: the first --threads GPUs)')
+def generate_reads(fasta, vcf, sample_name, bed, modelfile, coverage, seed, fastq1, fastq2, threads, deterministic, corrupt, devices):
+  """Generate simulated reads (--threads = number of GPUs to use)"""
   import mitty_b200.simulation.readgenerate as reads
   read_module, model = get_read_model(modelfile)
   reads.process_multi_threaded(
     fasta, vcf, sample_name, bed, read_module, model, coverage,
     fastq1, fastq2, threads=threads, seed=seed,
-    mode='deterministic' if deterministic else 'philox', corrupt=corrupt, device=device)
+    mode='deterministic' if deterministic else 'philox', corrupt=corrupt,
+    devices=[int(x) for x in devices.split(',')] if devices else None)
 
 
 @cli.command('corrupt-reads', short_help='Apply corruption model to FASTQ file of reads')

@@ -185,6 +185,11 @@ Copy::~Copy() { pool_free(owner, d_nodes); pool_free(owner, d_hap); pool_free(ow
 
 extern "C" {
 
+int mg_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 int mg_ctx_create(int device, void *stream, mg_ctx **out) {
   if (!out) return MG_EINVAL;
   *out = nullptr;
@@ -225,6 +230,21 @@ int mg_synchronize(mg_ctx *ctx) {
   if (!ctx) return MG_EINVAL;
   DeviceGuard g(ctx->device);
   CU(cudaStreamSynchronize(ctx->stream));
+  return MG_OK;
+}
+
+int mg_host_alloc(mg_ctx *ctx, int64_t bytes, void **out) {
+  if (!ctx || !out || bytes <= 0) return fail(ctx, MG_EINVAL, "mg_host_alloc: bad arguments");
+  DeviceGuard g(ctx->device);
+  CU(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+  return MG_OK;
+}
+
+int mg_host_free(mg_ctx *ctx, void *p) {
+  if (!ctx) return MG_EINVAL;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaFreeHost(p));
   return MG_OK;
 }
 

@@ -37,9 +37,13 @@ class Engine(object):
     self.device = device
     self.rlen = None
     self._keep = []
+    self._pinned = []
 
   def close(self):
     if getattr(self, '_h', None):
+      for p in self._pinned:
+        self._L.mg_host_free(self._h, p)
+      self._pinned = []
       self._L.mg_ctx_destroy(self._h)
       self._h = None
 
@@ -63,6 +67,15 @@ class Engine(object):
 
   def synchronize(self):
     self._check(self._L.mg_synchronize(self._h))
+
+  # -- pinned host buffers ----------------------------------------------------------------------
+  def pinned(self, nbytes):
+    """uint8 numpy array over page-locked host memory (freed with the engine)."""
+    p = C.c_void_p()
+    self._check(self._L.mg_host_alloc(self._h, int(nbytes), C.byref(p)))
+    self._pinned.append(p)
+    buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
+    return np.frombuffer(buf, dtype=np.uint8)
 
   # -- model -------------------------------------------------------------------------------------
   def load_model(self, model, rlen=None):
@@ -203,6 +216,10 @@ class Engine(object):
     ms, n, b, tl, pms = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
     self._L.mg_prof_get(self._h, C.byref(ms), C.byref(n), C.byref(b), C.byref(tl), C.byref(pms))
     return {'emit_ms': ms.value, 'emit_launches': n.value, 'emit_bytes': b.value, 'total_launches': tl.value, 'plan_ms': pms.value}
+
+
+def device_count():
+  return int(_lib.lib().mg_device_count())
 
 
 _default = None

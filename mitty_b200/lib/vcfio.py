@@ -17,6 +17,7 @@ The per-copy result is a ``VariantList``: flat numpy arrays ready for the C-ABI
 """
 import gzip
 import logging
+import threading
 
 import numpy as np
 
@@ -241,12 +242,14 @@ class FastaFile(object):
       self._seqs[name] = (eol + 1, bounds[k + 1])
     self._data = data
     self._cache = {}
+    self._lock = threading.Lock()
 
   def _contig(self, name):
-    if name not in self._cache:
-      s, e = self._seqs[name]
-      self._cache = {name: np.frombuffer(self._data[s:e].translate(None, b'\r\n'), dtype=np.uint8)}
-    return self._cache[name]
+    with self._lock:   # one worker thread per GPU may fetch concurrently
+      if name not in self._cache:
+        s, e = self._seqs[name]
+        self._cache[name] = np.frombuffer(self._data[s:e].translate(None, b'\r\n'), dtype=np.uint8)
+      return self._cache[name]
 
   def fetch(self, reference=None, start=None, end=None):
     return self._contig(reference)[start:end]

@@ -98,22 +98,77 @@ def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sam
                               corrupt=corrupt, corrupt_seed=corrupt_seed, out=out, fetch=fetch)
 
 
+def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,
+                corrupt_seed, n_buffers, done, free_q, stop):
+  """One thread per GPU: its units, in schedule order, each into a pinned buffer pair."""
+  engine = None
+  try:
+    engine = Engine(device)
+    engine.load_model(read_model)
+    cache = RegionCache(engine, vcf_df, fetch_ref)
+    rlen = int(read_model['rlen'])
+    # pinned buffers sized for this GPU's largest unit (~5/6 of the candidates survive)
+    span = max([vcf_df[schedule[k]['region_idx']]['region'][2] - vcf_df[schedule[k]['region_idx']]['region'][1] for k in my_units] + [1])
+    est = int(span * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150) * 0.9) + (1 << 20)
+    for _ in range(n_buffers):
+      free_q.put((engine.pinned(est), engine.pinned(est)))
+    for k in my_units:
+      wd = schedule[k]
+      buf = free_q.get()
+      if buf is None or stop.is_set():
+        return
+      r_idx, cpy = wd['region_idx'], wd['region_cpy']
+      cp = cache.copy(r_idx, cpy)
+      f1, f2, cnt, _, _ = generate_unit(engine, read_module, read_model, cp, vcf_df[r_idx]['region'][0], cpy, int(wd['rng_seed']),
+                                        sample_name, 0, k, mode=mode, corrupt=corrupt, corrupt_seed=corrupt_seed, out=buf)
+      done[k].put((f1, f2, cnt, buf))
+    stop.wait()          # keep the pinned buffers alive until the writer has drained them
+  except BaseException as e:  # noqa: B902 -- handed to the writer, which re-raises
+    for k in my_units:
+      done[k].put(e)
+  finally:
+    if engine is not None:
+      engine.close()
+
+
 def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_module, model, coverage,
                            fastq1_fname, fastq2_fname, threads=2, seed=7, mode='philox', corrupt=False,
-                           corrupt_seed=None, device=0):
+                           corrupt_seed=None, devices=None):
   """Same signature as the reference (readgenerate.py:76-78) plus keyword-only extras.
 
-  threads is accepted for command-line compatibility; one GPU runs every unit of this process
-  (one process per GPU: see mitty_b200.multigpu for the sharded driver).  Output order and qname
-  serials are those of the reference's ``--threads 1`` run (worker id 0, unit index = schedule
-  index), whatever the GPU count.
+  ``threads`` = number of GPUs to use (capped by the GPUs present; ``devices`` overrides).  Work
+  units are dealt to the GPUs by longest-processing-time-first; one host thread drives each GPU,
+  filling pinned buffers while this thread appends finished units to the two files IN SCHEDULE
+  ORDER (sequential writes only: the targets may be FIFOs).  Output order and qname serials are
+  those of the reference's ``--threads 1`` run (worker id 0, unit index = schedule index), whatever
+  the GPU count.
   """
+  import queue
+  import threading
+  from mitty_b200 import multigpu
+  from mitty_b200.engine import device_count
+
   read_model = read_module.read_model_params(model, coverage)
   vcf_df = vio.load_variant_file(vcf_fname, sample_name, bed_fname)
   fasta = vio.FastaFile(fasta_fname)
-  engine = Engine(device)
-  engine.load_model(read_model)
-  cache = RegionCache(engine, vcf_df, lambda region: fasta.fetch(reference=region[0], start=region[1], end=region[2]))
+  fetch_ref = lambda region: fasta.fetch(reference=region[0], start=region[1], end=region[2])  # noqa: E731
+  schedule = list(get_data_for_workers(read_model, vcf_df, seed))
+  if devices is None:
+    n_dev = device_count()
+    if n_dev < 1:
+      raise RuntimeError('mitty_b200: no CUDA device; the engine has no CPU fallback')
+    devices = list(range(max(1, min(int(threads), n_dev))))
+  weights = [vcf_df[wd['region_idx']]['region'][2] - vcf_df[wd['region_idx']]['region'][1] for wd in schedule]
+  assign = multigpu.assign_units(weights, len(devices)) if schedule else [[] for _ in devices]
+  done = [queue.Queue(1) for _ in schedule]
+  stop = threading.Event()
+  free_qs = [queue.Queue() for _ in devices]
+  cs = seed if corrupt_seed is None else corrupt_seed
+  workers = [threading.Thread(target=_gpu_worker, daemon=True,
+                              args=(dev, assign[i], schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,
+                                    cs, 2, done, free_qs[i], stop))
+             for i, dev in enumerate(devices)]
+  owner = {k: i for i, units in enumerate(assign) for k in units}
 
   t0 = time.time()
   total = 0
@@ -121,21 +176,27 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   if fastq2_fname is not None:
     fastq_l += [open(fastq2_fname, 'wb')]
   try:
-    for ps, wd in enumerate(get_data_for_workers(read_model, vcf_df, seed)):
-      r_idx, cpy, rng_seed = wd['region_idx'], wd['region_cpy'], int(wd['rng_seed'])
-      region = vcf_df[r_idx]['region']
-      cp = cache.copy(r_idx, cpy)
-      f1, f2, cnt, _, _ = generate_unit(engine, read_module, read_model, cp, region[0], cpy, rng_seed, sample_name, 0, ps,
-                                        mode=mode, corrupt=corrupt,
-                                        corrupt_seed=seed if corrupt_seed is None else corrupt_seed)
+    for w in workers:
+      w.start()
+    for k in range(len(schedule)):
+      item = done[k].get()
+      if isinstance(item, BaseException):
+        raise item
+      f1, f2, cnt, buf = item
       for fp, r in zip(fastq_l, (f1, f2)):                          # writer, readgenerate.py:246-248
         fp.write(memoryview(r))
+      free_qs[owner[k]].put(buf)
       total += cnt
-      logger.debug('Unit {} ({}, copy {}): {} templates'.format(ps, region, cpy, cnt))
+      logger.debug('Unit {}: {} templates'.format(k, cnt))
   finally:
+    stop.set()
+    for q in free_qs:                                                 # unblock workers waiting for a buffer
+      q.put(None)
     for fp in fastq_l:
       fp.close()
-    engine.close()
+    for w in workers:
+      if w.is_alive():
+        w.join(timeout=60)
   t1 = time.time()
   logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s)'.format(total, t1 - t0, total / max(t1 - t0, 1e-9)))
 

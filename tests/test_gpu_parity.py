@@ -224,3 +224,29 @@ def test_cli_files_deterministic(tmp_path):
                                  '--threads', '1', '--deterministic'], catch_exceptions=False)
   assert res.exit_code == 0, res.output
   assert open(c1, 'rb').read() == H.golden_fastq('edge.c1.fq.gz') and open(c2, 'rb').read() == H.golden_fastq('edge.c2.fq.gz')
+
+
+@pytest.mark.parametrize('devices', [[0, 0], [0, 0, 0], 'all'])
+def test_sharded_workers_identical_output(tmp_path, devices):
+  """Units dealt to several GPU workers (LPT), appended in schedule order: the bytes must not
+  depend on the worker count.  [0, 0]: two workers with their own contexts on one GPU (the host
+  logic of the multi-GPU path on a 1-GPU box); 'all': one worker per GPU present."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  from mitty_b200.engine import device_count
+  info = H.golden()['fastq']['edge']
+  wl = synth.edge_workload()
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'))
+  devs = list(range(device_count())) if devices == 'all' else devices
+  r1, r2 = str(tmp_path / 'r1.fq'), str(tmp_path / 'r2.fq')
+  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model(info['model']), info['coverage'], r1, r2,
+                            threads=len(devs), seed=info['seed'], mode='deterministic', devices=devs)
+  assert open(r1, 'rb').read() == H.golden_fastq('edge.r1.fq.gz') and open(r2, 'rb').read() == H.golden_fastq('edge.r2.fq.gz')
+  # production mode: same bytes for 1 worker and for several
+  p1, p2 = str(tmp_path / 'p1.fq'), str(tmp_path / 'p2.fq')
+  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model(info['model']), info['coverage'], p1, p2,
+                            threads=len(devs), seed=5, mode='philox', corrupt=True, devices=devs)
+  q1, q2 = str(tmp_path / 'q1.fq'), str(tmp_path / 'q2.fq')
+  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model(info['model']), info['coverage'], q1, q2,
+                            threads=1, seed=5, mode='philox', corrupt=True, devices=[0])
+  assert open(p1, 'rb').read() == open(q1, 'rb').read() and open(p2, 'rb').read() == open(q2, 'rb').read()

@@ -1,0 +1,22 @@
+"""Full command line to a file sink: FASTA / VCF / BED on disk -> two FASTQ files (tmpfs)."""
+import os, sys, time, tempfile
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+from click.testing import CliRunner
+from mitty_b200 import synth
+from mitty_b200.cli import cli
+n_mb = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+threads = sys.argv[2] if len(sys.argv) > 2 else '1'
+d = tempfile.mkdtemp(dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+wl = synth.chr1_shaped(seed=7, length=n_mb * 1000000, n_runs=max(3, n_mb // 6))
+t0 = time.perf_counter(); fa, vcf, bed = synth.write_workload(wl, os.path.join(d, 'w')); t1 = time.perf_counter()
+print('wrote inputs (%d Mb FASTA, %d VCF records) in %.1f s' % (n_mb, len(wl['tables'][0]), t1 - t0))
+for extra in ([], ['--corrupt']):
+  r1, r2 = os.path.join(d, 'r1.fq'), os.path.join(d, 'r2.fq')
+  t0 = time.perf_counter()
+  res = CliRunner().invoke(cli, ['generate-reads', fa, vcf, wl['sample'], bed, 'hiseq-X-v2.5-Garvan.pkl', '30', '7', r1, '--fastq2', r2, '--threads', threads] + extra, catch_exceptions=False)
+  t1 = time.perf_counter()
+  assert res.exit_code == 0, res.output
+  sz = os.path.getsize(r1)
+  pairs = sum(1 for _ in open(r1, 'rb')) // 4
+  print('generate-reads %s --threads %s: %d pairs, 2 x %.2f GB to %s in %.2f s = %.2f M pairs/s' % (' '.join(extra), threads, pairs, sz / 1e9, d, t1 - t0, pairs / (t1 - t0) / 1e6))
+  os.remove(r1); os.remove(r2)

@@ -250,29 +250,58 @@ struct MgCountWriter {
   MG_HD void put_word(uint32_t) { n += 4; }
 };
 
+// Address-space policies.  The emit kernel formats records into its warp's shared-memory stage:
+// MgSharedSpace addresses it with 32-bit offsets into the kernel's dynamic shared memory, so every
+// store is a plain STS (generic 64-bit pointers cost 3-4 instructions per store).  MgGenericSpace
+// is any memory: host emulation, and the rare record that is larger than the stage.
+struct MgGenericSpace {
+  typedef uint8_t *ptr;
+  static MG_HD void st8(ptr p, uint8_t v) { *p = v; }
+  static MG_HD void st32(ptr p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
+  static MG_HD uint32_t ld32(ptr p) { return *reinterpret_cast<const uint32_t *>(p); }
+  static MG_HD uint32_t low2(ptr p) { return (uint32_t)((uintptr_t)p & 3); }
+};
+#if defined(__CUDACC__)
+struct MgSharedSpace {
+  typedef uint32_t ptr;   // byte offset into the dynamic shared memory of the running kernel
+  static __device__ __forceinline__ uint8_t *base() { extern __shared__ __align__(16) uint8_t mg_dyn_smem[]; return mg_dyn_smem; }
+  static __device__ __forceinline__ void st8(ptr p, uint8_t v) { base()[p] = v; }
+  static __device__ __forceinline__ void st32(ptr p, uint32_t v) { *reinterpret_cast<uint32_t *>(base() + p) = v; }
+  static __device__ __forceinline__ uint32_t ld32(ptr p) { return *reinterpret_cast<const uint32_t *>(base() + p); }
+  static __device__ __forceinline__ uint32_t low2(ptr p) { return p & 3u; }
+};
+#endif
+
 // plain byte stores: used for the qname, whose per-lane byte counts differ (a shared word
 // stream would flush on a different iteration in every lane and serialise the warp)
+template <class SP>
 struct MgByteWriter {
   static constexpr bool is_bytes = true;
-  uint8_t *p;
-  MG_HD void put(uint8_t c) { *p++ = c; }
+  typedef SP space;
+  typename SP::ptr p;
+  MG_HD void put(uint8_t c) { SP::st8(p, c); p += 1; }
 };
 
+template <class SP> MG_NI void mg_store_tail(typename SP::ptr b, uint32_t carry, uint32_t nb) {
+  for (uint32_t i = 0; i < nb; i++) SP::st8(b + i, (uint8_t)(carry >> (8 * i)));
+}
+
+template <class SP>
 struct MgWordStream {
   static constexpr bool is_bytes = false;
-  uint32_t *wp;     // next aligned word
-  uint32_t carry;   // pending bytes, low nb bytes valid
-  uint32_t nb;      // pending byte count 0..3
+  typename SP::ptr wp;   // next aligned word
+  uint32_t carry;        // pending bytes, low nb bytes valid
+  uint32_t nb;           // pending byte count 0..3
 
   // The bytes before dst inside its word were written earlier BY THIS THREAD (the tail of its own
   // qname / separator): they are read back and carried, so every flush is a plain word store.
-  MG_HD void begin_rmw(uint8_t *dst) {
-    uintptr_t a = (uintptr_t)dst & 3;
-    wp = (uint32_t *)(dst - a);
-    nb = (uint32_t)a;
-    carry = a ? (*wp & (0xFFFFFFFFu >> (32 - 8 * (uint32_t)a))) : 0u;
+  MG_HD void begin_rmw(typename SP::ptr dst) {
+    const uint32_t a = SP::low2(dst);
+    wp = dst - a;
+    nb = a;
+    carry = a ? (SP::ld32(wp) & (0xFFFFFFFFu >> (32 - 8 * a))) : 0u;
   }
-  MG_HD void flush_word(uint32_t w) { *wp++ = w; }
+  MG_HD void flush_word(uint32_t w) { SP::st32(wp, w); wp += 4; }
   MG_HD void put(uint8_t c) {
     carry |= (uint32_t)c << (8 * nb);
     if (++nb == 4) { flush_word(carry); carry = 0; nb = 0; }
@@ -283,31 +312,28 @@ struct MgWordStream {
     carry = mg_funnel_l(w, 0u, sh);          // the top nb bytes of w (0 when nb == 0)
   }
   // the last partial word is shared with the NEXT record (another thread): byte stores
-  MG_HD void end();
+  MG_HD void end() { mg_store_tail<SP>(wp, carry, nb); nb = 0; }
 };
 
-MG_NI void mg_store_tail(uint8_t *b, uint32_t carry, uint32_t nb) {
-  for (uint32_t i = 0; i < nb; i++) b[i] = (uint8_t)(carry >> (8 * i));
-}
-MG_HD void MgWordStream::end() { mg_store_tail((uint8_t *)wp, carry, nb); nb = 0; }
-
 // decimal digits of v at p (byte stores), returns the advanced pointer
-MG_NI uint8_t *mg_put_u32_p(uint8_t *p, uint32_t v) {
+template <class SP> MG_NI typename SP::ptr mg_put_u32_p(typename SP::ptr p, uint32_t v) {
   uint64_t acc = 0;
   int n = 0;
   do { uint32_t q = v / 10u; acc = (acc << 4) | (v - q * 10u); v = q; n++; } while (v);
-  for (; n; n--) { *p++ = (uint8_t)('0' + ((uint32_t)acc & 15u)); acc >>= 4; }
+  for (; n; n--) { SP::st8(p, (uint8_t)('0' + ((uint32_t)acc & 15u))); p += 1; acc >>= 4; }
   return p;
 }
 
 template <class W>
 MG_HD void mg_put_u32(W &w, uint32_t v) {
-  if constexpr (W::is_bytes) { w.p = mg_put_u32_p(w.p, v); return; }
-  // digits are stacked as nibbles in a register pair (no local-memory array); /10 is a multiply
-  uint64_t acc = 0;
-  int n = 0;
-  do { uint32_t q = v / 10u; acc = (acc << 4) | (v - q * 10u); v = q; n++; } while (v);
-  for (; n; n--) { w.put((uint8_t)('0' + ((uint32_t)acc & 15u))); acc >>= 4; }
+  if constexpr (W::is_bytes) { w.p = mg_put_u32_p<typename W::space>(w.p, v); return; }
+  else {
+    // digits are stacked as nibbles in a register pair (no local-memory array); /10 is a multiply
+    uint64_t acc = 0;
+    int n = 0;
+    do { uint32_t q = v / 10u; acc = (acc << 4) | (v - q * 10u); v = q; n++; } while (v);
+    for (; n; n--) { w.put((uint8_t)('0' + ((uint32_t)acc & 15u))); acc >>= 4; }
+  }
 }
 
 template <class W>
@@ -451,10 +477,10 @@ MG_HD void mg_fmt_qname(W &w, const uint8_t *prefix, int prefix_len, uint64_t cn
 }
 
 // qname + newline as bytes at dst (one shared copy per kernel), returns the advanced pointer
-template <class NP>
-MG_NI uint8_t *mg_qname_bytes(uint8_t *dst, const uint8_t *prefix, int prefix_len, uint64_t cnt,
-                              const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
-  MgByteWriter bw; bw.p = dst;
+template <class SP, class NP>
+MG_NI typename SP::ptr mg_qname_bytes(typename SP::ptr dst, const uint8_t *prefix, int prefix_len, uint64_t cnt,
+                                      const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
+  MgByteWriter<SP> bw; bw.p = dst;
   mg_fmt_qname(bw, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
   bw.put('\n');
   return bw.p;
@@ -577,8 +603,8 @@ MG_NI int mg_count_N(EP exc, int n_exc, uint32_t x, int L) {
 // overwrite the bases of a written read (seq points at its first byte) that fall in exception
 // runs.  The reference's translate table only maps ATCGN (readgenerate.py:56), so an exception
 // byte is copied unchanged on either strand; only its position is mirrored on strand 1.
-template <class EP>
-MG_NI void mg_patch_exc(uint8_t *seq, EP exc, int n_exc, uint32_t x, int L, int strand) {
+template <class SP, class EP>
+MG_NI void mg_patch_exc(typename SP::ptr seq, EP exc, int n_exc, uint32_t x, int L, int strand) {
   for (int k = mg_exc_first(exc, n_exc, x); k < n_exc; k++) {
     MgExc e = exc[k];
     if ((uint64_t)e.start >= (uint64_t)x + L) break;
@@ -586,7 +612,7 @@ MG_NI void mg_patch_exc(uint8_t *seq, EP exc, int n_exc, uint32_t x, int L, int 
     uint64_t b = (uint64_t)e.start + e.len < (uint64_t)x + L ? (uint64_t)e.start + e.len : (uint64_t)x + L;
     for (uint64_t i = a; i < b; i++) {
       int idx = (int)(i - x);
-      seq[strand ? (L - 1 - idx) : idx] = (uint8_t)e.byte;
+      SP::st8(seq + (uint32_t)(strand ? (L - 1 - idx) : idx), (uint8_t)e.byte);
     }
   }
 }
@@ -673,40 +699,40 @@ MG_HD void mg_emit_seq_src(WR &w, MgSeqSrc<MAXW, HP> &S) {
 // One FASTQ record (fastq_lines, readgenerate.py:227-230):  qname \n SEQ \n+\n ~~~~ \n
 // S = the read that goes into this file (already loaded); first/second give the qname's file order.
 // qlen = length of the qname line without its newline (known from the sizing pass).
-template <int MAXW, class NP, class HP, class EP>
-MG_HD void mg_emit_record(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
+template <class SP, int MAXW, class NP, class HP, class EP>
+MG_HD void mg_emit_record(typename SP::ptr dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
                           const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second,
                           MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc) {
   const int L = S.L;
-  MgWordStream ws;
-  ws.begin_rmw(mg_qname_bytes(dst, prefix, prefix_len, cnt, mid, mid_len, nodes, first, second, L));
+  MgWordStream<SP> ws;
+  ws.begin_rmw(mg_qname_bytes<SP>(dst, prefix, prefix_len, cnt, mid, mid_len, nodes, first, second, L));
   mg_emit_seq_src(ws, S);
   ws.put('\n'); ws.put('+'); ws.put('\n');
   mg_emit_fill(ws, '~', L);
   ws.put('\n');
   ws.end();
-  if (n_exc) mg_patch_exc(dst + qlen + 1, exc, n_exc, S.x, L, S.strand);
+  if (n_exc) mg_patch_exc<SP>(dst + (qlen + 1), exc, n_exc, S.x, L, S.strand);
 }
 
 // The other file's record has the same qname, the same offsets and (for perfect reads) the same
 // quality line: only the L sequence bytes are rewritten in place.
-template <int MAXW, class HP, class EP>
-MG_HD void mg_rewrite_seq(uint8_t *seq_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc) {
-  MgWordStream ws;
+template <class SP, int MAXW, class HP, class EP>
+MG_HD void mg_rewrite_seq(typename SP::ptr seq_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc) {
+  MgWordStream<SP> ws;
   ws.begin_rmw(seq_dst);
   mg_emit_seq_src(ws, S);
   ws.end();
-  if (n_exc) mg_patch_exc(seq_dst, exc, n_exc, S.x, S.L, S.strand);
+  if (n_exc) mg_patch_exc<SP>(seq_dst, exc, n_exc, S.x, S.L, S.strand);
 }
 
 // qname line + the three separator newlines of a record whose SEQ / QUAL lines are written by
 // mg_emit_seq_corrupt (fused corruption).
-template <class NP>
-MG_HD void mg_emit_frame(uint8_t *dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
+template <class SP, class NP>
+MG_HD void mg_emit_frame(typename SP::ptr dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
                          const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
-  mg_qname_bytes(dst, prefix, prefix_len, cnt, mid, mid_len, nodes, first, second, L);
-  uint8_t *p = dst + qlen + 1 + L;
-  p[0] = '\n'; p[1] = '+'; p[2] = '\n'; p[3 + L] = '\n';
+  mg_qname_bytes<SP>(dst, prefix, prefix_len, cnt, mid, mid_len, nodes, first, second, L);
+  const typename SP::ptr p = dst + (qlen + 1 + (uint32_t)L);
+  SP::st8(p, '\n'); SP::st8(p + 1, '+'); SP::st8(p + 2, '\n'); SP::st8(p + (3 + (uint32_t)L), '\n');
 }
 
 // ------------------------------------------------------------------------------------------
@@ -788,12 +814,12 @@ MG_HD void mg_corrupt4(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n
 
 // SEQ and QUAL lines of one read, corrupted on the fly: every thread of a warp is at the same
 // cycle of its own record, so the alias row (one 256-byte line pair) is shared by the warp.
-template <int MAXW, class HP, class EP>
-MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc,
+template <class SP, int MAXW, class HP, class EP>
+MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc,
                                const MgCorruptCtx &C, uint32_t serial, uint32_t f) {
   const int L = S.L;
   const struct { uint32_t x; int strand; } mine = {S.x, S.strand};
-  MgWordStream ws, wq;
+  MgWordStream<SP> ws, wq;
   ws.begin_rmw(seq_dst); wq.begin_rmw(qual_dst);
   mg_for_each_chunk(S, [&](uint32_t codes, int c) {
     MG_NOUNROLL
@@ -826,7 +852,7 @@ MG_HD void mg_emit_seq_corrupt(uint8_t *seq_dst, uint8_t *qual_dst, MgSeqSrc<MAX
         const MgPhilox r = mg_philox_corrupt(serial, f, (uint32_t)(n >> 1), C.k0, C.k1);
         uint32_t base = e.byte, qual;
         mg_corrupt_one(C, f, n, (n & 1) ? r.v[2] : r.v[0], (n & 1) ? r.v[3] : r.v[1], base, qual);
-        seq_dst[n] = (uint8_t)base;
+        SP::st8(seq_dst + (uint32_t)n, (uint8_t)base);
       }
     }
   }

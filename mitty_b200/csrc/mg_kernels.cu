@@ -461,13 +461,30 @@ void mg_launch_plan(const MgUnitParams &P, cudaStream_t st) {
 // Phase 2: one WARP owns 32 consecutive kept templates (every lane busy), formats their records
 // into its own shared-memory stage and copies the byte range out with coalesced 128-bit stores.
 // No block barrier and no scan: placement was decided by k_unit_plan.
+// a record larger than the whole stage (only possible with absurdly long CIGARs): straight to
+// global memory through generic pointers, streaming sequence source; cold and out of line
+template <bool CORRUPT>
+__device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const MgUnitParams &P, const MgCorruptCtx &cor,
+                                           unsigned long long cnt, MgReadRef first, MgReadRef second, MgReadRef mine, int f) {
+  const int L = P.rlen;
+  MgSeqSrc<0, const uint32_t *> S;
+  S.load(P.hap, mine.x, L, mine.strand);
+  if constexpr (CORRUPT) {
+    mg_emit_frame<MgGenericSpace>(dst, qlen, P.prefix, P.prefix_len, cnt, P.mid, P.mid_len, P.nodes, first, second, L);
+    mg_emit_seq_corrupt<MgGenericSpace>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)(cnt - 1), (uint32_t)f);
+  } else {
+    mg_emit_record<MgGenericSpace>(dst, qlen, P.prefix, P.prefix_len, cnt, P.mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
+  }
+}
+
 template <int MAXW, bool CORRUPT>
 __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
   __shared__ MgErr s_err[CORRUPT ? 128 : 1];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  uint8_t *stage = smem + (size_t)wid * (P.stage_cap + 16);
+  const uint32_t stage_off = (uint32_t)wid * (uint32_t)(P.stage_cap + 16);   // this warp's stage, as an offset into smem
+  uint8_t *stage = smem + stage_off;
   const int L = P.rlen;
   MgCorruptCtx cor = P.cor;
   if constexpr (CORRUPT) { s_err[t & 127] = P.cor.err[t & 127]; cor.err = s_err; }   // error thresholds: 2 KB, shared memory
@@ -512,16 +529,20 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
         if (f >= 0 && P.out[f] == nullptr) continue;
         if (mine) {
           if (f >= 0) {
-            uint8_t *dst = oversize ? (P.out[f] + pl.off) : (stage + pad + (uint32_t)(pl.off - goff));
-            // the stage keeps the qname (and, for perfect reads, the quality line) of file 0 in
-            // place: the other file only rewrites its L sequence bytes
-            const bool full = (f == 0) || oversize || (P.out[0] == nullptr);
-            if constexpr (CORRUPT) {
-              if (full) mg_emit_frame(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
-              mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)rank, (uint32_t)f);
+            if (!oversize) {
+              const uint32_t dst = stage_off + pad + (uint32_t)(pl.off - goff);
+              // the stage keeps the qname (and, for perfect reads, the quality line) of file 0 in
+              // place: the other file only rewrites its L sequence bytes
+              const bool full = (f == 0) || (P.out[0] == nullptr);
+              if constexpr (CORRUPT) {
+                if (full) mg_emit_frame<MgSharedSpace>(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
+                mg_emit_seq_corrupt<MgSharedSpace>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)rank, (uint32_t)f);
+              } else {
+                if (full) mg_emit_record<MgSharedSpace>(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
+                else mg_rewrite_seq<MgSharedSpace>(dst + qlen + 1, S, P.exc, P.n_exc);
+              }
             } else {
-              if (full) mg_emit_record(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
-              else mg_rewrite_seq(dst + qlen + 1, S, P.exc, P.n_exc);
+              emit_oversize<CORRUPT>(P.out[f] + pl.off, qlen, P, cor, cnt, first, second, f ? second : first, f);
             }
           }
           if (f < 1) {

@@ -48,17 +48,17 @@ static int64_t emul_unit_t(const uint32_t *hap, uint32_t hap_len, const MgNode *
     MgSeqSrc<MAXW, const uint32_t *> S;
     S.load(hap, first.x, L, first.strand);
     if (corrupt) {
-      mg_emit_frame(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, L);
-      mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, exc, n_exc, cor, (uint32_t)(cnt - 1), 0u);
+      mg_emit_frame<MgGenericSpace>(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, L);
+      mg_emit_seq_corrupt<MgGenericSpace>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, exc, n_exc, cor, (uint32_t)(cnt - 1), 0u);
       memcpy(out1 + off, dst, rec);
       S.load(hap, second.x, L, second.strand);
-      mg_emit_seq_corrupt(dst + qlen + 1, dst + qlen + 1 + L + 3, S, exc, n_exc, cor, (uint32_t)(cnt - 1), 1u);
+      mg_emit_seq_corrupt<MgGenericSpace>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, exc, n_exc, cor, (uint32_t)(cnt - 1), 1u);
       memcpy(out2 + off, dst, rec);
     } else {
-      mg_emit_record(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, S, exc, n_exc);
+      mg_emit_record<MgGenericSpace>(dst, qlen, (const uint8_t *)prefix, pl, cnt, (const uint8_t *)mid, ml, nodes, first, second, S, exc, n_exc);
       memcpy(out1 + off, dst, rec);
       S.load(hap, second.x, L, second.strand);
-      mg_rewrite_seq(dst + qlen + 1, S, exc, n_exc);
+      mg_rewrite_seq<MgGenericSpace>(dst + qlen + 1, S, exc, n_exc);
       memcpy(out2 + off, dst, rec);
     }
     sz_sum += sz; cnt2++;

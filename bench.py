@@ -234,13 +234,17 @@ def main():
   units = [(cpy, ps) for cpy in range(len(r['v'])) for ps in range(rm['passes'])]
 
   def step(seed, rid, out=None, fetch=False):
-    """Both copies built from the region, then the 4 units. Returns (pairs, fastq bytes)."""
+    """Both copies built from the region, then the 4 units. Returns (pairs, fastq bytes).
+    out: two pinned buffer pairs used alternately; the D2H of unit k overlaps the kernels of k+1."""
     pairs = nbytes = 0
     copies = [eng.build_copy(rid, vl) for vl in r['v']]
     for k, (cpy, ps) in enumerate(units):
       _, _, cnt, _, nb = rg.generate_unit(eng, il, rm, copies[cpy], region[0], cpy, (seed * 7919 + k * 104729) & 0xFFFFFFFF,
-                                          wl['sample'], 0, k, mode='philox', corrupt=corrupt, corrupt_seed=seed, out=out, fetch=fetch)
+                                          wl['sample'], 0, k, mode='philox', corrupt=corrupt, corrupt_seed=seed,
+                                          out=out[k & 1] if out else None, fetch=fetch, wait=not fetch)
       pairs += cnt; nbytes += 2 * nb
+    if fetch:
+      eng.wait_copies()
     for cp in copies:
       eng.free_copy(cp)
     return pairs, nbytes
@@ -276,7 +280,7 @@ def main():
   e2e = None
   if not args.no_e2e:
     est = int((args.contig_len * rm['p'] * 1.2) * (2 * L + 110)) + (1 << 20)
-    out = (torch.empty(est, dtype=torch.uint8).pin_memory().numpy(), torch.empty(est, dtype=torch.uint8).pin_memory().numpy())
+    out = [(eng.pinned(est), eng.pinned(est)) for _ in range(2)]
     def e2e_step(seed):
       rid_ = eng.load_region(ref_np, region[1])
       p_, b_ = step(seed, rid_, out=out, fetch=True)

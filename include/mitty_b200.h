@@ -110,6 +110,14 @@ int mg_sample_templates(mg_ctx *ctx, const mg_unit_desc *d, int64_t *ts_out, int
 int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap,
                      int64_t *n_bytes, int64_t *n_templates, int64_t *n_te_kept);
 
+/* same, but returns as soon as the kernels have finished and the device-to-host copies are
+ * ENQUEUED (on the context's copy stream): the next unit's kernels overlap with them.  out1/out2
+ * (pinned memory) are valid after mg_wait_copies(); at most two units may be in flight, i.e. a
+ * buffer pair may be reused for the unit after next.                                            */
+int mg_unit_generate_async(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap,
+                           int64_t *n_bytes, int64_t *n_templates, int64_t *n_te_kept);
+int mg_wait_copies(mg_ctx *ctx);
+
 /* ---- corrupt-reads: replaces readcorrupt.multi_process / illumina.corrupt_template
  * (mitty/simulation/readcorrupt.py:18-118, illumina.py:113-162) over whole FASTQ buffers.
  * in2/out2 may be NULL (single-end).  DET mode consumes the reference's draws: for read k (file-1

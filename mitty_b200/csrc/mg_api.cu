@@ -39,7 +39,8 @@ struct Region {
   int64_t len = 0, bed_start = 0;
   uint32_t *d_ref = nullptr;      // packed, with MG_HAP_PAD words of padding on both sides
   std::vector<ExcRun> exc;        // non-ACGT runs, region-relative
-  ~Region() { if (d_ref) cudaFree(d_ref); }
+  mg_ctx *owner = nullptr;
+  ~Region();
 };
 
 
@@ -77,9 +78,12 @@ struct mg_ctx {
   std::map<int64_t, std::unique_ptr<Copy>> copies;
   int64_t next_id = 1;
   // scratch
-  DevBuf s_raw, s_exc, s_ts, s_u, s_fo, s_tsorted, s_partial, s_state, s_out[2], s_str, s_qn, s_plan, s_sample[3];
+  DevBuf s_raw, s_exc, s_ts, s_u, s_fo, s_tsorted, s_partial, s_state, s_out[2][2], s_str, s_qn, s_plan, s_sample[3];
   DevBuf c_in[2], c_out[2], c_nl[2], c_cnt, c_sz[2], c_off[2], c_tmp, c_draw[4];
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  cudaStream_t copy_stream = nullptr;              // D2H of finished units, overlapping the next unit's kernels
+  cudaEvent_t ev_d2h[2] = {nullptr, nullptr};      // per output-buffer set: its last D2H has finished
+  int ob = 0;                                      // output-buffer set of the next unit
   double plan_ms = 0;
   double emit_ms = 0; int64_t emit_launches = 0, emit_bytes = 0, total_launches = 0;
 };
@@ -179,6 +183,7 @@ void pool_free(mg_ctx *ctx, void *p) {
   cudaFree(p);
 }
 
+Region::~Region() { pool_free(owner, d_ref); }
 Copy::~Copy() { pool_free(owner, d_nodes); pool_free(owner, d_hap); pool_free(owner, d_blk); pool_free(owner, d_exc); }
 
 }  // namespace
@@ -206,6 +211,8 @@ int mg_ctx_create(int device, void *stream, mg_ctx **out) {
   if (stream) ctx->stream = reinterpret_cast<cudaStream_t>(stream);
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MG_ECUDA; } ctx->own_stream = true; }
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2);
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_d2h[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_d2h[1], cudaEventDisableTiming);
   *out = ctx;
   return MG_OK;
 }
@@ -214,6 +221,8 @@ void mg_ctx_destroy(mg_ctx *ctx) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (int i = 0; i < 2; i++) if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
   ctx->regions.clear(); ctx->copies.clear();
   for (auto &b : ctx->pool) cudaFree(b.first);
   ctx->pool.clear(); ctx->block_size.clear();
@@ -320,7 +329,8 @@ int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t b
   std::unique_ptr<Region> R(new Region());
   R->len = len; R->bed_start = bed_start;
   int64_t words = (len + 15) / 16;
-  CU(cudaMalloc(&R->d_ref, sizeof(uint32_t) * (words + 2 * MG_HAP_PAD)));
+  R->owner = ctx;
+  CU(pool_get(ctx, (void **)&R->d_ref, sizeof(uint32_t) * (words + 2 * MG_HAP_PAD)));
   CU(cudaMemsetAsync(R->d_ref, 0, sizeof(uint32_t) * (words + 2 * MG_HAP_PAD), ctx->stream));
   if (len > 0) {
     CU(ctx->s_raw.need((size_t)len + 32));
@@ -619,8 +629,8 @@ int mg_sample_templates(mg_ctx *ctx, const mg_unit_desc *d, int64_t *ts_out, int
   return MG_OK;
 }
 
-int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *n_bytes,
-                     int64_t *n_templates, int64_t *n_te_kept) {
+static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *n_bytes,
+                         int64_t *n_templates, int64_t *n_te_kept, bool wait_copies) {
   if (!ctx) return MG_EINVAL;
   DeviceGuard g(ctx->device);
   MgUnitParams P; const Copy *C;
@@ -677,9 +687,12 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
   mg_launch_plan(P, ctx->stream);
   CU(cudaGetLastError());
   for (int attempt = 0; attempt < 2; attempt++) {
-    CU(ctx->s_out[0].need(est)); CU(ctx->s_out[1].need(est));
-    P.out[0] = ctx->s_out[0].as<uint8_t>(); P.out[1] = ctx->s_out[1].as<uint8_t>();
-    P.cap = std::min(ctx->s_out[0].cap, ctx->s_out[1].cap);
+    DevBuf *ob = ctx->s_out[ctx->ob];
+    if (ob[0].cap < est || ob[1].cap < est) CU(cudaStreamSynchronize(ctx->copy_stream));   // regrowing frees the old block
+    CU(ob[0].need(est)); CU(ob[1].need(est));
+    P.out[0] = ob[0].as<uint8_t>(); P.out[1] = ob[1].as<uint8_t>();
+    P.cap = std::min(ob[0].cap, ob[1].cap);
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[ctx->ob], 0));   // this buffer set's previous D2H must be done
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     mg_launch_unit(P, grid, smem, ctx->stream);
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -703,10 +716,31 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
   if (n_te_kept) *n_te_kept = (int64_t)tot[0];
   if (want_out) {
     if ((int64_t)tot[2] > cap) return fail(ctx, MG_ECAP, "output needs %lld bytes per file, caller gave %lld", (long long)tot[2], (long long)cap);
-    if (out1 && tot[2]) CU(cudaMemcpyAsync(out1, P.out[0], (size_t)tot[2], cudaMemcpyDeviceToHost, ctx->stream));
-    if (out2 && tot[2]) CU(cudaMemcpyAsync(out2, P.out[1], (size_t)tot[2], cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    // the kernels have finished (totals were read back): the copies go to their own stream, so the
+    // next unit's kernels overlap with them
+    if (out1 && tot[2]) CU(cudaMemcpyAsync(out1, P.out[0], (size_t)tot[2], cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (out2 && tot[2]) CU(cudaMemcpyAsync(out2, P.out[1], (size_t)tot[2], cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_d2h[ctx->ob], ctx->copy_stream));
+    ctx->ob ^= 1;
+    if (wait_copies) CU(cudaStreamSynchronize(ctx->copy_stream));
   }
+  return MG_OK;
+}
+
+int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *n_bytes,
+                     int64_t *n_templates, int64_t *n_te_kept) {
+  return unit_generate(ctx, d, out1, out2, cap, n_bytes, n_templates, n_te_kept, true);
+}
+
+int mg_unit_generate_async(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *n_bytes,
+                           int64_t *n_templates, int64_t *n_te_kept) {
+  return unit_generate(ctx, d, out1, out2, cap, n_bytes, n_templates, n_te_kept, false);
+}
+
+int mg_wait_copies(mg_ctx *ctx) {
+  if (!ctx) return MG_EINVAL;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->copy_stream));
   return MG_OK;
 }
 

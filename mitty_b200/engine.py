@@ -161,11 +161,13 @@ class Engine(object):
     return ts_o[:n], te_o[:n], fo_o[:n]
 
   def generate_unit(self, cp, n, p, mode, seed, prefix, mid, ts=None, u_tlen=None, tl=None, fo=None,
-                    corrupt=False, corrupt_seed=0, out=None, fetch=True):
+                    corrupt=False, corrupt_seed=0, out=None, fetch=True, wait=True):
     """One work unit -> (fastq1, fastq2, n_templates, n_te_kept).
 
     out: optional pair of preallocated uint8 arrays (e.g. pinned) to receive the bytes; the
     returned arrays are views of them.  fetch=False leaves the result on the device.
+    wait=False (needs pinned ``out``) returns once the device-to-host copies are enqueued: the next
+    unit's kernels overlap with them and the bytes are valid after ``wait_copies()``.
     """
     d, keep = self._desc(cp, n, p, mode, seed, ts, u_tlen, tl, fo, prefix, mid, corrupt, corrupt_seed)
     nb, nt, nk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
@@ -176,12 +178,16 @@ class Engine(object):
       est = int(n) * (2 * self.rlen + 120 + len(prefix) + len(mid)) // 1 + 4096
       out = (np.empty(est, dtype=np.uint8), np.empty(est, dtype=np.uint8))
     o1, o2 = out
-    rc = self._L.mg_unit_generate(self._h, C.byref(d), _ptr(o1), _ptr(o2), min(o1.size, o2.size), C.byref(nb), C.byref(nt), C.byref(nk))
+    gen = self._L.mg_unit_generate if wait else self._L.mg_unit_generate_async
+    rc = gen(self._h, C.byref(d), _ptr(o1), _ptr(o2), min(o1.size, o2.size), C.byref(nb), C.byref(nt), C.byref(nk))
     if rc == _lib.MG_ECAP:
       o1, o2 = np.empty(nb.value, dtype=np.uint8), np.empty(nb.value, dtype=np.uint8)
       rc = self._L.mg_unit_generate(self._h, C.byref(d), _ptr(o1), _ptr(o2), nb.value, C.byref(nb), C.byref(nt), C.byref(nk))
     self._check(rc)
     return o1[:nb.value], o2[:nb.value], nt.value, nk.value, nb.value
+
+  def wait_copies(self):
+    self._check(self._L.mg_wait_copies(self._h))
 
   # -- corruption --------------------------------------------------------------------------------
   def corrupt_fastq(self, fq1, fq2=None, mode=MODE_PHILOX, seed=0, draws=None):

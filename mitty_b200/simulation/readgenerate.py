@@ -82,7 +82,7 @@ class RegionCache(object):
 
 
 def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sample_name, worker_id, ps,
-                  mode='philox', corrupt=False, corrupt_seed=0, out=None, fetch=True):
+                  mode='philox', corrupt=False, corrupt_seed=0, out=None, fetch=True, wait=True):
   """One work unit (the body of read_generating_worker's loop, readgenerate.py:183-214)
   -> (fastq1 bytes, fastq2 bytes, template count)."""
   n = int((cp.p_max - cp.p_min) * read_model['p'] * 1.2)          # illumina.py:69
@@ -91,11 +91,11 @@ def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sam
   if mode == 'deterministic':
     ts, u, fo = read_module.unit_draws(read_model, cp.p_min, cp.p_max, rng_seed)
     return engine.generate_unit(cp, n, read_model['p'], MODE_DET, rng_seed, prefix, mid, ts=ts, u_tlen=u, fo=fo,
-                                out=out, fetch=fetch)
+                                out=out, fetch=fetch, wait=wait)
   if not (0 <= rng_seed <= SEED_MAX):
     raise ValueError('Seed value {} is out of range 0 - {}'.format(rng_seed, SEED_MAX))
   return engine.generate_unit(cp, n, read_model['p'], MODE_PHILOX, rng_seed, prefix, mid,
-                              corrupt=corrupt, corrupt_seed=corrupt_seed, out=out, fetch=fetch)
+                              corrupt=corrupt, corrupt_seed=corrupt_seed, out=out, fetch=fetch, wait=wait)
 
 
 def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,

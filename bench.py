@@ -45,6 +45,8 @@ def parse():
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--perfect', action='store_true', help='perfect reads only (no fused corruption)')
+  ap.add_argument('--workload', default='chr1', choices=['chr1', 'wgs'], help="'wgs': BASELINE.json configs[3], GRCh37-shaped genome sharded by contig over the ranks (strong scaling)")
+  ap.add_argument('--scale', type=float, default=1.0, help='length scale of the wgs workload')
   return ap.parse_args()
 
 
@@ -192,6 +194,12 @@ def run_reference(args):
 
 
 def config_dict(args):
+  if getattr(args, 'workload', 'chr1') == 'wgs':
+    return {'workload': 'configs[3]: GRCh37-shaped synthetic genome (24 contigs, lengths x {}, ~8% N, diploid autosomes, haploid X/Y), '
+                        '30x paired 2x150, Philox mode{}, contigs dealt to the ranks by LPT'.format(args.scale, '' if args.perfect else ' + fused Illumina corruption'),
+            'read_model': MODEL + ' (mean_rlen 150)', 'coverage': COVERAGE, 'seed': args.seed,
+            'parallelism': 'contigs sharded over GPUs, units independent, no collective',
+            'l2': 'every unit streams its FASTQ through L2 (>> 126 MB for the large contigs)'}
   return {'workload': 'configs[2]: chr1-shaped synthetic contig ({} bp, ~10% N, GIAB-density diploid VCF), 30x paired 2x150, '
                       'Philox mode{}'.format(args.contig_len, '' if args.perfect else ' + fused Illumina corruption'),
           'read_model': MODEL + ' (mean_rlen 150)', 'coverage': COVERAGE, 'units_per_step': 4, 'seed': args.seed,
@@ -223,30 +231,48 @@ def main():
   model = load_model(MODEL)
   rm = il.read_model_params(model, COVERAGE)
   L = int(rm['rlen'])
-  wl, region, r = make_workload(args, rank)
   stream = torch.cuda.Stream()
   eng = Engine(local, stream=stream.cuda_stream)
   eng.load_model(rm)
-  ref_host = torch.from_numpy(np.ascontiguousarray(wl['contigs'][0][1])).pin_memory()
-  ref_np = ref_host.numpy()
   corrupt = not args.perfect
+  # work items of this rank: (region, per-copy variants, pinned reference bytes)
+  if args.workload == 'wgs':
+    from mitty_b200 import multigpu, synth
+    from mitty_b200.lib import vcfio
+    mine = multigpu.assign_units([int(max(20000, n * args.scale)) for _, n in synth.GRCH37_CONTIGS], world)[rank]   # LPT by contig length
+    gw = synth.grch37_shaped(scale=args.scale, seed=args.seed, only=set(mine))
+    wl = gw
+    items = []
+    for (name, seq), vt, region in zip(gw['contigs'], gw['tables'], gw['regions']):
+      items.append((region, vcfio.from_variant_table(vt, region), torch.from_numpy(np.ascontiguousarray(seq)).pin_memory().numpy()))
+    max_len = max(it[0][2] for it in items)
+  else:
+    wl, region, r = make_workload(args, rank)
+    items = [(region, r, torch.from_numpy(np.ascontiguousarray(wl['contigs'][0][1])).pin_memory().numpy())]
+    max_len = args.contig_len
 
-  units = [(cpy, ps) for cpy in range(len(r['v'])) for ps in range(rm['passes'])]
-
-  def step(seed, rid, out=None, fetch=False):
-    """Both copies built from the region, then the 4 units. Returns (pairs, fastq bytes).
-    out: two pinned buffer pairs used alternately; the D2H of unit k overlaps the kernels of k+1."""
+  def step(seed, rids, out=None, fetch=False):
+    """Every item of this rank: its copies built from the (resident or just loaded) region, then
+    copies x passes work units.  Returns (pairs, fastq bytes).  out: two pinned buffer pairs used
+    alternately; the D2H of unit k overlaps the kernels of unit k+1."""
     pairs = nbytes = 0
-    copies = [eng.build_copy(rid, vl) for vl in r['v']]
-    for k, (cpy, ps) in enumerate(units):
-      _, _, cnt, _, nb = rg.generate_unit(eng, il, rm, copies[cpy], region[0], cpy, (seed * 7919 + k * 104729) & 0xFFFFFFFF,
-                                          wl['sample'], 0, k, mode='philox', corrupt=corrupt, corrupt_seed=seed,
-                                          out=out[k & 1] if out else None, fetch=fetch, wait=not fetch)
-      pairs += cnt; nbytes += 2 * nb
-    if fetch:
-      eng.wait_copies()
-    for cp in copies:
-      eng.free_copy(cp)
+    k = 0
+    for (region_, r_, ref_), rid in zip(items, rids):
+      if rid is None:
+        rid = eng.load_region(ref_, region_[1])
+      copies = [eng.build_copy(rid, vl) for vl in r_['v']]
+      for cpy in range(len(copies)):
+        for ps in range(rm['passes']):
+          _, _, cnt, _, nb = rg.generate_unit(eng, il, rm, copies[cpy], region_[0], cpy, (seed * 7919 + k * 104729) & 0xFFFFFFFF,
+                                              wl['sample'], 0, k, mode='philox', corrupt=corrupt, corrupt_seed=seed,
+                                              out=out[k & 1] if out else None, fetch=fetch, wait=not fetch)
+          pairs += cnt; nbytes += 2 * nb; k += 1
+      if fetch:
+        eng.wait_copies()
+      for cp in copies:
+        eng.free_copy(cp)
+      if fetch:
+        eng.free_region(rid)
     return pairs, nbytes
 
   def barrier():
@@ -256,9 +282,9 @@ def main():
       torch.cuda.synchronize()
 
   # ---- value: inputs resident in HBM, outputs stay in HBM
-  rid = eng.load_region(ref_np, region[1])
+  rids = [eng.load_region(ref_, region_[1]) for region_, _, ref_ in items]
   for w in range(args.warmup):
-    step(1000 + w, rid)
+    step(1000 + w, rids)
   barrier()
   eng.prof_reset()
   clocks = ClockSampler(local); clocks.start()
@@ -267,25 +293,23 @@ def main():
   with torch.cuda.stream(stream):
     ev0.record(stream)
     for s in range(args.steps):
-      p_, b_ = step(2000 + s, rid)
+      p_, b_ = step(2000 + s, rids)
       pairs += p_; nbytes += b_
     ev1.record(stream)
   barrier()
   ms = ev0.elapsed_time(ev1)
   clk = clocks.stop()
   prof = eng.prof()
-  eng.free_region(rid)
+  for rid in rids:
+    eng.free_region(rid)
 
   # ---- e2e: host buffers in, host buffers out
   e2e = None
   if not args.no_e2e:
-    est = int((args.contig_len * rm['p'] * 1.2) * (2 * L + 110)) + (1 << 20)
+    est = int((max_len * rm['p'] * 1.2) * (2 * L + 110)) + (1 << 20)
     out = [(eng.pinned(est), eng.pinned(est)) for _ in range(2)]
     def e2e_step(seed):
-      rid_ = eng.load_region(ref_np, region[1])
-      p_, b_ = step(seed, rid_, out=out, fetch=True)
-      eng.free_region(rid_)
-      return p_, b_
+      return step(seed, [None] * len(items), out=out, fetch=True)
     for w in range(min(args.warmup, 3)):
       e2e_step(3000 + w)
     barrier()
@@ -296,7 +320,7 @@ def main():
       ep += p_; eb += b_
     torch.cuda.synchronize()
     e_wall = time.perf_counter() - t0
-    h2d = ref_np.nbytes + sum(v.pos.nbytes + v.op.nbytes + v.oplen.nbytes + v.alt_pool.nbytes + v.alt_off.nbytes for v in r['v'])
+    h2d = sum(ref_.nbytes + sum(v.pos.nbytes + v.op.nbytes + v.oplen.nbytes + v.alt_pool.nbytes + v.alt_off.nbytes for v in r_['v']) for _, r_, ref_ in items)
     e2e = [ep, e_wall, h2d, eb / max(1, args.steps)]
 
   # ---- aggregate over ranks: max time, summed work
@@ -326,7 +350,7 @@ def main():
         traffic = None
     line = {'metric': 'read pairs/sec (2x150, FASTQ-formatted, corrupted)' if corrupt else 'read pairs/sec (2x150, FASTQ-formatted, perfect reads)',
             'value': pairs_all / (ms * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if args.workload == 'wgs' else 'weak', 'vs_baseline': None, 'dtype': 'u8',
             'data': 'synthetic', 'config': config_dict(args), 'clocks': clk,
             'gpu_launches': prof['total_launches'],
             'roofline': {'bound': 'hbm', 'kernel': 'k_unit_emit', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
@@ -341,7 +365,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
       import oracle
       oracle.build()
-      n, wall, sl = cpu_baseline(args, wl, 1)
+      n, wall, sl = cpu_baseline(args, wl if args.workload == 'chr1' else {'contigs': [wl['contigs'][0]], 'tables': [wl['tables'][0]]}, 1)
       line['cpu_baseline'] = {'value': n / wall, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port',
                               'sample': 'one {} Mb-slice work unit of the same contig (generate + corrupt, {} pairs), C oracle, 1 thread'.format(sl // 1000000, n)}
     print(json.dumps(line))

@@ -311,3 +311,21 @@ def edge_workload(seed=11):
   return {'contigs': [('e', e), ('f', f), ('g', g), ('h', h)], 'tables': [te, tf, tg, th],
           'regions': [('e', 1000, 14000), ('e', 15000, 29000), ('f', 0, 20000), ('g', 0, 8000), ('h', 0, 5000)],
           'sample': 'EDGE'}
+
+
+def grch37_shaped(scale=1.0, seed=7, per_mb=1330.0, n_frac=0.08, only=None):
+  """BASELINE.json configs[3]: 24 contigs with GRCh37 primary-assembly lengths (times ``scale``),
+  ~4 M variants at scale 1, autosomes diploid, X / Y haploid GT (docs/preparing_vcfs.rst:10-23),
+  N runs at the contig ends and inside (telomere / centromere-like gaps)."""
+  contigs, tables, regions = [], [], []
+  for k, (name, length) in enumerate(GRCH37_CONTIGS):
+    if only is not None and k not in only:   # a rank of a sharded run synthesises its own contigs only
+      continue
+    n = max(20000, int(length * scale))
+    runs = max(2, int(round(n / 6.0e6)))
+    seq = synth_contig(n, seed=seed * 1000 + k, n_frac=n_frac, n_run_min=min(10000, max(200, n // 200)), n_runs=runs)
+    ploidy = 1 if name in ('X', 'Y') else 2
+    vt = synth_variants(name, seq, 0, n, seed=seed * 1000 + 500 + k, per_mb=per_mb, ploidy=ploidy,
+                        long_ins=max(1, int(20 * n / 249250621)), end_margin=min(1000, n // 20))
+    contigs.append((name, seq)); tables.append(vt); regions.append((name, 0, n))
+  return {'contigs': contigs, 'tables': tables, 'regions': regions, 'sample': 'INTEGRATION'}

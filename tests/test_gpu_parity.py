@@ -250,3 +250,32 @@ def test_sharded_workers_identical_output(tmp_path, devices):
   rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model(info['model']), info['coverage'], q1, q2,
                             threads=1, seed=5, mode='philox', corrupt=True, devices=[0])
   assert open(p1, 'rb').read() == open(q1, 'rb').read() and open(p2, 'rb').read() == open(q2, 'rb').read()
+
+
+def test_grch37_shaped_deterministic(eng):
+  """BASELINE.json configs[3] at 1/500 scale: 24 GRCh37-shaped contigs with N runs, diploid
+  autosomes and haploid X / Y (46 copies, 92 units): deterministic mode == the oracle's
+  generate-reads + corrupt-reads, byte for byte."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readcorrupt as rc
+  from mitty_b200.engine import MODE_DET
+  wl = synth.grch37_shaped(scale=0.002)
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  regs = H.workload_regions(wl)
+  assert [len(r['v']) for r in regs] == [2] * 22 + [1, 1]
+  f1, f2, n = gpu_generate(eng, wl, m, 30.0, 7, 'deterministic', regions=regs)
+  o1, o2, on = oracle.generate_reads_cmd(H.oracle_regions(regs), m, 30.0, 7, wl['sample'])
+  assert n == on and n > 400000
+  assert H.sha256(f1) == H.sha256(o1) and H.sha256(f2) == H.sha256(o2)
+  # corrupt a slice of it in deterministic mode (the host-side MT draws are the slow part)
+  cut = f1.index(b'\n@', 20000000) + 1 if len(f1) > 20000000 else len(f1)
+  nrec = f1[:cut].count(b'\n') // 4
+  cut2 = len(b'\n'.join(f2.split(b'\n')[:4 * nrec])) + 1
+  a1, a2 = np.frombuffer(f1[:cut], dtype=np.uint8), np.frombuffer(f2[:cut2], dtype=np.uint8)
+  ws = int(np.random.RandomState(7).randint(il.SEED_MAX))
+  l1, l2 = rc.seq_lengths(a1), rc.seq_lengths(a2)
+  lens = np.empty(2 * l1.size, dtype=np.int64); lens[0::2] = l1; lens[1::2] = l2
+  eng.load_model(m)
+  c1, c2, cn = eng.corrupt_fastq(a1, a2, mode=MODE_DET, draws=il.corrupt_draws(lens.tolist(), np.random.RandomState(ws)))
+  w1, w2, wn = oracle.corrupt_fastq(m['cum_bq_mat'], ws, f1[:cut], f2[:cut2])
+  assert cn == wn == nrec and c1.tobytes() == w1 and c2.tobytes() == w2

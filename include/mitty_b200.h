@@ -121,11 +121,16 @@ int mg_wait_copies(mg_ctx *ctx);
 /* ---- corrupt-reads: replaces readcorrupt.multi_process / illumina.corrupt_template
  * (mitty/simulation/readcorrupt.py:18-118, illumina.py:113-162) over whole FASTQ buffers.
  * in2/out2 may be NULL (single-end).  DET mode consumes the reference's draws: for read k (file-1
- * read then file-2 read of each template) bq_rnd/call_rnd/base_rnd[draw_off[k] + cycle].          */
+ * read then file-2 read of each template) bq_rnd/call_rnd/base_rnd[draw_off[k] + cycle].
+ * Large files are streamed in chunks: only COMPLETE templates present in both buffers are
+ * processed; consumed1/2 = input bytes they occupied (carry the rest into the next call) and
+ * first_template = number of templates processed by earlier calls (keeps the Philox counters,
+ * hence the output, independent of the chunking).                                                */
 int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_t *in2, int64_t len2, int32_t mode,
                      uint32_t seed, const double *bq_rnd, const double *call_rnd, const uint8_t *base_rnd,
                      const int64_t *draw_off, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *out_len1,
-                     int64_t *out_len2, int64_t *n_templates);
+                     int64_t *out_len2, int64_t *n_templates, int64_t first_template, int64_t *consumed1,
+                     int64_t *consumed2);
 
 /* ---- profiling: device time (CUDA events on the launch stream) of the emit / corrupt kernel
  * (emit_ms over emit_launches launches, emit_bytes written) and of the planning kernel (plan_ms);

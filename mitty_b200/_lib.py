@@ -85,7 +85,8 @@ def lib():
     L.mg_wait_copies.argtypes = [C.c_void_p]
     L.mg_corrupt_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_uint32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mg_prof_reset.argtypes = [C.c_void_p]
     L.mg_prof_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     _lib = L

@@ -749,8 +749,11 @@ int mg_wait_copies(mg_ctx *ctx) {
 int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_t *in2, int64_t len2, int32_t mode,
                      uint32_t seed, const double *bq_rnd, const double *call_rnd, const uint8_t *base_rnd,
                      const int64_t *draw_off, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *out_len1,
-                     int64_t *out_len2, int64_t *n_templates) {
+                     int64_t *out_len2, int64_t *n_templates, int64_t first_template, int64_t *consumed1,
+                     int64_t *consumed2) {
   if (!ctx || !in1 || len1 < 0 || (in2 && len2 < 0)) return fail(ctx, MG_EINVAL, "mg_corrupt_fastq: bad arguments");
+  if (consumed1) *consumed1 = 0;
+  if (consumed2) *consumed2 = 0;
   if (ctx->rlen == 0) return fail(ctx, MG_EINVAL, "no read model loaded (mg_model_load)");
   if (mode != MG_MODE_PHILOX && mode != MG_MODE_DET) return fail(ctx, MG_EINVAL, "unknown mode %d", mode);
   DeviceGuard g(ctx->device);
@@ -788,6 +791,15 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
   if (out_len2) *out_len2 = 0;
   if (n_templates) *n_templates = n_rec;
   if (n_rec == 0) return MG_OK;
+  P.first = first_template;
+  {  // bytes of each input that belong to the n_rec complete templates (the caller streams a large
+     // file in chunks and carries the rest over)
+    int64_t last[2] = {0, 0};
+    for (int f = 0; f < nf; f++) CU(cudaMemcpyAsync(&last[f], P.nl[f] + (4 * n_rec - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (consumed1) *consumed1 = last[0] + 1;
+    if (consumed2 && nf > 1) *consumed2 = last[1] + 1;
+  }
 
   CU(ctx->s_state.need(64));
   P.err = ctx->s_state.as<unsigned long long>();

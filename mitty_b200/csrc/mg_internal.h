@@ -64,6 +64,7 @@ struct MgCorruptParams {     // standalone corrupt-reads over FASTQ resident in 
   const int64_t *nl[2];      // newline positions of each input file
   const int64_t *out_off[2]; // output record offsets [n_rec + 1]
   int64_t n_rec; int n_files;
+  int64_t first;             // index of the first template of this buffer in the whole file (Philox counter)
   const double *cum_bq; int n_cycles, n_bq; const double *phred;
   int mode;                  // MG_MODE_PHILOX / MG_MODE_DET
   MgCorruptCtx cor;          // PHILOX: alias tables + keys

@@ -763,7 +763,8 @@ __global__ void __launch_bounds__(256) k_corrupt(MgCorruptParams P) {
         }
       } else {
         for (int pr = lane; 2 * pr < L; pr += 32) {
-          const MgPhilox rr = mg_philox_corrupt((uint32_t)r, (uint32_t)(r >> 32) * 2u + (uint32_t)f, (uint32_t)pr, P.cor.k0, P.cor.k1);
+          const int64_t gr = P.first + r;   // template index in the whole file
+          const MgPhilox rr = mg_philox_corrupt((uint32_t)gr, (uint32_t)(gr >> 32) * 2u + (uint32_t)f, (uint32_t)pr, P.cor.k0, P.cor.k1);
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             const int n = 2 * pr + h;

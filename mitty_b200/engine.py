@@ -190,19 +190,27 @@ class Engine(object):
     self._check(self._L.mg_wait_copies(self._h))
 
   # -- corruption --------------------------------------------------------------------------------
-  def corrupt_fastq(self, fq1, fq2=None, mode=MODE_PHILOX, seed=0, draws=None):
+  def corrupt_fastq(self, fq1, fq2=None, mode=MODE_PHILOX, seed=0, draws=None, first_template=0, out=None, partial=False):
     """Whole-buffer corrupt-reads.  fq1/fq2: bytes or uint8 arrays of 4-line FASTQ records.
-    draws (deterministic mode): (bq_rnd f64, call_rnd f64, base_rnd u8, draw_off i64[n_reads+1])."""
+    draws (deterministic mode): (bq_rnd f64, call_rnd f64, base_rnd u8, draw_off i64[n_reads+1]).
+    partial=True (chunked streaming): only the complete templates present in both buffers are
+    processed and the consumed input byte counts are returned as a 4th / 5th value; first_template =
+    templates processed by earlier chunks.  out: optional (pinned) output buffer pair."""
     a1 = np.frombuffer(fq1, dtype=np.uint8) if not isinstance(fq1, np.ndarray) else fq1
     a2 = None if fq2 is None else (np.frombuffer(fq2, dtype=np.uint8) if not isinstance(fq2, np.ndarray) else fq2)
-    if a1.size and a1[-1] != 10:
-      a1 = np.concatenate([a1, np.array([10], dtype=np.uint8)])
-    if a2 is not None and a2.size and a2[-1] != 10:
-      a2 = np.concatenate([a2, np.array([10], dtype=np.uint8)])
+    if not partial:
+      if a1.size and a1[-1] != 10:
+        a1 = np.concatenate([a1, np.array([10], dtype=np.uint8)])
+      if a2 is not None and a2.size and a2[-1] != 10:
+        a2 = np.concatenate([a2, np.array([10], dtype=np.uint8)])
     cap = int(a1.size + (a2.size if a2 is not None else 0)) + 64
-    o1 = np.empty(cap, dtype=np.uint8)
-    o2 = np.empty(cap, dtype=np.uint8) if a2 is not None else None
-    l1, l2, nt = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    if out is not None:
+      o1, o2 = out
+      cap = min(o1.size, o2.size) if a2 is not None else o1.size
+    else:
+      o1 = np.empty(cap, dtype=np.uint8)
+      o2 = np.empty(cap, dtype=np.uint8) if a2 is not None else None
+    l1, l2, nt, c1, c2 = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
     bq = call = base = off = None
     if mode == MODE_DET:
       bq, call, base, off = draws
@@ -211,8 +219,10 @@ class Engine(object):
     self._check(self._L.mg_corrupt_fastq(self._h, _ptr(a1) if a1.size else _ptr(np.zeros(1, np.uint8)), a1.size,
                                          _ptr(a2) if a2 is not None else None, a2.size if a2 is not None else 0,
                                          int(mode), int(seed) & 0xFFFFFFFF, _ptr(bq), _ptr(call), _ptr(base), _ptr(off),
-                                         _ptr(o1), _ptr(o2), cap, C.byref(l1), C.byref(l2), C.byref(nt)))
-    return o1[:l1.value], (o2[:l2.value] if o2 is not None else None), nt.value
+                                         _ptr(o1), _ptr(o2) if a2 is not None else None, cap, C.byref(l1), C.byref(l2), C.byref(nt),
+                                         int(first_template), C.byref(c1), C.byref(c2)))
+    res = (o1[:l1.value], (o2[:l2.value] if a2 is not None else None), nt.value)
+    return res + (c1.value, c2.value) if partial else res
 
   # -- profiling ---------------------------------------------------------------------------------
   def prof_reset(self):

@@ -38,39 +38,90 @@ def seq_lengths(buf):
   return (nl[1:4 * n_rec:4] - nl[0:4 * n_rec:4] - 1).astype(np.int64)
 
 
+class _Stream(object):
+  """A FASTQ file read in chunks into one (pinned) buffer; the unconsumed tail is carried over."""
+
+  def __init__(self, fname, buf):
+    import gzip
+    with open(fname, 'rb') as fp:
+      magic = fp.read(2)
+    self.fp = gzip.open(fname, 'rb') if magic == b'\x1f\x8b' else open(fname, 'rb')
+    self.buf, self.fill, self.eof = buf, 0, False
+
+  def refill(self):
+    mv = memoryview(self.buf)
+    while self.fill < self.buf.size and not self.eof:
+      n = self.fp.readinto(mv[self.fill:])
+      if not n:
+        self.eof = True
+        if self.fill and self.buf[self.fill - 1] != 10 and self.fill < self.buf.size:
+          self.buf[self.fill] = 10; self.fill += 1           # last line without a newline
+      else:
+        self.fill += n
+
+  def consume(self, n):
+    rest = self.fill - n
+    if rest:
+      self.buf[:rest] = self.buf[n:self.fill].copy()
+    self.fill = rest
+
+
 def multi_process(read_module, read_model, fastq1_in, fastq1_out, fastq2_in=None, fastq2_out=None, processes=2, seed=7,
-                  mode='philox', device=0):
+                  mode='philox', device=0, chunk_bytes=256 << 20):
   """Same signature as the reference (readcorrupt.py:18) plus keyword-only extras.  ``processes``
   is accepted for command-line compatibility (one GPU does all the work).  Note the reference
-  passes the RAW model dict here (cli.py:155-157), and so does the CLI of this package."""
+  passes the RAW model dict here (cli.py:155-157), and so does the CLI of this package.
+
+  The files are streamed in chunks through pinned buffers: the device indexes the records of each
+  chunk, corrupts the complete templates and reports how many input bytes they occupied; the rest
+  is carried into the next chunk.  The output does not depend on the chunk size."""
   t0 = time.time()
   engine = Engine(device)
+  cnt = 0
   try:
-    a1 = _read(fastq1_in)
-    a2 = _read(fastq2_in) if fastq2_in is not None else None
-    if a1.size and a1[-1] != 10:
-      a1 = np.concatenate([a1, np.array([10], dtype=np.uint8)])
-    if a2 is not None and a2.size and a2[-1] != 10:
-      a2 = np.concatenate([a2, np.array([10], dtype=np.uint8)])
     rlen = read_model['mean_rlen'] if 'mean_rlen' in read_model else read_model['rlen']
     engine.load_model(read_model, rlen=rlen)
-    draws = None
+    paired = fastq2_in is not None
+    ins = [_Stream(fastq1_in, engine.pinned(chunk_bytes))] + ([_Stream(fastq2_in, engine.pinned(chunk_bytes))] if paired else [])
+    outs = (engine.pinned(2 * chunk_bytes + 64), engine.pinned(2 * chunk_bytes + 64) if paired else None)
+    rng = None
     if mode == 'deterministic':
       worker_seed = np.random.RandomState(seed).randint(SEED_MAX)   # worker 0, readcorrupt.py:31,36
-      l1 = seq_lengths(a1)
-      if a2 is not None:
-        l2 = seq_lengths(a2)
-        n = min(l1.size, l2.size)
-        lens = np.empty(2 * n, dtype=np.int64); lens[0::2] = l1[:n]; lens[1::2] = l2[:n]
-      else:
-        lens = l1
-      draws = read_module.corrupt_draws(lens.tolist(), np.random.RandomState(worker_seed))
-    o1, o2, cnt = engine.corrupt_fastq(a1, a2, mode=MODE_DET if mode == 'deterministic' else MODE_PHILOX, seed=seed, draws=draws)
-    with open(fastq1_out, 'wb') as fp:
-      fp.write(memoryview(o1))
-    if fastq2_out is not None and o2 is not None:
-      with open(fastq2_out, 'wb') as fp:
-        fp.write(memoryview(o2))
+      rng = np.random.RandomState(worker_seed)
+    fps = [open(fastq1_out, 'wb')] + ([open(fastq2_out, 'wb')] if paired and fastq2_out is not None else [])
+    try:
+      while True:
+        for st in ins:
+          st.refill()
+        a1 = ins[0].buf[:ins[0].fill]
+        a2 = ins[1].buf[:ins[1].fill] if paired else None
+        if a1.size == 0 or (paired and a2.size == 0):
+          break
+        draws = None
+        if rng is not None:
+          l1 = seq_lengths(a1)
+          if paired:
+            l2 = seq_lengths(a2)
+            n = min(l1.size, l2.size)
+            lens = np.empty(2 * n, dtype=np.int64); lens[0::2] = l1[:n]; lens[1::2] = l2[:n]
+          else:
+            lens = l1
+          draws = read_module.corrupt_draws(lens.tolist(), rng)
+        o1, o2, n, c1, c2 = engine.corrupt_fastq(a1, a2, mode=MODE_DET if rng is not None else MODE_PHILOX, seed=seed, draws=draws,
+                                                 first_template=cnt, out=outs, partial=True)
+        if n == 0:
+          if all(st.eof for st in ins):
+            break
+          raise ValueError('a FASTQ record is larger than the chunk size ({} bytes)'.format(chunk_bytes))
+        for fp, o in zip(fps, (o1, o2)):
+          fp.write(memoryview(o))
+        ins[0].consume(c1)
+        if paired:
+          ins[1].consume(c2)
+        cnt += n
+    finally:
+      for fp in fps:
+        fp.close()
   finally:
     engine.close()
   t1 = time.time()

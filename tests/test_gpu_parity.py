@@ -279,3 +279,31 @@ def test_grch37_shaped_deterministic(eng):
   c1, c2, cn = eng.corrupt_fastq(a1, a2, mode=MODE_DET, draws=il.corrupt_draws(lens.tolist(), np.random.RandomState(ws)))
   w1, w2, wn = oracle.corrupt_fastq(m['cum_bq_mat'], ws, f1[:cut], f2[:cut2])
   assert cn == wn == nrec and c1.tobytes() == w1 and c2.tobytes() == w2
+
+
+@pytest.mark.parametrize('chunk', [1 << 20, 70000, 256 << 20])
+def test_corrupt_reads_streaming_chunks(tmp_path, chunk):
+  """corrupt-reads streams its inputs in chunks (the device reports the bytes the complete
+  templates occupied, the rest is carried over): the result must not depend on the chunk size, in
+  deterministic mode (== the reference golden) and in production mode (== one big chunk)."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readcorrupt as rc
+  info = H.golden()['fastq']['edge']
+  m = H.model(info['model'])
+  r1, r2 = str(tmp_path / 'r1.fq'), str(tmp_path / 'r2.fq.gz')
+  open(r1, 'wb').write(H.golden_fastq('edge.r1.fq.gz'))
+  import gzip
+  with gzip.open(r2, 'wb') as fp:                       # one plain, one gzip input
+    fp.write(H.golden_fastq('edge.r2.fq.gz'))
+  c1, c2 = str(tmp_path / 'c1.fq'), str(tmp_path / 'c2.fq')
+  rc.multi_process(il, m, r1, c1, r2, c2, processes=1, seed=info['seed'], mode='deterministic', chunk_bytes=chunk)
+  assert open(c1, 'rb').read() == H.golden_fastq('edge.c1.fq.gz') and open(c2, 'rb').read() == H.golden_fastq('edge.c2.fq.gz')
+  p1, p2 = str(tmp_path / 'p1.fq'), str(tmp_path / 'p2.fq')
+  rc.multi_process(il, m, r1, p1, r2, p2, processes=1, seed=3, mode='philox', chunk_bytes=chunk)
+  q1, q2 = str(tmp_path / 'q1.fq'), str(tmp_path / 'q2.fq')
+  rc.multi_process(il, m, r1, q1, r2, q2, processes=1, seed=3, mode='philox', chunk_bytes=64 << 20)
+  assert open(p1, 'rb').read() == open(q1, 'rb').read() and open(p2, 'rb').read() == open(q2, 'rb').read()
+  # single-end
+  s1 = str(tmp_path / 's1.fq')
+  rc.multi_process(il, m, r1, s1, None, None, processes=1, seed=3, mode='philox', chunk_bytes=chunk)
+  assert open(s1, 'rb').read() == open(q1, 'rb').read()

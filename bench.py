@@ -67,7 +67,12 @@ class ClockSampler(object):
 
   def _read(self):
     for line in self.p.stdout:
-      self.rows.append([x.strip() for x in line.split(',')])
+      self.rows.append((time.perf_counter(), [x.strip() for x in line.split(',')]))
+
+  def mark(self):
+    """start of the timed region (the sampler itself is started before the warm-up: nvidia-smi takes
+    longer to start than a short timed region lasts)"""
+    self.t_mark = time.perf_counter()
 
   def stop(self):
     if self.p is None:
@@ -78,7 +83,11 @@ class ClockSampler(object):
     except Exception:
       self.p.kill()
     sm, mx, reasons = [], [], set()
-    for r in self.rows:
+    rows = [r for t, r in self.rows if t >= getattr(self, 't_mark', 0.0)]
+    window = 'timed region'
+    if not rows:   # no sample fell into a very short timed region: use the warm-up samples (same load)
+      rows, window = [r for t, r in self.rows], 'warm-up + timed region'
+    for r in rows:
       try:
         sm.append(float(r[1])); mx.append(float(r[2]))
         for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
@@ -87,7 +96,7 @@ class ClockSampler(object):
       except Exception:
         pass
     return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-            'reasons': sorted(reasons), 'samples': len(sm)}
+            'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 def measured_peak():
@@ -283,11 +292,12 @@ def main():
 
   # ---- value: inputs resident in HBM, outputs stay in HBM
   rids = [eng.load_region(ref_, region_[1]) for region_, _, ref_ in items]
+  clocks = ClockSampler(local); clocks.start()
   for w in range(args.warmup):
     step(1000 + w, rids)
   barrier()
   eng.prof_reset()
-  clocks = ClockSampler(local); clocks.start()
+  clocks.mark()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   pairs = nbytes = 0
   with torch.cuda.stream(stream):

@@ -263,7 +263,8 @@ def edge_workload(seed=11):
     SNP+INS and INS+SNP at the same POS,
   * an N run and N triplets (the ``> 2 N`` template drop, readgenerate.py:204),
   * long insertions (the '>p:nI' CIGAR), dense variants (multi-node reads),
-  * triploid, haploid and variant-free (assumed diploid, vcfio.py:74-76) regions.
+  * triploid, haploid and variant-free (assumed diploid, vcfio.py:74-76) regions,
+  * a soft-masked (lower-case) run, IUPAC codes and lower-case 'n' in the variant-free contig.
   """
   rng = np.random.RandomState(seed)
 
@@ -307,6 +308,12 @@ def edge_workload(seed=11):
   g = seq_of(8000, 2)
   tg = synth_variants('g', g, 0, 8000, seed=seed * 100 + 52, per_mb=3000.0, ploidy=1, long_ins=0, min_gap=15, end_margin=100)
   h = seq_of(5000, 3)
+  # soft-masked and IUPAC bases: copied verbatim, not complemented on the reverse strand
+  # (rpc.py:21 translate table covers ATCGN only), lower-case 'n' not counted by seq.count('N')
+  h[1000:1400] += 32
+  h[2000:2003] = np.frombuffer(b'RYM', np.uint8)
+  h[3000] = ord('K')
+  h[4000:4004] = ord('n')
   th = _empty_table('h', 2)
   return {'contigs': [('e', e), ('f', f), ('g', g), ('h', h)], 'tables': [te, tf, tg, th],
           'regions': [('e', 1000, 14000), ('e', 15000, 29000), ('f', 0, 20000), ('g', 0, 8000), ('h', 0, 5000)],

@@ -183,6 +183,11 @@ def main():
 
   c1 = synth.config1()
   p, info = run_pair(c1, tmp, 'config1', 'hiseq-X-v2.5-Garvan.pkl', corrupt=full)
+  if not full and os.path.exists(os.path.join(HERE, 'golden.json')):
+    # keep the corrupted-file hashes of an earlier --full run while the perfect files are unchanged
+    old = json.load(open(os.path.join(HERE, 'golden.json')))['fastq'].get('config1', {})
+    if all(old.get(k) == info[k] for k in ('r1', 'r2')):
+      info.update({k: old[k] for k in ('c1', 'c2') if k in old})
   files['config1'] = info
   G['fastq'] = files
 

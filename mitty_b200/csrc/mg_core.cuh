@@ -255,6 +255,7 @@ struct MgCountWriter {
 // store is a plain STS (generic 64-bit pointers cost 3-4 instructions per store).  MgGenericSpace
 // is any memory: host emulation, and the rare record that is larger than the stage.
 struct MgGenericSpace {
+  static constexpr bool is_generic = true;
   typedef uint8_t *ptr;
   static MG_HD void st8(ptr p, uint8_t v) { *p = v; }
   static MG_HD void st32(ptr p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
@@ -263,11 +264,17 @@ struct MgGenericSpace {
 };
 #if defined(__CUDACC__)
 struct MgSharedSpace {
-  typedef uint32_t ptr;   // byte offset into the dynamic shared memory of the running kernel
-  static __device__ __forceinline__ uint8_t *base() { extern __shared__ __align__(16) uint8_t mg_dyn_smem[]; return mg_dyn_smem; }
-  static __device__ __forceinline__ void st8(ptr p, uint8_t v) { base()[p] = v; }
-  static __device__ __forceinline__ void st32(ptr p, uint32_t v) { *reinterpret_cast<uint32_t *>(base() + p) = v; }
-  static __device__ __forceinline__ uint32_t ld32(ptr p) { return *reinterpret_cast<const uint32_t *>(base() + p); }
+  static constexpr bool is_generic = false;
+  // a byte address in the shared window (cvta.to.shared of the kernel's stage): plain 32-bit
+  // st.shared / ld.shared with no generic-address arithmetic at the use sites
+  typedef uint32_t ptr;
+  static __device__ __forceinline__ void st8(ptr p, uint8_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(p), "r"((uint32_t)v)); }
+  static __device__ __forceinline__ void st32(ptr p, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(p), "r"(v)); }
+  static __device__ __forceinline__ uint32_t ld32(ptr p) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(p));
+    return v;
+  }
   static __device__ __forceinline__ uint32_t low2(ptr p) { return p & 3u; }
 };
 #endif
@@ -290,29 +297,29 @@ template <class SP>
 struct MgWordStream {
   static constexpr bool is_bytes = false;
   typename SP::ptr wp;   // next aligned word
-  uint32_t carry;        // pending bytes, low nb bytes valid
-  uint32_t nb;           // pending byte count 0..3
+  uint32_t prev;         // the pending bytes are the TOP sh / 8 bytes of prev
+  uint32_t sh;           // 8 * pending byte count: 0, 8, 16 or 24
 
   // The bytes before dst inside its word were written earlier BY THIS THREAD (the tail of its own
   // qname / separator): they are read back and carried, so every flush is a plain word store.
   MG_HD void begin_rmw(typename SP::ptr dst) {
     const uint32_t a = SP::low2(dst);
     wp = dst - a;
-    nb = a;
-    carry = a ? (SP::ld32(wp) & (0xFFFFFFFFu >> (32 - 8 * a))) : 0u;
+    sh = 8 * a;
+    prev = a ? (SP::ld32(wp) << (32 - sh)) : 0u;
   }
   MG_HD void flush_word(uint32_t w) { SP::st32(wp, w); wp += 4; }
   MG_HD void put(uint8_t c) {
-    carry |= (uint32_t)c << (8 * nb);
-    if (++nb == 4) { flush_word(carry); carry = 0; nb = 0; }
+    prev = (prev >> 8) | ((uint32_t)c << 24);
+    sh += 8;
+    if (sh == 32) { flush_word(prev); sh = 0; }
   }
-  MG_HD void put_word(uint32_t w) {  // four bytes, little-endian order; branch-free in nb
-    const uint32_t sh = 8 * nb;
-    flush_word(carry | (w << sh));           // nb == 0: carry is 0 and sh is 0
-    carry = mg_funnel_l(w, 0u, sh);          // the top nb bytes of w (0 when nb == 0)
+  MG_HD void put_word(uint32_t w) {  // four bytes, little-endian order: one funnel shift, one store
+    flush_word(mg_funnel_l(prev, w, sh));    // (w << sh) | (prev >> (32 - sh)); sh == 0 gives w
+    prev = w;
   }
   // the last partial word is shared with the NEXT record (another thread): byte stores
-  MG_HD void end() { mg_store_tail<SP>(wp, carry, nb); nb = 0; }
+  MG_HD void end() { if (sh) mg_store_tail<SP>(wp, prev >> (32 - sh), sh >> 3); sh = 0; }
 };
 
 // decimal digits of v at p (byte stores), returns the advanced pointer
@@ -754,7 +761,14 @@ struct MgCorruptCtx {
   const MgErr *err;        // [128]
   int kshift, n_cycles;
   uint32_t k0, k1;
+  uint32_t thr_s;          // device hot path: shared-window address of a u32[128] copy of err[].thr
 };
+
+// which of the three alternatives: w_call is uniform on [0, thr) given an error
+MG_HD uint32_t mg_sub_index(uint32_t w_call, uint32_t thr) {
+  const uint32_t q = thr / 3u, r = thr - 3u * q;          // floor(2 thr / 3) = 2 q + (r == 2), without 64-bit arithmetic
+  return (uint32_t)(w_call >= q) + (uint32_t)(w_call >= 2u * q + (r >> 1));
+}
 
 // -> bit 2 = substitution happened, bits 0-1 = which of the three alternatives; qual = ASCII quality
 MG_HD uint32_t mg_corrupt_finish(const MgCorruptCtx &C, uint32_t w_bq, uint32_t e, uint32_t w_call, uint32_t &qual) {
@@ -762,9 +776,9 @@ MG_HD uint32_t mg_corrupt_finish(const MgCorruptCtx &C, uint32_t w_bq, uint32_t 
   const uint32_t frac = (w_bq << C.kshift) >> 8;
   const uint32_t bq = frac < (e >> 7) ? idx : (e & 127u);
   qual = bq + 33u;
-  if (w_call >= C.err[bq].thr) return 0u;                     // the common case: one load, one compare
-  const MgErr t = C.err[bq];
-  return 4u | ((uint32_t)(w_call >= t.t1) + (uint32_t)(w_call >= t.t2));
+  const uint32_t thr = C.err[bq].thr;
+  if (w_call >= thr) return 0u;
+  return 4u | mg_sub_index(w_call, thr);
 }
 
 MG_HD uint32_t mg_corrupt_draw(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &qual) {
@@ -780,34 +794,66 @@ MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_b
 // base_rot on 2-bit codes (A=0 C=1 G=2 T=3): A->CTG, C->ATG, G->ACT, T->ACG as 2-bit triples
 #define MG_ROT_TBL (45u | (44u << 6) | (52u << 12) | (36u << 18))
 
+template <bool ES>
+MG_HD uint32_t mg_err_thr(const MgCorruptCtx &C, uint32_t bq) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (ES) {
+    uint32_t v;
+    asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(C.thr_s + 4u * bq));   // the table is read-only while the kernel runs
+    return v;
+  }
+#endif
+  return C.err[bq].thr;
+}
+
 // four bases (chunk word q, first base index n0) corrupted on the 2-bit codes -> new codes + ASCII
-// qualities.  Both Philox blocks are generated first and the four alias loads are issued
+// qualities, in two steps so that the caller can put independent work between the table loads and
+// their first use.  Both Philox blocks are generated first and the four alias loads are issued
 // together, so their (L2) latencies overlap; cycles >= L read a valid row and are masked out.
-template <bool FULL>   // FULL: all four cycles are inside the read (n0 + 4 <= L), no per-base bounds logic
-MG_HD void mg_corrupt4(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, uint32_t &b4, uint32_t &qw) {
+// The four error tests feed ONE branch: substitutions are handled out of the main line.
+struct MgDraw4 { uint32_t wb[4], wc[4], e[4]; };
+
+template <bool FULL>   // FULL: all four cycles are inside the read (n0 + 4 <= L)
+MG_HD void mg_corrupt4_draw(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, MgDraw4 &D) {
   const MgPhilox r0 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1), C.k0, C.k1);
   const MgPhilox r1 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1) + 1u, C.k0, C.k1);
-  const uint32_t wb[4] = {r0.v[0], r0.v[2], r1.v[0], r1.v[2]};
-  const uint32_t wc[4] = {r0.v[1], r0.v[3], r1.v[1], r1.v[3]};
-  const uint32_t *row = C.alias + ((f * (uint32_t)C.n_cycles + (uint32_t)n0) << C.kshift);
-  uint32_t e[4];
+  D.wb[0] = r0.v[0]; D.wb[1] = r0.v[2]; D.wb[2] = r1.v[0]; D.wb[3] = r1.v[2];
+  D.wc[0] = r0.v[1]; D.wc[1] = r0.v[3]; D.wc[2] = r1.v[1]; D.wc[3] = r1.v[3];
+  const uint32_t ks = (uint32_t)C.kshift;
+  const uint32_t row = (f * (uint32_t)C.n_cycles + (uint32_t)n0) << ks;   // 32-bit index arithmetic: one IMAD.WIDE per load
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
     const uint32_t nj = (FULL || n0 + j < L) ? (uint32_t)j : 0u;            // stay inside the table at the read's end
-    e[j] = row[(nj << C.kshift) | (wb[j] >> (32 - C.kshift))];
+    D.e[j] = C.alias[row + (nj << ks) + (D.wb[j] >> (32u - ks))];
   }
-  qw = 0;
+}
+
+template <bool FULL, bool ES>   // ES: error thresholds staged in shared memory (k_unit_emit)
+MG_HD void mg_corrupt4_apply(const MgCorruptCtx &C, const MgDraw4 &D, int n0, int L, uint32_t &b4, uint32_t &qw) {
+  const uint32_t ks = (uint32_t)C.kshift;
+  uint32_t bq[4], thr[4], any = 0;
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
-    uint32_t qual;
-    const uint32_t d = mg_corrupt_finish(C, wb[j], e[j], wc[j], qual);
-    if (FULL || n0 + j < L) {
-      if (d) {
+    const uint32_t frac = (D.wb[j] << ks) >> 8;
+    bq[j] = frac < (D.e[j] >> 7) ? (D.wb[j] >> (32u - ks)) : (D.e[j] & 127u);
+    thr[j] = mg_err_thr<ES>(C, bq[j]);
+    any |= (uint32_t)(D.wc[j] < thr[j] && (FULL || n0 + j < L)) << j;
+  }
+  if (FULL) {
+    qw = (bq[0] + (bq[1] << 8)) + ((bq[2] + (bq[3] << 8)) << 16) + 0x21212121u;
+  } else {
+    qw = 0;
+    MG_UNROLL
+    for (int j = 0; j < 4; j++) if (n0 + j < L) qw |= (bq[j] + 33u) << (8 * j);
+  }
+  if (any) {
+    MG_UNROLL
+    for (int j = 0; j < 4; j++) {
+      if (any & (1u << j)) {
         const uint32_t code = (b4 >> (2 * j)) & 3u;
-        const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * (d & 3u))) & 3u;
+        const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * mg_sub_index(D.wc[j], thr[j]))) & 3u;
         b4 ^= (code ^ nc) << (2 * j);
       }
-      qw |= qual << (8 * j);
     }
   }
 }
@@ -819,25 +865,36 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
                                const MgCorruptCtx &C, uint32_t serial, uint32_t f) {
   const int L = S.L;
   const struct { uint32_t x; int strand; } mine = {S.x, S.strand};
+  constexpr bool ES = !SP::is_generic;   // staged in shared memory <=> running in k_unit_emit with the threshold table staged too
   MgWordStream<SP> ws, wq;
   ws.begin_rmw(seq_dst); wq.begin_rmw(qual_dst);
+  // the output of a group is written one group late, between the next group's table loads and
+  // their first use: about 25 independent instructions under the L2 latency
+  uint32_t pb4 = 0, pqw = 0;
+  bool pend = false;
   mg_for_each_chunk(S, [&](uint32_t codes, int c) {
     MG_NOUNROLL
     for (int q = 0; q < 4; q++) {
       const int n0 = 16 * c + 4 * q;
       if (n0 < L) {
         uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw;
+        MgDraw4 D;
         if (n0 + 4 <= L) {
-          mg_corrupt4<true>(C, serial, f, n0, L, b4, qw);
-          ws.put_word(mg_chars4(b4)); wq.put_word(qw);
+          mg_corrupt4_draw<true>(C, serial, f, n0, L, D);
+          if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
+          mg_corrupt4_apply<true, ES>(C, D, n0, L, b4, qw);
+          pb4 = b4; pqw = qw; pend = true;
         } else {
-          mg_corrupt4<false>(C, serial, f, n0, L, b4, qw);
+          if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); pend = false; }
+          mg_corrupt4_draw<false>(C, serial, f, n0, L, D);
+          mg_corrupt4_apply<false, ES>(C, D, n0, L, b4, qw);
           const uint32_t ch = mg_chars4(b4);
           for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
         }
       }
     }
   });
+  if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
   ws.end(); wq.end();
   if (n_exc) {
     // bases in exception runs: the reference substitutes 'N' for any non-ACGT base on an error

@@ -464,14 +464,14 @@ void mg_launch_plan(const MgUnitParams &P, cudaStream_t st) {
 // a record larger than the whole stage (only possible with absurdly long CIGARs): straight to
 // global memory through generic pointers, streaming sequence source; cold and out of line
 template <bool CORRUPT>
-__device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const MgUnitParams &P, const MgCorruptCtx &cor,
+__device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const MgUnitParams &P,
                                            unsigned long long cnt, MgReadRef first, MgReadRef second, MgReadRef mine, int f) {
   const int L = P.rlen;
   MgSeqSrc<0, const uint32_t *> S;
   S.load(P.hap, mine.x, L, mine.strand);
   if constexpr (CORRUPT) {
     mg_emit_frame<MgGenericSpace>(dst, qlen, P.prefix, P.prefix_len, cnt, P.mid, P.mid_len, P.nodes, first, second, L);
-    mg_emit_seq_corrupt<MgGenericSpace>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)(cnt - 1), (uint32_t)f);
+    mg_emit_seq_corrupt<MgGenericSpace>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, P.cor, (uint32_t)(cnt - 1), (uint32_t)f);
   } else {
     mg_emit_record<MgGenericSpace>(dst, qlen, P.prefix, P.prefix_len, cnt, P.mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
   }
@@ -481,13 +481,19 @@ template <int MAXW, bool CORRUPT>
 __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
-  __shared__ MgErr s_err[CORRUPT ? 128 : 1];
+  __shared__ uint32_t s_thr[CORRUPT ? 128 : 1];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const uint32_t stage_off = (uint32_t)wid * (uint32_t)(P.stage_cap + 16);   // this warp's stage, as an offset into smem
-  uint8_t *stage = smem + stage_off;
+  uint8_t *stage = smem + (uint32_t)wid * (uint32_t)(P.stage_cap + 16);      // this warp's stage
+  // its shared-window address, pinned in a register (the compiler would otherwise rebuild it at every store)
+  uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  asm volatile("" : "+r"(stage_s));
   const int L = P.rlen;
   MgCorruptCtx cor = P.cor;
-  if constexpr (CORRUPT) { s_err[t & 127] = P.cor.err[t & 127]; cor.err = s_err; }   // error thresholds: 2 KB, shared memory
+  if constexpr (CORRUPT) {                                                   // error thresholds: 512 B of shared memory
+    s_thr[t & 127] = P.cor.err[t & 127].thr;
+    cor.thr_s = (uint32_t)__cvta_generic_to_shared(s_thr);
+    asm volatile("" : "+r"(cor.thr_s));
+  }
 #pragma unroll 1
   for (int i = t; i < P.prefix_len; i += MG_CTA) s_prefix[i] = P.prefix[i];
 #pragma unroll 1
@@ -530,7 +536,7 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
         if (mine) {
           if (f >= 0) {
             if (!oversize) {
-              const uint32_t dst = stage_off + pad + (uint32_t)(pl.off - goff);
+              const uint32_t dst = stage_s + pad + (uint32_t)(pl.off - goff);
               // the stage keeps the qname (and, for perfect reads, the quality line) of file 0 in
               // place: the other file only rewrites its L sequence bytes
               const bool full = (f == 0) || (P.out[0] == nullptr);
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
                 else mg_rewrite_seq<MgSharedSpace>(dst + qlen + 1, S, P.exc, P.n_exc);
               }
             } else {
-              emit_oversize<CORRUPT>(P.out[f] + pl.off, qlen, P, cor, cnt, first, second, f ? second : first, f);
+              emit_oversize<CORRUPT>(P.out[f] + pl.off, qlen, P, cnt, first, second, f ? second : first, f);
             }
           }
           if (f < 1) {

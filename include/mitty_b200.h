@@ -118,6 +118,13 @@ int mg_unit_generate_async(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, ui
                            int64_t *n_bytes, int64_t *n_templates, int64_t *n_te_kept);
 int mg_wait_copies(mg_ctx *ctx);
 
+/* streams a unit that was generated with out1 = out2 = NULL (bytes left on the device) through a
+ * small pinned ring instead of one unit-sized host buffer: copies bytes [offset, offset + bytes) of
+ * file `file` (0 / 1) of the MOST RECENT unit to dst, asynchronously on the copy stream; dst is
+ * valid after mg_wait_copies().  The writer loop of readgenerate.py:233-253 then appends chunk by
+ * chunk.                                                                                          */
+int mg_unit_read_async(mg_ctx *ctx, int32_t file, int64_t offset, int64_t bytes, uint8_t *dst);
+
 /* ---- corrupt-reads: replaces readcorrupt.multi_process / illumina.corrupt_template
  * (mitty/simulation/readcorrupt.py:18-118, illumina.py:113-162) over whole FASTQ buffers.
  * in2/out2 may be NULL (single-end).  DET mode consumes the reference's draws: for read k (file-1

@@ -22,7 +22,7 @@ MODE_PHILOX, MODE_DET, MODE_EXPLICIT = 0, 1, 2
 # every symbol include/mitty_b200.h declares
 SYMBOLS = ['mg_device_count', 'mg_ctx_create', 'mg_ctx_destroy', 'mg_last_error', 'mg_synchronize', 'mg_host_alloc', 'mg_host_free', 'mg_model_load', 'mg_model_tables',
            'mg_region_load', 'mg_region_free', 'mg_copy_build', 'mg_copy_free', 'mg_copy_nodes',
-           'mg_copy_haplotype', 'mg_sample_templates', 'mg_unit_generate', 'mg_unit_generate_async', 'mg_wait_copies', 'mg_corrupt_fastq',
+           'mg_copy_haplotype', 'mg_sample_templates', 'mg_unit_generate', 'mg_unit_generate_async', 'mg_wait_copies', 'mg_unit_read_async', 'mg_corrupt_fastq',
            'mg_prof_reset', 'mg_prof_get']
 
 
@@ -83,6 +83,7 @@ def lib():
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mg_unit_generate_async.argtypes = L.mg_unit_generate.argtypes
     L.mg_wait_copies.argtypes = [C.c_void_p]
+    L.mg_unit_read_async.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
     L.mg_corrupt_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_uint32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,

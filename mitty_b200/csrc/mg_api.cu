@@ -84,6 +84,7 @@ struct mg_ctx {
   cudaStream_t copy_stream = nullptr;              // D2H of finished units, overlapping the next unit's kernels
   cudaEvent_t ev_d2h[2] = {nullptr, nullptr};      // per output-buffer set: its last D2H has finished
   int ob = 0;                                      // output-buffer set of the next unit
+  int last_ob = 0; int64_t last_bytes = 0;         // where the most recent unit's bytes are (mg_unit_read_async)
   double plan_ms = 0;
   double emit_ms = 0; int64_t emit_launches = 0, emit_bytes = 0, total_launches = 0;
 };
@@ -711,6 +712,7 @@ static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint
     est = (size_t)tot[2] + 4096;
     CU(cudaMemsetAsync(P.totals + 3, 0, 8, ctx->stream));
   }
+  ctx->last_ob = ctx->ob; ctx->last_bytes = (int64_t)tot[2];
   if (n_bytes) *n_bytes = (int64_t)tot[2];
   if (n_templates) *n_templates = (int64_t)tot[1];
   if (n_te_kept) *n_te_kept = (int64_t)tot[0];
@@ -735,6 +737,15 @@ int mg_unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t 
 int mg_unit_generate_async(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint8_t *out2, int64_t cap, int64_t *n_bytes,
                            int64_t *n_templates, int64_t *n_te_kept) {
   return unit_generate(ctx, d, out1, out2, cap, n_bytes, n_templates, n_te_kept, false);
+}
+
+int mg_unit_read_async(mg_ctx *ctx, int32_t file, int64_t offset, int64_t bytes, uint8_t *dst) {
+  if (!ctx || !dst || file < 0 || file > 1 || offset < 0 || bytes < 0) return fail(ctx, MG_EINVAL, "mg_unit_read_async: bad arguments");
+  if (offset + bytes > ctx->last_bytes) return fail(ctx, MG_EINVAL, "mg_unit_read_async: range beyond the unit's %lld bytes", (long long)ctx->last_bytes);
+  DeviceGuard g(ctx->device);
+  if (bytes) CU(cudaMemcpyAsync(dst, ctx->s_out[ctx->last_ob][file].as<uint8_t>() + offset, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CU(cudaEventRecord(ctx->ev_d2h[ctx->last_ob], ctx->copy_stream));   // the next unit into this buffer set waits for it
+  return MG_OK;
 }
 
 int mg_wait_copies(mg_ctx *ctx) {

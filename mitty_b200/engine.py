@@ -189,6 +189,14 @@ class Engine(object):
   def wait_copies(self):
     self._check(self._L.mg_wait_copies(self._h))
 
+  def unit_read(self, file, offset, nbytes, dst):
+    """Enqueue the copy of bytes [offset, offset + nbytes) of file ``file`` of the most recent unit
+    (generated with fetch=False) into ``dst`` (pinned uint8 array); valid after wait_copies()."""
+    if dst.size < nbytes:
+      raise ValueError('unit_read: destination too small')
+    self._check(self._L.mg_unit_read_async(self._h, int(file), int(offset), int(nbytes), _ptr(dst)))
+    return dst[:nbytes]
+
   # -- corruption --------------------------------------------------------------------------------
   def corrupt_fastq(self, fq1, fq2=None, mode=MODE_PHILOX, seed=0, draws=None, first_template=0, out=None, partial=False):
     """Whole-buffer corrupt-reads.  fq1/fq2: bytes or uint8 arrays of 4-line FASTQ records.

@@ -98,30 +98,41 @@ def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sam
                               corrupt=corrupt, corrupt_seed=corrupt_seed, out=out, fetch=fetch, wait=wait)
 
 
+CHUNK_BYTES = 64 << 20     # pinned ring slot per file: a unit is streamed to the writer in pieces of this size
+
+
 def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,
                 corrupt_seed, n_buffers, done, free_q, stop):
-  """One thread per GPU: its units, in schedule order, each into a pinned buffer pair."""
+  """One thread per GPU: its units, in schedule order.  A unit's FASTQ bytes stay on the device and
+  are streamed through a small ring of pinned slot pairs (page-locking unit-sized host buffers
+  costs seconds for a chr1-sized unit)."""
   engine = None
   try:
     engine = Engine(device)
     engine.load_model(read_model)
     cache = RegionCache(engine, vcf_df, fetch_ref)
     rlen = int(read_model['rlen'])
-    # pinned buffers sized for this GPU's largest unit (~5/6 of the candidates survive)
     span = max([vcf_df[schedule[k]['region_idx']]['region'][2] - vcf_df[schedule[k]['region_idx']]['region'][1] for k in my_units] + [1])
     est = int(span * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150) * 0.9) + (1 << 20)
+    slot = min(CHUNK_BYTES, est)
     for _ in range(n_buffers):
-      free_q.put((engine.pinned(est), engine.pinned(est)))
+      free_q.put((engine.pinned(slot), engine.pinned(slot)))
     for k in my_units:
       wd = schedule[k]
-      buf = free_q.get()
-      if buf is None or stop.is_set():
-        return
       r_idx, cpy = wd['region_idx'], wd['region_cpy']
       cp = cache.copy(r_idx, cpy)
-      f1, f2, cnt, _, _ = generate_unit(engine, read_module, read_model, cp, vcf_df[r_idx]['region'][0], cpy, int(wd['rng_seed']),
-                                        sample_name, 0, k, mode=mode, corrupt=corrupt, corrupt_seed=corrupt_seed, out=buf)
-      done[k].put((f1, f2, cnt, buf))
+      _, _, cnt, _, nb = generate_unit(engine, read_module, read_model, cp, vcf_df[r_idx]['region'][0], cpy, int(wd['rng_seed']),
+                                       sample_name, 0, k, mode=mode, corrupt=corrupt, corrupt_seed=corrupt_seed, fetch=False)
+      for off in range(0, nb, slot):
+        buf = free_q.get()
+        if buf is None or stop.is_set():
+          return
+        n = min(slot, nb - off)
+        f1 = engine.unit_read(0, off, n, buf[0])
+        f2 = engine.unit_read(1, off, n, buf[1])
+        engine.wait_copies()
+        done[k].put((f1, f2, buf))
+      done[k].put(cnt)
     stop.wait()          # keep the pinned buffers alive until the writer has drained them
   except BaseException as e:  # noqa: B902 -- handed to the writer, which re-raises
     for k in my_units:
@@ -148,6 +159,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   from mitty_b200 import multigpu
   from mitty_b200.engine import device_count
 
+  t_in = time.time()
   read_model = read_module.read_model_params(model, coverage)
   vcf_df = vio.load_variant_file(vcf_fname, sample_name, bed_fname)
   fasta = vio.FastaFile(fasta_fname)
@@ -160,45 +172,60 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
     devices = list(range(max(1, min(int(threads), n_dev))))
   weights = [vcf_df[wd['region_idx']]['region'][2] - vcf_df[wd['region_idx']]['region'][1] for wd in schedule]
   assign = multigpu.assign_units(weights, len(devices)) if schedule else [[] for _ in devices]
-  done = [queue.Queue(1) for _ in schedule]
+  done = [queue.Queue() for _ in schedule]
   stop = threading.Event()
   free_qs = [queue.Queue() for _ in devices]
   cs = seed if corrupt_seed is None else corrupt_seed
   workers = [threading.Thread(target=_gpu_worker, daemon=True,
                               args=(dev, assign[i], schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,
-                                    cs, 2, done, free_qs[i], stop))
+                                    cs, 4, done, free_qs[i], stop))
              for i, dev in enumerate(devices)]
   owner = {k: i for i, units in enumerate(assign) for k in units}
 
   t0 = time.time()
   total = 0
+  t_wait = t_write = 0.0
   fastq_l = [open(fastq1_fname, 'wb')]
   if fastq2_fname is not None:
     fastq_l += [open(fastq2_fname, 'wb')]
+  # the two files are written concurrently (file writes release the GIL); each file still sees
+  # strictly sequential writes in schedule order, so FIFOs / process substitutions keep working
+  from concurrent.futures import ThreadPoolExecutor
+  pool = ThreadPoolExecutor(max_workers=len(fastq_l))
   try:
     for w in workers:
       w.start()
     for k in range(len(schedule)):
-      item = done[k].get()
-      if isinstance(item, BaseException):
-        raise item
-      f1, f2, cnt, buf = item
-      for fp, r in zip(fastq_l, (f1, f2)):                          # writer, readgenerate.py:246-248
-        fp.write(memoryview(r))
-      free_qs[owner[k]].put(buf)
-      total += cnt
-      logger.debug('Unit {}: {} templates'.format(k, cnt))
+      while True:
+        ta = time.time()
+        item = done[k].get()
+        tb = time.time()
+        t_wait += tb - ta
+        if isinstance(item, BaseException):
+          raise item
+        if not isinstance(item, tuple):                                 # the unit's template count: unit finished
+          total += item
+          logger.debug('Unit {}: {} templates'.format(k, item))
+          break
+        f1, f2, buf = item
+        futs = [pool.submit(fp.write, memoryview(r)) for fp, r in zip(fastq_l, (f1, f2))]   # writer, readgenerate.py:246-248
+        for fu in futs:
+          fu.result()
+        t_write += time.time() - tb
+        free_qs[owner[k]].put(buf)
   finally:
     stop.set()
     for q in free_qs:                                                 # unblock workers waiting for a buffer
       q.put(None)
+    pool.shutdown(wait=True)
     for fp in fastq_l:
       fp.close()
     for w in workers:
       if w.is_alive():
         w.join(timeout=60)
   t1 = time.time()
-  logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s)'.format(total, t1 - t0, total / max(t1 - t0, 1e-9)))
+  logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s); inputs {:0.2f}s, waiting for the GPU {:0.2f}s, writing {:0.2f}s'.format(
+    total, t1 - t0, total / max(t1 - t0, 1e-9), t0 - t_in, t_wait, t_write))
 
 
 # ---- the qname contract's inverse (readgenerate.py:256-291) --------------------------------------

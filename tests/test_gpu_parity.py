@@ -226,6 +226,22 @@ def test_cli_files_deterministic(tmp_path):
   assert open(c1, 'rb').read() == H.golden_fastq('edge.c1.fq.gz') and open(c2, 'rb').read() == H.golden_fastq('edge.c2.fq.gz')
 
 
+@pytest.mark.parametrize('chunk', [1000, 65536])
+def test_units_streamed_through_small_ring(tmp_path, monkeypatch, chunk):
+  """A unit's bytes leave the device through a ring of small pinned slots (mg_unit_read_async):
+  slots far smaller than a unit (even smaller than a few records) must give the same files."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  monkeypatch.setattr(rg, 'CHUNK_BYTES', chunk)
+  info = H.golden()['fastq']['edge']
+  wl = synth.edge_workload()
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'))
+  r1, r2 = str(tmp_path / 'r1.fq'), str(tmp_path / 'r2.fq')
+  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model(info['model']), info['coverage'], r1, r2,
+                            threads=2, seed=info['seed'], mode='deterministic', devices=[0, 0])
+  assert open(r1, 'rb').read() == H.golden_fastq('edge.r1.fq.gz') and open(r2, 'rb').read() == H.golden_fastq('edge.r2.fq.gz')
+
+
 @pytest.mark.parametrize('devices', [[0, 0], [0, 0, 0], 'all'])
 def test_sharded_workers_identical_output(tmp_path, devices):
   """Units dealt to several GPU workers (LPT), appended in schedule order: the bytes must not

@@ -13,9 +13,10 @@ print('wrote inputs (%d Mb FASTA, %d VCF records) in %.1f s' % (n_mb, len(wl['ta
 for extra in ([], ['--corrupt']):
   r1, r2 = os.path.join(d, 'r1.fq'), os.path.join(d, 'r2.fq')
   t0 = time.perf_counter()
-  res = CliRunner().invoke(cli, ['generate-reads', fa, vcf, wl['sample'], bed, 'hiseq-X-v2.5-Garvan.pkl', '30', '7', r1, '--fastq2', r2, '--threads', threads] + extra, catch_exceptions=False)
+  res = CliRunner().invoke(cli, ['-v', '4', 'generate-reads', fa, vcf, wl['sample'], bed, 'hiseq-X-v2.5-Garvan.pkl', '30', '7', r1, '--fastq2', r2, '--threads', threads] + extra, catch_exceptions=False)
   t1 = time.perf_counter()
   assert res.exit_code == 0, res.output
+  print('\n'.join(l for l in res.output.split('\n') if 'Finished' in l or 'phase' in l))
   sz = os.path.getsize(r1)
   pairs = sum(1 for _ in open(r1, 'rb')) // 4
   print('generate-reads %s --threads %s: %d pairs, 2 x %.2f GB to %s in %.2f s = %.2f M pairs/s' % (' '.join(extra), threads, pairs, sz / 1e9, d, t1 - t0, pairs / (t1 - t0) / 1e6))

@@ -99,68 +99,194 @@ def _open_bytes(fname):
     return fp.read()
 
 
-class VcfTable(object):
-  """All records of one sample, grouped by contig, as arrays.
+class _Contig(object):
+  """Records of one contig as arrays over the file's bytes (no per-record Python objects)."""
+  __slots__ = ('pos', 'reflen', 'rs', 're', 'as_', 'ae', 'gt', 'ploidy', 'exotic', 'slow')
 
-  Per contig: pos int64[n], reflen int64[n], ref list[str], alleles list[tuple[str]] (REF first),
-  gt list[tuple[int]] (as written for the sample; '.' -> None).
+  def __init__(self, pos, rs, re_, as_, ae, gt, ploidy, exotic, slow):
+    self.pos, self.rs, self.re, self.as_, self.ae = pos, rs, re_, as_, ae
+    self.reflen = re_ - rs
+    self.gt, self.ploidy, self.exotic, self.slow = gt, ploidy, exotic, slow
+
+  def merged(self, o):
+    n = self.pos.size
+    slow = dict(self.slow); slow.update({k + n: v for k, v in o.slow.items()})
+    w = max(self.gt.shape[1], o.gt.shape[1])
+    def widen(g):
+      out = np.full((g.shape[0], w), -2, dtype=np.int8); out[:, :g.shape[1]] = g
+      return out
+    cat = np.concatenate
+    return _Contig(cat([self.pos, o.pos]), cat([self.rs, o.rs]), cat([self.re, o.re]), cat([self.as_, o.as_]), cat([self.ae, o.ae]),
+                   cat([widen(self.gt), widen(o.gt)]), cat([self.ploidy, o.ploidy]), cat([self.exotic, o.exotic]), slow)
+
+
+def _gt_tuple(fmt, s):
+  if fmt != 'GT':
+    s = s.split(':')[fmt.split(':').index('GT')]
+  return tuple(None if g == '.' else int(g) for g in s.replace('/', '|').split('|'))
+
+
+class VcfTable(object):
+  """All records of one sample, grouped by contig, parsed with numpy over the raw bytes (a 4 M-record
+  WGS call set in seconds; the reference walks pysam records one by one, vcfio.py:59-62).
+
+  Per contig (``_Contig``): pos int64[n]; byte ranges of REF and ALT in ``self.buf``; gt int8[n, P]
+  (allele index per GT column, -1 for '.', -2 beyond the record's ploidy); ploidy int8[n].  Records
+  the array path does not cover -- multi-allelic ALT, FORMAT not starting with GT, allele indices
+  of more than one digit -- are parsed individually into ``slow`` {record: (ref, alleles, gt)}.
   """
 
   def __init__(self, fname, sample):
     if str(fname).endswith('bcf'):
       raise NotImplementedError('BCF input needs htslib; convert to VCF text (plain or gzip)')
-    text = _open_bytes(fname).decode()
+    data = _open_bytes(fname)
+    self.buf = buf = np.frombuffer(data, dtype=np.uint8)
     self.contigs = {}
-    col = None
-    cur_name, cur = None, None
-    for line in text.split('\n'):
-      if not line or line.startswith('##'):
-        continue
-      if line.startswith('#'):
-        hdr = line.split('\t')
-        if sample not in hdr[9:]:
-          raise ValueError('Sample {} not in VCF (samples: {})'.format(sample, hdr[9:]))
-        col = 9 + hdr[9:].index(sample)
-        continue
-      f = line.split('\t')
-      if len(f) <= (col or 9):
-        continue
-      if f[0] != cur_name:
-        cur_name = f[0]
-        cur = self.contigs.setdefault(cur_name, ([], [], [], []))
-      fmt = f[8]
-      s = f[col]
-      if fmt != 'GT':
-        s = s.split(':')[fmt.split(':').index('GT')]
-      gt = tuple(None if g == '.' else int(g) for g in s.replace('/', '|').split('|'))
-      cur[0].append(int(f[1])); cur[1].append(f[3]); cur[2].append((f[3],) + tuple(f[4].split(','))); cur[3].append(gt)
-    self._arr = {}
-    for name, (pos, ref, alleles, gt) in self.contigs.items():
-      self._arr[name] = (np.array(pos, dtype=np.int64), np.array([len(r) for r in ref], dtype=np.int64))
+    h = 0 if data.startswith(b'#CHROM') else data.find(b'\n#CHROM') + 1
+    if h == 0 and not data.startswith(b'#CHROM'):
+      raise ValueError('No #CHROM header line in {}'.format(fname))
+    he = data.find(b'\n', h)
+    he = len(data) if he < 0 else he
+    hdr = data[h:he].decode().rstrip('\r').split('\t')
+    if sample not in hdr[9:]:
+      raise ValueError('Sample {} not in VCF (samples: {})'.format(sample, hdr[9:]))
+    col = 9 + hdr[9:].index(sample)
+    body = min(he + 1, len(data))
+    nl = np.flatnonzero(buf[body:] == 10) + body
+    starts = np.concatenate([np.array([body], dtype=np.int64), nl + 1])
+    ends = np.concatenate([nl, np.array([len(data)], dtype=np.int64)])
+    keep = ends > starts
+    starts, ends = starts[keep], ends[keep]
+    if starts.size:
+      keep = buf[starts] != 35                                           # stray '#' lines
+      starts, ends = starts[keep], ends[keep]
+      ends = ends - (buf[ends - 1] == 13)                                # CRLF
+    tabs = np.flatnonzero(buf[body:] == 9) + body
+    t0 = np.searchsorted(tabs, starts)
+    ntab = np.searchsorted(tabs, ends) - t0
+    keep = ntab >= col                                                   # short lines are skipped
+    starts, ends, t0, ntab = starts[keep], ends[keep], t0[keep], ntab[keep]
+    n = starts.size
+    if n == 0:
+      return
+    tabs_p = np.concatenate([tabs, np.array([len(data)], dtype=np.int64)])
+
+    def fs(k):
+      return starts if k == 0 else tabs[t0 + k - 1] + 1
+
+    def fe(k):
+      return np.where(ntab > k, tabs_p[np.minimum(t0 + k, tabs.size)], ends)
+
+    def gather(s0, ln):
+      w = int(ln.max()) if ln.size else 0
+      mat = np.zeros((ln.size, w), dtype=np.uint8)
+      for k in range(w):
+        m = ln > k
+        mat[m, k] = buf[s0[m] + k]
+      return mat
+
+    # POS
+    ps, pe = fs(1), fe(1)
+    dig = gather(ps, pe - ps)
+    plen = pe - ps
+    pos = np.zeros(n, dtype=np.int64)
+    for k in range(dig.shape[1]):
+      m = plen > k
+      d = dig[m, k].astype(np.int64) - 48
+      if ((d < 0) | (d > 9)).any():
+        raise ValueError('Malformed POS field in {}'.format(fname))
+      pos[m] = pos[m] * 10 + d
+    rs, re_, as_, ae = fs(3), fe(3), fs(4), fe(4)
+    # which records need the per-line path
+    commas = np.flatnonzero(buf[body:] == 44) + body
+    exotic = (np.searchsorted(commas, ae) - np.searchsorted(commas, as_)) > 0
+    f8s, f8e = fs(8), fe(8)
+    flen = f8e - f8s
+    ok_fmt = (flen >= 2) & (buf[f8s] == 71) & (buf[np.minimum(f8s + 1, len(data) - 1)] == 84)
+    ok_fmt &= (flen == 2) | (buf[np.minimum(f8s + 2, len(data) - 1)] == 58)
+    ss, se = fs(col), fe(col)
+    colons = np.flatnonzero(buf[body:] == 58) + body
+    ci = np.searchsorted(colons, ss)
+    cpos = np.concatenate([colons, np.array([len(data)], dtype=np.int64)])[np.minimum(ci, colons.size)]
+    ge = np.minimum(cpos, se)
+    glen = ge - ss
+    gmat = gather(ss, np.minimum(glen, 15))
+    maxp = (gmat.shape[1] + 1) // 2
+    gt = np.full((n, max(maxp, 1)), -2, dtype=np.int8)
+    simple = (glen % 2 == 1) & (glen <= 15)
+    for j in range(maxp):
+      m = glen > 2 * j
+      c = gmat[m, 2 * j]
+      simple[m] &= ((c >= 48) & (c <= 57)) | (c == 46)
+      gt[m, j] = np.where(c == 46, -1, c.astype(np.int16) - 48).astype(np.int8)
+      if 2 * j + 1 < gmat.shape[1]:
+        m2 = glen > 2 * j + 1
+        sep = gmat[m2, 2 * j + 1]
+        simple[m2] &= (sep == 124) | (sep == 47)
+    exotic |= ~ok_fmt | ~simple
+    ploidy = ((glen + 1) // 2).astype(np.int16)
+    slow_all = {}
+    for i in np.flatnonzero(exotic).tolist():
+      f = data[starts[i]:ends[i]].decode().split('\t')
+      g = _gt_tuple(f[8], f[col])
+      slow_all[i] = (f[3], (f[3],) + tuple(f[4].split(',')), g)
+      ploidy[i] = len(g)
+    # contig runs
+    cmat = gather(starts, fe(0) - starts)
+    clen = fe(0) - starts
+    change = np.ones(n, dtype=bool)
+    if n > 1:
+      change[1:] = (cmat[1:] != cmat[:-1]).any(axis=1) | (clen[1:] != clen[:-1])
+    run0 = np.flatnonzero(change)
+    run1 = np.concatenate([run0[1:], np.array([n])])
+    for a, b in zip(run0.tolist(), run1.tolist()):
+      name = cmat[a, :clen[a]].tobytes().decode()
+      slow = {i - a: v for i, v in slow_all.items() if a <= i < b} if slow_all else {}
+      c = _Contig(pos[a:b], rs[a:b], re_[a:b], as_[a:b], ae[a:b], gt[a:b], ploidy[a:b], exotic[a:b], slow)
+      self.contigs[name] = self.contigs[name].merged(c) if name in self.contigs else c
 
   def fetch(self, contig, start, stop):
     """Indices of records overlapping 0-based [start, stop) -- htslib semantics (vcfio.py:62)."""
-    if contig not in self._arr:
+    if contig not in self.contigs:
       return contig, np.zeros(0, dtype=np.int64)
-    pos, reflen = self._arr[contig]
-    p0 = pos - 1
-    return contig, np.flatnonzero((p0 < stop) & (p0 + reflen > start))
+    c = self.contigs[contig]
+    p0 = c.pos - 1
+    return contig, np.flatnonzero((p0 < stop) & (p0 + c.reflen > start))
+
+  def gt_of(self, contig, i):
+    """GT of record i as the tuple pysam would give (None for '.')."""
+    c = self.contigs[contig]
+    if i in c.slow:
+      return c.slow[i][2]
+    return tuple(None if g == -1 else int(g) for g in c.gt[i, :c.ploidy[i]])
 
 
-def parse_copy(table, contig, idx, cpy):
-  """vcfio.parse over the records ``idx`` for copy ``cpy`` -> VariantList (vcfio.py:105-126)."""
-  if idx.size == 0:
-    return VariantList([], np.zeros(0, np.uint8), [], np.zeros(0, np.uint8), np.zeros(1, np.int64),
-                       np.zeros(0, np.uint8), np.zeros(1, np.int64))
-  pos_l, ref_l, alleles_l, gt_l = table.contigs[contig]
+def _pool(buf, s0, ln):
+  off = np.zeros(ln.size + 1, dtype=np.int64)
+  np.cumsum(ln, out=off[1:])
+  src = np.repeat(s0 - off[:-1], ln) + np.arange(off[-1])
+  return (buf[src] if src.size else np.zeros(0, dtype=np.uint8)), off
+
+
+def _parse_copy_records(table, contig, idx, cpy):
+  """Per-record path (vcfio.parse, vcfio.py:105-126) for selections that hold multi-allelic or
+  otherwise unusual records."""
+  c = table.contigs[contig]
+  buf = table.buf
   pos, op, oplen, alts, refs = [], [], [], [], []
   for i in idx.tolist():
-    g = gt_l[i][cpy]                       # IndexError on ragged ploidy, like the reference
+    if i in c.slow:
+      ref, alleles, gt = c.slow[i]
+    else:
+      ref = buf[c.rs[i]:c.re[i]].tobytes().decode()
+      alleles = (ref, buf[c.as_[i]:c.ae[i]].tobytes().decode())
+      gt = table.gt_of(contig, i)
+    g = gt[cpy]                            # IndexError on ragged ploidy, like the reference
     if g == 0:                             # not present on this copy (vcfio.py:112)
       continue
     if g is None:
-      raise ValueError('Missing GT allele at {}:{}'.format(contig, pos_l[i]))
-    ref, alt = ref_l[i], alleles_l[i][g]
+      raise ValueError('Missing GT allele at {}:{}'.format(contig, int(c.pos[i])))
+    alt = alleles[g]
     l_r, l_a = len(ref), len(alt)
     if l_r == 1:
       if l_a == 1:
@@ -171,11 +297,37 @@ def parse_copy(table, contig, idx, cpy):
       o, ol = 68, l_r - l_a                # 'D'
     else:
       raise ValueError("Complex variants present in VCF. Please filter or refactor these.")
-    pos.append(pos_l[i]); op.append(o); oplen.append(ol); alts.append(alt.encode()); refs.append(ref.encode())
+    pos.append(int(c.pos[i])); op.append(o); oplen.append(ol); alts.append(alt.encode()); refs.append(ref.encode())
   alt_off = np.zeros(len(pos) + 1, dtype=np.int64); np.cumsum([len(a) for a in alts], out=alt_off[1:])
   ref_off = np.zeros(len(pos) + 1, dtype=np.int64); np.cumsum([len(a) for a in refs], out=ref_off[1:])
   return VariantList(pos, np.array(op, dtype=np.uint8), oplen, np.frombuffer(b''.join(alts), dtype=np.uint8), alt_off,
                      np.frombuffer(b''.join(refs), dtype=np.uint8), ref_off)
+
+
+def parse_copy(table, contig, idx, cpy):
+  """vcfio.parse over the records ``idx`` for copy ``cpy`` -> VariantList (vcfio.py:105-126)."""
+  if idx.size == 0:
+    return VariantList([], np.zeros(0, np.uint8), [], np.zeros(0, np.uint8), np.zeros(1, np.int64),
+                       np.zeros(0, np.uint8), np.zeros(1, np.int64))
+  c = table.contigs[contig]
+  if c.exotic[idx].any():
+    return _parse_copy_records(table, contig, idx, cpy)
+  if (c.ploidy[idx] <= cpy).any():
+    raise IndexError('tuple index out of range')           # ragged ploidy, like the reference
+  g = c.gt[idx, cpy]
+  if (g == -1).any():
+    raise ValueError('Missing GT allele at {}:{}'.format(contig, int(c.pos[idx[np.flatnonzero(g == -1)[0]]])))
+  if (g > 1).any():
+    raise IndexError('tuple index out of range')           # allele index beyond the single ALT
+  sel = idx[g != 0]                                        # GT 0: not on this copy (vcfio.py:112)
+  l_r, l_a = c.reflen[sel], (c.ae - c.as_)[sel]
+  if ((l_r > 1) & (l_a > 1)).any():
+    raise ValueError("Complex variants present in VCF. Please filter or refactor these.")
+  op = np.where(l_r == 1, np.where(l_a == 1, 88, 73), 68).astype(np.uint8)
+  oplen = np.where(l_r == 1, l_a - 1, l_r - 1)
+  ap, ao = _pool(table.buf, c.as_[sel], l_a)
+  rp, ro = _pool(table.buf, c.rs[sel], l_r)
+  return VariantList(c.pos[sel], op, oplen, ap, ao, rp, ro)
 
 
 def split_copies(region, table, contig, idx):
@@ -184,7 +336,7 @@ def split_copies(region, table, contig, idx):
     logger.warning('Empty region ({}), assuming diploid'.format(region))
     ploidy = 2
   else:
-    ploidy = len(table.contigs[contig][3][int(idx[0])])
+    ploidy = len(table.gt_of(contig, int(idx[0])))
     logger.debug('Region: {}, ploidy: {}'.format(region, ploidy))
   return {'region': region, 'v': [parse_copy(table, contig, idx, cpy) for cpy in range(ploidy)]}
 
@@ -229,17 +381,19 @@ class FastaFile(object):
   def __init__(self, fname):
     data = _open_bytes(fname)
     self._seqs = {}
-    a = np.frombuffer(data, dtype=np.uint8)
-    hdr = np.flatnonzero(a == ord('>'))
-    # only '>' at line starts are headers
-    hdr = hdr[(hdr == 0) | (a[np.maximum(hdr - 1, 0)] == 10)]
-    bounds = list(hdr) + [a.size]
-    for k, h in enumerate(hdr.tolist()):
+    # headers are '>' at a line start; bytes.find runs at memchr speed (a 3 GB genome in a second)
+    hdr = []
+    h = 0 if data.startswith(b'>') else data.find(b'\n>') + 1
+    while h > 0 or (h == 0 and data.startswith(b'>') and not hdr):
+      hdr.append(h)
+      h = data.find(b'\n>', h) + 1
+    bounds = hdr + [len(data)]
+    for k, h in enumerate(hdr):
       eol = data.find(b'\n', h)
       if eol < 0:
         eol = len(data)
       name = data[h + 1:eol].split()[0].decode() if eol > h + 1 else ''
-      self._seqs[name] = (eol + 1, bounds[k + 1])
+      self._seqs[name] = (min(eol + 1, len(data)), bounds[k + 1])
     self._data = data
     self._cache = {}
     self._lock = threading.Lock()

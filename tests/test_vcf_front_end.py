@@ -1,0 +1,104 @@
+"""Host front end: the vectorised VCF parser against a line-by-line restatement
+of vcfio.parse (mitty/lib/vcfio.py:105-126) on records the array path does not cover."""
+import gzip
+
+import numpy as np
+import pytest
+
+from mitty_b200.lib import vcfio
+
+HDR = '##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS0\tS1\n'
+
+
+def simple_parse(text, sample, contig, start, stop, cpy):
+  """pysam-free restatement: overlap fetch + vcfio.parse for one copy -> [(pos, ref, alt, op, oplen)]."""
+  col, out = None, []
+  for line in text.replace('\r\n', '\n').split('\n'):
+    if line.startswith('#CHROM'):
+      col = line.split('\t').index(sample)
+    if not line or line.startswith('#'):
+      continue
+    f = line.split('\t')
+    pos, ref, alts = int(f[1]), f[3], f[4].split(',')
+    if f[0] != contig or not (pos - 1 < stop and pos - 1 + len(ref) > start):
+      continue
+    gts = f[col].split(':')[f[8].split(':').index('GT')].replace('/', '|').split('|')
+    g = gts[cpy]
+    if g == '0':
+      continue
+    alt = ([ref] + alts)[int(g)]
+    if len(ref) == 1 and len(alt) == 1:
+      out.append((pos, ref, alt, 'X', 0))
+    elif len(ref) == 1:
+      out.append((pos, ref, alt, 'I', len(alt) - 1))
+    elif len(alt) == 1:
+      out.append((pos, ref, alt, 'D', len(ref) - 1))
+    else:
+      raise ValueError('complex')
+  return out
+
+
+BODY = (
+  '1\t10\t.\tA\tC\t.\tPASS\tAC=1,2;X=a:b\tGT\t0|1\t1|1\n'
+  '1\t20\t.\tA\tC,G\t.\tPASS\t.\tGT\t1|2\t0|1\n'              # multi-allelic
+  '1\t30\t.\tAT\tA\t.\tPASS\t.\tGT:DP\t1/0:17\t0/0:3\n'       # unphased, extra FORMAT keys
+  '1\t40\t.\tA\tATTT\t.\tPASS\tDP=3\tGT\t1|1\t1|0\n'
+  '1\t50\t.\tC\tG\t.\tPASS\t.\tDP:GT\t9:0|1\t1:1|1\n'         # GT not first (not valid VCF, still parsed)
+  '2\t5\t.\tG\tT\t.\tPASS\t.\tGT\t1\t1\n'                     # haploid contig
+  '2\t9\t.\tGCA\tG\t.\tPASS\t.\tGT\t1\t0\n'
+  '1\t60\t.\tT\tA\t.\tPASS\t.\tGT\t1|0\t0|1\n'                # contig 1 again after contig 2
+)
+
+
+@pytest.mark.parametrize('crlf', [False, True])
+@pytest.mark.parametrize('gz', [False, True])
+def test_parser_matches_line_by_line(tmp_path, crlf, gz):
+  text = HDR + BODY
+  if crlf:
+    text = text.replace('\n', '\r\n')
+  path = str(tmp_path / ('a.vcf.gz' if gz else 'a.vcf'))
+  with (gzip.open(path, 'wb') if gz else open(path, 'wb')) as fp:
+    fp.write(text.encode())
+  bed = str(tmp_path / 'a.bed')
+  regions = [('1', 0, 100), ('1', 25, 45), ('2', 0, 20), ('2', 10, 20), ('3', 0, 10)]
+  open(bed, 'w').write(''.join('{}\t{}\t{}\n'.format(*r) for r in regions))
+  for sample in ('S0', 'S1'):
+    df = vcfio.load_variant_file(path, sample, bed)
+    assert [d['region'] for d in df] == regions
+    for d in df:
+      chrom, start, stop = d['region']
+      ploidy = 1 if chrom == '2' else 2          # sniffed from the first record; no records -> 2 (vcfio.py:74-79)
+      assert len(d['v']) == ploidy
+      for cpy, vl in enumerate(d['v']):
+        assert [v.tuple() for v in vl] == simple_parse(text, sample, chrom, start, stop, cpy)
+
+
+def test_parser_errors(tmp_path):
+  def load(body, sample='S0'):
+    path = str(tmp_path / 'e.vcf'); open(path, 'w').write(HDR + body)
+    bed = str(tmp_path / 'e.bed'); open(bed, 'w').write('1\t0\t100\n')
+    return vcfio.load_variant_file(path, sample, bed)
+  with pytest.raises(ValueError):
+    load('1\t10\t.\tAT\tGC\t.\tPASS\t.\tGT\t1|1\t0|0\n')                     # complex variant, vcfio.py:124
+  with pytest.raises(ValueError):
+    load('1\t10\t.\tAT\tGC,A\t.\tPASS\t.\tGT\t1|2\t0|0\n')                   # the same through the per-record path
+  with pytest.raises(ValueError):
+    load('1\t10\t.\tA\tC\t.\tPASS\t.\tGT\t0|1\t0|0\n', sample='nobody')
+  with pytest.raises(IndexError):
+    load('1\t10\t.\tA\tC\t.\tPASS\t.\tGT\t0|1\t0|0\n1\t20\t.\tA\tC\t.\tPASS\t.\tGT\t1\t0|0\n')   # ragged ploidy
+  assert [len(v) for v in load('1\t10\t.\tAT\tGC\t.\tPASS\t.\tGT\t0|0\t1|1\n')[0]['v']] == [0, 0]   # GT 0 is skipped before the check
+
+
+def test_parser_matches_synthetic_table(tmp_path):
+  """Same VariantLists from the VCF text as from the in-memory table the benchmark uses."""
+  from mitty_b200 import synth
+  wl = synth.edge_workload()
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'), gz=True)
+  df = vcfio.load_variant_file(vcf, wl['sample'], bed)
+  tables = {t.chrom: t for t in wl['tables']}
+  for d in df:
+    ref = vcfio.from_variant_table(tables[d['region'][0]], d['region'])
+    assert len(ref['v']) == len(d['v'])
+    for a, b in zip(ref['v'], d['v']):
+      assert np.array_equal(a.pos, b.pos) and np.array_equal(a.op, b.op) and np.array_equal(a.oplen, b.oplen)
+      assert np.array_equal(a.alt_pool, b.alt_pool) and np.array_equal(a.alt_off, b.alt_off)

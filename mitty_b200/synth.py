@@ -217,6 +217,30 @@ def config1(contig_len=1000000, seed=7, per_mb=740.0, names=('1', '10'), ploidy=
   return {'contigs': contigs, 'tables': tables, 'regions': regions, 'sample': 'INTEGRATION'}
 
 
+def config5(contig_len=200000, seed=9, viral_len=9000):
+  """BASELINE.json configs[4]: tumour / normal mix with a viral spike-in, as three workloads to be
+  run as three generate-reads invocations and concatenated -- how the reference makes mixes (the
+  sample name in the qname tells them apart, Readme.md:14-16).  All three share the reference
+  contigs ('1', an X-like 'X', 'virus'): normal = diploid autosome + haploid X; tumour = triploid
+  GT on both; virus = one haploid dummy variant on the viral contig.  Returns {'normal', 'tumor',
+  'virus'} -> workload dicts (each with its own regions / sample), plus the shared contigs."""
+  seqs = [('1', synth_contig(contig_len, seed=seed * 1000)), ('X', synth_contig(contig_len // 2, seed=seed * 1000 + 1)),
+          ('virus', synth_contig(viral_len, seed=seed * 1000 + 2))]
+  by = dict(seqs)
+
+  def tables(ploidy_1, ploidy_x, k):
+    return [synth_variants('1', by['1'], 0, contig_len, seed=seed * 1000 + 100 * k, per_mb=900.0, ploidy=ploidy_1, long_ins=1),
+            synth_variants('X', by['X'], 0, contig_len // 2, seed=seed * 1000 + 100 * k + 1, per_mb=900.0, ploidy=ploidy_x, long_ins=1)]
+
+  human = [('1', 0, contig_len), ('X', 0, contig_len // 2)]
+  p = viral_len // 2
+  ref = chr(by['virus'][p - 1])
+  dummy = table_from_records('virus', [(p, ref, {'A': 'C', 'C': 'G', 'G': 'T', 'T': 'A'}[ref], (1,))], 1)
+  return {'normal': {'contigs': seqs, 'tables': tables(2, 1, 1), 'regions': human, 'sample': 'NORMAL'},
+          'tumor': {'contigs': seqs, 'tables': tables(3, 3, 2), 'regions': human, 'sample': 'TUMOR'},
+          'virus': {'contigs': seqs, 'tables': [dummy], 'regions': [('virus', 0, viral_len)], 'sample': 'VIRUS'}}
+
+
 def write_workload(wl, prefix, gz=False):
   """Write FASTA / VCF / BED for a workload dict; returns (fasta, vcf, bed) paths."""
   fasta, vcf, bed = prefix + '.fasta', prefix + ('.vcf.gz' if gz else '.vcf'), prefix + '.bed'

@@ -323,3 +323,54 @@ def test_corrupt_reads_streaming_chunks(tmp_path, chunk):
   s1 = str(tmp_path / 's1.fq')
   rc.multi_process(il, m, r1, s1, None, None, processes=1, seed=3, mode='philox', chunk_bytes=chunk)
   assert open(s1, 'rb').read() == open(q1, 'rb').read()
+
+
+def test_tumor_normal_viral_mix(tmp_path):
+  """BASELINE.json configs[4] at test scale: three generate-reads invocations (diploid normal with a
+  haploid X, triploid tumour, haploid viral spike-in) concatenated the way the reference makes mixes.
+  Every read must re-derive from its qname against ITS sample's haplotypes, and the per-sample pair
+  counts must follow coverage x copies (each copy gets coverage / 2, illumina.py:12-40)."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  mix = synth.config5()
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  L = int(m['mean_rlen'])
+
+  def expected_pairs(wl, cov):
+    tables = {t.chrom: t for t in wl['tables']}
+    return sum((e - s) * tables[c].gt.shape[1] * (cov / 2.0) / (2 * L) for c, s, e in wl['regions'])
+
+  human = expected_pairs(mix['normal'], 30.0) + expected_pairs(mix['tumor'], 20.0)
+  cov_v = 30.0 * (0.01 * human / 0.99) / expected_pairs(mix['virus'], 30.0)      # ~1 % of all pairs
+  runs = [('normal', 30.0, 7), ('tumor', 20.0, 8), ('virus', cov_v, 9)]
+  cat1, cat2 = b'', b''
+  for name, cov, seed in runs:
+    wl = mix[name]
+    fa, vcf, bed = synth.write_workload(wl, str(tmp_path / name))
+    r1, r2 = str(tmp_path / (name + '.1.fq')), str(tmp_path / (name + '.2.fq'))
+    rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, cov, r1, r2, threads=1, seed=seed, mode='philox')
+    cat1 += open(r1, 'rb').read(); cat2 += open(r2, 'rb').read()
+  regs = {mix[k]['sample']: H.workload_regions(mix[k]) for k in mix}
+  idx, counts, errs = {}, {}, []
+  for which, buf in enumerate((cat1, cat2)):
+    lines = buf.decode().split('\n')
+    for k in range(0, len(lines) - 1, 4):
+      info = rg.parse_qname(lines[k][1:])[which]
+      key = (info.sample, info.chrom, info.cpy)
+      if key not in idx:
+        r = next(r for r in regs[info.sample] if r['region'][0] == info.chrom)
+        idx[key] = H.HaplotypeIndex(r['ref'], r['region'][1] + 1, H.oracle_cv(r['v'][info.cpy]))
+      e = idx[key].check(info, lines[k + 1])
+      if e:
+        errs.append((lines[k], e))
+      if which == 0:
+        counts[info.sample] = counts.get(info.sample, 0) + 1
+  assert not errs, errs[:3]
+  assert {k[0] for k in idx} == {'NORMAL', 'TUMOR', 'VIRUS'}
+  assert {k[2] for k in idx if k[0] == 'TUMOR'} == {0, 1, 2} and {k[2] for k in idx if k[:2] == ('NORMAL', 'X')} == {0}
+  for name, cov, _ in runs:
+    exp = expected_pairs(mix[name], cov)
+    got = counts[mix[name]['sample']]
+    assert abs(got - exp) < 0.04 * exp + 6 * np.sqrt(exp), (name, got, exp)   # edge effects: templates need te < p_max
+  frac = counts['VIRUS'] / float(sum(counts.values()))
+  assert 0.006 < frac < 0.014, frac

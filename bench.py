@@ -199,7 +199,7 @@ def run_reference(args):
           'config': config_dict(args),
           'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': procs, 'kind': 'port', 'sample': sample},
           'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-  print(json.dumps(line))
+  emit(line)
 
 
 def config_dict(args):
@@ -218,8 +218,30 @@ def config_dict(args):
 
 # ---- the engine --------------------------------------------------------------------------------------
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+  """The contract is ONE JSON line on stdout: anything a library prints there (NCCL's version
+  banner, for one) is sent to stderr instead; emit() writes to the real stdout."""
+  global _REAL_STDOUT
+  if _REAL_STDOUT is None:
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+  data = (json.dumps(line) + '\n').encode()
+  if _REAL_STDOUT is None:
+    sys.stdout.write(data.decode()); sys.stdout.flush()
+  else:
+    os.write(_REAL_STDOUT, data)
+
+
 def main():
   args = parse()
+  _guard_stdout()
   if args.impl == 'reference':
     return run_reference(args)
 
@@ -378,7 +400,7 @@ def main():
       n, wall, sl = cpu_baseline(args, wl if args.workload == 'chr1' else {'contigs': [wl['contigs'][0]], 'tables': [wl['tables'][0]]}, 1)
       line['cpu_baseline'] = {'value': n / wall, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port',
                               'sample': 'one {} Mb-slice work unit of the same contig (generate + corrupt, {} pairs), C oracle, 1 thread'.format(sl // 1000000, n)}
-    print(json.dumps(line))
+    emit(line)
   eng.close()
   if world > 1:
     dist.destroy_process_group()

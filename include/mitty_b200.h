@@ -68,8 +68,10 @@ int mg_region_free(mg_ctx *ctx, int64_t region_id);
 /* ---- chromosome copy: replaces rpc.create_node_list (mitty/simulation/rpc.py:38-116) and the
  * p_min/p_max computation (readgenerate.py:192).  Variants of ONE copy in VCF order (output of
  * vcfio.parse, mitty/lib/vcfio.py:105-126): pos 1-based, op 'X'/'I'/'D', oplen, ALT strings
- * pooled as alt_pool[alt_off[i] .. alt_off[i+1]).  Builds the node table, the packed haplotype
- * and the block lookup table in HBM.                                                           */
+ * pooled as alt_pool[alt_off[i] .. alt_off[i+1]).  Builds the node table (the greedy walk runs on
+ * the device), the packed haplotype and the block lookup table in HBM.  POS must be sorted, as the
+ * records of an indexed fetch are (MG_EVALUE otherwise); a node list that would end in 'D'
+ * (deletion across the region end, readgenerate.py:192) is MG_EVALUE too.                       */
 int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *pos, const uint8_t *op,
                   const int64_t *oplen, const uint8_t *alt_pool, const int64_t *alt_off, int64_t *copy_id,
                   int64_t *p_min, int64_t *p_max, int64_t *n_nodes);

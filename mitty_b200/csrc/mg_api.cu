@@ -1,6 +1,5 @@
-// C-ABI of the engine (include/mitty_b200.h): context, device-memory management, the host half
-// of the haplotype builder (the inherently sequential greedy variant walk of rpc.py:48-61) and
-// the launch sequences of the kernels in mg_kernels.cu.  No CPU fallback lives here.
+// C-ABI of the engine (include/mitty_b200.h): context, device-memory management and the launch
+// sequences of the kernels in mg_kernels.cu.  No CPU fallback lives here.
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -39,6 +38,7 @@ struct Region {
   int64_t len = 0, bed_start = 0;
   uint32_t *d_ref = nullptr;      // packed, with MG_HAP_PAD words of padding on both sides
   std::vector<ExcRun> exc;        // non-ACGT runs, region-relative
+  MgExc *d_exc = nullptr;         // the same runs on the device (sorted by start)
   mg_ctx *owner = nullptr;
   ~Region();
 };
@@ -48,7 +48,7 @@ struct Copy {
   int64_t region_id = 0;
   int64_t p_min = 0, p_max = 0;
   int64_t n_nodes = 0;
-  std::vector<MgExc> exc;
+  int64_t n_exc = 0;
   MgNode *d_nodes = nullptr; uint32_t *d_hap = nullptr; uint32_t *d_blk = nullptr; MgExc *d_exc = nullptr;
   int n_blk = 0; int64_t hap_words = 0;
   mg_ctx *owner = nullptr;
@@ -70,7 +70,6 @@ struct mg_ctx {
   int n_tlen = 0, n_mates = 0, n_cycles = 0, n_bq = 0, rlen = 0;
   int n64 = 0;   // leading cycles whose rows (all mates) put no mass on BQ >= 64: 64-entry alias rows are exact there
   std::vector<uint32_t> h_alias[2]; std::vector<MgErr> h_err;
-  std::vector<MgNode> h_dn; std::vector<uint32_t> h_seg_start; std::vector<uint64_t> h_seg_src;   // copy-build scratch
   std::vector<std::pair<void *, size_t>> pool;   // device blocks of freed copies, reused by the next build
   std::map<void *, size_t> block_size;
   // handles
@@ -184,7 +183,7 @@ void pool_free(mg_ctx *ctx, void *p) {
   cudaFree(p);
 }
 
-Region::~Region() { pool_free(owner, d_ref); }
+Region::~Region() { pool_free(owner, d_ref); pool_free(owner, d_exc); }
 Copy::~Copy() { pool_free(owner, d_nodes); pool_free(owner, d_hap); pool_free(owner, d_blk); pool_free(owner, d_exc); }
 
 }  // namespace
@@ -365,7 +364,13 @@ int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t b
       std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return st[a] < st[b]; });
       std::sort(en.begin(), en.end());
       R->exc.resize(cnt[0]);
-      for (uint32_t i = 0; i < cnt[0]; i++) R->exc[i] = ExcRun{st[order[i]], en[i] - st[order[i]] + 1, by[order[i]]};
+      std::vector<MgExc> dev(cnt[0]);
+      for (uint32_t i = 0; i < cnt[0]; i++) {
+        R->exc[i] = ExcRun{st[order[i]], en[i] - st[order[i]] + 1, by[order[i]]};
+        dev[i] = MgExc{(uint32_t)R->exc[i].start, (uint32_t)R->exc[i].len, R->exc[i].byte, 0};
+      }
+      CU(pool_get(ctx, (void **)&R->d_exc, sizeof(MgExc) * cnt[0]));
+      CU(cudaMemcpy(R->d_exc, dev.data(), sizeof(MgExc) * cnt[0], cudaMemcpyHostToDevice));
     }
   }
   int64_t id = ctx->next_id++;
@@ -388,121 +393,116 @@ int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *
                   int64_t *n_nodes) {
   if (!ctx || !copy_id || n_var < 0 || (n_var > 0 && (!pos || !op || !oplen || !alt_pool || !alt_off)))
     return fail(ctx, MG_EINVAL, "mg_copy_build: bad arguments");
+  if (n_var >= (1ll << 28)) return fail(ctx, MG_EVALUE, "%lld variants on one copy (limit 2^28)", (long long)n_var);
   auto it = ctx->regions.find(region_id);
   if (it == ctx->regions.end()) return fail(ctx, MG_EINVAL, "unknown region %lld", (long long)region_id);
   DeviceGuard g(ctx->device);
   Region &R = *it->second;
   std::unique_ptr<Copy> C(new Copy());
   C->region_id = region_id;
+  C->owner = ctx;
   Timer tm("copy_build");
-
-  // -- the greedy walk (rpc.py:48-61), one pass: device node table, haplotype segments (the
-  //    non-'D' nodes) and exception runs in sample space.  src: bit 63 set -> byte offset in the alt
-  //    pool, else base offset in the region's reference.  Scratch vectors live in the context.
+  const int V = (int)n_var;
   const int64_t start1 = R.bed_start + 1;            // ref_start_pos, readgenerate.py:190; also p_min
-  int64_t samp = start1, refp = start1;
-  std::vector<MgNode> &dn = ctx->h_dn;
-  std::vector<uint32_t> &seg_start = ctx->h_seg_start;
-  std::vector<uint64_t> &seg_src = ctx->h_seg_src;
-  dn.clear(); seg_start.clear(); seg_src.clear();
-  dn.reserve(2 * (size_t)n_var + 2); seg_start.reserve(2 * (size_t)n_var + 2); seg_src.reserve(2 * (size_t)n_var + 2);
-  const uint64_t ALT = 1ull << 63;
-  size_t rx = 0;                                      // cursor into the region's exception runs
-  bool bad = false;
-  auto add_exc = [&](int64_t s, int64_t l, uint8_t b) {
-    if (!C->exc.empty()) { MgExc &e = C->exc.back(); if ((int64_t)e.start + e.len == s && e.byte == b) { e.len += (uint32_t)l; return; } }
-    C->exc.push_back(MgExc{(uint32_t)s, (uint32_t)l, b, 0});
-  };
-  auto push = [&](int64_t ps, int64_t pr, uint8_t o, int64_t ol, uint64_t sr) {
-    const int64_t rel = ps - start1;
-    if (ol > INT32_MAX || pr >= (1ll << 31) || rel >= (int64_t)0xFFF00000ll) { bad = true; return; }
-    dn.push_back(MgNode{(uint32_t)(rel + (o == 'D' ? 1 : 0)), (int32_t)pr, (int32_t)ol, o});   // key: rpc.py:127
-    if (o == 'D' || ol == 0) return;
-    seg_start.push_back((uint32_t)rel); seg_src.push_back(sr);
-    if (o == '=') {
-      const int64_t a = (int64_t)sr, b = a + ol;
-      if (b > R.len) { bad = true; return; }
-      while (rx < R.exc.size() && R.exc[rx].start + R.exc[rx].len <= a) rx++;
-      for (size_t q = rx; q < R.exc.size() && R.exc[q].start < b; q++) {
-        int64_t s0 = std::max(a, R.exc[q].start), e0 = std::min(b, R.exc[q].start + R.exc[q].len);
-        if (e0 > s0) add_exc(rel + (s0 - a), e0 - s0, R.exc[q].byte);
-      }
-    } else {
-      const uint8_t *alt = alt_pool + (sr & ~ALT);
-      for (int64_t q = 0; q < ol; q++)
-        if (mg_base_code(alt[q]) > 3) add_exc(rel + q, 1, alt[q]);
-    }
-  };
-  for (int64_t i = 0; i < n_var; i++) {
-    const int64_t vp = pos[i];
-    if (vp < refp) continue;                          // rpc.py:55
-    if (op[i] == 'X') {                               // rpc.py:75-87
-      int64_t delta = vp - refp;
-      if (delta > 0) { push(samp, refp, '=', delta, (uint64_t)(refp - start1)); refp = vp; samp += delta; }
-      if (alt_off[i + 1] - alt_off[i] != 1) return fail(ctx, MG_EVALUE, "SNP at %lld has an ALT of length %lld", (long long)vp, (long long)(alt_off[i + 1] - alt_off[i]));
-      push(samp, refp, 'X', 1, ALT | (uint64_t)alt_off[i]);
-      refp += 1; samp += 1;
-    } else if (op[i] == 'I') {                        // rpc.py:90-102
-      int64_t delta = vp + 1 - refp;
-      if (delta > 0) { push(samp, refp, '=', delta, (uint64_t)(refp - start1)); samp += delta; }
-      refp = vp + 1;
-      if (alt_off[i + 1] - alt_off[i] - 1 != oplen[i]) return fail(ctx, MG_EVALUE, "insertion at %lld: oplen %lld does not match its ALT", (long long)vp, (long long)oplen[i]);
-      push(samp, refp, 'I', oplen[i], ALT | (uint64_t)(alt_off[i] + 1));
-      samp += oplen[i];
-    } else if (op[i] == 'D') {                        // rpc.py:105-116
-      int64_t delta = vp + 1 - refp;
-      if (delta > 0) { push(samp, refp, '=', delta, (uint64_t)(refp - start1)); samp += delta; }
-      refp = vp + 1 + oplen[i];
-      push(samp - 1, refp, 'D', oplen[i], 0);
-    } else {
-      return fail(ctx, MG_EVALUE, "variant %lld has op %d (expected X, I or D)", (long long)i, (int)op[i]);
-    }
+  const int64_t alt_bytes = V ? alt_off[V] : 0;
+  if (alt_bytes >= (1ll << 32)) return fail(ctx, MG_EVALUE, "alt allele pool of %lld bytes exceeds 2^32", (long long)alt_bytes);
+  // the walk's chain argument needs POS sorted (records of an indexed fetch always are)
+  for (int i = 1; i < V; i++)
+    if (pos[i] < pos[i - 1]) return fail(ctx, MG_EVALUE, "variants are not sorted by POS (record %d: %lld after %lld)", i, (long long)pos[i], (long long)pos[i - 1]);
+  tm.lap("check");
+
+  // -- scratch layout (all 16-byte aligned): variant arrays, walk state, node-sized arrays, alt pool
+  const size_t nv = (size_t)V, max_nodes = 2 * nv + 1;
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t o = 0;
+  const size_t o_pos = o; o += al(8 * (nv + 1));
+  const size_t o_oplen = o; o += al(8 * (nv + 1));
+  const size_t o_altoff = o; o += al(8 * (nv + 2));
+  const size_t o_op = o; o += al(nv + 1);
+  const size_t o_nxt = o; o += al(4 * (nv + 1));
+  const size_t o_j0 = o; o += al(4 * (nv + 1));
+  const size_t o_j1 = o; o += al(4 * (nv + 1));
+  const size_t o_pred = o; o += al(4 * (nv + 1));
+  const size_t o_mark = o; o += al(nv + 1);
+  const size_t o_packed = o; o += al(8 * (nv + 2));
+  const size_t o_scanned = o; o += al(8 * (nv + 3));
+  const size_t o_tmp = o; o += al(8 * ((max_nodes + 2) / 1024 + 4));
+  const size_t o_nalt = o; o += al(4 * max_nodes);
+  const size_t o_ecnt = o; o += al(8 * (max_nodes + 2));
+  const size_t o_eoff = o; o += al(8 * (max_nodes + 3));
+  const size_t o_sum = o; o += al(sizeof(MgWalkSummary));
+  const size_t o_alt = o; o += al((size_t)alt_bytes + 16);
+  CU(ctx->s_str.need(o));
+  uint8_t *sb = ctx->s_str.as<uint8_t>();
+  CU(pool_get(ctx, (void **)&C->d_nodes, sizeof(MgNode) * max_nodes));
+  if (V) {
+    CU(cudaMemcpyAsync(sb + o_pos, pos, 8 * nv, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(sb + o_oplen, oplen, 8 * nv, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(sb + o_altoff, alt_off, 8 * (nv + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(sb + o_op, op, nv, cudaMemcpyHostToDevice, ctx->stream));
+    if (alt_bytes) CU(cudaMemcpyAsync(sb + o_alt, alt_pool, (size_t)alt_bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
-  const int64_t offset = refp - start1;               // rpc.py:58-61
-  if (offset <= R.len) push(samp, refp, '=', R.len - offset, (uint64_t)offset);
-  if (dn.empty() || dn.back().op == 'D')
-    return fail(ctx, MG_EVALUE, "a deletion crosses the end of the region: the reference's node list would end in 'D' "
-                "(readgenerate.py:192 assumes it never does); trim the BED region or the VCF");
-  if (bad) return fail(ctx, MG_EVALUE, "a variant reaches beyond the region, or positions / node lengths exceed 2^31 (haplotypes 2^32)");
-  const size_t nn = dn.size();
-  C->n_nodes = (int64_t)nn;
-  C->p_min = start1;                                  // readgenerate.py:192: nodes[0].ps
-  C->p_max = start1 + ((int64_t)dn.back().key) + dn.back().oplen;   // nodes[-1].ps + nodes[-1].oplen (last node is not 'D')
-  const int64_t hap_len = C->p_max - C->p_min;
-  if (hap_len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "haplotype of %lld bases exceeds 2^32", (long long)hap_len);
+  MgWalkParams W;
+  W.pos = reinterpret_cast<int64_t *>(sb + o_pos); W.oplen = reinterpret_cast<int64_t *>(sb + o_oplen);
+  W.alt_off = reinterpret_cast<int64_t *>(sb + o_altoff); W.op = sb + o_op;
+  W.n_var = V; W.start1 = start1; W.region_len = R.len;
+  W.nxt = reinterpret_cast<uint32_t *>(sb + o_nxt);
+  W.jump[0] = reinterpret_cast<uint32_t *>(sb + o_j0); W.jump[1] = reinterpret_cast<uint32_t *>(sb + o_j1);
+  W.mark = sb + o_mark; W.pred = reinterpret_cast<int32_t *>(sb + o_pred);
+  W.packed = reinterpret_cast<int64_t *>(sb + o_packed); W.scanned = reinterpret_cast<int64_t *>(sb + o_scanned);
+  W.scan_tmp = reinterpret_cast<int64_t *>(sb + o_tmp);
+  W.nodes = C->d_nodes; W.node_alt = reinterpret_cast<uint32_t *>(sb + o_nalt);
+  W.sum = reinterpret_cast<MgWalkSummary *>(sb + o_sum);
+  ctx->total_launches += mg_launch_walk(W, ctx->stream) + 4;   // + exception count and its scan
+  // exception runs of the copy: count per node, scan
+  int64_t *e_cnt = reinterpret_cast<int64_t *>(sb + o_ecnt), *e_off = reinterpret_cast<int64_t *>(sb + o_eoff);
+  mg_launch_exc_count(C->d_nodes, W.node_alt, W.sum, (int)max_nodes, start1, sb + o_alt, R.d_exc, (int)R.exc.size(), e_cnt, ctx->stream);
+  mg_launch_scan_i64(e_cnt, e_off, (int64_t)max_nodes, W.scan_tmp, ctx->stream);
+  CU(cudaGetLastError());
+  MgWalkSummary sum;
+  int64_t n_exc = 0;
+  CU(cudaMemcpyAsync(&sum, W.sum, sizeof sum, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&n_exc, e_off + max_nodes, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  tm.lap("enqueue walk");
+  CU(cudaStreamSynchronize(ctx->stream));             // also: the caller's arrays have been consumed
   tm.lap("walk");
 
-  // -- upload + device builds
-  const int64_t alt_bytes = n_var ? alt_off[n_var] : 0;
+  if (sum.err != ~0ull) {
+    const long long i = (long long)(sum.err >> 8);
+    switch ((int)(sum.err & 0xFF)) {
+      case 1: return fail(ctx, MG_EVALUE, "SNP at %lld has an ALT of length %lld", (long long)pos[i], (long long)(alt_off[i + 1] - alt_off[i]));
+      case 2: return fail(ctx, MG_EVALUE, "insertion at %lld: oplen %lld does not match its ALT", (long long)pos[i], (long long)oplen[i]);
+      default: return fail(ctx, MG_EVALUE, "variant %lld has op %d (expected X, I or D) or a negative length", i, (int)op[i]);
+    }
+  }
+  if (sum.n_nodes == 0 || sum.ends_in_d)
+    return fail(ctx, MG_EVALUE, "a deletion crosses the end of the region: the reference's node list would end in 'D' "
+                "(readgenerate.py:192 assumes it never does); trim the BED region or the VCF");
+  if (sum.bad) return fail(ctx, MG_EVALUE, "a variant reaches beyond the region, or positions / node lengths exceed 2^31 (haplotypes 2^32)");
+  const size_t nn = (size_t)sum.n_nodes;
+  const int64_t hap_len = sum.hap_len;
+  if (hap_len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "haplotype of %lld bases exceeds 2^32", (long long)hap_len);
+  C->n_nodes = (int64_t)nn;
+  C->p_min = start1;                                  // readgenerate.py:192: nodes[0].ps
+  C->p_max = start1 + hap_len;                        // nodes[-1].ps + nodes[-1].oplen (the last node is never 'D')
+  C->n_exc = n_exc;
+
+  // -- device builds that need the sizes: exception runs, haplotype, block table
   C->hap_words = (hap_len + 15) / 16;
   C->n_blk = (int)((hap_len >> BLK_SHIFT) + 1);
-  C->owner = ctx;
-  CU(pool_get(ctx, (void **)&C->d_nodes, sizeof(MgNode) * nn));
   CU(pool_get(ctx, (void **)&C->d_hap, sizeof(uint32_t) * (C->hap_words + 2 * MG_HAP_PAD)));
   CU(pool_get(ctx, (void **)&C->d_blk, sizeof(uint32_t) * C->n_blk));
-  CU(pool_get(ctx, (void **)&C->d_exc, sizeof(MgExc) * std::max<size_t>(1, C->exc.size())));
-  CU(cudaMemcpyAsync(C->d_nodes, dn.data(), sizeof(MgNode) * nn, cudaMemcpyHostToDevice, ctx->stream));
-  if (!C->exc.empty()) CU(cudaMemcpyAsync(C->d_exc, C->exc.data(), sizeof(MgExc) * C->exc.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(C->d_hap, 0, sizeof(uint32_t) * (C->hap_words + 2 * MG_HAP_PAD), ctx->stream));
-  const size_t ns = seg_start.size();
-  if (ns && hap_len > 0) {
-    // scratch layout: [seg_src u64 x ns][seg_start u32 x ns][alt bytes]
-    size_t o_start = 8 * ns, o_alt = o_start + ((4 * ns + 15) & ~(size_t)15);
-    CU(ctx->s_str.need(o_alt + (size_t)alt_bytes + 16));
-    uint8_t *sb = ctx->s_str.as<uint8_t>();
-    CU(cudaMemcpyAsync(sb, seg_src.data(), 8 * ns, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(sb + o_start, seg_start.data(), 4 * ns, cudaMemcpyHostToDevice, ctx->stream));
-    if (alt_bytes) CU(cudaMemcpyAsync(sb + o_alt, alt_pool, (size_t)alt_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    mg_launch_hap_build(R.d_ref + MG_HAP_PAD, sb + o_alt, reinterpret_cast<uint32_t *>(sb + o_start),
-                        reinterpret_cast<uint64_t *>(sb), (int)ns, (uint32_t)hap_len, C->d_hap + MG_HAP_PAD, C->hap_words, ctx->stream);
-    ctx->total_launches++;
-  }
+  CU(pool_get(ctx, (void **)&C->d_exc, sizeof(MgExc) * std::max<size_t>(1, (size_t)n_exc)));
+  if (n_exc) mg_launch_exc_write(C->d_nodes, W.node_alt, W.sum, (int)max_nodes, start1, sb + o_alt, R.d_exc, (int)R.exc.size(), e_off, C->d_exc, ctx->stream);
+  CU(cudaMemsetAsync(C->d_hap, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
+  CU(cudaMemsetAsync(C->d_hap + MG_HAP_PAD + C->hap_words, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
+  if (hap_len > 0)
+    mg_launch_hap_build(R.d_ref + MG_HAP_PAD, sb + o_alt, C->d_nodes, W.node_alt, (int)nn, start1, (uint32_t)hap_len,
+                        C->d_hap + MG_HAP_PAD, C->hap_words, ctx->stream);
   mg_launch_blk_table(C->d_nodes, (int)nn, C->d_blk, C->n_blk, BLK_SHIFT, ctx->stream);
-  ctx->total_launches++;
+  ctx->total_launches += 2 + (n_exc ? 1 : 0);
   CU(cudaGetLastError());
-  tm.lap("enqueue");
-  CU(cudaStreamSynchronize(ctx->stream));   // host vectors above go out of scope
-  tm.lap("sync");
+  tm.lap("enqueue build");                            // stream-ordered: units launched next wait for these kernels
 
   int64_t id = ctx->next_id++;
   if (p_min) *p_min = C->p_min;
@@ -548,7 +548,9 @@ int mg_copy_haplotype(mg_ctx *ctx, int64_t copy_id, uint8_t *out, int64_t cap) {
   CU(cudaStreamSynchronize(ctx->stream));
   if (C.hap_words) CU(cudaMemcpy(w.data(), C.d_hap + MG_HAP_PAD, 4 * (size_t)C.hap_words, cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n; i++) out[i] = (uint8_t)("ACGT"[(w[i >> 4] >> (2 * (i & 15))) & 3]);
-  for (const MgExc &e : C.exc) for (uint32_t q = 0; q < e.len; q++) out[e.start + q] = (uint8_t)e.byte;
+  std::vector<MgExc> exc((size_t)C.n_exc);
+  if (C.n_exc) CU(cudaMemcpy(exc.data(), C.d_exc, sizeof(MgExc) * exc.size(), cudaMemcpyDeviceToHost));
+  for (const MgExc &e : exc) for (uint32_t q = 0; q < e.len; q++) out[e.start + q] = (uint8_t)e.byte;
   return MG_OK;
 }
 
@@ -571,7 +573,7 @@ static int fill_unit_params(mg_ctx *ctx, const mg_unit_desc *d, MgUnitParams &P,
     P.hap = C.d_hap + MG_HAP_PAD; P.hap_len = (uint32_t)(C.p_max - C.p_min); P.p_min = C.p_min;
     P.nodes = C.d_nodes; P.n_nodes = (int)C.n_nodes;
     P.blk = C.d_blk; P.blk_shift = BLK_SHIFT; P.n_blk = C.n_blk;
-    P.exc = C.d_exc; P.n_exc = (int)C.exc.size();
+    P.exc = C.d_exc; P.n_exc = (int)C.n_exc;
   }
   P.cum_tlen = ctx->m_tlen.as<double>(); P.n_tlen = ctx->n_tlen; P.rlen = ctx->rlen;
   P.tlen_alias = ctx->has_tlen_alias ? ctx->m_tlen_alias.as<uint32_t>() : nullptr;

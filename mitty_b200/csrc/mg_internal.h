@@ -75,8 +75,30 @@ struct MgCorruptParams {     // standalone corrupt-reads over FASTQ resident in 
 // launchers (all asynchronous on `st`)
 void mg_launch_pack_ref(const uint8_t *raw, int64_t len, uint32_t *packed, uint32_t *exc_cnt, int64_t *exc_start,
                         uint8_t *exc_byte, int64_t *exc_end, uint32_t exc_cap, cudaStream_t st);
-void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const uint32_t *seg_start, const uint64_t *seg_src,
-                         int n_seg, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st);
+// device node-list walk (k_walk_*): inputs are the copy's variants, sorted by POS
+struct MgWalkSummary {
+  unsigned long long err;     // (variant index << 8 | code) of the first invalid accepted variant, ~0 if none
+  long long n_nodes, hap_len; // nodes written; p_max - p_min
+  uint32_t i0; int32_t last;  // first / last accepted variant
+  int32_t ends_in_d, bad;
+};
+
+struct MgWalkParams {
+  const int64_t *pos, *oplen, *alt_off; const uint8_t *op;
+  int n_var; int64_t start1, region_len;
+  uint32_t *nxt, *jump[2]; uint8_t *mark; int32_t *pred;
+  int64_t *packed, *scanned, *scan_tmp;
+  MgNode *nodes; uint32_t *node_alt;
+  MgWalkSummary *sum;
+};
+
+int mg_launch_walk(const MgWalkParams &W, cudaStream_t st);   // -> number of kernels launched
+void mg_launch_exc_count(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes, int64_t start1,
+                         const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *cnt, cudaStream_t st);
+void mg_launch_exc_write(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes, int64_t start1,
+                         const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *off, MgExc *out, cudaStream_t st);
+void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const MgNode *nodes, const uint32_t *node_alt,
+                         int n_seg, int64_t start1, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st);
 void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st);
 void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
                         cudaStream_t st);

@@ -95,36 +95,248 @@ void mg_launch_pack_ref(const uint8_t *raw, int64_t len, uint32_t *packed, uint3
 }
 
 // ------------------------------------------------------------------------------------------
-// k_hap_build: one thread per 16-base haplotype word.  Segments (the non-'D' nodes) tile the
-// haplotype: seg_start[k] .. seg_start[k+1].  seg_src bit 63 = 1 -> alt pool byte offset,
-// else base offset into the packed reference.
+// k_walk_*: the node list of one chromosome copy (rpc.create_node_list, rpc.py:38-116) on the device.
+//
+// The reference walks the variants in order and skips every variant with v.pos < ref_pos (rpc.py:55),
+// where ref_pos is where the previously ACCEPTED variant left the reference cursor.  That cursor
+// depends only on the accepted variant itself -- end_ref(i) = pos+1 (SNP, insertion) or pos+1+oplen
+// (deletion) -- so the accepted variants form a chain i0 -> nxt(i0) -> nxt(nxt(i0)) ... with
+// nxt(i) = first j with pos[j] >= end_ref(i) (POS is sorted: the records come from an indexed
+// fetch).  The chain is marked by pointer doubling (ceil(log2 V) rounds), every accepted variant
+// then sizes its nodes (an optional '=' run up to it, then X / I / D), one exclusive scan of
+// (node count, sample-space advance) places them, and a last kernel writes the node table.
+
+#define MG_WALK_ADV_BITS 34
+#define MG_WALK_ADV_MASK ((1ull << MG_WALK_ADV_BITS) - 1)
+
+__device__ __forceinline__ int64_t walk_end_ref(const int64_t *pos, const uint8_t *op, const int64_t *oplen, int i) {
+  return pos[i] + 1 + (op[i] == 'D' ? oplen[i] : 0);
+}
+
+__device__ __forceinline__ uint32_t walk_lower_bound(const int64_t *pos, int V, int64_t x) {   // first j with pos[j] >= x
+  int lo = 0, hi = V;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (pos[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return (uint32_t)lo;
+}
+
+__device__ __forceinline__ void walk_error(MgWalkSummary *sum, int idx, int code) {   // the first error in variant order wins
+  atomicMin(&sum->err, ((unsigned long long)(uint32_t)idx << 8) | (unsigned long long)code);
+}
+
+__global__ void __launch_bounds__(256) k_walk_next(const int64_t *__restrict__ pos, const uint8_t *__restrict__ op,
+                                                   const int64_t *__restrict__ oplen, int V, int64_t start1, uint32_t *__restrict__ nxt,
+                                                   uint32_t *__restrict__ jump, uint8_t *__restrict__ mark, int32_t *__restrict__ pred,
+                                                   MgWalkSummary *sum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    sum->i0 = walk_lower_bound(pos, V, start1);      // variants before the region start are skipped (rpc.py:55)
+    sum->last = -1; sum->err = ~0ull; sum->n_nodes = 0; sum->hap_len = 0; sum->ends_in_d = 0; sum->bad = 0;
+  }
+  if (i >= V) return;
+  const uint32_t j = walk_lower_bound(pos, V, walk_end_ref(pos, op, oplen, i));
+  nxt[i] = j; jump[i] = j; mark[i] = 0; pred[i] = -1;
+}
+
+// one doubling round: marked variants mark the variant 2^k links ahead, links double
+__global__ void __launch_bounds__(256) k_walk_round(const uint32_t *__restrict__ jin, uint32_t *__restrict__ jout, uint8_t *mark,
+                                                    const MgWalkSummary *__restrict__ sum, int V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const uint32_t j = jin[i];
+  const bool first = (uint32_t)i == sum->i0;
+  if (first) mark[i] = 1;
+  if ((first || mark[i]) && j < (uint32_t)V) mark[j] = 1;
+  jout[i] = j < (uint32_t)V ? jin[j] : (uint32_t)V;
+}
+
+__global__ void __launch_bounds__(256) k_walk_pred(const uint32_t *__restrict__ nxt, const uint8_t *__restrict__ mark,
+                                                   int32_t *__restrict__ pred, MgWalkSummary *sum, int V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V || !mark[i]) return;
+  const uint32_t j = nxt[i];
+  if (j < (uint32_t)V) pred[j] = i; else sum->last = i;
+}
+
+// per accepted variant: node count and sample-space advance, packed for one scan; validation
+__global__ void __launch_bounds__(256) k_walk_measure(const int64_t *__restrict__ pos, const uint8_t *__restrict__ op,
+                                                      const int64_t *__restrict__ oplen, const int64_t *__restrict__ alt_off,
+                                                      const uint8_t *__restrict__ mark, const int32_t *__restrict__ pred, int V,
+                                                      int64_t start1, int64_t region_len, int64_t *__restrict__ packed, MgWalkSummary *sum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > V) return;
+  if (i == V || !mark[i]) { packed[i] = 0; return; }
+  const int64_t R = pred[i] < 0 ? start1 : walk_end_ref(pos, op, oplen, pred[i]);
+  const int64_t vp = pos[i], alt_len = alt_off[i + 1] - alt_off[i];
+  int64_t delta, adv, cnt;
+  if (op[i] == 'X') {                                   // rpc.py:75-87
+    delta = vp - R; cnt = (delta > 0) + 1; adv = delta + 1;
+    if (alt_len != 1) walk_error(sum, i, 1);
+  } else if (op[i] == 'I') {                            // rpc.py:90-102
+    delta = vp + 1 - R; cnt = 2; adv = delta + oplen[i];
+    if (alt_len - 1 != oplen[i] || oplen[i] < 0) walk_error(sum, i, 2);
+  } else if (op[i] == 'D') {                            // rpc.py:105-116
+    delta = vp + 1 - R; cnt = 2; adv = delta;
+    if (oplen[i] < 0) walk_error(sum, i, 3);
+  } else {
+    delta = 0; cnt = 0; adv = 0;
+    walk_error(sum, i, 3);
+  }
+  if ((R - start1) + delta > region_len || oplen[i] > 0x7FFFFFFFll || adv < 0 || adv > (int64_t)MG_WALK_ADV_MASK) { sum->bad = 1; adv = 0; }
+  packed[i] = (int64_t)(((unsigned long long)cnt << MG_WALK_ADV_BITS) | (unsigned long long)adv);
+}
+
+// node table + per-node alt-pool offsets; the thread past the last variant writes the tail node
+// (rpc.py:58-61) and the summary
+__global__ void __launch_bounds__(256) k_walk_nodes(const int64_t *__restrict__ pos, const uint8_t *__restrict__ op,
+                                                    const int64_t *__restrict__ oplen, const int64_t *__restrict__ alt_off,
+                                                    const uint8_t *__restrict__ mark, const int32_t *__restrict__ pred, int V,
+                                                    int64_t start1, int64_t region_len, const int64_t *__restrict__ scanned,
+                                                    MgNode *__restrict__ nodes, uint32_t *__restrict__ node_alt, MgWalkSummary *sum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > V) return;
+  const unsigned long long pre = (unsigned long long)scanned[i];
+  uint32_t k = (uint32_t)(pre >> MG_WALK_ADV_BITS);
+  int64_t S = (int64_t)(pre & MG_WALK_ADV_MASK);          // sample position relative to p_min
+  if (i == V) {
+    const int last = sum->last;
+    const int64_t refp = last < 0 ? start1 : walk_end_ref(pos, op, oplen, last);
+    const int64_t offset = refp - start1;
+    if (offset <= region_len) {
+      if (S >= 0xFFF00000ll || refp >= (1ll << 31)) sum->bad = 1;
+      nodes[k] = MgNode{(uint32_t)S, (int32_t)refp, (int32_t)(region_len - offset), '='};
+      node_alt[k] = 0;
+      sum->n_nodes = (long long)k + 1; sum->hap_len = S + (region_len - offset); sum->ends_in_d = 0;
+    } else {                                              // a deletion crossed the region end: the list ends in 'D'
+      sum->n_nodes = k; sum->hap_len = S; sum->ends_in_d = 1;
+    }
+    return;
+  }
+  if (!mark[i]) return;
+  const int64_t R = pred[i] < 0 ? start1 : walk_end_ref(pos, op, oplen, pred[i]);
+  const int64_t vp = pos[i];
+  const uint8_t o = op[i];
+  const int64_t delta = (o == 'X') ? vp - R : vp + 1 - R;
+  if (S + delta + (o == 'I' ? oplen[i] : 1) >= 0xFFF00000ll || vp + 1 + (o == 'D' ? oplen[i] : 0) >= (1ll << 31)) { sum->bad = 1; return; }
+  if (delta > 0) {
+    nodes[k] = MgNode{(uint32_t)S, (int32_t)R, (int32_t)delta, '='};
+    node_alt[k] = 0;
+    k++; S += delta;
+  }
+  if (o == 'X') { nodes[k] = MgNode{(uint32_t)S, (int32_t)vp, 1, 'X'}; node_alt[k] = (uint32_t)alt_off[i]; }
+  else if (o == 'I') { nodes[k] = MgNode{(uint32_t)S, (int32_t)(vp + 1), (int32_t)oplen[i], 'I'}; node_alt[k] = (uint32_t)(alt_off[i] + 1); }
+  else if (o == 'D') { nodes[k] = MgNode{(uint32_t)S /* ps + 1, rpc.py:127 */, (int32_t)(vp + 1 + oplen[i]), (int32_t)oplen[i], 'D'}; node_alt[k] = 0; }
+}
+
+int mg_launch_walk(const MgWalkParams &W, cudaStream_t st) {   // -> kernels launched
+  const int V = W.n_var;
+  const unsigned g = (unsigned)((V + 1 + 255) / 256);
+  k_walk_next<<<g, 256, 0, st>>>(W.pos, W.op, W.oplen, V, W.start1, W.nxt, W.jump[0], W.mark, W.pred, W.sum);
+  int cur = 0, launches = 6;       // next, measure, 3 x scan, nodes
+  if (V > 0) {
+    int rounds = 1;
+    while ((1ll << rounds) < (long long)V + 1) rounds++;
+    for (int r = 0; r < rounds; r++) { k_walk_round<<<g, 256, 0, st>>>(W.jump[cur], W.jump[cur ^ 1], W.mark, W.sum, V); cur ^= 1; }
+    k_walk_pred<<<g, 256, 0, st>>>(W.nxt, W.mark, W.pred, W.sum, V);
+    launches += rounds + 1;
+  }
+  k_walk_measure<<<g, 256, 0, st>>>(W.pos, W.op, W.oplen, W.alt_off, W.mark, W.pred, V, W.start1, W.region_len, W.packed, W.sum);
+  mg_launch_scan_i64(W.packed, W.scanned, (int64_t)V + 1, W.scan_tmp, st);
+  k_walk_nodes<<<g, 256, 0, st>>>(W.pos, W.op, W.oplen, W.alt_off, W.mark, W.pred, V, W.start1, W.region_len, W.scanned, W.nodes, W.node_alt, W.sum);
+  return launches;
+}
+
+// exception runs of a copy in sample coordinates: the region's non-ACGT runs under every '='
+// node, non-ACGT bytes of inserted / substituted alleles.  Count, scan, write.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_exc_map(const MgNode *__restrict__ nodes, const uint32_t *__restrict__ node_alt,
+                                                 const MgWalkSummary *__restrict__ sum, int max_nodes, int64_t start1,
+                                                 const uint8_t *__restrict__ alt_pool, const MgExc *__restrict__ rexc, int n_rexc,
+                                                 int64_t *cnt_or_off, MgExc *__restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= max_nodes) return;
+  if (k >= sum->n_nodes) { if (!WRITE) cnt_or_off[k] = 0; return; }
+  const MgNode nd = nodes[k];
+  int64_t c = WRITE ? cnt_or_off[k] : 0;
+  if (nd.op == '=' && nd.oplen > 0) {
+    const int64_t a = (int64_t)nd.pr - start1, b = a + nd.oplen;
+    int lo = 0, hi = n_rexc;                                  // first run that ends after a
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)rexc[mid].start + rexc[mid].len <= a) lo = mid + 1; else hi = mid;
+    }
+    for (int q = lo; q < n_rexc && (int64_t)rexc[q].start < b; q++) {
+      const int64_t s0 = max(a, (int64_t)rexc[q].start), e0 = min(b, (int64_t)rexc[q].start + rexc[q].len);
+      if (WRITE) out[c] = MgExc{(uint32_t)(nd.key + (s0 - a)), (uint32_t)(e0 - s0), rexc[q].byte, 0};
+      c++;
+    }
+  } else if (nd.op == 'X' || nd.op == 'I') {
+    const uint8_t *alt = alt_pool + node_alt[k];
+    int run = -1;                                             // start of the current run of equal non-ACGT bytes
+    for (int t = 0; t <= nd.oplen; t++) {
+      const bool exc = t < nd.oplen && mg_base_code(alt[t]) > 3;
+      if (run >= 0 && (!exc || alt[t] != alt[run])) {
+        if (WRITE) out[c] = MgExc{(uint32_t)(nd.key + run), (uint32_t)(t - run), alt[run], 0};
+        c++; run = -1;
+      }
+      if (exc && run < 0) run = t;
+    }
+  }
+  if (!WRITE) cnt_or_off[k] = c;
+}
+
+void mg_launch_exc_count(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes, int64_t start1,
+                         const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *cnt, cudaStream_t st) {
+  k_exc_map<false><<<(unsigned)((max_nodes + 255) / 256), 256, 0, st>>>(nodes, node_alt, sum, max_nodes, start1, alt_pool, rexc, n_rexc, cnt, nullptr);
+}
+
+void mg_launch_exc_write(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes, int64_t start1,
+                         const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *off, MgExc *out, cudaStream_t st) {
+  k_exc_map<true><<<(unsigned)((max_nodes + 255) / 256), 256, 0, st>>>(nodes, node_alt, sum, max_nodes, start1, alt_pool, rexc, n_rexc, off, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_hap_build: one thread per 16-base haplotype word.  The non-'D' nodes tile the haplotype:
+// node k covers [key[k], key[k+1]) ('D' nodes share the key of their successor and are empty).
+// '=' nodes copy from the packed reference, 'X' / 'I' nodes from the alt pool.
+
+__device__ __forceinline__ uint64_t hap_node_src(const MgNode &nd, uint32_t alt, int64_t start1) {
+  return nd.op == '=' ? (uint64_t)((int64_t)nd.pr - start1) : ((1ull << 63) | (uint64_t)alt);
+}
 
 __global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ ref, const uint8_t *__restrict__ alt_pool,
-                                                   const uint32_t *__restrict__ seg_start, const uint64_t *__restrict__ seg_src,
-                                                   int n_seg, uint32_t hap_len, uint32_t *__restrict__ hap, int64_t hap_words) {
+                                                   const MgNode *__restrict__ nodes, const uint32_t *__restrict__ node_alt,
+                                                   int n_seg, int64_t start1, uint32_t hap_len, uint32_t *__restrict__ hap, int64_t hap_words) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= hap_words) return;
   uint64_t s0 = (uint64_t)w * 16;
   if (s0 >= hap_len) { hap[w] = 0; return; }
-  // last segment with seg_start <= s0
+  // last node with key <= s0 (of equal keys the later one: never the empty 'D')
   int lo = 0, hi = n_seg - 1;
   while (lo < hi) {
     int mid = (lo + hi + 1) >> 1;
-    if ((uint64_t)seg_start[mid] <= s0) lo = mid; else hi = mid - 1;
+    if ((uint64_t)nodes[mid].key <= s0) lo = mid; else hi = mid - 1;
   }
   int k = lo;
-  uint64_t seg_end = (k + 1 < n_seg) ? seg_start[k + 1] : hap_len;
-  uint64_t src = seg_src[k];
+  MgNode nd = nodes[k];
+  uint64_t seg_end = (k + 1 < n_seg) ? nodes[k + 1].key : hap_len;
+  uint64_t src = hap_node_src(nd, node_alt[k], start1);
   uint32_t word;
   if (!(src >> 63) && s0 + 16 <= seg_end) {
-    word = mg_codes16(ref, (int64_t)(src + (s0 - seg_start[k])));        // whole word from the reference
+    word = mg_codes16(ref, (int64_t)(src + (s0 - nd.key)));        // whole word from the reference
   } else {
     word = 0;
     for (int i = 0; i < 16; i++) {
       uint64_t s = s0 + i;
       if (s >= hap_len) break;
-      while (s >= seg_end) { k++; seg_end = (k + 1 < n_seg) ? seg_start[k + 1] : hap_len; src = seg_src[k]; }
-      uint64_t off = s - seg_start[k];
+      while (s >= seg_end) {
+        k++; nd = nodes[k];
+        seg_end = (k + 1 < n_seg) ? nodes[k + 1].key : hap_len;
+        src = hap_node_src(nd, node_alt[k], start1);
+      }
+      uint64_t off = s - nd.key;
       uint32_t code;
       if (src >> 63) {
         code = mg_base_code(alt_pool[(src & ~(1ull << 63)) + off]);
@@ -139,10 +351,10 @@ __global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ 
   hap[w] = word;
 }
 
-void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const uint32_t *seg_start, const uint64_t *seg_src,
-                         int n_seg, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st) {
+void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const MgNode *nodes, const uint32_t *node_alt,
+                         int n_seg, int64_t start1, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st) {
   if (hap_words == 0) return;
-  k_hap_build<<<(unsigned)((hap_words + 255) / 256), 256, 0, st>>>(ref, alt_pool, seg_start, seg_src, n_seg, hap_len, hap, hap_words);
+  k_hap_build<<<(unsigned)((hap_words + 255) / 256), 256, 0, st>>>(ref, alt_pool, nodes, node_alt, n_seg, start1, hap_len, hap, hap_words);
 }
 
 __global__ void __launch_bounds__(256) k_blk_table(const MgNode *__restrict__ nodes, int n_nodes, uint32_t *__restrict__ blk,

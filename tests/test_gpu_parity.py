@@ -81,6 +81,52 @@ def test_edge_nodes_and_haplotypes(eng):
       nl.free()
 
 
+@pytest.mark.parametrize('seed', [1, 2, 3, 4])
+def test_device_walk_dense_overlapping_variants(eng, seed):
+  """The device node-list walk (chain marking by pointer doubling) against the oracle's sequential
+  walk on variant sets built to stress the greedy skip rule (rpc.py:55): long deletions that swallow
+  runs of later variants, chains of overlapping deletions, several records at one POS, variants
+  before the region start, non-ACGT bytes in ALT alleles and in the reference."""
+  import mitty_b200.simulation.rpc as rpc
+  rs = np.random.RandomState(seed)
+  n = 6000
+  ref = synth.synth_contig(n, seed=100 + seed)
+  ref[1000:1100] = ord('N'); ref[3000] = ord('R'); ref[3500:3503] = ord('n')
+  bed_start = 40
+  recs = []
+  for _ in range([400, 1500, 3000, 800][seed - 1]):
+    pos = int(rs.randint(1, n - 560))                 # no deletion reaches the region end (that case is rejected, below)
+    kind = rs.randint(0, 3)
+    r0 = chr(ref[pos - 1]).upper()
+    r0 = r0 if r0 in 'ACGT' else 'A'
+    if kind == 0:
+      recs.append((pos, r0, 'ACGTN'[rs.randint(0, 5)], 'X', 0))
+    elif kind == 1:
+      ol = int(rs.randint(1, 40))
+      recs.append((pos, r0, r0 + ''.join('ACGTRN'[i] for i in rs.randint(0, 6, size=ol)), 'I', ol))
+    else:
+      ol = int(rs.randint(1, [8, 30, 50, 200][seed - 1]))
+      recs.append((pos, 'A' * (ol + 1), 'A', 'D', ol))
+  recs.sort(key=lambda t: t[0])                       # stable: records at one POS keep their order
+  region = ref[bed_start:n - 300]
+  vl = vcfio.VariantList.from_variants([vcfio.Variant(*t) for t in recs])
+  want = oracle.create_node_list(region, bed_start + 1, H.oracle_cv(vl))
+  assert want[-1][2] == '=' and sum(1 for w in want if w[2] != '=') < len(recs)     # some records were skipped
+  nl = rpc.create_node_list(region, bed_start + 1, vl, engine=eng)
+  assert nl.tuples() == want
+  # the materialised haplotype (with its non-ACGT exception runs) is the concatenation of the node sequences
+  cp = eng.build_copy(eng.load_region(region, bed_start), vl)
+  assert eng.copy_haplotype(cp).tobytes().decode() == ''.join(w[4] for w in want)
+  nl.free()
+
+
+def test_unsorted_variants_are_rejected(eng):
+  import mitty_b200.simulation.rpc as rpc
+  vl = vcfio.VariantList.from_variants([vcfio.Variant(12, 'A', 'C', 'X', 0), vcfio.Variant(5, 'A', 'T', 'X', 0)])
+  with pytest.raises(ValueError):
+    rpc.create_node_list(H.TINY_SEQ, 1, vl, engine=eng)
+
+
 def test_deletion_across_region_end_is_rejected(eng):
   import mitty_b200.simulation.rpc as rpc
   vl = vcfio.VariantList.from_variants([vcfio.Variant(20, 'GTTAC', 'G', 'D', 4)])

@@ -18,6 +18,18 @@ def cli(verbose):
   logging.basicConfig(level=[logging.ERROR, logging.WARNING, logging.INFO, logging.DEBUG][min(verbose, 3)])
 
 
+@cli.command('filter-variants', short_help='Remove complex variants from VCF')
+@click.argument('vcfin', type=click.Path(exists=True))
+@click.argument('sample')
+@click.argument('bed')
+@click.argument('vcfout', type=click.Path())
+def filter_vcf(vcfin, sample, bed, vcfout):
+  """Subset VCF for given sample, apply BED file and filter out complex variants
+   making it suitable to use for read generation (cli.py:20-29 of the reference)"""
+  import mitty_b200.lib.vcfio as mvio
+  mvio.prepare_variant_file(vcfin, sample, bed, vcfout)
+
+
 @cli.command('list-read-models')
 @click.option('-d', type=click.Path(exists=True), help='List models in this directory')
 def list_read_models(d):

@@ -16,6 +16,7 @@ The per-copy result is a ``VariantList``: flat numpy arrays ready for the C-ABI
 (``mg_copy_build``), which also behaves like the reference's ``list`` of ``Variant`` objects.
 """
 import gzip
+import time
 import logging
 import threading
 
@@ -101,10 +102,12 @@ def _open_bytes(fname):
 
 class _Contig(object):
   """Records of one contig as arrays over the file's bytes (no per-record Python objects)."""
-  __slots__ = ('pos', 'reflen', 'rs', 're', 'as_', 'ae', 'gt', 'ploidy', 'exotic', 'slow')
+  __slots__ = ('pos', 'reflen', 'rs', 're', 'as_', 'ae', 'gt', 'ploidy', 'exotic', 'slow', 'ls', 'le', 'f9e', 'ss', 'se')
 
-  def __init__(self, pos, rs, re_, as_, ae, gt, ploidy, exotic, slow):
+  def __init__(self, pos, rs, re_, as_, ae, gt, ploidy, exotic, slow, lines=None):
     self.pos, self.rs, self.re, self.as_, self.ae = pos, rs, re_, as_, ae
+    # byte ranges of the whole line, of its first nine columns and of the sample column (filter-variants)
+    self.ls, self.le, self.f9e, self.ss, self.se = lines if lines is not None else (None,) * 5
     self.reflen = re_ - rs
     self.gt, self.ploidy, self.exotic, self.slow = gt, ploidy, exotic, slow
 
@@ -117,7 +120,8 @@ class _Contig(object):
       return out
     cat = np.concatenate
     return _Contig(cat([self.pos, o.pos]), cat([self.rs, o.rs]), cat([self.re, o.re]), cat([self.as_, o.as_]), cat([self.ae, o.ae]),
-                   cat([widen(self.gt), widen(o.gt)]), cat([self.ploidy, o.ploidy]), cat([self.exotic, o.exotic]), slow)
+                   cat([widen(self.gt), widen(o.gt)]), cat([self.ploidy, o.ploidy]), cat([self.exotic, o.exotic]), slow,
+                   tuple(cat([a, b]) for a, b in zip((self.ls, self.le, self.f9e, self.ss, self.se), (o.ls, o.le, o.f9e, o.ss, o.se))))
 
 
 def _gt_tuple(fmt, s):
@@ -141,7 +145,9 @@ class VcfTable(object):
       raise NotImplementedError('BCF input needs htslib; convert to VCF text (plain or gzip)')
     data = _open_bytes(fname)
     self.buf = buf = np.frombuffer(data, dtype=np.uint8)
+    self.data = data
     self.contigs = {}
+    self.sample = sample
     h = 0 if data.startswith(b'#CHROM') else data.find(b'\n#CHROM') + 1
     if h == 0 and not data.startswith(b'#CHROM'):
       raise ValueError('No #CHROM header line in {}'.format(fname))
@@ -151,6 +157,7 @@ class VcfTable(object):
     if sample not in hdr[9:]:
       raise ValueError('Sample {} not in VCF (samples: {})'.format(sample, hdr[9:]))
     col = 9 + hdr[9:].index(sample)
+    self.header_end = h                                                 # the '##' meta lines are data[:h]
     body = min(he + 1, len(data))
     nl = np.flatnonzero(buf[body:] == 10) + body
     starts = np.concatenate([np.array([body], dtype=np.int64), nl + 1])
@@ -242,7 +249,8 @@ class VcfTable(object):
     for a, b in zip(run0.tolist(), run1.tolist()):
       name = cmat[a, :clen[a]].tobytes().decode()
       slow = {i - a: v for i, v in slow_all.items() if a <= i < b} if slow_all else {}
-      c = _Contig(pos[a:b], rs[a:b], re_[a:b], as_[a:b], ae[a:b], gt[a:b], ploidy[a:b], exotic[a:b], slow)
+      c = _Contig(pos[a:b], rs[a:b], re_[a:b], as_[a:b], ae[a:b], gt[a:b], ploidy[a:b], exotic[a:b], slow,
+                  (starts[a:b], ends[a:b], f8e[a:b], ss[a:b], se[a:b]))
       self.contigs[name] = self.contigs[name].merged(c) if name in self.contigs else c
 
   def fetch(self, contig, start, stop):
@@ -346,6 +354,46 @@ def load_variant_file(fname, sample, bed_fname):
   table = VcfTable(fname, sample)
   return [split_copies(region, table, *table.fetch(region[0], region[1], region[2]))
           for region in read_bed(bed_fname)]
+
+
+def prepare_variant_file(fname_in, sample, bed_fname, fname_out, write_mode='w'):
+  """filter-variants (vcfio.prepare_variant_file, vcfio.py:128-169): the VCF restricted to one sample
+  and to the BED regions, with complex calls removed -- a record is dropped when an allele the sample
+  carries has len(REF) > 1 and len(allele) > 1 and differs from REF.  As in the reference, a record
+  overlapping two regions is written once per region.  Output is VCF text (gzip if the name ends in
+  '.gz'); the meta lines are kept and the column header names only ``sample``."""
+  t0 = time.time()
+  table = VcfTable(fname_in, sample)
+  data = table.data
+  out = [data[:table.header_end], ('#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t' + sample + '\n').encode()]
+  v_cnt = fltr_cnt = 0
+  for region in read_bed(bed_fname):
+    contig, idx = table.fetch(region[0], region[1], region[2])
+    if idx.size == 0:
+      continue
+    c = table.contigs[contig]
+    cx = (c.reflen[idx] > 1) & ((c.ae - c.as_)[idx] > 1) & (c.gt[idx] == 1).any(axis=1)
+    for k, i in enumerate(idx.tolist()):
+      if i in c.slow:
+        ref, alleles, gt = c.slow[i]
+        cx[k] = any(len(ref) > 1 and len(alleles[g]) > 1 and alleles[g] != ref for g in gt if g is not None and g < len(alleles))
+      elif c.exotic[i]:
+        cx[k] = False
+    v_cnt += int(idx.size)
+    fltr_cnt += int(cx.sum())
+    for i in idx[~cx].tolist():
+      out.append(data[c.ls[i]:c.f9e[i]] + b'\t' + data[c.ss[i]:c.se[i]] + b'\n')
+  blob = b''.join(out)
+  if str(fname_out).endswith('.gz'):
+    with gzip.open(fname_out, 'wb') as fp:
+      fp.write(blob)
+  else:
+    with open(fname_out, 'wb') as fp:
+      fp.write(blob)
+  logger.debug('Processed {} variants'.format(v_cnt))
+  logger.debug('Filtered out {} complex variants'.format(fltr_cnt))
+  logger.debug('Took {} s'.format(time.time() - t0))
+  return v_cnt, fltr_cnt
 
 
 def from_variant_table(vt, region):

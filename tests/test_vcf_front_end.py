@@ -102,3 +102,34 @@ def test_parser_matches_synthetic_table(tmp_path):
     for a, b in zip(ref['v'], d['v']):
       assert np.array_equal(a.pos, b.pos) and np.array_equal(a.op, b.op) and np.array_equal(a.oplen, b.oplen)
       assert np.array_equal(a.alt_pool, b.alt_pool) and np.array_equal(a.alt_off, b.alt_off)
+
+
+def test_filter_variants(tmp_path):
+  """filter-variants (vcfio.py:128-169): one sample, BED-restricted, complex calls dropped; the result
+  feeds generate-reads' loader without the complex-variant error."""
+  from click.testing import CliRunner
+  from mitty_b200.cli import cli
+  body = (
+    '1\t10\t.\tA\tC\t.\tPASS\t.\tGT\t0|1\t1|1\n'
+    '1\t20\t.\tAT\tGC\t.\tPASS\t.\tGT\t1|0\t0|0\n'          # complex for S0, not carried by S1
+    '1\t30\t.\tAT\tA,GCC\t.\tPASS\t.\tGT\t1|1\t1|2\n'       # S1 carries the complex second ALT
+    '1\t40\t.\tA\tATT\t.\tPASS\t.\tGT:DP\t1|1:5\t0|1:7\n'
+    '1\t500\t.\tG\tT\t.\tPASS\t.\tGT\t1|1\t1|1\n'            # outside the BED
+    '2\t7\t.\tGCA\tG\t.\tPASS\t.\tGT\t1\t1\n'
+  )
+  vin = str(tmp_path / 'in.vcf'); open(vin, 'w').write(HDR + body)
+  bed = str(tmp_path / 'r.bed'); open(bed, 'w').write('1\t0\t100\n2\t0\t50\n')
+  for sample, kept in (('S0', [10, 30, 40, 7]), ('S1', [10, 20, 40, 7])):
+    vout = str(tmp_path / (sample + '.vcf.gz'))
+    res = CliRunner().invoke(cli, ['filter-variants', vin, sample, bed, vout], catch_exceptions=False)
+    assert res.exit_code == 0, res.output
+    text = gzip.open(vout, 'rt').read()
+    recs = [l.split('\t') for l in text.split('\n') if l and not l.startswith('#')]
+    assert [int(r[1]) for r in recs] == kept
+    assert all(len(r) == 10 for r in recs)
+    assert [l for l in text.split('\n') if l.startswith('#CHROM')][0].split('\t')[9:] == [sample]
+    assert text.startswith('##fileformat')
+    df = vcfio.load_variant_file(vout, sample, bed)                       # no complex-variant error any more
+    assert [d['region'][0] for d in df] == ['1', '2']
+  with pytest.raises(ValueError):
+    vcfio.load_variant_file(vin, 'S0', bed)

@@ -51,12 +51,14 @@ int mg_host_free(mg_ctx *ctx, void *p);
 int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double *cum_bq_mat, int n_mates,
                   int n_cycles, int n_bq, const double *phred_p, int rlen);
 
-/* production-mode tables derived from the model at load time (for tests / inspection):
- * alias_out u32[n_mates][n_cycles][1 << kshift] (kshift 6 or 7) = Vose alias rows
- * (prob24 << 7 | alias) of the per-cycle quality distribution; n64 = number of leading cycles for
- * which the 64-entry rows are exact (the emit kernel uses them when rlen <= n64);
- * err_out u32[128][4] = {thr, thr/3, 2*thr/3, 0} with thr = floor(phred_p[bq] * 2^32).          */
-int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t alias_cap, int32_t *n64, uint32_t *err_out);
+/* production-mode tables derived from the model at load time (for tests / inspection; the draw
+ * layout is documented at MgCorruptCtx in mitty_b200/csrc/mg_core.cuh):
+ * thr_out u32[n_mates][n_cycles] = per-cycle miscall thresholds floor(perr * 2^32), perr =
+ * sum_q P(q) phred_p[q]; alias_out u32[n_mates][n_cycles][2][1 << kshift] (kshift 6 or 7) = Vose
+ * alias rows (prob24 << 7 | alias) of the quality given a correct call ([0]) and given a miscall
+ * ([1]); n64 = number of leading cycles for which the 64-entry rows are exact (all mass on
+ * qualities < 64).                                                                              */
+int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t alias_cap, int32_t *n64, uint32_t *thr_out);
 
 /* ---- region: replaces fasta.fetch(chrom, start, end) + the str the worker keeps
  * (mitty/simulation/readgenerate.py:186).  ref_bytes = the region's bases as in the FASTA

@@ -69,7 +69,7 @@ struct mg_ctx {
   bool has_tlen_alias = false;   // n_tlen + 1 <= 1024 outcomes: 1024-entry alias table of the template-length model   // alias[0]: 64-entry rows, alias[1]: 128-entry rows
   int n_tlen = 0, n_mates = 0, n_cycles = 0, n_bq = 0, rlen = 0;
   int n64 = 0;   // leading cycles whose rows (all mates) put no mass on BQ >= 64: 64-entry alias rows are exact there
-  std::vector<uint32_t> h_alias[2]; std::vector<MgErr> h_err;
+  std::vector<uint32_t> h_alias[2]; std::vector<uint32_t> h_thr; std::vector<double> h_phred;
   std::vector<std::pair<void *, size_t>> pool;   // device blocks of freed copies, reused by the next build
   std::map<void *, size_t> block_size;
   // handles
@@ -138,9 +138,22 @@ std::vector<double> ss_left_probs(const double *cum, int n, int K, int clip) {
   return q;
 }
 
-// alias row of one (mate, cycle) of the quality model: outcome clipped to 93 (illumina.py:156)
-void build_alias_row(const double *cum, int n_bq, int K, uint32_t *out) {
-  vose(ss_left_probs(cum, n_bq, K, 93), K, 24, 7, out);
+// One (mate, cycle) of the quality model, outcome clipped to 93 (illumina.py:156): the miscall
+// probability perr = sum_q P(q) phred_p[q] as a 32-bit threshold and the two alias rows of the
+// quality given a correct call (out[0..K)) and given a miscall (out[K..2K)).  See MgCorruptCtx.
+uint32_t build_quality_rows(const double *cum, int n_bq, int K, const double *phred_p, uint32_t *out) {
+  const std::vector<double> q = ss_left_probs(cum, n_bq, K, 93);
+  std::vector<double> qe(K), qo(K);
+  double se = 0.0, so = 0.0;
+  for (int k = 0; k < K; k++) {
+    const double p = k < 100 ? phred_p[k] : 0.0;
+    qe[k] = q[k] * p; qo[k] = q[k] * (1.0 - p);
+    se += qe[k]; so += qo[k];
+  }
+  for (int k = 0; k < K; k++) { qe[k] = se > 0.0 ? qe[k] / se : q[k]; qo[k] = so > 0.0 ? qo[k] / so : q[k]; }
+  vose(qo, K, 24, 7, out);
+  vose(qe, K, 24, 7, out + K);
+  return se >= 1.0 ? 0xFFFFFFFFu : (se <= 0.0 ? 0u : (uint32_t)std::floor(se * 4294967296.0));
 }
 
 struct Timer {   // MG_TIMING=1: host-side section timings on stderr
@@ -278,14 +291,18 @@ int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double 
       const double at63 = n_bq > 63 ? row[63] : (n_bq ? row[n_bq - 1] : 0.0);   // mass on outcomes <= 63
       if (n_bq == 0 || at63 < 1.0) { if (c < n64) n64 = c; break; }
     }
+  ctx->h_thr.assign((size_t)n_mates * n_cycles, 0u);
   for (int t = 0; t < 2; t++) {
     const int K = 64 << t;
-    ctx->h_alias[t].assign((size_t)n_mates * n_cycles * K, 0u);
+    ctx->h_alias[t].assign((size_t)n_mates * n_cycles * 2 * K, 0u);
     for (size_t r = 0; r < (size_t)n_mates * n_cycles; r++)
-      if (t == 1 || (int)(r % n_cycles) < n64) build_alias_row(cum_bq_mat + r * n_bq, n_bq, K, ctx->h_alias[t].data() + r * K);
+      if (t == 1 || (int)(r % n_cycles) < n64)
+        ctx->h_thr[r] = build_quality_rows(cum_bq_mat + r * n_bq, n_bq, K, phred_p, ctx->h_alias[t].data() + r * 2 * K);
     CU(ctx->m_alias[t].need(4 * ctx->h_alias[t].size()));
     CU(cudaMemcpyAsync(ctx->m_alias[t].p, ctx->h_alias[t].data(), 4 * ctx->h_alias[t].size(), cudaMemcpyHostToDevice, ctx->stream));
   }
+  CU(ctx->m_err.need(4 * ctx->h_thr.size()));
+  CU(cudaMemcpyAsync(ctx->m_err.p, ctx->h_thr.data(), 4 * ctx->h_thr.size(), cudaMemcpyHostToDevice, ctx->stream));
   ctx->has_tlen_alias = (n_tlen + 1 <= MG_TLEN_K);
   if (ctx->has_tlen_alias) {
     std::vector<uint32_t> ta(MG_TLEN_K);
@@ -293,20 +310,12 @@ int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double 
     CU(ctx->m_tlen_alias.need(4 * MG_TLEN_K));
     CU(cudaMemcpy(ctx->m_tlen_alias.p, ta.data(), 4 * MG_TLEN_K, cudaMemcpyHostToDevice));
   }
-  ctx->h_err.assign(128, MgErr{0, 0, 0, 0});
-  for (int b = 0; b < 100; b++) {
-    double pe = phred_p[b];
-    uint32_t thr = pe >= 1.0 ? 0xFFFFFFFFu : (pe <= 0.0 ? 0u : (uint32_t)std::floor(pe * 4294967296.0));
-    ctx->h_err[b] = MgErr{thr, thr / 3u, (uint32_t)((2ull * thr) / 3ull), 0};
-  }
-  CU(ctx->m_err.need(sizeof(MgErr) * 128));
-  CU(cudaMemcpyAsync(ctx->m_err.p, ctx->h_err.data(), sizeof(MgErr) * 128, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->n_tlen = n_tlen; ctx->n_mates = n_mates; ctx->n_cycles = n_cycles; ctx->n_bq = n_bq; ctx->rlen = rlen; ctx->n64 = n64;
   return MG_OK;
 }
 
-int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t alias_cap, int32_t *n64, uint32_t *err_out) {
+int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t alias_cap, int32_t *n64, uint32_t *thr_out) {
   if (!ctx || ctx->rlen == 0) return fail(ctx, MG_EINVAL, "no read model loaded");
   if (kshift != 6 && kshift != 7) return fail(ctx, MG_EINVAL, "kshift must be 6 or 7");
   const std::vector<uint32_t> &h = ctx->h_alias[kshift - 6];
@@ -315,7 +324,7 @@ int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t al
     if (alias_cap < (int64_t)h.size()) return fail(ctx, MG_ECAP, "alias table needs %lld entries", (long long)h.size());
     memcpy(alias_out, h.data(), 4 * h.size());
   }
-  if (err_out) memcpy(err_out, ctx->h_err.data(), sizeof(MgErr) * 128);
+  if (thr_out) memcpy(thr_out, ctx->h_thr.data(), 4 * ctx->h_thr.size());
   return MG_OK;
 }
 
@@ -657,7 +666,8 @@ static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint
   if (pl > MG_QN_MAX || ml > MG_QN_MAX) return fail(ctx, MG_EVALUE, "sample / chromosome name too long for the qname buffers (%d)", MG_QN_MAX);
   P.corrupt = d->corrupt;
   P.cor.kshift = (L <= ctx->n64) ? 6 : 7;
-  P.cor.alias = ctx->m_alias[P.cor.kshift - 6].as<uint32_t>(); P.cor.err = ctx->m_err.as<MgErr>(); P.cor.n_cycles = ctx->n_cycles;
+  P.cor.alias = ctx->m_alias[P.cor.kshift - 6].as<uint32_t>(); P.cor.thr = ctx->m_err.as<uint32_t>();
+  P.cor.n_cycles = ctx->n_cycles; P.cor.n_mates = ctx->n_mates; P.cor.thr_s = 0; P.cor.lp = 0;
   P.cor.k0 = d->corrupt_seed; P.cor.k1 = d->unit_seed ^ 0x636f7231u;
   P.L_nd = mg_ndigits32((uint32_t)L);
 
@@ -798,7 +808,8 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
   P.cum_bq = ctx->m_bq.as<double>(); P.n_cycles = ctx->n_cycles; P.n_bq = ctx->n_bq; P.phred = ctx->m_phred.as<double>();
   P.mode = mode;
   P.cor.kshift = 7;   // any read length up to n_cycles
-  P.cor.alias = ctx->m_alias[1].as<uint32_t>(); P.cor.err = ctx->m_err.as<MgErr>(); P.cor.n_cycles = ctx->n_cycles;
+  P.cor.alias = ctx->m_alias[1].as<uint32_t>(); P.cor.thr = ctx->m_err.as<uint32_t>();
+  P.cor.n_cycles = ctx->n_cycles; P.cor.n_mates = ctx->n_mates; P.cor.thr_s = 0; P.cor.lp = 0;
   P.cor.k0 = seed; P.cor.k1 = 0x636f7232u;
   if (out_len1) *out_len1 = 0;
   if (out_len2) *out_len2 = 0;

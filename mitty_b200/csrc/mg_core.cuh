@@ -745,45 +745,55 @@ MG_HD void mg_emit_frame(typename SP::ptr dst, uint32_t qlen, const uint8_t *pre
 // ------------------------------------------------------------------------------------------
 // Production-mode corruption (Philox draws, alias-method quality sampling).
 //
+// The reference draws a quality per cycle and then a miscall with probability phred_p[quality]
+// (illumina.py:151-160).  The same joint distribution is sampled in the other order, which takes
+// the table lookup out of the miscall decision: per (file, cycle) the model gives
+//     perr = sum_q P(q) phred_p[q],      P(q | miscall) = P(q) phred_p[q] / perr,
+//                                        P(q | correct) = P(q) (1 - phred_p[q]) / (1 - perr)
+// so the miscall is decided from a per-cycle threshold the whole warp shares, and only the
+// quality comes from an alias row -- the row of (file, cycle, miscall).
+//
 // Draw layout (the specification tests/philox_ref.py restates in numpy): for template serial s
 // (0-based count within the unit), file f and cycle pair q = n / 2,
 //     r = Philox4x32-7(counter = (s, f, q, MG_STREAM_CORRUPT), key = (k0, k1))
 // cycle 2q uses (r[0], r[1]), cycle 2q+1 uses (r[2], r[3]) as (w_bq, w_call):
+//     T = thr[f][n] = min(2^32-1, floor(perr * 2^32));   miscall iff w_call < T
+//     substituted base = base_rot[base][(w_call >= T/3) + (w_call >= floor(2T/3))]   (illumina.py:131-136,160;
+//     given a miscall, w_call is uniform on [0, T), so no third draw is needed)
 //     idx = w_bq >> (32 - kshift); frac = (w_bq << kshift) >> 8        (24 bits)
-//     e = alias[(f * n_cycles + n) << kshift | idx]; bq = frac < (e >> 7) ? idx : (e & 127)
-//     error iff w_call < thr[bq], thr = min(2^32-1, floor(phred_p[bq] * 2^32))   (illumina.py:137,159)
-//     substituted base = base_rot[base][(w_call >= thr/3) + (w_call >= 2*thr/3)]  (illumina.py:131-136,160;
-//     given an error, w_call is uniform on [0, thr), so no third draw is needed)
-struct alignas(16) MgErr { uint32_t thr, t1, t2, pad; };
-
+//     e = alias[((f * n_cycles + n) * 2 + miscall) << kshift | idx]; bq = frac < (e >> 7) ? idx : (e & 127)
 struct MgCorruptCtx {
-  const uint32_t *alias;   // [n_mates][n_cycles][1 << kshift]
-  const MgErr *err;        // [128]
-  int kshift, n_cycles;
+  const uint32_t *alias;   // [n_mates][n_cycles][2][1 << kshift]
+  const uint32_t *thr;     // [n_mates][n_cycles] miscall thresholds
+  int kshift, n_cycles, n_mates;
   uint32_t k0, k1;
-  uint32_t thr_s;          // device hot path: shared-window address of a u32[128] copy of err[].thr
+  uint32_t thr_s, lp;      // device hot path: shared-window address of a staged copy of thr, laid out [file][lp]
 };
 
-// which of the three alternatives: w_call is uniform on [0, thr) given an error
+MG_HD uint32_t mg_ctz4(uint32_t m) {   // index of the lowest set bit of a non-zero 4-bit mask
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__ffs((int)m) - 1u;
+#else
+  return (m & 1u) ? 0u : (m & 2u) ? 1u : (m & 4u) ? 2u : 3u;
+#endif
+}
+
+// which of the three alternatives: w_call is uniform on [0, thr) given a miscall
 MG_HD uint32_t mg_sub_index(uint32_t w_call, uint32_t thr) {
   const uint32_t q = thr / 3u, r = thr - 3u * q;          // floor(2 thr / 3) = 2 q + (r == 2), without 64-bit arithmetic
   return (uint32_t)(w_call >= q) + (uint32_t)(w_call >= 2u * q + (r >> 1));
 }
 
-// -> bit 2 = substitution happened, bits 0-1 = which of the three alternatives; qual = ASCII quality
-MG_HD uint32_t mg_corrupt_finish(const MgCorruptCtx &C, uint32_t w_bq, uint32_t e, uint32_t w_call, uint32_t &qual) {
-  const uint32_t idx = w_bq >> (32 - C.kshift);
-  const uint32_t frac = (w_bq << C.kshift) >> 8;
-  const uint32_t bq = frac < (e >> 7) ? idx : (e & 127u);
-  qual = bq + 33u;
-  const uint32_t thr = C.err[bq].thr;
-  if (w_call >= thr) return 0u;
-  return 4u | mg_sub_index(w_call, thr);
-}
-
+// one base -> bit 2 = substitution happened, bits 0-1 = which of the three alternatives; qual = ASCII quality
 MG_HD uint32_t mg_corrupt_draw(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &qual) {
-  const uint32_t e = C.alias[((f * (uint32_t)C.n_cycles + (uint32_t)n) << C.kshift) | (w_bq >> (32 - C.kshift))];
-  return mg_corrupt_finish(C, w_bq, e, w_call, qual);
+  const uint32_t cyc = f * (uint32_t)C.n_cycles + (uint32_t)n;
+  const uint32_t T = C.thr[cyc];
+  const uint32_t miss = (uint32_t)(w_call < T);
+  const uint32_t idx = w_bq >> (32 - C.kshift);
+  const uint32_t e = C.alias[((2u * cyc + miss) << C.kshift) | idx];
+  const uint32_t frac = (w_bq << C.kshift) >> 8;
+  qual = (frac < (e >> 7) ? idx : (e & 127u)) + 33u;
+  return miss ? (4u | mg_sub_index(w_call, T)) : 0u;
 }
 
 MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &base, uint32_t &qual) {
@@ -794,68 +804,73 @@ MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_b
 // base_rot on 2-bit codes (A=0 C=1 G=2 T=3): A->CTG, C->ATG, G->ACT, T->ACG as 2-bit triples
 #define MG_ROT_TBL (45u | (44u << 6) | (52u << 12) | (36u << 18))
 
-template <bool ES>
-MG_HD uint32_t mg_err_thr(const MgCorruptCtx &C, uint32_t bq) {
+// four bases (chunk word q, first base index n0) corrupted on the 2-bit codes -> new codes + ASCII
+// qualities, in three steps so that everything that does not need the alias rows runs while their
+// loads are in flight: draw (Philox, miscall bits, loads issued), subst (the miscalled codes are
+// replaced; the caller also writes the previous group's output here), qual (the loaded entries
+// become quality bytes).  Cycles >= L read a valid row and are masked out.
+struct MgDraw4 { uint32_t wb[4], wc[4], e[4], T[4], miss; };
+
+template <bool FULL, bool ES>   // FULL: all four cycles are inside the read (n0 + 4 <= L); ES: thresholds staged in shared memory
+MG_HD void mg_corrupt4_draw(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, MgDraw4 &D) {
+  const uint32_t cyc = f * (uint32_t)C.n_cycles + (uint32_t)n0;
+  bool staged = false;
 #if defined(__CUDA_ARCH__)
-  if constexpr (ES) {
-    uint32_t v;
-    asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(C.thr_s + 4u * bq));   // the table is read-only while the kernel runs
-    return v;
+  if constexpr (ES) {   // one 16-byte load: the four cycles' thresholds (n0 is a multiple of 4, lp too)
+    asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(D.T[0]), "=r"(D.T[1]), "=r"(D.T[2]), "=r"(D.T[3]) : "r"(C.thr_s + 4u * (f * C.lp + (uint32_t)n0)));
+    staged = true;
   }
 #endif
-  return C.err[bq].thr;
-}
-
-// four bases (chunk word q, first base index n0) corrupted on the 2-bit codes -> new codes + ASCII
-// qualities, in two steps so that the caller can put independent work between the table loads and
-// their first use.  Both Philox blocks are generated first and the four alias loads are issued
-// together, so their (L2) latencies overlap; cycles >= L read a valid row and are masked out.
-// The four error tests feed ONE branch: substitutions are handled out of the main line.
-struct MgDraw4 { uint32_t wb[4], wc[4], e[4]; };
-
-template <bool FULL>   // FULL: all four cycles are inside the read (n0 + 4 <= L)
-MG_HD void mg_corrupt4_draw(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, MgDraw4 &D) {
+  if (!staged) {
+    MG_UNROLL
+    for (int j = 0; j < 4; j++) D.T[j] = C.thr[cyc + ((FULL || n0 + j < L) ? (uint32_t)j : 0u)];
+  }
   const MgPhilox r0 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1), C.k0, C.k1);
   const MgPhilox r1 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1) + 1u, C.k0, C.k1);
   D.wb[0] = r0.v[0]; D.wb[1] = r0.v[2]; D.wb[2] = r1.v[0]; D.wb[3] = r1.v[2];
   D.wc[0] = r0.v[1]; D.wc[1] = r0.v[3]; D.wc[2] = r1.v[1]; D.wc[3] = r1.v[3];
   const uint32_t ks = (uint32_t)C.kshift;
-  const uint32_t row = (f * (uint32_t)C.n_cycles + (uint32_t)n0) << ks;   // 32-bit index arithmetic: one IMAD.WIDE per load
+  const uint32_t row = (2u * cyc) << ks;                  // 32-bit index arithmetic: one IMAD.WIDE per load
+  D.miss = 0;
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
-    const uint32_t nj = (FULL || n0 + j < L) ? (uint32_t)j : 0u;            // stay inside the table at the read's end
-    D.e[j] = C.alias[row + (nj << ks) + (D.wb[j] >> (32u - ks))];
+    const bool in = FULL || n0 + j < L;
+    const uint32_t nj = in ? (uint32_t)j : 0u;            // stay inside the table at the read's end
+    const uint32_t m = (uint32_t)(D.wc[j] < D.T[j]);
+    D.e[j] = C.alias[row + ((2u * nj + m) << ks) + (D.wb[j] >> (32u - ks))];
+    D.miss |= (in ? m : 0u) << j;
   }
 }
 
-template <bool FULL, bool ES>   // ES: error thresholds staged in shared memory (k_unit_emit)
-MG_HD void mg_corrupt4_apply(const MgCorruptCtx &C, const MgDraw4 &D, int n0, int L, uint32_t &b4, uint32_t &qw) {
+// substitutions (about 2 % of the bases): each lane walks ITS OWN miscall bits, so the warp runs this
+// loop as often as its worst lane has miscalls among the four bases -- almost always once
+MG_HD void mg_corrupt4_subst(const MgDraw4 &D, uint32_t &b4) {
+  uint32_t any = D.miss;
+  while (any) {
+    const uint32_t j = mg_ctz4(any);
+    any &= any - 1u;
+    const uint32_t w = j == 0 ? D.wc[0] : j == 1 ? D.wc[1] : j == 2 ? D.wc[2] : D.wc[3];
+    const uint32_t t = j == 0 ? D.T[0] : j == 1 ? D.T[1] : j == 2 ? D.T[2] : D.T[3];
+    const uint32_t code = (b4 >> (2u * j)) & 3u;
+    const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * mg_sub_index(w, t))) & 3u;
+    b4 ^= (code ^ nc) << (2u * j);
+  }
+}
+
+template <bool FULL>
+MG_HD uint32_t mg_corrupt4_qual(const MgCorruptCtx &C, const MgDraw4 &D, int n0, int L) {
   const uint32_t ks = (uint32_t)C.kshift;
-  uint32_t bq[4], thr[4], any = 0;
+  uint32_t bq[4];
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
     const uint32_t frac = (D.wb[j] << ks) >> 8;
     bq[j] = frac < (D.e[j] >> 7) ? (D.wb[j] >> (32u - ks)) : (D.e[j] & 127u);
-    thr[j] = mg_err_thr<ES>(C, bq[j]);
-    any |= (uint32_t)(D.wc[j] < thr[j] && (FULL || n0 + j < L)) << j;
   }
-  if (FULL) {
-    qw = (bq[0] + (bq[1] << 8)) + ((bq[2] + (bq[3] << 8)) << 16) + 0x21212121u;
-  } else {
-    qw = 0;
-    MG_UNROLL
-    for (int j = 0; j < 4; j++) if (n0 + j < L) qw |= (bq[j] + 33u) << (8 * j);
-  }
-  if (any) {
-    MG_UNROLL
-    for (int j = 0; j < 4; j++) {
-      if (any & (1u << j)) {
-        const uint32_t code = (b4 >> (2 * j)) & 3u;
-        const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * mg_sub_index(D.wc[j], thr[j]))) & 3u;
-        b4 ^= (code ^ nc) << (2 * j);
-      }
-    }
-  }
+  if (FULL) return (bq[0] + (bq[1] << 8)) + ((bq[2] + (bq[3] << 8)) << 16) + 0x21212121u;
+  uint32_t qw = 0;
+  MG_UNROLL
+  for (int j = 0; j < 4; j++) if (n0 + j < L) qw |= (bq[j] + 33u) << (8 * j);
+  return qw;
 }
 
 // SEQ and QUAL lines of one read, corrupted on the fly: every thread of a warp is at the same
@@ -869,7 +884,7 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
   MgWordStream<SP> ws, wq;
   ws.begin_rmw(seq_dst); wq.begin_rmw(qual_dst);
   // the output of a group is written one group late, between the next group's table loads and
-  // their first use: about 25 independent instructions under the L2 latency
+  // their first use, together with this group's substitutions: independent work under the L2 latency
   uint32_t pb4 = 0, pqw = 0;
   bool pend = false;
   mg_for_each_chunk(S, [&](uint32_t codes, int c) {
@@ -880,14 +895,15 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
         uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw;
         MgDraw4 D;
         if (n0 + 4 <= L) {
-          mg_corrupt4_draw<true>(C, serial, f, n0, L, D);
+          mg_corrupt4_draw<true, ES>(C, serial, f, n0, L, D);
           if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
-          mg_corrupt4_apply<true, ES>(C, D, n0, L, b4, qw);
-          pb4 = b4; pqw = qw; pend = true;
+          mg_corrupt4_subst(D, b4);
+          pb4 = b4; pqw = mg_corrupt4_qual<true>(C, D, n0, L); pend = true;
         } else {
           if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); pend = false; }
-          mg_corrupt4_draw<false>(C, serial, f, n0, L, D);
-          mg_corrupt4_apply<false, ES>(C, D, n0, L, b4, qw);
+          mg_corrupt4_draw<false, ES>(C, serial, f, n0, L, D);
+          mg_corrupt4_subst(D, b4);
+          qw = mg_corrupt4_qual<false>(C, D, n0, L);
           const uint32_t ch = mg_chars4(b4);
           for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
         }

@@ -693,7 +693,6 @@ template <int MAXW, bool CORRUPT>
 __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
-  __shared__ uint32_t s_thr[CORRUPT ? 128 : 1];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   uint8_t *stage = smem + (uint32_t)wid * (uint32_t)(P.stage_cap + 16);      // this warp's stage
   // its shared-window address, pinned in a register (the compiler would otherwise rebuild it at every store)
@@ -701,9 +700,17 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
   asm volatile("" : "+r"(stage_s));
   const int L = P.rlen;
   MgCorruptCtx cor = P.cor;
-  if constexpr (CORRUPT) {                                                   // error thresholds: 512 B of shared memory
-    s_thr[t & 127] = P.cor.err[t & 127].thr;
+  if constexpr (CORRUPT) {
+    // per-cycle miscall thresholds of both files, staged behind the stages: [file][lp], lp = L rounded up to 4
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(smem + (MG_CTA / 32) * (uint32_t)(P.stage_cap + 16));
+    const int lp = (L + 3) & ~3;
+#pragma unroll 1
+    for (int i = t; i < 2 * lp; i += MG_CTA) {
+      const int f = i / lp, n = i - f * lp;
+      s_thr[i] = (n < P.cor.n_cycles && f < P.cor.n_mates) ? P.cor.thr[f * P.cor.n_cycles + n] : 0u;
+    }
     cor.thr_s = (uint32_t)__cvta_generic_to_shared(s_thr);
+    cor.lp = (uint32_t)lp;
     asm volatile("" : "+r"(cor.thr_s));
   }
 #pragma unroll 1
@@ -799,7 +806,7 @@ static unit_kernel_t unit_kernel(int L, int corrupt) {
 }
 
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
-  int smem = (MG_CTA / 32) * (stage_cap + 16);
+  int smem = (MG_CTA / 32) * (stage_cap + 16) + (corrupt ? 2 * 4 * ((L + 3) & ~3) : 0);   // stages + staged miscall thresholds
   *smem_bytes = smem;
   unit_kernel_t k = unit_kernel(L, corrupt);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

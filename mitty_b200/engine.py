@@ -90,13 +90,15 @@ class Engine(object):
                                       cum_bq.shape[1], cum_bq.shape[2], _ptr(PHRED_P), self.rlen))
 
   def model_tables(self, kshift):
-    """-> (alias u32[n_mates, n_cycles, 1 << kshift], n64, err u32[128, 4]) as built at load time."""
+    """-> (alias u32[n_mates, n_cycles, 2, 1 << kshift], n64, thr u32[n_mates, n_cycles]) as built at
+    load time: quality alias rows given a correct call / a miscall, per-cycle miscall thresholds."""
     n64 = C.c_int32(0)
     self._check(self._L.mg_model_tables(self._h, kshift, None, 0, C.byref(n64), None))
-    alias = np.zeros(self._model_shape[0] * self._model_shape[1] << kshift, dtype=np.uint32)
-    err = np.zeros((128, 4), dtype=np.uint32)
-    self._check(self._L.mg_model_tables(self._h, kshift, _ptr(alias), alias.size, C.byref(n64), _ptr(err)))
-    return alias.reshape(self._model_shape[0], self._model_shape[1], 1 << kshift), n64.value, err
+    nm, nc = self._model_shape[0], self._model_shape[1]
+    alias = np.zeros((nm * nc * 2) << kshift, dtype=np.uint32)
+    thr = np.zeros(nm * nc, dtype=np.uint32)
+    self._check(self._L.mg_model_tables(self._h, kshift, _ptr(alias), alias.size, C.byref(n64), _ptr(thr)))
+    return alias.reshape(nm, nc, 2, 1 << kshift), n64.value, thr.reshape(nm, nc)
 
   # -- haplotypes --------------------------------------------------------------------------------
   def load_region(self, ref_bytes, bed_start):

@@ -16,7 +16,7 @@ static int64_t emul_unit_t(const uint32_t *hap, uint32_t hap_len, const MgNode *
                   int corrupt, const uint32_t *alias, int kshift, int n_cycles, const uint32_t *err, uint32_t k0, uint32_t k1) {
   const int pl = (int)strlen(prefix), ml = (int)strlen(mid);
   const int L_nd = mg_ndigits32((uint32_t)L);
-  MgCorruptCtx cor; cor.alias = alias; cor.err = (const MgErr *)err; cor.kshift = kshift; cor.n_cycles = n_cycles; cor.k0 = k0; cor.k1 = k1;
+  MgCorruptCtx cor; cor.alias = alias; cor.thr = err; cor.kshift = kshift; cor.n_cycles = n_cycles; cor.n_mates = 2; cor.k0 = k0; cor.k1 = k1; cor.thr_s = 0; cor.lp = 0;
   uint64_t sz_sum = 0, cnt1 = 0, cnt2 = 0;
   static uint8_t stage_raw[1 << 16];
   for (int64_t j = 0; j < n; j++) {

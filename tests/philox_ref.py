@@ -1,6 +1,6 @@
 """Numpy restatement of the engine's PRODUCTION-mode corruption (the draw layout documented at
-MgCorruptCtx in mitty_b200/csrc/mg_core.cuh): Philox4x32 counters, Vose alias rows, integer
-error thresholds.  Test infrastructure: lets the fused GPU path be checked byte for byte, not only
+MgCorruptCtx in mitty_b200/csrc/mg_core.cuh): Philox4x32 counters, per-cycle miscall thresholds,
+Vose alias rows of the quality given a correct call / a miscall.  Test infrastructure: lets the fused GPU path be checked byte for byte, not only
 statistically."""
 import numpy as np
 
@@ -40,14 +40,37 @@ def exact64_cycles(cum_bq_mat):
   return n64
 
 
-def alias_tables(cum_bq_mat, kshift, n_rows=None):
-  """-> alias u32[n_mates, n_cycles, 1 << kshift]: Vose's method per (mate, cycle) row, the same
-  operation order as build_alias_row in mg_api.cu (entry = prob24 << 7 | alias).  Only the first
-  n_rows cycles are built (the rest stay zero)."""
+def _vose(q, K):
+  """Vose's alias method, the same operation order as vose() in mg_api.cu (entry = prob24 << 7 | alias)."""
+  q = list(q)
+  small, large = [], []
+  for i in range(K):
+    q[i] *= K
+    (small if q[i] < 1.0 else large).append(i)
+  prob, alias = [1.0] * K, list(range(K))
+  while small and large:
+    s, l = small.pop(), large.pop()
+    prob[s], alias[s] = q[s], l
+    q[l] = (q[l] + q[s]) - 1.0
+    (small if q[l] < 1.0 else large).append(l)
+  out = np.zeros(K, dtype=np.uint32)
+  for i in range(K):
+    pr = min(max(prob[i], 0.0), 1.0)
+    pq = min(int(np.floor(pr * 16777216.0 + 0.5)), 1 << 24)
+    out[i] = (pq << 7) | alias[i]
+  return out
+
+
+def quality_tables(cum_bq_mat, phred_p, kshift, n_rows=None):
+  """-> (alias u32[n_mates, n_cycles, 2, 1 << kshift], thr u32[n_mates, n_cycles]): per (mate, cycle)
+  the miscall threshold floor(perr * 2^32), perr = sum_q P(q) phred_p[q], and the alias rows of the
+  quality given a correct call ([0]) / given a miscall ([1]) -- build_quality_rows in mg_api.cu, same
+  operation order.  Only the first n_rows cycles are built (the rest stay zero)."""
   m = np.asarray(cum_bq_mat, dtype=np.float64)
   n_mates, n_cycles, n_bq = m.shape
   K = 1 << kshift
-  out = np.zeros((n_mates, n_cycles, K), dtype=np.uint32)
+  out = np.zeros((n_mates, n_cycles, 2, K), dtype=np.uint32)
+  thr = np.zeros((n_mates, n_cycles), dtype=np.uint32)
   for mi in range(n_mates):
     for ci in range(n_cycles if n_rows is None else min(n_rows, n_cycles)):
       row = m[mi, ci]
@@ -62,30 +85,20 @@ def alias_tables(cum_bq_mat, kshift, n_rows=None):
         prev = c
       if min(n_bq, 93) < K:
         q[min(n_bq, 93)] += 1.0 - prev
-      small, large = [], []
-      for i in range(K):
-        q[i] *= K
-        (small if q[i] < 1.0 else large).append(i)
-      prob, alias = [1.0] * K, list(range(K))
-      while small and large:
-        s, l = small.pop(), large.pop()
-        prob[s], alias[s] = q[s], l
-        q[l] = (q[l] + q[s]) - 1.0
-        (small if q[l] < 1.0 else large).append(l)
-      for i in range(K):
-        pr = min(max(prob[i], 0.0), 1.0)
-        pq = min(int(np.floor(pr * 16777216.0 + 0.5)), 1 << 24)
-        out[mi, ci, i] = (pq << 7) | alias[i]
-  return out
-
-
-def err_table(phred_p):
-  t = np.zeros((128, 4), dtype=np.uint32)
-  for b in range(100):
-    pe = float(phred_p[b])
-    thr = 0xFFFFFFFF if pe >= 1.0 else (0 if pe <= 0.0 else int(np.floor(pe * 4294967296.0)))
-    t[b] = (thr, thr // 3, (2 * thr) // 3, 0)
-  return t
+      qe, qo, se, so = [0.0] * K, [0.0] * K, 0.0, 0.0
+      for k in range(K):
+        p = float(phred_p[k]) if k < 100 else 0.0
+        qe[k] = q[k] * p
+        qo[k] = q[k] * (1.0 - p)
+        se += qe[k]
+        so += qo[k]
+      for k in range(K):
+        qe[k] = qe[k] / se if se > 0.0 else q[k]
+        qo[k] = qo[k] / so if so > 0.0 else q[k]
+      out[mi, ci, 0] = _vose(qo, K)
+      out[mi, ci, 1] = _vose(qe, K)
+      thr[mi, ci] = 0xFFFFFFFF if se >= 1.0 else (0 if se <= 0.0 else int(np.floor(se * 4294967296.0)))
+  return out, thr
 
 
 def alias_distribution(alias_row, kshift):
@@ -99,12 +112,18 @@ def alias_distribution(alias_row, kshift):
   return p
 
 
+def joint_distribution(alias_pair, thr, kshift):
+  """(P(bq, correct), P(bq, miscall)) encoded by one cycle's two rows and its threshold."""
+  pe = int(thr) / 4294967296.0
+  return (1.0 - pe) * alias_distribution(alias_pair[0], kshift), pe * alias_distribution(alias_pair[1], kshift)
+
+
 ROT = {ord('A'): b'CTG', ord('C'): b'ATG', ord('T'): b'ACG', ord('G'): b'ACT'}
 
 
-def corrupt_file(fq, f, alias, kshift, err, k0, k1, serials=None):
-  """Corrupt a perfect FASTQ buffer (file index f) -> bytes.  serials: per-record template serial
-  (default 0..n-1, the standalone kernel's numbering)."""
+def corrupt_file(fq, f, alias, kshift, thr, k0, k1, serials=None):
+  """Corrupt a perfect FASTQ buffer (file index f) -> bytes.  alias, thr: quality_tables().
+  serials: per-record template serial (default 0..n-1, the standalone kernel's numbering)."""
   lines = fq.split(b'\n')
   n_rec = (len(lines) - 1) // 4
   if serials is None:
@@ -121,14 +140,14 @@ def corrupt_file(fq, f, alias, kshift, err, k0, k1, serials=None):
     Lr = len(seq)
     w_bq = w[rec, :, 0::2].reshape(-1)[:Lr].astype(np.uint64)     # cycle 2q -> r[0], 2q+1 -> r[2]
     w_call = w[rec, :, 1::2].reshape(-1)[:Lr].astype(np.uint64)
+    T = thr[f, :Lr].astype(np.uint64)
+    miss = w_call < T
     idx = (w_bq >> np.uint64(32 - kshift)).astype(np.int64)
     frac = ((w_bq << np.uint64(kshift)) & MASK) >> np.uint64(8)
-    e = alias[f, np.arange(Lr), idx].astype(np.uint64)
+    e = alias[f, np.arange(Lr), miss.astype(np.int64), idx].astype(np.uint64)
     bq = np.where(frac < (e >> np.uint64(7)), idx, (e & np.uint64(127)).astype(np.int64))
-    thr = err[bq]
-    is_err = w_call < thr[:, 0]
-    rot = (w_call >= thr[:, 1]).astype(np.int64) + (w_call >= thr[:, 2]).astype(np.int64)
-    for n in np.flatnonzero(is_err):
+    rot = (w_call >= T // np.uint64(3)).astype(np.int64) + (w_call >= (np.uint64(2) * T) // np.uint64(3)).astype(np.int64)
+    for n in np.flatnonzero(miss):
       seq[n] = ROT.get(seq[n], b'NNN')[rot[n]]
     out.append(lines[4 * rec] + b'\n' + bytes(seq) + b'\n+\n' + (bq + 33).astype(np.uint8).tobytes() + b'\n')
   return b''.join(out)

@@ -191,13 +191,15 @@ def test_fused_philox_corruption_matches_numpy_spec(emul, L, kshift, maxw):
   from tests import philox_ref as PR
   m = H.model('hiseq-X-v2.5-Garvan.pkl')
   assert PR.exact64_cycles(m['cum_bq_mat']) == 150
-  alias = PR.alias_tables(m['cum_bq_mat'], kshift, n_rows=150)
-  err = PR.err_table(oracle.PHRED_P)
-  # the alias rows encode the model's per-cycle distribution (searchsorted-left outcomes)
+  alias, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, kshift, n_rows=150)
+  # threshold + the two alias rows of a cycle encode the model's joint distribution of (quality,
+  # miscall): P(q) from the searchsorted-left outcomes, miscall with probability phred_p[q]
   for mate in (0, 1):
     pm = np.diff(np.concatenate([np.zeros((150, 1)), m['cum_bq_mat'][mate, :150, :]], axis=1), axis=1)
     for cyc in (0, 1, 75, 149):
-      assert np.abs(PR.alias_distribution(alias[mate, cyc], kshift)[:94] - pm[cyc]).max() < 1e-8
+      ok, miss = PR.joint_distribution(alias[mate, cyc], err[mate, cyc], kshift)
+      assert np.abs(miss[:94] - pm[cyc] * oracle.PHRED_P[:94]).max() < 1e-8
+      assert np.abs(ok[:94] - pm[cyc] * (1.0 - oracle.PHRED_P[:94])).max() < 1e-8
   regs = H.workload_regions(synth.edge_workload())
   r = regs[0]
   cv = H.oracle_cv(r['v'][1])

@@ -175,8 +175,8 @@ def test_philox_large_unit_exact(eng):
 
 
 def test_philox_corruption_exact_vs_numpy_spec(eng):
-  """Production-mode corruption is fully specified (Philox counters, alias rows, integer error
-  thresholds): the fused emit kernel and the standalone corrupt kernel must reproduce the numpy
+  """Production-mode corruption is fully specified (Philox counters, per-cycle miscall thresholds,
+  alias rows): the fused emit kernel and the standalone corrupt kernel must reproduce the numpy
   restatement of that specification byte for byte."""
   import mitty_b200.simulation.illumina as il
   from mitty_b200.engine import MODE_PHILOX
@@ -185,14 +185,15 @@ def test_philox_corruption_exact_vs_numpy_spec(eng):
   rm = il.read_model_params(m, 30.0)
   eng.load_model(rm)
   # the tables the library built at load time == the Python restatement of Vose's method
-  err = PR.err_table(oracle.PHRED_P)
   for kshift in (6, 7):
-    alias, n64, lerr = eng.model_tables(kshift)
+    alias, n64, lthr = eng.model_tables(kshift)
     assert n64 == PR.exact64_cycles(m['cum_bq_mat']) == 150
-    want = PR.alias_tables(m['cum_bq_mat'], kshift, n_rows=n64 if kshift == 6 else None)
+    want, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, kshift, n_rows=n64 if kshift == 6 else None)
     np.testing.assert_array_equal(alias, want)
-    np.testing.assert_array_equal(lerr, err)
-  alias6, alias7 = PR.alias_tables(m['cum_bq_mat'], 6, n_rows=150), PR.alias_tables(m['cum_bq_mat'], 7)
+    if kshift == 7:
+      np.testing.assert_array_equal(lthr, err)
+  alias6 = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 6, n_rows=150)[0]
+  alias7, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 7)
   r = H.workload_regions(synth.edge_workload())[0]
   rid = eng.load_region(r['ref'], r['region'][1])
   cp = eng.build_copy(rid, r['v'][1])

@@ -334,7 +334,7 @@ int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t b
   if (!ctx || !region_id || len < 0 || (len > 0 && !ref_bytes)) return fail(ctx, MG_EINVAL, "mg_region_load: bad arguments");
   if (len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "region of %lld bases exceeds the 2^32 addressing of one region", (long long)len);
   DeviceGuard g(ctx->device);
-  const uint32_t EXC_CAP = 1u << 20;
+  uint32_t exc_cap = 1u << 20;                        // grown on demand: a soft-masked chromosome has ~10^6 case runs
   std::unique_ptr<Region> R(new Region());
   R->len = len; R->bed_start = bed_start;
   int64_t words = (len + 15) / 16;
@@ -343,25 +343,30 @@ int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t b
   CU(cudaMemsetAsync(R->d_ref, 0, sizeof(uint32_t) * (words + 2 * MG_HAP_PAD), ctx->stream));
   if (len > 0) {
     CU(ctx->s_raw.need((size_t)len + 32));
-    // exception scratch: [cnt u32 x2 (padded to 16 B)][start i64 x cap][end i64 x cap][byte u8 x cap]
-    size_t exc_bytes = 16 + (size_t)EXC_CAP * 17;
-    CU(ctx->s_exc.need(exc_bytes));
-    uint8_t *eb = ctx->s_exc.as<uint8_t>();
-    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(eb);
-    int64_t *d_start = reinterpret_cast<int64_t *>(eb + 16);
-    int64_t *d_end = d_start + EXC_CAP;
-    uint8_t *d_byte = reinterpret_cast<uint8_t *>(d_end + EXC_CAP);
-    CU(cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
     CU(cudaMemcpyAsync(ctx->s_raw.p, ref_bytes, (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
-    mg_launch_pack_ref(ctx->s_raw.as<uint8_t>(), len, R->d_ref + MG_HAP_PAD, d_cnt, d_start, d_byte, d_end, EXC_CAP, ctx->stream);
-    ctx->total_launches++;
-    CU(cudaGetLastError());
-    uint32_t cnt[2];
-    CU(cudaMemcpyAsync(cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (cnt[0] != cnt[1]) return fail(ctx, MG_ECUDA, "internal: exception run starts (%u) != ends (%u)", cnt[0], cnt[1]);
-    if (cnt[0] > EXC_CAP)
-      return fail(ctx, MG_EVALUE, "reference has %u runs of non-ACGT bytes (limit %u): soft-masked (lower-case) references are not supported yet", cnt[0], EXC_CAP);
+    uint32_t cnt[2] = {0, 0};
+    int64_t *d_start = nullptr, *d_end = nullptr;
+    uint8_t *d_byte = nullptr;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      // exception scratch: [cnt u32 x2 (padded to 16 B)][start i64 x cap][end i64 x cap][byte u8 x cap]
+      CU(ctx->s_exc.need(16 + (size_t)exc_cap * 17));
+      uint8_t *eb = ctx->s_exc.as<uint8_t>();
+      uint32_t *d_cnt = reinterpret_cast<uint32_t *>(eb);
+      d_start = reinterpret_cast<int64_t *>(eb + 16);
+      d_end = d_start + exc_cap;
+      d_byte = reinterpret_cast<uint8_t *>(d_end + exc_cap);
+      CU(cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
+      mg_launch_pack_ref(ctx->s_raw.as<uint8_t>(), len, R->d_ref + MG_HAP_PAD, d_cnt, d_start, d_byte, d_end, exc_cap, ctx->stream);
+      ctx->total_launches++;
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (cnt[0] != cnt[1]) return fail(ctx, MG_ECUDA, "internal: exception run starts (%u) != ends (%u)", cnt[0], cnt[1]);
+      if (cnt[0] <= exc_cap) break;
+      if (attempt == 1 || cnt[0] > (1u << 27))
+        return fail(ctx, MG_EVALUE, "reference has %u runs of non-ACGT bytes / lower-case stretches (limit 2^27)", cnt[0]);
+      exc_cap = cnt[0];                               // second pass with room for every run
+    }
     if (cnt[0]) {
       std::vector<int64_t> st(cnt[0]), en(cnt[0]);
       std::vector<uint8_t> by(cnt[0]);
@@ -559,7 +564,8 @@ int mg_copy_haplotype(mg_ctx *ctx, int64_t copy_id, uint8_t *out, int64_t cap) {
   for (int64_t i = 0; i < n; i++) out[i] = (uint8_t)("ACGT"[(w[i >> 4] >> (2 * (i & 15))) & 3]);
   std::vector<MgExc> exc((size_t)C.n_exc);
   if (C.n_exc) CU(cudaMemcpy(exc.data(), C.d_exc, sizeof(MgExc) * exc.size(), cudaMemcpyDeviceToHost));
-  for (const MgExc &e : exc) for (uint32_t q = 0; q < e.len; q++) out[e.start + q] = (uint8_t)e.byte;
+  for (const MgExc &e : exc)
+    for (uint32_t q = 0; q < e.len; q++) out[e.start + q] = e.byte == MG_EXC_CASE ? (uint8_t)(out[e.start + q] | 0x20) : (uint8_t)e.byte;
   return MG_OK;
 }
 

@@ -48,7 +48,10 @@ struct alignas(16) MgNode {
   uint32_t op;
 };
 
-// Maximal run of one non-ACGT byte on the haplotype, in sample-relative coordinates.
+// Maximal run of one non-ACGT byte on the haplotype, in sample-relative coordinates -- or, with
+// byte == MG_EXC_CASE, a maximal run of lower-case a/c/g/t (a soft-masked stretch): those bases keep
+// their 2-bit codes in the packed sequence and the run only records the case.
+#define MG_EXC_CASE 1u
 struct alignas(16) MgExc {
   uint32_t start;
   uint32_t len;
@@ -609,9 +612,18 @@ MG_NI int mg_count_N(EP exc, int n_exc, uint32_t x, int L) {
 
 // overwrite the bases of a written read (seq points at its first byte) that fall in exception
 // runs.  The reference's translate table only maps ATCGN (readgenerate.py:56), so an exception
-// byte is copied unchanged on either strand; only its position is mirrored on strand 1.
-template <class SP, class EP>
-MG_NI void mg_patch_exc(typename SP::ptr seq, EP exc, int n_exc, uint32_t x, int L, int strand) {
+// byte -- lower-case bases included -- is copied unchanged on either strand; only its position is
+// mirrored on strand 1.
+// the forward-strand byte of haplotype position i under exception run e: the run's byte, or the
+// lower-case letter of the packed code for a case run
+template <class HP>
+MG_HD uint8_t mg_exc_byte(const MgExc &e, HP hap, uint64_t i) {
+  if (e.byte != MG_EXC_CASE) return (uint8_t)e.byte;
+  return (uint8_t)("acgt"[(hap[i >> 4] >> (2 * (i & 15))) & 3u]);
+}
+
+template <class SP, class EP, class HP>
+MG_NI void mg_patch_exc(typename SP::ptr seq, EP exc, int n_exc, HP hap, uint32_t x, int L, int strand) {
   for (int k = mg_exc_first(exc, n_exc, x); k < n_exc; k++) {
     MgExc e = exc[k];
     if ((uint64_t)e.start >= (uint64_t)x + L) break;
@@ -619,7 +631,7 @@ MG_NI void mg_patch_exc(typename SP::ptr seq, EP exc, int n_exc, uint32_t x, int
     uint64_t b = (uint64_t)e.start + e.len < (uint64_t)x + L ? (uint64_t)e.start + e.len : (uint64_t)x + L;
     for (uint64_t i = a; i < b; i++) {
       int idx = (int)(i - x);
-      SP::st8(seq + (uint32_t)(strand ? (L - 1 - idx) : idx), (uint8_t)e.byte);
+      SP::st8(seq + (uint32_t)(strand ? (L - 1 - idx) : idx), mg_exc_byte(e, hap, i));
     }
   }
 }
@@ -718,7 +730,7 @@ MG_HD void mg_emit_record(typename SP::ptr dst, uint32_t qlen, const uint8_t *pr
   mg_emit_fill(ws, '~', L);
   ws.put('\n');
   ws.end();
-  if (n_exc) mg_patch_exc<SP>(dst + (qlen + 1), exc, n_exc, S.x, L, S.strand);
+  if (n_exc) mg_patch_exc<SP>(dst + (qlen + 1), exc, n_exc, S.hap, S.x, L, S.strand);
 }
 
 // The other file's record has the same qname, the same offsets and (for perfect reads) the same
@@ -729,7 +741,7 @@ MG_HD void mg_rewrite_seq(typename SP::ptr seq_dst, MgSeqSrc<MAXW, HP> &S, EP ex
   ws.begin_rmw(seq_dst);
   mg_emit_seq_src(ws, S);
   ws.end();
-  if (n_exc) mg_patch_exc<SP>(seq_dst, exc, n_exc, S.x, S.L, S.strand);
+  if (n_exc) mg_patch_exc<SP>(seq_dst, exc, n_exc, S.hap, S.x, S.L, S.strand);
 }
 
 // qname line + the three separator newlines of a record whose SEQ / QUAL lines are written by
@@ -879,7 +891,7 @@ template <class SP, int MAXW, class HP, class EP>
 MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc,
                                const MgCorruptCtx &C, uint32_t serial, uint32_t f) {
   const int L = S.L;
-  const struct { uint32_t x; int strand; } mine = {S.x, S.strand};
+  const struct { uint32_t x; int strand; HP hap; } mine = {S.x, S.strand, S.hap};
   constexpr bool ES = !SP::is_generic;   // staged in shared memory <=> running in k_unit_emit with the threshold table staged too
   MgWordStream<SP> ws, wq;
   ws.begin_rmw(seq_dst); wq.begin_rmw(qual_dst);
@@ -923,7 +935,7 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
       for (uint64_t i = a; i < b; i++) {
         const int idx = (int)(i - mine.x), n = mine.strand ? (L - 1 - idx) : idx;
         const MgPhilox r = mg_philox_corrupt(serial, f, (uint32_t)(n >> 1), C.k0, C.k1);
-        uint32_t base = e.byte, qual;
+        uint32_t base = mg_exc_byte(e, mine.hap, i), qual;
         mg_corrupt_one(C, f, n, (n & 1) ? r.v[2] : r.v[0], (n & 1) ? r.v[3] : r.v[1], base, qual);
         SP::st8(seq_dst + (uint32_t)n, (uint8_t)base);
       }

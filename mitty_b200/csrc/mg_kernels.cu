@@ -70,17 +70,28 @@ __global__ void __launch_bounds__(256) k_pack_ref(const uint8_t *__restrict__ ra
     if (pos >= len) break;
     uint32_t code = mg_base_code(c[1 + i]);
     if (code > 3) {
-      bool is_start = (pos == 0) || (c[i] != c[1 + i]);
-      bool is_end = (pos == len - 1) || (c[2 + i] != c[1 + i]);
+      // runs of one identical non-ACGT byte; lower-case a/c/g/t form "case runs" of any mix of the
+      // four letters and keep their codes
+      const uint32_t lc = mg_base_code((uint8_t)(c[1 + i] ^ 0x20));   // code of the upper-case letter, if c is lower-case acgt
+      const bool soft = c[1 + i] >= 'a' && lc <= 3;
+      bool is_start, is_end;
+      if (soft) {
+        const bool prev_soft = pos > 0 && c[i] >= 'a' && mg_base_code((uint8_t)(c[i] ^ 0x20)) <= 3;
+        const bool next_soft = pos < len - 1 && c[2 + i] >= 'a' && mg_base_code((uint8_t)(c[2 + i] ^ 0x20)) <= 3;
+        is_start = !prev_soft; is_end = !next_soft;
+      } else {
+        is_start = (pos == 0) || (c[i] != c[1 + i]);
+        is_end = (pos == len - 1) || (c[2 + i] != c[1 + i]);
+      }
       if (is_start) {
         uint32_t k = atomicAdd(&exc_cnt[0], 1u);
-        if (k < exc_cap) { exc_start[k] = pos; exc_byte[k] = c[1 + i]; }
+        if (k < exc_cap) { exc_start[k] = pos; exc_byte[k] = soft ? (uint8_t)MG_EXC_CASE : c[1 + i]; }
       }
       if (is_end) {
         uint32_t k = atomicAdd(&exc_cnt[1], 1u);
         if (k < exc_cap) exc_end[k] = pos;
       }
-      code = 0;
+      code = soft ? lc : 0;
     }
     word |= code << (2 * i);
   }

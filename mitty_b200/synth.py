@@ -344,6 +344,30 @@ def edge_workload(seed=11):
           'sample': 'EDGE'}
 
 
+def softmask_workload(seed=21, length=40000):
+  """A soft-masked reference: about half of the contig in lower-case stretches (repeat-masker
+  style, mean length ~300), with an N run and IUPAC codes inside and outside of them.  The
+  reference copies lower-case bases verbatim, does not complement them on the reverse strand
+  (rpc.py:21 maps ATCGN only) and turns them into N on a miscall (illumina.py:160).  The VCF is
+  written in upper case, as callers do."""
+  rs = np.random.RandomState(seed)
+  seq = synth_contig(length, seed=seed * 100)
+  upper = seq.copy()
+  pos = 0
+  low = False
+  while pos < length:
+    n = int(rs.geometric(1.0 / 300.0))
+    if low:
+      seq[pos:pos + n] |= 0x20
+    pos += n
+    low = not low
+  for a, b, ch in ((5000, 5400, 'N'), (9000, 9003, 'n'), (12000, 12001, 'R'), (12500, 12502, 'y'), (20000, 20002, 'N')):
+    seq[a:b] = ord(ch)
+    upper[a:b] = ord(ch.upper())
+  vt = synth_variants('s', upper, 0, length, seed=seed * 100 + 1, per_mb=3000.0, ploidy=2, long_ins=2, min_gap=15, end_margin=100)
+  return {'contigs': [('s', seq)], 'tables': [vt], 'regions': [('s', 0, length)], 'sample': 'SOFT'}
+
+
 def grch37_shaped(scale=1.0, seed=7, per_mb=1330.0, n_frac=0.08, only=None):
   """BASELINE.json configs[3]: 24 contigs with GRCh37 primary-assembly lengths (times ``scale``),
   ~4 M variants at scale 1, autosomes diploid, X / Y haploid GT (docs/preparing_vcfs.rst:10-23),

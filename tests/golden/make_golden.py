@@ -166,6 +166,10 @@ def main():
   p, info = run_pair(edge, tmp, 'edge250', '1kg-pcr-free.pkl', coverage=20.0, seed=99)
   files['edge250'] = info
 
+  # soft-masked reference (half of the bases lower case): sha256 of the four files
+  p, info = run_pair(synth.softmask_workload(), tmp, 'softmask', 'hiseq-X-v2.5-Garvan.pkl', coverage=30.0, seed=11)
+  files['softmask'] = info
+
   mid = synth.config1(contig_len=100000)
   p, info = run_pair(mid, tmp, 'mid', 'hiseq-X-v2.5-Garvan.pkl')
   files['mid'] = info

@@ -41,19 +41,23 @@ def device_layout(ref, ref_start_pos, cv, blk_shift=8):
     nd[i] = (ps - p_min + (1 if op == 'D' else 0), pr, oplen, ord(op))
   hb = np.frombuffer(hap.encode(), dtype=np.uint8)
   code = np.full(256, 4, dtype=np.uint8); code[[65, 67, 71, 84]] = [0, 1, 2, 3]
-  c = code[hb]
+  soft = np.isin(hb, np.frombuffer(b'acgt', dtype=np.uint8))      # lower-case a/c/g/t keep their codes (case runs)
+  c = np.where(soft, code[hb ^ 0x20], code[hb])
   n_words = (len(hap) + 15) // 16
   cc = np.zeros(n_words * 16, dtype=np.uint64); cc[:len(hap)] = np.where(c > 3, 0, c)
   words = (cc.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
   packed = np.zeros(n_words + 2 * PAD, dtype=np.uint32); packed[PAD:PAD + n_words] = words
+  # exception runs as k_pack_ref / k_exc_map make them: maximal runs of one non-ACGT byte, and
+  # maximal runs of lower-case a/c/g/t with the MG_EXC_CASE marker (1) as their byte
+  cls = np.where(soft, 1, np.where(c > 3, hb.astype(np.int64), 0))
   exc = []
   i = 0
-  bad = np.flatnonzero(c > 3)
+  bad = np.flatnonzero(cls != 0)
   while i < bad.size:
     j = i
-    while j + 1 < bad.size and bad[j + 1] == bad[j] + 1 and hb[bad[j + 1]] == hb[bad[i]]:
+    while j + 1 < bad.size and bad[j + 1] == bad[j] + 1 and cls[bad[j + 1]] == cls[bad[i]]:
       j += 1
-    exc.append((bad[i], j - i + 1, hb[bad[i]], 0)); i = j + 1
+    exc.append((bad[i], j - i + 1, cls[bad[i]], 0)); i = j + 1
   ex = np.array(exc, dtype=np.uint32).reshape(-1, 4) if exc else np.zeros((1, 4), dtype=np.uint32)
   n_blk = (len(hap) >> blk_shift) + 1
   blk = (np.searchsorted(nd['key'], np.arange(n_blk, dtype=np.uint64) << blk_shift, side='right') - 1).astype(np.uint32)
@@ -216,3 +220,38 @@ def test_fused_philox_corruption_matches_numpy_spec(emul, L, kshift, maxw):
   assert c1 == PR.corrupt_file(p1, 0, alias, kshift, err, cor['k0'], cor['k1'])
   assert c2 == PR.corrupt_file(p2, 1, alias, kshift, err, cor['k0'], cor['k1'])
   assert c1 != p1 and b'N' in c1
+
+
+@pytest.mark.parametrize('L,maxw', [(150, 12), (37, 0)])
+def test_soft_masked_haplotype(emul, L, maxw):
+  """Case runs (lower-case a/c/g/t keep their 2-bit codes, the run only records the case): perfect
+  reads == the oracle's, fused corruption == the numpy spec (a miscalled lower-case base becomes N,
+  illumina.py:160)."""
+  from tests import philox_ref as PR
+  r = H.workload_regions(synth.softmask_workload())[0]
+  cv = H.oracle_cv(r['v'][0])
+  lay = device_layout(r['ref'], r['region'][1] + 1, cv)
+  assert (lay['exc'][:, 2] == 1).sum() > 50                 # many case runs
+  rs = np.random.RandomState(8)
+  n = 1500
+  ts = rs.randint(lay['p_min'], lay['p_max'] - 3 * L, size=n).astype(np.int64)
+  tl = rs.randint(L, 3 * L, size=n).astype(np.int64)
+  fo = rs.randint(0, 2, size=n).astype(np.int8)
+  p1, p2, cnt = run_emul(emul, lay, L, ts, tl, fo, '@S:0:0:', '|s|0', maxw=maxw)
+  # every emitted read re-derives from its qname the way the reference would have written it
+  idx = H.HaplotypeIndex(r['ref'], r['region'][1] + 1, cv)
+  from mitty_b200.simulation.readgenerate import parse_qname
+  low = 0
+  for which, buf in enumerate((p1, p2)):
+    lines = buf.decode().split('\n')
+    for k in range(0, len(lines) - 1, 4):
+      info = parse_qname(lines[k][1:])[which]
+      assert idx.check(info, lines[k + 1]) is None, (lines[k], lines[k + 1])
+      low += sum(1 for ch in lines[k + 1] if ch.islower())
+  assert low > 10000
+  alias, thr = PR.quality_tables(H.model('hiseq-X-v2.5-Garvan.pkl')['cum_bq_mat'], oracle.PHRED_P, 7, n_rows=150)
+  cor = dict(alias=alias, kshift=7, err=thr, k0=99, k1=0x1234)
+  c1, c2, ccnt = run_emul(emul, lay, L, ts, tl, fo, '@S:0:0:', '|s|0', corrupt=cor, maxw=maxw)
+  assert ccnt == cnt
+  assert c1 == PR.corrupt_file(p1, 0, alias, 7, thr, 99, 0x1234)
+  assert c2 == PR.corrupt_file(p2, 1, alias, 7, thr, 99, 0x1234)

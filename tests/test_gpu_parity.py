@@ -208,6 +208,7 @@ def test_empty_and_tiny_units(eng):
 
 @pytest.mark.parametrize('name,wl_fn', [('edge', synth.edge_workload), ('edge250', synth.edge_workload),
                                         ('mid', lambda: synth.config1(contig_len=100000)),
+                                        ('softmask', synth.softmask_workload),
                                         ('config1', synth.config1)])
 def test_deterministic_fastq_golden(eng, name, wl_fn):
   """generate-reads (+ corrupt-reads) in deterministic mode == the unmodified reference with

@@ -174,7 +174,8 @@ def test_philox_large_unit_exact(eng):
   eng.free_copy(cp); eng.free_region(rid)
 
 
-def test_philox_corruption_exact_vs_numpy_spec(eng):
+@pytest.mark.parametrize('wl_fn,cpy', [(synth.edge_workload, 1), (synth.softmask_workload, 0)])
+def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy):
   """Production-mode corruption is fully specified (Philox counters, per-cycle miscall thresholds,
   alias rows): the fused emit kernel and the standalone corrupt kernel must reproduce the numpy
   restatement of that specification byte for byte."""
@@ -194,9 +195,9 @@ def test_philox_corruption_exact_vs_numpy_spec(eng):
       np.testing.assert_array_equal(lthr, err)
   alias6 = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 6, n_rows=150)[0]
   alias7, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 7)
-  r = H.workload_regions(synth.edge_workload())[0]
+  r = H.workload_regions(wl_fn())[0]
   rid = eng.load_region(r['ref'], r['region'][1])
-  cp = eng.build_copy(rid, r['v'][1])
+  cp = eng.build_copy(rid, r['v'][cpy])
   n = int((cp.p_max - cp.p_min) * 0.1)
   unit_seed, cseed = 4242, 77
   p1, p2, cnt, _, _ = eng.generate_unit(cp, n, 0.1, MODE_PHILOX, unit_seed, '@E:0:0:', '|e|1')

@@ -215,7 +215,8 @@ def test_edge_nodes_and_reads():
 
 @pytest.mark.parametrize('name,wl_fn', [('edge', synth.edge_workload),
                                         ('edge250', synth.edge_workload),
-                                        ('mid', lambda: synth.config1(contig_len=100000))])
+                                        ('mid', lambda: synth.config1(contig_len=100000)),
+                                        ('softmask', synth.softmask_workload)])
 def test_fastq_golden(name, wl_fn):
   """generate-reads + corrupt-reads (--threads 1) of the oracle == the reference, byte for byte."""
   info = H.golden()['fastq'][name]

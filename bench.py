@@ -47,6 +47,7 @@ def parse():
   ap.add_argument('--perfect', action='store_true', help='perfect reads only (no fused corruption)')
   ap.add_argument('--workload', default='chr1', choices=['chr1', 'wgs'], help="'wgs': BASELINE.json configs[3], GRCh37-shaped genome sharded by contig over the ranks (strong scaling)")
   ap.add_argument('--scale', type=float, default=1.0, help='length scale of the wgs workload')
+  ap.add_argument('--soft-masked', action='store_true', help='chr1 workload with half of the bases in lower-case stretches (not the headline configuration)')
   return ap.parse_args()
 
 
@@ -115,6 +116,12 @@ def make_workload(args, rank):
   length = args.contig_len
   scale = length / 249250621.0
   wl = synth.chr1_shaped(seed=args.seed + 101 * rank, length=length, n_runs=max(3, int(39 * scale)))
+  if getattr(args, 'soft_masked', False):        # repeat-masker style: alternating stretches, mean length 300
+    seq = wl['contigs'][0][1]
+    edges = np.cumsum(np.random.RandomState(5).geometric(1.0 / 300.0, size=2 * length // 300 + 64))
+    edges = edges[edges < length]
+    low = (np.searchsorted(edges, np.arange(length), side='right') & 1).astype(bool) & (seq != ord('N'))
+    seq[low] |= 0x20
   region = wl['regions'][0]
   r = vcfio.from_variant_table(wl['tables'][0], region)
   return wl, region, r
@@ -210,7 +217,8 @@ def config_dict(args):
             'parallelism': 'contigs sharded over GPUs, units independent, no collective',
             'l2': 'every unit streams its FASTQ through L2 (>> 126 MB for the large contigs)'}
   return {'workload': 'configs[2]: chr1-shaped synthetic contig ({} bp, ~10% N, GIAB-density diploid VCF), 30x paired 2x150, '
-                      'Philox mode{}'.format(args.contig_len, '' if args.perfect else ' + fused Illumina corruption'),
+                      'Philox mode{}{}'.format(args.contig_len, '' if args.perfect else ' + fused Illumina corruption',
+                                               ', SOFT-MASKED variant (half of the bases lower case)' if getattr(args, 'soft_masked', False) else ''),
           'read_model': MODEL + ' (mean_rlen 150)', 'coverage': COVERAGE, 'units_per_step': 4, 'seed': args.seed,
           'parallelism': 'one contig per GPU, units independent, no collective',
           'l2': 'each unit streams ~4.6 GB of FASTQ through L2 (>> 126 MB), so nothing is re-read warm between timed units'}

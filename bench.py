@@ -259,6 +259,8 @@ def main():
   local = int(os.environ.get('LOCAL_RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
   torch.cuda.set_device(local)
+  from mitty_b200.engine import bind_host_thread_to_gpu
+  numa_cores = bind_host_thread_to_gpu(local) if world > 1 else None   # pinned buffers next to the GPU
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
@@ -391,7 +393,7 @@ def main():
     line = {'metric': 'read pairs/sec (2x150, FASTQ-formatted, corrupted)' if corrupt else 'read pairs/sec (2x150, FASTQ-formatted, perfect reads)',
             'value': pairs_all / (ms * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if args.workload == 'wgs' else 'weak', 'vs_baseline': None, 'dtype': 'u8',
-            'data': 'synthetic', 'config': config_dict(args), 'clocks': clk,
+            'data': 'synthetic', 'config': dict(config_dict(args), host_binding=('rank 0 on cores {}..{} (GPU-local, NVML)'.format(numa_cores[0], numa_cores[-1]) if numa_cores else 'none')), 'clocks': clk,
             'gpu_launches': prof['total_launches'],
             'roofline': {'bound': 'hbm', 'kernel': 'k_unit_emit', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                          'traffic': traffic, 'peak_source': peak_src, 'launches': prof['emit_launches'],

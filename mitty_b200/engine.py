@@ -244,6 +244,28 @@ class Engine(object):
     return {'emit_ms': ms.value, 'emit_launches': n.value, 'emit_bytes': b.value, 'total_launches': tl.value, 'plan_ms': pms.value}
 
 
+def bind_host_thread_to_gpu(device):
+  """Pin the calling host thread to the CPU cores next to ``device`` (NVML's affinity mask), so that
+  the pinned FASTQ buffers it allocates afterwards land in that socket's memory and the device-to-host
+  copies do not cross the inter-socket link.  Best effort: returns the core list or None."""
+  import os
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+    n_words = (os.cpu_count() + 63) // 64
+    mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+    cores = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+    allowed = os.sched_getaffinity(0)
+    cores = [c for c in cores if c in allowed]
+    if cores:
+      os.sched_setaffinity(0, cores)
+      return cores
+  except Exception:
+    pass
+  return None
+
+
 def device_count():
   return int(_lib.lib().mg_device_count())
 

@@ -108,6 +108,8 @@ def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read
   costs seconds for a chr1-sized unit)."""
   engine = None
   try:
+    from mitty_b200.engine import bind_host_thread_to_gpu
+    bind_host_thread_to_gpu(device)      # the pinned ring of this worker lands in the GPU's socket
     engine = Engine(device)
     engine.load_model(read_model)
     cache = RegionCache(engine, vcf_df, fetch_ref)

@@ -21,7 +21,10 @@ PAD = 8
 @pytest.fixture(scope='module')
 def emul(tmp_path_factory):
   so = str(tmp_path_factory.mktemp('emul') / 'libemul.so')
-  subprocess.check_call(['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-x', 'c++', os.path.join(HERE, 'emul', 'emul.cpp'), '-o', so])
+  # MG_EMUL_SANITIZE=1 (run with LD_PRELOAD=$(g++ -print-file-name=libasan.so)): AddressSanitizer + UBSan over the
+  # very header the kernels execute -- the bounds check of the per-thread logic this GPU-less box can do
+  san = ['-fsanitize=address,undefined', '-fno-omit-frame-pointer', '-g'] if os.environ.get('MG_EMUL_SANITIZE') else []
+  subprocess.check_call(['g++', '-O1', '-std=c++17', '-shared', '-fPIC'] + san + ['-x', 'c++', os.path.join(HERE, 'emul', 'emul.cpp'), '-o', so])
   lib = C.CDLL(so)
   lib.emul_unit.restype = C.c_int64
   lib.emul_digit_sum.restype = C.c_uint64

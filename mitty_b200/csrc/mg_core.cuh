@@ -841,16 +841,19 @@ MG_HD void mg_corrupt4_draw(const MgCorruptCtx &C, uint32_t serial, uint32_t f, 
   const MgPhilox r1 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1) + 1u, C.k0, C.k1);
   D.wb[0] = r0.v[0]; D.wb[1] = r0.v[2]; D.wb[2] = r1.v[0]; D.wb[3] = r1.v[2];
   D.wc[0] = r0.v[1]; D.wc[1] = r0.v[3]; D.wc[2] = r1.v[1]; D.wc[3] = r1.v[3];
-  const uint32_t ks = (uint32_t)C.kshift;
-  const uint32_t row = (2u * cyc) << ks;                  // 32-bit index arithmetic: one IMAD.WIDE per load
+  const uint32_t ks = (uint32_t)C.kshift, K = 1u << ks;
   D.miss = 0;
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
     const bool in = FULL || n0 + j < L;
     const uint32_t nj = in ? (uint32_t)j : 0u;            // stay inside the table at the read's end
-    const uint32_t m = (uint32_t)(D.wc[j] < D.T[j]);
-    D.e[j] = C.alias[row + ((2u * nj + m) << ks) + (D.wb[j] >> (32u - ks))];
-    D.miss |= (in ? m : 0u) << j;
+    const bool m = D.wc[j] < D.T[j];
+    // (row of (cycle, correct) << ks) | idx in one funnel shift, + K for the miscall row; 32-bit index
+    // arithmetic, so the address is one IMAD.WIDE
+    uint32_t ix = mg_funnel_l(D.wb[j], 2u * (cyc + nj), ks);
+    if (m) ix += K;
+    D.e[j] = C.alias[ix];
+    D.miss |= (in && m ? 1u : 0u) << j;
   }
 }
 

@@ -13,6 +13,7 @@
 //   k_scan_*          generic exclusive scan (int64)
 //   k_nl_*            FASTQ newline index
 //   k_corrupt_*       standalone corrupt-reads over FASTQ in HBM
+#include <cstdlib>
 #include "mg_internal.h"
 
 #define FULL 0xffffffffu
@@ -818,6 +819,7 @@ static unit_kernel_t unit_kernel(int L, int corrupt) {
 
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
   int smem = (MG_CTA / 32) * (stage_cap + 16) + (corrupt ? 2 * 4 * ((L + 3) & ~3) : 0);   // stages + staged miscall thresholds
+  if (const char *x = getenv("MG_EXTRA_SMEM")) smem += atoi(x);   // occupancy experiments only
   *smem_bytes = smem;
   unit_kernel_t k = unit_kernel(L, corrupt);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

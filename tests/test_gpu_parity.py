@@ -421,3 +421,49 @@ def test_tumor_normal_viral_mix(tmp_path):
     assert abs(got - exp) < 0.04 * exp + 6 * np.sqrt(exp), (name, got, exp)   # edge effects: templates need te < p_max
   frac = counts['VIRUS'] / float(sum(counts.values()))
   assert 0.006 < frac < 0.014, frac
+
+
+def test_corrupt_reads_edge_inputs(tmp_path):
+  """corrupt-reads on the inputs the reference's reader loop meets (readcorrupt.py:49-55): empty
+  files, single-end input, ragged read lengths in one file, a second file with fewer records (zip
+  truncation), a last record without a trailing newline -- deterministic mode == the oracle."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readcorrupt as rc
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  rs = np.random.RandomState(3)
+
+  def fq(lengths, tag, newline=True):
+    recs = []
+    for k, L in enumerate(lengths):
+      seq = ''.join('ACGTNacgtR'[i] for i in rs.randint(0, 10, size=L))
+      recs.append('@{}{}\n{}\n+\n{}\n'.format(tag, k, seq, '~' * L))
+    s = ''.join(recs)
+    return (s if newline else s[:-1]).encode()
+
+  cases = {
+    'empty': (b'', b''),
+    'single': (fq([150, 150, 30, 1, 300, 75], 'a'), None),
+    'ragged': (fq([150, 1, 299, 40, 150], 'b'), fq([10, 150, 150, 300, 2], 'c')),
+    'shorter2': (fq([100, 100, 100, 100], 'd'), fq([100, 100], 'e')),
+    'no_final_newline': (fq([50, 60], 'f', newline=False), fq([70, 80], 'g', newline=False)),
+  }
+  for name, (b1, b2) in cases.items():
+    i1, o1 = str(tmp_path / (name + '.1.fq')), str(tmp_path / (name + '.1.out.fq'))
+    open(i1, 'wb').write(b1)
+    i2 = o2 = None
+    if b2 is not None:
+      i2, o2 = str(tmp_path / (name + '.2.fq')), str(tmp_path / (name + '.2.out.fq'))
+      open(i2, 'wb').write(b2)
+    rc.multi_process(il, m, i1, o1, i2, o2, processes=1, seed=11, mode='deterministic')
+    want1, want2, n = oracle.corrupt_reads_cmd(m, 11, b1, b2) if b1 else (b'', b'' if b2 is not None else None, 0)
+    assert open(o1, 'rb').read() == want1, name
+    if b2 is not None:
+      assert open(o2, 'rb').read() == want2, name
+    # production mode: same framing (names, lengths), deterministic for a seed, independent of the chunk size
+    p1, p2 = str(tmp_path / (name + '.1.p.fq')), (str(tmp_path / (name + '.2.p.fq')) if b2 is not None else None)
+    q1, q2 = str(tmp_path / (name + '.1.q.fq')), (str(tmp_path / (name + '.2.q.fq')) if b2 is not None else None)
+    rc.multi_process(il, m, i1, p1, i2, p2, processes=1, seed=11)
+    rc.multi_process(il, m, i1, q1, i2, q2, processes=1, seed=11, chunk_bytes=700)
+    assert open(p1, 'rb').read() == open(q1, 'rb').read(), name
+    got = open(p1, 'rb').read().split(b'\n')
+    assert [len(x) for x in got] == [len(x) for x in want1.split(b'\n')] and got[0::4] == want1.split(b'\n')[0::4], name

@@ -83,7 +83,13 @@ def multi_process(read_module, read_model, fastq1_in, fastq1_out, fastq2_in=None
     engine.load_model(read_model, rlen=rlen)
     paired = fastq2_in is not None
     ins = [_Stream(fastq1_in, engine.pinned(chunk_bytes))] + ([_Stream(fastq2_in, engine.pinned(chunk_bytes))] if paired else [])
-    outs = (engine.pinned(2 * chunk_bytes + 64), engine.pinned(2 * chunk_bytes + 64) if paired else None)
+    # two output buffer sets: the files of chunk k are written (one thread per file) while chunk k+1
+    # is read (one thread per file) and corrupted
+    outs = [(engine.pinned(2 * chunk_bytes + 64), engine.pinned(2 * chunk_bytes + 64) if paired else None) for _ in range(2)]
+    pending = [[], []]
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=4)
+    k = 0
     rng = None
     if mode == 'deterministic':
       worker_seed = np.random.RandomState(seed).randint(SEED_MAX)   # worker 0, readcorrupt.py:31,36
@@ -91,8 +97,8 @@ def multi_process(read_module, read_model, fastq1_in, fastq1_out, fastq2_in=None
     fps = [open(fastq1_out, 'wb')] + ([open(fastq2_out, 'wb')] if paired and fastq2_out is not None else [])
     try:
       while True:
-        for st in ins:
-          st.refill()
+        for fu in [pool.submit(st.refill) for st in ins]:
+          fu.result()
         a1 = ins[0].buf[:ins[0].fill]
         a2 = ins[1].buf[:ins[1].fill] if paired else None
         if a1.size == 0 or (paired and a2.size == 0):
@@ -107,19 +113,25 @@ def multi_process(read_module, read_model, fastq1_in, fastq1_out, fastq2_in=None
           else:
             lens = l1
           draws = read_module.corrupt_draws(lens.tolist(), rng)
+        for fu in pending[k]:                                   # this buffer set's previous writes
+          fu.result()
+        pending[k] = []
         o1, o2, n, c1, c2 = engine.corrupt_fastq(a1, a2, mode=MODE_DET if rng is not None else MODE_PHILOX, seed=seed, draws=draws,
-                                                 first_template=cnt, out=outs, partial=True)
+                                                 first_template=cnt, out=outs[k], partial=True)
         if n == 0:
           if all(st.eof for st in ins):
             break
           raise ValueError('a FASTQ record is larger than the chunk size ({} bytes)'.format(chunk_bytes))
-        for fp, o in zip(fps, (o1, o2)):
-          fp.write(memoryview(o))
+        pending[k] = [pool.submit(fp.write, memoryview(o)) for fp, o in zip(fps, (o1, o2))]
+        k ^= 1
         ins[0].consume(c1)
         if paired:
           ins[1].consume(c2)
         cnt += n
     finally:
+      for fu in pending[0] + pending[1]:
+        fu.result()
+      pool.shutdown(wait=True)
       for fp in fps:
         fp.close()
   finally:

@@ -64,21 +64,60 @@ def get_data_for_workers(model, vcf, seed):
     yield region
 
 
-class RegionCache(object):
-  """Regions and chromosome copies resident in HBM, built on first use."""
+def _without_end_crossing_deletions(vl, region):
+  """A deletion reaching beyond the region end would make the reference's node list end in 'D'
+  (readgenerate.py:192 assumes that never happens; its p_max then overshoots the haplotype and the
+  reads at the end come out short).  BED files that cut through a call set hit this routinely, so
+  such deletions are left out here, with a warning, instead of failing the run."""
+  cross = (vl.op == ord('D')) & (vl.pos + vl.oplen > region[2])
+  if not cross.any():
+    return vl
+  logger.warning('Region {}: ignoring {} deletion(s) that reach beyond the region end'.format(region, int(cross.sum())))
+  keep = np.flatnonzero(~cross)
 
-  def __init__(self, engine, vcf_df, fetch_ref):
+  def pool(p, off):
+    ln = (off[1:] - off[:-1])[keep]
+    noff = np.zeros(keep.size + 1, dtype=np.int64); np.cumsum(ln, out=noff[1:])
+    src = np.repeat(off[:-1][keep] - noff[:-1], ln) + np.arange(noff[-1])
+    return (p[src] if src.size else np.zeros(0, dtype=np.uint8)), noff
+  ap, ao = pool(vl.alt_pool, vl.alt_off)
+  rp, ro = pool(vl.ref_pool, vl.ref_off) if vl.ref_pool is not None else (None, None)
+  return vio.VariantList(vl.pos[keep], vl.op[keep], vl.oplen[keep], ap, ao, rp, ro)
+
+
+class RegionCache(object):
+  """Regions and chromosome copies resident in HBM, built on first use and released after their
+  last unit (``expect``: {(region idx, copy): number of units that will ask for it})."""
+
+  def __init__(self, engine, vcf_df, fetch_ref, expect=None):
     self.engine, self.vcf_df, self.fetch_ref = engine, vcf_df, fetch_ref
     self.regions, self.copies = {}, {}
+    self.left = dict(expect) if expect else None
+    self.left_copies = {}
+    for (r_idx, _cpy) in (expect or {}):
+      self.left_copies[r_idx] = self.left_copies.get(r_idx, 0) + 1
 
   def copy(self, r_idx, cpy):
     key = (r_idx, cpy)
     if key not in self.copies:
+      region = self.vcf_df[r_idx]['region']
       if r_idx not in self.regions:
-        region = self.vcf_df[r_idx]['region']
         self.regions[r_idx] = self.engine.load_region(self.fetch_ref(region), region[1])
-      self.copies[key] = self.engine.build_copy(self.regions[r_idx], self.vcf_df[r_idx]['v'][cpy])
+      self.copies[key] = self.engine.build_copy(self.regions[r_idx], _without_end_crossing_deletions(self.vcf_df[r_idx]['v'][cpy], region))
     return self.copies[key]
+
+  def done(self, r_idx, cpy):
+    """One unit of (region, copy) has been generated."""
+    if self.left is None:
+      return
+    key = (r_idx, cpy)
+    self.left[key] -= 1
+    if self.left[key] == 0:
+      self.engine.free_copy(self.copies.pop(key))
+      del self.left[key]
+      self.left_copies[r_idx] -= 1
+      if self.left_copies[r_idx] == 0:
+        self.engine.free_region(self.regions.pop(r_idx))
 
 
 def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sample_name, worker_id, ps,
@@ -112,7 +151,11 @@ def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read
     bind_host_thread_to_gpu(device)      # the pinned ring of this worker lands in the GPU's socket
     engine = Engine(device)
     engine.load_model(read_model)
-    cache = RegionCache(engine, vcf_df, fetch_ref)
+    expect = {}
+    for k in my_units:
+      key = (schedule[k]['region_idx'], schedule[k]['region_cpy'])
+      expect[key] = expect.get(key, 0) + 1
+    cache = RegionCache(engine, vcf_df, fetch_ref, expect)
     rlen = int(read_model['rlen'])
     span = max([vcf_df[schedule[k]['region_idx']]['region'][2] - vcf_df[schedule[k]['region_idx']]['region'][1] for k in my_units] + [1])
     est = int(span * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150) * 0.9) + (1 << 20)
@@ -135,6 +178,7 @@ def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read
         engine.wait_copies()
         done[k].put((f1, f2, buf))
       done[k].put(cnt)
+      cache.done(r_idx, cpy)
     stop.wait()          # keep the pinned buffers alive until the writer has drained them
   except BaseException as e:  # noqa: B902 -- handed to the writer, which re-raises
     for k in my_units:

@@ -467,3 +467,41 @@ def test_corrupt_reads_edge_inputs(tmp_path):
     assert open(p1, 'rb').read() == open(q1, 'rb').read(), name
     got = open(p1, 'rb').read().split(b'\n')
     assert [len(x) for x in got] == [len(x) for x in want1.split(b'\n')] and got[0::4] == want1.split(b'\n')[0::4], name
+
+
+def test_bed_cutting_through_a_deletion(tmp_path, caplog):
+  """A BED region that ends inside a deletion: the reference's node list would end in 'D' and its
+  reads at the region end come out short (readgenerate.py:192).  The command line leaves such a
+  deletion out with a warning; every read still re-derives from its qname against the haplotype
+  built without it, and regions are released after their last unit."""
+  import logging
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  wl = synth.config1(contig_len=60000, names=('1',))
+  seq = wl['contigs'][0][1]
+  far = np.abs(wl['tables'][0].pos - 30000) > 200
+  d_ref = seq[29999:30009].tobytes().decode()           # POS 30000, ten bases -> one: deletes 30001..30009
+  wl['tables'][0] = synth.merge_tables(synth._subset(wl['tables'][0], far), synth.table_from_records('1', [(30000, d_ref, d_ref[0], (1, 1))], 2))
+  cut = 30004                                          # 0-based end inside the deleted bases
+  wl['regions'] = [('1', 1000, cut), ('1', cut + 500, 59000)]
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'cut'))
+  r1, r2 = str(tmp_path / 'r1.fq'), str(tmp_path / 'r2.fq')
+  with caplog.at_level(logging.WARNING):
+    rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model('hiseq-X-v2.5-Garvan.pkl'), 30.0, r1, r2, threads=1, seed=3, mode='philox')
+  assert any('reach beyond the region end' in rec.getMessage() for rec in caplog.records)
+  regs = H.workload_regions(wl)
+  idx = {}
+  def index_for(chrom, cpy, pos):
+    r = regs[0] if pos <= cut else regs[1]
+    key = (r['region'], cpy)
+    if key not in idx:
+      idx[key] = H.HaplotypeIndex(r['ref'], r['region'][1] + 1, H.oracle_cv(rg._without_end_crossing_deletions(r['v'][cpy], r['region'])))
+    return idx[key]
+  n = 0
+  for which, path in enumerate((r1, r2)):
+    lines = open(path).read().split('\n')
+    for k in range(0, len(lines) - 1, 4):
+      info = rg.parse_qname(lines[k][1:])[which]
+      assert index_for(info.chrom, info.cpy, info.pos).check(info, lines[k + 1]) is None, lines[k]
+      n += 1
+  assert n > 5000

@@ -162,12 +162,16 @@ def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read
     slot = min(CHUNK_BYTES, est)
     for _ in range(n_buffers):
       free_q.put((engine.pinned(slot), engine.pinned(slot)))
+    t_build = t_gen = t_copy = 0.0
     for k in my_units:
       wd = schedule[k]
       r_idx, cpy = wd['region_idx'], wd['region_cpy']
+      ta = time.perf_counter()
       cp = cache.copy(r_idx, cpy)
+      tb = time.perf_counter()
       _, _, cnt, _, nb = generate_unit(engine, read_module, read_model, cp, vcf_df[r_idx]['region'][0], cpy, int(wd['rng_seed']),
                                        sample_name, 0, k, mode=mode, corrupt=corrupt, corrupt_seed=corrupt_seed, fetch=False)
+      tc = time.perf_counter()
       for off in range(0, nb, slot):
         buf = free_q.get()
         if buf is None or stop.is_set():
@@ -179,6 +183,10 @@ def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read
         done[k].put((f1, f2, buf))
       done[k].put(cnt)
       cache.done(r_idx, cpy)
+      td = time.perf_counter()
+      t_build += tb - ta; t_gen += tc - tb; t_copy += td - tc
+    logger.info('GPU {}: {} units; region/copy builds {:0.2f}s, unit kernels {:0.2f}s, copies + hand-over {:0.2f}s'.format(
+      device, len(my_units), t_build, t_gen, t_copy))
     stop.wait()          # keep the pinned buffers alive until the writer has drained them
   except BaseException as e:  # noqa: B902 -- handed to the writer, which re-raises
     for k in my_units:

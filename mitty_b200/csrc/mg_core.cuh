@@ -225,7 +225,6 @@ MG_HD int mg_ndigits(uint64_t v) {
   return d;
 }
 
-MG_HD int mg_nchars_int(int64_t v) { return v < 0 ? 1 + mg_ndigits((uint64_t)(-v)) : mg_ndigits((uint64_t)v); }
 
 // sum of the decimal lengths of 1..m  (closed form; used to place records whose qname carries a
 // serial number that is only known after the block/grid scan):  d*(m+1) - 11..1 (d ones)
@@ -353,11 +352,6 @@ MG_HD void mg_put_uint(W &w, uint64_t v) {   // v < 10^16
   int n = 0;
   do { acc = (acc << 4) | (v % 10); v /= 10; n++; } while (v);
   for (; n; n--) { w.put((uint8_t)('0' + (acc & 15))); acc >>= 4; }
-}
-
-template <class W>
-MG_HD void mg_put_int(W &w, int64_t v) {
-  if (v < 0) { w.put('-'); mg_put_uint(w, (uint64_t)(-v)); } else mg_put_uint(w, (uint64_t)v);
 }
 
 template <class W>
@@ -496,31 +490,6 @@ MG_NI typename SP::ptr mg_qname_bytes(typename SP::ptr dst, const uint8_t *prefi
   return bw.p;
 }
 
-// L bases of the haplotype starting at relative offset x, forward (strand 0) or reverse
-// complemented (strand 1, readgenerate.py:205-206), as ASCII through the writer.
-template <class W, class HP>
-MG_HD void mg_emit_seq(W &w, HP hap, uint32_t x, int L, int strand) {
-  int nfull = L >> 4;
-  for (int c = 0; c <= nfull; c++) {
-    int nb = (c < nfull) ? 16 : (L & 15);
-    if (nb == 0) break;
-    uint32_t codes;
-    if (strand == 0) {
-      codes = mg_codes16(hap, (int64_t)x + 16 * c);
-    } else {
-      // output bases [16c, 16c+16) are the complement of forward bases [L-16c-16, L-16c) reversed
-      int64_t s = (int64_t)x + L - 16 * (int64_t)c - 16;   // may dip up to 15 below x: hap is front-padded
-      codes = mg_revcomp16(mg_codes16(hap, s));
-    }
-    int k = 0;
-    for (; k + 4 <= nb; k += 4) w.put_word(mg_chars4((codes >> (2 * k)) & 0xFFu));
-    if (k < nb) {
-      uint32_t ch = mg_chars4((codes >> (2 * k)) & 0xFFu);
-      for (; k < nb; k++) { w.put((uint8_t)ch); ch >>= 8; }
-    }
-  }
-}
-
 // Register window over a read: the 2-bit words covering it are fetched up front (independent
 // loads, all in flight at once) and, for the reverse strand, reversed and complemented word by
 // word in descending order, so that BOTH strands become a forward extraction
@@ -555,25 +524,6 @@ template <int MAXW>
 MG_HD void mg_win_slide2(MgWin<MAXW> &W) {
   MG_UNROLL
   for (int i = 0; i < MAXW; i++) W.w[i] = (i + 2 < MAXW) ? W.w[i + 2] : 0u;
-}
-
-template <class WR, int MAXW>
-MG_HD void mg_emit_seq_win(WR &w, const MgWin<MAXW> &W, int L) {
-  MG_UNROLL
-  for (int c = 0; c < MAXW - 1; c++) {
-    if (16 * c < L) {
-      const uint32_t codes = mg_win_codes(W, c);
-      MG_UNROLL
-      for (int q = 0; q < 4; q++) {
-        const int n0 = 16 * c + 4 * q;
-        if (n0 + 4 <= L) w.put_word(mg_chars4((codes >> (8 * q)) & 0xFFu));
-        else if (n0 < L) {
-          uint32_t ch = mg_chars4((codes >> (8 * q)) & 0xFFu);
-          for (int j = 0; n0 + j < L; j++) { w.put((uint8_t)ch); ch >>= 8; }
-        }
-      }
-    }
-  }
 }
 
 template <class W>
@@ -956,18 +906,3 @@ MG_HD void mg_corrupt_call(uint8_t *seq, uint8_t *qual, int n, DP cum_row, int n
   qual[n] = (uint8_t)(bq + 33);
 }
 
-// Production mode: both uniforms come from one Philox half-block; the substitution choice reuses
-// the conditional uniformity of u_call given u_call < p (no third draw).
-template <class DP>
-MG_HD void mg_corrupt_call_philox(uint8_t *seq, uint8_t *qual, int n, DP cum_row, int n_bq, DP phred,
-                                  uint32_t w_bq, uint32_t w_call) {
-  double u_bq = (double)w_bq * (1.0 / 4294967296.0), u_call = (double)w_call * (1.0 / 4294967296.0);
-  int bq = mg_lower_bound_f64(cum_row, n_bq, u_bq);
-  if (bq > 93) bq = 93;
-  double p = phred[bq];
-  if (u_call < p) {
-    int rot = (int)(3.0 * (u_call / p));
-    seq[n] = mg_base_rot(seq[n], rot > 2 ? 2 : rot);
-  }
-  qual[n] = (uint8_t)(bq + 33);
-}

@@ -174,27 +174,32 @@ def test_philox_large_unit_exact(eng):
   eng.free_copy(cp); eng.free_region(rid)
 
 
-@pytest.mark.parametrize('wl_fn,cpy', [(synth.edge_workload, 1), (synth.softmask_workload, 0)])
-def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy):
+@pytest.mark.parametrize('wl_fn,cpy,model_name', [(synth.edge_workload, 1, 'hiseq-X-v2.5-Garvan.pkl'),
+                                                  (synth.softmask_workload, 0, 'hiseq-X-v2.5-Garvan.pkl'),
+                                                  (synth.edge_workload, 0, '1kg-pcr-free.pkl')])   # 2x250: the wide register window
+def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy, model_name):
   """Production-mode corruption is fully specified (Philox counters, per-cycle miscall thresholds,
   alias rows): the fused emit kernel and the standalone corrupt kernel must reproduce the numpy
   restatement of that specification byte for byte."""
   import mitty_b200.simulation.illumina as il
   from mitty_b200.engine import MODE_PHILOX
   from tests import philox_ref as PR
-  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  m = H.model(model_name)
   rm = il.read_model_params(m, 30.0)
   eng.load_model(rm)
   # the tables the library built at load time == the Python restatement of Vose's method
+  n64_want = PR.exact64_cycles(m['cum_bq_mat'])
   for kshift in (6, 7):
     alias, n64, lthr = eng.model_tables(kshift)
-    assert n64 == PR.exact64_cycles(m['cum_bq_mat']) == 150
+    assert n64 == n64_want
     want, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, kshift, n_rows=n64 if kshift == 6 else None)
     np.testing.assert_array_equal(alias, want)
     if kshift == 7:
       np.testing.assert_array_equal(lthr, err)
-  alias6 = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 6, n_rows=150)[0]
+  alias6 = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 6, n_rows=n64_want)[0]
   alias7, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 7)
+  ks_fused = 6 if rm['rlen'] <= n64_want else 7            # the emit kernel's choice (64-entry rows while they are exact)
+  alias_fused = alias6 if ks_fused == 6 else alias7
   r = H.workload_regions(wl_fn())[0]
   rid = eng.load_region(r['ref'], r['region'][1])
   cp = eng.build_copy(rid, r['v'][cpy])
@@ -204,8 +209,8 @@ def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy):
   c1, c2, ccnt, _, _ = eng.generate_unit(cp, n, 0.1, MODE_PHILOX, unit_seed, '@E:0:0:', '|e|1', corrupt=True, corrupt_seed=cseed)
   assert cnt == ccnt and cnt > 500
   k1 = unit_seed ^ 0x636f7231
-  assert c1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, alias6, 6, err, cseed, k1)
-  assert c2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, alias6, 6, err, cseed, k1)
+  assert c1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, alias_fused, ks_fused, err, cseed, k1)
+  assert c2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, alias_fused, ks_fused, err, cseed, k1)
   # standalone corrupt-reads over the same perfect reads
   eng.load_model(m)
   s1, s2, scnt = eng.corrupt_fastq(p1, p2, mode=MODE_PHILOX, seed=cseed)

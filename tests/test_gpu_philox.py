@@ -176,7 +176,8 @@ def test_philox_large_unit_exact(eng):
 
 @pytest.mark.parametrize('wl_fn,cpy,model_name', [(synth.edge_workload, 1, 'hiseq-X-v2.5-Garvan.pkl'),
                                                   (synth.softmask_workload, 0, 'hiseq-X-v2.5-Garvan.pkl'),
-                                                  (synth.edge_workload, 0, '1kg-pcr-free.pkl')])   # 2x250: the wide register window
+                                                  (synth.edge_workload, 0, '1kg-pcr-free.pkl'),   # 2x250: the wide register window
+                                                  (synth.edge_workload, 1, 'hiseq-X-v2.5-Garvan.pkl:200')])   # reads longer than max_rlen: 128-entry rows, BQ 93
 def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy, model_name):
   """Production-mode corruption is fully specified (Philox counters, per-cycle miscall thresholds,
   alias rows): the fused emit kernel and the standalone corrupt kernel must reproduce the numpy
@@ -184,7 +185,9 @@ def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy, model_name):
   import mitty_b200.simulation.illumina as il
   from mitty_b200.engine import MODE_PHILOX
   from tests import philox_ref as PR
-  m = H.model(model_name)
+  m = dict(H.model(model_name.split(':')[0]))
+  if ':' in model_name:
+    m['mean_rlen'] = int(model_name.split(':')[1])       # legal: the path reads only mean_rlen (illumina.py:20)
   rm = il.read_model_params(m, 30.0)
   eng.load_model(rm)
   # the tables the library built at load time == the Python restatement of Vose's method

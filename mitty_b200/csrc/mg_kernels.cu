@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
         const uint32_t nvec = (batch_bytes - head) >> 4;
         const uint4 *sv = reinterpret_cast<const uint4 *>(ssrc + head);
         uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
-        for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
+        for (uint32_t v = lane; v < nvec; v += 32) __stcs(gv + v, sv[v]);   // streaming: the FASTQ bytes must not push the haplotype out of L2
         const uint32_t done = head + (nvec << 4);
         if (done + lane < batch_bytes) gdst[done + lane] = ssrc[done + lane];
         __syncwarp();

@@ -55,7 +55,7 @@ int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double 
  * layout is documented at MgCorruptCtx in mitty_b200/csrc/mg_core.cuh):
  * thr_out u32[n_mates][n_cycles] = per-cycle miscall thresholds floor(perr * 2^32), perr =
  * sum_q P(q) phred_p[q]; alias_out u32[n_mates][n_cycles][2][1 << kshift] (kshift 6 or 7) = Vose
- * alias rows (prob24 << 7 | alias) of the quality given a correct call ([0]) and given a miscall
+ * alias rows (prob24 << 8 | alias) of the quality given a correct call ([0]) and given a miscall
  * ([1]); n64 = number of leading cycles for which the 64-entry rows are exact (all mass on
  * qualities < 64).                                                                              */
 int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t alias_cap, int32_t *n64, uint32_t *thr_out);

@@ -151,8 +151,8 @@ uint32_t build_quality_rows(const double *cum, int n_bq, int K, const double *ph
     se += qe[k]; so += qo[k];
   }
   for (int k = 0; k < K; k++) { qe[k] = se > 0.0 ? qe[k] / se : q[k]; qo[k] = so > 0.0 ? qo[k] / so : q[k]; }
-  vose(qo, K, 24, 7, out);
-  vose(qe, K, 24, 7, out + K);
+  vose(qo, K, 24, 8, out);
+  vose(qe, K, 24, 8, out + K);
   return se >= 1.0 ? 0xFFFFFFFFu : (se <= 0.0 ? 0u : (uint32_t)std::floor(se * 4294967296.0));
 }
 
@@ -683,7 +683,7 @@ static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint
   if (stage > 48 * 1024) stage = 48 * 1024;
   P.stage_cap = stage & ~15;
   int smem = 0;
-  const int grid = mg_unit_grid(L, d->corrupt, P.stage_cap, &smem);
+  const int grid = mg_unit_grid(L, d->corrupt ? P.cor.kshift : 0, P.stage_cap, &smem);
 
   // scan state: [totals 4 x u64][tile counter (16 B)][descA][descB]
   const size_t state_bytes = 48 + 16 * (size_t)std::max(P.n_tiles, 1);

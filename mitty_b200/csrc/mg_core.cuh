@@ -723,7 +723,8 @@ MG_HD void mg_emit_frame(typename SP::ptr dst, uint32_t qlen, const uint8_t *pre
 //     substituted base = base_rot[base][(w_call >= T/3) + (w_call >= floor(2T/3))]   (illumina.py:131-136,160;
 //     given a miscall, w_call is uniform on [0, T), so no third draw is needed)
 //     idx = w_bq >> (32 - kshift); frac = (w_bq << kshift) >> 8        (24 bits)
-//     e = alias[((f * n_cycles + n) * 2 + miscall) << kshift | idx]; bq = frac < (e >> 7) ? idx : (e & 127)
+//     e = alias[((f * n_cycles + n) * 2 + miscall) << kshift | idx]  (entry = prob24 << 8 | alias);
+//     bq = frac < (e >> 8) ? idx : (e & 255), evaluated as (w_bq << kshift) < (e & ~255)
 struct MgCorruptCtx {
   const uint32_t *alias;   // [n_mates][n_cycles][2][1 << kshift]
   const uint32_t *thr;     // [n_mates][n_cycles] miscall thresholds
@@ -753,8 +754,7 @@ MG_HD uint32_t mg_corrupt_draw(const MgCorruptCtx &C, uint32_t f, int n, uint32_
   const uint32_t miss = (uint32_t)(w_call < T);
   const uint32_t idx = w_bq >> (32 - C.kshift);
   const uint32_t e = C.alias[((2u * cyc + miss) << C.kshift) | idx];
-  const uint32_t frac = (w_bq << C.kshift) >> 8;
-  qual = (frac < (e >> 7) ? idx : (e & 127u)) + 33u;
+  qual = ((w_bq << C.kshift) < (e & 0xFFFFFF00u) ? idx : (e & 255u)) + 33u;
   return miss ? (4u | mg_sub_index(w_call, T)) : 0u;
 }
 
@@ -773,7 +773,8 @@ MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_b
 // become quality bytes).  Cycles >= L read a valid row and are masked out.
 struct MgDraw4 { uint32_t wb[4], wc[4], e[4], T[4], miss; };
 
-template <bool FULL, bool ES>   // FULL: all four cycles are inside the read (n0 + 4 <= L); ES: thresholds staged in shared memory
+template <bool FULL, bool ES, int KS>   // FULL: all four cycles are inside the read (n0 + 4 <= L); ES: thresholds staged in
+                                        // shared memory; KS: kshift known at compile time (0 = read it from the context)
 MG_HD void mg_corrupt4_draw(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, MgDraw4 &D) {
   const uint32_t cyc = f * (uint32_t)C.n_cycles + (uint32_t)n0;
   bool staged = false;
@@ -791,7 +792,7 @@ MG_HD void mg_corrupt4_draw(const MgCorruptCtx &C, uint32_t serial, uint32_t f, 
   const MgPhilox r1 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1) + 1u, C.k0, C.k1);
   D.wb[0] = r0.v[0]; D.wb[1] = r0.v[2]; D.wb[2] = r1.v[0]; D.wb[3] = r1.v[2];
   D.wc[0] = r0.v[1]; D.wc[1] = r0.v[3]; D.wc[2] = r1.v[1]; D.wc[3] = r1.v[3];
-  const uint32_t ks = (uint32_t)C.kshift, K = 1u << ks;
+  const uint32_t ks = KS ? (uint32_t)KS : (uint32_t)C.kshift, K = 1u << ks;
   D.miss = 0;
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
@@ -822,14 +823,13 @@ MG_HD void mg_corrupt4_subst(const MgDraw4 &D, uint32_t &b4) {
   }
 }
 
-template <bool FULL>
+template <bool FULL, int KS>
 MG_HD uint32_t mg_corrupt4_qual(const MgCorruptCtx &C, const MgDraw4 &D, int n0, int L) {
-  const uint32_t ks = (uint32_t)C.kshift;
+  const uint32_t ks = KS ? (uint32_t)KS : (uint32_t)C.kshift;
   uint32_t bq[4];
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
-    const uint32_t frac = (D.wb[j] << ks) >> 8;
-    bq[j] = frac < (D.e[j] >> 7) ? (D.wb[j] >> (32u - ks)) : (D.e[j] & 127u);
+    bq[j] = (D.wb[j] << ks) < (D.e[j] & 0xFFFFFF00u) ? (D.wb[j] >> (32u - ks)) : (D.e[j] & 255u);   // frac24 < prob24
   }
   if (FULL) return (bq[0] + (bq[1] << 8)) + ((bq[2] + (bq[3] << 8)) << 16) + 0x21212121u;
   uint32_t qw = 0;
@@ -840,7 +840,7 @@ MG_HD uint32_t mg_corrupt4_qual(const MgCorruptCtx &C, const MgDraw4 &D, int n0,
 
 // SEQ and QUAL lines of one read, corrupted on the fly: every thread of a warp is at the same
 // cycle of its own record, so the alias row (one 256-byte line pair) is shared by the warp.
-template <class SP, int MAXW, class HP, class EP>
+template <class SP, int KS = 0, int MAXW, class HP, class EP>
 MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc,
                                const MgCorruptCtx &C, uint32_t serial, uint32_t f) {
   const int L = S.L;
@@ -860,15 +860,15 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
         uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw;
         MgDraw4 D;
         if (n0 + 4 <= L) {
-          mg_corrupt4_draw<true, ES>(C, serial, f, n0, L, D);
+          mg_corrupt4_draw<true, ES, KS>(C, serial, f, n0, L, D);
           if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
           mg_corrupt4_subst(D, b4);
-          pb4 = b4; pqw = mg_corrupt4_qual<true>(C, D, n0, L); pend = true;
+          pb4 = b4; pqw = mg_corrupt4_qual<true, KS>(C, D, n0, L); pend = true;
         } else {
           if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); pend = false; }
-          mg_corrupt4_draw<false, ES>(C, serial, f, n0, L, D);
+          mg_corrupt4_draw<false, ES, KS>(C, serial, f, n0, L, D);
           mg_corrupt4_subst(D, b4);
-          qw = mg_corrupt4_qual<false>(C, D, n0, L);
+          qw = mg_corrupt4_qual<false, KS>(C, D, n0, L);
           const uint32_t ch = mg_chars4(b4);
           for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
         }

@@ -687,7 +687,7 @@ void mg_launch_plan(const MgUnitParams &P, cudaStream_t st) {
 // No block barrier and no scan: placement was decided by k_unit_plan.
 // a record larger than the whole stage (only possible with absurdly long CIGARs): straight to
 // global memory through generic pointers, streaming sequence source; cold and out of line
-template <bool CORRUPT>
+template <int CORRUPT>
 __device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const MgUnitParams &P,
                                            unsigned long long cnt, MgReadRef first, MgReadRef second, MgReadRef mine, int f) {
   const int L = P.rlen;
@@ -701,7 +701,8 @@ __device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const Mg
   }
 }
 
-template <int MAXW, bool CORRUPT>
+// CORRUPT: 0 = perfect reads; 6 / 7 = fused corruption with that kshift (64- / 128-entry alias rows)
+template <int MAXW, int CORRUPT>
 __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
@@ -773,7 +774,7 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
               const bool full = (f == 0) || (P.out[0] == nullptr);
               if constexpr (CORRUPT) {
                 if (full) mg_emit_frame<MgSharedSpace>(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
-                mg_emit_seq_corrupt<MgSharedSpace>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)rank, (uint32_t)f);
+                mg_emit_seq_corrupt<MgSharedSpace, CORRUPT>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)rank, (uint32_t)f);
               } else {
                 if (full) mg_emit_record<MgSharedSpace>(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
                 else mg_rewrite_seq<MgSharedSpace>(dst + qlen + 1, S, P.exc, P.n_exc);
@@ -810,11 +811,11 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
 
 typedef void (*unit_kernel_t)(const MgUnitParams);
 
-static unit_kernel_t unit_kernel(int L, int corrupt) {
+static unit_kernel_t unit_kernel(int L, int corrupt) {   // corrupt: 0, or the kshift (6 / 7) of the fused corruption
   // register window: MAXW - 1 >= ceil((15 + L) / 16)
-  if (L <= 161) return corrupt ? k_unit_emit<12, true> : k_unit_emit<12, false>;
-  if (L <= 305) return corrupt ? k_unit_emit<21, true> : k_unit_emit<21, false>;
-  return corrupt ? k_unit_emit<0, true> : k_unit_emit<0, false>;
+  if (L <= 161) return corrupt == 0 ? k_unit_emit<12, 0> : corrupt == 6 ? k_unit_emit<12, 6> : k_unit_emit<12, 7>;
+  if (L <= 305) return corrupt == 0 ? k_unit_emit<21, 0> : corrupt == 6 ? k_unit_emit<21, 6> : k_unit_emit<21, 7>;
+  return corrupt == 0 ? k_unit_emit<0, 0> : corrupt == 6 ? k_unit_emit<0, 6> : k_unit_emit<0, 7>;
 }
 
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
@@ -833,7 +834,7 @@ int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
 
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st) {
   if (P.n_tiles == 0) return;
-  unit_kernel(P.rlen, P.corrupt)<<<grid, MG_CTA, smem_bytes, st>>>(P);
+  unit_kernel(P.rlen, P.corrupt ? P.cor.kshift : 0)<<<grid, MG_CTA, smem_bytes, st>>>(P);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -41,7 +41,8 @@ def exact64_cycles(cum_bq_mat):
 
 
 def _vose(q, K):
-  """Vose's alias method, the same operation order as vose() in mg_api.cu (entry = prob24 << 7 | alias)."""
+  """Vose's alias method, the same operation order as vose() in mg_api.cu (entry = prob24 << 8 | alias; prob24 is capped at 2^24 - 1, as any
+  entry that fills its 32 bits is)."""
   q = list(q)
   small, large = [], []
   for i in range(K):
@@ -56,8 +57,8 @@ def _vose(q, K):
   out = np.zeros(K, dtype=np.uint32)
   for i in range(K):
     pr = min(max(prob[i], 0.0), 1.0)
-    pq = min(int(np.floor(pr * 16777216.0 + 0.5)), 1 << 24)
-    out[i] = (pq << 7) | alias[i]
+    pq = min(int(np.floor(pr * 16777216.0 + 0.5)), (1 << 24) - 1)
+    out[i] = (pq << 8) | alias[i]
   return out
 
 
@@ -106,7 +107,7 @@ def alias_distribution(alias_row, kshift):
   K = 1 << kshift
   p = np.zeros(128)
   for i in range(K):
-    pq, al = int(alias_row[i]) >> 7, int(alias_row[i]) & 127
+    pq, al = int(alias_row[i]) >> 8, int(alias_row[i]) & 255
     p[i] += pq / float(1 << 24) / K
     p[al] += (1.0 - pq / float(1 << 24)) / K
   return p
@@ -145,7 +146,7 @@ def corrupt_file(fq, f, alias, kshift, thr, k0, k1, serials=None):
     idx = (w_bq >> np.uint64(32 - kshift)).astype(np.int64)
     frac = ((w_bq << np.uint64(kshift)) & MASK) >> np.uint64(8)
     e = alias[f, np.arange(Lr), miss.astype(np.int64), idx].astype(np.uint64)
-    bq = np.where(frac < (e >> np.uint64(7)), idx, (e & np.uint64(127)).astype(np.int64))
+    bq = np.where(frac < (e >> np.uint64(8)), idx, (e & np.uint64(255)).astype(np.int64))
     rot = (w_call >= T // np.uint64(3)).astype(np.int64) + (w_call >= (np.uint64(2) * T) // np.uint64(3)).astype(np.int64)
     for n in np.flatnonzero(miss):
       seq[n] = ROT.get(seq[n], b'NNN')[rot[n]]

@@ -679,7 +679,7 @@ static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint
 
   P.n_tiles = (int)((n + MG_PLAN_TILE - 1) / MG_PLAN_TILE);
   // per-warp stage of the emit kernel: 32 records with an average qname; larger batches are split
-  int stage = 32 * (2 * L + 5 + 100);
+  int stage = 32 * (2 * L + 5 + 96);
   if (stage > 48 * 1024) stage = 48 * 1024;
   P.stage_cap = stage & ~15;
   int smem = 0;

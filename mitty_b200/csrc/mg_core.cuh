@@ -730,7 +730,7 @@ struct MgCorruptCtx {
   const uint32_t *thr;     // [n_mates][n_cycles] miscall thresholds
   int kshift, n_cycles, n_mates;
   uint32_t k0, k1;
-  uint32_t thr_s, lp;      // device hot path: shared-window address of a staged copy of thr, laid out [file][lp]
+  uint32_t thr_s, lp;      // device hot path: shared-window address of the staged thresholds, planes [T][T/3][2T/3], each [file][lp]
 };
 
 MG_HD uint32_t mg_ctz4(uint32_t m) {   // index of the lowest set bit of a non-zero 4-bit mask
@@ -808,17 +808,32 @@ MG_HD void mg_corrupt4_draw(const MgCorruptCtx &C, uint32_t serial, uint32_t f, 
   }
 }
 
-// substitutions (about 2 % of the bases): each lane walks ITS OWN miscall bits, so the warp runs this
-// loop as often as its worst lane has miscalls among the four bases -- almost always once
-MG_HD void mg_corrupt4_subst(const MgDraw4 &D, uint32_t &b4) {
+// substitutions (2-7 % of the bases with the shipped models): each lane walks ITS OWN miscall bits, so
+// the warp runs this loop as often as its worst lane has miscalls among the four bases.  In the
+// emit kernel the thirds of the thresholds are staged next to them ([T][T/3][2T/3] planes), so the
+// loop only selects its w_call.
+template <bool ES>
+MG_HD void mg_corrupt4_subst(const MgCorruptCtx &C, const MgDraw4 &D, uint32_t f, int n0, uint32_t &b4) {
   uint32_t any = D.miss;
   while (any) {
     const uint32_t j = mg_ctz4(any);
     any &= any - 1u;
     const uint32_t w = j == 0 ? D.wc[0] : j == 1 ? D.wc[1] : j == 2 ? D.wc[2] : D.wc[3];
-    const uint32_t t = j == 0 ? D.T[0] : j == 1 ? D.T[1] : j == 2 ? D.T[2] : D.T[3];
+    uint32_t sub;
+    bool staged = false;
+#if defined(__CUDA_ARCH__)
+    if constexpr (ES) {
+      uint32_t t1, t2;
+      const uint32_t a = C.thr_s + 4u * ((2u + f) * C.lp + (uint32_t)n0 + j);
+      asm("ld.shared.b32 %0, [%1];" : "=r"(t1) : "r"(a));
+      asm("ld.shared.b32 %0, [%1];" : "=r"(t2) : "r"(a + 8u * C.lp));
+      sub = (uint32_t)(w >= t1) + (uint32_t)(w >= t2);
+      staged = true;
+    }
+#endif
+    if (!staged) sub = mg_sub_index(w, j == 0 ? D.T[0] : j == 1 ? D.T[1] : j == 2 ? D.T[2] : D.T[3]);
     const uint32_t code = (b4 >> (2u * j)) & 3u;
-    const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * mg_sub_index(w, t))) & 3u;
+    const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * sub)) & 3u;
     b4 ^= (code ^ nc) << (2u * j);
   }
 }
@@ -862,12 +877,12 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
         if (n0 + 4 <= L) {
           mg_corrupt4_draw<true, ES, KS>(C, serial, f, n0, L, D);
           if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
-          mg_corrupt4_subst(D, b4);
+          mg_corrupt4_subst<ES>(C, D, f, n0, b4);
           pb4 = b4; pqw = mg_corrupt4_qual<true, KS>(C, D, n0, L); pend = true;
         } else {
           if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); pend = false; }
           mg_corrupt4_draw<false, ES, KS>(C, serial, f, n0, L, D);
-          mg_corrupt4_subst(D, b4);
+          mg_corrupt4_subst<ES>(C, D, f, n0, b4);
           qw = mg_corrupt4_qual<false, KS>(C, D, n0, L);
           const uint32_t ch = mg_chars4(b4);
           for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }

@@ -714,13 +714,16 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
   const int L = P.rlen;
   MgCorruptCtx cor = P.cor;
   if constexpr (CORRUPT) {
-    // per-cycle miscall thresholds of both files, staged behind the stages: [file][lp], lp = L rounded up to 4
+    // per-cycle miscall thresholds of both files and their thirds, staged behind the stages:
+    // planes [T][T/3][2T/3], each [file][lp], lp = L rounded up to 4
     uint32_t *s_thr = reinterpret_cast<uint32_t *>(smem + (MG_CTA / 32) * (uint32_t)(P.stage_cap + 16));
     const int lp = (L + 3) & ~3;
 #pragma unroll 1
     for (int i = t; i < 2 * lp; i += MG_CTA) {
       const int f = i / lp, n = i - f * lp;
-      s_thr[i] = (n < P.cor.n_cycles && f < P.cor.n_mates) ? P.cor.thr[f * P.cor.n_cycles + n] : 0u;
+      const uint32_t T = (n < P.cor.n_cycles && f < P.cor.n_mates) ? P.cor.thr[f * P.cor.n_cycles + n] : 0u;
+      const uint32_t q = T / 3u, r = T - 3u * q;
+      s_thr[i] = T; s_thr[2 * lp + i] = q; s_thr[4 * lp + i] = 2u * q + (r >> 1);   // mg_sub_index's thirds
     }
     cor.thr_s = (uint32_t)__cvta_generic_to_shared(s_thr);
     cor.lp = (uint32_t)lp;
@@ -819,7 +822,7 @@ static unit_kernel_t unit_kernel(int L, int corrupt) {   // corrupt: 0, or the k
 }
 
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
-  int smem = (MG_CTA / 32) * (stage_cap + 16) + (corrupt ? 2 * 4 * ((L + 3) & ~3) : 0);   // stages + staged miscall thresholds
+  int smem = (MG_CTA / 32) * (stage_cap + 16) + (corrupt ? 3 * 2 * 4 * ((L + 3) & ~3) : 0);   // stages + staged miscall thresholds and their thirds
   if (const char *x = getenv("MG_EXTRA_SMEM")) smem += atoi(x);   // occupancy experiments only
   *smem_bytes = smem;
   unit_kernel_t k = unit_kernel(L, corrupt);

@@ -660,6 +660,11 @@ template <class WR, int MAXW, class HP>
 MG_HD void mg_emit_seq_src(WR &w, MgSeqSrc<MAXW, HP> &S) {
   const int L = S.L;
   mg_for_each_chunk(S, [&](uint32_t codes, int c) {
+    if (16 * c + 16 <= L) {              // a whole chunk: four words, no bounds logic
+      MG_NOUNROLL
+      for (int q = 0; q < 4; q++, codes >>= 8) w.put_word(mg_chars4(codes & 0xFFu));
+      return;
+    }
     MG_NOUNROLL
     for (int q = 0; q < 4; q++) if (16 * c + 4 * q < L) mg_put_bases4(w, (codes >> (8 * q)) & 0xFFu, 16 * c + 4 * q, L);
   });
@@ -868,8 +873,21 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
   uint32_t pb4 = 0, pqw = 0;
   bool pend = false;
   mg_for_each_chunk(S, [&](uint32_t codes, int c) {
+    if (16 * c + 16 <= L) {              // a whole chunk: four full groups, no per-group bounds logic
+      int n0 = 16 * c;
+      MG_NOUNROLL
+      for (int q = 0; q < 4; q++, n0 += 4, codes >>= 8) {
+        uint32_t b4 = codes & 0xFFu;
+        MgDraw4 D;
+        mg_corrupt4_draw<true, ES, KS>(C, serial, f, n0, L, D);
+        if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
+        mg_corrupt4_subst<ES>(C, D, f, n0, b4);
+        pb4 = b4; pqw = mg_corrupt4_qual<true, KS>(C, D, n0, L); pend = true;
+      }
+      return;
+    }
     MG_NOUNROLL
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 4; q++) {        // the last, partial chunk
       const int n0 = 16 * c + 4 * q;
       if (n0 < L) {
         uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw;

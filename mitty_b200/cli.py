@@ -74,15 +74,18 @@ def print_qname(ctx, param, value):
 @click.option('--deterministic', is_flag=True, help="Consume the reference's numpy draws: byte-exact vs `mitty generate-reads --threads 1`")
 @click.option('--corrupt', is_flag=True, help='Fuse the Illumina corruption model into read generation (Philox draws)')
 @click.option('--devices', default=None, help='comma separated CUDA devices (default: the first --threads GPUs)')
-def generate_reads(fasta, vcf, sample_name, bed, modelfile, coverage, seed, fastq1, fastq2, threads, deterministic, corrupt, devices):
+@click.option('--drop-end-deletions', is_flag=True, help='Leave out deletions that reach beyond the end of their BED region (default: error; the reference mis-handles them)')
+def generate_reads(fasta, vcf, sample_name, bed, modelfile, coverage, seed, fastq1, fastq2, threads, deterministic, corrupt, devices, drop_end_deletions):
   """Generate simulated reads (--threads = number of GPUs to use)"""
   import mitty_b200.simulation.readgenerate as reads
+  if deterministic and corrupt:
+    raise click.UsageError('--corrupt draws from Philox; for --deterministic run generate-reads and then corrupt-reads, as the reference does')
   read_module, model = get_read_model(modelfile)
   reads.process_multi_threaded(
     fasta, vcf, sample_name, bed, read_module, model, coverage,
     fastq1, fastq2, threads=threads, seed=seed,
     mode='deterministic' if deterministic else 'philox', corrupt=corrupt,
-    devices=[int(x) for x in devices.split(',')] if devices else None)
+    devices=[int(x) for x in devices.split(',')] if devices else None, drop_end_deletions=drop_end_deletions)
 
 
 @cli.command('corrupt-reads', short_help='Apply corruption model to FASTQ file of reads')

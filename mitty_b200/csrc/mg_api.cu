@@ -223,9 +223,17 @@ int mg_ctx_create(int device, void *stream, mg_ctx **out) {
   ctx->device = device;
   if (stream) ctx->stream = reinterpret_cast<cudaStream_t>(stream);
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MG_ECUDA; } ctx->own_stream = true; }
-  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2);
-  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&ctx->ev_d2h[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_d2h[1], cudaEventDisableTiming);
+  cudaError_t ce = cudaEventCreate(&ctx->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&ctx->ev1);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&ctx->ev2);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_d2h[0], cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_d2h[1], cudaEventDisableTiming);
+  if (ce != cudaSuccess) {
+    fprintf(stderr, "mitty_b200: cannot create the context's streams / events on device %d: %s\n", device, cudaGetErrorString(ce));
+    mg_ctx_destroy(ctx);
+    return MG_ECUDA;
+  }
   *out = ctx;
   return MG_OK;
 }
@@ -233,7 +241,7 @@ int mg_ctx_create(int device, void *stream, mg_ctx **out) {
 void mg_ctx_destroy(mg_ctx *ctx) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (int i = 0; i < 2; i++) if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
   ctx->regions.clear(); ctx->copies.clear();
@@ -266,6 +274,7 @@ int mg_host_free(mg_ctx *ctx, void *p) {
   if (!ctx) return MG_EINVAL;
   DeviceGuard g(ctx->device);
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));   // the pinned FASTQ buffers are written by this stream
   CU(cudaFreeHost(p));
   return MG_OK;
 }

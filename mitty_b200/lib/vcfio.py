@@ -16,6 +16,7 @@ The per-copy result is a ``VariantList``: flat numpy arrays ready for the C-ABI
 (``mg_copy_build``), which also behaves like the reference's ``list`` of ``Variant`` objects.
 """
 import gzip
+import re
 import time
 import logging
 import threading
@@ -158,6 +159,9 @@ class VcfTable(object):
       raise ValueError('Sample {} not in VCF (samples: {})'.format(sample, hdr[9:]))
     col = 9 + hdr[9:].index(sample)
     self.header_end = h                                                 # the '##' meta lines are data[:h]
+    # contigs the header declares (##contig=<ID=...>): with the contigs seen in the body these are the
+    # names an indexed fetch accepts; pysam raises ValueError for any other (vcfio.py:62)
+    self.header_contigs = set(m.decode() for m in re.findall(rb'^##contig=<(?:[^>\n]*,)?ID=([^,>\n]+)', data[:h], flags=re.M))
     body = min(he + 1, len(data))
     nl = np.flatnonzero(buf[body:] == 10) + body
     starts = np.concatenate([np.array([body], dtype=np.int64), nl + 1])
@@ -256,6 +260,11 @@ class VcfTable(object):
   def fetch(self, contig, start, stop):
     """Indices of records overlapping 0-based [start, stop) -- htslib semantics (vcfio.py:62)."""
     if contig not in self.contigs:
+      if contig not in self.header_contigs:
+        # pysam: "ValueError: invalid contig `chr1`" -- e.g. a BED that says 'chr1' over a VCF that says '1'.
+        # Going on would silently produce variant-free reads with truth qnames.
+        raise ValueError('invalid contig `{}`: not in the VCF header (##contig) nor among its records ({})'.format(
+          contig, ', '.join(sorted(set(self.contigs) | self.header_contigs)[:8]) or 'no contigs at all'))
       return contig, np.zeros(0, dtype=np.int64)
     c = self.contigs[contig]
     p0 = c.pos - 1
@@ -373,6 +382,9 @@ def prepare_variant_file(fname_in, sample, bed_fname, fname_out, write_mode='w')
       continue
     c = table.contigs[contig]
     cx = (c.reflen[idx] > 1) & ((c.ae - c.as_)[idx] > 1) & (c.gt[idx] == 1).any(axis=1)
+    for k in np.flatnonzero(cx & (c.reflen[idx] == (c.ae - c.as_)[idx])).tolist():   # `_v.ref != alt` (vcfio.py:143)
+      i = int(idx[k])
+      cx[k] = data[c.rs[i]:c.re[i]] != data[c.as_[i]:c.ae[i]]
     for k, i in enumerate(idx.tolist()):
       if i in c.slow:
         ref, alleles, gt = c.slow[i]
@@ -384,7 +396,11 @@ def prepare_variant_file(fname_in, sample, bed_fname, fname_out, write_mode='w')
     for i in idx[~cx].tolist():
       out.append(data[c.ls[i]:c.f9e[i]] + b'\t' + data[c.ss[i]:c.se[i]] + b'\n')
   blob = b''.join(out)
-  if str(fname_out).endswith('.gz'):
+  if str(fname_out) == '-':                 # `filter-variants ... - | bgzip -c > x.vcf.gz` (examples/reads/run.sh:9)
+    import sys
+    sys.stdout.buffer.write(blob)
+    sys.stdout.buffer.flush()
+  elif str(fname_out).endswith('.gz'):
     with gzip.open(fname_out, 'wb') as fp:
       fp.write(blob)
   else:

@@ -21,14 +21,16 @@ from mitty_b200.engine import MODE_DET, MODE_PHILOX, SEED_MAX, Engine
 logger = logging.getLogger(__name__)
 
 
-def _read(fname):
+def open_fastq(fname):
+  """One open() per input, gzip sniffed from the first bytes of that same stream: the inputs may
+  be FIFOs or /dev/fd/N process substitutions (examples/reads/run.sh:13-16 of the reference feeds
+  corrupt-reads from FIFOs), where a second open() blocks for ever or loses the bytes already read."""
   import gzip
-  with open(fname, 'rb') as fp:
-    magic = fp.read(2)
-  if magic == b'\x1f\x8b':
-    with gzip.open(fname, 'rb') as fp:
-      return np.frombuffer(fp.read(), dtype=np.uint8)
-  return np.fromfile(fname, dtype=np.uint8)
+  import io
+  fp = io.open(fname, 'rb', buffering=1 << 20)      # BufferedReader: peek() does not consume
+  if fp.peek(2)[:2] == b'\x1f\x8b':
+    return gzip.GzipFile(fileobj=fp, mode='rb')
+  return fp
 
 
 def seq_lengths(buf):
@@ -42,11 +44,11 @@ class _Stream(object):
   """A FASTQ file read in chunks into one (pinned) buffer; the unconsumed tail is carried over."""
 
   def __init__(self, fname, buf):
-    import gzip
-    with open(fname, 'rb') as fp:
-      magic = fp.read(2)
-    self.fp = gzip.open(fname, 'rb') if magic == b'\x1f\x8b' else open(fname, 'rb')
+    self.fp = open_fastq(fname)
     self.buf, self.fill, self.eof = buf, 0, False
+
+  def close(self):
+    self.fp.close()
 
   def refill(self):
     mv = memoryview(self.buf)

@@ -64,15 +64,20 @@ def get_data_for_workers(model, vcf, seed):
     yield region
 
 
-def _without_end_crossing_deletions(vl, region):
-  """A deletion reaching beyond the region end would make the reference's node list end in 'D'
+def _without_end_crossing_deletions(vl, region, drop):
+  """A deletion reaching beyond the region end makes the reference's node list end in 'D'
   (readgenerate.py:192 assumes that never happens; its p_max then overshoots the haplotype and the
-  reads at the end come out short).  BED files that cut through a call set hit this routinely, so
-  such deletions are left out here, with a warning, instead of failing the run."""
+  reads at the region end come out short).  That output cannot be reproduced, so by default such a
+  region is an error (the message of mg_copy_build); with ``drop`` (``--drop-end-deletions``) the
+  offending deletions are left out -- a documented deviation from the reference -- and counted."""
   cross = (vl.op == ord('D')) & (vl.pos + vl.oplen > region[2])
   if not cross.any():
-    return vl
-  logger.warning('Region {}: ignoring {} deletion(s) that reach beyond the region end'.format(region, int(cross.sum())))
+    return vl, 0
+  if not drop:
+    raise ValueError('Region {}: {} deletion(s) reach beyond the region end (first at POS {}): the reference\'s node list would '
+                     'end in \'D\' (readgenerate.py:192 assumes it never does). Trim the BED region or the VCF, or pass '
+                     '--drop-end-deletions to leave these deletions out'.format(region, int(cross.sum()), int(vl.pos[cross][0])))
+  logger.warning('Region {}: leaving out {} deletion(s) that reach beyond the region end'.format(region, int(cross.sum())))
   keep = np.flatnonzero(~cross)
 
   def pool(p, off):
@@ -82,15 +87,16 @@ def _without_end_crossing_deletions(vl, region):
     return (p[src] if src.size else np.zeros(0, dtype=np.uint8)), noff
   ap, ao = pool(vl.alt_pool, vl.alt_off)
   rp, ro = pool(vl.ref_pool, vl.ref_off) if vl.ref_pool is not None else (None, None)
-  return vio.VariantList(vl.pos[keep], vl.op[keep], vl.oplen[keep], ap, ao, rp, ro)
+  return vio.VariantList(vl.pos[keep], vl.op[keep], vl.oplen[keep], ap, ao, rp, ro), int(cross.sum())
 
 
 class RegionCache(object):
   """Regions and chromosome copies resident in HBM, built on first use and released after their
   last unit (``expect``: {(region idx, copy): number of units that will ask for it})."""
 
-  def __init__(self, engine, vcf_df, fetch_ref, expect=None):
+  def __init__(self, engine, vcf_df, fetch_ref, expect=None, drop_end_deletions=False):
     self.engine, self.vcf_df, self.fetch_ref = engine, vcf_df, fetch_ref
+    self.drop_end_deletions, self.dropped = drop_end_deletions, 0
     self.regions, self.copies = {}, {}
     self.left = dict(expect) if expect else None
     self.left_copies = {}
@@ -103,7 +109,9 @@ class RegionCache(object):
       region = self.vcf_df[r_idx]['region']
       if r_idx not in self.regions:
         self.regions[r_idx] = self.engine.load_region(self.fetch_ref(region), region[1])
-      self.copies[key] = self.engine.build_copy(self.regions[r_idx], _without_end_crossing_deletions(self.vcf_df[r_idx]['v'][cpy], region))
+      vl, n_drop = _without_end_crossing_deletions(self.vcf_df[r_idx]['v'][cpy], region, self.drop_end_deletions)
+      self.dropped += n_drop
+      self.copies[key] = self.engine.build_copy(self.regions[r_idx], vl)
     return self.copies[key]
 
   def done(self, r_idx, cpy):
@@ -141,7 +149,7 @@ CHUNK_BYTES = 64 << 20     # pinned ring slot per file: a unit is streamed to th
 
 
 def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,
-                corrupt_seed, n_buffers, done, free_q, stop):
+                corrupt_seed, n_buffers, done, free_q, stop, drop_end_deletions=False):
   """One thread per GPU: its units, in schedule order.  A unit's FASTQ bytes stay on the device and
   are streamed through a small ring of pinned slot pairs (page-locking unit-sized host buffers
   costs seconds for a chr1-sized unit)."""
@@ -155,7 +163,7 @@ def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read
     for k in my_units:
       key = (schedule[k]['region_idx'], schedule[k]['region_cpy'])
       expect[key] = expect.get(key, 0) + 1
-    cache = RegionCache(engine, vcf_df, fetch_ref, expect)
+    cache = RegionCache(engine, vcf_df, fetch_ref, expect, drop_end_deletions)
     rlen = int(read_model['rlen'])
     span = max([vcf_df[schedule[k]['region_idx']]['region'][2] - vcf_df[schedule[k]['region_idx']]['region'][1] for k in my_units] + [1])
     est = int(span * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150) * 0.9) + (1 << 20)
@@ -198,7 +206,7 @@ def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read
 
 def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_module, model, coverage,
                            fastq1_fname, fastq2_fname, threads=2, seed=7, mode='philox', corrupt=False,
-                           corrupt_seed=None, devices=None):
+                           corrupt_seed=None, devices=None, drop_end_deletions=False):
   """Same signature as the reference (readgenerate.py:76-78) plus keyword-only extras.
 
   ``threads`` = number of GPUs to use (capped by the GPUs present; ``devices`` overrides).  Work
@@ -214,8 +222,17 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   from mitty_b200.engine import device_count
 
   t_in = time.time()
+  if mode not in ('philox', 'deterministic'):
+    raise ValueError('mode must be "philox" or "deterministic"')
+  if corrupt and mode == 'deterministic':
+    # checked before any file is opened (and truncated) or any GPU work is started
+    raise ValueError('fused corruption draws from Philox; for the deterministic mode run generate-reads --deterministic '
+                     'and then corrupt-reads --deterministic, as the reference does')
   read_model = read_module.read_model_params(model, coverage)
   vcf_df = vio.load_variant_file(vcf_fname, sample_name, bed_fname)
+  for r in vcf_df:                       # inputs the engine rejects: found before the outputs are opened
+    for vl in r['v']:
+      _without_end_crossing_deletions(vl, r['region'], drop_end_deletions)
   fasta = vio.FastaFile(fasta_fname)
   fetch_ref = lambda region: fasta.fetch(reference=region[0], start=region[1], end=region[2])  # noqa: E731
   schedule = list(get_data_for_workers(read_model, vcf_df, seed))
@@ -232,7 +249,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   cs = seed if corrupt_seed is None else corrupt_seed
   workers = [threading.Thread(target=_gpu_worker, daemon=True,
                               args=(dev, assign[i], schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,
-                                    cs, 4, done, free_qs[i], stop))
+                                    cs, 4, done, free_qs[i], stop, drop_end_deletions))
              for i, dev in enumerate(devices)]
   owner = {k: i for i, units in enumerate(assign) for k in units}
 
@@ -284,26 +301,36 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
 
 # ---- the qname contract's inverse (readgenerate.py:256-291) --------------------------------------
 
-from collections import namedtuple  # noqa: E402
+class ReadInfo(tuple):
+  """What the qname says about one read: the fields of the reference's ``ri`` tuple, in its order."""
+  __slots__ = ()
+  _fields = ('sample', 'rid', 'chrom', 'cpy', 'strand', 'pos', 'rlen', 'cigar', 'special_cigar', 'v_list')
 
-ri = namedtuple('ReadInfo', ['sample', 'rid', 'chrom', 'cpy', 'strand', 'pos', 'rlen', 'cigar', 'special_cigar', 'v_list'])
+  def __new__(cls, *a):
+    return tuple.__new__(cls, a)
+
+  def __getattr__(self, name):
+    try:
+      return self[self._fields.index(name)]
+    except ValueError:
+      raise AttributeError(name)
 
 
 def parse_qname(qname):
-  """qname (without the leading '@') -> one ReadInfo per read, in file order."""
-  def _parse_(_cigar, _v_list):
-    if _cigar[0] == '>':  # read from inside a long insertion
-      _special_cigar = _cigar
-      _cigar = _cigar.split(':')[-1]
-    else:
-      _special_cigar = None
-    return _cigar, _special_cigar, [int(v) for v in _v_list.split(',') if v != '']
+  """qname (without the leading '@') -> [ReadInfo of the read in file 1, ReadInfo of the read in file 2].
 
-  d = qname.split('|')
-  rid, chrom, cpy = d[:3]
-  sample, _ = rid.split(':', 1)
-  cpy = int(cpy)
-  return [
-    ri(sample, rid, chrom, cpy, int(strand), int(pos), int(rlen), *_parse_(cigar, v_list))
-    for strand, pos, rlen, cigar, v_list in zip(d[3::5], d[4::5], d[5::5], d[6::5], d[7::5])
-  ]
+  Layout (``__qname_format__``): three template fields, then five fields per read.  A read taken from
+  inside a long insertion carries '>p:nI' as its CIGAR: the plain CIGAR is then 'nI' and the original
+  string is kept as ``special_cigar`` (readgenerate.py:277-283)."""
+  f = qname.split('|')
+  rid, chrom, cpy = f[0], f[1], int(f[2])
+  sample = rid.split(':', 1)[0]
+  out = []
+  for k in range(3, len(f) - 4, 5):
+    strand, pos, rlen, cigar, vs = f[k:k + 5]
+    special = cigar if cigar.startswith('>') else None
+    if special is not None:
+      cigar = cigar.rsplit(':', 1)[1]
+    out.append(ReadInfo(sample, rid, chrom, cpy, int(strand), int(pos), int(rlen), cigar, special,
+                        [int(v) for v in vs.split(',') if v]))
+  return out

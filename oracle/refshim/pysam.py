@@ -15,6 +15,9 @@ Only I/O semantics are provided, as the reference uses them:
   ``[POS-1, POS-1+len(REF))`` and is returned iff that interval overlaps ``[start, stop)``
   (pinned by the reference's own test_vcfio.py:9-18).
 * ``FastxFile(f)`` yielding ``.name .sequence .quality``  (readcorrupt.py:49-55)
+* ``VariantFile(f, mode='w', header=...)`` + ``.write(record)`` as ``prepare_variant_file`` uses them
+  (vcfio.py:156-164): the meta lines, a column header naming the subset sample, and each written
+  record's first nine columns plus that sample's column.
 """
 import gzip
 
@@ -68,10 +71,11 @@ class _Samples(object):
 
 
 class _Record(object):
-  __slots__ = ('contig', 'pos', 'ref', 'alts', 'samples', 'rlen')
+  __slots__ = ('contig', 'pos', 'ref', 'alts', 'samples', 'rlen', 'fields')
 
-  def __init__(self, contig, pos, ref, alts, gt):
+  def __init__(self, contig, pos, ref, alts, gt, fields=None):
     self.contig, self.pos, self.ref, self.alts = contig, pos, ref, alts
+    self.fields = fields      # first nine columns + the subset sample's column (for VariantFile.write)
     self.rlen = len(ref)
     all_alleles = (ref,) + alts
     self.samples = _Samples(_Sample(gt, tuple(all_alleles[g] if g is not None else None for g in gt)))
@@ -83,9 +87,20 @@ class VariantFile(object):
     self._sample_col = None
     self._rows = []  # (contig, pos, ref, alts, [sample fields...], fmt)
     self._samples = []
+    self._meta = []
+    self._out = None
+    if mode.startswith('w'):
+      # header = the input VariantFile (its .header is itself here): meta lines + the subset sample
+      import sys
+      self._out = sys.stdout if fname == '-' else open(fname, 'w')
+      self._out.write(''.join(header._meta))
+      names = [header._samples[header._subset]] if header._subset is not None else header._samples
+      self._out.write('#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t' + '\t'.join(names) + '\n')
+      return
     with _open_text(fname) as fp:
       for line in fp:
         if line.startswith('##'):
+          self._meta.append(line)
           continue
         f = line.rstrip('\n').split('\t')
         if line.startswith('#'):
@@ -98,6 +113,24 @@ class VariantFile(object):
 
   def subset_samples(self, names):
     self._subset = self._samples.index(names[0])
+
+  @property
+  def header(self):
+    return self
+
+  def write(self, rec):
+    self._out.write('\t'.join(rec.fields) + '\n')
+
+  def close(self):
+    if self._out is not None:
+      self._out.flush()
+
+  def __del__(self):
+    try:
+      if self._out is not None:
+        self._out.flush()
+    except Exception:
+      pass
 
   def fetch(self, contig=None, start=None, stop=None):
     col = 9 + (self._subset if self._subset is not None else 0)
@@ -113,7 +146,7 @@ class VariantFile(object):
       fmt = f[8].split(':')
       gt_s = f[col].split(':')[fmt.index('GT')]
       gt = tuple(None if g == '.' else int(g) for g in gt_s.replace('/', '|').split('|'))
-      yield _Record(contig, pos, ref, alts, gt)
+      yield _Record(contig, pos, ref, alts, gt, f[:9] + [f[col]])
 
 
 class _Fastx(object):

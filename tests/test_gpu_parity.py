@@ -471,9 +471,10 @@ def test_corrupt_reads_edge_inputs(tmp_path):
 
 def test_bed_cutting_through_a_deletion(tmp_path, caplog):
   """A BED region that ends inside a deletion: the reference's node list would end in 'D' and its
-  reads at the region end come out short (readgenerate.py:192).  The command line leaves such a
-  deletion out with a warning; every read still re-derives from its qname against the haplotype
-  built without it, and regions are released after their last unit."""
+  reads at the region end come out short (readgenerate.py:192).  By default that is an error raised
+  before anything is written; with drop_end_deletions (--drop-end-deletions) the deletion is left out
+  with a warning, every read still re-derives from its qname against the haplotype built without it,
+  and regions are released after their last unit."""
   import logging
   import mitty_b200.simulation.illumina as il
   import mitty_b200.simulation.readgenerate as rg
@@ -486,8 +487,12 @@ def test_bed_cutting_through_a_deletion(tmp_path, caplog):
   wl['regions'] = [('1', 1000, cut), ('1', cut + 500, 59000)]
   fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'cut'))
   r1, r2 = str(tmp_path / 'r1.fq'), str(tmp_path / 'r2.fq')
-  with caplog.at_level(logging.WARNING):
+  with pytest.raises(ValueError, match='reach beyond the region end'):
     rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model('hiseq-X-v2.5-Garvan.pkl'), 30.0, r1, r2, threads=1, seed=3, mode='philox')
+  assert not os.path.exists(r1) and not os.path.exists(r2)          # nothing was opened, let alone truncated
+  with caplog.at_level(logging.WARNING):
+    rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model('hiseq-X-v2.5-Garvan.pkl'), 30.0, r1, r2, threads=1, seed=3, mode='philox',
+                              drop_end_deletions=True)
   assert any('reach beyond the region end' in rec.getMessage() for rec in caplog.records)
   regs = H.workload_regions(wl)
   idx = {}
@@ -495,7 +500,7 @@ def test_bed_cutting_through_a_deletion(tmp_path, caplog):
     r = regs[0] if pos <= cut else regs[1]
     key = (r['region'], cpy)
     if key not in idx:
-      idx[key] = H.HaplotypeIndex(r['ref'], r['region'][1] + 1, H.oracle_cv(rg._without_end_crossing_deletions(r['v'][cpy], r['region'])))
+      idx[key] = H.HaplotypeIndex(r['ref'], r['region'][1] + 1, H.oracle_cv(rg._without_end_crossing_deletions(r['v'][cpy], r['region'], True)[0]))
     return idx[key]
   n = 0
   for which, path in enumerate((r1, r2)):
@@ -505,3 +510,108 @@ def test_bed_cutting_through_a_deletion(tmp_path, caplog):
       assert index_for(info.chrom, info.cpy, info.pos).check(info, lines[k + 1]) is None, lines[k]
       n += 1
   assert n > 5000
+
+
+@pytest.mark.timeout(300)
+def test_fifo_pipeline_like_the_reference_example(tmp_path):
+  """examples/reads/run.sh:13-16 of the reference: generate-reads writes into two FIFOs, corrupt-reads
+  reads them (`<(cat < tf1)`) and writes into two more pipes.  Everything is sequential I/O on
+  streams that can be opened exactly once; the result must equal the reference's golden files."""
+  import threading
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readcorrupt as rc
+  import mitty_b200.simulation.readgenerate as rg
+  info = H.golden()['fastq']['edge']
+  m = H.model(info['model'])
+  wl = synth.edge_workload()
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'))
+  tf1, tf2, of1, of2 = (str(tmp_path / x) for x in ('tf1', 'tf2', 'of1', 'of2'))
+  for f in (tf1, tf2, of1, of2):
+    os.mkfifo(f)
+  got, errs = {}, []
+
+  def drain(name, path):
+    with open(path, 'rb') as fp:
+      got[name] = fp.read()
+
+  def generate():
+    try:
+      rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, info['coverage'], tf1, tf2, threads=1, seed=info['seed'], mode='deterministic')
+    except BaseException as e:  # noqa: B902
+      errs.append(e)
+
+  threads = [threading.Thread(target=drain, args=('c1', of1), daemon=True), threading.Thread(target=drain, args=('c2', of2), daemon=True),
+             threading.Thread(target=generate, daemon=True)]
+  for t in threads:
+    t.start()
+  rc.multi_process(il, m, tf1, of1, tf2, of2, processes=1, seed=info['seed'], mode='deterministic')
+  for t in threads:
+    t.join(timeout=120)
+  assert not errs, errs
+  assert got['c1'] == H.golden_fastq('edge.c1.fq.gz') and got['c2'] == H.golden_fastq('edge.c2.fq.gz')
+
+
+def test_generate_reads_without_fastq2(tmp_path):
+  """`generate-reads` without --fastq2: the writer zips the template's records with the open files
+  (readgenerate.py:246-248), so only file 1 is written -- with the same bytes as in a paired run
+  (the qname still describes both reads)."""
+  from click.testing import CliRunner
+  from mitty_b200.cli import cli
+  info = H.golden()['fastq']['edge']
+  wl = synth.edge_workload()
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'))
+  r1 = str(tmp_path / 'only1.fq')
+  res = CliRunner().invoke(cli, ['generate-reads', fa, vcf, wl['sample'], bed, info['model'], str(info['coverage']), str(info['seed']),
+                                 r1, '--threads', '1', '--deterministic'], catch_exceptions=False)
+  assert res.exit_code == 0, res.output
+  assert open(r1, 'rb').read() == H.golden_fastq('edge.r1.fq.gz')
+  assert not [x for x in os.listdir(str(tmp_path)) if x.endswith('.fq') and x != 'only1.fq']      # no second file appears
+  # --deterministic with --corrupt is refused before any output is opened
+  r3 = str(tmp_path / 'never.fq')
+  res = CliRunner().invoke(cli, ['generate-reads', fa, vcf, wl['sample'], bed, info['model'], '30', '7', r3, '--deterministic', '--corrupt'])
+  assert res.exit_code != 0 and not os.path.exists(r3)
+
+
+@pytest.mark.timeout(1500)
+def test_bench_unit_full_size_exact(eng):
+  """ONE unit of exactly the workload bench.py's number is quoted on -- synth.chr1_shaped(seed=7,
+  length=249250621), copy 1, Philox mode, perfect reads: 5.7 M templates, 4.3 GB per file, byte
+  offsets above 2^32, template starts near 2.5e8 -- against the oracle fed with the device's own
+  draws: count and sha256 of both files.  (About 75 s of oracle time.)  The fused-corruption twin of
+  the same unit is then checked against the numpy specification on a 1 % sample of its records."""
+  import hashlib
+  import mitty_b200.simulation.illumina as il
+  from mitty_b200.engine import MODE_PHILOX
+  from tests import philox_ref as PR
+  wl = synth.chr1_shaped(seed=7, length=249250621, n_runs=39)
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  rm = il.read_model_params(m, 30.0)
+  eng.load_model(rm)
+  r = H.workload_regions(wl)[0]
+  rid = eng.load_region(r['ref'], 0)
+  cp = eng.build_copy(rid, r['v'][1])
+  n = int((cp.p_max - cp.p_min) * rm['p'] * 1.2)
+  seed = (2000 * 7919 + 2 * 104729) & 0xFFFFFFFF        # bench.py's seed of its first timed step, unit k = 2 (copy 1, pass 0)
+  ts, te, fo = eng.sample_templates(n, rm['p'], MODE_PHILOX, seed, cp=cp)
+  keep = te >= 0
+  f1, f2, cnt, nk, nb = eng.generate_unit(cp, n, rm['p'], MODE_PHILOX, seed, '@S:0:2:', '|1|1')
+  assert nb > (1 << 32) and cnt > 5000000 and cnt < nk
+  o1, o2, ocnt = oracle.generate_unit(r['ref'], 1, H.oracle_cv(r['v'][1]), rm['rlen'], ts[keep], te[keep], fo[keep], 'S:0:2', '1', 1,
+                                      cap=int(nb) + 4096)
+  assert cnt == ocnt and len(o1) == nb == f1.size
+  assert hashlib.sha256(f1).hexdigest() == H.sha256(o1) and hashlib.sha256(f2).hexdigest() == H.sha256(o2)
+  del o1, o2
+  # fused corruption of the same unit vs the numpy specification, on every 100th record
+  c1, c2, ccnt, _, cnb = eng.generate_unit(cp, n, rm['p'], MODE_PHILOX, seed, '@S:0:2:', '|1|1', corrupt=True, corrupt_seed=2000)
+  assert ccnt == cnt and cnb == nb
+  tables = PR.fused_tables(eng, m, rm['rlen'])
+  for perfect, corrupted, f in ((f1, c1, 0), (f2, c2, 1)):
+    nl = np.flatnonzero(perfect == 10)
+    assert nl.size == 4 * cnt
+    starts = np.concatenate([[0], nl[3:-1:4] + 1])
+    ends = nl[3::4] + 1
+    pick = np.arange(0, cnt, 100)
+    sample = b''.join(perfect[starts[i]:ends[i]].tobytes() for i in pick)
+    want = PR.corrupt_file(sample, f, tables, 2000, seed ^ 0x636f7231, serials=pick)
+    assert b''.join(corrupted[starts[i]:ends[i]].tobytes() for i in pick) == want
+  eng.free_copy(cp); eng.free_region(rid)

@@ -7,7 +7,7 @@ import pytest
 
 from mitty_b200.lib import vcfio
 
-HDR = '##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS0\tS1\n'
+HDR = '##fileformat=VCFv4.2\n##contig=<ID=1>\n##contig=<ID=3>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS0\tS1\n'
 
 
 def simple_parse(text, sample, contig, start, stop, cpy):
@@ -132,4 +132,40 @@ def test_filter_variants(tmp_path):
     df = vcfio.load_variant_file(vout, sample, bed)                       # no complex-variant error any more
     assert [d['region'][0] for d in df] == ['1', '2']
   with pytest.raises(ValueError):
+    vcfio.load_variant_file(vin, 'S0', bed)
+
+
+def test_filter_variants_matches_reference(tmp_path, capsysbinary):
+  """The records filter-variants keeps == what the unmodified reference's prepare_variant_file keeps
+  (`_complex_variant`, mitty/lib/vcfio.py:139-146) on the same VCF/BED, sample by sample
+  (tests/golden/filter_variants.json, written by tests/golden/make_filter_golden.py)."""
+  import json
+  import os
+  from tests import helpers as H
+  g = json.load(open(os.path.join(H.GOLDEN, 'filter_variants.json')))
+  vin = str(tmp_path / 'in.vcf'); open(vin, 'w').write(g['vcf'])
+  bed = str(tmp_path / 'r.bed'); open(bed, 'w').write(g['bed'])
+  for sample, want in sorted(g['kept'].items()):
+    vout = str(tmp_path / (sample + '.vcf'))
+    vcfio.prepare_variant_file(vin, sample, bed, vout)
+    recs = [l.split('\t') for l in open(vout).read().split('\n') if l and not l.startswith('#')]
+    assert [[r[0], int(r[1]), r[3], r[4], r[9]] for r in recs] == want
+    # '-' writes the same text to stdout (examples/reads/run.sh:9 pipes it into bgzip)
+    capsysbinary.readouterr()
+    vcfio.prepare_variant_file(vin, sample, bed, '-')
+    assert capsysbinary.readouterr().out == open(vout, 'rb').read()
+
+
+def test_unknown_contig_is_an_error(tmp_path):
+  """A BED contig that the VCF neither declares (##contig) nor holds is pysam's
+  `ValueError: invalid contig` (vcfio.py:62), e.g. 'chr1' over a VCF that says '1'; a declared contig
+  without records is an empty region (diploid by default, vcfio.py:74-76)."""
+  hdr = HDR.replace('##contig=<ID=3>', '##contig=<length=500,ID=7,assembly=x>')
+  vin = str(tmp_path / 'c.vcf'); open(vin, 'w').write(hdr + '1\t10\t.\tA\tC\t.\tPASS\t.\tGT\t0|1\t1|1\n')
+  bed = str(tmp_path / 'c.bed')
+  open(bed, 'w').write('1\t0\t100\n7\t0\t100\n')
+  df = vcfio.load_variant_file(vin, 'S0', bed)
+  assert [len(d['v']) for d in df] == [2, 2] and len(df[1]['v'][0]) == 0
+  open(bed, 'w').write('chr1\t0\t100\n')
+  with pytest.raises(ValueError, match='invalid contig'):
     vcfio.load_variant_file(vin, 'S0', bed)

@@ -28,7 +28,7 @@ typedef struct mg_ctx mg_ctx;
 #define MG_EVALUE (-4)     /* input the reference would reject or cannot represent */
 #define MG_EINDEX (-5)     /* read longer than the model (IndexError, illumina.py:156) */
 
-#define MG_MODE_PHILOX_C 0 /* production: counter-based Philox4x32-10 draws on the device       */
+#define MG_MODE_PHILOX_C 0 /* production: counter-based Philox draws on the device (4x32-10; corruption stream 4x32-7) */
 #define MG_MODE_DET_C 1    /* deterministic: the reference's numpy RandomState draws, from host  */
 #define MG_MODE_EXPLICIT_C 2 /* test hook: explicit template starts and lengths                 */
 
@@ -51,14 +51,15 @@ int mg_host_free(mg_ctx *ctx, void *p);
 int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double *cum_bq_mat, int n_mates,
                   int n_cycles, int n_bq, const double *phred_p, int rlen);
 
-/* production-mode tables derived from the model at load time (for tests / inspection; the draw
- * layout is documented at MgCorruptCtx in mitty_b200/csrc/mg_core.cuh):
- * thr_out u32[n_mates][n_cycles] = per-cycle miscall thresholds floor(perr * 2^32), perr =
- * sum_q P(q) phred_p[q]; alias_out u32[n_mates][n_cycles][2][1 << kshift] (kshift 6 or 7) = Vose
- * alias rows (prob24 << 8 | alias) of the quality given a correct call ([0]) and given a miscall
- * ([1]); n64 = number of leading cycles for which the 64-entry rows are exact (all mass on
- * qualities < 64).                                                                              */
-int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t alias_cap, int32_t *n64, uint32_t *thr_out);
+/* production-mode corruption tables derived from the model at load time (for tests / inspection;
+ * the draw layout is documented at MgCorruptCtx in mitty_b200/csrc/mg_core.cuh): per (mate, cycle) ONE
+ * Vose alias row over the joint outcomes (quality, substitution) of illumina.corrupt_single_read
+ * (illumina.py:151-160).  which = 0: the table of the fused emit kernel (cycles < rlen); 1: the table of
+ * the standalone corrupt kernel (all n_cycles).  alias_out u32[n_mates][n_cycles][1 << *kshift];
+ * *code9 = 1 when the outcome codes are 9 bits wide (some quality >= 64 carries mass), else 8 bits;
+ * *n_rows = number of leading cycles that were built.                                            */
+int mg_model_tables(mg_ctx *ctx, int32_t which, uint32_t *alias_out, int64_t alias_cap, int32_t *kshift, int32_t *code9,
+                    int32_t *n_rows);
 
 /* ---- region: replaces fasta.fetch(chrom, start, end) + the str the worker keeps
  * (mitty/simulation/readgenerate.py:186).  ref_bytes = the region's bases as in the FASTA

@@ -65,11 +65,12 @@ struct mg_ctx {
   bool own_stream = false;
   std::string err;
   // model
-  DevBuf m_tlen, m_bq, m_phred, m_alias[2], m_err, m_tlen_alias;
-  bool has_tlen_alias = false;   // n_tlen + 1 <= 1024 outcomes: 1024-entry alias table of the template-length model   // alias[0]: 64-entry rows, alias[1]: 128-entry rows
+  DevBuf m_tlen, m_bq, m_phred, m_alias[2], m_tlen_alias;
+  bool has_tlen_alias = false;   // n_tlen + 1 <= 1024 outcomes: 1024-entry alias table of the template-length model
   int n_tlen = 0, n_mates = 0, n_cycles = 0, n_bq = 0, rlen = 0;
-  int n64 = 0;   // leading cycles whose rows (all mates) put no mass on BQ >= 64: 64-entry alias rows are exact there
-  std::vector<uint32_t> h_alias[2]; std::vector<uint32_t> h_thr; std::vector<double> h_phred;
+  // production-mode corruption tables (MgCorruptCtx): [0] the emit kernel's (cycles < rlen), [1] the
+  // standalone corrupt kernel's (every cycle of the model); kshift / code9 are chosen per table
+  std::vector<uint32_t> h_alias[2]; int a_kshift[2] = {0, 0}, a_code9[2] = {0, 0}, a_rows[2] = {0, 0};
   std::vector<std::pair<void *, size_t>> pool;   // device blocks of freed copies, reused by the next build
   std::map<void *, size_t> block_size;
   // handles
@@ -77,7 +78,7 @@ struct mg_ctx {
   std::map<int64_t, std::unique_ptr<Copy>> copies;
   int64_t next_id = 1;
   // scratch
-  DevBuf s_raw, s_exc, s_ts, s_u, s_fo, s_tsorted, s_partial, s_state, s_out[2][2], s_str, s_qn, s_plan, s_sample[3];
+  DevBuf s_raw, s_exc, s_ts, s_u, s_fo, s_tsorted, s_partial, s_state, s_out[2][2], s_str, s_plan, s_sample[3];
   DevBuf c_in[2], c_out[2], c_nl[2], c_cnt, c_sz[2], c_off[2], c_tmp, c_draw[4];
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   cudaStream_t copy_stream = nullptr;              // D2H of finished units, overlapping the next unit's kernels
@@ -102,10 +103,10 @@ int fail(mg_ctx *c, int code, const char *fmt, ...) {
 // Vose's alias method over K outcomes with probabilities q (sum 1): entry i = prob << alias_bits | alias,
 // prob quantised to prob_bits.  A draw takes idx uniform in [0, K) and frac uniform in [0, 2^prob_bits):
 // outcome = frac < prob ? idx : alias.
-void vose(std::vector<double> q, int K, int prob_bits, int alias_bits, uint32_t *out) {
+void vose_raw(std::vector<double> q, int K, std::vector<double> &prob, std::vector<int> &alias) {
   std::vector<int> small, large;
   for (int i = 0; i < K; i++) { q[i] *= K; (q[i] < 1.0 ? small : large).push_back(i); }
-  std::vector<double> prob(K, 1.0); std::vector<int> alias(K);
+  prob.assign(K, 1.0); alias.resize(K);
   for (int i = 0; i < K; i++) alias[i] = i;
   while (!small.empty() && !large.empty()) {
     int s = small.back(); small.pop_back();
@@ -114,6 +115,11 @@ void vose(std::vector<double> q, int K, int prob_bits, int alias_bits, uint32_t 
     q[l] = (q[l] + q[s]) - 1.0;
     (q[l] < 1.0 ? small : large).push_back(l);
   }
+}
+
+void vose(std::vector<double> q, int K, int prob_bits, int alias_bits, uint32_t *out) {
+  std::vector<double> prob; std::vector<int> alias;
+  vose_raw(q, K, prob, alias);
   const double scale = (double)(1u << prob_bits);
   for (int i = 0; i < K; i++) {
     double pr = prob[i] < 0.0 ? 0.0 : (prob[i] > 1.0 ? 1.0 : prob[i]);
@@ -138,22 +144,48 @@ std::vector<double> ss_left_probs(const double *cum, int n, int K, int clip) {
   return q;
 }
 
-// One (mate, cycle) of the quality model, outcome clipped to 93 (illumina.py:156): the miscall
-// probability perr = sum_q P(q) phred_p[q] as a 32-bit threshold and the two alias rows of the
-// quality given a correct call (out[0..K)) and given a miscall (out[K..2K)).  See MgCorruptCtx.
-uint32_t build_quality_rows(const double *cum, int n_bq, int K, const double *phred_p, uint32_t *out) {
-  const std::vector<double> q = ss_left_probs(cum, n_bq, K, 93);
-  std::vector<double> qe(K), qo(K);
-  double se = 0.0, so = 0.0;
-  for (int k = 0; k < K; k++) {
-    const double p = k < 100 ? phred_p[k] : 0.0;
-    qe[k] = q[k] * p; qo[k] = q[k] * (1.0 - p);
-    se += qe[k]; so += qo[k];
+// One (mate, cycle) of the quality model as the list of its outcomes (q, s) with non-zero mass
+// (MgCorruptCtx in mg_core.cuh): quality q clipped to 93 (illumina.py:156); s = 0 "called correctly"
+// with P(q) (1 - phred_p[q]), s = 1..3 "called as base ^ s" with P(q) phred_p[q] / 3 each.
+// code = s << qb | q.
+struct Outcome { uint32_t code; double mass; };
+
+std::vector<Outcome> row_outcomes(const double *cum, int n_bq, const double *phred_p, int qb) {
+  const std::vector<double> q = ss_left_probs(cum, n_bq, 94, 93);
+  std::vector<Outcome> out;
+  for (int b = 0; b < 94; b++) {
+    if (!(q[b] > 0.0)) continue;
+    const double p = b < 100 ? phred_p[b] : 0.0;
+    const double m0 = q[b] * (1.0 - p), m = q[b] * p / 3.0;
+    if (m0 > 0.0) out.push_back({(uint32_t)b, m0});
+    if (m > 0.0) for (uint32_t sub = 1; sub <= 3; sub++) out.push_back({(sub << qb) | (uint32_t)b, m});
   }
-  for (int k = 0; k < K; k++) { qe[k] = se > 0.0 ? qe[k] / se : q[k]; qo[k] = so > 0.0 ? qo[k] / so : q[k]; }
-  vose(qo, K, 24, 8, out);
-  vose(qe, K, 24, 8, out + K);
-  return se >= 1.0 ? 0xFFFFFFFFu : (se <= 0.0 ? 0u : (uint32_t)std::floor(se * 4294967296.0));
+  return out;
+}
+
+// Vose alias row of one (mate, cycle): entry = thr << (32 - tb) | self code << cb | alias code,
+// (tb, cb) = (16, 8) or (14, 9).  Entries beyond the outcome list have threshold 0 and carry their
+// alias' code twice; an entry whose threshold rounds to 0 (to the maximum) carries its alias' (its own)
+// code in both fields, so quantisation never produces an outcome the model gives no mass.
+void build_joint_row(const double *cum, int n_bq, const double *phred_p, int K, int code9, uint32_t *out) {
+  const int tb = code9 ? 14 : 16, cb = code9 ? 9 : 8;
+  const std::vector<Outcome> oc = row_outcomes(cum, n_bq, phred_p, code9 ? 7 : 6);
+  double tot = 0.0;
+  for (const Outcome &o : oc) tot += o.mass;
+  std::vector<double> q((size_t)K, 0.0);
+  for (size_t i = 0; i < oc.size(); i++) q[i] = oc[i].mass / tot;
+  std::vector<double> prob; std::vector<int> alias;
+  vose_raw(q, K, prob, alias);
+  for (int i = 0; i < K; i++) {
+    const double pr = prob[i] < 0.0 ? 0.0 : (prob[i] > 1.0 ? 1.0 : prob[i]);
+    uint32_t t = (uint32_t)std::floor(pr * (double)(1u << tb) + 0.5);
+    if (t > (1u << tb) - 1u) t = (1u << tb) - 1u;
+    uint32_t a = (size_t)alias[i] < oc.size() ? oc[(size_t)alias[i]].code : oc[0].code;
+    uint32_t sf = (size_t)i < oc.size() ? oc[(size_t)i].code : a;
+    if (t == 0) sf = a;
+    if (t == (1u << tb) - 1u) a = sf;
+    out[i] = (t << (32 - tb)) | (sf << cb) | a;
+  }
 }
 
 struct Timer {   // MG_TIMING=1: host-side section timings on stderr
@@ -290,28 +322,33 @@ int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double 
   CU(cudaMemcpyAsync(ctx->m_tlen.p, cum_tlen, sizeof(double) * n_tlen, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->m_bq.p, cum_bq_mat, sizeof(double) * (size_t)n_mates * n_cycles * n_bq, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->m_phred.p, phred_p, sizeof(double) * 100, cudaMemcpyHostToDevice, ctx->stream));
-  // production-mode tables: alias rows per (mate, cycle) and integer error thresholds per BQ.
-  // Rows are built twice: 64 entries (one 256-byte line pair per warp-wide lookup; exact while all
-  // mass sits on BQ < 64, true for every cycle < max_rlen of the shipped models) and 128 entries.
-  int n64 = n_cycles;
-  for (int m = 0; m < n_mates; m++)
-    for (int c = 0; c < n_cycles; c++) {
-      const double *row = cum_bq_mat + ((size_t)m * n_cycles + c) * n_bq;
-      const double at63 = n_bq > 63 ? row[63] : (n_bq ? row[n_bq - 1] : 0.0);   // mass on outcomes <= 63
-      if (n_bq == 0 || at63 < 1.0) { if (c < n64) n64 = c; break; }
-    }
-  ctx->h_thr.assign((size_t)n_mates * n_cycles, 0u);
+  // production-mode tables: one joint (quality, substitution) alias row per (mate, cycle).  Built
+  // twice: for the emit kernel over the cycles a read of this model has (rlen), and for the standalone
+  // corrupt kernel over every cycle (reads of any length up to n_cycles; the rows beyond the model's
+  // max_rlen are all-zero, i.e. quality 93, which needs the 9-bit codes).
   for (int t = 0; t < 2; t++) {
-    const int K = 64 << t;
-    ctx->h_alias[t].assign((size_t)n_mates * n_cycles * 2 * K, 0u);
-    for (size_t r = 0; r < (size_t)n_mates * n_cycles; r++)
-      if (t == 1 || (int)(r % n_cycles) < n64)
-        ctx->h_thr[r] = build_quality_rows(cum_bq_mat + r * n_bq, n_bq, K, phred_p, ctx->h_alias[t].data() + r * 2 * K);
+    const int rows = t == 0 ? std::min(rlen, n_cycles) : n_cycles;
+    int code9 = 0; size_t longest = 1;
+    for (int m = 0; m < n_mates; m++)
+      for (int c = 0; c < rows; c++) {
+        const double *row = cum_bq_mat + ((size_t)m * n_cycles + c) * n_bq;
+        const std::vector<double> qm = ss_left_probs(row, n_bq, 94, 93);
+        for (int b = 64; b < 94; b++) if (qm[b] > 0.0) code9 = 1;
+        longest = std::max(longest, row_outcomes(row, n_bq, phred_p, 7).size());
+      }
+    int ks = 5;
+    while ((size_t)1 << ks < longest) ks++;
+    const int K = 1 << ks;
+    ctx->a_kshift[t] = ks; ctx->a_code9[t] = code9; ctx->a_rows[t] = rows;
+    ctx->h_alias[t].assign((size_t)n_mates * n_cycles * K, 0u);
+    for (int m = 0; m < n_mates; m++)
+      for (int c = 0; c < rows; c++) {
+        const size_t r = (size_t)m * n_cycles + c;
+        build_joint_row(cum_bq_mat + r * n_bq, n_bq, phred_p, K, code9, ctx->h_alias[t].data() + r * K);
+      }
     CU(ctx->m_alias[t].need(4 * ctx->h_alias[t].size()));
     CU(cudaMemcpyAsync(ctx->m_alias[t].p, ctx->h_alias[t].data(), 4 * ctx->h_alias[t].size(), cudaMemcpyHostToDevice, ctx->stream));
   }
-  CU(ctx->m_err.need(4 * ctx->h_thr.size()));
-  CU(cudaMemcpyAsync(ctx->m_err.p, ctx->h_thr.data(), 4 * ctx->h_thr.size(), cudaMemcpyHostToDevice, ctx->stream));
   ctx->has_tlen_alias = (n_tlen + 1 <= MG_TLEN_K);
   if (ctx->has_tlen_alias) {
     std::vector<uint32_t> ta(MG_TLEN_K);
@@ -320,20 +357,21 @@ int mg_model_load(mg_ctx *ctx, const double *cum_tlen, int n_tlen, const double 
     CU(cudaMemcpy(ctx->m_tlen_alias.p, ta.data(), 4 * MG_TLEN_K, cudaMemcpyHostToDevice));
   }
   CU(cudaStreamSynchronize(ctx->stream));
-  ctx->n_tlen = n_tlen; ctx->n_mates = n_mates; ctx->n_cycles = n_cycles; ctx->n_bq = n_bq; ctx->rlen = rlen; ctx->n64 = n64;
+  ctx->n_tlen = n_tlen; ctx->n_mates = n_mates; ctx->n_cycles = n_cycles; ctx->n_bq = n_bq; ctx->rlen = rlen;
   return MG_OK;
 }
 
-int mg_model_tables(mg_ctx *ctx, int32_t kshift, uint32_t *alias_out, int64_t alias_cap, int32_t *n64, uint32_t *thr_out) {
+int mg_model_tables(mg_ctx *ctx, int32_t which, uint32_t *alias_out, int64_t alias_cap, int32_t *kshift, int32_t *code9, int32_t *n_rows) {
   if (!ctx || ctx->rlen == 0) return fail(ctx, MG_EINVAL, "no read model loaded");
-  if (kshift != 6 && kshift != 7) return fail(ctx, MG_EINVAL, "kshift must be 6 or 7");
-  const std::vector<uint32_t> &h = ctx->h_alias[kshift - 6];
-  if (n64) *n64 = ctx->n64;
+  if (which != 0 && which != 1) return fail(ctx, MG_EINVAL, "which must be 0 (emit kernel) or 1 (corrupt kernel)");
+  const std::vector<uint32_t> &h = ctx->h_alias[which];
+  if (kshift) *kshift = ctx->a_kshift[which];
+  if (code9) *code9 = ctx->a_code9[which];
+  if (n_rows) *n_rows = ctx->a_rows[which];
   if (alias_out) {
     if (alias_cap < (int64_t)h.size()) return fail(ctx, MG_ECAP, "alias table needs %lld entries", (long long)h.size());
     memcpy(alias_out, h.data(), 4 * h.size());
   }
-  if (thr_out) memcpy(thr_out, ctx->h_thr.data(), 4 * ctx->h_thr.size());
   return MG_OK;
 }
 
@@ -671,18 +709,18 @@ static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint
   const int pl = (int)strlen(d->qname_prefix), ml = (int)strlen(d->qname_mid);
   const int L = ctx->rlen;
 
-  // qname constants
-  DevBuf &strb = ctx->s_qn;
-  CU(strb.need((size_t)pl + ml + 32));
-  CU(cudaMemcpyAsync(strb.p, d->qname_prefix, pl, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(strb.as<uint8_t>() + pl, d->qname_mid, ml, cudaMemcpyHostToDevice, ctx->stream));
-  P.prefix = strb.as<uint8_t>(); P.prefix_len = pl; P.mid = strb.as<uint8_t>() + pl; P.mid_len = ml;
-
+  // qname constants, tokenised on the host (mg_qn_const): they travel in the kernel parameters
   if (pl > MG_QN_MAX || ml > MG_QN_MAX) return fail(ctx, MG_EVALUE, "sample / chromosome name too long for the qname buffers (%d)", MG_QN_MAX);
+  mg_qn_const(P.qn, reinterpret_cast<const uint8_t *>(d->qname_prefix), pl, reinterpret_cast<const uint8_t *>(d->qname_mid), ml, L);
+  P.qn_len = pl + ml;
+  {
+    static const bool lsu = getenv("MG_COPYOUT_LSU") != nullptr;     // experiments: copy-out with plain loads / stores
+    P.bulk = lsu ? 0 : 1;
+  }
   P.corrupt = d->corrupt;
-  P.cor.kshift = (L <= ctx->n64) ? 6 : 7;
-  P.cor.alias = ctx->m_alias[P.cor.kshift - 6].as<uint32_t>(); P.cor.thr = ctx->m_err.as<uint32_t>();
-  P.cor.n_cycles = ctx->n_cycles; P.cor.n_mates = ctx->n_mates; P.cor.thr_s = 0; P.cor.lp = 0;
+  P.cor.kshift = ctx->a_kshift[0]; P.cor.code9 = ctx->a_code9[0];
+  P.cor.alias = ctx->m_alias[0].as<uint32_t>();
+  P.cor.n_cycles = ctx->n_cycles; P.cor.n_mates = ctx->n_mates;
   P.cor.k0 = d->corrupt_seed; P.cor.k1 = d->unit_seed ^ 0x636f7231u;
   P.L_nd = mg_ndigits32((uint32_t)L);
 
@@ -692,7 +730,8 @@ static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint
   if (stage > 48 * 1024) stage = 48 * 1024;
   P.stage_cap = stage & ~15;
   int smem = 0;
-  const int grid = mg_unit_grid(L, d->corrupt ? P.cor.kshift : 0, P.stage_cap, &smem);
+  const int grid = mg_unit_grid(L, d->corrupt ? 1 + P.cor.code9 : 0, P.stage_cap, &smem);
+  if (grid <= 0) return fail(ctx, MG_EVALUE, "the emit kernel's staging area (%d bytes for reads of %d bases) exceeds the shared memory of this device", smem, L);
 
   // scan state: [totals 4 x u64][tile counter (16 B)][descA][descB]
   const size_t state_bytes = 48 + 16 * (size_t)std::max(P.n_tiles, 1);
@@ -822,9 +861,9 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
   P.n_rec = n_rec; P.n_files = nf;
   P.cum_bq = ctx->m_bq.as<double>(); P.n_cycles = ctx->n_cycles; P.n_bq = ctx->n_bq; P.phred = ctx->m_phred.as<double>();
   P.mode = mode;
-  P.cor.kshift = 7;   // any read length up to n_cycles
-  P.cor.alias = ctx->m_alias[1].as<uint32_t>(); P.cor.thr = ctx->m_err.as<uint32_t>();
-  P.cor.n_cycles = ctx->n_cycles; P.cor.n_mates = ctx->n_mates; P.cor.thr_s = 0; P.cor.lp = 0;
+  P.cor.kshift = ctx->a_kshift[1]; P.cor.code9 = ctx->a_code9[1];   // the table over every cycle: any read length up to n_cycles
+  P.cor.alias = ctx->m_alias[1].as<uint32_t>();
+  P.cor.n_cycles = ctx->n_cycles; P.cor.n_mates = ctx->n_mates;
   P.cor.k0 = seed; P.cor.k1 = 0x636f7232u;
   if (out_len1) *out_len1 = 0;
   if (out_len2) *out_len2 = 0;

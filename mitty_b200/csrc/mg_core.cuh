@@ -100,6 +100,17 @@ MG_HD uint32_t mg_prmt(uint32_t a, uint32_t sel) {  // byte i of result = byte (
 #endif
 }
 
+MG_HD uint32_t mg_prmt2(uint32_t a, uint32_t b, uint32_t sel) {  // byte i of result = byte (nibble i of sel & 7) of b:a
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, b, sel);
+#else
+  const uint64_t ab = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= (uint32_t)((ab >> (8 * ((sel >> (4 * i)) & 7))) & 0xFFu) << (8 * i);
+  return r;
+#endif
+}
+
 // 16 consecutive 2-bit codes starting at base index s (s >= 0) of a packed sequence
 // (16 bases per 32-bit word, base i in bits [2i, 2i+1] of word i/16).
 template <class P>
@@ -242,8 +253,9 @@ MG_NI uint64_t mg_digit_sum(uint64_t m) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Writers.  CountWriter sizes a record, WordStream writes it (any byte alignment) with aligned
-// 32-bit stores in the interior and byte stores only for the first / last partial word.
+// Writers.  CountWriter sizes a record; MgStream writes it at any byte alignment with aligned
+// 32-bit stores: whole words (sequence, qualities) cost one funnel shift + one store, tokens of
+// 0..8 bytes (the qname's numbers and separators) are appended without a branch.
 
 struct MgCountWriter {
   static constexpr bool is_bytes = false;
@@ -262,6 +274,7 @@ struct MgGenericSpace {
   static MG_HD void st8(ptr p, uint8_t v) { *p = v; }
   static MG_HD void st32(ptr p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
   static MG_HD uint32_t ld32(ptr p) { return *reinterpret_cast<const uint32_t *>(p); }
+  static MG_HD uint32_t ld8(ptr p) { return *p; }
   static MG_HD uint32_t low2(ptr p) { return (uint32_t)((uintptr_t)p & 3); }
 };
 #if defined(__CUDACC__)
@@ -277,40 +290,51 @@ struct MgSharedSpace {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(p));
     return v;
   }
+  static __device__ __forceinline__ uint32_t ld8(ptr p) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p));
+    return v;
+  }
   static __device__ __forceinline__ uint32_t low2(ptr p) { return p & 3u; }
 };
 #endif
-
-// plain byte stores: used for the qname, whose per-lane byte counts differ (a shared word
-// stream would flush on a different iteration in every lane and serialise the warp)
-template <class SP>
-struct MgByteWriter {
-  static constexpr bool is_bytes = true;
-  typedef SP space;
-  typename SP::ptr p;
-  MG_HD void put(uint8_t c) { SP::st8(p, c); p += 1; }
-};
 
 template <class SP> MG_NI void mg_store_tail(typename SP::ptr b, uint32_t carry, uint32_t nb) {
   for (uint32_t i = 0; i < nb; i++) SP::st8(b + i, (uint8_t)(carry >> (8 * i)));
 }
 
+// A token: n <= 8 bytes, first byte in the lowest byte of lo; the bytes beyond n are zero.
+struct MgTok { uint32_t lo, hi, n; };
+
 template <class SP>
-struct MgWordStream {
+struct MgStream {
   static constexpr bool is_bytes = false;
   typename SP::ptr wp;   // next aligned word
   uint32_t prev;         // the pending bytes are the TOP sh / 8 bytes of prev
   uint32_t sh;           // 8 * pending byte count: 0, 8, 16 or 24
+  uint32_t skip;         // generic space only: low bytes of the first word that belong to the previous record
 
+  // Start of a record.  The bytes before dst inside its word are the tail of the PREVIOUS record
+  // (another thread's).  In the shared-memory stage the first word is stored whole and the previous
+  // record's tail bytes are written afterwards (every stream ends with byte stores, and the kernel
+  // puts a __syncwarp between the two); anywhere else the first word is written byte by byte.
+  MG_HD void begin(typename SP::ptr dst) {
+    const uint32_t a = SP::low2(dst);
+    wp = dst - a; sh = 8 * a; prev = 0u; skip = a;
+  }
   // The bytes before dst inside its word were written earlier BY THIS THREAD (the tail of its own
   // qname / separator): they are read back and carried, so every flush is a plain word store.
   MG_HD void begin_rmw(typename SP::ptr dst) {
     const uint32_t a = SP::low2(dst);
-    wp = dst - a;
-    sh = 8 * a;
+    wp = dst - a; sh = 8 * a; skip = 0;
     prev = a ? (SP::ld32(wp) << (32 - sh)) : 0u;
   }
-  MG_HD void flush_word(uint32_t w) { SP::st32(wp, w); wp += 4; }
+  MG_HD void flush_word(uint32_t w) {
+    if constexpr (SP::is_generic) {
+      if (skip) { for (uint32_t i = skip; i < 4; i++) SP::st8(wp + i, (uint8_t)(w >> (8 * i))); skip = 0; wp += 4; return; }
+    }
+    SP::st32(wp, w); wp += 4;
+  }
   MG_HD void put(uint8_t c) {
     prev = (prev >> 8) | ((uint32_t)c << 24);
     sh += 8;
@@ -320,43 +344,94 @@ struct MgWordStream {
     flush_word(mg_funnel_l(prev, w, sh));    // (w << sh) | (prev >> (32 - sh)); sh == 0 gives w
     prev = w;
   }
+  // 0..8 bytes without a branch: the (at most two) completed words are stored under predicates
+  MG_HD void append(MgTok t) {
+    const uint32_t pend = mg_funnel_l(prev, 0u, sh);            // pending bytes in the low positions (sh == 0: none)
+    const uint32_t w0 = pend | (t.lo << sh);
+    const uint32_t w1 = mg_funnel_l(t.lo, t.hi, sh);
+    const uint32_t w2 = mg_funnel_l(t.hi, 0u, sh);
+    const uint32_t tb = sh + 8u * t.n;                          // total pending bits, < 96
+    if constexpr (SP::is_generic) {
+      if (tb >= 32u) flush_word(w0);
+      if (tb >= 64u) flush_word(w1);
+    } else {
+      if (tb >= 32u) SP::st32(wp, w0);
+      if (tb >= 64u) SP::st32(wp + 4, w1);
+      wp += (tb >> 3) & ~3u;
+    }
+    const uint32_t keep = tb >= 64u ? w2 : (tb >= 32u ? w1 : w0);
+    sh = tb & 31u;
+    prev = keep << ((32u - sh) & 31u);                          // back to the top of prev (sh == 0: nothing is pending)
+  }
   // the last partial word is shared with the NEXT record (another thread): byte stores
-  MG_HD void end() { if (sh) mg_store_tail<SP>(wp, prev >> (32 - sh), sh >> 3); sh = 0; }
+  MG_HD void end() {
+    if (sh) {
+      const uint32_t nb = sh >> 3, carry = prev >> (32 - sh);
+      if constexpr (SP::is_generic) { const uint32_t k = skip; skip = 0; for (uint32_t i = k; i < nb; i++) SP::st8(wp + i, (uint8_t)(carry >> (8 * i))); }
+      else mg_store_tail<SP>(wp, carry, nb);
+    }
+    sh = 0;
+  }
+  // pending bytes stored as one word whose upper bytes are zero: only where those upper bytes are the
+  // writer's own, still unwritten, territory (the sequence line after the qname)
+  MG_HD void flush_own() { if (sh) flush_word(prev >> (32 - sh)); sh = 0; }
 };
 
-// decimal digits of v at p (byte stores), returns the advanced pointer
-template <class SP> MG_NI typename SP::ptr mg_put_u32_p(typename SP::ptr p, uint32_t v) {
+// ---- decimal text without loops or branches -------------------------------------------------------
+
+MG_HD uint32_t mg_dec4(uint32_t x) {   // x < 10000 -> its 4 digits as ASCII, first digit in the lowest byte
+  const uint32_t c = (x * 5243u) >> 19;                     // x / 100
+  const uint32_t d = x - c * 100u;
+  const uint32_t p = c | (d << 16);                         // two values < 100 in the two halves
+  const uint32_t t = ((p * 103u) >> 10) & 0x000F000Fu;      // their tens
+  const uint32_t o = p - t * 10u;                           // their ones
+  return (t | (o << 8)) + 0x30303030u;
+}
+
+// pre (npre <= 3 bytes) followed by the decimal digits of v: two tokens, A = pre + the digits above
+// 10^8 (at most 2), B = the other (at most 8) digits
+MG_HD void mg_tok_num(uint32_t v, uint32_t pre, uint32_t npre, MgTok &A, MgTok &B) {
+  const uint32_t top = v / 100000000u, low = v - top * 100000000u;
+  const uint32_t a = low / 10000u, b = low - a * 10000u;
+  uint32_t lo = mg_dec4(a), hi = mg_dec4(b);
+  // leading zeros of the 8-digit text (bytes equal to '0' before the first other byte)
+  const uint32_t xl = lo ^ 0x30303030u, xh = hi ^ 0x30303030u;
+  uint32_t lz;
+#if defined(__CUDA_ARCH__)
+  lz = xl ? ((uint32_t)__ffs((int)xl) - 1u) >> 3 : (xh ? 4u + (((uint32_t)__ffs((int)xh) - 1u) >> 3) : 7u);
+#else
+  lz = xl ? ((uint32_t)__builtin_ctz(xl)) >> 3 : (xh ? 4u + (((uint32_t)__builtin_ctz(xh)) >> 3) : 7u);
+#endif
+  if (top) lz = 0u;                                          // the high part is printed: keep all eight
+  // drop lz bytes from the front of (lo, hi)
+  const bool big = lz >= 4u;
+  const uint32_t l1 = big ? hi : lo, h1 = big ? 0u : hi, s2 = 8u * (lz & 3u);
+  B.lo = mg_funnel_r(l1, h1, s2); B.hi = h1 >> s2; B.n = 8u - lz;
+  // the high part: 0, 1 or 2 digits after the prefix
+  const uint32_t tt = (top * 103u) >> 10, to = top - tt * 10u;
+  const uint32_t nt = top >= 10u ? 2u : (top ? 1u : 0u);
+  const uint32_t dig = top >= 10u ? ((tt + 48u) | ((to + 48u) << 8)) : (top ? to + 48u : 0u);
+  // pre occupies npre <= 3 bytes, dig up to 2: five bytes over (lo, hi)
+  const uint32_t ps = 8u * npre;
+  A.lo = pre | (dig << ps); A.hi = mg_funnel_l(dig, 0u, ps); A.n = npre + nt;
+}
+
+template <class SP>
+MG_HD void mg_put_num(MgStream<SP> &w, uint32_t v, uint32_t pre, uint32_t npre) {
+  MgTok A, B;
+  mg_tok_num(v, pre, npre, A, B);
+  w.append(A); w.append(B);
+}
+
+MG_HD MgTok mg_tok(uint32_t lo, uint32_t hi, uint32_t n) { MgTok t; t.lo = lo; t.hi = hi; t.n = n; return t; }
+
+// decimal digits through a byte-at-a-time writer (the sizing cross-check of the emulation tests)
+template <class W>
+MG_HD void mg_put_u32(W &w, uint32_t v) {
   uint64_t acc = 0;
   int n = 0;
   do { uint32_t q = v / 10u; acc = (acc << 4) | (v - q * 10u); v = q; n++; } while (v);
-  for (; n; n--) { SP::st8(p, (uint8_t)('0' + ((uint32_t)acc & 15u))); p += 1; acc >>= 4; }
-  return p;
-}
-
-template <class W>
-MG_HD void mg_put_u32(W &w, uint32_t v) {
-  if constexpr (W::is_bytes) { w.p = mg_put_u32_p<typename W::space>(w.p, v); return; }
-  else {
-    // digits are stacked as nibbles in a register pair (no local-memory array); /10 is a multiply
-    uint64_t acc = 0;
-    int n = 0;
-    do { uint32_t q = v / 10u; acc = (acc << 4) | (v - q * 10u); v = q; n++; } while (v);
-    for (; n; n--) { w.put((uint8_t)('0' + ((uint32_t)acc & 15u))); acc >>= 4; }
-  }
-}
-
-template <class W>
-MG_HD void mg_put_uint(W &w, uint64_t v) {   // v < 10^16
-  if (v <= 0xFFFFFFFFull) { mg_put_u32(w, (uint32_t)v); return; }
-  uint64_t acc = 0;
-  int n = 0;
-  do { acc = (acc << 4) | (v % 10); v /= 10; n++; } while (v);
-  for (; n; n--) { w.put((uint8_t)('0' + (acc & 15))); acc >>= 4; }
-}
-
-template <class W>
-MG_HD void mg_put_bytes(W &w, const uint8_t *s, int n) {
-  for (int i = 0; i < n; i++) w.put(s[i]);
+  for (; n; n--) { w.put((uint8_t)('0' + ((uint32_t)acc & 15u))); acc >>= 4; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -462,17 +537,18 @@ MG_HD void mg_fmt_read(W &w, NP nodes, int n0, int n1, uint32_t x, int L, int st
   }
 }
 
-// Whole qname line without the trailing newline:
+// Whole qname line:
 //   '@' stub ':' cnt '|' chrom '|' cpy  + per read in FILE order '|strand|pos|rlen|cigar|vlist'
 // prefix = "@<sample>:<worker>:<ps>:"   mid = "|<chrom>|<cpy>"
 struct MgReadRef { uint32_t x; int n0, n1, strand; };
 
+// byte-at-a-time restatement (sizing cross-check of the emulation tests; never on a kernel's path)
 template <class W, class NP>
 MG_HD void mg_fmt_qname(W &w, const uint8_t *prefix, int prefix_len, uint64_t cnt, bool with_cnt,
                         const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
-  mg_put_bytes(w, prefix, prefix_len);
-  if (with_cnt) { if (cnt <= 0xFFFFFFFFull) mg_put_u32(w, (uint32_t)cnt); else mg_put_uint(w, cnt); }
-  mg_put_bytes(w, mid, mid_len);
+  for (int i = 0; i < prefix_len; i++) w.put(prefix[i]);
+  if (with_cnt) mg_put_u32(w, (uint32_t)cnt);
+  for (int i = 0; i < mid_len; i++) w.put(mid[i]);
   MG_NOUNROLL
   for (int r = 0; r < 2; r++) {
     const MgReadRef R = r ? second : first;
@@ -480,14 +556,97 @@ MG_HD void mg_fmt_qname(W &w, const uint8_t *prefix, int prefix_len, uint64_t cn
   }
 }
 
-// qname + newline as bytes at dst (one shared copy per kernel), returns the advanced pointer
+// Per-CTA constants of the qname: the strings every record repeats, ready as tokens (the emit
+// kernel keeps one copy in shared memory).
+//   pre[]      = "@<sample>:<worker>:<ps>:"   mid[] = "|<chrom>|<cpy>"     (eight bytes per token)
+//   tail[0..1] = "|<L>|<L>=|"  (what follows POS when the read lies inside one '=' node: rlen, CIGAR, empty v_list)
+//   rl         = "|<L>|"       (what follows POS otherwise)
+#define MG_QN_TOKS 24            // 8 * 24 = MG_QN_MAX bytes
+struct MgQnConst {
+  MgTok pre[MG_QN_TOKS], mid[MG_QN_TOKS];
+  int n_pre, n_mid;
+  MgTok tail[2], rl;
+  uint32_t Lnd;   // number of digits of L, or 0: "L is absurdly long, write it digit by digit"
+};
+
+MG_HD MgTok mg_tok_bytes(const uint8_t *t, int from, int cnt) {
+  MgTok k; k.lo = 0; k.hi = 0; k.n = (uint32_t)(cnt < 0 ? 0 : (cnt > 8 ? 8 : cnt));
+  for (uint32_t i = 0; i < k.n; i++) { if (i < 4) k.lo |= (uint32_t)t[from + i] << (8 * i); else k.hi |= (uint32_t)t[from + i] << (8 * (i - 4)); }
+  return k;
+}
+
+MG_HD void mg_qn_const(MgQnConst &Q, const uint8_t *prefix, int prefix_len, const uint8_t *mid, int mid_len, int L) {
+  Q.n_pre = (prefix_len + 7) / 8; Q.n_mid = (mid_len + 7) / 8;
+  for (int i = 0; i < Q.n_pre; i++) Q.pre[i] = mg_tok_bytes(prefix, 8 * i, prefix_len - 8 * i);
+  for (int i = 0; i < Q.n_mid; i++) Q.mid[i] = mg_tok_bytes(mid, 8 * i, mid_len - 8 * i);
+  // "|<L>|<L>=|", bytewise: once per CTA, not per record
+  uint8_t d[12], t[28]; int nd = 0, n = 0;
+  uint32_t v = (uint32_t)L;
+  do { d[nd++] = (uint8_t)('0' + v % 10u); v /= 10u; } while (v);
+  t[n++] = '|';
+  for (int i = nd - 1; i >= 0; i--) t[n++] = d[i];
+  t[n++] = '|';
+  const int nrl = n;
+  for (int i = nd - 1; i >= 0; i--) t[n++] = d[i];
+  t[n++] = '='; t[n++] = '|';
+  const bool ok = n <= 16;                           // up to 6 digits
+  Q.Lnd = ok ? (uint32_t)nd : 0u;
+  Q.rl = mg_tok_bytes(t, 0, ok ? nrl : 0);
+  Q.tail[0] = mg_tok_bytes(t, 0, ok ? n : 0);
+  Q.tail[1] = mg_tok_bytes(t, 8, ok ? n - 8 : 0);
+}
+
+// '|strand|pos|rlen|cigar|vlist' of one read into the stream (fastq_lines, readgenerate.py:224-225,
+// over generate_read, rpc.py:144-158).  x = read start relative to p_min.
 template <class SP, class NP>
-MG_NI typename SP::ptr mg_qname_bytes(typename SP::ptr dst, const uint8_t *prefix, int prefix_len, uint64_t cnt,
-                                      const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
-  MgByteWriter<SP> bw; bw.p = dst;
-  mg_fmt_qname(bw, prefix, prefix_len, cnt, true, mid, mid_len, nodes, first, second, L);
-  bw.put('\n');
-  return bw.p;
+MG_HD void mg_put_read(MgStream<SP> &w, const MgQnConst &Q, NP nodes, MgReadRef R, int L) {
+  const MgNode f = nodes[R.n0];
+  const bool single = (R.n0 == R.n1);
+  mg_put_num(w, (uint32_t)mg_read_pos(f, single, R.x), (uint32_t)'|' | ((uint32_t)('0' + R.strand) << 8) | ((uint32_t)'|' << 16), 3u);
+  if (single && f.op == '=' && Q.Lnd) {                                       // the common case: "<L>=" + empty v_list
+    w.append(Q.tail[0]); w.append(Q.tail[1]);
+    return;
+  }
+  if (Q.Lnd) w.append(Q.rl); else mg_put_num(w, (uint32_t)L, '|', 1u), w.append(mg_tok('|', 0, 1));
+  if (single && f.op == '=') {                                               // (absurd L only)
+    mg_put_num(w, (uint32_t)L, 0u, 0u); w.append(mg_tok((uint32_t)'=' | ((uint32_t)'|' << 8), 0, 2));
+    return;
+  }
+  if (single && f.op == 'I') {                                               // rpc.py:154  ">p:<L>I" and "|<oplen>"
+    mg_put_num(w, (uint32_t)((int64_t)R.x - (int64_t)f.key), '>', 1u);
+    mg_put_num(w, (uint32_t)L, ':', 1u);
+    mg_put_num(w, (uint32_t)f.oplen, (uint32_t)'I' | ((uint32_t)'|' << 8), 2u);
+    return;
+  }
+  uint32_t pre = 0, npre = 0;
+  for (int k = R.n0; k <= R.n1; k++) {                                       // rpc.py:145: <len><op> per node
+    const MgNode n = nodes[k];
+    mg_put_num(w, (uint32_t)mg_cigar_len(n, R.x, L), pre, npre);
+    pre = n.op; npre = 1;
+  }
+  pre |= (uint32_t)'|' << 8; npre = 2;                                       // last op, then the field separator
+  bool firstv = true;
+  for (int k = R.n0; k <= R.n1; k++) {                                       // rpc.py:144: v_list
+    const MgNode n = nodes[k];
+    if (n.op == '=') continue;
+    if (!firstv) { pre = ','; npre = 1; }
+    firstv = false;
+    if (n.op == 'D') { pre |= (uint32_t)'-' << (8 * npre); npre++; }
+    mg_put_num(w, n.op == 'X' ? 0u : (uint32_t)n.oplen, pre, npre);
+    npre = 0; pre = 0;
+  }
+  if (npre) w.append(mg_tok(pre, 0, npre));                                  // no variant at all (cannot happen here: the read spans > 1 node)
+}
+
+// qname line + '\n' through the stream (which then goes on with the sequence line)
+template <class SP, class NP>
+MG_HD void mg_put_qname(MgStream<SP> &w, const MgQnConst &Q, uint32_t cnt, NP nodes, MgReadRef first, MgReadRef second, int L) {
+  for (int i = 0; i < Q.n_pre; i++) w.append(Q.pre[i]);
+  mg_put_num(w, cnt, 0u, 0u);
+  for (int i = 0; i < Q.n_mid; i++) w.append(Q.mid[i]);
+  MG_NOUNROLL
+  for (int r = 0; r < 2; r++) mg_put_read(w, Q, nodes, r ? second : first, L);
+  w.append(mg_tok('\n', 0, 1));
 }
 
 // Register window over a read: the 2-bit words covering it are fetched up front (independent
@@ -508,7 +667,15 @@ MG_HD void mg_win_load(MgWin<MAXW> &W, HP hap, uint32_t x, int L, int strand) {
   for (int i = 0; i < MAXW; i++) {
     uint32_t v = 0;
     if (i < nw) v = hap[strand ? w_last - i : w_first + i];
-    W.w[i] = strand ? mg_revcomp16(v) : v;
+    W.w[i] = v;                 // raw: the reverse strand is turned around by mg_win_prep, when the words are first USED
+  }
+}
+
+template <int MAXW>
+MG_HD void mg_win_prep(MgWin<MAXW> &W, int strand) {
+  if (strand) {
+    MG_UNROLL
+    for (int i = 0; i < MAXW; i++) W.w[i] = mg_revcomp16(W.w[i]);
   }
 }
 
@@ -545,13 +712,16 @@ MG_HD int mg_exc_first(EP exc, int n_exc, uint32_t x) {
   return lo;
 }
 
-// number of 'N' in the read (seq.count('N'), readgenerate.py:204)
+// number of 'N' in the read (seq.count('N'), readgenerate.py:204); touch = the read overlaps an
+// exception run of any kind (its bases need patching after the word-stream emission)
 template <class EP>
-MG_NI int mg_count_N(EP exc, int n_exc, uint32_t x, int L) {
+MG_NI int mg_count_N(EP exc, int n_exc, uint32_t x, int L, bool &touch) {
   int cnt = 0;
+  touch = false;
   for (int k = mg_exc_first(exc, n_exc, x); k < n_exc; k++) {
     MgExc e = exc[k];
     if ((uint64_t)e.start >= (uint64_t)x + L) break;
+    touch = true;
     if (e.byte != 'N') continue;
     uint64_t a = e.start > x ? e.start : x;
     uint64_t b = (uint64_t)e.start + e.len < (uint64_t)x + L ? (uint64_t)e.start + e.len : (uint64_t)x + L;
@@ -623,6 +793,9 @@ struct MgSeqSrc {
     hap = hap_; x = x_; L = L_; strand = strand_;
     if constexpr (MAXW > 0) mg_win_load(W, hap, x, L, strand);
   }
+  // Between load() and prep() nothing waits for the loads: the kernel issues load() for the next file
+  // before the copy-out of the current one, and prep() runs when the emission starts.
+  MG_HD void prep() { if constexpr (MAXW > 0) mg_win_prep(W, strand); }
   // streaming source only (MAXW == 0)
   MG_HD uint32_t codes(int c) const {
     if (strand == 0) return mg_codes16(hap, (int64_t)x + 16 * c);
@@ -672,247 +845,220 @@ MG_HD void mg_emit_seq_src(WR &w, MgSeqSrc<MAXW, HP> &S) {
 
 // One FASTQ record (fastq_lines, readgenerate.py:227-230):  qname \n SEQ \n+\n ~~~~ \n
 // S = the read that goes into this file (already loaded); first/second give the qname's file order.
-// qlen = length of the qname line without its newline (known from the sizing pass).
-template <class SP, int MAXW, class NP, class HP, class EP>
-MG_HD void mg_emit_record(typename SP::ptr dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
-                          const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second,
-                          MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc) {
+// The stream is left OPEN: the caller ends it (tail bytes) after every thread of the warp has stored
+// its first word -- see MgStream::begin -- and then patches the exception bases (mg_patch_exc).
+template <class SP, int MAXW, class NP, class HP>
+MG_HD void mg_emit_record(MgStream<SP> &ws, typename SP::ptr dst, const MgQnConst &Q, uint32_t cnt, NP nodes, MgReadRef first,
+                          MgReadRef second, MgSeqSrc<MAXW, HP> &S) {
   const int L = S.L;
-  MgWordStream<SP> ws;
-  ws.begin_rmw(mg_qname_bytes<SP>(dst, prefix, prefix_len, cnt, mid, mid_len, nodes, first, second, L));
+  ws.begin(dst);
+  mg_put_qname(ws, Q, cnt, nodes, first, second, L);
+  S.prep();
   mg_emit_seq_src(ws, S);
-  ws.put('\n'); ws.put('+'); ws.put('\n');
+  ws.append(mg_tok((uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16), 0, 3));
   mg_emit_fill(ws, '~', L);
-  ws.put('\n');
-  ws.end();
-  if (n_exc) mg_patch_exc<SP>(dst + (qlen + 1), exc, n_exc, S.hap, S.x, L, S.strand);
+  ws.append(mg_tok('\n', 0, 1));
 }
 
 // The other file's record has the same qname, the same offsets and (for perfect reads) the same
 // quality line: only the L sequence bytes are rewritten in place.
 template <class SP, int MAXW, class HP, class EP>
 MG_HD void mg_rewrite_seq(typename SP::ptr seq_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc) {
-  MgWordStream<SP> ws;
+  MgStream<SP> ws;
   ws.begin_rmw(seq_dst);
+  S.prep();
   mg_emit_seq_src(ws, S);
   ws.end();
   if (n_exc) mg_patch_exc<SP>(seq_dst, exc, n_exc, S.hap, S.x, S.L, S.strand);
 }
 
-// qname line + the three separator newlines of a record whose SEQ / QUAL lines are written by
-// mg_emit_seq_corrupt (fused corruption).
+// Fused corruption: the qname line first (its last partial word is stored whole: the bytes above it
+// are this record's own sequence line, still to be written) ...
 template <class SP, class NP>
-MG_HD void mg_emit_frame(typename SP::ptr dst, uint32_t qlen, const uint8_t *prefix, int prefix_len, uint64_t cnt,
-                         const uint8_t *mid, int mid_len, NP nodes, MgReadRef first, MgReadRef second, int L) {
-  mg_qname_bytes<SP>(dst, prefix, prefix_len, cnt, mid, mid_len, nodes, first, second, L);
+MG_HD void mg_emit_frame_qname(typename SP::ptr dst, const MgQnConst &Q, uint32_t cnt, NP nodes, MgReadRef first, MgReadRef second, int L) {
+  MgStream<SP> ws;
+  ws.begin(dst);
+  mg_put_qname(ws, Q, cnt, nodes, first, second, L);
+  ws.flush_own();
+}
+// ... then (after the warp has synchronised: the record's last byte shares its word with the next
+// record's first bytes) the three separator newlines around the SEQ / QUAL lines that
+// mg_emit_seq_corrupt writes
+template <class SP>
+MG_HD void mg_emit_frame_seps(typename SP::ptr dst, uint32_t qlen, int L) {
   const typename SP::ptr p = dst + (qlen + 1 + (uint32_t)L);
   SP::st8(p, '\n'); SP::st8(p + 1, '+'); SP::st8(p + 2, '\n'); SP::st8(p + (3 + (uint32_t)L), '\n');
 }
 
 // ------------------------------------------------------------------------------------------
-// Production-mode corruption (Philox draws, alias-method quality sampling).
+// Production-mode corruption (Philox draws, ONE alias-table lookup per base).
 //
-// The reference draws a quality per cycle and then a miscall with probability phred_p[quality]
-// (illumina.py:151-160).  The same joint distribution is sampled in the other order, which takes
-// the table lookup out of the miscall decision: per (file, cycle) the model gives
-//     perr = sum_q P(q) phred_p[q],      P(q | miscall) = P(q) phred_p[q] / perr,
-//                                        P(q | correct) = P(q) (1 - phred_p[q]) / (1 - perr)
-// so the miscall is decided from a per-cycle threshold the whole warp shares, and only the
-// quality comes from an alias row -- the row of (file, cycle, miscall).
+// The reference draws a quality per cycle, then a miscall with probability phred_p[quality], then
+// one of the three other bases (illumina.py:151-160).  Per (file, cycle) that is one joint
+// distribution over the outcomes (q, s): q the quality, s = 0 "called correctly" or s = 1..3 "called
+// as base code ^ s" (A=0 C=1 G=2 T=3: code ^ 1, ^ 2, ^ 3 are the three other bases, each with
+// probability 1/3, as base_rot + randint(0,3) give them):
+//     P(q, 0) = P(q) (1 - phred_p[q]),        P(q, s) = P(q) phred_p[q] / 3,  s = 1, 2, 3
+// It is sampled with ONE 32-bit Philox word and ONE lookup in a Vose alias row of K = 2^kshift
+// entries that lists the row's outcomes with non-zero mass (built at model load, mg_api.cu):
 //
-// Draw layout (the specification tests/philox_ref.py restates in numpy): for template serial s
-// (0-based count within the unit), file f and cycle pair q = n / 2,
-//     r = Philox4x32-7(counter = (s, f, q, MG_STREAM_CORRUPT), key = (k0, k1))
-// cycle 2q uses (r[0], r[1]), cycle 2q+1 uses (r[2], r[3]) as (w_bq, w_call):
-//     T = thr[f][n] = min(2^32-1, floor(perr * 2^32));   miscall iff w_call < T
-//     substituted base = base_rot[base][(w_call >= T/3) + (w_call >= floor(2T/3))]   (illumina.py:131-136,160;
-//     given a miscall, w_call is uniform on [0, T), so no third draw is needed)
-//     idx = w_bq >> (32 - kshift); frac = (w_bq << kshift) >> 8        (24 bits)
-//     e = alias[((f * n_cycles + n) * 2 + miscall) << kshift | idx]  (entry = prob24 << 8 | alias);
-//     bq = frac < (e >> 8) ? idx : (e & 255), evaluated as (w_bq << kshift) < (e & ~255)
+// Draw layout (the specification tests/philox_ref.py restates in numpy): for template serial t
+// (0-based count within the unit; 64-bit template index of the whole file for corrupt-reads), file f
+// and cycle group g = n / 4,
+//     r = Philox4x32-7(counter = (t_lo, 2 t_hi + f, g, MG_STREAM_CORRUPT), key = (k0, k1)),  w = r[n % 4]
+//     e = alias[((f * n_cycles + n) << kshift) | (w >> (32 - kshift))]
+//     take = (w << kshift  mod 2^32) < e          (e's top bits are the acceptance threshold)
+//     code = take ? e's SELF field : e's ALIAS field,   fields of 8 bits (s << 6 | q, all q < 64):
+//            e = thr16 << 16 | self8 << 8 | alias8,  or of 9 bits (s << 7 | q): e = thr14 << 18 | self9 << 9 | alias9
+//     quality = code's q;  an A/C/G/T base becomes "ACGT"[code_of_base ^ s]; any other byte (N, IUPAC,
+//     lower case) becomes 'N' when s != 0 (base_rot.get(base, 'NNN'), illumina.py:160) and stays otherwise.
 struct MgCorruptCtx {
-  const uint32_t *alias;   // [n_mates][n_cycles][2][1 << kshift]
-  const uint32_t *thr;     // [n_mates][n_cycles] miscall thresholds
-  int kshift, n_cycles, n_mates;
+  const uint32_t *alias;   // [n_mates][n_cycles][1 << kshift]
+  int kshift, code9, n_cycles, n_mates;
   uint32_t k0, k1;
-  uint32_t thr_s, lp;      // device hot path: shared-window address of the staged thresholds, planes [T][T/3][2T/3], each [file][lp]
 };
 
-MG_HD uint32_t mg_ctz4(uint32_t m) {   // index of the lowest set bit of a non-zero 4-bit mask
-#if defined(__CUDA_ARCH__)
-  return (uint32_t)__ffs((int)m) - 1u;
-#else
-  return (m & 1u) ? 0u : (m & 2u) ? 1u : (m & 4u) ? 2u : 3u;
-#endif
+// outcome code of one base: bits 0..(6|7) the quality, the two bits above the substitution
+template <bool C9>
+MG_HD uint32_t mg_corrupt_code(const uint32_t *alias, uint32_t ks, uint32_t row, uint32_t w) {
+  const uint32_t e = alias[mg_funnel_l(w, row, ks)];
+  const bool take = (w << ks) < e;
+  return C9 ? ((take ? e >> 9 : e) & 0x1FFu) : ((take ? e >> 8 : e) & 0xFFu);
 }
 
-// which of the three alternatives: w_call is uniform on [0, thr) given a miscall
-MG_HD uint32_t mg_sub_index(uint32_t w_call, uint32_t thr) {
-  const uint32_t q = thr / 3u, r = thr - 3u * q;          // floor(2 thr / 3) = 2 q + (r == 2), without 64-bit arithmetic
-  return (uint32_t)(w_call >= q) + (uint32_t)(w_call >= 2u * q + (r >> 1));
-}
-
-// one base -> bit 2 = substitution happened, bits 0-1 = which of the three alternatives; qual = ASCII quality
-MG_HD uint32_t mg_corrupt_draw(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &qual) {
-  const uint32_t cyc = f * (uint32_t)C.n_cycles + (uint32_t)n;
-  const uint32_t T = C.thr[cyc];
-  const uint32_t miss = (uint32_t)(w_call < T);
-  const uint32_t idx = w_bq >> (32 - C.kshift);
-  const uint32_t e = C.alias[((2u * cyc + miss) << C.kshift) | idx];
-  qual = ((w_bq << C.kshift) < (e & 0xFFFFFF00u) ? idx : (e & 255u)) + 33u;
-  return miss ? (4u | mg_sub_index(w_call, T)) : 0u;
-}
-
-MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w_bq, uint32_t w_call, uint32_t &base, uint32_t &qual) {
-  const uint32_t d = mg_corrupt_draw(C, f, n, w_bq, w_call, qual);
-  if (d) base = mg_base_rot((uint8_t)base, (int)(d & 3u));
-}
-
-// base_rot on 2-bit codes (A=0 C=1 G=2 T=3): A->CTG, C->ATG, G->ACT, T->ACG as 2-bit triples
-#define MG_ROT_TBL (45u | (44u << 6) | (52u << 12) | (36u << 18))
-
-// four bases (chunk word q, first base index n0) corrupted on the 2-bit codes -> new codes + ASCII
-// qualities, in three steps so that everything that does not need the alias rows runs while their
-// loads are in flight: draw (Philox, miscall bits, loads issued), subst (the miscalled codes are
-// replaced; the caller also writes the previous group's output here), qual (the loaded entries
-// become quality bytes).  Cycles >= L read a valid row and are masked out.
-struct MgDraw4 { uint32_t wb[4], wc[4], e[4], T[4], miss; };
-
-template <bool FULL, bool ES, int KS>   // FULL: all four cycles are inside the read (n0 + 4 <= L); ES: thresholds staged in
-                                        // shared memory; KS: kshift known at compile time (0 = read it from the context)
-MG_HD void mg_corrupt4_draw(const MgCorruptCtx &C, uint32_t serial, uint32_t f, int n0, int L, MgDraw4 &D) {
-  const uint32_t cyc = f * (uint32_t)C.n_cycles + (uint32_t)n0;
-  bool staged = false;
-#if defined(__CUDA_ARCH__)
-  if constexpr (ES) {   // one 16-byte load: the four cycles' thresholds (n0 is a multiple of 4, lp too)
-    asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(D.T[0]), "=r"(D.T[1]), "=r"(D.T[2]), "=r"(D.T[3]) : "r"(C.thr_s + 4u * (f * C.lp + (uint32_t)n0)));
-    staged = true;
+// one base given as ASCII (the standalone corrupt-reads kernel's tail path, exception bases)
+MG_HD void mg_corrupt_one(const MgCorruptCtx &C, uint32_t f, int n, uint32_t w, uint32_t &base, uint32_t &qual) {
+  const uint32_t row = f * (uint32_t)C.n_cycles + (uint32_t)n;
+  const uint32_t code = C.code9 ? mg_corrupt_code<true>(C.alias, (uint32_t)C.kshift, row, w) : mg_corrupt_code<false>(C.alias, (uint32_t)C.kshift, row, w);
+  const uint32_t qb = C.code9 ? 7u : 6u, s = code >> qb;
+  qual = (code & ((1u << qb) - 1u)) + 33u;
+  if (s) {
+    const uint32_t c = mg_base_code((uint8_t)base);
+    base = c > 3 ? (uint32_t)'N' : (0x54474341u >> (8u * (c ^ s))) & 0xFFu;
   }
-#endif
-  if (!staged) {
+}
+
+// Four cycles at once.  draw: the Philox block and the four table loads; decode: the four entries
+// become four ASCII quality bytes and the four substitutions as nibbles (s_j in bits 4j, 4j+1), which
+// is the layout of the PRMT selector that turns 2-bit codes into letters (mg_chars4).
+struct MgGrp { uint32_t w[4], e[4], b4; };
+
+template <bool FULL>   // FULL: all four cycles are inside the read
+MG_HD void mg_grp_draw(const MgCorruptCtx &C, uint32_t ks, uint32_t t_lo, uint32_t t_hi2f, uint32_t row0, int n0, int L, MgGrp &G) {
+  const MgPhilox r = mg_philox_corrupt(t_lo, t_hi2f, (uint32_t)(n0 >> 2), C.k0, C.k1);
+  MG_UNROLL
+  for (int j = 0; j < 4; j++) {
+    G.w[j] = r.v[j];
+    const uint32_t rj = row0 + ((FULL || n0 + j < L) ? (uint32_t)j : 0u);    // stay inside the table at the read's end
+    G.e[j] = C.alias[mg_funnel_l(G.w[j], rj, ks)];
+  }
+}
+
+template <bool C9>
+MG_HD void mg_grp_decode(const MgGrp &G, uint32_t ks, uint32_t &q4, uint32_t &snib) {
+  if constexpr (!C9) {
+    uint32_t c[4];
     MG_UNROLL
-    for (int j = 0; j < 4; j++) D.T[j] = C.thr[cyc + ((FULL || n0 + j < L) ? (uint32_t)j : 0u)];
-  }
-  const MgPhilox r0 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1), C.k0, C.k1);
-  const MgPhilox r1 = mg_philox_corrupt(serial, f, (uint32_t)(n0 >> 1) + 1u, C.k0, C.k1);
-  D.wb[0] = r0.v[0]; D.wb[1] = r0.v[2]; D.wb[2] = r1.v[0]; D.wb[3] = r1.v[2];
-  D.wc[0] = r0.v[1]; D.wc[1] = r0.v[3]; D.wc[2] = r1.v[1]; D.wc[3] = r1.v[3];
-  const uint32_t ks = KS ? (uint32_t)KS : (uint32_t)C.kshift, K = 1u << ks;
-  D.miss = 0;
-  MG_UNROLL
-  for (int j = 0; j < 4; j++) {
-    const bool in = FULL || n0 + j < L;
-    const uint32_t nj = in ? (uint32_t)j : 0u;            // stay inside the table at the read's end
-    const bool m = D.wc[j] < D.T[j];
-    // (row of (cycle, correct) << ks) | idx in one funnel shift, + K for the miscall row; 32-bit index
-    // arithmetic, so the address is one IMAD.WIDE
-    uint32_t ix = mg_funnel_l(D.wb[j], 2u * (cyc + nj), ks);
-    if (m) ix += K;
-    D.e[j] = C.alias[ix];
-    D.miss |= (in && m ? 1u : 0u) << j;
-  }
-}
-
-// substitutions (2-7 % of the bases with the shipped models): each lane walks ITS OWN miscall bits, so
-// the warp runs this loop as often as its worst lane has miscalls among the four bases.  In the
-// emit kernel the thirds of the thresholds are staged next to them ([T][T/3][2T/3] planes), so the
-// loop only selects its w_call.
-template <bool ES>
-MG_HD void mg_corrupt4_subst(const MgCorruptCtx &C, const MgDraw4 &D, uint32_t f, int n0, uint32_t &b4) {
-  uint32_t any = D.miss;
-  while (any) {
-    const uint32_t j = mg_ctz4(any);
-    any &= any - 1u;
-    const uint32_t w = j == 0 ? D.wc[0] : j == 1 ? D.wc[1] : j == 2 ? D.wc[2] : D.wc[3];
-    uint32_t sub;
-    bool staged = false;
-#if defined(__CUDA_ARCH__)
-    if constexpr (ES) {
-      uint32_t t1, t2;
-      const uint32_t a = C.thr_s + 4u * ((2u + f) * C.lp + (uint32_t)n0 + j);
-      asm("ld.shared.b32 %0, [%1];" : "=r"(t1) : "r"(a));
-      asm("ld.shared.b32 %0, [%1];" : "=r"(t2) : "r"(a + 8u * C.lp));
-      sub = (uint32_t)(w >= t1) + (uint32_t)(w >= t2);
-      staged = true;
+    for (int j = 0; j < 4; j++) c[j] = ((G.w[j] << ks) < G.e[j]) ? G.e[j] >> 8 : G.e[j];
+    const uint32_t t4 = mg_prmt2(mg_prmt2(c[0], c[1], 0x0040u), mg_prmt2(c[2], c[3], 0x0040u), 0x5410u);   // the four code bytes
+    q4 = (t4 & 0x3F3F3F3Fu) + 0x21212121u;
+    uint32_t u = (t4 >> 6) & 0x03030303u;                 // s_j in bits 8j, 8j+1 -> bits 4j, 4j+1
+    u = (u | (u >> 4)) & 0x00330033u;
+    snib = (u | (u >> 8)) & 0x3333u;
+  } else {
+    q4 = 0x21212121u; snib = 0;
+    MG_UNROLL
+    for (int j = 0; j < 4; j++) {
+      const uint32_t c = (((G.w[j] << ks) < G.e[j]) ? G.e[j] >> 9 : G.e[j]) & 0x1FFu;
+      q4 += (c & 127u) << (8 * j);
+      snib |= (c >> 7) << (4 * j);
     }
-#endif
-    if (!staged) sub = mg_sub_index(w, j == 0 ? D.T[0] : j == 1 ? D.T[1] : j == 2 ? D.T[2] : D.T[3]);
-    const uint32_t code = (b4 >> (2u * j)) & 3u;
-    const uint32_t nc = (MG_ROT_TBL >> (6u * code + 2u * sub)) & 3u;
-    b4 ^= (code ^ nc) << (2u * j);
   }
 }
 
-template <bool FULL, int KS>
-MG_HD uint32_t mg_corrupt4_qual(const MgCorruptCtx &C, const MgDraw4 &D, int n0, int L) {
-  const uint32_t ks = KS ? (uint32_t)KS : (uint32_t)C.kshift;
-  uint32_t bq[4];
-  MG_UNROLL
-  for (int j = 0; j < 4; j++) {
-    bq[j] = (D.wb[j] << ks) < (D.e[j] & 0xFFFFFF00u) ? (D.wb[j] >> (32u - ks)) : (D.e[j] & 255u);   // frac24 < prob24
-  }
-  if (FULL) return (bq[0] + (bq[1] << 8)) + ((bq[2] + (bq[3] << 8)) << 16) + 0x21212121u;
-  uint32_t qw = 0;
-  MG_UNROLL
-  for (int j = 0; j < 4; j++) if (n0 + j < L) qw |= (bq[j] + 33u) << (8 * j);
-  return qw;
+// four 2-bit codes (low byte of b) with substitutions -> four ASCII bases
+MG_HD uint32_t mg_chars4_sub(uint32_t b, uint32_t snib) {
+  uint32_t y = (b | (b << 4)) & 0x0F0Fu;
+  uint32_t z = ((y | (y << 2)) & 0x3333u) ^ snib;
+  return mg_prmt(0x54474341u /* 'A','C','G','T' little-endian */, z);
 }
 
 // SEQ and QUAL lines of one read, corrupted on the fly: every thread of a warp is at the same
-// cycle of its own record, so the alias row (one 256-byte line pair) is shared by the warp.
-template <class SP, int KS = 0, int MAXW, class HP, class EP>
+// cycle of its own record, so the alias row is shared by the warp.
+//
+// The read's 2-bit codes are first parked, strand-normalised and byte-aligned (one byte per group of
+// four cycles), in the tail of the record's OWN quality line: byte coff + g, coff = L - 4 ceil(L / 16).
+// The quality bytes written later never reach a parked byte that is still to be read (checked below),
+// the register window dies before the main loop, and that loop can be rolled over the groups.
+//
+// Main loop: two groups per trip in two register sets (A, B); a set's table loads are issued one
+// group of work before its decode (draw B, flush A, draw A', flush B, ...) and never copied.
+template <class SP, bool C9, int MAXW, class HP, class EP>
 MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_dst, MgSeqSrc<MAXW, HP> &S, EP exc, int n_exc,
-                               const MgCorruptCtx &C, uint32_t serial, uint32_t f) {
+                               const MgCorruptCtx &C, uint32_t t_lo, uint32_t t_hi2f, uint32_t f) {
   const int L = S.L;
   const struct { uint32_t x; int strand; HP hap; } mine = {S.x, S.strand, S.hap};
-  constexpr bool ES = !SP::is_generic;   // staged in shared memory <=> running in k_unit_emit with the threshold table staged too
-  MgWordStream<SP> ws, wq;
+  const uint32_t ks = (uint32_t)C.kshift;
+  const uint32_t rowf = f * (uint32_t)C.n_cycles;
+  const int NCH = (L + 15) >> 4, NG = L >> 2, rem = L & 3;
+  const int coff = L - 4 * NCH;                       // >= 0 iff L >= 4
+  S.prep();
+  uint32_t b_last = 0;                                // the codes of the last, partial group
+  if (L >= 4) {
+    MgStream<SP> cs;
+    cs.begin_rmw(qual_dst + (uint32_t)coff);
+    if constexpr (MAXW > 0) {
+      MG_UNROLL
+      for (int c = 0; c < MAXW - 1; c++) if (16 * c < L) cs.put_word(mg_win_codes(S.W, c));
+    } else {
+      for (int c = 0; 16 * c < L; c++) cs.put_word(S.codes(c));
+    }
+    cs.end();
+    if (rem) b_last = SP::ld8(qual_dst + (uint32_t)(coff + NG));
+  } else {
+    if constexpr (MAXW > 0) b_last = mg_win_codes(S.W, 0) & 0xFFu; else b_last = S.codes(0) & 0xFFu;
+  }
+  // a quality byte never lands on a parked byte before that byte has been read: the draw of group
+  // g + 2 (reading byte coff + g + 2) follows the flush of group g (quality bytes up to 4g + 3), and
+  // coff + g + 2 > 4g + 3 for every g + 2 < NG whenever L >= 4 (coff >= 12 k + r - 4 for L = 16 k + r).
+  MgStream<SP> ws, wq;
   ws.begin_rmw(seq_dst); wq.begin_rmw(qual_dst);
-  // the output of a group is written one group late, between the next group's table loads and
-  // their first use, together with this group's substitutions: independent work under the L2 latency
-  uint32_t pb4 = 0, pqw = 0;
-  bool pend = false;
-  mg_for_each_chunk(S, [&](uint32_t codes, int c) {
-    if (16 * c + 16 <= L) {              // a whole chunk: four full groups, no per-group bounds logic
-      int n0 = 16 * c;
-      MG_NOUNROLL
-      for (int q = 0; q < 4; q++, n0 += 4, codes >>= 8) {
-        uint32_t b4 = codes & 0xFFu;
-        MgDraw4 D;
-        mg_corrupt4_draw<true, ES, KS>(C, serial, f, n0, L, D);
-        if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
-        mg_corrupt4_subst<ES>(C, D, f, n0, b4);
-        pb4 = b4; pqw = mg_corrupt4_qual<true, KS>(C, D, n0, L); pend = true;
-      }
-      return;
-    }
+  const typename SP::ptr cbase = qual_dst + (uint32_t)(coff < 0 ? 0 : coff);
+  auto draw = [&](MgGrp &G, int g) {
+    G.b4 = SP::ld8(cbase + (uint32_t)g);
+    mg_grp_draw<true>(C, ks, t_lo, t_hi2f, rowf + 4u * (uint32_t)g, 4 * g, L, G);
+  };
+  auto flush = [&](const MgGrp &G) {
+    uint32_t q4, snib;
+    mg_grp_decode<C9>(G, ks, q4, snib);
+    ws.put_word(mg_chars4_sub(G.b4, snib)); wq.put_word(q4);
+  };
+  if (NG > 0) {
+    MgGrp A, B;
+    int g = 0;
+    draw(A, 0);
     MG_NOUNROLL
-    for (int q = 0; q < 4; q++) {        // the last, partial chunk
-      const int n0 = 16 * c + 4 * q;
-      if (n0 < L) {
-        uint32_t b4 = (codes >> (8 * q)) & 0xFFu, qw;
-        MgDraw4 D;
-        if (n0 + 4 <= L) {
-          mg_corrupt4_draw<true, ES, KS>(C, serial, f, n0, L, D);
-          if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
-          mg_corrupt4_subst<ES>(C, D, f, n0, b4);
-          pb4 = b4; pqw = mg_corrupt4_qual<true, KS>(C, D, n0, L); pend = true;
-        } else {
-          if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); pend = false; }
-          mg_corrupt4_draw<false, ES, KS>(C, serial, f, n0, L, D);
-          mg_corrupt4_subst<ES>(C, D, f, n0, b4);
-          qw = mg_corrupt4_qual<false, KS>(C, D, n0, L);
-          const uint32_t ch = mg_chars4(b4);
-          for (int j = 0; n0 + j < L; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(qw >> (8 * j))); }
-        }
-      }
+    while (g + 2 < NG) {
+      draw(B, g + 1); flush(A);
+      draw(A, g + 2); flush(B);
+      g += 2;
     }
-  });
-  if (pend) { ws.put_word(mg_chars4(pb4)); wq.put_word(pqw); }
+    if (g + 1 < NG) { draw(B, g + 1); flush(A); flush(B); }
+    else flush(A);
+  }
+  if (rem) {
+    MgGrp G;
+    G.b4 = b_last;
+    mg_grp_draw<false>(C, ks, t_lo, t_hi2f, rowf + 4u * (uint32_t)NG, 4 * NG, L, G);
+    uint32_t q4, snib;
+    mg_grp_decode<C9>(G, ks, q4, snib);
+    const uint32_t ch = mg_chars4_sub(G.b4, snib);
+    for (int j = 0; j < rem; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(q4 >> (8 * j))); }
+  }
   ws.end(); wq.end();
   if (n_exc) {
-    // bases in exception runs: the reference substitutes 'N' for any non-ACGT base on an error
-    // (base_rot.get(base, 'NNN'), illumina.py:160) and leaves it alone otherwise
+    // bases in exception runs: a non-ACGT byte becomes 'N' on a miscall (base_rot.get(base, 'NNN'),
+    // illumina.py:160) and is copied otherwise; the quality line is already right
     for (int k = mg_exc_first(exc, n_exc, mine.x); k < n_exc; k++) {
       const MgExc e = exc[k];
       if ((uint64_t)e.start >= (uint64_t)mine.x + L) break;
@@ -920,9 +1066,9 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
       uint64_t b = (uint64_t)e.start + e.len < (uint64_t)mine.x + L ? (uint64_t)e.start + e.len : (uint64_t)mine.x + L;
       for (uint64_t i = a; i < b; i++) {
         const int idx = (int)(i - mine.x), n = mine.strand ? (L - 1 - idx) : idx;
-        const MgPhilox r = mg_philox_corrupt(serial, f, (uint32_t)(n >> 1), C.k0, C.k1);
+        const MgPhilox r = mg_philox_corrupt(t_lo, t_hi2f, (uint32_t)(n >> 2), C.k0, C.k1);
         uint32_t base = mg_exc_byte(e, mine.hap, i), qual;
-        mg_corrupt_one(C, f, n, (n & 1) ? r.v[2] : r.v[0], (n & 1) ? r.v[3] : r.v[1], base, qual);
+        mg_corrupt_one(C, f, n, r.v[n & 3], base, qual);
         SP::st8(seq_dst + (uint32_t)n, (uint8_t)base);
       }
     }

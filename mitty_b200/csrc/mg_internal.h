@@ -17,7 +17,7 @@ struct alignas(16) MgPlan {
   uint32_t xa, xb;     // read starts relative to p_min (mate 0 forward, mate 1 reverse)
   int32_t n0a, n0b;    // first node of each read
   uint32_t dn;         // (n1 - n0) of mate 0 | mate 1 << 16
-  uint32_t fo_sz;      // file-order bit << 31 | record bytes (with the serial's digits)
+  uint32_t fo_sz;      // file-order bit << 31 | mate 0 / mate 1 touches an exception run << 30 / 29 | record bytes (with the serial's digits)
   uint64_t off;        // byte offset of the record in each file
 };
 
@@ -40,8 +40,11 @@ struct MgUnitParams {
   const int8_t *fo_in;       // DET / EXPLICIT: file-order bits, consumed in te<p_max survivor order
   const uint32_t *ts_sorted; // PHILOX: cumulative geometric gaps (+1), relative to p_min
   uint32_t key_tlen0, key_tlen1, key_perm0, key_perm1, half_bits;
-  // qname constants: prefix = "@sample:worker:ps:", mid = "|chrom|cpy"
-  const uint8_t *prefix; int prefix_len; const uint8_t *mid; int mid_len;
+  // qname constants as tokens: "@sample:worker:ps:", "|chrom|cpy", "|<L>|<L>=|" (built on the host, read from
+  // the kernel's parameter space)
+  MgQnConst qn;
+  int qn_len;                // bytes of the two constant strings
+  int bulk;                  // copy-out through cp.async.bulk (1) or 128-bit loads / stores (0, experiments)
   // outputs
   uint8_t *out[2]; uint64_t cap;
   MgPlan *plan;              // [n_cand] written by k_unit_plan, read by k_unit_emit

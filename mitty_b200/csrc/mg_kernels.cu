@@ -5,10 +5,12 @@
 //   k_hap_build       packed reference + variant segments -> packed haplotype of one copy
 //   k_blk_table       node keys -> block lookup table
 //   k_gap_*           Philox geometric gaps -> grid-wide inclusive scan (template starts)
-//   k_unit_emit       THE hot kernel: template sampling + filters + node lookup + qname/CIGAR
-//                     formatting + sequence extraction/revcomp (+ fused Philox corruption),
-//                     decoupled look-back scan for record placement, smem-staged coalesced
-//                     FASTQ writes
+//   k_walk_*          node list of a chromosome copy (pointer doubling over the variant chain)
+//   k_unit_plan       phase 1 of a unit: template sampling, te < p_max / N filters, node lookup, record
+//                     sizes, decoupled look-back scan -> one 32-byte plan per kept template
+//   k_unit_emit       THE hot kernel, phase 2: qname/CIGAR formatting + sequence extraction/revcomp
+//                     (+ fused Philox corruption) into per-warp shared-memory stages, bulk-copied
+//                     (cp.async.bulk) to the two FASTQ buffers
 //   k_sample          template sampling only (read-module plugin generate_reads)
 //   k_scan_*          generic exclusive scan (int64)
 //   k_nl_*            FASTQ newline index
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_unit_plan(const __grid_constan
     const int tile = (int)s_tile;
     if (tile >= P.n_tiles) break;
     const uint32_t j = (uint32_t)tile * PLAN_THREADS + t;
-    bool k1 = false, k2 = false;
+    bool k1 = false, k2 = false, ta = false, tb = false;
     uint32_t xa = 0, xb = 0, fo = 0, sz = 0;
     int n0a = 0, n1a = 0, n0b = 0, n1b = 0;
     if (j < P.n_cand) {
@@ -617,13 +619,16 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_unit_plan(const __grid_constan
       if (k1) {
         xa = (uint32_t)c.ts_rel; xb = (uint32_t)(c.te_rel - L);                 // illumina.py:95-96
         k2 = true;
-        if (P.n_exc) k2 = (mg_count_N(P.exc, P.n_exc, xa, L) <= 2) && (mg_count_N(P.exc, P.n_exc, xb, L) <= 2);  // readgenerate.py:204
+        if (P.n_exc) {                                                           // readgenerate.py:204
+          const int na = mg_count_N(P.exc, P.n_exc, xa, L, ta), nb = mg_count_N(P.exc, P.n_exc, xb, L, tb);
+          k2 = na <= 2 && nb <= 2;
+        }
         if (k2) {
           n0a = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xa);
           n1a = mg_last_node(P.nodes, n0a, P.n_nodes, xa, L);
           n0b = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xb);
           n1b = mg_last_node(P.nodes, n0b, P.n_nodes, xb, L);
-          sz = (uint32_t)(P.prefix_len + P.mid_len) + mg_read_fields_len(P.nodes, n0a, n1a, xa, L, P.L_nd) +
+          sz = (uint32_t)P.qn_len + mg_read_fields_len(P.nodes, n0a, n1a, xa, L, P.L_nd) +
                mg_read_fields_len(P.nodes, n0b, n1b, xb, L, P.L_nd) + 2u * (uint32_t)L + 5u;
         }
       }
@@ -668,7 +673,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_unit_plan(const __grid_constan
       MgPlan pl;
       pl.xa = xa; pl.xb = xb; pl.n0a = n0a; pl.n0b = n0b;
       pl.dn = (uint32_t)(n1a - n0a) | ((uint32_t)(n1b - n0b) << 16);
-      pl.fo_sz = (my_fo << 31) | (sz + (uint32_t)mg_ndigits32((uint32_t)(rank + 1)));
+      pl.fo_sz = (my_fo << 31) | ((ta ? 1u : 0u) << 30) | ((tb ? 1u : 0u) << 29) | (sz + (uint32_t)mg_ndigits32((uint32_t)(rank + 1)));
       pl.off = off;
       P.plan[rank] = pl;
     }
@@ -683,8 +688,10 @@ void mg_launch_plan(const MgUnitParams &P, cudaStream_t st) {
 
 // ---- k_unit_emit ---------------------------------------------------------------------------
 // Phase 2: one WARP owns 32 consecutive kept templates (every lane busy), formats their records
-// into its own shared-memory stage and copies the byte range out with coalesced 128-bit stores.
-// No block barrier and no scan: placement was decided by k_unit_plan.
+// into its own shared-memory stage and hands the 16-byte aligned body of the byte range to the bulk
+// copy engine (cp.async.bulk shared -> global, L2 evict-first); only the unaligned head / tail bytes
+// go through the load/store pipe.  No block barrier and no scan: placement was decided by k_unit_plan.
+
 // a record larger than the whole stage (only possible with absurdly long CIGARs): straight to
 // global memory through generic pointers, streaming sequence source; cold and out of line
 template <int CORRUPT>
@@ -694,54 +701,54 @@ __device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const Mg
   MgSeqSrc<0, const uint32_t *> S;
   S.load(P.hap, mine.x, L, mine.strand);
   if constexpr (CORRUPT) {
-    mg_emit_frame<MgGenericSpace>(dst, qlen, P.prefix, P.prefix_len, cnt, P.mid, P.mid_len, P.nodes, first, second, L);
-    mg_emit_seq_corrupt<MgGenericSpace>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, P.cor, (uint32_t)(cnt - 1), (uint32_t)f);
+    mg_emit_frame_qname<MgGenericSpace>(dst, P.qn, (uint32_t)cnt, P.nodes, first, second, L);
+    mg_emit_frame_seps<MgGenericSpace>(dst, qlen, L);
+    mg_emit_seq_corrupt<MgGenericSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, P.cor, (uint32_t)(cnt - 1), (uint32_t)f, (uint32_t)f);
   } else {
-    mg_emit_record<MgGenericSpace>(dst, qlen, P.prefix, P.prefix_len, cnt, P.mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
+    MgStream<MgGenericSpace> ws;
+    mg_emit_record<MgGenericSpace>(ws, dst, P.qn, (uint32_t)cnt, P.nodes, first, second, S);
+    ws.end();
+    if (P.n_exc) mg_patch_exc<MgGenericSpace>(dst + (qlen + 1), P.exc, P.n_exc, S.hap, S.x, L, S.strand);
   }
 }
 
-// CORRUPT: 0 = perfect reads; 6 / 7 = fused corruption with that kshift (64- / 128-entry alias rows)
+__device__ __forceinline__ void bulk_store(uint8_t *gdst, uint32_t ssrc, uint32_t bytes, unsigned long long policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :: "l"(gdst), "r"(ssrc), "r"(bytes), "l"(policy) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// CORRUPT: 0 = perfect reads; 1 / 2 = fused corruption with 8- / 9-bit outcome codes
 template <int MAXW, int CORRUPT>
 __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint8_t s_prefix[MG_QN_MAX], s_mid[MG_QN_MAX];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   uint8_t *stage = smem + (uint32_t)wid * (uint32_t)(P.stage_cap + 16);      // this warp's stage
   // its shared-window address, pinned in a register (the compiler would otherwise rebuild it at every store)
   uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   asm volatile("" : "+r"(stage_s));
   const int L = P.rlen;
-  MgCorruptCtx cor = P.cor;
-  if constexpr (CORRUPT) {
-    // per-cycle miscall thresholds of both files and their thirds, staged behind the stages:
-    // planes [T][T/3][2T/3], each [file][lp], lp = L rounded up to 4
-    uint32_t *s_thr = reinterpret_cast<uint32_t *>(smem + (MG_CTA / 32) * (uint32_t)(P.stage_cap + 16));
-    const int lp = (L + 3) & ~3;
-#pragma unroll 1
-    for (int i = t; i < 2 * lp; i += MG_CTA) {
-      const int f = i / lp, n = i - f * lp;
-      const uint32_t T = (n < P.cor.n_cycles && f < P.cor.n_mates) ? P.cor.thr[f * P.cor.n_cycles + n] : 0u;
-      const uint32_t q = T / 3u, r = T - 3u * q;
-      s_thr[i] = T; s_thr[2 * lp + i] = q; s_thr[4 * lp + i] = 2u * q + (r >> 1);   // mg_sub_index's thirds
-    }
-    cor.thr_s = (uint32_t)__cvta_generic_to_shared(s_thr);
-    cor.lp = (uint32_t)lp;
-    asm volatile("" : "+r"(cor.thr_s));
-  }
-#pragma unroll 1
-  for (int i = t; i < P.prefix_len; i += MG_CTA) s_prefix[i] = P.prefix[i];
-#pragma unroll 1
-  for (int i = t; i < P.mid_len; i += MG_CTA) s_mid[i] = P.mid[i];
-  __syncthreads();
   const unsigned long long n_kept = P.totals[1], n_bytes = P.totals[2];
   if (n_bytes > P.cap) { if (t == 0 && blockIdx.x == 0) P.totals[3] = 1ull; return; }   // host regrows and relaunches
+  unsigned long long policy = 0;
+  if (P.bulk) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));   // the FASTQ bytes must not push the haplotype out of L2
+  bool in_flight = false;          // a bulk copy may still be reading this warp's stage
   const unsigned long long n_wt = (n_kept + 31) / 32;
   for (unsigned long long wt = (unsigned long long)blockIdx.x * (MG_CTA / 32) + wid; wt < n_wt; wt += (unsigned long long)gridDim.x * (MG_CTA / 32)) {
     const unsigned long long rank = wt * 32 + lane;
     const bool active = rank < n_kept;
     MgPlan pl = P.plan[active ? rank : n_kept - 1];
-    const uint32_t rec = pl.fo_sz & 0x7FFFFFFFu, my_fo = pl.fo_sz >> 31;
+    const uint32_t rec = pl.fo_sz & 0x1FFFFFFFu, my_fo = pl.fo_sz >> 31;
+    // exception runs (N, IUPAC, lower case) are searched only for the reads the plan flagged
+    const int ne_a = (pl.fo_sz & (1u << 30)) ? P.n_exc : 0, ne_b = (pl.fo_sz & (1u << 29)) ? P.n_exc : 0;
+    const int ne_first = my_fo ? ne_b : ne_a, ne_second = my_fo ? ne_a : ne_b;
+    // the next tile's plan records, and the first node of each of this tile's reads, on their way into L2 / L1
+    {
+      const unsigned long long nr = rank + (unsigned long long)gridDim.x * MG_CTA;
+      if (nr < n_kept) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.plan + nr));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(P.nodes + pl.n0a));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(P.nodes + pl.n0b));
+    }
     const uint32_t qlen = rec - (2u * (uint32_t)L + 5u);
     const unsigned long long cnt = rank + 1;
     MgReadRef ra, rb;
@@ -763,73 +770,102 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
       const uint32_t batch_bytes = (uint32_t)(gend - goff);
       const bool oversize = (pad + batch_bytes) > (uint32_t)P.stage_cap;         // only a record larger than the stage
       const bool mine = active && lane >= lo && lane < hi;
+      const uint32_t dst = stage_s + pad + (uint32_t)(pl.off - goff);
       MgSeqSrc<MAXW, const uint32_t *> S;
       // software pipeline with ONE load site: iteration f emits file f from the window loaded in
       // iteration f-1 and then starts the loads of file f+1 (they overlap with the copy-out)
       for (int f = -1; f < 2; f++) {
         if (f >= 0 && P.out[f] == nullptr) continue;
-        if (mine) {
-          if (f >= 0) {
-            if (!oversize) {
-              const uint32_t dst = stage_s + pad + (uint32_t)(pl.off - goff);
-              // the stage keeps the qname (and, for perfect reads, the quality line) of file 0 in
-              // place: the other file only rewrites its L sequence bytes
-              const bool full = (f == 0) || (P.out[0] == nullptr);
-              if constexpr (CORRUPT) {
-                if (full) mg_emit_frame<MgSharedSpace>(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, L);
-                mg_emit_seq_corrupt<MgSharedSpace, CORRUPT>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)rank, (uint32_t)f);
-              } else {
-                if (full) mg_emit_record<MgSharedSpace>(dst, qlen, s_prefix, P.prefix_len, cnt, s_mid, P.mid_len, P.nodes, first, second, S, P.exc, P.n_exc);
-                else mg_rewrite_seq<MgSharedSpace>(dst + qlen + 1, S, P.exc, P.n_exc);
+        // the stage keeps the qname (and, for perfect reads, the quality line) of the first file
+        // written in place: the other file only rewrites its L sequence (and quality) bytes
+        const bool full = (f == 0) || (P.out[0] == nullptr);
+        const int ne_f = f ? ne_second : ne_first;           // file f holds `second` iff f == 1
+        if (f >= 0 && !oversize) {
+          if (in_flight) {                                  // the previous copy must have read the stage
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            in_flight = false;
+          }
+          if constexpr (CORRUPT) {
+            if (full) {
+              if (mine) mg_emit_frame_qname<MgSharedSpace>(dst, P.qn, (uint32_t)cnt, P.nodes, first, second, L);
+              __syncwarp();                                 // every first word is stored: now the bytes that share a word with a neighbour
+              if (mine) mg_emit_frame_seps<MgSharedSpace>(dst, qlen, L);
+            }
+            if (mine) mg_emit_seq_corrupt<MgSharedSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, ne_f, P.cor, (uint32_t)rank, (uint32_t)f, (uint32_t)f);
+          } else {
+            if (full) {
+              MgStream<MgSharedSpace> ws;
+              if (mine) mg_emit_record<MgSharedSpace>(ws, dst, P.qn, (uint32_t)cnt, P.nodes, first, second, S);
+              __syncwarp();
+              if (mine) {
+                ws.end();
+                if (ne_f) mg_patch_exc<MgSharedSpace>(dst + (qlen + 1), P.exc, ne_f, S.hap, S.x, L, S.strand);
               }
-            } else {
-              emit_oversize<CORRUPT>(P.out[f] + pl.off, qlen, P, cnt, first, second, f ? second : first, f);
+            } else if (mine) {
+              mg_rewrite_seq<MgSharedSpace>(dst + qlen + 1, S, P.exc, ne_f);
             }
           }
-          if (f < 1) {
-            const MgReadRef nxt = (f < 0 && P.out[0] != nullptr) ? first : second;
-            S.load(P.hap, nxt.x, L, nxt.strand);
-          }
+        } else if (f >= 0 && mine) {
+          emit_oversize<CORRUPT>(P.out[f] + pl.off, qlen, P, cnt, first, second, f ? second : first, f);
+        }
+        if (mine && f < 1) {
+          const MgReadRef nxt = (f < 0 && P.out[0] != nullptr) ? first : second;
+          S.load(P.hap, nxt.x, L, nxt.strand);
         }
         if (f < 0 || oversize) continue;
-        __syncwarp();
-        // coalesced copy-out: smem and global share the same 16-byte phase (pad)
+        // copy-out: smem and global share the same 16-byte phase (pad)
         uint8_t *gdst = P.out[f] + goff;
         const uint8_t *ssrc = stage + pad;
         uint32_t head = (16u - pad) & 15u;
         if (head > batch_bytes) head = batch_bytes;
-        if ((uint32_t)lane < head) gdst[lane] = ssrc[lane];
         const uint32_t nvec = (batch_bytes - head) >> 4;
-        const uint4 *sv = reinterpret_cast<const uint4 *>(ssrc + head);
-        uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
-        for (uint32_t v = lane; v < nvec; v += 32) __stcs(gv + v, sv[v]);   // streaming: the FASTQ bytes must not push the haplotype out of L2
         const uint32_t done = head + (nvec << 4);
-        if (done + lane < batch_bytes) gdst[done + lane] = ssrc[done + lane];
-        __syncwarp();
+        if (P.bulk) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // this thread's stage writes -> visible to the copy engine
+          __syncwarp();
+          if (lane == 0 && nvec) bulk_store(gdst + head, stage_s + pad + head, nvec << 4, policy);
+          in_flight = nvec != 0;
+          if ((uint32_t)lane < head) gdst[lane] = ssrc[lane];
+          if (done + lane < batch_bytes) gdst[done + lane] = ssrc[done + lane];
+        } else {
+          __syncwarp();
+          if ((uint32_t)lane < head) gdst[lane] = ssrc[lane];
+          const uint4 *sv = reinterpret_cast<const uint4 *>(ssrc + head);
+          uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
+          for (uint32_t v = lane; v < nvec; v += 32) __stcs(gv + v, sv[v]);   // streaming stores
+          if (done + lane < batch_bytes) gdst[done + lane] = ssrc[done + lane];
+          __syncwarp();
+        }
       }
       lo = hi;
     }
   }
+  // bulk copies still reading shared memory must finish before the CTA's shared memory is released
+  if (P.bulk && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 typedef void (*unit_kernel_t)(const MgUnitParams);
 
-static unit_kernel_t unit_kernel(int L, int corrupt) {   // corrupt: 0, or the kshift (6 / 7) of the fused corruption
+static unit_kernel_t unit_kernel(int L, int corrupt) {   // corrupt: 0, or 1 / 2 = fused corruption with 8- / 9-bit outcome codes
   // register window: MAXW - 1 >= ceil((15 + L) / 16)
-  if (L <= 161) return corrupt == 0 ? k_unit_emit<12, 0> : corrupt == 6 ? k_unit_emit<12, 6> : k_unit_emit<12, 7>;
-  if (L <= 305) return corrupt == 0 ? k_unit_emit<21, 0> : corrupt == 6 ? k_unit_emit<21, 6> : k_unit_emit<21, 7>;
-  return corrupt == 0 ? k_unit_emit<0, 0> : corrupt == 6 ? k_unit_emit<0, 6> : k_unit_emit<0, 7>;
+  if (L <= 161) return corrupt == 0 ? k_unit_emit<12, 0> : corrupt == 1 ? k_unit_emit<12, 1> : k_unit_emit<12, 2>;
+  if (L <= 305) return corrupt == 0 ? k_unit_emit<21, 0> : corrupt == 1 ? k_unit_emit<21, 1> : k_unit_emit<21, 2>;
+  return corrupt == 0 ? k_unit_emit<0, 0> : corrupt == 1 ? k_unit_emit<0, 1> : k_unit_emit<0, 2>;
 }
 
+// -> CTAs to launch (SMs x resident CTAs per SM), or 0 when the staging area does not fit this device
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
-  int smem = (MG_CTA / 32) * (stage_cap + 16) + (corrupt ? 3 * 2 * 4 * ((L + 3) & ~3) : 0);   // stages + staged miscall thresholds and their thirds
+  int smem = (MG_CTA / 32) * (stage_cap + 16);
   if (const char *x = getenv("MG_EXTRA_SMEM")) smem += atoi(x);   // occupancy experiments only
   *smem_bytes = smem;
   unit_kernel_t k = unit_kernel(L, corrupt);
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  int per_sm = 0, dev = 0, sms = 0;
+  int per_sm = 0, dev = 0, sms = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (smem > optin) return 0;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, MG_CTA, smem);
   if (per_sm < 1) per_sm = 1;
   return sms * per_sm;
@@ -837,7 +873,7 @@ int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
 
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st) {
   if (P.n_tiles == 0) return;
-  unit_kernel(P.rlen, P.corrupt ? P.cor.kshift : 0)<<<grid, MG_CTA, smem_bytes, st>>>(P);
+  unit_kernel(P.rlen, P.corrupt ? 1 + P.cor.code9 : 0)<<<grid, MG_CTA, smem_bytes, st>>>(P);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1004,15 +1040,15 @@ __global__ void __launch_bounds__(256) k_corrupt(MgCorruptParams P) {
           mg_corrupt_call(seq, qual, n, row, P.n_bq, P.phred, P.bq_rnd[d0 + n], P.call_rnd[d0 + n], (int)P.base_rnd[d0 + n]);
         }
       } else {
-        for (int pr = lane; 2 * pr < L; pr += 32) {
+        for (int g = lane; 4 * g < L; g += 32) {
           const int64_t gr = P.first + r;   // template index in the whole file
-          const MgPhilox rr = mg_philox_corrupt((uint32_t)gr, (uint32_t)(gr >> 32) * 2u + (uint32_t)f, (uint32_t)pr, P.cor.k0, P.cor.k1);
+          const MgPhilox rr = mg_philox_corrupt((uint32_t)gr, (uint32_t)(gr >> 32) * 2u + (uint32_t)f, (uint32_t)g, P.cor.k0, P.cor.k1);
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int n = 2 * pr + h;
+          for (int h = 0; h < 4; h++) {
+            const int n = 4 * g + h;
             if (n < L) {
               uint32_t base = seq[n], q;
-              mg_corrupt_one(P.cor, (uint32_t)f, n, h ? rr.v[2] : rr.v[0], h ? rr.v[3] : rr.v[1], base, q);
+              mg_corrupt_one(P.cor, (uint32_t)f, n, rr.v[h], base, q);
               seq[n] = (uint8_t)base; qual[n] = (uint8_t)q;
             }
           }

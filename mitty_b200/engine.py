@@ -89,16 +89,16 @@ class Engine(object):
     self._check(self._L.mg_model_load(self._h, _ptr(cum_tlen), cum_tlen.size, _ptr(cum_bq), cum_bq.shape[0],
                                       cum_bq.shape[1], cum_bq.shape[2], _ptr(PHRED_P), self.rlen))
 
-  def model_tables(self, kshift):
-    """-> (alias u32[n_mates, n_cycles, 2, 1 << kshift], n64, thr u32[n_mates, n_cycles]) as built at
-    load time: quality alias rows given a correct call / a miscall, per-cycle miscall thresholds."""
-    n64 = C.c_int32(0)
-    self._check(self._L.mg_model_tables(self._h, kshift, None, 0, C.byref(n64), None))
+  def model_tables(self, which=0):
+    """-> (alias u32[n_mates, n_cycles, 1 << kshift], kshift, code9) as built at load time: the joint
+    (quality, substitution) alias rows of production-mode corruption.  which = 0: the fused emit kernel's
+    table (cycles < rlen), 1: the standalone corrupt kernel's (every cycle)."""
+    ks, c9, nr = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    self._check(self._L.mg_model_tables(self._h, int(which), None, 0, C.byref(ks), C.byref(c9), C.byref(nr)))
     nm, nc = self._model_shape[0], self._model_shape[1]
-    alias = np.zeros((nm * nc * 2) << kshift, dtype=np.uint32)
-    thr = np.zeros(nm * nc, dtype=np.uint32)
-    self._check(self._L.mg_model_tables(self._h, kshift, _ptr(alias), alias.size, C.byref(n64), _ptr(thr)))
-    return alias.reshape(nm, nc, 2, 1 << kshift), n64.value, thr.reshape(nm, nc)
+    alias = np.zeros((nm * nc) << ks.value, dtype=np.uint32)
+    self._check(self._L.mg_model_tables(self._h, int(which), _ptr(alias), alias.size, C.byref(ks), C.byref(c9), C.byref(nr)))
+    return alias.reshape(nm, nc, 1 << ks.value), ks.value, c9.value
 
   # -- haplotypes --------------------------------------------------------------------------------
   def load_region(self, ref_bytes, bed_start):

@@ -22,12 +22,18 @@ logger = logging.getLogger(__name__)
 
 
 def open_fastq(fname):
-  """One open() per input, gzip sniffed from the first bytes of that same stream: the inputs may
-  be FIFOs or /dev/fd/N process substitutions (examples/reads/run.sh:13-16 of the reference feeds
-  corrupt-reads from FIFOs), where a second open() blocks for ever or loses the bytes already read."""
-  import gzip
+  """One open() per input: the inputs may be FIFOs or /dev/fd/N process substitutions
+  (examples/reads/run.sh:13-16 of the reference feeds corrupt-reads from FIFOs), where a second
+  open() blocks for ever or loses the bytes already read.  Nothing is read here: see sniff_gzip."""
   import io
-  fp = io.open(fname, 'rb', buffering=1 << 20)      # BufferedReader: peek() does not consume
+  return io.open(fname, 'rb', buffering=1 << 20)      # BufferedReader: peek() does not consume
+
+
+def sniff_gzip(fp):
+  """gzip is recognised from the first bytes of the one open stream -- at the first READ, not at
+  open time: a writer that opens its two FIFOs one after the other only starts to write once BOTH
+  have a reader, so blocking on the first input's bytes before opening the second would deadlock."""
+  import gzip
   if fp.peek(2)[:2] == b'\x1f\x8b':
     return gzip.GzipFile(fileobj=fp, mode='rb')
   return fp
@@ -45,12 +51,15 @@ class _Stream(object):
 
   def __init__(self, fname, buf):
     self.fp = open_fastq(fname)
+    self.sniffed = False
     self.buf, self.fill, self.eof = buf, 0, False
 
   def close(self):
     self.fp.close()
 
   def refill(self):
+    if not self.sniffed:
+      self.fp, self.sniffed = sniff_gzip(self.fp), True
     mv = memoryview(self.buf)
     while self.fill < self.buf.size and not self.eof:
       n = self.fp.readinto(mv[self.fill:])

@@ -80,9 +80,9 @@ def run_emul(lib, lay, L, ts, tl, fo, prefix, mid, corrupt=None, maxw=None):
                     C.c_void_p(lay['exc'].ctypes.data), C.c_int(lay['n_exc']), C.c_int(L), C.c_int64(len(ts)),
                     C.c_void_p(ts_rel.ctypes.data), C.c_void_p(tl.ctypes.data), C.c_void_p(fo.ctypes.data),
                     prefix.encode(), mid.encode(), C.c_void_p(o1.ctypes.data), C.c_void_p(o2.ctypes.data), C.c_int64(cap), C.byref(nb),
-                    *((C.c_int(0), None, C.c_int(6), C.c_int(0), None, C.c_uint32(0), C.c_uint32(0)) if corrupt is None else
-                      (C.c_int(1), C.c_void_p(corrupt['alias'].ctypes.data), C.c_int(corrupt['kshift']), C.c_int(corrupt['alias'].shape[1]),
-                       C.c_void_p(corrupt['err'].ctypes.data), C.c_uint32(corrupt['k0']), C.c_uint32(corrupt['k1']))),
+                    *((C.c_int(0), None, C.c_int(6), C.c_int(0), C.c_int(0), C.c_uint32(0), C.c_uint32(0)) if corrupt is None else
+                      (C.c_int(1), C.c_void_p(corrupt['alias'].ctypes.data), C.c_int(corrupt['kshift']), C.c_int(corrupt['code9']),
+                       C.c_int(corrupt['alias'].shape[1]), C.c_uint32(corrupt['k0']), C.c_uint32(corrupt['k1']))),
                     C.c_int((12 if L <= 161 else 21 if L <= 305 else 0) if maxw is None else maxw))
   assert n >= 0, n
   return o1[:nb.value].tobytes(), o2[:nb.value].tobytes(), n
@@ -191,22 +191,46 @@ def test_corrupt_call_matches_oracle(emul):
     assert s.tobytes().decode() != seq
 
 
-@pytest.mark.parametrize('L,kshift,maxw', [(150, 6, 12), (150, 7, 0), (37, 6, 21), (5, 7, 12)])
-def test_fused_philox_corruption_matches_numpy_spec(emul, L, kshift, maxw):
-  """Fused production-mode corruption (inline in the emit path, alias rows + Philox) == the numpy
-  restatement of its draw layout applied to the perfect reads, incl. N / exception bases."""
+def test_token_numbers(emul):
+  """mg_put_num (branch-free decimal text, two tokens, any start phase) == str(v), and nothing outside
+  the written range is touched."""
+  out = (C.c_uint8 * 32)()
+  rs = np.random.RandomState(1)
+  vals = [0, 1, 9, 10, 99, 100, 999, 1000, 9999, 10000, 99999, 100000, 9999999, 10000000, 99999999, 100000000, 999999999,
+          1000000000, 2147483647, 4294967295, 249250621, 150] + [int(x) for x in rs.randint(0, 1 << 31, size=300)] + \
+         [int(10 ** rs.uniform(0, 9.6)) for _ in range(300)]
+  for k, v in enumerate(vals):
+    for pre in (b'', b'|', b'|1|', b',-'):
+      n = emul.emul_put_num(C.c_uint32(v), C.c_uint32(int.from_bytes(pre, 'little')), C.c_uint32(len(pre)), C.c_int(k % 4), out)
+      assert n >= 0 and bytes(out[:n]) == pre + str(v).encode(), (v, pre, n, bytes(out[:max(n, 0)]))
+
+
+@pytest.mark.parametrize('L,rows,maxw', [(150, 150, 12), (150, 300, 0), (37, 150, 21), (5, 300, 12), (150, 300, 12), (3, 150, 12), (2, 300, 0),
+                                         (4, 150, 12), (16, 150, 12), (17, 150, 0), (33, 150, 12), (161, 300, 12), (250, 300, 21)])
+def test_fused_philox_corruption_matches_numpy_spec(emul, L, rows, maxw):
+  """Fused production-mode corruption (inline in the emit path: one Philox word and one joint alias
+  lookup per base) == the numpy restatement of its draw layout applied to the perfect reads, incl.
+  N / exception bases.  rows = 150: 8-bit codes; rows = 300 includes the all-zero rows beyond the
+  model's max_rlen (quality 93): 9-bit codes."""
   from tests import philox_ref as PR
   m = H.model('hiseq-X-v2.5-Garvan.pkl')
-  assert PR.exact64_cycles(m['cum_bq_mat']) == 150
-  alias, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, kshift, n_rows=150)
-  # threshold + the two alias rows of a cycle encode the model's joint distribution of (quality,
-  # miscall): P(q) from the searchsorted-left outcomes, miscall with probability phred_p[q]
+  kshift, code9 = PR.table_shape(m['cum_bq_mat'], oracle.PHRED_P, rows)
+  assert code9 == (1 if rows > 150 else 0) and kshift == 7
+  alias = PR.joint_tables(m['cum_bq_mat'], oracle.PHRED_P, kshift, code9, n_rows=rows)
+  # a row encodes the model's joint distribution of (quality, substitution): P(q) from the
+  # searchsorted-left outcomes, a miscall with probability phred_p[q], each alternative a third of it
+  qb = 7 if code9 else 6
   for mate in (0, 1):
     pm = np.diff(np.concatenate([np.zeros((150, 1)), m['cum_bq_mat'][mate, :150, :]], axis=1), axis=1)
     for cyc in (0, 1, 75, 149):
-      ok, miss = PR.joint_distribution(alias[mate, cyc], err[mate, cyc], kshift)
-      assert np.abs(miss[:94] - pm[cyc] * oracle.PHRED_P[:94]).max() < 1e-8
-      assert np.abs(ok[:94] - pm[cyc] * (1.0 - oracle.PHRED_P[:94])).max() < 1e-8
+      d = PR.row_distribution(alias[mate, cyc], kshift, code9)
+      tol = 2.0 ** -(13 if code9 else 15)
+      assert code9 or pm[cyc][64:].sum() == 0.0
+      for q in range(94 if code9 else 64):
+        assert abs(d.get(q, 0.0) - pm[cyc][q] * (1.0 - oracle.PHRED_P[q])) < tol
+        for sub in (1, 2, 3):
+          assert abs(d.get((sub << qb) | q, 0.0) - pm[cyc][q] * oracle.PHRED_P[q] / 3.0) < tol
+      assert abs(sum(d.values()) - 1.0) < 1e-9
   regs = H.workload_regions(synth.edge_workload())
   r = regs[0]
   cv = H.oracle_cv(r['v'][1])
@@ -217,11 +241,11 @@ def test_fused_philox_corruption_matches_numpy_spec(emul, L, kshift, maxw):
   tl = rs.randint(L, 3 * L, size=n).astype(np.int64)
   fo = rs.randint(0, 2, size=n).astype(np.int8)
   p1, p2, cnt = run_emul(emul, lay, L, ts, tl, fo, '@E:0:0:', '|e|1', maxw=maxw)
-  cor = dict(alias=alias, kshift=kshift, err=err, k0=12345, k1=0xdeadbeef)
+  cor = dict(alias=alias, kshift=kshift, code9=code9, k0=12345, k1=0xdeadbeef)
   c1, c2, ccnt = run_emul(emul, lay, L, ts, tl, fo, '@E:0:0:', '|e|1', corrupt=cor, maxw=maxw)
   assert ccnt == cnt and cnt > 800
-  assert c1 == PR.corrupt_file(p1, 0, alias, kshift, err, cor['k0'], cor['k1'])
-  assert c2 == PR.corrupt_file(p2, 1, alias, kshift, err, cor['k0'], cor['k1'])
+  assert c1 == PR.corrupt_file(p1, 0, (alias, kshift, code9), cor['k0'], cor['k1'])
+  assert c2 == PR.corrupt_file(p2, 1, (alias, kshift, code9), cor['k0'], cor['k1'])
   assert c1 != p1 and b'N' in c1
 
 
@@ -252,9 +276,11 @@ def test_soft_masked_haplotype(emul, L, maxw):
       assert idx.check(info, lines[k + 1]) is None, (lines[k], lines[k + 1])
       low += sum(1 for ch in lines[k + 1] if ch.islower())
   assert low > 10000
-  alias, thr = PR.quality_tables(H.model('hiseq-X-v2.5-Garvan.pkl')['cum_bq_mat'], oracle.PHRED_P, 7, n_rows=150)
-  cor = dict(alias=alias, kshift=7, err=thr, k0=99, k1=0x1234)
+  cbm = H.model('hiseq-X-v2.5-Garvan.pkl')['cum_bq_mat']
+  ks, c9 = PR.table_shape(cbm, oracle.PHRED_P, 150)
+  alias = PR.joint_tables(cbm, oracle.PHRED_P, ks, c9, n_rows=150)
+  cor = dict(alias=alias, kshift=ks, code9=c9, k0=99, k1=0x1234)
   c1, c2, ccnt = run_emul(emul, lay, L, ts, tl, fo, '@S:0:0:', '|s|0', corrupt=cor, maxw=maxw)
   assert ccnt == cnt
-  assert c1 == PR.corrupt_file(p1, 0, alias, 7, thr, 99, 0x1234)
-  assert c2 == PR.corrupt_file(p2, 1, alias, 7, thr, 99, 0x1234)
+  assert c1 == PR.corrupt_file(p1, 0, (alias, ks, c9), 99, 0x1234)
+  assert c2 == PR.corrupt_file(p2, 1, (alias, ks, c9), 99, 0x1234)

@@ -604,7 +604,7 @@ def test_bench_unit_full_size_exact(eng):
   # fused corruption of the same unit vs the numpy specification, on every 100th record
   c1, c2, ccnt, _, cnb = eng.generate_unit(cp, n, rm['p'], MODE_PHILOX, seed, '@S:0:2:', '|1|1', corrupt=True, corrupt_seed=2000)
   assert ccnt == cnt and cnb == nb
-  tables = PR.fused_tables(eng, m, rm['rlen'])
+  tables = PR.fused_tables(eng, 0)
   for perfect, corrupted, f in ((f1, c1, 0), (f2, c2, 1)):
     nl = np.flatnonzero(perfect == 10)
     assert nl.size == 4 * cnt

@@ -176,12 +176,14 @@ def test_philox_large_unit_exact(eng):
 
 @pytest.mark.parametrize('wl_fn,cpy,model_name', [(synth.edge_workload, 1, 'hiseq-X-v2.5-Garvan.pkl'),
                                                   (synth.softmask_workload, 0, 'hiseq-X-v2.5-Garvan.pkl'),
-                                                  (synth.edge_workload, 0, '1kg-pcr-free.pkl'),   # 2x250: the wide register window
-                                                  (synth.edge_workload, 1, 'hiseq-X-v2.5-Garvan.pkl:200')])   # reads longer than max_rlen: 128-entry rows, BQ 93
+                                                  (synth.edge_workload, 0, '1kg-pcr-free.pkl'),   # 2x250: the wide register window, 256-entry rows
+                                                  (synth.edge_workload, 1, 'hiseq-2500-v1-pcr-free.pkl'),
+                                                  (synth.edge_workload, 1, 'hiseq-X-v2.5-Garvan.pkl:200')])   # reads longer than max_rlen: BQ 93, 9-bit codes
 def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy, model_name):
-  """Production-mode corruption is fully specified (Philox counters, per-cycle miscall thresholds,
-  alias rows): the fused emit kernel and the standalone corrupt kernel must reproduce the numpy
-  restatement of that specification byte for byte."""
+  """Production-mode corruption is fully specified (Philox counters, one joint alias row per (mate,
+  cycle)): the fused emit kernel and the standalone corrupt kernel must reproduce the numpy
+  restatement of that specification byte for byte, and the tables the library builds at load time
+  must equal the Python restatement of Vose's method."""
   import mitty_b200.simulation.illumina as il
   from mitty_b200.engine import MODE_PHILOX
   from tests import philox_ref as PR
@@ -190,19 +192,15 @@ def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy, model_name):
     m['mean_rlen'] = int(model_name.split(':')[1])       # legal: the path reads only mean_rlen (illumina.py:20)
   rm = il.read_model_params(m, 30.0)
   eng.load_model(rm)
-  # the tables the library built at load time == the Python restatement of Vose's method
-  n64_want = PR.exact64_cycles(m['cum_bq_mat'])
-  for kshift in (6, 7):
-    alias, n64, lthr = eng.model_tables(kshift)
-    assert n64 == n64_want
-    want, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, kshift, n_rows=n64 if kshift == 6 else None)
-    np.testing.assert_array_equal(alias, want)
-    if kshift == 7:
-      np.testing.assert_array_equal(lthr, err)
-  alias6 = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 6, n_rows=n64_want)[0]
-  alias7, err = PR.quality_tables(m['cum_bq_mat'], oracle.PHRED_P, 7)
-  ks_fused = 6 if rm['rlen'] <= n64_want else 7            # the emit kernel's choice (64-entry rows while they are exact)
-  alias_fused = alias6 if ks_fused == 6 else alias7
+  tabs = []
+  for which, rows in ((0, int(rm['rlen'])), (1, m['cum_bq_mat'].shape[1])):
+    alias, ks, c9 = eng.model_tables(which)
+    assert (ks, c9) == PR.table_shape(m['cum_bq_mat'], oracle.PHRED_P, rows)
+    np.testing.assert_array_equal(alias, PR.joint_tables(m['cum_bq_mat'], oracle.PHRED_P, ks, c9, n_rows=rows))
+    tabs.append((alias, ks, c9))
+  assert tabs[1][2] == 1                                 # the rows beyond max_rlen are quality 93
+  if ':' in model_name:
+    assert tabs[0][2] == 1
   r = H.workload_regions(wl_fn())[0]
   rid = eng.load_region(r['ref'], r['region'][1])
   cp = eng.build_copy(rid, r['v'][cpy])
@@ -212,14 +210,14 @@ def test_philox_corruption_exact_vs_numpy_spec(eng, wl_fn, cpy, model_name):
   c1, c2, ccnt, _, _ = eng.generate_unit(cp, n, 0.1, MODE_PHILOX, unit_seed, '@E:0:0:', '|e|1', corrupt=True, corrupt_seed=cseed)
   assert cnt == ccnt and cnt > 500
   k1 = unit_seed ^ 0x636f7231
-  assert c1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, alias_fused, ks_fused, err, cseed, k1)
-  assert c2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, alias_fused, ks_fused, err, cseed, k1)
+  assert c1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, tabs[0], cseed, k1)
+  assert c2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, tabs[0], cseed, k1)
   # standalone corrupt-reads over the same perfect reads
   eng.load_model(m)
   s1, s2, scnt = eng.corrupt_fastq(p1, p2, mode=MODE_PHILOX, seed=cseed)
   assert scnt == cnt
-  assert s1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, alias7, 7, err, cseed, 0x636f7232)
-  assert s2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, alias7, 7, err, cseed, 0x636f7232)
+  assert s1.tobytes() == PR.corrupt_file(p1.tobytes(), 0, tabs[1], cseed, 0x636f7232)
+  assert s2.tobytes() == PR.corrupt_file(p2.tobytes(), 1, tabs[1], cseed, 0x636f7232)
   eng.free_copy(cp); eng.free_region(rid)
 
 

@@ -299,8 +299,10 @@ struct MgSharedSpace {
 };
 #endif
 
-template <class SP> MG_NI void mg_store_tail(typename SP::ptr b, uint32_t carry, uint32_t nb) {
-  for (uint32_t i = 0; i < nb; i++) SP::st8(b + i, (uint8_t)(carry >> (8 * i)));
+template <class SP> MG_HD void mg_store_tail(typename SP::ptr b, uint32_t carry, uint32_t nb) {   // nb <= 3: three predicated stores
+  if (nb > 0) SP::st8(b, (uint8_t)carry);
+  if (nb > 1) SP::st8(b + 1, (uint8_t)(carry >> 8));
+  if (nb > 2) SP::st8(b + 2, (uint8_t)(carry >> 16));
 }
 
 // A token: n <= 8 bytes, first byte in the lowest byte of lo; the bytes beyond n are zero.
@@ -421,6 +423,24 @@ MG_HD void mg_put_num(MgStream<SP> &w, uint32_t v, uint32_t pre, uint32_t npre) 
   MgTok A, B;
   mg_tok_num(v, pre, npre, A, B);
   w.append(A); w.append(B);
+}
+
+// the same for the numbers that are almost always small (CIGAR lengths, variant sizes): below 10^4
+// it is one token -- pre (<= 3 bytes) + at most four digits
+template <class SP>
+MG_HD void mg_put_small(MgStream<SP> &w, uint32_t v, uint32_t pre, uint32_t npre) {
+  if (v >= 10000u) { mg_put_num(w, v, pre, npre); return; }
+  const uint32_t d = mg_dec4(v), x = d ^ 0x30303030u;
+  uint32_t lz;                                               // leading '0' bytes, at most 3 (v == 0 prints "0")
+#if defined(__CUDA_ARCH__)
+  lz = (x & 0x00FFFFFFu) ? ((uint32_t)__ffs((int)x) - 1u) >> 3 : 3u;
+#else
+  lz = (x & 0x00FFFFFFu) ? ((uint32_t)__builtin_ctz(x)) >> 3 : 3u;
+#endif
+  const uint32_t dig = d >> (8u * lz), ps = 8u * npre;
+  MgTok t;
+  t.lo = pre | (dig << ps); t.hi = mg_funnel_l(dig, 0u, ps); t.n = npre + 4u - lz;
+  w.append(t);
 }
 
 MG_HD MgTok mg_tok(uint32_t lo, uint32_t hi, uint32_t n) { MgTok t; t.lo = lo; t.hi = hi; t.n = n; return t; }
@@ -613,26 +633,31 @@ MG_HD void mg_put_read(MgStream<SP> &w, const MgQnConst &Q, NP nodes, MgReadRef 
     return;
   }
   if (single && f.op == 'I') {                                               // rpc.py:154  ">p:<L>I" and "|<oplen>"
-    mg_put_num(w, (uint32_t)((int64_t)R.x - (int64_t)f.key), '>', 1u);
-    mg_put_num(w, (uint32_t)L, ':', 1u);
-    mg_put_num(w, (uint32_t)f.oplen, (uint32_t)'I' | ((uint32_t)'|' << 8), 2u);
+    mg_put_small(w, (uint32_t)((int64_t)R.x - (int64_t)f.key), '>', 1u);
+    mg_put_small(w, (uint32_t)L, ':', 1u);
+    mg_put_small(w, (uint32_t)f.oplen, (uint32_t)'I' | ((uint32_t)'|' << 8), 2u);
     return;
   }
+  // the read spans several nodes (or sits on one that is not '='): the first three are fetched at once
+  // -- one memory latency instead of one per step of the two walks below
+  const int k1 = R.n0 + 1 <= R.n1 ? R.n0 + 1 : R.n1, k2 = R.n0 + 2 <= R.n1 ? R.n0 + 2 : R.n1;
+  const MgNode c1 = nodes[k1], c2 = nodes[k2];
+  auto node_at = [&](int k) -> MgNode { const int d = k - R.n0; if (d == 0) return f; if (d == 1) return c1; if (d == 2) return c2; return nodes[k]; };
   uint32_t pre = 0, npre = 0;
   for (int k = R.n0; k <= R.n1; k++) {                                       // rpc.py:145: <len><op> per node
-    const MgNode n = nodes[k];
-    mg_put_num(w, (uint32_t)mg_cigar_len(n, R.x, L), pre, npre);
+    const MgNode n = node_at(k);
+    mg_put_small(w, (uint32_t)mg_cigar_len(n, R.x, L), pre, npre);
     pre = n.op; npre = 1;
   }
   pre |= (uint32_t)'|' << 8; npre = 2;                                       // last op, then the field separator
   bool firstv = true;
   for (int k = R.n0; k <= R.n1; k++) {                                       // rpc.py:144: v_list
-    const MgNode n = nodes[k];
+    const MgNode n = node_at(k);
     if (n.op == '=') continue;
     if (!firstv) { pre = ','; npre = 1; }
     firstv = false;
     if (n.op == 'D') { pre |= (uint32_t)'-' << (8 * npre); npre++; }
-    mg_put_num(w, n.op == 'X' ? 0u : (uint32_t)n.oplen, pre, npre);
+    mg_put_small(w, n.op == 'X' ? 0u : (uint32_t)n.oplen, pre, npre);
     npre = 0; pre = 0;
   }
   if (npre) w.append(mg_tok(pre, 0, npre));                                  // no variant at all (cannot happen here: the read spans > 1 node)
@@ -834,8 +859,8 @@ MG_HD void mg_emit_seq_src(WR &w, MgSeqSrc<MAXW, HP> &S) {
   const int L = S.L;
   mg_for_each_chunk(S, [&](uint32_t codes, int c) {
     if (16 * c + 16 <= L) {              // a whole chunk: four words, no bounds logic
-      MG_NOUNROLL
-      for (int q = 0; q < 4; q++, codes >>= 8) w.put_word(mg_chars4(codes & 0xFFu));
+      MG_UNROLL
+      for (int q = 0; q < 4; q++) w.put_word(mg_chars4((codes >> (8 * q)) & 0xFFu));
       return;
     }
     MG_NOUNROLL
@@ -906,8 +931,9 @@ MG_HD void mg_emit_frame_seps(typename SP::ptr dst, uint32_t qlen, int L) {
 // (0-based count within the unit; 64-bit template index of the whole file for corrupt-reads), file f
 // and cycle group g = n / 4,
 //     r = Philox4x32-7(counter = (t_lo, 2 t_hi + f, g, MG_STREAM_CORRUPT), key = (k0, k1)),  w = r[n % 4]
-//     e = alias[((f * n_cycles + n) << kshift) | (w >> (32 - kshift))]
-//     take = (w << kshift  mod 2^32) < e          (e's top bits are the acceptance threshold)
+//     e = alias[((f * n_cycles + n) << kshift) | (w & (2^kshift - 1))]        (the entry: w's LOW bits)
+//     take = w < e                                (e's top bits are the acceptance threshold: w's HIGH bits decide,
+//                                                  independently of the low ones up to 2^(kshift - 32))
 //     code = take ? e's SELF field : e's ALIAS field,   fields of 8 bits (s << 6 | q, all q < 64):
 //            e = thr16 << 16 | self8 << 8 | alias8,  or of 9 bits (s << 7 | q): e = thr14 << 18 | self9 << 9 | alias9
 //     quality = code's q;  an A/C/G/T base becomes "ACGT"[code_of_base ^ s]; any other byte (N, IUPAC,
@@ -921,8 +947,8 @@ struct MgCorruptCtx {
 // outcome code of one base: bits 0..(6|7) the quality, the two bits above the substitution
 template <bool C9>
 MG_HD uint32_t mg_corrupt_code(const uint32_t *alias, uint32_t ks, uint32_t row, uint32_t w) {
-  const uint32_t e = alias[mg_funnel_l(w, row, ks)];
-  const bool take = (w << ks) < e;
+  const uint32_t e = alias[(row << ks) | (w & ((1u << ks) - 1u))];
+  const bool take = w < e;
   return C9 ? ((take ? e >> 9 : e) & 0x1FFu) : ((take ? e >> 8 : e) & 0xFFu);
 }
 
@@ -946,11 +972,12 @@ struct MgGrp { uint32_t w[4], e[4], b4; };
 template <bool FULL>   // FULL: all four cycles are inside the read
 MG_HD void mg_grp_draw(const MgCorruptCtx &C, uint32_t ks, uint32_t t_lo, uint32_t t_hi2f, uint32_t row0, int n0, int L, MgGrp &G) {
   const MgPhilox r = mg_philox_corrupt(t_lo, t_hi2f, (uint32_t)(n0 >> 2), C.k0, C.k1);
+  const uint32_t mask = (1u << ks) - 1u;
   MG_UNROLL
   for (int j = 0; j < 4; j++) {
     G.w[j] = r.v[j];
     const uint32_t rj = row0 + ((FULL || n0 + j < L) ? (uint32_t)j : 0u);    // stay inside the table at the read's end
-    G.e[j] = C.alias[mg_funnel_l(G.w[j], rj, ks)];
+    G.e[j] = C.alias[(rj << ks) | (G.w[j] & mask)];
   }
 }
 
@@ -959,7 +986,7 @@ MG_HD void mg_grp_decode(const MgGrp &G, uint32_t ks, uint32_t &q4, uint32_t &sn
   if constexpr (!C9) {
     uint32_t c[4];
     MG_UNROLL
-    for (int j = 0; j < 4; j++) c[j] = ((G.w[j] << ks) < G.e[j]) ? G.e[j] >> 8 : G.e[j];
+    for (int j = 0; j < 4; j++) c[j] = (G.w[j] < G.e[j]) ? G.e[j] >> 8 : G.e[j];
     const uint32_t t4 = mg_prmt2(mg_prmt2(c[0], c[1], 0x0040u), mg_prmt2(c[2], c[3], 0x0040u), 0x5410u);   // the four code bytes
     q4 = (t4 & 0x3F3F3F3Fu) + 0x21212121u;
     uint32_t u = (t4 >> 6) & 0x03030303u;                 // s_j in bits 8j, 8j+1 -> bits 4j, 4j+1
@@ -969,7 +996,7 @@ MG_HD void mg_grp_decode(const MgGrp &G, uint32_t ks, uint32_t &q4, uint32_t &sn
     q4 = 0x21212121u; snib = 0;
     MG_UNROLL
     for (int j = 0; j < 4; j++) {
-      const uint32_t c = (((G.w[j] << ks) < G.e[j]) ? G.e[j] >> 9 : G.e[j]) & 0x1FFu;
+      const uint32_t c = ((G.w[j] < G.e[j]) ? G.e[j] >> 9 : G.e[j]) & 0x1FFu;
       q4 += (c & 127u) << (8 * j);
       snib |= (c >> 7) << (4 * j);
     }

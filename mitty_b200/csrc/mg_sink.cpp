@@ -1,0 +1,306 @@
+// Output sink of generate-reads / corrupt-reads: the reference's FASTQ writer process
+// (mitty/simulation/readgenerate.py:233-253, readcorrupt.py:100-118) and the `>(gzip > r1.fq.gz)`
+// it is always piped into (Readme.md:170, examples/reads/run.sh:15-16) as native threads inside the
+// library -- no GIL, no Python objects.
+//
+// Producers (one per GPU) fill page-locked slot pairs (file 1 / file 2 bytes of one piece of a work
+// unit) from their OWN pool and commit them with (unit, offset in the unit).  The files are written in
+// SCHEDULE order, whatever the order of arrival:
+//   plain, seekable target   pwrite() at base[unit] + offset by any writer thread, as soon as the sizes of
+//                            all earlier units are known (a unit's size is announced right after its kernels)
+//   plain, FIFO / pipe       sequential write(), one piece at a time per file, in (unit, offset) order
+//   gzip                     pieces are deflated in parallel (one gzip member per piece, zlib), the members
+//                            appended in order: the file is a valid multi-member .gz (what bgzip / pigz write)
+// A slot goes back to its producer's pool when both of its pieces are on disk (plain) or deflated (gzip).
+// Deadlock freedom: every producer works through its units in increasing schedule order and announces a
+// unit's size before asking for a slot, and pools are per producer; so the lowest unfinished unit always
+// has its base offset known and slots to travel in.
+#include <cuda_runtime.h>
+#include <zlib.h>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mitty_b200.h"
+
+namespace {
+
+struct Slot { uint8_t *buf[2]; int producer; int refs; };
+
+struct Piece {                 // one file's share of a committed slot
+  int file; int64_t unit, off, bytes;
+  const uint8_t *data; Slot *slot;
+  std::vector<uint8_t> z;      // gzip: the deflated member
+  bool deflated = false;
+};
+
+}  // namespace
+
+struct mg_sink {
+  int fd[2] = {-1, -1};
+  bool seekable[2] = {false, false};
+  int n_files = 0, gzip = 0;
+  int64_t n_units = 0, chunk = 0;
+  std::vector<int64_t> size, base;         // per unit: bytes per file (-1 unknown), offset of its first byte
+  int64_t known = 0;                       // sizes of units [0, known) are known -> base[0..known] are valid
+  std::vector<std::vector<Slot *>> pool;   // free slots per producer
+  std::vector<Slot *> all_slots;
+  std::deque<Piece *> ready;               // plain + seekable: writable now; gzip: to be deflated
+  std::multimap<int64_t, Piece *> waiting; // plain + seekable: base of the unit not known yet
+  std::map<std::pair<int64_t, int64_t>, Piece *> ordered[2];   // sequential targets: (unit, off) -> piece (deflated if gzip)
+  int64_t cur_unit[2] = {0, 0}, cur_off[2] = {0, 0};
+  bool writing[2] = {false, false};        // one sequential writer per file at a time
+  int64_t written[2] = {0, 0};
+  std::mutex mu;
+  std::condition_variable cv_work, cv_slot, cv_idle;
+  std::vector<std::thread> threads;
+  int64_t in_flight = 0;                   // committed pieces not yet written
+  bool closing = false, failed = false;
+  std::string err;
+};
+
+namespace {
+
+void fail(mg_sink *s, const char *fmt, ...) {          // with s->mu held
+  if (s->failed) return;
+  char b[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof b, fmt, ap); va_end(ap);
+  s->err = b; s->failed = true;
+  s->cv_work.notify_all(); s->cv_slot.notify_all(); s->cv_idle.notify_all();
+}
+
+bool write_all(int fd, const uint8_t *p, int64_t n, int64_t off, bool positional) {
+  while (n > 0) {
+    const size_t want = (size_t)(n > (1 << 30) ? (1 << 30) : n);
+    const ssize_t w = positional ? pwrite(fd, p, want, (off_t)off) : write(fd, p, want);
+    if (w < 0) { if (errno == EINTR) continue; return false; }
+    p += w; n -= w; off += w;
+  }
+  return true;
+}
+
+void release(mg_sink *s, Piece *p) {                   // with s->mu held
+  if (p->slot && --p->slot->refs == 0) { s->pool[(size_t)p->slot->producer].push_back(p->slot); s->cv_slot.notify_all(); }
+  p->slot = nullptr;
+}
+
+bool sequential(const mg_sink *s, int f) { return s->gzip || !s->seekable[f]; }
+
+// skip units that are known to be empty / finished on a sequential target
+void advance(mg_sink *s, int f) {                       // with s->mu held
+  while (s->cur_unit[f] < s->n_units && s->size[(size_t)s->cur_unit[f]] >= 0 && s->cur_off[f] >= s->size[(size_t)s->cur_unit[f]]) {
+    s->cur_unit[f]++; s->cur_off[f] = 0;
+  }
+}
+
+void deflate_piece(Piece *p, int level) {
+  z_stream z; memset(&z, 0, sizeof z);
+  deflateInit2(&z, level, Z_DEFLATED, 15 + 16 /* gzip wrapper */, 8, Z_DEFAULT_STRATEGY);
+  p->z.resize(deflateBound(&z, (uLong)p->bytes) + 64);
+  z.next_in = const_cast<Bytef *>(p->data); z.avail_in = (uInt)p->bytes;
+  z.next_out = p->z.data(); z.avail_out = (uInt)p->z.size();
+  deflate(&z, Z_FINISH);
+  p->z.resize(p->z.size() - z.avail_out);
+  deflateEnd(&z);
+}
+
+void worker(mg_sink *s) {
+  std::unique_lock<std::mutex> lk(s->mu);
+  while (true) {
+    Piece *p = nullptr; int seq_file = -1;
+    // 1. a sequential target whose next piece has arrived (and, for gzip, is deflated)
+    for (int f = 0; f < s->n_files && !p; f++) {
+      if (!sequential(s, f) || s->writing[f]) continue;
+      advance(s, f);
+      auto it = s->ordered[f].find({s->cur_unit[f], s->cur_off[f]});
+      if (it != s->ordered[f].end() && (!s->gzip || it->second->deflated)) { p = it->second; s->ordered[f].erase(it); s->writing[f] = true; seq_file = f; }
+    }
+    // 2. anything in the ready queue (positional write, or a piece to deflate)
+    if (!p && !s->ready.empty()) { p = s->ready.front(); s->ready.pop_front(); }
+    if (!p) {
+      if (s->failed || (s->closing && s->in_flight == 0)) return;
+      s->cv_work.wait(lk);
+      continue;
+    }
+    if (s->failed) { release(s, p); delete p; s->in_flight--; if (seq_file >= 0) s->writing[seq_file] = false; s->cv_idle.notify_all(); continue; }
+    if (seq_file >= 0) {                                 // ordered append
+      lk.unlock();
+      const bool ok = s->gzip ? write_all(s->fd[seq_file], p->z.data(), (int64_t)p->z.size(), 0, false)
+                              : write_all(s->fd[seq_file], p->data, p->bytes, 0, false);
+      const int e = errno;
+      lk.lock();
+      s->writing[seq_file] = false;
+      if (!ok) fail(s, "write to FASTQ file %d failed: %s", seq_file + 1, strerror(e));
+      s->written[seq_file] += s->gzip ? (int64_t)p->z.size() : p->bytes;
+      s->cur_off[seq_file] += p->bytes;
+      if (!s->gzip) release(s, p);
+      delete p; s->in_flight--;
+      s->cv_work.notify_all(); s->cv_idle.notify_all();
+    } else if (s->gzip) {                                // deflate, then queue for the ordered append
+      lk.unlock();
+      deflate_piece(p, s->gzip);
+      lk.lock();
+      p->deflated = true; p->data = nullptr;
+      release(s, p);                                     // the pinned slot is free as soon as its bytes are deflated
+      s->ordered[p->file][{p->unit, p->off}] = p;
+      s->cv_work.notify_all();
+    } else {                                             // positional write
+      const int64_t at = s->base[(size_t)p->unit] + p->off;
+      lk.unlock();
+      const bool ok = write_all(s->fd[p->file], p->data, p->bytes, at, true);
+      const int e = errno;
+      lk.lock();
+      if (!ok) fail(s, "write to FASTQ file %d failed: %s", p->file + 1, strerror(e));
+      s->written[p->file] += p->bytes;
+      release(s, p);
+      delete p; s->in_flight--;
+      s->cv_idle.notify_all();
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mg_sink_create(const char *path1, const char *path2, int64_t n_units, int32_t n_producers, int32_t slots_per_producer,
+                   int64_t chunk_bytes, int32_t gzip_level, int32_t n_threads, mg_sink **out) {
+  if (!out || !path1 || n_units < 0 || n_producers < 1 || slots_per_producer < 2 || chunk_bytes < 1 || gzip_level < 0 || gzip_level > 9 ||
+      chunk_bytes > (1ll << 31) - 65536) return MG_EINVAL;
+  *out = nullptr;
+  mg_sink *s = new mg_sink();
+  s->n_units = n_units; s->chunk = chunk_bytes; s->gzip = gzip_level;
+  s->size.assign((size_t)n_units, -1); s->base.assign((size_t)n_units + 1, 0);
+  const char *paths[2] = {path1, path2};
+  for (int f = 0; f < 2; f++) {
+    if (!paths[f]) break;
+    // O_TRUNC only means something for regular files; FIFOs and /dev/fd/N open as they are ('w' of the reference's writer)
+    s->fd[f] = open(paths[f], O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0666);
+    if (s->fd[f] < 0) {
+      fprintf(stderr, "mitty_b200: cannot open %s for writing: %s\n", paths[f], strerror(errno));
+      for (int g = 0; g < f; g++) close(s->fd[g]);
+      delete s;
+      return MG_EVALUE;
+    }
+    struct stat st;
+    s->seekable[f] = fstat(s->fd[f], &st) == 0 && S_ISREG(st.st_mode);
+    s->n_files = f + 1;
+  }
+  s->pool.resize((size_t)n_producers);
+  for (int p = 0; p < n_producers; p++)
+    for (int k = 0; k < slots_per_producer; k++) {
+      Slot *sl = new Slot();
+      sl->producer = p; sl->refs = 0; sl->buf[0] = sl->buf[1] = nullptr;
+      for (int f = 0; f < s->n_files; f++)
+        if (cudaHostAlloc((void **)&sl->buf[f], (size_t)chunk_bytes, cudaHostAllocPortable) != cudaSuccess) {
+          fprintf(stderr, "mitty_b200: cannot page-lock %lld bytes for the output sink\n", (long long)chunk_bytes);
+          cudaGetLastError();
+          s->all_slots.push_back(sl);
+          mg_sink_close(s, nullptr, nullptr);
+          return MG_ECUDA;
+        }
+      s->all_slots.push_back(sl);
+      s->pool[(size_t)p].push_back(sl);
+    }
+  if (n_threads < 1) n_threads = 1;
+  for (int t = 0; t < n_threads; t++) s->threads.emplace_back(worker, s);
+  *out = s;
+  return MG_OK;
+}
+
+const char *mg_sink_error(mg_sink *s) { return s ? s->err.c_str() : "null sink"; }
+
+int mg_sink_unit_size(mg_sink *s, int64_t unit, int64_t bytes_per_file) {
+  if (!s || unit < 0 || unit >= s->n_units || bytes_per_file < 0) return MG_EINVAL;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->failed) return MG_EVALUE;
+  if (s->size[(size_t)unit] >= 0) { fail(s, "unit %lld announced twice", (long long)unit); return MG_EINVAL; }
+  s->size[(size_t)unit] = bytes_per_file;
+  while (s->known < s->n_units && s->size[(size_t)s->known] >= 0) {
+    s->base[(size_t)s->known + 1] = s->base[(size_t)s->known] + s->size[(size_t)s->known];
+    s->known++;
+  }
+  for (auto it = s->waiting.begin(); it != s->waiting.end() && it->first < s->known;) { s->ready.push_back(it->second); it = s->waiting.erase(it); }
+  s->cv_work.notify_all();
+  return MG_OK;
+}
+
+int mg_sink_acquire(mg_sink *s, int32_t producer, void **buf1, void **buf2, void **slot) {
+  if (!s || !slot || producer < 0 || (size_t)producer >= s->pool.size()) return MG_EINVAL;
+  std::unique_lock<std::mutex> lk(s->mu);
+  while (s->pool[(size_t)producer].empty() && !s->failed) s->cv_slot.wait(lk);
+  if (s->failed) return MG_EVALUE;
+  Slot *sl = s->pool[(size_t)producer].back(); s->pool[(size_t)producer].pop_back();
+  if (buf1) *buf1 = sl->buf[0];
+  if (buf2) *buf2 = sl->buf[1];
+  *slot = sl;
+  return MG_OK;
+}
+
+int mg_sink_commit(mg_sink *s, void *slot, int64_t unit, int64_t offset, int64_t bytes) {
+  if (!s || !slot || unit < 0 || unit >= s->n_units || offset < 0 || bytes < 0 || bytes > s->chunk) return MG_EINVAL;
+  Slot *sl = static_cast<Slot *>(slot);
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->failed || bytes == 0) { s->pool[(size_t)sl->producer].push_back(sl); s->cv_slot.notify_all(); return s->failed ? MG_EVALUE : MG_OK; }
+  if (s->size[(size_t)unit] < 0 || offset + bytes > s->size[(size_t)unit]) { fail(s, "piece of unit %lld outside its announced size", (long long)unit); return MG_EINVAL; }
+  sl->refs = s->n_files;
+  for (int f = 0; f < s->n_files; f++) {
+    Piece *p = new Piece();
+    p->file = f; p->unit = unit; p->off = offset; p->bytes = bytes; p->data = sl->buf[f]; p->slot = sl;
+    s->in_flight++;
+    if (s->gzip) s->ready.push_back(p);                                        // deflate first
+    else if (!s->seekable[f]) s->ordered[f][{unit, offset}] = p;
+    else if (unit < s->known) s->ready.push_back(p);
+    else s->waiting.insert({unit, p});
+  }
+  s->cv_work.notify_all();
+  return MG_OK;
+}
+
+void mg_sink_abort(mg_sink *s, const char *why) {
+  if (!s) return;
+  std::lock_guard<std::mutex> lk(s->mu);
+  fail(s, "%s", why ? why : "aborted");
+}
+
+int mg_sink_close(mg_sink *s, int64_t *written1, int64_t *written2) {
+  if (!s) return MG_EINVAL;
+  {
+    std::unique_lock<std::mutex> lk(s->mu);
+    while (s->in_flight > 0 && !s->failed) s->cv_idle.wait(lk);
+    if (!s->failed)
+      for (int64_t u = 0; u < s->n_units; u++)
+        if (s->size[(size_t)u] < 0) { fail(s, "unit %lld was never written", (long long)u); break; }
+    s->closing = true;
+    s->cv_work.notify_all();
+  }
+  for (auto &t : s->threads) t.join();
+  const bool failed = s->failed;
+  if (written1) *written1 = s->written[0];
+  if (written2) *written2 = s->written[1];
+  for (int f = 0; f < s->n_files; f++) if (s->fd[f] >= 0 && close(s->fd[f]) != 0 && !failed) { s->err = std::string("close: ") + strerror(errno); }
+  for (auto &kv : s->waiting) delete kv.second;
+  for (Piece *p : s->ready) delete p;
+  for (int f = 0; f < 2; f++) for (auto &kv : s->ordered[f]) delete kv.second;
+  for (Slot *sl : s->all_slots) { for (int f = 0; f < 2; f++) if (sl->buf[f]) cudaFreeHost(sl->buf[f]); delete sl; }
+  const int rc = failed || !s->err.empty() ? MG_EVALUE : MG_OK;
+  if (rc != MG_OK) fprintf(stderr, "mitty_b200: output sink: %s\n", s->err.c_str());
+  delete s;
+  return rc;
+}
+
+}  // extern "C"

@@ -104,12 +104,12 @@ void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0
 uint64_t emul_digit_sum(uint64_t m) { return mg_digit_sum(m); }
 
 // pre (npre bytes) + decimal digits of v through the token path -> bytes written
-int emul_put_num(uint32_t v, uint32_t pre, uint32_t npre, int phase, uint8_t *out) {
+int emul_put_num(uint32_t v, uint32_t pre, uint32_t npre, int phase, uint8_t *out, int small) {
   uint8_t buf[64];
   memset(buf, 0xEE, sizeof buf);
   MgStream<MgGenericSpace> w;
   w.begin(buf + 8 + phase);
-  mg_put_num(w, v, pre, npre);
+  if (small) mg_put_small(w, v, pre, npre); else mg_put_num(w, v, pre, npre);
   uint8_t *wp = w.wp; uint32_t sh = w.sh;
   w.end();
   const int n = (int)(wp - (buf + 8 + phase)) + (int)(sh >> 3);   // wp is word aligned: negative part = the start's own phase

@@ -129,7 +129,7 @@ def joint_tables(cum_bq_mat, phred_p, kshift, code9, n_rows=None):
 
 def row_distribution(alias_row, kshift, code9):
   """{code: probability} encoded by one alias row (exact rational arithmetic on the 32-bit entries:
-  take iff (w << kshift mod 2^32) < e, w uniform)."""
+  take iff w < e, w uniform)."""
   K = 1 << kshift
   cb = 9 if code9 else 8
   p = {}
@@ -175,9 +175,9 @@ def corrupt_file(fq, f, tables, k0, k1, serials=None):
     seq = bytearray(lines[4 * rec + 1])
     Lr = len(seq)
     w = w_all[rec, :Lr].astype(np.uint64)
-    idx = (w >> np.uint64(32 - kshift)).astype(np.int64)
+    idx = (w & np.uint64((1 << kshift) - 1)).astype(np.int64)          # the entry: w's low bits
     e = flat[(np.arange(Lr, dtype=np.int64) << kshift) | idx]
-    take = ((w << np.uint64(kshift)) & MASK) < e
+    take = w < e                                                       # the threshold sits in e's top bits: w's high bits decide
     code = np.where(take, e >> np.uint64(cb), e) & np.uint64((1 << cb) - 1)
     q = (code & np.uint64((1 << qb) - 1)).astype(np.int64)
     s = (code >> np.uint64(qb)).astype(np.int64)

@@ -201,8 +201,9 @@ def test_token_numbers(emul):
          [int(10 ** rs.uniform(0, 9.6)) for _ in range(300)]
   for k, v in enumerate(vals):
     for pre in (b'', b'|', b'|1|', b',-'):
-      n = emul.emul_put_num(C.c_uint32(v), C.c_uint32(int.from_bytes(pre, 'little')), C.c_uint32(len(pre)), C.c_int(k % 4), out)
-      assert n >= 0 and bytes(out[:n]) == pre + str(v).encode(), (v, pre, n, bytes(out[:max(n, 0)]))
+      for small in (0, 1):
+        n = emul.emul_put_num(C.c_uint32(v), C.c_uint32(int.from_bytes(pre, 'little')), C.c_uint32(len(pre)), C.c_int(k % 4), out, C.c_int(small))
+        assert n >= 0 and bytes(out[:n]) == pre + str(v).encode(), (v, pre, n, small, bytes(out[:max(n, 0)]))
 
 
 @pytest.mark.parametrize('L,rows,maxw', [(150, 150, 12), (150, 300, 0), (37, 150, 21), (5, 300, 12), (150, 300, 12), (3, 150, 12), (2, 300, 0),

@@ -575,8 +575,8 @@ def test_generate_reads_without_fastq2(tmp_path):
 @pytest.mark.timeout(1500)
 def test_bench_unit_full_size_exact(eng):
   """ONE unit of exactly the workload bench.py's number is quoted on -- synth.chr1_shaped(seed=7,
-  length=249250621), copy 1, Philox mode, perfect reads: 5.7 M templates, 4.3 GB per file, byte
-  offsets above 2^32, template starts near 2.5e8 -- against the oracle fed with the device's own
+  length=249250621), copy 1, Philox mode, perfect reads: 5.7 M templates, 2.1 GB per file (4.2 GB per
+  launch), template starts near 2.5e8 -- against the oracle fed with the device's own
   draws: count and sha256 of both files.  (About 75 s of oracle time.)  The fused-corruption twin of
   the same unit is then checked against the numpy specification on a 1 % sample of its records."""
   import hashlib
@@ -595,7 +595,7 @@ def test_bench_unit_full_size_exact(eng):
   ts, te, fo = eng.sample_templates(n, rm['p'], MODE_PHILOX, seed, cp=cp)
   keep = te >= 0
   f1, f2, cnt, nk, nb = eng.generate_unit(cp, n, rm['p'], MODE_PHILOX, seed, '@S:0:2:', '|1|1')
-  assert nb > (1 << 32) and cnt > 5000000 and cnt < nk
+  assert nb > 2000000000 and cnt > 5000000 and cnt < nk
   o1, o2, ocnt = oracle.generate_unit(r['ref'], 1, H.oracle_cv(r['v'][1]), rm['rlen'], ts[keep], te[keep], fo[keep], 'S:0:2', '1', 1,
                                       cap=int(nb) + 4096)
   assert cnt == ocnt and len(o1) == nb == f1.size

@@ -130,6 +130,45 @@ int mg_wait_copies(mg_ctx *ctx);
  * chunk.                                                                                          */
 int mg_unit_read_async(mg_ctx *ctx, int32_t file, int64_t offset, int64_t bytes, uint8_t *dst);
 
+/* ---- output sink: replaces the FASTQ writer process (mitty/simulation/readgenerate.py:233-253,
+ * readcorrupt.py:100-118) and the `>(gzip > r1.fq.gz)` the reference is piped into (Readme.md:170).
+ * Native writer threads: producers (one per GPU) fill page-locked slot pairs from their own pool and
+ * commit them with (unit, offset); the files receive the units in SCHEDULE order whatever the order of
+ * arrival -- pwrite() at the final offset for regular files, ordered sequential writes for FIFOs /
+ * pipes, and with gzip_level > 0 one deflated gzip member per piece, appended in order (a valid
+ * multi-member .gz).  path2 may be NULL (`generate-reads` without --fastq2: only file 1 is written).   */
+typedef struct mg_sink mg_sink;
+int mg_sink_create(const char *path1, const char *path2, int64_t n_units, int32_t n_producers, int32_t slots_per_producer,
+                   int64_t chunk_bytes, int32_t gzip_level, int32_t n_threads, mg_sink **out);
+/* the same for several PROCESSES sharing one pair of (regular) output files, e.g. one rank per GPU:
+ * table_path names a small file (on /dev/shm) that carries the unit sizes and the next-unit counter;
+ * the process with table_owner = 1 creates it and truncates the outputs, the others open both after a
+ * barrier of the callers.  Plain output to regular files only.                                       */
+int mg_sink_create_shared(const char *path1, const char *path2, int64_t n_units, int32_t n_producers, int32_t slots_per_producer,
+                          int64_t chunk_bytes, int32_t gzip_level, int32_t n_threads, const char *table_path, int32_t table_owner,
+                          mg_sink **out);
+/* hands out the schedule's units one by one (to threads or, with a shared table, to processes): the
+ * next unit index, or -1 when all are taken.  Whoever takes a unit must announce its size.            */
+int64_t mg_sink_next_unit(mg_sink *s);
+/* bytes per file of a unit: announced once per unit (0 for an empty one), before its pieces          */
+int mg_sink_unit_size(mg_sink *s, int64_t unit, int64_t bytes_per_file);
+/* a free slot pair of the producer's pool (blocks while all are in flight)                           */
+int mg_sink_acquire(mg_sink *s, int32_t producer, void **buf1, void **buf2, void **slot);
+/* bytes [offset, offset + bytes) of `unit` (both files) are in the slot: write them, recycle the slot  */
+int mg_sink_commit(mg_sink *s, void *slot, int64_t unit, int64_t offset, int64_t bytes);
+void mg_sink_abort(mg_sink *s, const char *why);   /* wakes every blocked producer with an error       */
+const char *mg_sink_error(mg_sink *s);
+int64_t mg_sink_chunk_bytes(mg_sink *s);          /* bytes per slot, as given at creation             */
+/* waits for everything committed, closes the files, frees the sink; bytes written per file           */
+int mg_sink_close(mg_sink *s, int64_t *written1, int64_t *written2);
+
+/* streams the MOST RECENT unit of ctx (generated with out1 = out2 = NULL: its bytes are still on the
+ * device) into the sink as schedule unit `unit`: announces its size and returns; a thread of the
+ * context copies it out piece by piece (copy stream) while the caller generates the next unit.  The
+ * unit after next waits for this one's device buffers.  mg_drain_wait: everything queued is committed. */
+int mg_unit_drain_async(mg_ctx *ctx, mg_sink *sink, int32_t producer, int64_t unit);
+int mg_drain_wait(mg_ctx *ctx);
+
 /* ---- corrupt-reads: replaces readcorrupt.multi_process / illumina.corrupt_template
  * (mitty/simulation/readcorrupt.py:18-118, illumina.py:113-162) over whole FASTQ buffers.
  * in2/out2 may be NULL (single-end).  DET mode consumes the reference's draws: for read k (file-1

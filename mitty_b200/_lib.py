@@ -11,10 +11,10 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libmitty_b200.so')
-SOURCES = ['mg_api.cu', 'mg_kernels.cu']
-HEADERS = ['mg_core.cuh', 'mg_internal.h', os.path.join('..', '..', 'include', 'mitty_b200.h')]
+SOURCES = ['mg_api.cu', 'mg_kernels.cu', 'mg_sink.cpp']
+HEADERS = ['mg_core.cuh', 'mg_internal.h', 'mg_sink.cpp', os.path.join('..', '..', 'include', 'mitty_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC', '-shared', '-lz']
 
 MG_OK, MG_ECUDA, MG_EINVAL, MG_ECAP, MG_EVALUE, MG_EINDEX = 0, -1, -2, -3, -4, -5
 MODE_PHILOX, MODE_DET, MODE_EXPLICIT = 0, 1, 2
@@ -23,7 +23,8 @@ MODE_PHILOX, MODE_DET, MODE_EXPLICIT = 0, 1, 2
 SYMBOLS = ['mg_device_count', 'mg_ctx_create', 'mg_ctx_destroy', 'mg_last_error', 'mg_synchronize', 'mg_host_alloc', 'mg_host_free', 'mg_model_load', 'mg_model_tables',
            'mg_region_load', 'mg_region_free', 'mg_copy_build', 'mg_copy_free', 'mg_copy_nodes',
            'mg_copy_haplotype', 'mg_sample_templates', 'mg_unit_generate', 'mg_unit_generate_async', 'mg_wait_copies', 'mg_unit_read_async', 'mg_corrupt_fastq',
-           'mg_prof_reset', 'mg_prof_get']
+           'mg_prof_reset', 'mg_prof_get', 'mg_sink_create', 'mg_sink_create_shared', 'mg_sink_next_unit', 'mg_sink_unit_size', 'mg_sink_acquire', 'mg_sink_commit', 'mg_sink_abort',
+           'mg_sink_error', 'mg_sink_chunk_bytes', 'mg_sink_close', 'mg_unit_drain_async', 'mg_drain_wait']
 
 
 class UnitDesc(C.Structure):
@@ -90,5 +91,21 @@ def lib():
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mg_prof_reset.argtypes = [C.c_void_p]
     L.mg_prof_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.mg_sink_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.mg_sink_create_shared.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.mg_sink_next_unit.argtypes = [C.c_void_p]
+    L.mg_sink_next_unit.restype = C.c_int64
+    L.mg_sink_unit_size.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.mg_sink_acquire.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.mg_sink_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+    L.mg_sink_abort.argtypes = [C.c_void_p, C.c_char_p]
+    L.mg_sink_abort.restype = None
+    L.mg_sink_error.argtypes = [C.c_void_p]
+    L.mg_sink_error.restype = C.c_char_p
+    L.mg_sink_chunk_bytes.argtypes = [C.c_void_p]
+    L.mg_sink_chunk_bytes.restype = C.c_int64
+    L.mg_sink_close.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.mg_unit_drain_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]
+    L.mg_drain_wait.argtypes = [C.c_void_p]
     _lib = L
   return _lib

@@ -7,9 +7,13 @@
 #include <cstring>
 #include <ctime>
 #include <cstdlib>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mitty_b200.h"
@@ -87,6 +91,15 @@ struct mg_ctx {
   int last_ob = 0; int64_t last_bytes = 0;         // where the most recent unit's bytes are (mg_unit_read_async)
   double plan_ms = 0;
   double emit_ms = 0; int64_t emit_launches = 0, emit_bytes = 0, total_launches = 0;
+  // drain thread: streams finished units from the device output buffers into an mg_sink
+  struct DrainJob { mg_sink *sink; int producer; int64_t unit; int ob; int64_t bytes; };
+  std::thread drain_thread;
+  std::mutex dmu; std::condition_variable dcv;
+  std::deque<DrainJob> djobs;
+  int dbusy[2] = {0, 0};                            // queued or running drains per output-buffer set
+  bool dstop = false, dfailed = false;
+  std::string derr;
+  cudaEvent_t ev_drain[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -273,6 +286,12 @@ int mg_ctx_create(int device, void *stream, mg_ctx **out) {
 void mg_ctx_destroy(mg_ctx *ctx) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);
+  if (ctx->drain_thread.joinable()) {
+    { std::lock_guard<std::mutex> lk(ctx->dmu); ctx->dstop = true; }
+    ctx->dcv.notify_all();
+    ctx->drain_thread.join();
+  }
+  for (int i = 0; i < 2; i++) if (ctx->ev_drain[i]) cudaEventDestroy(ctx->ev_drain[i]);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (int i = 0; i < 2; i++) if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
@@ -753,6 +772,11 @@ static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint
   CU(cudaEventRecord(ctx->ev2, ctx->stream));
   mg_launch_plan(P, ctx->stream);
   CU(cudaGetLastError());
+  {   // a drain still reading this buffer set (the unit before last) must finish first
+    std::unique_lock<std::mutex> lk(ctx->dmu);
+    while (ctx->dbusy[ctx->ob] > 0 && !ctx->dfailed) ctx->dcv.wait(lk);
+    if (ctx->dfailed) return fail(ctx, MG_EVALUE, "output sink: %s", ctx->derr.c_str());
+  }
   for (int attempt = 0; attempt < 2; attempt++) {
     DevBuf *ob = ctx->s_out[ctx->ob];
     if (ob[0].cap < est || ob[1].cap < est) CU(cudaStreamSynchronize(ctx->copy_stream));   // regrowing frees the old block
@@ -782,6 +806,7 @@ static int unit_generate(mg_ctx *ctx, const mg_unit_desc *d, uint8_t *out1, uint
   if (n_bytes) *n_bytes = (int64_t)tot[2];
   if (n_templates) *n_templates = (int64_t)tot[1];
   if (n_te_kept) *n_te_kept = (int64_t)tot[0];
+  if (!want_out) ctx->ob ^= 1;            // the bytes stay in this set (mg_unit_read_async / mg_unit_drain_async): the next unit takes the other one
   if (want_out) {
     if ((int64_t)tot[2] > cap) return fail(ctx, MG_ECAP, "output needs %lld bytes per file, caller gave %lld", (long long)tot[2], (long long)cap);
     // the kernels have finished (totals were read back): the copies go to their own stream, so the
@@ -924,6 +949,72 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->emit_ms += ms; ctx->emit_launches++; ctx->total_launches++;
   ctx->emit_bytes += 2 * (total[0] + total[1]);
+  return MG_OK;
+}
+
+// ---- draining units into an output sink -----------------------------------------------------------
+
+static void drain_loop(mg_ctx *ctx) {
+  cudaSetDevice(ctx->device);
+  std::unique_lock<std::mutex> lk(ctx->dmu);
+  while (true) {
+    while (ctx->djobs.empty() && !ctx->dstop) ctx->dcv.wait(lk);
+    if (ctx->djobs.empty()) return;
+    const mg_ctx::DrainJob job = ctx->djobs.front(); ctx->djobs.pop_front();
+    lk.unlock();
+    std::string err;
+    // two pieces in flight: the copy of piece i + 1 is enqueued before piece i is handed to the writers
+    void *slot[2] = {nullptr, nullptr}; int64_t s_off[2] = {0, 0}, s_n[2] = {0, 0};
+    const int64_t chunk = mg_sink_chunk_bytes(job.sink);
+    int k = 0;
+    auto finish = [&](int i) {
+      if (!slot[i]) return;
+      if (cudaEventSynchronize(ctx->ev_drain[i]) != cudaSuccess && err.empty()) err = "device-to-host copy failed";
+      if (mg_sink_commit(job.sink, slot[i], job.unit, s_off[i], err.empty() ? s_n[i] : 0) != MG_OK && err.empty()) err = mg_sink_error(job.sink);
+      slot[i] = nullptr;
+    };
+    for (int64_t off = 0; off < job.bytes && err.empty(); off += chunk, k ^= 1) {
+      finish(k);                                            // the piece that used this event two steps ago
+      void *b1 = nullptr, *b2 = nullptr;
+      if (mg_sink_acquire(job.sink, job.producer, &b1, &b2, &slot[k]) != MG_OK) { err = mg_sink_error(job.sink); slot[k] = nullptr; break; }
+      const int64_t n = std::min(chunk, job.bytes - off);
+      s_off[k] = off; s_n[k] = n;
+      cudaError_t e = cudaMemcpyAsync(b1, ctx->s_out[job.ob][0].as<uint8_t>() + off, (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream);
+      if (e == cudaSuccess && b2) e = cudaMemcpyAsync(b2, ctx->s_out[job.ob][1].as<uint8_t>() + off, (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_drain[k], ctx->copy_stream);
+      if (e != cudaSuccess) err = cudaGetErrorString(e);
+    }
+    finish(k); finish(k ^ 1);
+    lk.lock();
+    ctx->dbusy[job.ob]--;
+    if (!err.empty() && !ctx->dfailed) { ctx->dfailed = true; ctx->derr = err; mg_sink_abort(job.sink, err.c_str()); }
+    ctx->dcv.notify_all();
+  }
+}
+
+int mg_unit_drain_async(mg_ctx *ctx, mg_sink *sink, int32_t producer, int64_t unit) {
+  if (!ctx || !sink) return MG_EINVAL;
+  if (mg_sink_unit_size(sink, unit, ctx->last_bytes) != MG_OK) return fail(ctx, MG_EVALUE, "output sink: %s", mg_sink_error(sink));
+  if (ctx->last_bytes == 0) return MG_OK;
+  std::lock_guard<std::mutex> lk(ctx->dmu);
+  if (ctx->dfailed) return fail(ctx, MG_EVALUE, "output sink: %s", ctx->derr.c_str());
+  if (!ctx->drain_thread.joinable()) {
+    DeviceGuard g(ctx->device);
+    for (int i = 0; i < 2; i++)
+      if (!ctx->ev_drain[i] && cudaEventCreateWithFlags(&ctx->ev_drain[i], cudaEventDisableTiming) != cudaSuccess) return fail(ctx, MG_ECUDA, "cannot create the drain events");
+    ctx->drain_thread = std::thread(drain_loop, ctx);
+  }
+  ctx->dbusy[ctx->last_ob]++;
+  ctx->djobs.push_back({sink, producer, unit, ctx->last_ob, ctx->last_bytes});
+  ctx->dcv.notify_all();
+  return MG_OK;
+}
+
+int mg_drain_wait(mg_ctx *ctx) {
+  if (!ctx) return MG_EINVAL;
+  std::unique_lock<std::mutex> lk(ctx->dmu);
+  while ((ctx->dbusy[0] > 0 || ctx->dbusy[1] > 0) && !ctx->dfailed) ctx->dcv.wait(lk);
+  if (ctx->dfailed) return fail(ctx, MG_EVALUE, "output sink: %s", ctx->derr.c_str());
   return MG_OK;
 }
 

@@ -12,6 +12,9 @@
 //   gzip                     pieces are deflated in parallel (one gzip member per piece, zlib), the members
 //                            appended in order: the file is a valid multi-member .gz (what bgzip / pigz write)
 // A slot goes back to its producer's pool when both of its pieces are on disk (plain) or deflated (gzip).
+// Several PROCESSES (one per GPU, e.g. torchrun ranks) can share one pair of output files: with a table
+// path the unit sizes and the "next unit" counter live in a small shared mapping (a file on /dev/shm);
+// every process runs its own sink on the same files and pwrite()s its own units at their final offsets.
 // Deadlock freedom: every producer works through its units in increasing schedule order and announces a
 // unit's size before asking for a slot, and pools are per producer; so the lowest unfinished unit always
 // has its base offset known and slots to travel in.
@@ -19,10 +22,12 @@
 #include <zlib.h>
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
 #include <cerrno>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -39,7 +44,7 @@
 
 namespace {
 
-struct Slot { uint8_t *buf[2]; int producer; int refs; };
+struct Slot { uint8_t *buf[2]; int producer; int refs; bool pinned; };
 
 struct Piece {                 // one file's share of a committed slot
   int file; int64_t unit, off, bytes;
@@ -55,7 +60,12 @@ struct mg_sink {
   bool seekable[2] = {false, false};
   int n_files = 0, gzip = 0;
   int64_t n_units = 0, chunk = 0;
-  std::vector<int64_t> size, base;         // per unit: bytes per file (-1 unknown), offset of its first byte
+  std::vector<int64_t> size_own, base;     // per unit: bytes per file (-1 unknown), offset of its first byte
+  int64_t *size = nullptr;                 // -> size_own, or into the shared table
+  int64_t *next = nullptr;                 // "next unit to hand out" counter (own or shared)
+  int64_t next_own = 0;
+  void *shm = nullptr; size_t shm_bytes = 0;
+  bool shared = false;
   int64_t known = 0;                       // sizes of units [0, known) are known -> base[0..known] are valid
   std::vector<std::vector<Slot *>> pool;   // free slots per producer
   std::vector<Slot *> all_slots;
@@ -66,7 +76,7 @@ struct mg_sink {
   bool writing[2] = {false, false};        // one sequential writer per file at a time
   int64_t written[2] = {0, 0};
   std::mutex mu;
-  std::condition_variable cv_work, cv_slot, cv_idle;
+  std::condition_variable cv_work, cv_slot, cv_idle, cv_poll;
   std::vector<std::thread> threads;
   int64_t in_flight = 0;                   // committed pieces not yet written
   bool closing = false, failed = false;
@@ -102,8 +112,30 @@ bool sequential(const mg_sink *s, int f) { return s->gzip || !s->seekable[f]; }
 
 // skip units that are known to be empty / finished on a sequential target
 void advance(mg_sink *s, int f) {                       // with s->mu held
-  while (s->cur_unit[f] < s->n_units && s->size[(size_t)s->cur_unit[f]] >= 0 && s->cur_off[f] >= s->size[(size_t)s->cur_unit[f]]) {
+  while (s->cur_unit[f] < s->n_units && s->size[s->cur_unit[f]] >= 0 && s->cur_off[f] >= s->size[s->cur_unit[f]]) {
     s->cur_unit[f]++; s->cur_off[f] = 0;
+  }
+}
+
+// extend the prefix of units whose sizes are known; pieces whose base became known are made writable
+void refresh_known(mg_sink *s) {                        // with s->mu held
+  bool moved = false;
+  while (s->known < s->n_units) {
+    const int64_t sz = __atomic_load_n(&s->size[s->known], __ATOMIC_ACQUIRE);
+    if (sz < 0) break;
+    s->base[(size_t)s->known + 1] = s->base[(size_t)s->known] + sz;
+    s->known++;
+  }
+  for (auto it = s->waiting.begin(); it != s->waiting.end() && it->first < s->known;) { s->ready.push_back(it->second); it = s->waiting.erase(it); moved = true; }
+  if (moved) s->cv_work.notify_all();
+}
+
+// shared table only: another process may have announced the size a waiting piece depends on
+void poller(mg_sink *s) {
+  std::unique_lock<std::mutex> lk(s->mu);
+  while (!s->closing && !s->failed) {
+    if (!s->waiting.empty()) refresh_known(s);
+    s->cv_poll.wait_for(lk, std::chrono::microseconds(200));
   }
 }
 
@@ -177,19 +209,43 @@ void worker(mg_sink *s) {
 
 extern "C" {
 
-int mg_sink_create(const char *path1, const char *path2, int64_t n_units, int32_t n_producers, int32_t slots_per_producer,
-                   int64_t chunk_bytes, int32_t gzip_level, int32_t n_threads, mg_sink **out) {
+int mg_sink_create_shared(const char *path1, const char *path2, int64_t n_units, int32_t n_producers, int32_t slots_per_producer,
+                          int64_t chunk_bytes, int32_t gzip_level, int32_t n_threads, const char *table_path, int32_t table_owner,
+                          mg_sink **out) {
   if (!out || !path1 || n_units < 0 || n_producers < 1 || slots_per_producer < 2 || chunk_bytes < 1 || gzip_level < 0 || gzip_level > 9 ||
-      chunk_bytes > (1ll << 31) - 65536) return MG_EINVAL;
+      chunk_bytes > (1ll << 31) - 65536 || (table_path && gzip_level)) return MG_EINVAL;
   *out = nullptr;
   mg_sink *s = new mg_sink();
   s->n_units = n_units; s->chunk = chunk_bytes; s->gzip = gzip_level;
-  s->size.assign((size_t)n_units, -1); s->base.assign((size_t)n_units + 1, 0);
+  s->base.assign((size_t)n_units + 1, 0);
+  if (table_path) {
+    // [0] next-unit counter, [1] n_units, [2 ...] sizes.  The owner creates and fills it BEFORE the others open it
+    // (the callers put a barrier in between); the same goes for truncating the output files.
+    s->shared = true;
+    s->shm_bytes = sizeof(int64_t) * (size_t)(n_units + 2);
+    const int tfd = open(table_path, table_owner ? (O_RDWR | O_CREAT | O_TRUNC | O_CLOEXEC) : (O_RDWR | O_CLOEXEC), 0600);
+    if (tfd < 0 || (table_owner && ftruncate(tfd, (off_t)s->shm_bytes) != 0)) {
+      fprintf(stderr, "mitty_b200: cannot open the shared unit table %s: %s\n", table_path, strerror(errno));
+      if (tfd >= 0) close(tfd);
+      delete s;
+      return MG_EVALUE;
+    }
+    s->shm = mmap(nullptr, s->shm_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, tfd, 0);
+    close(tfd);
+    if (s->shm == MAP_FAILED) { delete s; return MG_EVALUE; }
+    int64_t *t = static_cast<int64_t *>(s->shm);
+    if (table_owner) { t[0] = 0; t[1] = n_units; for (int64_t u = 0; u < n_units; u++) t[2 + u] = -1; __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+    else if (t[1] != n_units) { fprintf(stderr, "mitty_b200: shared unit table %s is for %lld units, not %lld\n", table_path, (long long)t[1], (long long)n_units); munmap(s->shm, s->shm_bytes); delete s; return MG_EVALUE; }
+    s->next = t; s->size = t + 2;
+  } else {
+    s->size_own.assign((size_t)n_units + 1, -1);
+    s->size = s->size_own.data(); s->next = &s->next_own;
+  }
   const char *paths[2] = {path1, path2};
   for (int f = 0; f < 2; f++) {
     if (!paths[f]) break;
     // O_TRUNC only means something for regular files; FIFOs and /dev/fd/N open as they are ('w' of the reference's writer)
-    s->fd[f] = open(paths[f], O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0666);
+    s->fd[f] = open(paths[f], (table_path && !table_owner) ? (O_WRONLY | O_CLOEXEC) : (O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC), 0666);
     if (s->fd[f] < 0) {
       fprintf(stderr, "mitty_b200: cannot open %s for writing: %s\n", paths[f], strerror(errno));
       for (int g = 0; g < f; g++) close(s->fd[g]);
@@ -199,42 +255,66 @@ int mg_sink_create(const char *path1, const char *path2, int64_t n_units, int32_
     struct stat st;
     s->seekable[f] = fstat(s->fd[f], &st) == 0 && S_ISREG(st.st_mode);
     s->n_files = f + 1;
+    if (table_path && !s->seekable[f]) {
+      fprintf(stderr, "mitty_b200: %s is not a regular file: several processes can only share seekable targets\n", paths[f]);
+      for (int g = 0; g <= f; g++) close(s->fd[g]);
+      munmap(s->shm, s->shm_bytes);
+      delete s;
+      return MG_EVALUE;
+    }
   }
   s->pool.resize((size_t)n_producers);
+  bool pinned = true;
   for (int p = 0; p < n_producers; p++)
     for (int k = 0; k < slots_per_producer; k++) {
       Slot *sl = new Slot();
-      sl->producer = p; sl->refs = 0; sl->buf[0] = sl->buf[1] = nullptr;
-      for (int f = 0; f < s->n_files; f++)
-        if (cudaHostAlloc((void **)&sl->buf[f], (size_t)chunk_bytes, cudaHostAllocPortable) != cudaSuccess) {
-          fprintf(stderr, "mitty_b200: cannot page-lock %lld bytes for the output sink\n", (long long)chunk_bytes);
+      sl->producer = p; sl->refs = 0; sl->buf[0] = sl->buf[1] = nullptr; sl->pinned = pinned;
+      for (int f = 0; f < s->n_files; f++) {
+        if (pinned && cudaHostAlloc((void **)&sl->buf[f], (size_t)chunk_bytes, cudaHostAllocPortable) != cudaSuccess) {
+          // no CUDA driver (the host logic is being exercised on a GPU-less box) or no more lockable memory:
+          // ordinary memory carries the bytes just as well, the device-to-host copies are merely slower
           cudaGetLastError();
+          pinned = false; sl->pinned = f > 0;
+        }
+        if (!pinned && !sl->buf[f] && posix_memalign((void **)&sl->buf[f], 4096, (size_t)chunk_bytes) != 0) {
+          fprintf(stderr, "mitty_b200: cannot allocate %lld bytes for the output sink\n", (long long)chunk_bytes);
           s->all_slots.push_back(sl);
           mg_sink_close(s, nullptr, nullptr);
           return MG_ECUDA;
         }
+      }
       s->all_slots.push_back(sl);
       s->pool[(size_t)p].push_back(sl);
     }
   if (n_threads < 1) n_threads = 1;
   for (int t = 0; t < n_threads; t++) s->threads.emplace_back(worker, s);
+  if (s->shared) s->threads.emplace_back(poller, s);
   *out = s;
   return MG_OK;
 }
 
+int mg_sink_create(const char *path1, const char *path2, int64_t n_units, int32_t n_producers, int32_t slots_per_producer,
+                   int64_t chunk_bytes, int32_t gzip_level, int32_t n_threads, mg_sink **out) {
+  return mg_sink_create_shared(path1, path2, n_units, n_producers, slots_per_producer, chunk_bytes, gzip_level, n_threads, nullptr, 1, out);
+}
+
+int64_t mg_sink_next_unit(mg_sink *s) {
+  if (!s) return -1;
+  const int64_t k = __atomic_fetch_add(s->next, 1, __ATOMIC_ACQ_REL);
+  return k < s->n_units ? k : -1;
+}
+
 const char *mg_sink_error(mg_sink *s) { return s ? s->err.c_str() : "null sink"; }
+
+int64_t mg_sink_chunk_bytes(mg_sink *s) { return s ? s->chunk : 0; }
 
 int mg_sink_unit_size(mg_sink *s, int64_t unit, int64_t bytes_per_file) {
   if (!s || unit < 0 || unit >= s->n_units || bytes_per_file < 0) return MG_EINVAL;
   std::lock_guard<std::mutex> lk(s->mu);
   if (s->failed) return MG_EVALUE;
-  if (s->size[(size_t)unit] >= 0) { fail(s, "unit %lld announced twice", (long long)unit); return MG_EINVAL; }
-  s->size[(size_t)unit] = bytes_per_file;
-  while (s->known < s->n_units && s->size[(size_t)s->known] >= 0) {
-    s->base[(size_t)s->known + 1] = s->base[(size_t)s->known] + s->size[(size_t)s->known];
-    s->known++;
-  }
-  for (auto it = s->waiting.begin(); it != s->waiting.end() && it->first < s->known;) { s->ready.push_back(it->second); it = s->waiting.erase(it); }
+  if (s->size[unit] >= 0) { fail(s, "unit %lld announced twice", (long long)unit); return MG_EINVAL; }
+  __atomic_store_n(&s->size[unit], bytes_per_file, __ATOMIC_RELEASE);
+  refresh_known(s);
   s->cv_work.notify_all();
   return MG_OK;
 }
@@ -256,7 +336,7 @@ int mg_sink_commit(mg_sink *s, void *slot, int64_t unit, int64_t offset, int64_t
   Slot *sl = static_cast<Slot *>(slot);
   std::lock_guard<std::mutex> lk(s->mu);
   if (s->failed || bytes == 0) { s->pool[(size_t)sl->producer].push_back(sl); s->cv_slot.notify_all(); return s->failed ? MG_EVALUE : MG_OK; }
-  if (s->size[(size_t)unit] < 0 || offset + bytes > s->size[(size_t)unit]) { fail(s, "piece of unit %lld outside its announced size", (long long)unit); return MG_EINVAL; }
+  if (s->size[unit] < 0 || offset + bytes > s->size[unit]) { fail(s, "piece of unit %lld outside its announced size", (long long)unit); return MG_EINVAL; }
   sl->refs = s->n_files;
   for (int f = 0; f < s->n_files; f++) {
     Piece *p = new Piece();
@@ -282,11 +362,11 @@ int mg_sink_close(mg_sink *s, int64_t *written1, int64_t *written2) {
   {
     std::unique_lock<std::mutex> lk(s->mu);
     while (s->in_flight > 0 && !s->failed) s->cv_idle.wait(lk);
-    if (!s->failed)
+    if (!s->failed && !s->shared)
       for (int64_t u = 0; u < s->n_units; u++)
-        if (s->size[(size_t)u] < 0) { fail(s, "unit %lld was never written", (long long)u); break; }
+        if (s->size[u] < 0) { fail(s, "unit %lld was never written", (long long)u); break; }
     s->closing = true;
-    s->cv_work.notify_all();
+    s->cv_work.notify_all(); s->cv_poll.notify_all();
   }
   for (auto &t : s->threads) t.join();
   const bool failed = s->failed;
@@ -296,7 +376,11 @@ int mg_sink_close(mg_sink *s, int64_t *written1, int64_t *written2) {
   for (auto &kv : s->waiting) delete kv.second;
   for (Piece *p : s->ready) delete p;
   for (int f = 0; f < 2; f++) for (auto &kv : s->ordered[f]) delete kv.second;
-  for (Slot *sl : s->all_slots) { for (int f = 0; f < 2; f++) if (sl->buf[f]) cudaFreeHost(sl->buf[f]); delete sl; }
+  for (Slot *sl : s->all_slots) {
+    for (int f = 0; f < 2; f++) if (sl->buf[f]) { if (cudaFreeHost(sl->buf[f]) != cudaSuccess) { cudaGetLastError(); free(sl->buf[f]); } }
+    delete sl;
+  }
+  if (s->shm) munmap(s->shm, s->shm_bytes);
   const int rc = failed || !s->err.empty() ? MG_EVALUE : MG_OK;
   if (rc != MG_OK) fprintf(stderr, "mitty_b200: output sink: %s\n", s->err.c_str());
   delete s;

@@ -199,6 +199,14 @@ class Engine(object):
     self._check(self._L.mg_unit_read_async(self._h, int(file), int(offset), int(nbytes), _ptr(dst)))
     return dst[:nbytes]
 
+  def drain_async(self, sink, producer, unit):
+    """Queue the most recent unit (generated with fetch=False) for streaming into ``sink`` as
+    schedule unit ``unit``; returns at once, a thread of the context does the copies."""
+    self._check(self._L.mg_unit_drain_async(self._h, sink._h, int(producer), int(unit)))
+
+  def drain_wait(self):
+    self._check(self._L.mg_drain_wait(self._h))
+
   # -- corruption --------------------------------------------------------------------------------
   def corrupt_fastq(self, fq1, fq2=None, mode=MODE_PHILOX, seed=0, draws=None, first_template=0, out=None, partial=False):
     """Whole-buffer corrupt-reads.  fq1/fq2: bytes or uint8 arrays of 4-line FASTQ records.
@@ -242,6 +250,62 @@ class Engine(object):
     ms, n, b, tl, pms = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
     self._L.mg_prof_get(self._h, C.byref(ms), C.byref(n), C.byref(b), C.byref(tl), C.byref(pms))
     return {'emit_ms': ms.value, 'emit_launches': n.value, 'emit_bytes': b.value, 'total_launches': tl.value, 'plan_ms': pms.value}
+
+
+class Sink(object):
+  """The native output sink (mg_sink_*): writer threads inside the library put the units into the two
+  FASTQ files in schedule order -- pwrite for regular files, ordered sequential writes for FIFOs /
+  pipes, one gzip member per piece with ``gzip_level`` > 0.  ``slots`` page-locked slot pairs of
+  ``chunk_bytes`` per producer (GPU) are the spill that lets GPUs run ahead of the files."""
+
+  def __init__(self, path1, path2, n_units, n_producers=1, slots=4, chunk_bytes=64 << 20, gzip_level=0, threads=4, table=None, owner=True):
+    """table: path of a shared unit table (a file on /dev/shm) when several PROCESSES write the same
+    pair of regular files; ``owner`` creates it and truncates the outputs, the others open after a barrier."""
+    self._L = _lib.lib()
+    h = C.c_void_p()
+    rc = self._L.mg_sink_create_shared(str(path1).encode(), str(path2).encode() if path2 is not None else None, int(n_units), int(n_producers),
+                                       int(slots), int(chunk_bytes), int(gzip_level), int(threads),
+                                       str(table).encode() if table is not None else None, int(bool(owner)), C.byref(h))
+    if rc != 0:
+      raise (OSError if rc == _lib.MG_EVALUE else RuntimeError)('mitty_b200: cannot create the output sink for {} / {} (rc={})'.format(path1, path2, rc))
+    self._h = h
+    self.chunk_bytes = int(chunk_bytes)
+
+  def next_unit(self):
+    """The next unit of the schedule that nobody has taken yet, or -1."""
+    return int(self._L.mg_sink_next_unit(self._h))
+
+  def unit_size(self, unit, nbytes):
+    if self._L.mg_sink_unit_size(self._h, int(unit), int(nbytes)) != 0:
+      raise RuntimeError('output sink: ' + self._L.mg_sink_error(self._h).decode())
+
+  def put(self, producer, unit, offset, b1, b2=None):
+    """Host bytes of one piece (test / corrupt-reads path): copied into a slot pair and committed."""
+    p1, p2, slot = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    if self._L.mg_sink_acquire(self._h, int(producer), C.byref(p1), C.byref(p2), C.byref(slot)) != 0:
+      raise RuntimeError('output sink: ' + self._L.mg_sink_error(self._h).decode())
+    n = len(b1)
+    C.memmove(p1.value, (C.c_char * n).from_buffer_copy(bytes(b1)) if not isinstance(b1, np.ndarray) else b1.ctypes.data, n)
+    if b2 is not None and p2.value:
+      C.memmove(p2.value, (C.c_char * n).from_buffer_copy(bytes(b2)) if not isinstance(b2, np.ndarray) else b2.ctypes.data, n)
+    if self._L.mg_sink_commit(self._h, slot, int(unit), int(offset), n) != 0:
+      raise RuntimeError('output sink: ' + self._L.mg_sink_error(self._h).decode())
+
+  def abort(self, why):
+    if self._h:
+      self._L.mg_sink_abort(self._h, str(why).encode()[:400])
+
+  def close(self):
+    """-> (bytes written to file 1, to file 2); raises if any write failed."""
+    if not self._h:
+      return None
+    w1, w2 = C.c_int64(0), C.c_int64(0)
+    err = self._L.mg_sink_error(self._h).decode()
+    rc = self._L.mg_sink_close(self._h, C.byref(w1), C.byref(w2))
+    self._h = None
+    if rc != 0:
+      raise IOError('mitty_b200: output sink failed: ' + (err or 'see stderr'))
+    return w1.value, w2.value
 
 
 def bind_host_thread_to_gpu(device):

@@ -16,6 +16,7 @@ Multi-GPU: units are independent (each carries its own seed), so they are dealt 
 longest-processing-time-first; there is no collective, only the ordered concatenation done here.
 """
 import logging
+import os
 import time
 
 import numpy as np
@@ -91,10 +92,12 @@ def _without_end_crossing_deletions(vl, region, drop):
 
 
 class RegionCache(object):
-  """Regions and chromosome copies resident in HBM, built on first use and released after their
-  last unit (``expect``: {(region idx, copy): number of units that will ask for it})."""
+  """Regions and chromosome copies resident in HBM, built on first use.  With ``expect``
+  ({(region idx, copy): number of units that will ask for it}) each is released after its last
+  unit; without it (units are pulled dynamically, nobody knows who gets what) the least recently
+  used ones are released once ``budget`` bytes of packed sequence are resident."""
 
-  def __init__(self, engine, vcf_df, fetch_ref, expect=None, drop_end_deletions=False):
+  def __init__(self, engine, vcf_df, fetch_ref, expect=None, drop_end_deletions=False, budget=24 << 30):
     self.engine, self.vcf_df, self.fetch_ref = engine, vcf_df, fetch_ref
     self.drop_end_deletions, self.dropped = drop_end_deletions, 0
     self.regions, self.copies = {}, {}
@@ -102,16 +105,40 @@ class RegionCache(object):
     self.left_copies = {}
     for (r_idx, _cpy) in (expect or {}):
       self.left_copies[r_idx] = self.left_copies.get(r_idx, 0) + 1
+    self.budget, self.resident, self.clock, self.used = budget, 0, 0, {}
+
+  def _cost(self, r_idx):
+    region = self.vcf_df[r_idx]['region']
+    return (region[2] - region[1]) // 4 + 4096
+
+  def _evict(self, keep):
+    """LRU: copies first (a region can only go when none of its copies is resident)."""
+    while self.resident > self.budget:
+      cands = [k for k in self.copies if k != keep]
+      if not cands:
+        break
+      k = min(cands, key=lambda c: self.used.get(c, 0))
+      self.engine.free_copy(self.copies.pop(k))
+      self.resident -= self._cost(k[0])
+      if not any(c[0] == k[0] for c in self.copies) and k[0] != keep[0]:
+        self.engine.free_region(self.regions.pop(k[0]))
+        self.resident -= self._cost(k[0])
 
   def copy(self, r_idx, cpy):
     key = (r_idx, cpy)
+    self.clock += 1
+    self.used[key] = self.clock
     if key not in self.copies:
       region = self.vcf_df[r_idx]['region']
       if r_idx not in self.regions:
         self.regions[r_idx] = self.engine.load_region(self.fetch_ref(region), region[1])
+        self.resident += self._cost(r_idx)
       vl, n_drop = _without_end_crossing_deletions(self.vcf_df[r_idx]['v'][cpy], region, self.drop_end_deletions)
       self.dropped += n_drop
       self.copies[key] = self.engine.build_copy(self.regions[r_idx], vl)
+      self.resident += self._cost(r_idx)
+      if self.left is None:
+        self._evict(key)
     return self.copies[key]
 
   def done(self, r_idx, cpy):
@@ -131,7 +158,8 @@ class RegionCache(object):
 def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sample_name, worker_id, ps,
                   mode='philox', corrupt=False, corrupt_seed=0, out=None, fetch=True, wait=True):
   """One work unit (the body of read_generating_worker's loop, readgenerate.py:183-214)
-  -> (fastq1 bytes, fastq2 bytes, template count)."""
+  -> (fastq1 bytes, fastq2 bytes, template count, templates that passed te < p_max, bytes per file);
+  the two byte arrays are None with fetch=False (the unit stays on the device)."""
   n = int((cp.p_max - cp.p_min) * read_model['p'] * 1.2)          # illumina.py:69
   prefix = '@{}:{}:{}:'.format(sample_name, worker_id, ps)         # readgenerate.py:195, 210
   mid = '|{}|{}'.format(chrom, cpy)                                # readgenerate.py:223
@@ -145,33 +173,30 @@ def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sam
                               corrupt=corrupt, corrupt_seed=corrupt_seed, out=out, fetch=fetch, wait=wait)
 
 
-CHUNK_BYTES = 64 << 20     # pinned ring slot per file: a unit is streamed to the writer in pieces of this size
+CHUNK_BYTES = 64 << 20     # sink slot per file: a unit travels to the writer threads in pieces of this size
+SLOTS_PER_GPU = 6          # page-locked slot pairs per GPU: the spill that lets GPUs run ahead of the files
 
 
-def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,
-                corrupt_seed, n_buffers, done, free_q, stop, drop_end_deletions=False):
-  """One thread per GPU: its units, in schedule order.  A unit's FASTQ bytes stay on the device and
-  are streamed through a small ring of pinned slot pairs (page-locking unit-sized host buffers
-  costs seconds for a chr1-sized unit)."""
-  engine = None
+def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, corrupt_seed,
+               drop_end_deletions=False, stats=None):
+  """One host thread (or process) per GPU.  Units are PULLED from the sink's counter one at a time, in
+  schedule order across all workers, so the sizes the file offsets depend on become known in order
+  and a fast GPU never runs far ahead of the files.  Per unit: region / copy from the cache, the
+  unit's kernels (its bytes stay on the device), then the context's drain thread copies it out piece
+  by piece into the sink while this thread already generates the next unit.
+  -> templates written by this worker."""
+  from mitty_b200.engine import bind_host_thread_to_gpu
+  bind_host_thread_to_gpu(device)        # the worker's pinned memory traffic stays in the GPU's socket
+  engine = Engine(device)
+  total = 0
+  t_build = t_gen = 0.0
   try:
-    from mitty_b200.engine import bind_host_thread_to_gpu
-    bind_host_thread_to_gpu(device)      # the pinned ring of this worker lands in the GPU's socket
-    engine = Engine(device)
     engine.load_model(read_model)
-    expect = {}
-    for k in my_units:
-      key = (schedule[k]['region_idx'], schedule[k]['region_cpy'])
-      expect[key] = expect.get(key, 0) + 1
-    cache = RegionCache(engine, vcf_df, fetch_ref, expect, drop_end_deletions)
-    rlen = int(read_model['rlen'])
-    span = max([vcf_df[schedule[k]['region_idx']]['region'][2] - vcf_df[schedule[k]['region_idx']]['region'][1] for k in my_units] + [1])
-    est = int(span * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150) * 0.9) + (1 << 20)
-    slot = min(CHUNK_BYTES, est)
-    for _ in range(n_buffers):
-      free_q.put((engine.pinned(slot), engine.pinned(slot)))
-    t_build = t_gen = t_copy = 0.0
-    for k in my_units:
+    cache = RegionCache(engine, vcf_df, fetch_ref, None, drop_end_deletions)
+    while True:
+      k = sink.next_unit()
+      if k < 0:
+        break
       wd = schedule[k]
       r_idx, cpy = wd['region_idx'], wd['region_cpy']
       ta = time.perf_counter()
@@ -179,47 +204,41 @@ def _gpu_worker(device, my_units, schedule, vcf_df, fetch_ref, read_module, read
       tb = time.perf_counter()
       _, _, cnt, _, nb = generate_unit(engine, read_module, read_model, cp, vcf_df[r_idx]['region'][0], cpy, int(wd['rng_seed']),
                                        sample_name, 0, k, mode=mode, corrupt=corrupt, corrupt_seed=corrupt_seed, fetch=False)
+      engine.drain_async(sink, producer, k)            # announces the unit's size, then streams it
+      total += cnt
       tc = time.perf_counter()
-      for off in range(0, nb, slot):
-        buf = free_q.get()
-        if buf is None or stop.is_set():
-          return
-        n = min(slot, nb - off)
-        f1 = engine.unit_read(0, off, n, buf[0])
-        f2 = engine.unit_read(1, off, n, buf[1])
-        engine.wait_copies()
-        done[k].put((f1, f2, buf))
-      done[k].put(cnt)
-      cache.done(r_idx, cpy)
-      td = time.perf_counter()
-      t_build += tb - ta; t_gen += tc - tb; t_copy += td - tc
-    logger.info('GPU {}: {} units; region/copy builds {:0.2f}s, unit kernels {:0.2f}s, copies + hand-over {:0.2f}s'.format(
-      device, len(my_units), t_build, t_gen, t_copy))
-    stop.wait()          # keep the pinned buffers alive until the writer has drained them
-  except BaseException as e:  # noqa: B902 -- handed to the writer, which re-raises
-    for k in my_units:
-      done[k].put(e)
+      t_build += tb - ta; t_gen += tc - tb
+      logger.debug('Unit {}: {} templates'.format(k, cnt))
+    engine.drain_wait()
+    logger.info('GPU {}: {} templates; region/copy builds {:0.2f}s, unit kernels {:0.2f}s'.format(device, total, t_build, t_gen))
+    if stats is not None:
+      stats.update(build_s=t_build, gen_s=t_gen, dropped=cache.dropped)
+    return total
+  except BaseException as e:
+    sink.abort('{}: {}'.format(type(e).__name__, e))   # wakes every producer and writer
+    raise
   finally:
-    if engine is not None:
-      engine.close()
+    engine.close()
 
 
 def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_module, model, coverage,
                            fastq1_fname, fastq2_fname, threads=2, seed=7, mode='philox', corrupt=False,
-                           corrupt_seed=None, devices=None, drop_end_deletions=False):
+                           corrupt_seed=None, devices=None, drop_end_deletions=False, gzip_level=None, sink_threads=None):
   """Same signature as the reference (readgenerate.py:76-78) plus keyword-only extras.
 
-  ``threads`` = number of GPUs to use (capped by the GPUs present; ``devices`` overrides).  Work
-  units are dealt to the GPUs by longest-processing-time-first; one host thread drives each GPU,
-  filling pinned buffers while this thread appends finished units to the two files IN SCHEDULE
-  ORDER (sequential writes only: the targets may be FIFOs).  Output order and qname serials are
-  those of the reference's ``--threads 1`` run (worker id 0, unit index = schedule index), whatever
-  the GPU count.
+  ``threads`` = number of GPUs to use (capped by the GPUs present; ``devices`` overrides).  One host
+  thread drives each GPU; the units are handed out in schedule order and written by the native
+  output sink (writer threads inside the library) IN SCHEDULE ORDER: pwrite at the final offset for
+  regular files, ordered sequential writes when the targets are FIFOs / process substitutions.
+  Output order and qname serials are those of the reference's ``--threads 1`` run (worker id 0, unit
+  index = schedule index), whatever the GPU count.
+
+  gzip_level: 1-9 writes multi-member gzip (what the reference's ``>(gzip > r1.fq.gz)`` produces,
+  Readme.md:170, without the external process); None = by file name ('.gz'), 0 = plain.
+  Page-locked memory: SLOTS_PER_GPU x CHUNK_BYTES per file and GPU (768 MB per GPU for a pair).
   """
-  import queue
   import threading
-  from mitty_b200 import multigpu
-  from mitty_b200.engine import device_count
+  from mitty_b200.engine import Sink, device_count
 
   t_in = time.time()
   if mode not in ('philox', 'deterministic'):
@@ -241,62 +260,46 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
     if n_dev < 1:
       raise RuntimeError('mitty_b200: no CUDA device; the engine has no CPU fallback')
     devices = list(range(max(1, min(int(threads), n_dev))))
-  weights = [vcf_df[wd['region_idx']]['region'][2] - vcf_df[wd['region_idx']]['region'][1] for wd in schedule]
-  assign = multigpu.assign_units(weights, len(devices)) if schedule else [[] for _ in devices]
-  done = [queue.Queue() for _ in schedule]
-  stop = threading.Event()
-  free_qs = [queue.Queue() for _ in devices]
+  if gzip_level is None:
+    gzip_level = 1 if str(fastq1_fname).endswith('.gz') else 0
   cs = seed if corrupt_seed is None else corrupt_seed
-  workers = [threading.Thread(target=_gpu_worker, daemon=True,
-                              args=(dev, assign[i], schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt,
-                                    cs, 4, done, free_qs[i], stop, drop_end_deletions))
-             for i, dev in enumerate(devices)]
-  owner = {k: i for i, units in enumerate(assign) for k in units}
-
+  span = max([r['region'][2] - r['region'][1] for r in vcf_df] + [1])
+  rlen = int(read_model['rlen'])
+  est = int(span * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150)) + (1 << 16)      # bytes per file of the largest unit
+  chunk = max(256, min(CHUNK_BYTES, est))
+  n_writers = sink_threads or max(2, min(16, 2 * len(devices) if not gzip_level else (os.cpu_count() or 4)))
+  sink = Sink(fastq1_fname, fastq2_fname, len(schedule), n_producers=len(devices), slots=SLOTS_PER_GPU, chunk_bytes=chunk,
+              gzip_level=gzip_level, threads=n_writers)
   t0 = time.time()
-  total = 0
-  t_wait = t_write = 0.0
-  fastq_l = [open(fastq1_fname, 'wb')]
-  if fastq2_fname is not None:
-    fastq_l += [open(fastq2_fname, 'wb')]
-  # the two files are written concurrently (file writes release the GIL); each file still sees
-  # strictly sequential writes in schedule order, so FIFOs / process substitutions keep working
-  from concurrent.futures import ThreadPoolExecutor
-  pool = ThreadPoolExecutor(max_workers=len(fastq_l))
+  totals, errors = [0] * len(devices), []
+
+  def run(i, dev):
+    try:
+      totals[i] = gpu_worker(dev, i, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, cs,
+                             drop_end_deletions)
+    except BaseException as e:  # noqa: B902 -- re-raised below, in the caller's thread
+      errors.append(e)
+
+  workers = [threading.Thread(target=run, args=(i, dev), daemon=True) for i, dev in enumerate(devices)]
   try:
     for w in workers:
       w.start()
-    for k in range(len(schedule)):
-      while True:
-        ta = time.time()
-        item = done[k].get()
-        tb = time.time()
-        t_wait += tb - ta
-        if isinstance(item, BaseException):
-          raise item
-        if not isinstance(item, tuple):                                 # the unit's template count: unit finished
-          total += item
-          logger.debug('Unit {}: {} templates'.format(k, item))
-          break
-        f1, f2, buf = item
-        futs = [pool.submit(fp.write, memoryview(r)) for fp, r in zip(fastq_l, (f1, f2))]   # writer, readgenerate.py:246-248
-        for fu in futs:
-          fu.result()
-        t_write += time.time() - tb
-        free_qs[owner[k]].put(buf)
-  finally:
-    stop.set()
-    for q in free_qs:                                                 # unblock workers waiting for a buffer
-      q.put(None)
-    pool.shutdown(wait=True)
-    for fp in fastq_l:
-      fp.close()
     for w in workers:
-      if w.is_alive():
-        w.join(timeout=60)
+      w.join()
+  finally:
+    if errors:
+      sink.abort(str(errors[0]))
+    try:
+      sink.close()
+    except IOError:
+      if not errors:
+        raise
+  if errors:
+    raise errors[0]
   t1 = time.time()
-  logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s); inputs {:0.2f}s, waiting for the GPU {:0.2f}s, writing {:0.2f}s'.format(
-    total, t1 - t0, total / max(t1 - t0, 1e-9), t0 - t_in, t_wait, t_write))
+  total = sum(totals)
+  logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s); inputs {:0.2f}s'.format(total, t1 - t0, total / max(t1 - t0, 1e-9), t0 - t_in))
+  return None
 
 
 # ---- the qname contract's inverse (readgenerate.py:256-291) --------------------------------------

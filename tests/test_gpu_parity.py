@@ -275,8 +275,9 @@ def test_cli_files_deterministic(tmp_path):
 
 @pytest.mark.parametrize('chunk', [1000, 65536])
 def test_units_streamed_through_small_ring(tmp_path, monkeypatch, chunk):
-  """A unit's bytes leave the device through a ring of small pinned slots (mg_unit_read_async):
-  slots far smaller than a unit (even smaller than a few records) must give the same files."""
+  """A unit's bytes leave the device piece by piece through the sink's page-locked slots (drain
+  thread -> writer threads): slots far smaller than a unit (even smaller than a few records) must
+  give the same files."""
   import mitty_b200.simulation.illumina as il
   import mitty_b200.simulation.readgenerate as rg
   monkeypatch.setattr(rg, 'CHUNK_BYTES', chunk)
@@ -549,6 +550,27 @@ def test_fifo_pipeline_like_the_reference_example(tmp_path):
     t.join(timeout=120)
   assert not errs, errs
   assert got['c1'] == H.golden_fastq('edge.c1.fq.gz') and got['c2'] == H.golden_fastq('edge.c2.fq.gz')
+
+
+@pytest.mark.parametrize('level', [1, 6])
+def test_gzip_sink_gunzips_to_the_plain_bytes(tmp_path, monkeypatch, level):
+  """`--gzip`: multi-member gzip written by the sink's deflate threads (one member per piece) must
+  gunzip to exactly the bytes of the plain run -- what `>(gzip > r1.fq.gz)` gives the reference
+  (Readme.md:170).  A .gz file name switches it on by itself."""
+  import gzip
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  monkeypatch.setattr(rg, 'CHUNK_BYTES', 50000)        # several members per unit
+  info = H.golden()['fastq']['edge']
+  wl = synth.edge_workload()
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'))
+  r1, r2 = str(tmp_path / 'r1.fq.gz'), str(tmp_path / 'r2.fq.gz')
+  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, H.model(info['model']), info['coverage'], r1, r2,
+                            threads=2, seed=info['seed'], mode='deterministic', devices=[0, 0], gzip_level=level if level != 1 else None)
+  raw1 = open(r1, 'rb').read()
+  assert raw1[:2] == b'\x1f\x8b' and raw1.count(b'\x1f\x8b\x08') > 3
+  assert gzip.open(r1, 'rb').read() == H.golden_fastq('edge.r1.fq.gz') and gzip.open(r2, 'rb').read() == H.golden_fastq('edge.r2.fq.gz')
+  assert len(raw1) < 0.5 * len(H.golden_fastq('edge.r1.fq.gz'))
 
 
 def test_generate_reads_without_fastq2(tmp_path):

@@ -46,6 +46,23 @@ namespace {
 
 struct Slot { uint8_t *buf[2]; int producer; int refs; bool pinned; };
 
+// Page-locking is slow (hundreds of ms per GB): the buffers of closed sinks are kept for the next one.
+std::mutex g_cache_mu;
+std::multimap<int64_t, uint8_t *> g_cache;      // chunk bytes -> page-locked buffer
+
+uint8_t *cache_get(int64_t bytes) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  auto it = g_cache.find(bytes);
+  if (it == g_cache.end()) return nullptr;
+  uint8_t *p = it->second; g_cache.erase(it);
+  return p;
+}
+
+void cache_put(int64_t bytes, uint8_t *p) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  g_cache.insert({bytes, p});
+}
+
 struct Piece {                 // one file's share of a committed slot
   int file; int64_t unit, off, bytes;
   const uint8_t *data; Slot *slot;
@@ -253,7 +270,8 @@ int mg_sink_create_shared(const char *path1, const char *path2, int64_t n_units,
       return MG_EVALUE;
     }
     struct stat st;
-    s->seekable[f] = fstat(s->fd[f], &st) == 0 && S_ISREG(st.st_mode);
+    // positional writes: regular files, and /dev/null-like character devices (FIFOs, pipes and ttys are not seekable)
+    s->seekable[f] = fstat(s->fd[f], &st) == 0 && (S_ISREG(st.st_mode) || (S_ISCHR(st.st_mode) && lseek(s->fd[f], 0, SEEK_CUR) != (off_t)-1));
     s->n_files = f + 1;
     if (table_path && !s->seekable[f]) {
       fprintf(stderr, "mitty_b200: %s is not a regular file: several processes can only share seekable targets\n", paths[f]);
@@ -270,6 +288,7 @@ int mg_sink_create_shared(const char *path1, const char *path2, int64_t n_units,
       Slot *sl = new Slot();
       sl->producer = p; sl->refs = 0; sl->buf[0] = sl->buf[1] = nullptr; sl->pinned = pinned;
       for (int f = 0; f < s->n_files; f++) {
+        if ((sl->buf[f] = cache_get(chunk_bytes)) != nullptr) continue;
         if (pinned && cudaHostAlloc((void **)&sl->buf[f], (size_t)chunk_bytes, cudaHostAllocPortable) != cudaSuccess) {
           // no CUDA driver (the host logic is being exercised on a GPU-less box) or no more lockable memory:
           // ordinary memory carries the bytes just as well, the device-to-host copies are merely slower
@@ -377,7 +396,7 @@ int mg_sink_close(mg_sink *s, int64_t *written1, int64_t *written2) {
   for (Piece *p : s->ready) delete p;
   for (int f = 0; f < 2; f++) for (auto &kv : s->ordered[f]) delete kv.second;
   for (Slot *sl : s->all_slots) {
-    for (int f = 0; f < 2; f++) if (sl->buf[f]) { if (cudaFreeHost(sl->buf[f]) != cudaSuccess) { cudaGetLastError(); free(sl->buf[f]); } }
+    for (int f = 0; f < 2; f++) if (sl->buf[f]) cache_put(s->chunk, sl->buf[f]);      // kept for the next sink of this process
     delete sl;
   }
   if (s->shm) munmap(s->shm, s->shm_bytes);

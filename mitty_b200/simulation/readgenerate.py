@@ -178,20 +178,24 @@ SLOTS_PER_GPU = 6          # page-locked slot pairs per GPU: the spill that lets
 
 
 def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, corrupt_seed,
-               drop_end_deletions=False, stats=None):
+               drop_end_deletions=False, stats=None, engine=None):
   """One host thread (or process) per GPU.  Units are PULLED from the sink's counter one at a time, in
   schedule order across all workers, so the sizes the file offsets depend on become known in order
   and a fast GPU never runs far ahead of the files.  Per unit: region / copy from the cache, the
   unit's kernels (its bytes stay on the device), then the context's drain thread copies it out piece
   by piece into the sink while this thread already generates the next unit.
   -> templates written by this worker."""
-  from mitty_b200.engine import bind_host_thread_to_gpu
-  bind_host_thread_to_gpu(device)        # the worker's pinned memory traffic stays in the GPU's socket
-  engine = Engine(device)
+  own_engine = engine is None
+  if own_engine:                         # (a caller that keeps an engine across calls has loaded the model)
+    from mitty_b200.engine import bind_host_thread_to_gpu
+    bind_host_thread_to_gpu(device)      # the worker's pinned memory traffic stays in the GPU's socket
+    engine = Engine(device)
   total = 0
   t_build = t_gen = 0.0
+  cache = None
   try:
-    engine.load_model(read_model)
+    if own_engine:
+      engine.load_model(read_model)
     cache = RegionCache(engine, vcf_df, fetch_ref, None, drop_end_deletions)
     while True:
       k = sink.next_unit()
@@ -218,7 +222,17 @@ def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module,
     sink.abort('{}: {}'.format(type(e).__name__, e))   # wakes every producer and writer
     raise
   finally:
-    engine.close()
+    if own_engine:
+      engine.close()
+    elif cache is not None:              # the caller's engine lives on: give the regions and copies back
+      try:
+        engine.drain_wait()
+      except Exception:
+        pass
+      for cp in cache.copies.values():
+        engine.free_copy(cp)
+      for rid in cache.regions.values():
+        engine.free_region(rid)
 
 
 def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_module, model, coverage,

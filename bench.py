@@ -332,7 +332,11 @@ def pick_sink(args, bytes_per_step):
     try:
       st = os.statvfs('/dev/shm')
       free = st.f_bavail * st.f_frsize
-      want = '/dev/shm' if free > 1.25 * bytes_per_step + (8 << 30) else '/dev/null'
+      avail = free
+      for ln in open('/proc/meminfo'):
+        if ln.startswith('MemAvailable:'):
+          avail = int(ln.split()[1]) * 1024
+      want = '/dev/shm' if min(free, avail) > 1.25 * bytes_per_step + (24 << 30) else '/dev/null'
     except OSError:
       want = '/dev/null'
   if want == '/dev/null':
@@ -456,15 +460,12 @@ def main():
   if not args.no_e2e:
     schedule = list(rg.get_data_for_workers(rm, vcf_df, args.seed))
     bytes_per_step = nbytes_all / max(1, args.steps)
-    p1, p2, sink_desc = pick_sink(args, bytes_per_step)
     table = '/dev/shm/mitty_b200_bench_{}.tbl'.format(os.environ.get('MASTER_PORT', str(os.getpid()))) if world > 1 else None
     span = max(r[2] - r[1] for r in wl['regions'])
     chunk = max(1 << 16, min(rg.CHUNK_BYTES, int(span * 1.05 * rm['p'] * 1.2 * (2 * L + 150)) + (1 << 16)))
-    n_writers = max(2, min(8, (os.cpu_count() or 8) // max(1, world)))
-    e_steps = args.e2e_steps if args.e2e_steps is not None else max(1, min(args.steps, int(120.0 / max(1e-3, bytes_per_step / 45e9))))
-    e_warm = min(args.warmup, 3)
+    n_writers = max(2, min(32, (os.cpu_count() or 8) // max(1, world)))
 
-    def e2e_step(seed):
+    def e2e_step(seed, p1, p2):
       sink = None
       if rank == 0:
         sink = Sink(p1, p2, len(schedule), n_producers=1, slots=rg.SLOTS_PER_GPU, chunk_bytes=chunk, threads=n_writers, table=table, owner=True)
@@ -481,18 +482,34 @@ def main():
         dist.barrier()
       return n, w[0] + w[1], time.perf_counter() - t0
 
-    for w in range(e_warm):
-      e2e_step(3000 + w)
-    ep = eb = 0
-    e_wall = 0.0
-    for s in range(e_steps):
-      n, wb, dt = e2e_step(4000 + s)
-      ep += n; eb += wb; e_wall += dt
-    for f in (p1, p2, table):
-      if rank == 0 and f and f != '/dev/null' and os.path.exists(f):
-        os.remove(f)
+    def e2e_leg(p1, p2, warm, steps):
+      for w in range(warm):
+        e2e_step(3000 + w, p1, p2)
+      ep = eb = 0
+      e_wall = 0.0
+      for s in range(steps):
+        n, wb, dt = e2e_step(4000 + s, p1, p2)
+        ep += n; eb += wb; e_wall += dt
+      for f in (p1, p2, table):
+        if rank == 0 and f and f != '/dev/null' and os.path.exists(f):
+          os.remove(f)
+      return {'pairs': allsum(ep), 'wall': allmax(e_wall), 'bytes': allsum(eb), 'steps': steps}
+
+    # primary: host buffers (the sink's page-locked slots), handed in schedule order to the writer threads, target
+    # /dev/null -- the device-to-host side of the path, what `generate-reads ... >(consumer)` sees from the engine
+    e_steps = args.e2e_steps if args.e2e_steps is not None else max(1, min(args.steps, int(120.0 / max(1e-3, bytes_per_step / 45e9))))
+    _, _, null_desc = pick_sink(argparse.Namespace(sink='/dev/null'), bytes_per_step)
+    e2e = e2e_leg('/dev/null', '/dev/null', min(args.warmup, 3), e_steps)
     h2d = sum(refs[r['region']].nbytes + sum(v.pos.nbytes + v.op.nbytes + v.oplen.nbytes + v.alt_pool.nbytes + v.alt_off.nbytes for v in r['v']) for r in vcf_df)
-    e2e = {'pairs': allsum(ep), 'wall': allmax(e_wall), 'bytes': allsum(eb), 'steps': e_steps, 'h2d': h2d, 'sink': sink_desc, 'writers': n_writers}
+    e2e.update(h2d=h2d, sink=null_desc, writers=n_writers)
+    # second figure: the same into real files on tmpfs, when a step's FASTQ fits there (and in RAM)
+    f1, f2, file_desc = pick_sink(args, bytes_per_step)
+    if f1 != '/dev/null':
+      fs = e2e_leg(f1, f2, 1, max(1, min(3, e_steps)))
+      e2e['file'] = {'value': fs['pairs'] / fs['wall'], 'unit': 'pairs/s', 'pairs_per_min': 60.0 * fs['pairs'] / fs['wall'], 'sink': file_desc,
+                     'gbs_written': fs['bytes'] / fs['wall'] / 1e9, 'steps': fs['steps'], 'writer_threads_per_rank': n_writers}
+    else:
+      e2e['file'] = {'value': None, 'sink': 'not measured: one step ({:.0f} GB of FASTQ) does not fit /dev/shm + RAM of this box'.format(bytes_per_step / 1e9)}
 
     # the ceiling of e2e: N concurrent page-locked device-to-host streams, one per rank (tools/pcie_bw.py does the same stand-alone)
     nb = 1 << 30
@@ -542,6 +559,7 @@ def main():
                      'd2h_bytes_per_step': int(e2e['bytes'] / max(1, e2e['steps'])), 'steps': e2e['steps'], 'sink': e2e['sink'],
                      'writer_threads_per_rank': e2e['writers'], 'gbs_written': e2e['bytes'] / e2e['wall'] / 1e9,
                      'd2h_ceiling_gbs': e2e['d2h_ceiling_gbs'], 'frac_of_d2h_ceiling': (e2e['bytes'] / e2e['wall'] / 1e9) / max(1e-9, e2e['d2h_ceiling_gbs']),
+                     'file_sink': e2e['file'],
                      'path': 'readgenerate.gpu_worker (units pulled in schedule order) -> drain thread (D2H) -> native sink'}
     if not args.no_cpu_baseline and world == 1:
       cwl = wl if args.workload == 'chr1' else {'contigs': [wl['contigs'][0]], 'tables': [wl['tables'][0]], 'sample': wl['sample']}

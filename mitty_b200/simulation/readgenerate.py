@@ -173,6 +173,7 @@ def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sam
                               corrupt=corrupt, corrupt_seed=corrupt_seed, out=out, fetch=fetch, wait=wait)
 
 
+last_run = {}              # statistics of the most recent process_multi_threaded call (the reference returns nothing)
 CHUNK_BYTES = 64 << 20     # sink slot per file: a unit travels to the writer threads in pieces of this size
 SLOTS_PER_GPU = 6          # page-locked slot pairs per GPU: the spill that lets GPUs run ahead of the files
 
@@ -313,6 +314,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   t1 = time.time()
   total = sum(totals)
   logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s); inputs {:0.2f}s'.format(total, t1 - t0, total / max(t1 - t0, 1e-9), t0 - t_in))
+  last_run.update(templates=total, seconds=t1 - t0, input_seconds=t0 - t_in, gpus=len(devices), writers=n_writers, gzip_level=gzip_level)
   return None
 
 

@@ -183,6 +183,25 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
                      int64_t *out_len2, int64_t *n_templates, int64_t first_template, int64_t *consumed1,
                      int64_t *consumed2);
 
+/* ---- round-trip checker: the god-aligner contract (mitty/benchmarking/god_aligner.py:141-183 over
+ * readgenerate.parse_qname, mitty/simulation/readgenerate.py:259-291) verified on the device for EVERY
+ * read of a FASTQ pair of PERFECT reads: (chrom, copy, strand, POS, CIGAR) from the qname + reference +
+ * node list must re-derive the bases in the file ('=' equals the reference, 'X' equals the haplotype and
+ * differs from the reference, 'I' carries the inserted bases, 'D' skips reference, '>p:nI' lies inside one
+ * insertion; strand 1 is reverse-complemented first).
+ * mg_check_add_copy registers a built copy under the (chrom, copy) the qnames name; reference and
+ * haplotype are expanded to text views on the device.  mg_check_fastq checks the COMPLETE templates
+ * present in both buffers (consumed1/2 as for mg_corrupt_fastq) and reports the first bad_cap failures:
+ * bad_index = file * n_records + record, bad_code = 1 malformed qname, 2 unknown chrom/copy, 3 length,
+ * 4 '=' mismatch, 5 'X' mismatch, 6 inserted bases, 7 no insertion at POS, 8 unknown op, 9 out of range,
+ * 10 not a 4-line record with a bare '+' line.                                                        */
+typedef struct mg_checker mg_checker;
+int mg_check_open(mg_ctx *ctx, mg_checker **out);
+void mg_check_close(mg_checker *k);
+int mg_check_add_copy(mg_checker *k, int64_t copy_id, const char *chrom, int32_t cpy);
+int mg_check_fastq(mg_checker *k, const uint8_t *in1, int64_t len1, const uint8_t *in2, int64_t len2, int64_t *n_records,
+                   int64_t *n_bad, int64_t *bad_index, int32_t *bad_code, int32_t bad_cap, int64_t *consumed1, int64_t *consumed2);
+
 /* ---- profiling: device time (CUDA events on the launch stream) of the emit / corrupt kernel
  * (emit_ms over emit_launches launches, emit_bytes written) and of the planning kernel (plan_ms);
  * total_launches counts every kernel this context launched since the last reset.               */

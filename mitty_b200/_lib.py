@@ -11,8 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libmitty_b200.so')
-SOURCES = ['mg_api.cu', 'mg_kernels.cu', 'mg_sink.cpp']
-HEADERS = ['mg_core.cuh', 'mg_internal.h', 'mg_sink.cpp', os.path.join('..', '..', 'include', 'mitty_b200.h')]
+SOURCES = ['mg_api.cu', 'mg_kernels.cu', 'mg_check.cu', 'mg_sink.cpp']
+HEADERS = ['mg_core.cuh', 'mg_internal.h', 'mg_sink.cpp', 'mg_check.cu', os.path.join('..', '..', 'include', 'mitty_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared', '-lz']
 
@@ -24,7 +24,8 @@ SYMBOLS = ['mg_device_count', 'mg_ctx_create', 'mg_ctx_destroy', 'mg_last_error'
            'mg_region_load', 'mg_region_free', 'mg_copy_build', 'mg_copy_free', 'mg_copy_nodes',
            'mg_copy_haplotype', 'mg_sample_templates', 'mg_unit_generate', 'mg_unit_generate_async', 'mg_wait_copies', 'mg_unit_read_async', 'mg_corrupt_fastq',
            'mg_prof_reset', 'mg_prof_get', 'mg_sink_create', 'mg_sink_create_shared', 'mg_sink_next_unit', 'mg_sink_unit_size', 'mg_sink_acquire', 'mg_sink_commit', 'mg_sink_abort',
-           'mg_sink_error', 'mg_sink_chunk_bytes', 'mg_sink_close', 'mg_unit_drain_async', 'mg_drain_wait']
+           'mg_sink_error', 'mg_sink_chunk_bytes', 'mg_sink_close', 'mg_unit_drain_async', 'mg_drain_wait',
+           'mg_check_open', 'mg_check_close', 'mg_check_add_copy', 'mg_check_fastq']
 
 
 class UnitDesc(C.Structure):
@@ -107,5 +108,11 @@ def lib():
     L.mg_sink_close.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mg_unit_drain_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]
     L.mg_drain_wait.argtypes = [C.c_void_p]
+    L.mg_check_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mg_check_close.argtypes = [C.c_void_p]
+    L.mg_check_close.restype = None
+    L.mg_check_add_copy.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int32]
+    L.mg_check_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                 C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     _lib = L
   return _lib

@@ -89,6 +89,29 @@ def generate_reads(fasta, vcf, sample_name, bed, modelfile, coverage, seed, fast
     devices=[int(x) for x in devices.split(',')] if devices else None, drop_end_deletions=drop_end_deletions, gzip_level=gzip_level)
 
 
+@cli.command('check-reads', short_help='Verify that every read re-derives from its qname (god-aligner contract)')
+@click.argument('fasta')
+@click.argument('vcf')
+@click.argument('sample_name')
+@click.argument('bed')
+@click.argument('fastq1', type=click.Path(exists=True))
+@click.option('--fastq2', type=click.Path(exists=True))
+@click.option('--device', default=0, help='CUDA device')
+@click.option('--max-report', default=20, help='how many failing reads to print')
+@click.option('--drop-end-deletions', is_flag=True, help='as given to generate-reads')
+def check_reads(fasta, vcf, sample_name, bed, fastq1, fastq2, device, max_report, drop_end_deletions):
+  """Re-derive every read of a FASTQ (pair) of PERFECT reads from its qname -- chrom, copy, strand,
+  POS, CIGAR -- plus FASTA / VCF / BED, the way `mitty god-aligner` trusts it, and compare it with
+  the bases in the file.  Exit status 1 if any read fails."""
+  import mitty_b200.simulation.readcheck as chk
+  res = chk.check_fastq(fasta, vcf, sample_name, bed, fastq1, fastq2, device=device, max_report=max_report, drop_end_deletions=drop_end_deletions)
+  for f, rec, why, qname in res['examples']:
+    click.echo('file {} record {}: {}: {}'.format(f, rec, why, qname))
+  click.echo('{} reads of {} templates checked in {:0.2f}s: {} failed'.format(res['reads'], res['templates'], res['seconds'], res['bad']))
+  if res['bad']:
+    raise SystemExit(1)
+
+
 @cli.command('corrupt-reads', short_help='Apply corruption model to FASTQ file of reads')
 @click.argument('modelfile')
 @click.argument('fastq1_in', type=click.Path(exists=True))

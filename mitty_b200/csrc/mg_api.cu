@@ -952,6 +952,33 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
   return MG_OK;
 }
 
+}  // extern "C"
+
+// ---- internal views for mg_check.cu ----------------------------------------------------------------
+int mg_internal_copy_view(mg_ctx *ctx, int64_t copy_id, int64_t *region_id, const MgNode **nodes, int *n_nodes, const uint32_t **hap, uint32_t *hap_len,
+                          const MgExc **exc, int *n_exc, int64_t *start1) {
+  auto it = ctx->copies.find(copy_id);
+  if (it == ctx->copies.end()) return fail(ctx, MG_EINVAL, "unknown copy %lld", (long long)copy_id);
+  const Copy &C = *it->second;
+  *region_id = C.region_id; *nodes = C.d_nodes; *n_nodes = (int)C.n_nodes; *hap = C.d_hap + MG_HAP_PAD; *hap_len = (uint32_t)(C.p_max - C.p_min);
+  *exc = C.d_exc; *n_exc = (int)C.n_exc; *start1 = C.p_min;
+  return MG_OK;
+}
+
+int mg_internal_region_view(mg_ctx *ctx, int64_t region_id, const uint32_t **ref, int64_t *len, const MgExc **exc, int *n_exc) {
+  auto it = ctx->regions.find(region_id);
+  if (it == ctx->regions.end()) return fail(ctx, MG_EINVAL, "unknown region %lld", (long long)region_id);
+  const Region &R = *it->second;
+  *ref = R.d_ref + MG_HAP_PAD; *len = R.len; *exc = R.d_exc; *n_exc = (int)R.exc.size();
+  return MG_OK;
+}
+
+cudaStream_t mg_internal_stream(mg_ctx *ctx) { return ctx->stream; }
+int mg_internal_device(mg_ctx *ctx) { return ctx->device; }
+int mg_internal_fail(mg_ctx *ctx, int code, const char *msg) { return fail(ctx, code, "%s", msg); }
+
+extern "C" {
+
 // ---- draining units into an output sink -----------------------------------------------------------
 
 static void drain_loop(mg_ctx *ctx) {

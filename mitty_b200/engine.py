@@ -252,6 +252,45 @@ class Engine(object):
     return {'emit_ms': ms.value, 'emit_launches': n.value, 'emit_bytes': b.value, 'total_launches': tl.value, 'plan_ms': pms.value}
 
 
+CHECK_CODES = {1: 'malformed qname', 2: 'chrom / copy / POS not among the loaded regions', 3: 'read length differs from rlen / CIGAR',
+               4: "'=' segment differs from the reference", 5: "'X' base differs from the haplotype (or equals the reference)",
+               6: 'inserted bases differ', 7: 'no insertion at that reference position', 8: 'unknown CIGAR op', 9: 'position out of range',
+               10: "not a 4-line record with a bare '+' line"}
+
+
+class Checker(object):
+  """The god-aligner round trip on the device (mg_check_*): every read of a FASTQ pair of perfect
+  reads is re-derived from its qname (chrom, copy, strand, POS, CIGAR), the reference and the node
+  lists of the copies registered with ``add_copy``."""
+
+  def __init__(self, engine):
+    self.engine, self._L = engine, engine._L
+    h = C.c_void_p()
+    engine._check(self._L.mg_check_open(engine._h, C.byref(h)))
+    self._h = h
+
+  def add_copy(self, cp, chrom, cpy):
+    self.engine._check(self._L.mg_check_add_copy(self._h, cp.id, str(chrom).encode(), int(cpy)))
+
+  def check(self, fq1, fq2=None, max_report=64):
+    """-> (templates checked, bad reads, [(file, record, code)], consumed bytes of fq1, of fq2)."""
+    a1 = np.frombuffer(fq1, dtype=np.uint8) if not isinstance(fq1, np.ndarray) else fq1
+    a2 = None if fq2 is None else (np.frombuffer(fq2, dtype=np.uint8) if not isinstance(fq2, np.ndarray) else fq2)
+    n, bad, c1, c2 = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    idx, code = np.zeros(max(1, max_report), dtype=np.int64), np.zeros(max(1, max_report), dtype=np.int32)
+    self.engine._check(self._L.mg_check_fastq(self._h, _ptr(a1) if a1.size else _ptr(np.zeros(1, np.uint8)), a1.size,
+                                              _ptr(a2) if a2 is not None else None, a2.size if a2 is not None else 0,
+                                              C.byref(n), C.byref(bad), _ptr(idx), _ptr(code), int(max_report), C.byref(c1), C.byref(c2)))
+    k = min(bad.value, max_report)
+    rep = [(int(i // max(1, n.value)), int(i % max(1, n.value)), int(c)) for i, c in zip(idx[:k], code[:k])]
+    return n.value, bad.value, rep, c1.value, c2.value
+
+  def close(self):
+    if self._h:
+      self._L.mg_check_close(self._h)
+      self._h = None
+
+
 class Sink(object):
   """The native output sink (mg_sink_*): writer threads inside the library put the units into the two
   FASTQ files in schedule order -- pwrite for regular files, ordered sequential writes for FIFOs /

@@ -57,6 +57,7 @@ def parse():
   ap.add_argument('--scale', type=float, default=1.0, help='length scale of the wgs workload')
   ap.add_argument('--sink', default=None, help="e2e target directory, or /dev/null (default: /dev/shm when a step's FASTQ fits, else /dev/null)")
   ap.add_argument('--e2e-steps', type=int, default=None, help='timed e2e steps (default: --steps, capped so that the leg stays within minutes)')
+  ap.add_argument('--mode', default='generate-reads', choices=['generate-reads', 'corrupt-reads'], help="'corrupt-reads': the standalone corrupt kernel over a resident FASTQ pair (second-figure roofline, 1480 B/pair)")
   ap.add_argument('--soft-masked', action='store_true', help='chr1 workload with half of the bases in lower-case stretches (not the headline configuration)')
   a = ap.parse_args()
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -343,7 +344,7 @@ def pick_sink(args, bytes_per_step):
     return '/dev/null', '/dev/null', '/dev/null (page-locked slots -> native writer threads, bytes discarded by the kernel)'
   tag = os.environ.get('MASTER_PORT', str(os.getppid()))
   return (os.path.join(want, 'mitty_b200_bench_{}.1.fq'.format(tag)), os.path.join(want, 'mitty_b200_bench_{}.2.fq'.format(tag)),
-          '{} (tmpfs files, pwrite at the final offsets by the native writer threads)'.format(want))
+          '{} (tmpfs files; the native writer threads copy every piece to its final offset through a shared mapping)'.format(want))
 
 
 def main():
@@ -377,6 +378,9 @@ def main():
   eng = Engine(local, stream=stream.cuda_stream)
   eng.load_model(rm)
   corrupt = not args.perfect
+
+  if args.mode == 'corrupt-reads':
+    return bench_corrupt_reads(args, eng, rm, model)
 
   # ---- the workload: every rank holds all of it (the e2e leg hands units out dynamically)
   if args.workload == 'wgs':
@@ -583,6 +587,62 @@ def main():
   eng.close()
   if world > 1:
     dist.destroy_process_group()
+
+
+def bench_corrupt_reads(args, eng, rm, model):
+  """Standalone `corrupt-reads` (readcorrupt.multi_process's kernel path) over the perfect reads of one
+  chr1-shaped unit: the kernel alone (CUDA events inside the library) against its 1480 B/pair roofline
+  -- every FASTQ byte of both files read once and written once -- and through the C ABI
+  with host buffers (H2D of the perfect reads, D2H of the corrupted ones)."""
+  import mitty_b200.simulation.illumina as il
+  from mitty_b200.engine import MODE_PHILOX
+  from mitty_b200.lib import vcfio
+  wl = make_chr1(args)
+  region = wl['regions'][0]
+  r = vcfio.from_variant_table(wl['tables'][0], region)
+  rid = eng.load_region(np.ascontiguousarray(wl['contigs'][0][1]), region[1])
+  cp = eng.build_copy(rid, r['v'][0])
+  n = int((cp.p_max - cp.p_min) * rm['p'] * 1.2)
+  f1, f2, cnt, _, nb = eng.generate_unit(cp, n, rm['p'], MODE_PHILOX, 4242, '@S:0:0:', '|1|0')
+  eng.free_copy(cp); eng.free_region(rid)
+  eng.load_model(model)
+  chunk = 512 << 20
+  p1, p2 = eng.pinned(chunk), eng.pinned(chunk)
+  outs = (eng.pinned(chunk + (1 << 20)), eng.pinned(chunk + (1 << 20)))
+
+  def one_pass():
+    o1 = o2 = 0; done = 0
+    while o1 < f1.size:
+      a1 = f1[o1:o1 + chunk]; a2 = f2[o2:o2 + chunk]
+      p1[:a1.size] = a1; p2[:a2.size] = a2
+      _, _, k, c1, c2 = eng.corrupt_fastq(p1[:a1.size], p2[:a2.size], mode=MODE_PHILOX, seed=args.seed, first_template=done, out=outs, partial=True)
+      o1 += c1; o2 += c2; done += k
+    return done
+
+  for _ in range(max(1, min(args.warmup, 2))):
+    one_pass()
+  eng.prof_reset()
+  t0 = time.perf_counter()
+  pairs = 0
+  for _ in range(args.steps):
+    pairs += one_pass()
+  wall = time.perf_counter() - t0
+  prof = eng.prof()
+  peak, peak_src = measured_peak()
+  alg = 2.0 * (f1.size + f2.size) * args.steps                          # read once + written once, both files
+  ach = alg / (prof['emit_ms'] * 1e-3) / 1e9
+  line = {'metric': 'read pairs/sec (2x150, corrupt-reads over resident FASTQ)', 'value': pairs / (prof['emit_ms'] * 1e-3), 'unit': 'pairs/s', 'n_gpus': 1,
+          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': prof['emit_ms'] / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+          'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+          'config': {'workload': 'corrupt-reads over the perfect reads of one chr1-shaped unit ({} pairs, 2 x {:.2f} GB), Philox mode, 512 MB chunks'.format(cnt, f1.size / 1e9)},
+          'gpu_launches': prof['total_launches'],
+          'roofline': {'bound': 'hbm', 'kernel': 'k_corrupt_staged', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                       'peak_source': peak_src, 'launches': prof['emit_launches'], 'avg_launch_ms': prof['emit_ms'] / max(1, prof['emit_launches']),
+                       'algorithmic_bytes_per_pair': alg / max(1, pairs)},
+          'e2e': {'value': pairs / wall, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(f1.size + f2.size), 'd2h_bytes_per_step': int(f1.size + f2.size),
+                  'sink': 'pinned host memory (mg_corrupt_fastq with host buffers; includes the host-side staging memcpy of this script)'}}
+  emit(line)
+  eng.close()
 
 
 def other_kernels():

@@ -906,7 +906,7 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
 
   CU(ctx->s_state.need(64));
   P.err = ctx->s_state.as<unsigned long long>();
-  CU(cudaMemsetAsync(P.err, 0, 8, ctx->stream));
+  CU(cudaMemsetAsync(P.err, 0, 16, ctx->stream));
   CU(ctx->c_tmp.need(8 * (size_t)mg_scan_tmp_elems(n_rec)));
   for (int f = 0; f < nf; f++) { CU(ctx->c_sz[f].need(8 * (size_t)n_rec)); CU(ctx->c_off[f].need(8 * (size_t)(n_rec + 1))); }
   mg_launch_corrupt_sizes(P, ctx->c_sz[0].as<int64_t>(), nf > 1 ? ctx->c_sz[1].as<int64_t>() : nullptr, ctx->stream);
@@ -917,9 +917,10 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
     P.out_off[f] = ctx->c_off[f].as<int64_t>();
     ctx->total_launches += 3;
   }
-  unsigned long long err = 0;
-  CU(cudaMemcpyAsync(&err, P.err, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long errv[2] = {0, 0};
+  CU(cudaMemcpyAsync(errv, P.err, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  const unsigned long long err = errv[0];
   if (err) return fail(ctx, MG_EINDEX, "a read is longer than the model's %d cycles (IndexError in the reference, illumina.py:156)", ctx->n_cycles);
   if (out_len1) *out_len1 = total[0];
   if (out_len2) *out_len2 = total[1];
@@ -940,7 +941,12 @@ int mg_corrupt_fastq(mg_ctx *ctx, const uint8_t *in1, int64_t len1, const uint8_
     P.base_rnd = ctx->c_draw[2].as<uint8_t>(); P.draw_off = ctx->c_draw[3].as<int64_t>();
   }
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  mg_launch_corrupt(P, ctx->stream);
+  {
+    static const bool lsu = getenv("MG_COPYOUT_LSU") != nullptr, old = getenv("MG_CORRUPT_SIMPLE") != nullptr;
+    // production mode, every record fits a warp's stage: the staged kernel; else (deterministic draws, giant names) the simple one
+    if (mode == MG_MODE_PHILOX && !old && errv[1] + 16 <= (unsigned long long)mg_corrupt_stage_cap()) mg_launch_corrupt_staged(P, !lsu, ctx->stream);
+    else mg_launch_corrupt(P, ctx->stream);
+  }
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   CU(cudaGetLastError());
   if (out1) CU(cudaMemcpyAsync(out1, P.out[0], (size_t)total[0], cudaMemcpyDeviceToHost, ctx->stream));

@@ -72,7 +72,7 @@ struct MgCorruptParams {     // standalone corrupt-reads over FASTQ resident in 
   int mode;                  // MG_MODE_PHILOX / MG_MODE_DET
   MgCorruptCtx cor;          // PHILOX: alias tables + keys
   const double *bq_rnd, *call_rnd; const uint8_t *base_rnd; const int64_t *draw_off;  // DET: per read [2*n_rec+1]
-  unsigned long long *err;   // [0] != 0 -> a read is longer than the model
+  unsigned long long *err;   // [0] != 0 -> a read is longer than the model; [1] = bytes of the largest output record
 };
 
 // launchers (all asynchronous on `st`)
@@ -116,3 +116,5 @@ void mg_launch_nl_write(const uint8_t *buf, int64_t len, const int64_t *off, int
 int64_t mg_nl_chunks(int64_t len);
 void mg_launch_corrupt_sizes(const MgCorruptParams &P, int64_t *sz0, int64_t *sz1, cudaStream_t st);
 void mg_launch_corrupt(const MgCorruptParams &P, cudaStream_t st);
+void mg_launch_corrupt_staged(const MgCorruptParams &P, bool bulk, cudaStream_t st);   // PHILOX mode, every record <= mg_corrupt_stage_cap()
+int mg_corrupt_stage_cap(void);

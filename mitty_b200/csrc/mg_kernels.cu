@@ -997,12 +997,15 @@ __global__ void __launch_bounds__(256) k_corrupt_sizes(MgCorruptParams P, int64_
   int64_t L0 = s1 - s0;
   if (L0 > P.n_cycles) atomicExch(P.err, 1ull);
   sz0[r] = 2 * L0 + name_len + 6;
+  int64_t big = 2 * L0 + name_len + 6;
   if (P.n_files > 1) {
     fq_lines(P.nl[1], r, h0, h1, s0, s1);
     int64_t L1 = s1 - s0;
     if (L1 > P.n_cycles) atomicExch(P.err, 1ull);
     sz1[r] = 2 * L1 + name_len + 6;
+    if (L1 > L0) big = 2 * L1 + name_len + 6;
   }
+  atomicMax(P.err + 1, (unsigned long long)big);      // the staged kernel needs every record to fit a warp's stage
 }
 
 void mg_launch_corrupt_sizes(const MgCorruptParams &P, int64_t *sz0, int64_t *sz1, cudaStream_t st) {
@@ -1057,6 +1060,199 @@ __global__ void __launch_bounds__(256) k_corrupt(MgCorruptParams P) {
       __syncwarp();
     }
   }
+}
+
+// ---- k_corrupt_staged: production-mode corrupt-reads on the emit kernel's machinery ---------------
+// One WARP owns 32 consecutive templates (lane = record, so every lane is at the same cycle and the
+// alias row of a cycle is shared by the warp); per file the records are rebuilt -- '@' + read 1's name,
+// the sequence corrupted four cycles per step (one Philox block, four joint-table lookups, branch-free
+// substitution on the letters), "+", the qualities -- in the warp's shared-memory stage and leave
+// through the bulk copy engine, like k_unit_emit's.  Input bytes are read with aligned 32-bit loads and
+// a funnel shift per lane.
+
+// four letters with substitutions: A/C/G/T become "ACGT"[code ^ s]; any other byte becomes 'N' when s != 0
+__device__ __forceinline__ uint32_t letters4_sub(uint32_t a4, uint32_t snib) {
+  const uint32_t x = (a4 >> 1) & 0x03030303u;                   // A 0, C 1, T 2, G 3 (bits 1-2 of the letter)
+  const uint32_t sd = x ^ ((x >> 1) & 0x01010101u);              // -> A 0, C 1, G 2, T 3
+  uint32_t u = (sd | (sd >> 4)) & 0x00330033u;
+  const uint32_t z = (u | (u >> 8)) & 0x3333u;                   // as PRMT selector nibbles
+  const uint32_t plain = __byte_perm(0x54474341u, 0u, z);
+  uint32_t out = __byte_perm(0x54474341u, 0u, z ^ snib);
+  if (plain != a4) {                                             // some byte is not an upper-case A/C/G/T (N, IUPAC, lower case)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t c = (a4 >> (8 * j)) & 0xFFu;
+      if (((plain >> (8 * j)) & 0xFFu) != c) {
+        const uint32_t nb = ((snib >> (4 * j)) & 3u) ? (uint32_t)'N' : c;       // base_rot.get(base, 'NNN'), illumina.py:160
+        out = (out & ~(0xFFu << (8 * j))) | (nb << (8 * j));
+      }
+    }
+  }
+  return out;
+}
+
+template <bool C9>
+__global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_constant__ MgCorruptParams P, const int stage_cap, const int bulk) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  uint8_t *stage = smem + (uint32_t)wid * (uint32_t)(stage_cap + 16);
+  uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  asm volatile("" : "+r"(stage_s));
+  unsigned long long policy = 0;
+  if (bulk) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  bool in_flight = false;
+  const MgCorruptCtx &C = P.cor;
+  const uint32_t ks = (uint32_t)C.kshift;
+  const int64_t n_wt = (P.n_rec + 31) / 32;
+  for (int64_t wt = (int64_t)blockIdx.x * (MG_CTA / 32) + wid; wt < n_wt; wt += (int64_t)gridDim.x * (MG_CTA / 32)) {
+    const int64_t r = wt * 32 + lane;
+    const bool active = r < P.n_rec;
+    const int64_t rr = active ? r : P.n_rec - 1;
+    const int64_t gr = P.first + rr;                           // template index in the whole file: the Philox counter
+    int64_t nh0, nh1, s0, s1;
+    fq_lines(P.nl[0], rr, nh0, nh1, s0, s1);
+    const int n_act = (int)(P.n_rec - wt * 32 < 32 ? P.n_rec - wt * 32 : 32);
+    for (int f = 0; f < P.n_files; f++) {
+      if (f) { int64_t h0, h1; fq_lines(P.nl[f], rr, h0, h1, s0, s1); }
+      const int64_t off = P.out_off[f][rr];
+      const uint32_t rec = (uint32_t)(P.out_off[f][rr + 1] - off);
+      const int L = (int)(s1 - s0);
+      const int name_len = (int)rec - 2 * L - 6;
+      const unsigned long long my_end = active ? (unsigned long long)(off + rec) : 0ull;
+      const uint8_t *src = P.in[f] + s0;
+      const uint32_t rowf = (uint32_t)f * (uint32_t)C.n_cycles, t_lo = (uint32_t)gr, t_hi2f = (uint32_t)((unsigned long long)gr >> 32) * 2u + (uint32_t)f;
+      int lo = 0;
+      while (lo < n_act) {
+        const unsigned long long goff = __shfl_sync(FULL, (unsigned long long)off, lo);
+        const uint32_t pad = (uint32_t)(goff & 15);
+        const bool fits = active && lane >= lo && (my_end - goff + pad) <= (unsigned long long)stage_cap;
+        int hi = lo + __popc(__ballot_sync(FULL, fits));
+        if (hi == lo) hi = lo + 1;                               // cannot happen: the host checked that every record fits
+        const unsigned long long gend = __shfl_sync(FULL, my_end, hi - 1);
+        const uint32_t batch_bytes = (uint32_t)(gend - goff);
+        const bool mine = active && lane >= lo && lane < hi;
+        const uint32_t dst = stage_s + pad + (uint32_t)((unsigned long long)off - goff);
+        if (in_flight) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+          in_flight = false;
+        }
+        if (mine) {                                              // '@' + read 1's name + '\n'
+          MgStream<MgSharedSpace> wn;
+          wn.begin(dst);
+          const uint8_t *np_ = P.in[0] + nh0 + 1;
+          const uint32_t sh = 8u * (uint32_t)((uintptr_t)np_ & 3);
+          const uint32_t *wp = reinterpret_cast<const uint32_t *>(np_ - ((uintptr_t)np_ & 3));
+          uint32_t carry = wp[0];
+          wn.append(mg_tok('@', 0, 1));
+          for (int i = 0; i < name_len; i += 8) {
+            const uint32_t w1 = wp[(i >> 2) + 1], w2 = wp[(i >> 2) + 2];
+            uint32_t lo4 = __funnelshift_r(carry, w1, sh), hi4 = __funnelshift_r(w1, w2, sh);
+            carry = w2;
+            const int m = name_len - i < 8 ? name_len - i : 8;
+            if (m < 8) { if (m <= 4) { hi4 = 0; lo4 = m == 4 ? lo4 : lo4 & ((1u << (8 * m)) - 1u); } else hi4 &= (1u << (8 * (m - 4))) - 1u; }
+            wn.append(mg_tok(lo4, hi4, (uint32_t)m));
+          }
+          wn.append(mg_tok('\n', 0, 1));
+          wn.flush_own();
+        }
+        __syncwarp();                                            // every first word is stored: now the bytes that share a word with a neighbour
+        if (mine) {
+          const uint32_t seq_dst = dst + (uint32_t)name_len + 2u, qual_dst = seq_dst + (uint32_t)L + 3u;
+          MgSharedSpace::st8(seq_dst + L, '\n'); MgSharedSpace::st8(seq_dst + L + 1, '+'); MgSharedSpace::st8(seq_dst + L + 2, '\n');
+          MgSharedSpace::st8(qual_dst + L, '\n');
+          MgStream<MgSharedSpace> ws, wq;
+          ws.begin_rmw(seq_dst); wq.begin_rmw(qual_dst);
+          const uint32_t ish = 8u * (uint32_t)((uintptr_t)src & 3);
+          const uint32_t *iw = reinterpret_cast<const uint32_t *>(src - ((uintptr_t)src & 3));
+          uint32_t icarry = iw[0];
+          const int NG = L >> 2, rem = L & 3;
+          auto draw = [&](MgGrp &G, int g) {
+            const uint32_t nx = iw[g + 1];
+            G.b4 = __funnelshift_r(icarry, nx, ish);             // the four letters of group g
+            icarry = nx;
+            mg_grp_draw<true>(C, ks, t_lo, t_hi2f, rowf + 4u * (uint32_t)g, 4 * g, L, G);
+          };
+          auto flush = [&](const MgGrp &G) {
+            uint32_t q4, snib;
+            mg_grp_decode<C9>(G, ks, q4, snib);
+            ws.put_word(letters4_sub(G.b4, snib)); wq.put_word(q4);
+          };
+          if (NG > 0) {
+            MgGrp A, B;
+            int g = 0;
+            draw(A, 0);
+#pragma unroll 1
+            while (g + 2 < NG) {
+              draw(B, g + 1); flush(A);
+              draw(A, g + 2); flush(B);
+              g += 2;
+            }
+            if (g + 1 < NG) { draw(B, g + 1); flush(A); flush(B); }
+            else flush(A);
+          }
+          if (rem) {
+            MgGrp G;
+            const uint32_t nx = iw[NG + 1];
+            G.b4 = __funnelshift_r(icarry, nx, ish);
+            G.b4 &= (1u << (8 * rem)) - 1u; G.b4 |= 0x41414141u << (8 * rem);       // the bytes beyond the read: harmless letters
+            mg_grp_draw<false>(C, ks, t_lo, t_hi2f, rowf + 4u * (uint32_t)NG, 4 * NG, L, G);
+            uint32_t q4, snib;
+            mg_grp_decode<C9>(G, ks, q4, snib);
+            const uint32_t ch = letters4_sub(G.b4, snib);
+            for (int j = 0; j < rem; j++) { ws.put((uint8_t)(ch >> (8 * j))); wq.put((uint8_t)(q4 >> (8 * j))); }
+          }
+          ws.end(); wq.end();
+        }
+        // copy-out, as in k_unit_emit
+        uint8_t *gdst = P.out[f] + goff;
+        const uint8_t *ssrc = stage + pad;
+        uint32_t head = (16u - pad) & 15u;
+        if (head > batch_bytes) head = batch_bytes;
+        const uint32_t nvec = (batch_bytes - head) >> 4;
+        const uint32_t done = head + (nvec << 4);
+        if (bulk) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && nvec) bulk_store(gdst + head, stage_s + pad + head, nvec << 4, policy);
+          in_flight = nvec != 0;
+          if ((uint32_t)lane < head) gdst[lane] = ssrc[lane];
+          if (done + lane < batch_bytes) gdst[done + lane] = ssrc[done + lane];
+        } else {
+          __syncwarp();
+          if ((uint32_t)lane < head) gdst[lane] = ssrc[lane];
+          const uint4 *sv = reinterpret_cast<const uint4 *>(ssrc + head);
+          uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
+          for (uint32_t v = lane; v < nvec; v += 32) __stcs(gv + v, sv[v]);
+          if (done + lane < batch_bytes) gdst[done + lane] = ssrc[done + lane];
+          __syncwarp();
+        }
+        lo = hi;
+      }
+    }
+  }
+  if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+#define MG_CORRUPT_STAGE (32 * (2 * 150 + 6 + 96) & ~15)     // bytes per warp: 32 records of 2 x 150 + a ~90-byte name
+
+int mg_corrupt_stage_cap(void) { return MG_CORRUPT_STAGE; }
+
+// staged == true: every output record fits a warp's stage (the caller checked): the fast kernel
+void mg_launch_corrupt_staged(const MgCorruptParams &P, bool bulk, cudaStream_t st) {
+  if (P.n_rec == 0) return;
+  const int smem = (MG_CTA / 32) * (MG_CORRUPT_STAGE + 16);
+  auto k = P.cor.code9 ? k_corrupt_staged<true> : k_corrupt_staged<false>;
+  static bool once[2] = {false, false};
+  if (!once[P.cor.code9 ? 1 : 0]) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once[P.cor.code9 ? 1 : 0] = true; }
+  int per_sm = 0, dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, MG_CTA, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (P.n_rec + 127) / 128;
+  if (blocks > (int64_t)sms * per_sm) blocks = (int64_t)sms * per_sm;
+  k<<<(unsigned)blocks, MG_CTA, smem, st>>>(P, MG_CORRUPT_STAGE, bulk ? 1 : 0);
 }
 
 void mg_launch_corrupt(const MgCorruptParams &P, cudaStream_t st) {

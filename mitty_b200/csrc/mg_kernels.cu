@@ -1120,6 +1120,10 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_const
       const int name_len = (int)rec - 2 * L - 6;
       const unsigned long long my_end = active ? (unsigned long long)(off + rec) : 0ull;
       const uint8_t *src = P.in[f] + s0;
+      if (f + 1 < P.n_files) {                                  // the other file's sequence line, on its way while this one is processed
+        const int64_t q0 = P.nl[f + 1][4 * rr] + 1, q1 = P.nl[f + 1][4 * rr + 1];
+        for (int64_t a = q0 & ~31ll; a < q1; a += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.in[f + 1] + a));
+      }
       const uint32_t rowf = (uint32_t)f * (uint32_t)C.n_cycles, t_lo = (uint32_t)gr, t_hi2f = (uint32_t)((unsigned long long)gr >> 32) * 2u + (uint32_t)f;
       int lo = 0;
       while (lo < n_act) {
@@ -1159,17 +1163,39 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_const
         __syncwarp();                                            // every first word is stored: now the bytes that share a word with a neighbour
         if (mine) {
           const uint32_t seq_dst = dst + (uint32_t)name_len + 2u, qual_dst = seq_dst + (uint32_t)L + 3u;
-          MgSharedSpace::st8(seq_dst + L, '\n'); MgSharedSpace::st8(seq_dst + L + 1, '+'); MgSharedSpace::st8(seq_dst + L + 2, '\n');
           MgSharedSpace::st8(qual_dst + L, '\n');
+          const int NG = L >> 2, rem = L & 3;
+          {   // 1. the letters as they are, parked in the record's own sequence line: eight independent loads in flight
+              //    at a time (the per-group loads of the main loop would each wait for DRAM on their own)
+            MgStream<MgSharedSpace> wl;
+            wl.begin_rmw(seq_dst);
+            const uint32_t ish = 8u * (uint32_t)((uintptr_t)src & 3);
+            const uint32_t *iw = reinterpret_cast<const uint32_t *>(src - ((uintptr_t)src & 3));
+            const int NW = (L + 3) >> 2;
+            uint32_t carry = iw[0];
+#pragma unroll 1
+            for (int w0 = 0; w0 < NW; w0 += 8) {
+              uint32_t v[8];
+#pragma unroll
+              for (int i = 0; i < 8; i++) v[i] = (w0 + i < NW) ? iw[w0 + i + 1] : 0u;
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                if (w0 + i < NG) wl.put_word(__funnelshift_r(carry, v[i], ish));
+                else if (w0 + i == NG && rem) { const uint32_t ch = __funnelshift_r(carry, v[i], ish); for (int j = 0; j < rem; j++) wl.put((uint8_t)(ch >> (8 * j))); }
+                carry = v[i];
+              }
+            }
+            wl.flush_own();                                     // the bytes above are this record's own '\n+\n' ...
+            MgSharedSpace::st8(seq_dst + L, '\n'); MgSharedSpace::st8(seq_dst + L + 1, '+'); MgSharedSpace::st8(seq_dst + L + 2, '\n');   // ... rewritten here
+          }
+          // 2. four cycles per step, in place: read the parked letters, substitute, write them back with the qualities
           MgStream<MgSharedSpace> ws, wq;
           ws.begin_rmw(seq_dst); wq.begin_rmw(qual_dst);
-          const uint32_t ish = 8u * (uint32_t)((uintptr_t)src & 3);
-          const uint32_t *iw = reinterpret_cast<const uint32_t *>(src - ((uintptr_t)src & 3));
-          uint32_t icarry = iw[0];
-          const int NG = L >> 2, rem = L & 3;
+          const uint32_t lsh = 8u * (seq_dst & 3u), lbase = seq_dst & ~3u;
+          uint32_t icarry = MgSharedSpace::ld32(lbase);
           auto draw = [&](MgGrp &G, int g) {
-            const uint32_t nx = iw[g + 1];
-            G.b4 = __funnelshift_r(icarry, nx, ish);             // the four letters of group g
+            const uint32_t nx = MgSharedSpace::ld32(lbase + 4u * (uint32_t)(g + 1));
+            G.b4 = __funnelshift_r(icarry, nx, lsh);            // the four letters of group g
             icarry = nx;
             mg_grp_draw<true>(C, ks, t_lo, t_hi2f, rowf + 4u * (uint32_t)g, 4 * g, L, G);
           };
@@ -1193,8 +1219,8 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_const
           }
           if (rem) {
             MgGrp G;
-            const uint32_t nx = iw[NG + 1];
-            G.b4 = __funnelshift_r(icarry, nx, ish);
+            const uint32_t nx = MgSharedSpace::ld32(lbase + 4u * (uint32_t)(NG + 1));
+            G.b4 = __funnelshift_r(icarry, nx, lsh);
             G.b4 &= (1u << (8 * rem)) - 1u; G.b4 |= 0x41414141u << (8 * rem);       // the bytes beyond the read: harmless letters
             mg_grp_draw<false>(C, ks, t_lo, t_hi2f, rowf + 4u * (uint32_t)NG, 4 * NG, L, G);
             uint32_t q4, snib;

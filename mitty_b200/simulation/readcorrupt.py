@@ -2,11 +2,17 @@
 
 Same entry point as the reference (``multi_process``, readcorrupt.py:18).  The FASTQ pair is
 indexed (newline scan), sized (exclusive scan) and corrupted on the device
-(``k_nl_*``, ``k_corrupt_sizes``, ``k_corrupt``); input qualities are discarded and read 1's name
-is written to both files, as the reference does (readcorrupt.py:55, 113).
+(``k_nl_*``, ``k_corrupt_sizes``, ``k_corrupt_staged``; ``k_corrupt`` for the deterministic draws);
+input qualities are discarded and read 1's name is written to both files, as the reference does
+(readcorrupt.py:55, 113).
+
+Page-locked memory: 2 input + 4 output buffers of ``chunk_bytes`` / 2 x ``chunk_bytes`` (2.5 GB with
+the default 256 MB chunks; pass a smaller ``chunk_bytes`` on small hosts -- the result does not
+depend on it).
 
 Modes
-  philox         production: Philox4x32-10 draws keyed by (seed, template index, file, cycle)
+  philox         production: Philox4x32-7 draws keyed by (seed, template index, file, cycle group);
+                 one joint (quality, substitution) alias lookup per base (MgCorruptCtx, mg_core.cuh)
   deterministic  the single worker's numpy RandomState stream of the reference
                  (seed -> RandomState(seed).randint(SEED_MAX), readcorrupt.py:31,36,84) is drawn on
                  the host, read by read, and consumed on the device: byte-exact vs ``--threads 1``

@@ -8,7 +8,8 @@ one kernel launch (``k_unit_emit``); the host only walks the schedule and append
 ranges to the two output files in schedule order.
 
 Modes
-  philox         production: all draws come from Philox4x32-10 on the device
+  philox         production: all draws come from Philox on the device (4x32-10 for template sampling,
+                 4x32-7 for the per-base corruption stream)
   deterministic  the reference's own numpy RandomState draws are made on the host and consumed on
                  the device; the output equals the reference's ``--threads 1`` FASTQ byte for byte
 

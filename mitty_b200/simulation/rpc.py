@@ -1,7 +1,7 @@
 """Read POS / CIGAR: the device-backed mirror of ``mitty/simulation/rpc.py``.
 
-``create_node_list`` builds the node table of one chromosome copy (greedy variant walk on the host,
-haplotype + lookup table on the GPU) and returns the same tuples as the reference's ``Node``s;
+``create_node_list`` builds the node table of one chromosome copy (the greedy variant walk, the
+haplotype and the lookup table all on the GPU: ``k_walk_*``, ``k_hap_build``, ``k_blk_table``) and returns the same tuples as the reference's ``Node``s;
 ``generate_read`` evaluates one read through the emit kernel and parses the result back.  These are
 convenience entry points for tests and for users of the reference's low-level API; the hot path
 (``readgenerate``) drives the same kernels unit-wise.

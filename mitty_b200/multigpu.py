@@ -30,6 +30,26 @@ def assign_units(weights, world):
   return [sorted(x) for x in out]
 
 
+def assign_by_region(schedule, weights, world):
+  """Units dealt to ``world`` workers so that all units of a BED region go to ONE worker (its packed
+  reference and chromosome copies are then built once): regions by LPT on their total weight, each
+  worker's units in ascending schedule order.  -> list (per worker) of unit indices."""
+  tot = {}
+  for k, wd in enumerate(schedule):
+    tot[wd['region_idx']] = tot.get(wd['region_idx'], 0.0) + float(weights[k])
+  regions = sorted(tot, key=lambda r: (-tot[r], r))
+  load = [0.0] * world
+  owner = {}
+  for r in regions:
+    w = min(range(world), key=lambda i: (load[i], i))
+    owner[r] = w
+    load[w] += tot[r]
+  out = [[] for _ in range(world)]
+  for k, wd in enumerate(schedule):
+    out[owner[wd['region_idx']]].append(k)
+  return out
+
+
 def write_part(part_prefix, rank, unit_bytes):
   """unit_bytes: iterable of (schedule idx, bytes file1, bytes file2) -> index list."""
   index = []

@@ -180,10 +180,11 @@ SLOTS_PER_GPU = 6          # page-locked slot pairs per GPU: the spill that lets
 
 
 def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, corrupt_seed,
-               drop_end_deletions=False, stats=None, engine=None):
-  """One host thread (or process) per GPU.  Units are PULLED from the sink's counter one at a time, in
-  schedule order across all workers, so the sizes the file offsets depend on become known in order
-  and a fast GPU never runs far ahead of the files.  Per unit: region / copy from the cache, the
+               drop_end_deletions=False, stats=None, engine=None, my_units=None):
+  """One host thread (or process) per GPU worker.  With ``my_units`` (ascending schedule indices: all
+  units of a region on one worker, so each region / copy is built once) the worker walks its list;
+  without, units are PULLED from the sink's counter one at a time, in schedule order across all
+  workers (several processes sharing one sink).  Per unit: region / copy from the cache, the
   unit's kernels (its bytes stay on the device), then the context's drain thread copies it out piece
   by piece into the sink while this thread already generates the next unit.
   -> templates written by this worker."""
@@ -198,9 +199,16 @@ def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module,
   try:
     if own_engine:
       engine.load_model(read_model)
-    cache = RegionCache(engine, vcf_df, fetch_ref, None, drop_end_deletions)
+    expect = None
+    if my_units is not None:
+      expect = {}
+      for k in my_units:
+        key = (schedule[k]['region_idx'], schedule[k]['region_cpy'])
+        expect[key] = expect.get(key, 0) + 1
+    cache = RegionCache(engine, vcf_df, fetch_ref, expect, drop_end_deletions)
+    todo = iter(my_units) if my_units is not None else None
     while True:
-      k = sink.next_unit()
+      k = next(todo, -1) if todo is not None else sink.next_unit()
       if k < 0:
         break
       wd = schedule[k]
@@ -211,6 +219,7 @@ def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module,
       _, _, cnt, _, nb = generate_unit(engine, read_module, read_model, cp, vcf_df[r_idx]['region'][0], cpy, int(wd['rng_seed']),
                                        sample_name, 0, k, mode=mode, corrupt=corrupt, corrupt_seed=corrupt_seed, fetch=False)
       engine.drain_async(sink, producer, k)            # announces the unit's size, then streams it
+      cache.done(r_idx, cpy)
       total += cnt
       tc = time.perf_counter()
       t_build += tb - ta; t_gen += tc - tb
@@ -239,7 +248,8 @@ def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module,
 
 def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_module, model, coverage,
                            fastq1_fname, fastq2_fname, threads=2, seed=7, mode='philox', corrupt=False,
-                           corrupt_seed=None, devices=None, drop_end_deletions=False, gzip_level=None, sink_threads=None):
+                           corrupt_seed=None, devices=None, drop_end_deletions=False, gzip_level=None, sink_threads=None,
+                           workers_per_gpu=None):
   """Same signature as the reference (readgenerate.py:76-78) plus keyword-only extras.
 
   ``threads`` = number of GPUs to use (capped by the GPUs present; ``devices`` overrides).  One host
@@ -249,6 +259,9 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   Output order and qname serials are those of the reference's ``--threads 1`` run (worker id 0, unit
   index = schedule index), whatever the GPU count.
 
+  workers_per_gpu: host threads (each with its own context and stream) per GPU; None = 1, or 4 when
+  the BED holds many small regions (an exome-style BED is bound by launch and synchronisation
+  latency per unit, which concurrent workers overlap).
   gzip_level: 1-9 writes multi-member gzip (what the reference's ``>(gzip > r1.fq.gz)`` produces,
   Readme.md:170, without the external process); None = by file name ('.gz'), 0 = plain.
   Page-locked memory: SLOTS_PER_GPU x CHUNK_BYTES per file and GPU (768 MB per GPU for a pair).
@@ -276,6 +289,13 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
     if n_dev < 1:
       raise RuntimeError('mitty_b200: no CUDA device; the engine has no CPU fallback')
     devices = list(range(max(1, min(int(threads), n_dev))))
+  span_max = max([r['region'][2] - r['region'][1] for r in vcf_df] + [1])
+  if workers_per_gpu is None:
+    workers_per_gpu = 4 if (len(vcf_df) >= 64 and span_max < 2000000) else 1
+  devices = [d for d in devices for _ in range(max(1, int(workers_per_gpu)))]
+  from mitty_b200 import multigpu
+  weights = [vcf_df[wd['region_idx']]['region'][2] - vcf_df[wd['region_idx']]['region'][1] for wd in schedule]
+  assign = multigpu.assign_by_region(schedule, weights, len(devices))
   if gzip_level is None:
     gzip_level = 1 if str(fastq1_fname).endswith('.gz') else 0
   cs = seed if corrupt_seed is None else corrupt_seed
@@ -292,7 +312,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   def run(i, dev):
     try:
       totals[i] = gpu_worker(dev, i, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, cs,
-                             drop_end_deletions)
+                             drop_end_deletions, my_units=assign[i])
     except BaseException as e:  # noqa: B902 -- re-raised below, in the caller's thread
       errors.append(e)
 

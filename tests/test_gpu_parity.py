@@ -637,3 +637,29 @@ def test_bench_unit_full_size_exact(eng):
     want = PR.corrupt_file(sample, f, tables, 2000, seed ^ 0x636f7231, serials=pick)
     assert b''.join(corrupted[starts[i]:ends[i]].tobytes() for i in pick) == want
   eng.free_copy(cp); eng.free_region(rid)
+
+
+@pytest.mark.parametrize('workers', [1, 4])
+def test_exome_style_bed_many_small_regions(tmp_path, workers):
+  """A BED of 1000 regions of 2 kb (4000 work units in the reference's shuffled schedule order,
+  readgenerate.py:129-159), several host workers per GPU: deterministic mode == the oracle's
+  generate-reads byte for byte, whatever the number of workers."""
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  n_reg, width = 1000, 2000
+  wl = synth.config1(contig_len=n_reg * width * 2 + 10000, names=('1',))
+  wl['regions'] = [('1', 5000 + 2 * width * k, 5000 + 2 * width * k + width) for k in range(n_reg)]
+  # variants whose deletions would cross a region end are not part of this test's subject
+  t = wl['tables'][0]
+  ends = np.array([r[2] for r in wl['regions']]); starts = np.array([r[1] for r in wl['regions']])
+  j = np.searchsorted(starts, t.pos - 1, side='right') - 1
+  reflen = t.ref_off[1:] - t.ref_off[:-1]
+  ok = (j < 0) | (t.pos - 1 >= ends[np.maximum(j, 0)]) | (t.pos - 1 + reflen + 1 < ends[np.maximum(j, 0)])
+  wl['tables'][0] = synth._subset(t, ok)
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'exome'))
+  r1, r2 = str(tmp_path / 'r1.fq'), str(tmp_path / 'r2.fq')
+  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, 30.0, r1, r2, threads=1, seed=7, mode='deterministic', workers_per_gpu=workers)
+  o1, o2, n = oracle.generate_reads_cmd(H.oracle_regions(H.workload_regions(wl)), m, 30.0, 7, wl['sample'])
+  assert n > 150000 and rg.last_run['templates'] == n
+  assert H.sha256(open(r1, 'rb').read()) == H.sha256(o1) and H.sha256(open(r2, 'rb').read()) == H.sha256(o2)

@@ -75,7 +75,7 @@ def print_qname(ctx, param, value):
 @click.option('--corrupt', is_flag=True, help='Fuse the Illumina corruption model into read generation (Philox draws)')
 @click.option('--devices', default=None, help='comma separated CUDA devices (default: the first --threads GPUs)')
 @click.option('--gzip', 'gzip_level', type=click.IntRange(0, 9), default=None, help='Write multi-member gzip at this level (default: 1 when FASTQ1 ends in .gz, else plain)')
-@click.option('--workers-per-gpu', type=int, default=None, help='Host threads (own context and stream) per GPU; default 1, or 4 for BED files of many small regions')
+@click.option('--workers-per-gpu', type=int, default=None, help='Host threads (own context and stream) per GPU (default 1)')
 @click.option('--drop-end-deletions', is_flag=True, help='Leave out deletions that reach beyond the end of their BED region (default: error; the reference mis-handles them)')
 def generate_reads(fasta, vcf, sample_name, bed, modelfile, coverage, seed, fastq1, fastq2, threads, deterministic, corrupt, devices, drop_end_deletions, gzip_level, workers_per_gpu):
   """Generate simulated reads (--threads = number of GPUs to use)"""

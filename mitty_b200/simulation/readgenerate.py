@@ -259,9 +259,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   Output order and qname serials are those of the reference's ``--threads 1`` run (worker id 0, unit
   index = schedule index), whatever the GPU count.
 
-  workers_per_gpu: host threads (each with its own context and stream) per GPU; None = 1, or 4 when
-  the BED holds many small regions (an exome-style BED is bound by launch and synchronisation
-  latency per unit, which concurrent workers overlap).
+  workers_per_gpu: host threads (each with its own context and stream) per GPU (default 1).
   gzip_level: 1-9 writes multi-member gzip (what the reference's ``>(gzip > r1.fq.gz)`` produces,
   Readme.md:170, without the external process); None = by file name ('.gz'), 0 = plain.
   Page-locked memory: SLOTS_PER_GPU x CHUNK_BYTES per file and GPU (768 MB per GPU for a pair).
@@ -291,7 +289,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
     devices = list(range(max(1, min(int(threads), n_dev))))
   span_max = max([r['region'][2] - r['region'][1] for r in vcf_df] + [1])
   if workers_per_gpu is None:
-    workers_per_gpu = 4 if (len(vcf_df) >= 64 and span_max < 2000000) else 1
+    workers_per_gpu = 1      # (measured: several contexts on one GPU do not overlap the per-unit latencies -- the driver serialises them)
   devices = [d for d in devices for _ in range(max(1, int(workers_per_gpu)))]
   from mitty_b200 import multigpu
   weights = [vcf_df[wd['region_idx']]['region'][2] - vcf_df[wd['region_idx']]['region'][1] for wd in schedule]

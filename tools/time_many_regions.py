@@ -18,7 +18,7 @@ try:
   m = load_model('hiseq-X-v2.5-Garvan.pkl')
   for w in tries:
     for rep in range(2):      # the second run is the warm one
-      rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, 30.0, r1, r2, threads=1, seed=7, mode='philox', corrupt=True, workers_per_gpu=w)
+      rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, 30.0, r1, r2, threads=1, seed=7, mode='philox', corrupt=True, workers_per_gpu=w, drop_end_deletions=True)
     st = rg.last_run
     print(json.dumps({'regions': n_reg, 'width': width, 'workers_per_gpu': w, 'seconds_units_to_files': st['seconds'], 'ms_per_region': 1e3 * st['seconds'] / n_reg,
                       'pairs': st['templates'], 'pairs_per_s': st['templates'] / st['seconds']}))

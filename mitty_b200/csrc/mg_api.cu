@@ -54,7 +54,9 @@ struct Copy {
   int64_t n_nodes = 0;
   int64_t n_exc = 0;
   MgNode *d_nodes = nullptr; uint32_t *d_hap = nullptr; uint32_t *d_blk = nullptr; MgExc *d_exc = nullptr;
-  int n_blk = 0; int64_t hap_words = 0;
+  int n_blk = 0; int64_t hap_words = 0, hap_len = 0;
+  std::vector<MgSegOut> segs;      // a batch of small regions: one entry per (region, copy)
+  std::vector<int64_t> seg_start1;
   mg_ctx *owner = nullptr;
   ~Copy();
 };
@@ -468,31 +470,26 @@ int mg_region_free(mg_ctx *ctx, int64_t region_id) {
 
 // ---- chromosome copy --------------------------------------------------------------------------
 
-int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *pos, const uint8_t *op, const int64_t *oplen,
-                  const uint8_t *alt_pool, const int64_t *alt_off, int64_t *copy_id, int64_t *p_min, int64_t *p_max,
-                  int64_t *n_nodes) {
-  if (!ctx || !copy_id || n_var < 0 || (n_var > 0 && (!pos || !op || !oplen || !alt_pool || !alt_off)))
-    return fail(ctx, MG_EINVAL, "mg_copy_build: bad arguments");
-  if (n_var >= (1ll << 28)) return fail(ctx, MG_EVALUE, "%lld variants on one copy (limit 2^28)", (long long)n_var);
-  auto it = ctx->regions.find(region_id);
-  if (it == ctx->regions.end()) return fail(ctx, MG_EINVAL, "unknown region %lld", (long long)region_id);
-  DeviceGuard g(ctx->device);
-  Region &R = *it->second;
-  std::unique_ptr<Copy> C(new Copy());
-  C->region_id = region_id;
-  C->owner = ctx;
+}  // extern "C"
+
+// Node tables, haplotype, block table and exception runs of ONE or MANY chromosome copies ("segments",
+// MgSeg) over one packed reference: the shared body of mg_copy_build (one segment) and mg_batch_build (all
+// small regions of a BED at once).  One stream synchronisation; seg_out = the per-segment results.
+static int build_segments(mg_ctx *ctx, const uint32_t *d_ref, const MgExc *d_rexc, int n_rexc, const std::vector<MgSeg> &segs,
+                          int64_t n_var, const int64_t *pos, const uint8_t *op, const int64_t *oplen, const uint8_t *alt_pool,
+                          const int64_t *alt_off, Copy &C, std::vector<MgSegOut> &seg_out) {
   Timer tm("copy_build");
-  const int V = (int)n_var;
-  const int64_t start1 = R.bed_start + 1;            // ref_start_pos, readgenerate.py:190; also p_min
+  const int V = (int)n_var, S = (int)segs.size();
   const int64_t alt_bytes = V ? alt_off[V] : 0;
   if (alt_bytes >= (1ll << 32)) return fail(ctx, MG_EVALUE, "alt allele pool of %lld bytes exceeds 2^32", (long long)alt_bytes);
-  // the walk's chain argument needs POS sorted (records of an indexed fetch always are)
-  for (int i = 1; i < V; i++)
-    if (pos[i] < pos[i - 1]) return fail(ctx, MG_EVALUE, "variants are not sorted by POS (record %d: %lld after %lld)", i, (long long)pos[i], (long long)pos[i - 1]);
+  // the walk's chain argument needs POS sorted inside every segment (records of an indexed fetch always are)
+  for (const MgSeg &sg : segs)
+    for (int i = sg.v0 + 1; i < sg.v1; i++)
+      if (pos[i] < pos[i - 1]) return fail(ctx, MG_EVALUE, "variants are not sorted by POS (record %d: %lld after %lld)", i - sg.v0, (long long)pos[i], (long long)pos[i - 1]);
   tm.lap("check");
 
   // -- scratch layout (all 16-byte aligned): variant arrays, walk state, node-sized arrays, alt pool
-  const size_t nv = (size_t)V, max_nodes = 2 * nv + 1;
+  const size_t nv = (size_t)V, ns = (size_t)S, ne = nv + ns, max_nodes = 2 * nv + ns;
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t o = 0;
   const size_t o_pos = o; o += al(8 * (nv + 1));
@@ -504,17 +501,19 @@ int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *
   const size_t o_j1 = o; o += al(4 * (nv + 1));
   const size_t o_pred = o; o += al(4 * (nv + 1));
   const size_t o_mark = o; o += al(nv + 1);
-  const size_t o_packed = o; o += al(8 * (nv + 2));
-  const size_t o_scanned = o; o += al(8 * (nv + 3));
-  const size_t o_tmp = o; o += al(8 * ((max_nodes + 2) / 1024 + 4));
-  const size_t o_nalt = o; o += al(4 * max_nodes);
+  const size_t o_packed = o; o += al(8 * (ne + 2));
+  const size_t o_scanned = o; o += al(8 * (ne + 3));
+  const size_t o_tmp = o; o += al(8 * ((std::max(max_nodes, ne) + 2) / 1024 + 4));
+  const size_t o_nalt = o; o += al(4 * (max_nodes + 1));
   const size_t o_ecnt = o; o += al(8 * (max_nodes + 2));
   const size_t o_eoff = o; o += al(8 * (max_nodes + 3));
   const size_t o_sum = o; o += al(sizeof(MgWalkSummary));
+  const size_t o_seg = o; o += al(sizeof(MgSeg) * ns);
+  const size_t o_segout = o; o += al(sizeof(MgSegOut) * ns);
   const size_t o_alt = o; o += al((size_t)alt_bytes + 16);
   CU(ctx->s_str.need(o));
   uint8_t *sb = ctx->s_str.as<uint8_t>();
-  CU(pool_get(ctx, (void **)&C->d_nodes, sizeof(MgNode) * max_nodes));
+  CU(pool_get(ctx, (void **)&C.d_nodes, sizeof(MgNode) * std::max<size_t>(max_nodes, 1)));
   if (V) {
     CU(cudaMemcpyAsync(sb + o_pos, pos, 8 * nv, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(sb + o_oplen, oplen, 8 * nv, cudaMemcpyHostToDevice, ctx->stream));
@@ -522,27 +521,31 @@ int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *
     CU(cudaMemcpyAsync(sb + o_op, op, nv, cudaMemcpyHostToDevice, ctx->stream));
     if (alt_bytes) CU(cudaMemcpyAsync(sb + o_alt, alt_pool, (size_t)alt_bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
+  CU(cudaMemcpyAsync(sb + o_seg, segs.data(), sizeof(MgSeg) * ns, cudaMemcpyHostToDevice, ctx->stream));
   MgWalkParams W;
   W.pos = reinterpret_cast<int64_t *>(sb + o_pos); W.oplen = reinterpret_cast<int64_t *>(sb + o_oplen);
   W.alt_off = reinterpret_cast<int64_t *>(sb + o_altoff); W.op = sb + o_op;
-  W.n_var = V; W.start1 = start1; W.region_len = R.len;
+  W.n_var = V;
+  W.segs = reinterpret_cast<const MgSeg *>(sb + o_seg); W.n_seg = S; W.seg_out = reinterpret_cast<MgSegOut *>(sb + o_segout);
   W.nxt = reinterpret_cast<uint32_t *>(sb + o_nxt);
   W.jump[0] = reinterpret_cast<uint32_t *>(sb + o_j0); W.jump[1] = reinterpret_cast<uint32_t *>(sb + o_j1);
   W.mark = sb + o_mark; W.pred = reinterpret_cast<int32_t *>(sb + o_pred);
   W.packed = reinterpret_cast<int64_t *>(sb + o_packed); W.scanned = reinterpret_cast<int64_t *>(sb + o_scanned);
   W.scan_tmp = reinterpret_cast<int64_t *>(sb + o_tmp);
-  W.nodes = C->d_nodes; W.node_alt = reinterpret_cast<uint32_t *>(sb + o_nalt);
+  W.nodes = C.d_nodes; W.node_alt = reinterpret_cast<uint32_t *>(sb + o_nalt);
   W.sum = reinterpret_cast<MgWalkSummary *>(sb + o_sum);
   ctx->total_launches += mg_launch_walk(W, ctx->stream) + 4;   // + exception count and its scan
   // exception runs of the copy: count per node, scan
   int64_t *e_cnt = reinterpret_cast<int64_t *>(sb + o_ecnt), *e_off = reinterpret_cast<int64_t *>(sb + o_eoff);
-  mg_launch_exc_count(C->d_nodes, W.node_alt, W.sum, (int)max_nodes, start1, sb + o_alt, R.d_exc, (int)R.exc.size(), e_cnt, ctx->stream);
+  mg_launch_exc_count(C.d_nodes, W.node_alt, W.sum, (int)max_nodes, sb + o_alt, d_rexc, n_rexc, e_cnt, ctx->stream);
   mg_launch_scan_i64(e_cnt, e_off, (int64_t)max_nodes, W.scan_tmp, ctx->stream);
   CU(cudaGetLastError());
   MgWalkSummary sum;
   int64_t n_exc = 0;
+  seg_out.resize(ns);
   CU(cudaMemcpyAsync(&sum, W.sum, sizeof sum, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(&n_exc, e_off + max_nodes, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(seg_out.data(), W.seg_out, sizeof(MgSegOut) * ns, cudaMemcpyDeviceToHost, ctx->stream));
   tm.lap("enqueue walk");
   CU(cudaStreamSynchronize(ctx->stream));             // also: the caller's arrays have been consumed
   tm.lap("walk");
@@ -562,32 +565,54 @@ int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *
   const size_t nn = (size_t)sum.n_nodes;
   const int64_t hap_len = sum.hap_len;
   if (hap_len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "haplotype of %lld bases exceeds 2^32", (long long)hap_len);
-  C->n_nodes = (int64_t)nn;
-  C->p_min = start1;                                  // readgenerate.py:192: nodes[0].ps
-  C->p_max = start1 + hap_len;                        // nodes[-1].ps + nodes[-1].oplen (the last node is never 'D')
-  C->n_exc = n_exc;
+  C.n_nodes = (int64_t)nn;
+  C.n_exc = n_exc;
+  C.hap_len = hap_len;
 
   // -- device builds that need the sizes: exception runs, haplotype, block table
-  C->hap_words = (hap_len + 15) / 16;
-  C->n_blk = (int)((hap_len >> BLK_SHIFT) + 1);
-  CU(pool_get(ctx, (void **)&C->d_hap, sizeof(uint32_t) * (C->hap_words + 2 * MG_HAP_PAD)));
-  CU(pool_get(ctx, (void **)&C->d_blk, sizeof(uint32_t) * C->n_blk));
-  CU(pool_get(ctx, (void **)&C->d_exc, sizeof(MgExc) * std::max<size_t>(1, (size_t)n_exc)));
-  if (n_exc) mg_launch_exc_write(C->d_nodes, W.node_alt, W.sum, (int)max_nodes, start1, sb + o_alt, R.d_exc, (int)R.exc.size(), e_off, C->d_exc, ctx->stream);
-  CU(cudaMemsetAsync(C->d_hap, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
-  CU(cudaMemsetAsync(C->d_hap + MG_HAP_PAD + C->hap_words, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
+  C.hap_words = (hap_len + 15) / 16;
+  C.n_blk = (int)((hap_len >> BLK_SHIFT) + 1);
+  CU(pool_get(ctx, (void **)&C.d_hap, sizeof(uint32_t) * (C.hap_words + 2 * MG_HAP_PAD)));
+  CU(pool_get(ctx, (void **)&C.d_blk, sizeof(uint32_t) * C.n_blk));
+  CU(pool_get(ctx, (void **)&C.d_exc, sizeof(MgExc) * std::max<size_t>(1, (size_t)n_exc)));
+  if (n_exc) mg_launch_exc_write(C.d_nodes, W.node_alt, W.sum, (int)max_nodes, sb + o_alt, d_rexc, n_rexc, e_off, C.d_exc, ctx->stream);
+  CU(cudaMemsetAsync(C.d_hap, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
+  CU(cudaMemsetAsync(C.d_hap + MG_HAP_PAD + C.hap_words, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
   if (hap_len > 0)
-    mg_launch_hap_build(R.d_ref + MG_HAP_PAD, sb + o_alt, C->d_nodes, W.node_alt, (int)nn, start1, (uint32_t)hap_len,
-                        C->d_hap + MG_HAP_PAD, C->hap_words, ctx->stream);
-  mg_launch_blk_table(C->d_nodes, (int)nn, C->d_blk, C->n_blk, BLK_SHIFT, ctx->stream);
+    mg_launch_hap_build(d_ref, sb + o_alt, C.d_nodes, W.node_alt, (int)nn, (uint32_t)hap_len, C.d_hap + MG_HAP_PAD, C.hap_words, ctx->stream);
+  mg_launch_blk_table(C.d_nodes, (int)nn, C.d_blk, C.n_blk, BLK_SHIFT, ctx->stream);
   ctx->total_launches += 2 + (n_exc ? 1 : 0);
   CU(cudaGetLastError());
   tm.lap("enqueue build");                            // stream-ordered: units launched next wait for these kernels
+  return MG_OK;
+}
 
+extern "C" {
+
+int mg_copy_build(mg_ctx *ctx, int64_t region_id, int64_t n_var, const int64_t *pos, const uint8_t *op, const int64_t *oplen,
+                  const uint8_t *alt_pool, const int64_t *alt_off, int64_t *copy_id, int64_t *p_min, int64_t *p_max,
+                  int64_t *n_nodes) {
+  if (!ctx || !copy_id || n_var < 0 || (n_var > 0 && (!pos || !op || !oplen || !alt_pool || !alt_off)))
+    return fail(ctx, MG_EINVAL, "mg_copy_build: bad arguments");
+  if (n_var >= (1ll << 28)) return fail(ctx, MG_EVALUE, "%lld variants on one copy (limit 2^28)", (long long)n_var);
+  auto it = ctx->regions.find(region_id);
+  if (it == ctx->regions.end()) return fail(ctx, MG_EINVAL, "unknown region %lld", (long long)region_id);
+  DeviceGuard g(ctx->device);
+  Region &R = *it->second;
+  std::unique_ptr<Copy> C(new Copy());
+  C->region_id = region_id;
+  C->owner = ctx;
+  MgSeg sg; memset(&sg, 0, sizeof sg);
+  sg.v0 = 0; sg.v1 = (int32_t)n_var; sg.roff = 0; sg.start1 = R.bed_start + 1; sg.region_len = R.len;   // ref_start_pos, readgenerate.py:190; also p_min
+  std::vector<MgSegOut> so;
+  const int rc = build_segments(ctx, R.d_ref + MG_HAP_PAD, R.d_exc, (int)R.exc.size(), std::vector<MgSeg>(1, sg), n_var, pos, op, oplen, alt_pool, alt_off, *C, so);
+  if (rc) return rc;
+  C->p_min = sg.start1;                               // readgenerate.py:192: nodes[0].ps
+  C->p_max = sg.start1 + C->hap_len;                  // nodes[-1].ps + nodes[-1].oplen (the last node is never 'D')
   int64_t id = ctx->next_id++;
   if (p_min) *p_min = C->p_min;
   if (p_max) *p_max = C->p_max;
-  if (n_nodes) *n_nodes = (int64_t)nn;
+  if (n_nodes) *n_nodes = C->n_nodes;
   ctx->copies[id] = std::move(C);
   *copy_id = id;
   return MG_OK;

@@ -78,30 +78,48 @@ struct MgCorruptParams {     // standalone corrupt-reads over FASTQ resident in 
 // launchers (all asynchronous on `st`)
 void mg_launch_pack_ref(const uint8_t *raw, int64_t len, uint32_t *packed, uint32_t *exc_cnt, int64_t *exc_start,
                         uint8_t *exc_byte, int64_t *exc_end, uint32_t exc_cap, cudaStream_t st);
-// device node-list walk (k_walk_*): inputs are the copy's variants, sorted by POS
+// device node-list walk (k_walk_*).  The variants of one or MANY chromosome copies ("segments": one per
+// (BED region, copy)), concatenated, each segment sorted by POS.  One launch sequence builds the node
+// tables of all segments back to back: node keys / haplotype coordinates run through the concatenation
+// (segment s owns [hap_base, hap_base + hap_len)), so a batch of small regions is ONE node table, ONE
+// haplotype and ONE block table.
+struct MgSeg {                // input, per segment
+  int32_t v0, v1;             // its variants: [v0, v1) of the concatenated arrays
+  uint32_t roff;              // offset of its region's first base in the (concatenated) packed reference
+  uint32_t pad;
+  int64_t start1;             // ref_start_pos = bed_start + 1 (readgenerate.py:190); also p_min
+  int64_t region_len;
+};
+struct MgSegOut {             // output, per segment
+  uint32_t hap_base, hap_len; // its haplotype: [hap_base, hap_base + hap_len) of the concatenation; p_max - p_min = hap_len
+  int32_t i0, last;           // first / last accepted variant (-1: none)
+  int32_t ends_in_d;          // a deletion crossed the region end: the reference's list would end in 'D'
+  uint32_t node0, n_nodes;    // its nodes: [node0, node0 + n_nodes)
+  uint32_t pad;
+};
 struct MgWalkSummary {
   unsigned long long err;     // (variant index << 8 | code) of the first invalid accepted variant, ~0 if none
-  long long n_nodes, hap_len; // nodes written; p_max - p_min
-  uint32_t i0; int32_t last;  // first / last accepted variant
+  long long n_nodes, hap_len; // nodes written; length of the concatenated haplotype
   int32_t ends_in_d, bad;
 };
 
 struct MgWalkParams {
   const int64_t *pos, *oplen, *alt_off; const uint8_t *op;
-  int n_var; int64_t start1, region_len;
+  int n_var;
+  const MgSeg *segs; int n_seg; MgSegOut *seg_out;
   uint32_t *nxt, *jump[2]; uint8_t *mark; int32_t *pred;
-  int64_t *packed, *scanned, *scan_tmp;
-  MgNode *nodes; uint32_t *node_alt;
+  int64_t *packed, *scanned, *scan_tmp;     // n_var + n_seg (+ 1) elements: every segment has a tail element after its variants
+  MgNode *nodes; uint32_t *node_alt;        // node_alt: source of the node's bases -- '=': offset in the packed reference; 'X' / 'I': offset in the alt pool
   MgWalkSummary *sum;
 };
 
 int mg_launch_walk(const MgWalkParams &W, cudaStream_t st);   // -> number of kernels launched
-void mg_launch_exc_count(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes, int64_t start1,
+void mg_launch_exc_count(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes,
                          const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *cnt, cudaStream_t st);
-void mg_launch_exc_write(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes, int64_t start1,
+void mg_launch_exc_write(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes,
                          const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *off, MgExc *out, cudaStream_t st);
 void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const MgNode *nodes, const uint32_t *node_alt,
-                         int n_seg, int64_t start1, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st);
+                         int n_nodes, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st);
 void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st);
 void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
                         cudaStream_t st);

@@ -15,6 +15,7 @@
 //   k_scan_*          generic exclusive scan (int64)
 //   k_nl_*            FASTQ newline index
 //   k_corrupt_*       standalone corrupt-reads over FASTQ in HBM
+#include <algorithm>
 #include <cstdlib>
 #include "mg_internal.h"
 
@@ -127,13 +128,25 @@ __device__ __forceinline__ int64_t walk_end_ref(const int64_t *pos, const uint8_
   return pos[i] + 1 + (op[i] == 'D' ? oplen[i] : 0);
 }
 
-__device__ __forceinline__ uint32_t walk_lower_bound(const int64_t *pos, int V, int64_t x) {   // first j with pos[j] >= x
-  int lo = 0, hi = V;
+__device__ __forceinline__ int walk_lower_bound(const int64_t *pos, int lo, int hi, int64_t x) {   // first j in [lo, hi) with pos[j] >= x, hi if none
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (pos[mid] < x) lo = mid + 1; else hi = mid;
   }
-  return (uint32_t)lo;
+  return lo;
+}
+
+// segment of variant i: the last segment with v0 <= i (empty segments share their v0 with the next one)
+__device__ __forceinline__ int seg_of_var(const MgSeg *segs, int n_seg, int i) {
+  int lo = 0, hi = n_seg - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].v0 <= i) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+// segment of element e (the elements of segment s are its variants v0 + s .. v1 + s - 1 and its tail v1 + s)
+__device__ __forceinline__ int seg_of_elem(const MgSeg *segs, int n_seg, int e) {
+  int lo = 0, hi = n_seg - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].v0 + mid <= e) lo = mid; else hi = mid - 1; }
+  return lo;
 }
 
 __device__ __forceinline__ void walk_error(MgWalkSummary *sum, int idx, int code) {   // the first error in variant order wins
@@ -141,48 +154,69 @@ __device__ __forceinline__ void walk_error(MgWalkSummary *sum, int idx, int code
 }
 
 __global__ void __launch_bounds__(256) k_walk_next(const int64_t *__restrict__ pos, const uint8_t *__restrict__ op,
-                                                   const int64_t *__restrict__ oplen, int V, int64_t start1, uint32_t *__restrict__ nxt,
+                                                   const int64_t *__restrict__ oplen, int V, const MgSeg *__restrict__ segs, int n_seg,
+                                                   MgSegOut *__restrict__ seg_out, uint32_t *__restrict__ nxt,
                                                    uint32_t *__restrict__ jump, uint8_t *__restrict__ mark, int32_t *__restrict__ pred,
                                                    MgWalkSummary *sum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
-    sum->i0 = walk_lower_bound(pos, V, start1);      // variants before the region start are skipped (rpc.py:55)
-    sum->last = -1; sum->err = ~0ull; sum->n_nodes = 0; sum->hap_len = 0; sum->ends_in_d = 0; sum->bad = 0;
+  if (i == 0) { sum->err = ~0ull; sum->n_nodes = 0; sum->hap_len = 0; sum->ends_in_d = 0; sum->bad = 0; }
+  if (i < n_seg) {                                   // variants before the region start are skipped (rpc.py:55)
+    const MgSeg sg = segs[i];
+    const int j = walk_lower_bound(pos, sg.v0, sg.v1, sg.start1);
+    MgSegOut o; o.hap_base = 0; o.hap_len = 0; o.i0 = j < sg.v1 ? j : -1; o.last = -1; o.ends_in_d = 0; o.node0 = 0; o.n_nodes = 0; o.pad = 0;
+    seg_out[i] = o;
   }
   if (i >= V) return;
-  const uint32_t j = walk_lower_bound(pos, V, walk_end_ref(pos, op, oplen, i));
-  nxt[i] = j; jump[i] = j; mark[i] = 0; pred[i] = -1;
+  const MgSeg sg = segs[seg_of_var(segs, n_seg, i)];
+  const int j = walk_lower_bound(pos, sg.v0, sg.v1, walk_end_ref(pos, op, oplen, i));
+  const uint32_t jj = j < sg.v1 ? (uint32_t)j : (uint32_t)V;          // the chain ends at its segment's end
+  nxt[i] = jj; jump[i] = jj; mark[i] = 0; pred[i] = -1;
+}
+
+__global__ void __launch_bounds__(256) k_walk_seed(const MgSegOut *__restrict__ seg_out, int n_seg, uint8_t *mark) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_seg && seg_out[s].i0 >= 0) mark[seg_out[s].i0] = 1;       // every segment's chain starts at its first accepted variant
 }
 
 // one doubling round: marked variants mark the variant 2^k links ahead, links double
-__global__ void __launch_bounds__(256) k_walk_round(const uint32_t *__restrict__ jin, uint32_t *__restrict__ jout, uint8_t *mark,
-                                                    const MgWalkSummary *__restrict__ sum, int V) {
+__global__ void __launch_bounds__(256) k_walk_round(const uint32_t *__restrict__ jin, uint32_t *__restrict__ jout, uint8_t *mark, int V) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V) return;
   const uint32_t j = jin[i];
-  const bool first = (uint32_t)i == sum->i0;
-  if (first) mark[i] = 1;
-  if ((first || mark[i]) && j < (uint32_t)V) mark[j] = 1;
+  if (mark[i] && j < (uint32_t)V) mark[j] = 1;
   jout[i] = j < (uint32_t)V ? jin[j] : (uint32_t)V;
 }
 
 __global__ void __launch_bounds__(256) k_walk_pred(const uint32_t *__restrict__ nxt, const uint8_t *__restrict__ mark,
-                                                   int32_t *__restrict__ pred, MgWalkSummary *sum, int V) {
+                                                   int32_t *__restrict__ pred, const MgSeg *__restrict__ segs, int n_seg,
+                                                   MgSegOut *__restrict__ seg_out, int V) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V || !mark[i]) return;
   const uint32_t j = nxt[i];
-  if (j < (uint32_t)V) pred[j] = i; else sum->last = i;
+  if (j < (uint32_t)V) pred[j] = i; else seg_out[seg_of_var(segs, n_seg, i)].last = i;
 }
 
-// per accepted variant: node count and sample-space advance, packed for one scan; validation
+// per element (accepted variant, or the tail of a segment): node count and sample-space advance, packed for one scan
 __global__ void __launch_bounds__(256) k_walk_measure(const int64_t *__restrict__ pos, const uint8_t *__restrict__ op,
                                                       const int64_t *__restrict__ oplen, const int64_t *__restrict__ alt_off,
                                                       const uint8_t *__restrict__ mark, const int32_t *__restrict__ pred, int V,
-                                                      int64_t start1, int64_t region_len, int64_t *__restrict__ packed, MgWalkSummary *sum) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > V) return;
-  if (i == V || !mark[i]) { packed[i] = 0; return; }
-  const int64_t R = pred[i] < 0 ? start1 : walk_end_ref(pos, op, oplen, pred[i]);
+                                                      const MgSeg *__restrict__ segs, int n_seg, const MgSegOut *__restrict__ seg_out,
+                                                      int64_t *__restrict__ packed, MgWalkSummary *sum) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= V + n_seg) return;
+  const int s = seg_of_elem(segs, n_seg, e);
+  const MgSeg sg = segs[s];
+  const int i = e - s;
+  if (i >= sg.v1) {                                     // the tail '=' node (rpc.py:58-61), absent when a deletion crossed the region end
+    const int last = seg_out[s].last;
+    const int64_t refp = last < 0 ? sg.start1 : walk_end_ref(pos, op, oplen, last);
+    const int64_t offset = refp - sg.start1;
+    const bool has = offset <= sg.region_len;
+    packed[e] = has ? (int64_t)((1ull << MG_WALK_ADV_BITS) | (unsigned long long)(sg.region_len - offset)) : 0;
+    return;
+  }
+  if (!mark[i]) { packed[e] = 0; return; }
+  const int64_t R = pred[i] < 0 ? sg.start1 : walk_end_ref(pos, op, oplen, pred[i]);
   const int64_t vp = pos[i], alt_len = alt_off[i + 1] - alt_off[i];
   int64_t delta, adv, cnt;
   if (op[i] == 'X') {                                   // rpc.py:75-87
@@ -198,45 +232,60 @@ __global__ void __launch_bounds__(256) k_walk_measure(const int64_t *__restrict_
     delta = 0; cnt = 0; adv = 0;
     walk_error(sum, i, 3);
   }
-  if ((R - start1) + delta > region_len || oplen[i] > 0x7FFFFFFFll || adv < 0 || adv > (int64_t)MG_WALK_ADV_MASK) { sum->bad = 1; adv = 0; }
-  packed[i] = (int64_t)(((unsigned long long)cnt << MG_WALK_ADV_BITS) | (unsigned long long)adv);
+  if ((R - sg.start1) + delta > sg.region_len || oplen[i] > 0x7FFFFFFFll || adv < 0 || adv > (int64_t)MG_WALK_ADV_MASK) { sum->bad = 1; adv = 0; }
+  packed[e] = (int64_t)(((unsigned long long)cnt << MG_WALK_ADV_BITS) | (unsigned long long)adv);
 }
 
-// node table + per-node alt-pool offsets; the thread past the last variant writes the tail node
-// (rpc.py:58-61) and the summary
+// node table + per-node sources; a segment's tail element also writes the segment's summary
 __global__ void __launch_bounds__(256) k_walk_nodes(const int64_t *__restrict__ pos, const uint8_t *__restrict__ op,
                                                     const int64_t *__restrict__ oplen, const int64_t *__restrict__ alt_off,
                                                     const uint8_t *__restrict__ mark, const int32_t *__restrict__ pred, int V,
-                                                    int64_t start1, int64_t region_len, const int64_t *__restrict__ scanned,
+                                                    const MgSeg *__restrict__ segs, int n_seg, MgSegOut *__restrict__ seg_out,
+                                                    const int64_t *__restrict__ scanned,
                                                     MgNode *__restrict__ nodes, uint32_t *__restrict__ node_alt, MgWalkSummary *sum) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > V) return;
-  const unsigned long long pre = (unsigned long long)scanned[i];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int E = V + n_seg;
+  if (e == E) {                                          // totals
+    const unsigned long long tot = (unsigned long long)scanned[E];
+    sum->n_nodes = (long long)(tot >> MG_WALK_ADV_BITS); sum->hap_len = (long long)(tot & MG_WALK_ADV_MASK);
+    return;
+  }
+  if (e > E) return;
+  const int s = seg_of_elem(segs, n_seg, e);
+  const MgSeg sg = segs[s];
+  const int i = e - s;
+  const unsigned long long pre = (unsigned long long)scanned[e];
   uint32_t k = (uint32_t)(pre >> MG_WALK_ADV_BITS);
-  int64_t S = (int64_t)(pre & MG_WALK_ADV_MASK);          // sample position relative to p_min
-  if (i == V) {
-    const int last = sum->last;
-    const int64_t refp = last < 0 ? start1 : walk_end_ref(pos, op, oplen, last);
-    const int64_t offset = refp - start1;
-    if (offset <= region_len) {
-      if (S >= 0xFFF00000ll || refp >= (1ll << 31)) sum->bad = 1;
-      nodes[k] = MgNode{(uint32_t)S, (int32_t)refp, (int32_t)(region_len - offset), '='};
-      node_alt[k] = 0;
-      sum->n_nodes = (long long)k + 1; sum->hap_len = S + (region_len - offset); sum->ends_in_d = 0;
+  int64_t S = (int64_t)(pre & MG_WALK_ADV_MASK);          // sample position in the concatenated haplotype
+  if (i >= sg.v1) {
+    const int last = seg_out[s].last;
+    const int64_t refp = last < 0 ? sg.start1 : walk_end_ref(pos, op, oplen, last);
+    const int64_t offset = refp - sg.start1;
+    const unsigned long long first = (unsigned long long)scanned[sg.v0 + s];   // the segment's first element
+    const uint32_t node0 = (uint32_t)(first >> MG_WALK_ADV_BITS);
+    const int64_t base = (int64_t)(first & MG_WALK_ADV_MASK);
+    if (offset <= sg.region_len) {
+      if (S + (sg.region_len - offset) >= 0xFFF00000ll || refp >= (1ll << 31)) sum->bad = 1;
+      nodes[k] = MgNode{(uint32_t)S, (int32_t)refp, (int32_t)(sg.region_len - offset), '='};
+      node_alt[k] = sg.roff + (uint32_t)offset;
+      seg_out[s].hap_base = (uint32_t)base; seg_out[s].hap_len = (uint32_t)(S + (sg.region_len - offset) - base);
+      seg_out[s].node0 = node0; seg_out[s].n_nodes = k + 1 - node0; seg_out[s].ends_in_d = 0;
     } else {                                              // a deletion crossed the region end: the list ends in 'D'
-      sum->n_nodes = k; sum->hap_len = S; sum->ends_in_d = 1;
+      seg_out[s].hap_base = (uint32_t)base; seg_out[s].hap_len = (uint32_t)(S - base);
+      seg_out[s].node0 = node0; seg_out[s].n_nodes = k - node0; seg_out[s].ends_in_d = 1;
+      sum->ends_in_d = 1;
     }
     return;
   }
   if (!mark[i]) return;
-  const int64_t R = pred[i] < 0 ? start1 : walk_end_ref(pos, op, oplen, pred[i]);
+  const int64_t R = pred[i] < 0 ? sg.start1 : walk_end_ref(pos, op, oplen, pred[i]);
   const int64_t vp = pos[i];
   const uint8_t o = op[i];
   const int64_t delta = (o == 'X') ? vp - R : vp + 1 - R;
   if (S + delta + (o == 'I' ? oplen[i] : 1) >= 0xFFF00000ll || vp + 1 + (o == 'D' ? oplen[i] : 0) >= (1ll << 31)) { sum->bad = 1; return; }
   if (delta > 0) {
     nodes[k] = MgNode{(uint32_t)S, (int32_t)R, (int32_t)delta, '='};
-    node_alt[k] = 0;
+    node_alt[k] = sg.roff + (uint32_t)(R - sg.start1);
     k++; S += delta;
   }
   if (o == 'X') { nodes[k] = MgNode{(uint32_t)S, (int32_t)vp, 1, 'X'}; node_alt[k] = (uint32_t)alt_off[i]; }
@@ -245,28 +294,29 @@ __global__ void __launch_bounds__(256) k_walk_nodes(const int64_t *__restrict__ 
 }
 
 int mg_launch_walk(const MgWalkParams &W, cudaStream_t st) {   // -> kernels launched
-  const int V = W.n_var;
-  const unsigned g = (unsigned)((V + 1 + 255) / 256);
-  k_walk_next<<<g, 256, 0, st>>>(W.pos, W.op, W.oplen, V, W.start1, W.nxt, W.jump[0], W.mark, W.pred, W.sum);
+  const int V = W.n_var, E = V + W.n_seg;
+  const unsigned gv = (unsigned)((std::max(V + 1, W.n_seg) + 255) / 256), ge = (unsigned)((E + 1 + 255) / 256);
+  k_walk_next<<<gv, 256, 0, st>>>(W.pos, W.op, W.oplen, V, W.segs, W.n_seg, W.seg_out, W.nxt, W.jump[0], W.mark, W.pred, W.sum);
   int cur = 0, launches = 6;       // next, measure, 3 x scan, nodes
   if (V > 0) {
+    k_walk_seed<<<(unsigned)((W.n_seg + 255) / 256), 256, 0, st>>>(W.seg_out, W.n_seg, W.mark);
     int rounds = 1;
     while ((1ll << rounds) < (long long)V + 1) rounds++;
-    for (int r = 0; r < rounds; r++) { k_walk_round<<<g, 256, 0, st>>>(W.jump[cur], W.jump[cur ^ 1], W.mark, W.sum, V); cur ^= 1; }
-    k_walk_pred<<<g, 256, 0, st>>>(W.nxt, W.mark, W.pred, W.sum, V);
-    launches += rounds + 1;
+    for (int r = 0; r < rounds; r++) { k_walk_round<<<gv, 256, 0, st>>>(W.jump[cur], W.jump[cur ^ 1], W.mark, V); cur ^= 1; }
+    k_walk_pred<<<gv, 256, 0, st>>>(W.nxt, W.mark, W.pred, W.segs, W.n_seg, W.seg_out, V);
+    launches += rounds + 2;
   }
-  k_walk_measure<<<g, 256, 0, st>>>(W.pos, W.op, W.oplen, W.alt_off, W.mark, W.pred, V, W.start1, W.region_len, W.packed, W.sum);
-  mg_launch_scan_i64(W.packed, W.scanned, (int64_t)V + 1, W.scan_tmp, st);
-  k_walk_nodes<<<g, 256, 0, st>>>(W.pos, W.op, W.oplen, W.alt_off, W.mark, W.pred, V, W.start1, W.region_len, W.scanned, W.nodes, W.node_alt, W.sum);
+  k_walk_measure<<<ge, 256, 0, st>>>(W.pos, W.op, W.oplen, W.alt_off, W.mark, W.pred, V, W.segs, W.n_seg, W.seg_out, W.packed, W.sum);
+  mg_launch_scan_i64(W.packed, W.scanned, (int64_t)E, W.scan_tmp, st);
+  k_walk_nodes<<<ge, 256, 0, st>>>(W.pos, W.op, W.oplen, W.alt_off, W.mark, W.pred, V, W.segs, W.n_seg, W.seg_out, W.scanned, W.nodes, W.node_alt, W.sum);
   return launches;
 }
 
-// exception runs of a copy in sample coordinates: the region's non-ACGT runs under every '='
-// node, non-ACGT bytes of inserted / substituted alleles.  Count, scan, write.
+// exception runs of the node table in haplotype coordinates: the reference's non-ACGT runs under every
+// '=' node, non-ACGT bytes of inserted / substituted alleles.  Count, scan, write.
 template <bool WRITE>
 __global__ void __launch_bounds__(256) k_exc_map(const MgNode *__restrict__ nodes, const uint32_t *__restrict__ node_alt,
-                                                 const MgWalkSummary *__restrict__ sum, int max_nodes, int64_t start1,
+                                                 const MgWalkSummary *__restrict__ sum, int max_nodes,
                                                  const uint8_t *__restrict__ alt_pool, const MgExc *__restrict__ rexc, int n_rexc,
                                                  int64_t *cnt_or_off, MgExc *__restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,7 +325,7 @@ __global__ void __launch_bounds__(256) k_exc_map(const MgNode *__restrict__ node
   const MgNode nd = nodes[k];
   int64_t c = WRITE ? cnt_or_off[k] : 0;
   if (nd.op == '=' && nd.oplen > 0) {
-    const int64_t a = (int64_t)nd.pr - start1, b = a + nd.oplen;
+    const int64_t a = (int64_t)node_alt[k], b = a + nd.oplen;   // the node's bases in the packed reference
     int lo = 0, hi = n_rexc;                                  // first run that ends after a
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -301,14 +351,14 @@ __global__ void __launch_bounds__(256) k_exc_map(const MgNode *__restrict__ node
   if (!WRITE) cnt_or_off[k] = c;
 }
 
-void mg_launch_exc_count(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes, int64_t start1,
+void mg_launch_exc_count(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes,
                          const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *cnt, cudaStream_t st) {
-  k_exc_map<false><<<(unsigned)((max_nodes + 255) / 256), 256, 0, st>>>(nodes, node_alt, sum, max_nodes, start1, alt_pool, rexc, n_rexc, cnt, nullptr);
+  k_exc_map<false><<<(unsigned)((max_nodes + 255) / 256), 256, 0, st>>>(nodes, node_alt, sum, max_nodes, alt_pool, rexc, n_rexc, cnt, nullptr);
 }
 
-void mg_launch_exc_write(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes, int64_t start1,
+void mg_launch_exc_write(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes,
                          const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *off, MgExc *out, cudaStream_t st) {
-  k_exc_map<true><<<(unsigned)((max_nodes + 255) / 256), 256, 0, st>>>(nodes, node_alt, sum, max_nodes, start1, alt_pool, rexc, n_rexc, off, out);
+  k_exc_map<true><<<(unsigned)((max_nodes + 255) / 256), 256, 0, st>>>(nodes, node_alt, sum, max_nodes, alt_pool, rexc, n_rexc, off, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -316,13 +366,13 @@ void mg_launch_exc_write(const MgNode *nodes, const uint32_t *node_alt, const Mg
 // node k covers [key[k], key[k+1]) ('D' nodes share the key of their successor and are empty).
 // '=' nodes copy from the packed reference, 'X' / 'I' nodes from the alt pool.
 
-__device__ __forceinline__ uint64_t hap_node_src(const MgNode &nd, uint32_t alt, int64_t start1) {
-  return nd.op == '=' ? (uint64_t)((int64_t)nd.pr - start1) : ((1ull << 63) | (uint64_t)alt);
+__device__ __forceinline__ uint64_t hap_node_src(const MgNode &nd, uint32_t alt) {   // '=': offset in the packed reference; else in the alt pool
+  return nd.op == '=' ? (uint64_t)alt : ((1ull << 63) | (uint64_t)alt);
 }
 
 __global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ ref, const uint8_t *__restrict__ alt_pool,
                                                    const MgNode *__restrict__ nodes, const uint32_t *__restrict__ node_alt,
-                                                   int n_seg, int64_t start1, uint32_t hap_len, uint32_t *__restrict__ hap, int64_t hap_words) {
+                                                   int n_seg, uint32_t hap_len, uint32_t *__restrict__ hap, int64_t hap_words) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= hap_words) return;
   uint64_t s0 = (uint64_t)w * 16;
@@ -336,7 +386,7 @@ __global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ 
   int k = lo;
   MgNode nd = nodes[k];
   uint64_t seg_end = (k + 1 < n_seg) ? nodes[k + 1].key : hap_len;
-  uint64_t src = hap_node_src(nd, node_alt[k], start1);
+  uint64_t src = hap_node_src(nd, node_alt[k]);
   uint32_t word;
   if (!(src >> 63) && s0 + 16 <= seg_end) {
     word = mg_codes16(ref, (int64_t)(src + (s0 - nd.key)));        // whole word from the reference
@@ -348,7 +398,7 @@ __global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ 
       while (s >= seg_end) {
         k++; nd = nodes[k];
         seg_end = (k + 1 < n_seg) ? nodes[k + 1].key : hap_len;
-        src = hap_node_src(nd, node_alt[k], start1);
+        src = hap_node_src(nd, node_alt[k]);
       }
       uint64_t off = s - nd.key;
       uint32_t code;
@@ -366,9 +416,9 @@ __global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ 
 }
 
 void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const MgNode *nodes, const uint32_t *node_alt,
-                         int n_seg, int64_t start1, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st) {
+                         int n_nodes, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st) {
   if (hap_words == 0) return;
-  k_hap_build<<<(unsigned)((hap_words + 255) / 256), 256, 0, st>>>(ref, alt_pool, nodes, node_alt, n_seg, start1, hap_len, hap, hap_words);
+  k_hap_build<<<(unsigned)((hap_words + 255) / 256), 256, 0, st>>>(ref, alt_pool, nodes, node_alt, n_nodes, hap_len, hap, hap_words);
 }
 
 __global__ void __launch_bounds__(256) k_blk_table(const MgNode *__restrict__ nodes, int n_nodes, uint32_t *__restrict__ blk,

@@ -156,6 +156,10 @@ int mg_sink_unit_size(mg_sink *s, int64_t unit, int64_t bytes_per_file);
 int mg_sink_acquire(mg_sink *s, int32_t producer, void **buf1, void **buf2, void **slot);
 /* bytes [offset, offset + bytes) of `unit` (both files) are in the slot: write them, recycle the slot  */
 int mg_sink_commit(mg_sink *s, void *slot, int64_t unit, int64_t offset, int64_t bytes);
+/* one slot carrying pieces of several units (a batch of small units): sub-piece i = bytes
+ * [slot_off[i], slot_off[i] + bytes[i]) of the slot = bytes [unit_off[i], ...) of unit[i]            */
+int mg_sink_commit_multi(mg_sink *s, void *slot, int32_t n, const int64_t *unit, const int64_t *unit_off, const int64_t *slot_off,
+                         const int64_t *bytes);
 void mg_sink_abort(mg_sink *s, const char *why);   /* wakes every blocked producer with an error       */
 const char *mg_sink_error(mg_sink *s);
 int64_t mg_sink_chunk_bytes(mg_sink *s);          /* bytes per slot, as given at creation             */
@@ -168,6 +172,32 @@ int mg_sink_close(mg_sink *s, int64_t *written1, int64_t *written2);
  * unit after next waits for this one's device buffers.  mg_drain_wait: everything queued is committed. */
 int mg_unit_drain_async(mg_ctx *ctx, mg_sink *sink, int32_t producer, int64_t unit);
 int mg_drain_wait(mg_ctx *ctx);
+
+/* ---- batches of small regions (an exome-style BED): what read_generating_worker does region by region
+ * and unit by unit (mitty/simulation/readgenerate.py:183-214) for MANY (region, copy) pairs and MANY
+ * work units in a handful of launches.  mg_batch_build packs the regions' reference bytes
+ * (ref_bytes[ref_off[r] .. ref_off[r + 1]), ref_off[0] = 0) back to back and builds ONE node table /
+ * haplotype / block table over all segments (a segment = one chromosome copy of one region: its variants
+ * are [seg_var_off[s], seg_var_off[s + 1]) of the variant arrays, as for mg_copy_build); seg_p_min /
+ * seg_p_max are what readgenerate.py:192 computes per copy.  mg_batch_generate runs the units (unit_seg =
+ * segment, unit_seed = rng_seed, unit_ncand = int((p_max - p_min) * p * 1.2) <= 2048, unit_index = index
+ * in the schedule, ascending; DET mode: the units' draws concatenated, cand_off[u] = first entry of unit
+ * u, cand_off[n_units] = their number) and, with a sink, streams their FASTQ into it (every unit's size
+ * announced, then the pieces committed by the context's drain thread); without a sink the units' bytes
+ * stay on the device back to back (mg_unit_read_async).  qnames are
+ * "@<sample>:0:<unit_index>:<serial>|<chrom_pool[chrom_off[s] .. chrom_off[s + 1])>|<seg_cpy[s]>|...".
+ * unit_bytes / unit_templates (n_units entries each, may be NULL): bytes per file and templates of
+ * every unit.  The bytes equal those of mg_unit_generate unit by unit.                               */
+int mg_batch_build(mg_ctx *ctx, int64_t n_regions, const uint8_t *ref_bytes, const int64_t *ref_off, const int64_t *bed_start,
+                   int64_t n_segs, const int32_t *seg_region, const int64_t *seg_var_off, const int64_t *pos, const uint8_t *op,
+                   const int64_t *oplen, const uint8_t *alt_pool, const int64_t *alt_off, int64_t *batch_id, int64_t *seg_p_min,
+                   int64_t *seg_p_max);
+int mg_batch_free(mg_ctx *ctx, int64_t batch_id);
+int mg_batch_generate(mg_ctx *ctx, int64_t batch_id, int64_t n_units, const int32_t *unit_seg, const uint32_t *unit_seed,
+                      const int64_t *unit_ncand, const int64_t *unit_index, const char *sample, const uint8_t *chrom_pool,
+                      const int64_t *chrom_off, const int32_t *seg_cpy, double p, int32_t mode, const int64_t *ts, const double *u_tlen,
+                      const int8_t *fo, const int64_t *cand_off, int32_t corrupt, uint32_t corrupt_seed, mg_sink *sink,
+                      int32_t producer, int64_t *n_templates, int64_t *n_bytes, int64_t *unit_bytes, int64_t *unit_templates);
 
 /* ---- corrupt-reads: replaces readcorrupt.multi_process / illumina.corrupt_template
  * (mitty/simulation/readcorrupt.py:18-118, illumina.py:113-162) over whole FASTQ buffers.

@@ -61,6 +61,12 @@ struct Copy {
   ~Copy();
 };
 
+// a batch of small regions: ONE packed reference, node table, haplotype and block table over all of its segments
+struct Batch {
+  std::unique_ptr<Region> R;
+  std::unique_ptr<Copy> C;
+};
+
 const int BLK_SHIFT = 8;
 
 }  // namespace
@@ -82,10 +88,12 @@ struct mg_ctx {
   // handles
   std::map<int64_t, std::unique_ptr<Region>> regions;
   std::map<int64_t, std::unique_ptr<Copy>> copies;
+  std::map<int64_t, std::unique_ptr<Batch>> batches;
   int64_t next_id = 1;
   // scratch
   DevBuf s_raw, s_exc, s_ts, s_u, s_fo, s_tsorted, s_partial, s_state, s_out[2][2], s_str, s_plan, s_sample[3];
   DevBuf c_in[2], c_out[2], c_nl[2], c_cnt, c_sz[2], c_off[2], c_tmp, c_draw[4];
+  DevBuf b_units, b_arr;                           // a batch of small units: unit table; per-unit counts and their prefixes
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   cudaStream_t copy_stream = nullptr;              // D2H of finished units, overlapping the next unit's kernels
   cudaEvent_t ev_d2h[2] = {nullptr, nullptr};      // per output-buffer set: its last D2H has finished
@@ -94,7 +102,11 @@ struct mg_ctx {
   double plan_ms = 0;
   double emit_ms = 0; int64_t emit_launches = 0, emit_bytes = 0, total_launches = 0;
   // drain thread: streams finished units from the device output buffers into an mg_sink
-  struct DrainJob { mg_sink *sink; int producer; int64_t unit; int ob; int64_t bytes; };
+  struct DrainJob {
+    mg_sink *sink; int producer; int64_t unit; int ob; int64_t bytes;
+    // a batch of small units in one stream: their schedule indices and the prefix of their sizes (n + 1 entries)
+    std::shared_ptr<std::vector<int64_t>> units, base;
+  };
   std::thread drain_thread;
   std::mutex dmu; std::condition_variable dcv;
   std::deque<DrainJob> djobs;
@@ -297,7 +309,7 @@ void mg_ctx_destroy(mg_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (int i = 0; i < 2; i++) if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
-  ctx->regions.clear(); ctx->copies.clear();
+  ctx->batches.clear(); ctx->regions.clear(); ctx->copies.clear();
   for (auto &b : ctx->pool) cudaFree(b.first);
   ctx->pool.clear(); ctx->block_size.clear();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -398,12 +410,12 @@ int mg_model_tables(mg_ctx *ctx, int32_t which, uint32_t *alias_out, int64_t ali
 
 // ---- region ---------------------------------------------------------------------------------
 
-int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t bed_start, int64_t *region_id) {
-  if (!ctx || !region_id || len < 0 || (len > 0 && !ref_bytes)) return fail(ctx, MG_EINVAL, "mg_region_load: bad arguments");
-  if (len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "region of %lld bases exceeds the 2^32 addressing of one region", (long long)len);
-  DeviceGuard g(ctx->device);
+}  // extern "C"
+
+// raw reference bytes (host) -> 2-bit packed words + sorted exception runs of a Region (k_pack_ref)
+static int load_packed(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t bed_start, std::unique_ptr<Region> &R) {
+  R.reset(new Region());
   uint32_t exc_cap = 1u << 20;                        // grown on demand: a soft-masked chromosome has ~10^6 case runs
-  std::unique_ptr<Region> R(new Region());
   R->len = len; R->bed_start = bed_start;
   int64_t words = (len + 15) / 16;
   R->owner = ctx;
@@ -455,6 +467,18 @@ int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t b
       CU(cudaMemcpy(R->d_exc, dev.data(), sizeof(MgExc) * cnt[0], cudaMemcpyHostToDevice));
     }
   }
+  return MG_OK;
+}
+
+extern "C" {
+
+int mg_region_load(mg_ctx *ctx, const uint8_t *ref_bytes, int64_t len, int64_t bed_start, int64_t *region_id) {
+  if (!ctx || !region_id || len < 0 || (len > 0 && !ref_bytes)) return fail(ctx, MG_EINVAL, "mg_region_load: bad arguments");
+  if (len >= (int64_t)0xFFF00000ll) return fail(ctx, MG_EVALUE, "region of %lld bases exceeds the 2^32 addressing of one region", (long long)len);
+  DeviceGuard g(ctx->device);
+  std::unique_ptr<Region> R;
+  const int rc = load_packed(ctx, ref_bytes, len, bed_start, R);
+  if (rc) return rc;
   int64_t id = ctx->next_id++;
   ctx->regions[id] = std::move(R);
   *region_id = id;
@@ -690,17 +714,16 @@ static int fill_unit_params(mg_ctx *ctx, const mg_unit_desc *d, MgUnitParams &P,
     if (n) {
       CU(ctx->s_tsorted.need(4 * n + 64));
       CU(ctx->s_partial.need(8 * (n / 2048 + 2)));
-      mg_launch_gap_scan((uint32_t)n, d->p, d->unit_seed, 0x67617031u, ctx->s_tsorted.as<uint32_t>(),
+      const MgUnitKeys K0 = mg_unit_keys(d->unit_seed, (uint32_t)n);
+      mg_launch_gap_scan((uint32_t)n, d->p, K0.gap0, K0.gap1, ctx->s_tsorted.as<uint32_t>(),
                          ctx->s_partial.as<unsigned long long>(), ctx->stream);
       ctx->total_launches += 3;
     }
     P.ts_sorted = ctx->s_tsorted.as<uint32_t>();
-    P.key_tlen0 = d->unit_seed; P.key_tlen1 = 0x746c6531u;
-    P.key_perm0 = d->unit_seed ^ 0x7368756bu; P.key_perm1 = d->unit_seed * 0x9E3779B1u + 0x66656973u;
-    uint32_t bits = 2;
-    while (bits < 32 && (1ull << bits) < (unsigned long long)std::max<size_t>(n, 2)) bits++;
-    if (bits & 1) bits++;
-    P.half_bits = bits / 2;
+    const MgUnitKeys K = mg_unit_keys(d->unit_seed, (uint32_t)n);
+    P.key_tlen0 = K.tlen0; P.key_tlen1 = K.tlen1;
+    P.key_perm0 = K.perm0; P.key_perm1 = K.perm1;
+    P.half_bits = K.half_bits;
   } else if (d->mode == MG_MODE_DET || d->mode == MG_MODE_EXPLICIT) {
     if (n && (!d->ts || (!d->fo && !sample_only) || (d->mode == MG_MODE_DET ? !d->u_tlen : !d->tl))) return fail(ctx, MG_EINVAL, "deterministic mode needs ts, fo and u_tlen/tl arrays");
     if (n) {
@@ -1025,10 +1048,27 @@ static void drain_loop(mg_ctx *ctx) {
     void *slot[2] = {nullptr, nullptr}; int64_t s_off[2] = {0, 0}, s_n[2] = {0, 0};
     const int64_t chunk = mg_sink_chunk_bytes(job.sink);
     int k = 0;
+    std::vector<int64_t> m_unit, m_uoff, m_soff, m_bytes;
     auto finish = [&](int i) {
       if (!slot[i]) return;
       if (cudaEventSynchronize(ctx->ev_drain[i]) != cudaSuccess && err.empty()) err = "device-to-host copy failed";
-      if (mg_sink_commit(job.sink, slot[i], job.unit, s_off[i], err.empty() ? s_n[i] : 0) != MG_OK && err.empty()) err = mg_sink_error(job.sink);
+      int rc;
+      if (job.units) {                                      // bytes [s_off, s_off + s_n) of the batch's stream: the units they belong to
+        const std::vector<int64_t> &ui = *job.units, &b = *job.base;
+        m_unit.clear(); m_uoff.clear(); m_soff.clear(); m_bytes.clear();
+        const int64_t lo = s_off[i], hi = s_off[i] + (err.empty() ? s_n[i] : 0);
+        size_t u = (size_t)(std::upper_bound(b.begin(), b.end(), lo) - b.begin());
+        u = u ? u - 1 : 0;                                  // the last unit that starts at or before lo
+        for (; u < ui.size() && b[u] < hi; u++) {
+          const int64_t a0 = std::max(lo, b[u]), a1 = std::min(hi, b[u + 1]);
+          if (a1 <= a0) continue;
+          m_unit.push_back(ui[u]); m_uoff.push_back(a0 - b[u]); m_soff.push_back(a0 - lo); m_bytes.push_back(a1 - a0);
+        }
+        rc = mg_sink_commit_multi(job.sink, slot[i], (int32_t)m_unit.size(), m_unit.data(), m_uoff.data(), m_soff.data(), m_bytes.data());
+      } else {
+        rc = mg_sink_commit(job.sink, slot[i], job.unit, s_off[i], err.empty() ? s_n[i] : 0);
+      }
+      if (rc != MG_OK && err.empty()) err = mg_sink_error(job.sink);
       slot[i] = nullptr;
     };
     for (int64_t off = 0; off < job.bytes && err.empty(); off += chunk, k ^= 1) {
@@ -1063,7 +1103,7 @@ int mg_unit_drain_async(mg_ctx *ctx, mg_sink *sink, int32_t producer, int64_t un
     ctx->drain_thread = std::thread(drain_loop, ctx);
   }
   ctx->dbusy[ctx->last_ob]++;
-  ctx->djobs.push_back({sink, producer, unit, ctx->last_ob, ctx->last_bytes});
+  ctx->djobs.push_back({sink, producer, unit, ctx->last_ob, ctx->last_bytes, nullptr, nullptr});
   ctx->dcv.notify_all();
   return MG_OK;
 }
@@ -1073,6 +1113,239 @@ int mg_drain_wait(mg_ctx *ctx) {
   std::unique_lock<std::mutex> lk(ctx->dmu);
   while ((ctx->dbusy[0] > 0 || ctx->dbusy[1] > 0) && !ctx->dfailed) ctx->dcv.wait(lk);
   if (ctx->dfailed) return fail(ctx, MG_EVALUE, "output sink: %s", ctx->derr.c_str());
+  return MG_OK;
+}
+
+// ---- batches of small regions -------------------------------------------------------------------
+
+int mg_batch_build(mg_ctx *ctx, int64_t n_regions, const uint8_t *ref_bytes, const int64_t *ref_off, const int64_t *bed_start,
+                   int64_t n_segs, const int32_t *seg_region, const int64_t *seg_var_off, const int64_t *pos, const uint8_t *op,
+                   const int64_t *oplen, const uint8_t *alt_pool, const int64_t *alt_off, int64_t *batch_id, int64_t *seg_p_min,
+                   int64_t *seg_p_max) {
+  if (!ctx || !batch_id || n_regions < 1 || n_segs < 1 || !ref_off || !bed_start || !seg_region || !seg_var_off)
+    return fail(ctx, MG_EINVAL, "mg_batch_build: bad arguments");
+  const int64_t total = ref_off[n_regions], n_var = seg_var_off[n_segs];
+  if (ref_off[0] != 0 || total < 0 || (total > 0 && !ref_bytes)) return fail(ctx, MG_EINVAL, "mg_batch_build: ref_off must start at 0");
+  if (n_var < 0 || (n_var > 0 && (!pos || !op || !oplen || !alt_pool || !alt_off))) return fail(ctx, MG_EINVAL, "mg_batch_build: variant arrays missing");
+  if (total >= (int64_t)0x7FF00000ll) return fail(ctx, MG_EVALUE, "the regions of one batch hold %lld bases (limit 2^31)", (long long)total);
+  if (n_var >= (1ll << 28) || n_segs >= (1ll << 24)) return fail(ctx, MG_EVALUE, "batch too large (%lld variants, %lld segments)", (long long)n_var, (long long)n_segs);
+  for (int64_t r = 0; r < n_regions; r++)
+    if (ref_off[r + 1] < ref_off[r]) return fail(ctx, MG_EINVAL, "mg_batch_build: ref_off must ascend");
+  DeviceGuard g(ctx->device);
+  std::unique_ptr<Batch> B(new Batch());
+  int rc = load_packed(ctx, ref_bytes, total, 0, B->R);
+  if (rc) return rc;
+  std::vector<MgSeg> segs((size_t)n_segs);
+  for (int64_t s = 0; s < n_segs; s++) {
+    const int32_t r = seg_region[s];
+    if (r < 0 || r >= n_regions || seg_var_off[s + 1] < seg_var_off[s]) return fail(ctx, MG_EINVAL, "mg_batch_build: segment %lld is malformed", (long long)s);
+    MgSeg &sg = segs[(size_t)s];
+    memset(&sg, 0, sizeof sg);
+    sg.v0 = (int32_t)seg_var_off[s]; sg.v1 = (int32_t)seg_var_off[s + 1];
+    sg.roff = (uint32_t)ref_off[r];
+    sg.start1 = bed_start[r] + 1;                     // ref_start_pos, readgenerate.py:190; also p_min
+    sg.region_len = ref_off[r + 1] - ref_off[r];
+  }
+  B->C.reset(new Copy());
+  B->C->owner = ctx;
+  rc = build_segments(ctx, B->R->d_ref + MG_HAP_PAD, B->R->d_exc, (int)B->R->exc.size(), segs, n_var, pos, op, oplen, alt_pool, alt_off, *B->C, B->C->segs);
+  if (rc) return rc;
+  B->C->seg_start1.resize((size_t)n_segs);
+  for (int64_t s = 0; s < n_segs; s++) {
+    B->C->seg_start1[(size_t)s] = segs[(size_t)s].start1;
+    if (seg_p_min) seg_p_min[s] = segs[(size_t)s].start1;                                   // readgenerate.py:192
+    if (seg_p_max) seg_p_max[s] = segs[(size_t)s].start1 + (int64_t)B->C->segs[(size_t)s].hap_len;
+  }
+  const int64_t id = ctx->next_id++;
+  ctx->batches[id] = std::move(B);
+  *batch_id = id;
+  return MG_OK;
+}
+
+int mg_batch_free(mg_ctx *ctx, int64_t batch_id) {
+  if (!ctx) return MG_EINVAL;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  return ctx->batches.erase(batch_id) ? MG_OK : fail(ctx, MG_EINVAL, "unknown batch %lld", (long long)batch_id);
+}
+
+int mg_batch_generate(mg_ctx *ctx, int64_t batch_id, int64_t n_units, const int32_t *unit_seg, const uint32_t *unit_seed,
+                      const int64_t *unit_ncand, const int64_t *unit_index, const char *sample, const uint8_t *chrom_pool,
+                      const int64_t *chrom_off, const int32_t *seg_cpy, double p, int32_t mode, const int64_t *ts, const double *u_tlen,
+                      const int8_t *fo, const int64_t *cand_off, int32_t corrupt, uint32_t corrupt_seed, mg_sink *sink,
+                      int32_t producer, int64_t *n_templates, int64_t *n_bytes, int64_t *unit_bytes, int64_t *unit_templates) {
+  if (!ctx || n_units < 0 || (n_units > 0 && (!unit_seg || !unit_seed || !unit_ncand || !unit_index || !sample || !chrom_pool || !chrom_off || !seg_cpy)))
+    return fail(ctx, MG_EINVAL, "mg_batch_generate: bad arguments");
+  if (n_templates) *n_templates = 0;
+  if (n_bytes) *n_bytes = 0;
+  auto it = ctx->batches.find(batch_id);
+  if (it == ctx->batches.end()) return fail(ctx, MG_EINVAL, "unknown batch %lld", (long long)batch_id);
+  if (ctx->rlen == 0) return fail(ctx, MG_EINVAL, "no read model loaded (mg_model_load)");
+  if (mode != MG_MODE_PHILOX && mode != MG_MODE_DET) return fail(ctx, MG_EINVAL, "a batch runs in PHILOX or DET mode");
+  if (mode == MG_MODE_PHILOX && !(p > 0.0 && p < 1.0)) return fail(ctx, MG_EINVAL, "PHILOX mode needs 0 < p < 1");
+  if (corrupt && mode != MG_MODE_PHILOX) return fail(ctx, MG_EINVAL, "fused corruption draws from Philox: use mg_corrupt_fastq for deterministic mode");
+  if (corrupt && ctx->rlen > ctx->n_cycles) return fail(ctx, MG_EINDEX, "read length %d exceeds the model's %d cycles", ctx->rlen, ctx->n_cycles);
+  if (corrupt && ctx->n_mates < 2) return fail(ctx, MG_EINVAL, "paired corruption needs a 2-mate model");
+  if (n_units >= (1ll << 24)) return fail(ctx, MG_EVALUE, "%lld units in one batch (limit 2^24)", (long long)n_units);
+  const Copy &C = *it->second->C;
+  const int64_t n_segs = (int64_t)C.segs.size();
+  const int L = ctx->rlen;
+  if (n_units == 0) { ctx->last_bytes = 0; return MG_OK; }
+  DeviceGuard g(ctx->device);
+
+  // -- the unit table
+  std::vector<MgBatchUnit> U((size_t)n_units);
+  int64_t n_plan = 0, n_draws = 0;
+  char text[96];
+  for (int64_t u = 0; u < n_units; u++) {
+    const int32_t sg = unit_seg[u];
+    if (sg < 0 || sg >= n_segs) return fail(ctx, MG_EINVAL, "unit %lld names segment %d of %lld", (long long)u, (int)sg, (long long)n_segs);
+    if (unit_ncand[u] < 0 || unit_ncand[u] > MG_BATCH_MAXC) return fail(ctx, MG_EVALUE, "unit %lld has %lld candidates: the batch path takes at most %d per unit", (long long)u, (long long)unit_ncand[u], MG_BATCH_MAXC);
+    if (u && unit_index[u] <= unit_index[u - 1]) return fail(ctx, MG_EINVAL, "the units of a batch must be in ascending schedule order");
+    MgBatchUnit &b = U[(size_t)u];
+    memset(&b, 0, sizeof b);
+    const int pl = snprintf(text, sizeof text, "@%s:0:%lld:", sample, (long long)unit_index[u]);          // readgenerate.py:195, 210
+    if (pl < 0 || pl > 32) return fail(ctx, MG_EVALUE, "sample name too long for the batch path (qname prefix of %d bytes, limit 32)", pl);
+    b.n_pre = (pl + 7) / 8;
+    for (int i = 0; i < b.n_pre; i++) b.pre[i] = mg_tok_bytes(reinterpret_cast<const uint8_t *>(text), 8 * i, pl - 8 * i);
+    const int64_t cl = chrom_off[sg + 1] - chrom_off[sg];
+    if (cl < 0 || cl > 20) return fail(ctx, MG_EVALUE, "chromosome name too long for the batch path (%lld bytes, limit 20)", (long long)cl);
+    int ml = 0;
+    text[ml++] = '|';
+    memcpy(text + ml, chrom_pool + chrom_off[sg], (size_t)cl); ml += (int)cl;
+    ml += snprintf(text + ml, sizeof text - (size_t)ml, "|%d", (int)seg_cpy[sg]);                         // readgenerate.py:223
+    if (ml > 32) return fail(ctx, MG_EVALUE, "chromosome name too long for the batch path");
+    b.n_mid = (ml + 7) / 8;
+    for (int i = 0; i < b.n_mid; i++) b.mid[i] = mg_tok_bytes(reinterpret_cast<const uint8_t *>(text), 8 * i, ml - 8 * i);
+    b.qn_len = (uint32_t)(pl + ml);
+    b.seed = unit_seed[u];
+    b.x0 = C.segs[(size_t)sg].hap_base; b.hap_len = C.segs[(size_t)sg].hap_len;
+    b.n_cand = (uint32_t)unit_ncand[u]; b.plan_off = (uint32_t)n_plan;
+    b.p_min = C.seg_start1[(size_t)sg];
+    if (mode == MG_MODE_DET) {
+      if (!cand_off || !ts || !u_tlen || !fo) return fail(ctx, MG_EINVAL, "deterministic mode needs ts, u_tlen, fo and cand_off");
+      b.draw_off = cand_off[u];
+      if (cand_off[u + 1] - cand_off[u] < unit_ncand[u]) return fail(ctx, MG_EINVAL, "unit %lld: fewer draws than candidates", (long long)u);
+      n_draws = cand_off[u + 1];
+    }
+    n_plan += unit_ncand[u];
+  }
+  if (n_plan >= (1ll << 32)) return fail(ctx, MG_EVALUE, "%lld candidates in one batch (limit 2^32)", (long long)n_plan);
+
+  MgUnitParams P; memset(&P, 0, sizeof P);
+  P.hap = C.d_hap + MG_HAP_PAD; P.hap_len = (uint32_t)C.hap_len; P.p_min = 0;
+  P.nodes = C.d_nodes; P.n_nodes = (int)C.n_nodes;
+  P.blk = C.d_blk; P.blk_shift = BLK_SHIFT; P.n_blk = C.n_blk;
+  P.exc = C.d_exc; P.n_exc = (int)C.n_exc;
+  P.cum_tlen = ctx->m_tlen.as<double>(); P.n_tlen = ctx->n_tlen; P.rlen = L;
+  P.tlen_alias = ctx->has_tlen_alias ? ctx->m_tlen_alias.as<uint32_t>() : nullptr;
+  P.mode = mode;
+  if (mode == MG_MODE_PHILOX) P.inv_log1mp = 1.0 / log(1.0 - p);
+  mg_qn_const(P.qn, nullptr, 0, nullptr, 0, L);       // the per-unit strings come from the unit table
+  P.bulk = 1;
+  P.corrupt = corrupt;
+  P.cor.kshift = ctx->a_kshift[0]; P.cor.code9 = ctx->a_code9[0];
+  P.cor.alias = ctx->m_alias[0].as<uint32_t>();
+  P.cor.n_cycles = ctx->n_cycles; P.cor.n_mates = ctx->n_mates;
+  P.cor.k0 = corrupt_seed;                            // k1: per unit, from its seed (k_unit_emit)
+  P.L_nd = mg_ndigits32((uint32_t)L);
+  int stage = 32 * (2 * L + 5 + 96);
+  if (stage > 48 * 1024) stage = 48 * 1024;
+  P.stage_cap = stage & ~15;
+  int smem = 0;
+  const int grid = mg_batch_grid(L, corrupt ? 1 + P.cor.code9 : 0, P.stage_cap, &smem);
+  if (grid <= 0) return fail(ctx, MG_EVALUE, "the emit kernel's staging area (%d bytes for reads of %d bases) exceeds the shared memory of this device", smem, L);
+
+  // -- device tables: [units][unit_kept n+1][unit_bytes n+1][unit_te n+1][kept_base n+2][byte_base n+2][scan tmp]
+  const size_t nu = (size_t)n_units;
+  CU(ctx->b_units.need(sizeof(MgBatchUnit) * nu));
+  const size_t tmp_elems = (size_t)mg_scan_tmp_elems((int64_t)nu);
+  CU(ctx->b_arr.need(8 * (3 * (nu + 1) + 2 * (nu + 2) + tmp_elems + 8)));
+  long long *arr = ctx->b_arr.as<long long>();
+  P.bunits = ctx->b_units.as<MgBatchUnit>(); P.n_bunits = (int)n_units;
+  P.unit_kept = arr; P.unit_bytes = arr + (nu + 1); P.unit_te = arr + 2 * (nu + 1);
+  long long *kept_base = arr + 3 * (nu + 1), *byte_base = kept_base + (nu + 2), *scan_tmp = byte_base + (nu + 2);
+  P.kept_base = kept_base; P.byte_base = byte_base;
+  CU(ctx->s_state.need(64));
+  P.totals = ctx->s_state.as<unsigned long long>();
+  CU(cudaMemsetAsync(P.totals, 0, 64, ctx->stream));
+  CU(ctx->s_plan.need(sizeof(MgPlan) * std::max<size_t>((size_t)n_plan, 1)));
+  P.plan = ctx->s_plan.as<MgPlan>();
+  CU(cudaMemcpyAsync(ctx->b_units.p, U.data(), sizeof(MgBatchUnit) * nu, cudaMemcpyHostToDevice, ctx->stream));
+  if (mode == MG_MODE_DET && n_draws) {
+    const size_t nd = (size_t)n_draws;
+    CU(ctx->s_ts.need(8 * nd)); CU(ctx->s_u.need(8 * nd)); CU(ctx->s_fo.need(nd));
+    CU(cudaMemcpyAsync(ctx->s_ts.p, ts, 8 * nd, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_u.p, u_tlen, 8 * nd, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_fo.p, fo, nd, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  P.ts_in = ctx->s_ts.as<int64_t>(); P.u_tlen = ctx->s_u.as<double>(); P.fo_in = ctx->s_fo.as<int8_t>();
+
+  CU(cudaEventRecord(ctx->ev2, ctx->stream));
+  mg_launch_batch_plan(P, ctx->stream);
+  mg_launch_scan_i64(reinterpret_cast<const int64_t *>(P.unit_kept), reinterpret_cast<int64_t *>(kept_base), (int64_t)nu, reinterpret_cast<int64_t *>(scan_tmp), ctx->stream);
+  mg_launch_scan_i64(reinterpret_cast<const int64_t *>(P.unit_bytes), reinterpret_cast<int64_t *>(byte_base), (int64_t)nu, reinterpret_cast<int64_t *>(scan_tmp), ctx->stream);
+  CU(cudaGetLastError());
+  ctx->total_launches += 7;
+  std::vector<long long> h_bytes(nu), h_kept(nu);
+  long long tot_kept = 0, tot_bytes = 0;
+  CU(cudaMemcpyAsync(h_bytes.data(), P.unit_bytes, 8 * nu, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h_kept.data(), P.unit_kept, 8 * nu, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&tot_kept, kept_base + nu, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&tot_bytes, byte_base + nu, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));             // the sizes: the one read-back of a batch
+
+  {   // a drain still reading this buffer set must finish first
+    std::unique_lock<std::mutex> lk(ctx->dmu);
+    while (ctx->dbusy[ctx->ob] > 0 && !ctx->dfailed) ctx->dcv.wait(lk);
+    if (ctx->dfailed) return fail(ctx, MG_EVALUE, "output sink: %s", ctx->derr.c_str());
+  }
+  DevBuf *ob = ctx->s_out[ctx->ob];
+  const size_t need = (size_t)tot_bytes + 4096;
+  if (ob[0].cap < need || ob[1].cap < need) CU(cudaStreamSynchronize(ctx->copy_stream));
+  CU(ob[0].need(need)); CU(ob[1].need(need));
+  P.out[0] = ob[0].as<uint8_t>(); P.out[1] = ob[1].as<uint8_t>();
+  P.cap = std::min(ob[0].cap, ob[1].cap);
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[ctx->ob], 0));
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  mg_launch_batch_emit(P, grid, smem, ctx->stream);
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));             // the drain thread copies from another stream
+  {
+    float ms = 0, ms_plan = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); cudaEventElapsedTime(&ms_plan, ctx->ev2, ctx->ev0);
+    ctx->plan_ms += ms_plan; ctx->emit_ms += ms; ctx->emit_launches++; ctx->total_launches++;
+    ctx->emit_bytes += 2 * (int64_t)tot_bytes;
+  }
+  ctx->last_ob = ctx->ob; ctx->last_bytes = (int64_t)tot_bytes;
+  ctx->ob ^= 1;
+  if (n_templates) *n_templates = (int64_t)tot_kept;
+  if (n_bytes) *n_bytes = (int64_t)tot_bytes;
+  for (size_t u = 0; u < nu; u++) {
+    if (unit_bytes) unit_bytes[u] = h_bytes[u];
+    if (unit_templates) unit_templates[u] = h_kept[u];
+  }
+  if (!sink) return MG_OK;
+
+  // -- every unit's size is announced before the first piece asks for a slot; then the stream is drained
+  auto ui = std::make_shared<std::vector<int64_t>>(nu), base = std::make_shared<std::vector<int64_t>>(nu + 1);
+  (*base)[0] = 0;
+  for (size_t u = 0; u < nu; u++) {
+    (*ui)[u] = unit_index[u]; (*base)[u + 1] = (*base)[u] + h_bytes[u];
+    if (mg_sink_unit_size(sink, unit_index[u], h_bytes[u]) != MG_OK) return fail(ctx, MG_EVALUE, "output sink: %s", mg_sink_error(sink));
+  }
+  if (tot_bytes == 0) return MG_OK;
+  std::lock_guard<std::mutex> lk(ctx->dmu);
+  if (ctx->dfailed) return fail(ctx, MG_EVALUE, "output sink: %s", ctx->derr.c_str());
+  if (!ctx->drain_thread.joinable()) {
+    for (int i = 0; i < 2; i++)
+      if (!ctx->ev_drain[i] && cudaEventCreateWithFlags(&ctx->ev_drain[i], cudaEventDisableTiming) != cudaSuccess) return fail(ctx, MG_ECUDA, "cannot create the drain events");
+    ctx->drain_thread = std::thread(drain_loop, ctx);
+  }
+  ctx->dbusy[ctx->last_ob]++;
+  ctx->djobs.push_back({sink, producer, -1, ctx->last_ob, ctx->last_bytes, ui, base});
+  ctx->dcv.notify_all();
   return MG_OK;
 }
 

@@ -664,11 +664,13 @@ MG_HD void mg_put_read(MgStream<SP> &w, const MgQnConst &Q, NP nodes, MgReadRef 
 }
 
 // qname line + '\n' through the stream (which then goes on with the sequence line)
-template <class SP, class NP>
-MG_HD void mg_put_qname(MgStream<SP> &w, const MgQnConst &Q, uint32_t cnt, NP nodes, MgReadRef first, MgReadRef second, int L) {
-  for (int i = 0; i < Q.n_pre; i++) w.append(Q.pre[i]);
+// STR: where the two per-unit strings come from -- the kernel's own MgQnConst, or the unit's entry of a batch table
+// (any type with pre[], n_pre, mid[], n_mid)
+template <class SP, class NP, class STR>
+MG_HD void mg_put_qname(MgStream<SP> &w, const MgQnConst &Q, const STR &str, uint32_t cnt, NP nodes, MgReadRef first, MgReadRef second, int L) {
+  for (int i = 0; i < str.n_pre; i++) w.append(str.pre[i]);
   mg_put_num(w, cnt, 0u, 0u);
-  for (int i = 0; i < Q.n_mid; i++) w.append(Q.mid[i]);
+  for (int i = 0; i < str.n_mid; i++) w.append(str.mid[i]);
   MG_NOUNROLL
   for (int r = 0; r < 2; r++) mg_put_read(w, Q, nodes, r ? second : first, L);
   w.append(mg_tok('\n', 0, 1));
@@ -872,12 +874,12 @@ MG_HD void mg_emit_seq_src(WR &w, MgSeqSrc<MAXW, HP> &S) {
 // S = the read that goes into this file (already loaded); first/second give the qname's file order.
 // The stream is left OPEN: the caller ends it (tail bytes) after every thread of the warp has stored
 // its first word -- see MgStream::begin -- and then patches the exception bases (mg_patch_exc).
-template <class SP, int MAXW, class NP, class HP>
-MG_HD void mg_emit_record(MgStream<SP> &ws, typename SP::ptr dst, const MgQnConst &Q, uint32_t cnt, NP nodes, MgReadRef first,
+template <class SP, int MAXW, class NP, class HP, class STR>
+MG_HD void mg_emit_record(MgStream<SP> &ws, typename SP::ptr dst, const MgQnConst &Q, const STR &str, uint32_t cnt, NP nodes, MgReadRef first,
                           MgReadRef second, MgSeqSrc<MAXW, HP> &S) {
   const int L = S.L;
   ws.begin(dst);
-  mg_put_qname(ws, Q, cnt, nodes, first, second, L);
+  mg_put_qname(ws, Q, str, cnt, nodes, first, second, L);
   S.prep();
   mg_emit_seq_src(ws, S);
   ws.append(mg_tok((uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16), 0, 3));
@@ -899,11 +901,11 @@ MG_HD void mg_rewrite_seq(typename SP::ptr seq_dst, MgSeqSrc<MAXW, HP> &S, EP ex
 
 // Fused corruption: the qname line first (its last partial word is stored whole: the bytes above it
 // are this record's own sequence line, still to be written) ...
-template <class SP, class NP>
-MG_HD void mg_emit_frame_qname(typename SP::ptr dst, const MgQnConst &Q, uint32_t cnt, NP nodes, MgReadRef first, MgReadRef second, int L) {
+template <class SP, class NP, class STR>
+MG_HD void mg_emit_frame_qname(typename SP::ptr dst, const MgQnConst &Q, const STR &str, uint32_t cnt, NP nodes, MgReadRef first, MgReadRef second, int L) {
   MgStream<SP> ws;
   ws.begin(dst);
-  mg_put_qname(ws, Q, cnt, nodes, first, second, L);
+  mg_put_qname(ws, Q, str, cnt, nodes, first, second, L);
   ws.flush_own();
 }
 // ... then (after the warp has synchronised: the record's last byte shares its word with the next

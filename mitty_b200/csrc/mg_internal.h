@@ -21,6 +21,19 @@ struct alignas(16) MgPlan {
   uint64_t off;        // byte offset of the record in each file
 };
 
+// One work unit of a BATCH of small units (one CTA of k_batch_plan each, all emitted by one launch).
+#define MG_BATCH_MAXC 2048   // candidates per unit: one block's worth of the gap scan
+struct MgBatchUnit {
+  MgTok pre[4], mid[4];      // "@sample:0:unit:" and "|chrom|copy" as tokens (at most 32 bytes each)
+  int n_pre, n_mid;
+  uint32_t qn_len;           // bytes of the two strings
+  uint32_t seed;             // rng_seed of the unit: every Philox key derives from it as in the one-unit path
+  uint32_t x0, hap_len;      // its copy's range of the concatenated haplotype
+  uint32_t n_cand, plan_off; // candidates; first plan record of the unit
+  int64_t draw_off;          // DET: first entry of the unit in the concatenated ts / u_tlen / fo arrays
+  int64_t p_min;             // 1-based sample coordinate of the unit's first haplotype base
+};
+
 struct MgUnitParams {
   // haplotype of one chromosome copy, resident in HBM
   const uint32_t *hap;       // 2-bit packed, 16 bases / word, pointer already biased past the front pad
@@ -55,7 +68,27 @@ struct MgUnitParams {
   unsigned long long *descA, *descB; uint32_t *tile_counter;
   unsigned long long *totals;  // [0] te<p_max survivors, [1] templates written, [2] bytes per file, [3] overflow
   int n_tiles; int stage_cap;
+  // a batch of small units: per-unit table, exclusive prefixes of kept templates / bytes per file over the units
+  const MgBatchUnit *bunits; int n_bunits;
+  const long long *kept_base, *byte_base;
+  long long *unit_kept, *unit_bytes, *unit_te;
+  double inv_log1mp;         // 1 / log(1 - p), computed on the host as for the one-unit gap scan
 };
+
+// the keys of a unit's Philox streams, all derived from its rng_seed: the one-unit path (mg_api.cu) and the
+// batch kernels must agree, so that a unit's bytes do not depend on the path it took
+struct MgUnitKeys { uint32_t gap0, gap1, tlen0, tlen1, perm0, perm1, half_bits; };
+__host__ __device__ inline MgUnitKeys mg_unit_keys(uint32_t seed, uint32_t n_cand) {
+  MgUnitKeys k;
+  k.gap0 = seed; k.gap1 = 0x67617031u;
+  k.tlen0 = seed; k.tlen1 = 0x746c6531u;
+  k.perm0 = seed ^ 0x7368756bu; k.perm1 = seed * 0x9E3779B1u + 0x66656973u;
+  uint32_t bits = 2;
+  while (bits < 32 && (1ull << bits) < (unsigned long long)(n_cand > 2 ? n_cand : 2)) bits++;
+  if (bits & 1) bits++;
+  k.half_bits = bits / 2;
+  return k;
+}
 
 struct MgSampleParams {      // template sampling only (the read-module plugin's generate_reads)
   MgUnitParams u;
@@ -126,6 +159,9 @@ void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes);
 void mg_launch_plan(const MgUnitParams &P, cudaStream_t st);
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st);
+void mg_launch_batch_plan(const MgUnitParams &P, cudaStream_t st);      // one CTA per unit of P.bunits
+int mg_batch_grid(int L, int corrupt, int stage_cap, int *smem_bytes);
+void mg_launch_batch_emit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st);
 void mg_launch_sample(const MgSampleParams &P, cudaStream_t st);
 void mg_launch_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st);  // exclusive, out[n] = total
 int64_t mg_scan_tmp_elems(int64_t n);

@@ -736,6 +736,120 @@ void mg_launch_plan(const MgUnitParams &P, cudaStream_t st) {
   k_unit_plan<<<grid, PLAN_THREADS, 0, st>>>(P);
 }
 
+// ---- k_batch_plan --------------------------------------------------------------------------
+// Phase 1 for a BATCH of small units (an exome-style BED: thousands of regions of a few kb): ONE CTA per
+// unit does what k_gap_* + k_unit_plan do for a big unit -- geometric gaps and their scan in shared
+// memory, sampling, filters, node lookup, sizes, block scans with a running carry -- so a whole batch is
+// one launch.  Same draws as the one-unit path (unit_keys), hence the same bytes.
+__global__ void __launch_bounds__(PLAN_THREADS) k_batch_plan(const __grid_constant__ MgUnitParams P) {
+  __shared__ uint32_t s_ts[MG_BATCH_MAXC];
+  __shared__ uint32_t s_tlen[MG_TLEN_K];
+  __shared__ unsigned long long s_w64[PLAN_THREADS / 32];
+  __shared__ uint32_t s_wc[PLAN_THREADS / 32], s_ws[PLAN_THREADS / 32];
+  __shared__ unsigned long long s_carry[3];          // te survivors, kept, bytes (without the serials' digits) so far
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int L = P.rlen;
+  const MgBatchUnit U = P.bunits[blockIdx.x];
+  const uint32_t n = U.n_cand;
+  const MgUnitKeys K = mg_unit_keys(U.seed, n);
+  if (P.mode == MG_MODE_PHILOX) {
+    if (P.tlen_alias) for (int i = t; i < MG_TLEN_K; i += PLAN_THREADS) s_tlen[i] = P.tlen_alias[i];
+    // template starts: cumulative geometric gaps (illumina.py:70), eight per thread, block scan
+    uint32_t g[8];
+    unsigned long long sum = 0;
+    const uint32_t i0 = (uint32_t)t * 8u;
+    if (i0 < n) { gaps8(i0, n, P.inv_log1mp, K.gap0, K.gap1, g); for (int q = 0; q < 8; q++) sum += g[q]; }
+    else { for (int q = 0; q < 8; q++) g[q] = 0; }
+    unsigned long long x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(FULL, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_w64[wid] = x;
+    __syncthreads();
+    unsigned long long run = x - sum;
+    for (int w = 0; w < wid; w++) run += s_w64[w];
+    for (int q = 0; q < 8; q++) {
+      run += g[q];
+      if (i0 + q < n) { const unsigned long long v = run + 1; s_ts[i0 + q] = v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v; }
+    }
+  }
+  if (t == 0) { s_carry[0] = 0; s_carry[1] = 0; s_carry[2] = 0; }
+  __syncthreads();
+  for (uint32_t c0 = 0; c0 < n; c0 += PLAN_THREADS) {
+    const uint32_t j = c0 + t;
+    bool k1 = false, k2 = false, ta = false, tb = false;
+    uint32_t xa = 0, xb = 0, fo = 0, sz = 0;
+    int n0a = 0, n1a = 0, n0b = 0, n1b = 0;
+    if (j < n) {
+      int64_t ts_rel, tl;
+      if (P.mode == MG_MODE_PHILOX) {
+        const uint32_t i = mg_permute(j, n, K.half_bits, K.perm0, K.perm1);
+        ts_rel = (int64_t)s_ts[i];
+        const MgPhilox r = mg_philox(j, 0u, 0u, MG_STREAM_TLEN, K.tlen0, K.tlen1);
+        if (P.tlen_alias) { const uint32_t idx = r.v[0] >> 22, e = s_tlen[idx]; tl = (r.v[0] & 0x3FFFFFu) < (e >> 10) ? idx : (e & 1023u); }
+        else tl = mg_lower_bound_f64(P.cum_tlen, P.n_tlen, mg_u53(r.v[0], r.v[1]));
+        fo = r.v[2] & 1u;
+      } else {
+        ts_rel = P.ts_in[U.draw_off + j] - U.p_min;
+        tl = mg_lower_bound_f64(P.cum_tlen, P.n_tlen, P.u_tlen[U.draw_off + j]);
+      }
+      if (tl < L) tl = L;                                                       // illumina.py:73
+      const int64_t te_rel = ts_rel + tl;
+      k1 = te_rel < (int64_t)U.hap_len && ts_rel >= 0;                           // illumina.py:75
+      if (k1) {
+        xa = U.x0 + (uint32_t)ts_rel; xb = U.x0 + (uint32_t)(te_rel - L);       // illumina.py:95-96, in the concatenated haplotype
+        k2 = true;
+        if (P.n_exc) {                                                           // readgenerate.py:204
+          const int na = mg_count_N(P.exc, P.n_exc, xa, L, ta), nb = mg_count_N(P.exc, P.n_exc, xb, L, tb);
+          k2 = na <= 2 && nb <= 2;
+        }
+        if (k2) {
+          n0a = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xa);
+          n1a = mg_last_node(P.nodes, n0a, P.n_nodes, xa, L);
+          n0b = mg_find_node(P.nodes, P.blk, P.blk_shift, P.n_blk, P.n_nodes, xb);
+          n1b = mg_last_node(P.nodes, n0b, P.n_nodes, xb, L);
+          sz = U.qn_len + mg_read_fields_len(P.nodes, n0a, n1a, xa, L, P.L_nd) + mg_read_fields_len(P.nodes, n0b, n1b, xb, L, P.L_nd) + 2u * (uint32_t)L + 5u;
+        }
+      }
+    }
+    const uint32_t cpk = (k1 ? 1u : 0u) | (k2 ? 0x10000u : 0u);
+    const uint32_t ic = warp_incl_scan_u32(cpk, lane), is = warp_incl_scan_u32(sz, lane);
+    if (lane == 31) { s_wc[wid] = ic; s_ws[wid] = is; }
+    __syncthreads();
+    uint32_t oc = 0, os = 0, tc = 0, ts_ = 0;
+#pragma unroll
+    for (int w = 0; w < PLAN_THREADS / 32; w++) {
+      if (w < wid) { oc += s_wc[w]; os += s_ws[w]; }
+      tc += s_wc[w]; ts_ += s_ws[w];
+    }
+    const uint32_t ec = oc + ic - cpk, es = os + is - sz;
+    const unsigned long long base1 = s_carry[0], base2 = s_carry[1], baseb = s_carry[2];
+    if (k2) {
+      const unsigned long long rank = base2 + (ec >> 16);                        // cnt - 1, readgenerate.py:209
+      const unsigned long long off = baseb + es + mg_digit_sum(rank);
+      const uint32_t my_fo = (P.mode == MG_MODE_PHILOX) ? fo : (uint32_t)(P.fo_in[U.draw_off + base1 + (ec & 0xFFFFu)] & 1);   // illumina.py:93
+      MgPlan pl;
+      pl.xa = xa; pl.xb = xb; pl.n0a = n0a; pl.n0b = n0b;
+      pl.dn = (uint32_t)(n1a - n0a) | ((uint32_t)(n1b - n0b) << 16);
+      pl.fo_sz = (my_fo << 31) | ((ta ? 1u : 0u) << 30) | ((tb ? 1u : 0u) << 29) | (sz + (uint32_t)mg_ndigits32((uint32_t)(rank + 1)));
+      pl.off = off | ((unsigned long long)blockIdx.x << 40);                     // bytes inside the unit (< 2^40) | the unit
+      P.plan[U.plan_off + rank] = pl;
+    }
+    __syncthreads();
+    if (t == 0) { s_carry[0] = base1 + (tc & 0xFFFFu); s_carry[1] = base2 + (tc >> 16); s_carry[2] = baseb + ts_; }
+    __syncthreads();
+  }
+  if (t == 0) {
+    P.unit_te[blockIdx.x] = (long long)s_carry[0];
+    P.unit_kept[blockIdx.x] = (long long)s_carry[1];
+    P.unit_bytes[blockIdx.x] = (long long)(s_carry[2] + mg_digit_sum(s_carry[1]));
+  }
+}
+
+void mg_launch_batch_plan(const MgUnitParams &P, cudaStream_t st) {
+  if (P.n_bunits == 0) return;
+  k_batch_plan<<<P.n_bunits, PLAN_THREADS, 0, st>>>(P);
+}
+
 // ---- k_unit_emit ---------------------------------------------------------------------------
 // Phase 2: one WARP owns 32 consecutive kept templates (every lane busy), formats their records
 // into its own shared-memory stage and hands the 16-byte aligned body of the byte range to the bulk
@@ -744,19 +858,19 @@ void mg_launch_plan(const MgUnitParams &P, cudaStream_t st) {
 
 // a record larger than the whole stage (only possible with absurdly long CIGARs): straight to
 // global memory through generic pointers, streaming sequence source; cold and out of line
-template <int CORRUPT>
-__device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const MgUnitParams &P,
+template <int CORRUPT, class STR>
+__device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const MgUnitParams &P, const STR &str, const MgCorruptCtx &cor,
                                            unsigned long long cnt, MgReadRef first, MgReadRef second, MgReadRef mine, int f) {
   const int L = P.rlen;
   MgSeqSrc<0, const uint32_t *> S;
   S.load(P.hap, mine.x, L, mine.strand);
   if constexpr (CORRUPT) {
-    mg_emit_frame_qname<MgGenericSpace>(dst, P.qn, (uint32_t)cnt, P.nodes, first, second, L);
+    mg_emit_frame_qname<MgGenericSpace>(dst, P.qn, str, (uint32_t)cnt, P.nodes, first, second, L);
     mg_emit_frame_seps<MgGenericSpace>(dst, qlen, L);
-    mg_emit_seq_corrupt<MgGenericSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, P.cor, (uint32_t)(cnt - 1), (uint32_t)f, (uint32_t)f);
+    mg_emit_seq_corrupt<MgGenericSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)(cnt - 1), (uint32_t)f, (uint32_t)f);
   } else {
     MgStream<MgGenericSpace> ws;
-    mg_emit_record<MgGenericSpace>(ws, dst, P.qn, (uint32_t)cnt, P.nodes, first, second, S);
+    mg_emit_record<MgGenericSpace>(ws, dst, P.qn, str, (uint32_t)cnt, P.nodes, first, second, S);
     ws.end();
     if (P.n_exc) mg_patch_exc<MgGenericSpace>(dst + (qlen + 1), P.exc, P.n_exc, S.hap, S.x, L, S.strand);
   }
@@ -769,7 +883,10 @@ __device__ __forceinline__ void bulk_store(uint8_t *gdst, uint32_t ssrc, uint32_
 }
 
 // CORRUPT: 0 = perfect reads; 1 / 2 = fused corruption with 8- / 9-bit outcome codes
-template <int MAXW, int CORRUPT>
+// BATCH: the templates of MANY small units (k_batch_plan) in one launch: a lane finds its unit in the
+// prefix of kept templates, takes the unit's strings and corruption key from the unit table and its byte
+// offset from the prefix of the units' bytes
+template <int MAXW, int CORRUPT, bool BATCH = false>
 __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__ MgUnitParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -778,24 +895,38 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
   uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   asm volatile("" : "+r"(stage_s));
   const int L = P.rlen;
-  const unsigned long long n_kept = P.totals[1], n_bytes = P.totals[2];
+  const unsigned long long n_kept = BATCH ? (unsigned long long)P.kept_base[P.n_bunits] : P.totals[1];
+  const unsigned long long n_bytes = BATCH ? (unsigned long long)P.byte_base[P.n_bunits] : P.totals[2];
   if (n_bytes > P.cap) { if (t == 0 && blockIdx.x == 0) P.totals[3] = 1ull; return; }   // host regrows and relaunches
+  if (n_kept == 0) return;
   unsigned long long policy = 0;
   if (P.bulk) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));   // the FASTQ bytes must not push the haplotype out of L2
   bool in_flight = false;          // a bulk copy may still be reading this warp's stage
   const unsigned long long n_wt = (n_kept + 31) / 32;
   for (unsigned long long wt = (unsigned long long)blockIdx.x * (MG_CTA / 32) + wid; wt < n_wt; wt += (unsigned long long)gridDim.x * (MG_CTA / 32)) {
-    const unsigned long long rank = wt * 32 + lane;
-    const bool active = rank < n_kept;
-    MgPlan pl = P.plan[active ? rank : n_kept - 1];
+    const unsigned long long grank = wt * 32 + lane;
+    const bool active = grank < n_kept;
+    unsigned long long rank = active ? grank : n_kept - 1;      // serial - 1 within the unit
+    MgPlan pl;
+    const MgBatchUnit *U = nullptr;
+    if constexpr (BATCH) {
+      int ulo = 0, uhi = P.n_bunits - 1;                        // the last unit whose first template is <= rank
+      while (ulo < uhi) { const int mid = (ulo + uhi + 1) >> 1; if ((unsigned long long)P.kept_base[mid] <= rank) ulo = mid; else uhi = mid - 1; }
+      U = P.bunits + ulo;
+      rank -= (unsigned long long)P.kept_base[ulo];
+      pl = P.plan[U->plan_off + rank];
+      pl.off = (unsigned long long)P.byte_base[ulo] + (pl.off & ((1ull << 40) - 1ull));
+    } else {
+      pl = P.plan[rank];
+    }
     const uint32_t rec = pl.fo_sz & 0x1FFFFFFFu, my_fo = pl.fo_sz >> 31;
     // exception runs (N, IUPAC, lower case) are searched only for the reads the plan flagged
     const int ne_a = (pl.fo_sz & (1u << 30)) ? P.n_exc : 0, ne_b = (pl.fo_sz & (1u << 29)) ? P.n_exc : 0;
     const int ne_first = my_fo ? ne_b : ne_a, ne_second = my_fo ? ne_a : ne_b;
     // the next tile's plan records, and the first node of each of this tile's reads, on their way into L2 / L1
     {
-      const unsigned long long nr = rank + (unsigned long long)gridDim.x * MG_CTA;
-      if (nr < n_kept) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.plan + nr));
+      const unsigned long long nr = grank + (unsigned long long)gridDim.x * MG_CTA;
+      if (!BATCH && nr < n_kept) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.plan + nr));
       asm volatile("prefetch.global.L1 [%0];" :: "l"(P.nodes + pl.n0a));
       asm volatile("prefetch.global.L1 [%0];" :: "l"(P.nodes + pl.n0b));
     }
@@ -838,15 +969,29 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
           }
           if constexpr (CORRUPT) {
             if (full) {
-              if (mine) mg_emit_frame_qname<MgSharedSpace>(dst, P.qn, (uint32_t)cnt, P.nodes, first, second, L);
+              if (mine) {
+                if constexpr (BATCH) mg_emit_frame_qname<MgSharedSpace>(dst, P.qn, *U, (uint32_t)cnt, P.nodes, first, second, L);
+                else mg_emit_frame_qname<MgSharedSpace>(dst, P.qn, P.qn, (uint32_t)cnt, P.nodes, first, second, L);
+              }
               __syncwarp();                                 // every first word is stored: now the bytes that share a word with a neighbour
               if (mine) mg_emit_frame_seps<MgSharedSpace>(dst, qlen, L);
             }
-            if (mine) mg_emit_seq_corrupt<MgSharedSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, ne_f, P.cor, (uint32_t)rank, (uint32_t)f, (uint32_t)f);
+            if (mine) {
+              if constexpr (BATCH) {
+                MgCorruptCtx cor = P.cor;
+                cor.k1 = U->seed ^ 0x636f7231u;              // the unit's corruption key, as mg_unit_generate derives it
+                mg_emit_seq_corrupt<MgSharedSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, ne_f, cor, (uint32_t)rank, (uint32_t)f, (uint32_t)f);
+              } else {
+                mg_emit_seq_corrupt<MgSharedSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, ne_f, P.cor, (uint32_t)rank, (uint32_t)f, (uint32_t)f);
+              }
+            }
           } else {
             if (full) {
               MgStream<MgSharedSpace> ws;
-              if (mine) mg_emit_record<MgSharedSpace>(ws, dst, P.qn, (uint32_t)cnt, P.nodes, first, second, S);
+              if (mine) {
+                if constexpr (BATCH) mg_emit_record<MgSharedSpace>(ws, dst, P.qn, *U, (uint32_t)cnt, P.nodes, first, second, S);
+                else mg_emit_record<MgSharedSpace>(ws, dst, P.qn, P.qn, (uint32_t)cnt, P.nodes, first, second, S);
+              }
               __syncwarp();
               if (mine) {
                 ws.end();
@@ -857,7 +1002,13 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
             }
           }
         } else if (f >= 0 && mine) {
-          emit_oversize<CORRUPT>(P.out[f] + pl.off, qlen, P, cnt, first, second, f ? second : first, f);
+          if constexpr (BATCH) {
+            MgCorruptCtx cor = P.cor;
+            cor.k1 = U->seed ^ 0x636f7231u;
+            emit_oversize<CORRUPT>(P.out[f] + pl.off, qlen, P, *U, cor, cnt, first, second, f ? second : first, f);
+          } else {
+            emit_oversize<CORRUPT>(P.out[f] + pl.off, qlen, P, P.qn, P.cor, cnt, first, second, f ? second : first, f);
+          }
         }
         if (mine && f < 1) {
           const MgReadRef nxt = (f < 0 && P.out[0] != nullptr) ? first : second;
@@ -924,6 +1075,32 @@ int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
 void mg_launch_unit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st) {
   if (P.n_tiles == 0) return;
   unit_kernel(P.rlen, P.corrupt ? 1 + P.cor.code9 : 0)<<<grid, MG_CTA, smem_bytes, st>>>(P);
+}
+
+static unit_kernel_t batch_kernel(int L, int corrupt) {
+  if (L <= 161) return corrupt == 0 ? k_unit_emit<12, 0, true> : corrupt == 1 ? k_unit_emit<12, 1, true> : k_unit_emit<12, 2, true>;
+  if (L <= 305) return corrupt == 0 ? k_unit_emit<21, 0, true> : corrupt == 1 ? k_unit_emit<21, 1, true> : k_unit_emit<21, 2, true>;
+  return corrupt == 0 ? k_unit_emit<0, 0, true> : corrupt == 1 ? k_unit_emit<0, 1, true> : k_unit_emit<0, 2, true>;
+}
+
+int mg_batch_grid(int L, int corrupt, int stage_cap, int *smem_bytes) {
+  const int smem = (MG_CTA / 32) * (stage_cap + 16);
+  *smem_bytes = smem;
+  unit_kernel_t k = batch_kernel(L, corrupt);
+  int per_sm = 0, dev = 0, sms = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (smem > optin) return 0;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, MG_CTA, smem);
+  if (per_sm < 1) per_sm = 1;
+  return sms * per_sm;
+}
+
+void mg_launch_batch_emit(const MgUnitParams &P, int grid, int smem_bytes, cudaStream_t st) {
+  if (P.n_bunits == 0) return;
+  batch_kernel(P.rlen, P.corrupt ? 1 + P.cor.code9 : 0)<<<grid, MG_CTA, smem_bytes, st>>>(P);
 }
 
 // ------------------------------------------------------------------------------------------

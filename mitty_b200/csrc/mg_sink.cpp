@@ -131,8 +131,9 @@ bool sequential(const mg_sink *s, int f) { return s->gzip || !s->seekable[f]; }
 
 // skip units that are known to be empty / finished on a sequential target
 void advance(mg_sink *s, int f) {                       // with s->mu held
+  // (a piece committed by mg_sink_commit_multi may run on through several whole units: the offset carries over)
   while (s->cur_unit[f] < s->n_units && s->size[s->cur_unit[f]] >= 0 && s->cur_off[f] >= s->size[s->cur_unit[f]]) {
-    s->cur_unit[f]++; s->cur_off[f] = 0;
+    s->cur_off[f] -= s->size[s->cur_unit[f]]; s->cur_unit[f]++;
   }
 }
 
@@ -392,6 +393,45 @@ int mg_sink_commit(mg_sink *s, void *slot, int64_t unit, int64_t offset, int64_t
     else if (unit < s->known) s->ready.push_back(p);
     else s->waiting.insert({unit, p});
   }
+  s->cv_work.notify_all();
+  return MG_OK;
+}
+
+// one slot carrying SEVERAL whole or partial units (a batch of small units leaves the device as one stream): sub-piece
+// i = bytes [slot_off[i], slot_off[i] + bytes[i]) of the slot = bytes [unit_off[i], ...) of unit[i].  Sub-pieces that
+// follow each other in the slot AND in the files (unit k to its end, then unit k + 1 from its start) travel as one piece.
+int mg_sink_commit_multi(mg_sink *s, void *slot, int32_t n, const int64_t *unit, const int64_t *unit_off, const int64_t *slot_off,
+                         const int64_t *bytes) {
+  if (!s || !slot || n < 0 || (n > 0 && (!unit || !unit_off || !slot_off || !bytes))) return MG_EINVAL;
+  Slot *sl = static_cast<Slot *>(slot);
+  std::lock_guard<std::mutex> lk(s->mu);
+  struct Run { int64_t unit, off, soff, bytes; };
+  std::vector<Run> runs;
+  for (int i = 0; i < n && !s->failed; i++) {
+    if (bytes[i] <= 0) continue;
+    if (unit[i] < 0 || unit[i] >= s->n_units || s->size[unit[i]] < 0 || unit_off[i] < 0 || unit_off[i] + bytes[i] > s->size[unit[i]] ||
+        slot_off[i] < 0 || slot_off[i] + bytes[i] > s->chunk) { fail(s, "piece of unit %lld outside its announced size", (long long)unit[i]); break; }
+    if (!runs.empty()) {
+      Run &r = runs.back();
+      // the run so far ends where its last unit ends, unit[i] is the next unit of the schedule (empty ones in between do not count)
+      int64_t k = r.unit, end = r.off + r.bytes;           // walk the run to its last unit
+      while (k < s->n_units && s->size[k] >= 0 && end >= s->size[k] && k < unit[i]) { end -= s->size[k]; k++; }
+      if (k == unit[i] && end == 0 && unit_off[i] == 0 && slot_off[i] == r.soff + r.bytes) { r.bytes += bytes[i]; continue; }
+    }
+    runs.push_back({unit[i], unit_off[i], slot_off[i], bytes[i]});
+  }
+  if (s->failed || runs.empty()) { s->pool[(size_t)sl->producer].push_back(sl); s->cv_slot.notify_all(); return s->failed ? MG_EVALUE : MG_OK; }
+  sl->refs = s->n_files * (int)runs.size();
+  for (const Run &r : runs)
+    for (int f = 0; f < s->n_files; f++) {
+      Piece *p = new Piece();
+      p->file = f; p->unit = r.unit; p->off = r.off; p->bytes = r.bytes; p->data = sl->buf[f] + r.soff; p->slot = sl;
+      s->in_flight++;
+      if (s->gzip) s->ready.push_back(p);
+      else if (!s->seekable[f]) s->ordered[f][{p->unit, p->off}] = p;
+      else if (p->unit < s->known) s->ready.push_back(p);
+      else s->waiting.insert({p->unit, p});
+    }
   s->cv_work.notify_all();
   return MG_OK;
 }

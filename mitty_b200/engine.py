@@ -26,6 +26,17 @@ class CopyHandle(object):
     self.id, self.p_min, self.p_max, self.n_nodes, self.region = id_, p_min, p_max, n_nodes, region
 
 
+class BatchHandle(object):
+  """Many small (region, copy) segments built as one node table / haplotype (mg_batch_build)."""
+  __slots__ = ('id', 'p_min', 'p_max', 'n_segs')
+
+  def __init__(self, id_, p_min, p_max):
+    self.id, self.p_min, self.p_max, self.n_segs = id_, p_min, p_max, len(p_min)
+
+
+BATCH_MAX_CANDIDATES = 2048   # MG_BATCH_MAXC: candidates per unit on the batch path
+
+
 class Engine(object):
   def __init__(self, device=0, stream=None):
     self._L = _lib.lib()
@@ -207,6 +218,68 @@ class Engine(object):
   def drain_wait(self):
     self._check(self._L.mg_drain_wait(self._h))
 
+  # -- batches of small regions ------------------------------------------------------------------
+  def build_batch(self, refs, bed_starts, seg_region, seg_variants):
+    """refs: one uint8 array of reference bytes per region; bed_starts: their BED starts; seg_region[s] /
+    seg_variants[s]: region index and VariantList of segment s (one chromosome copy of one region).
+    -> BatchHandle with the segments' p_min / p_max (readgenerate.py:192)."""
+    n_reg, n_seg = len(refs), len(seg_region)
+    ref_off = np.zeros(n_reg + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in refs], out=ref_off[1:])
+    ref = np.concatenate([np.asarray(r, dtype=np.uint8) for r in refs]) if n_reg else np.zeros(0, dtype=np.uint8)
+    if ref.size == 0:
+      ref = np.zeros(1, dtype=np.uint8)
+    bed = np.ascontiguousarray(bed_starts, dtype=np.int64)
+    sreg = np.ascontiguousarray(seg_region, dtype=np.int32)
+    var_off = np.zeros(n_seg + 1, dtype=np.int64)
+    np.cumsum([len(v) for v in seg_variants], out=var_off[1:])
+    cat = lambda name, dt: np.ascontiguousarray(np.concatenate([getattr(v, name) for v in seg_variants]) if n_seg else np.zeros(0), dtype=dt)  # noqa: E731
+    pos, op, oplen = cat('pos', np.int64), cat('op', np.uint8), cat('oplen', np.int64)
+    alt_pool = np.concatenate([v.alt_pool for v in seg_variants] + [np.zeros(1, dtype=np.uint8)]).astype(np.uint8)
+    alt_off = np.zeros(int(var_off[-1]) + 1, dtype=np.int64)
+    base = 0
+    for s, v in enumerate(seg_variants):                 # alt offsets into the concatenated pool
+      alt_off[var_off[s]:var_off[s + 1] + 1] = v.alt_off[:len(v) + 1] + base
+      base += int(v.alt_off[len(v)])
+    bid = C.c_int64(0)
+    p_min, p_max = np.zeros(n_seg, dtype=np.int64), np.zeros(n_seg, dtype=np.int64)
+    self._check(self._L.mg_batch_build(self._h, n_reg, _ptr(ref), _ptr(ref_off), _ptr(bed), n_seg, _ptr(sreg), _ptr(var_off), _ptr(pos),
+                                       _ptr(op), _ptr(oplen), _ptr(alt_pool), _ptr(alt_off), C.byref(bid), _ptr(p_min), _ptr(p_max)))
+    return BatchHandle(bid.value, p_min, p_max)
+
+  def free_batch(self, batch):
+    self._check(self._L.mg_batch_free(self._h, batch.id))
+
+  def generate_batch(self, batch, unit_seg, unit_seed, unit_ncand, unit_index, sample, seg_chrom, seg_cpy, p, mode=MODE_PHILOX,
+                     draws=None, corrupt=False, corrupt_seed=0, sink=None, producer=0):
+    """All units of a batch in one launch sequence (mg_batch_generate).  seg_chrom / seg_cpy: chromosome
+    name and copy index per SEGMENT; draws (deterministic mode): (ts, u_tlen, fo, cand_off) with the
+    units' draws concatenated.  With ``sink`` the bytes are streamed into it as schedule units
+    ``unit_index``; without, they stay on the device back to back (``unit_read``).
+    -> (templates, bytes per file, per-unit bytes, per-unit templates)."""
+    n = len(unit_seg)
+    useg = np.ascontiguousarray(unit_seg, dtype=np.int32)
+    useed = np.ascontiguousarray(np.asarray(unit_seed, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32)
+    ucand = np.ascontiguousarray(unit_ncand, dtype=np.int64)
+    uidx = np.ascontiguousarray(unit_index, dtype=np.int64)
+    names = [str(c).encode() for c in seg_chrom]
+    chrom_off = np.zeros(len(names) + 1, dtype=np.int64)
+    np.cumsum([len(c) for c in names], out=chrom_off[1:])
+    chrom_pool = np.frombuffer(b''.join(names) + b'\0', dtype=np.uint8)
+    scpy = np.ascontiguousarray(seg_cpy, dtype=np.int32)
+    ts = u = fo = coff = None
+    if mode == MODE_DET:
+      ts, u, fo, coff = draws
+      ts = np.ascontiguousarray(ts, dtype=np.int64); u = np.ascontiguousarray(u, dtype=np.float64)
+      fo = np.ascontiguousarray(fo, dtype=np.int8); coff = np.ascontiguousarray(coff, dtype=np.int64)
+    nt, nb = C.c_int64(0), C.c_int64(0)
+    ub, ut = np.zeros(max(1, n), dtype=np.int64), np.zeros(max(1, n), dtype=np.int64)
+    self._check(self._L.mg_batch_generate(self._h, batch.id, n, _ptr(useg), _ptr(useed), _ptr(ucand), _ptr(uidx), str(sample).encode(),
+                                          _ptr(chrom_pool), _ptr(chrom_off), _ptr(scpy), float(p), int(mode), _ptr(ts), _ptr(u), _ptr(fo),
+                                          _ptr(coff), int(bool(corrupt)), int(corrupt_seed) & 0xFFFFFFFF, sink._h if sink is not None else None,
+                                          int(producer), C.byref(nt), C.byref(nb), _ptr(ub), _ptr(ut)))
+    return nt.value, nb.value, ub[:n], ut[:n]
+
   # -- corruption --------------------------------------------------------------------------------
   def corrupt_fastq(self, fq1, fq2=None, mode=MODE_PHILOX, seed=0, draws=None, first_template=0, out=None, partial=False):
     """Whole-buffer corrupt-reads.  fq1/fq2: bytes or uint8 arrays of 4-line FASTQ records.
@@ -329,6 +402,35 @@ class Sink(object):
       C.memmove(p2.value, (C.c_char * n).from_buffer_copy(bytes(b2)) if not isinstance(b2, np.ndarray) else b2.ctypes.data, n)
     if self._L.mg_sink_commit(self._h, slot, int(unit), int(offset), n) != 0:
       raise RuntimeError('output sink: ' + self._L.mg_sink_error(self._h).decode())
+
+  def put_stream(self, producer, units, sizes, b1, b2=None):
+    """Host bytes of SEVERAL units back to back (what a batch of small units leaves the device as): their
+    sizes are announced, then the stream travels in slot-sized pieces that run through unit boundaries
+    (mg_sink_commit_multi).  units: ascending schedule indices; sizes: bytes per file of each."""
+    units, sizes = np.asarray(units, dtype=np.int64), np.asarray(sizes, dtype=np.int64)
+    base = np.zeros(units.size + 1, dtype=np.int64)
+    np.cumsum(sizes, out=base[1:])
+    for k, n in zip(units.tolist(), sizes.tolist()):
+      self.unit_size(k, n)
+    a1 = np.frombuffer(bytes(b1), dtype=np.uint8) if not isinstance(b1, np.ndarray) else b1
+    a2 = None if b2 is None else (np.frombuffer(bytes(b2), dtype=np.uint8) if not isinstance(b2, np.ndarray) else b2)
+    for lo in range(0, int(base[-1]), self.chunk_bytes):
+      hi = min(lo + self.chunk_bytes, int(base[-1]))
+      p1, p2, slot = C.c_void_p(), C.c_void_p(), C.c_void_p()
+      if self._L.mg_sink_acquire(self._h, int(producer), C.byref(p1), C.byref(p2), C.byref(slot)) != 0:
+        raise RuntimeError('output sink: ' + self._L.mg_sink_error(self._h).decode())
+      C.memmove(p1.value, a1[lo:hi].ctypes.data, hi - lo)
+      if a2 is not None and p2.value:
+        C.memmove(p2.value, a2[lo:hi].ctypes.data, hi - lo)
+      u0 = max(0, int(np.searchsorted(base, lo, side='right')) - 1)
+      u1 = int(np.searchsorted(base, hi, side='left'))
+      idx = np.arange(u0, min(u1, units.size))
+      s0, s1 = np.maximum(base[idx], lo), np.minimum(base[idx + 1], hi)
+      keep = s1 > s0
+      idx, s0, s1 = idx[keep], s0[keep], s1[keep]
+      un, uo, so, nb = (np.ascontiguousarray(x, dtype=np.int64) for x in (units[idx], s0 - base[idx], s0 - lo, s1 - s0))
+      if self._L.mg_sink_commit_multi(self._h, slot, int(idx.size), _ptr(un), _ptr(uo), _ptr(so), _ptr(nb)) != 0:
+        raise RuntimeError('output sink: ' + self._L.mg_sink_error(self._h).decode())
 
   def abort(self, why):
     if self._h:

@@ -23,7 +23,7 @@ import time
 import numpy as np
 
 import mitty_b200.lib.vcfio as vio
-from mitty_b200.engine import MODE_DET, MODE_PHILOX, SEED_MAX, Engine
+from mitty_b200.engine import BATCH_MAX_CANDIDATES, MODE_DET, MODE_PHILOX, SEED_MAX, Engine
 
 logger = logging.getLogger(__name__)
 
@@ -142,17 +142,19 @@ class RegionCache(object):
         self._evict(key)
     return self.copies[key]
 
-  def done(self, r_idx, cpy):
-    """One unit of (region, copy) has been generated."""
+  def done(self, r_idx, cpy, built=True):
+    """One unit of (region, copy) has been generated (built=False: on the batch path, which builds its own
+    segments -- nothing of it is resident here)."""
     if self.left is None:
       return
     key = (r_idx, cpy)
     self.left[key] -= 1
     if self.left[key] == 0:
-      self.engine.free_copy(self.copies.pop(key))
+      if key in self.copies:
+        self.engine.free_copy(self.copies.pop(key))
       del self.left[key]
       self.left_copies[r_idx] -= 1
-      if self.left_copies[r_idx] == 0:
+      if self.left_copies[r_idx] == 0 and r_idx in self.regions:
         self.engine.free_region(self.regions.pop(r_idx))
 
 
@@ -174,13 +176,108 @@ def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sam
                               corrupt=corrupt, corrupt_seed=corrupt_seed, out=out, fetch=fetch, wait=wait)
 
 
+# ---- batches of small regions ----------------------------------------------------------------------
+BATCH_MAX_BASES = 256 << 20   # reference bases of one batch (its regions are packed back to back)
+BATCH_MAX_UNITS = 1 << 18
+
+
+def batchable(vcf_df, read_model, sample_name, n_units):
+  """-> {(region idx, copy)} whose units may take the batch path: at most BATCH_MAX_CANDIDATES template
+  candidates per unit (illumina.py:69; the haplotype is at most the region plus every inserted base
+  long) and qname strings that fit the unit table (32 bytes each)."""
+  if len('@{}:0:{}:'.format(sample_name, max(0, n_units - 1)).encode()) > 32:
+    return set()
+  ok = set()
+  for r_idx, r in enumerate(vcf_df):
+    region = r['region']
+    if len(str(region[0]).encode()) > 20:
+      continue
+    for cpy, vl in enumerate(r['v']):
+      ins = int(vl.oplen[vl.op == ord('I')].sum()) if len(vl) else 0
+      if cpy < 10**9 and int((region[2] - region[1] + ins) * read_model['p'] * 1.2) <= BATCH_MAX_CANDIDATES:
+        ok.add((r_idx, cpy))
+  return ok
+
+
+def generate_batch(engine, read_module, read_model, units, schedule, vcf_df, fetch_ref, sample_name, mode='philox', corrupt=False,
+                   corrupt_seed=0, drop_end_deletions=False, sink=None, producer=0):
+  """The work units ``units`` (ascending schedule indices, all of them batchable) in ONE launch sequence:
+  their regions packed back to back, one node table / haplotype over all (region, copy) segments
+  (mg_batch_build), one planning CTA per unit and one emit launch (mg_batch_generate).  The bytes of
+  every unit equal those of ``generate_unit``.
+  -> (templates, bytes per file, per-unit bytes, per-unit templates, deletions dropped)."""
+  reg_of, seg_of = {}, {}
+  refs, bed_starts, seg_region, seg_variants, seg_chrom, seg_cpy = [], [], [], [], [], []
+  unit_seg, dropped = [], 0
+  for k in units:
+    wd = schedule[k]
+    r_idx, cpy = wd['region_idx'], wd['region_cpy']
+    region = vcf_df[r_idx]['region']
+    if r_idx not in reg_of:
+      reg_of[r_idx] = len(refs)
+      refs.append(np.asarray(fetch_ref(region), dtype=np.uint8))
+      bed_starts.append(region[1])
+    if (r_idx, cpy) not in seg_of:
+      seg_of[(r_idx, cpy)] = len(seg_region)
+      vl, n_drop = _without_end_crossing_deletions(vcf_df[r_idx]['v'][cpy], region, drop_end_deletions)
+      dropped += n_drop
+      seg_region.append(reg_of[r_idx]); seg_variants.append(vl); seg_chrom.append(region[0]); seg_cpy.append(cpy)
+    unit_seg.append(seg_of[(r_idx, cpy)])
+  batch = engine.build_batch(refs, bed_starts, seg_region, seg_variants)
+  try:
+    seeds = [int(schedule[k]['rng_seed']) for k in units]
+    ncand = [int((batch.p_max[sg] - batch.p_min[sg]) * read_model['p'] * 1.2) for sg in unit_seg]          # illumina.py:69
+    draws = None
+    if mode == 'deterministic':
+      per = [read_module.unit_draws(read_model, int(batch.p_min[sg]), int(batch.p_max[sg]), sd) for sg, sd in zip(unit_seg, seeds)]
+      off = np.zeros(len(per) + 1, dtype=np.int64)
+      np.cumsum([d[0].size for d in per], out=off[1:])
+      cat = lambda i, dt: np.concatenate([d[i] for d in per]).astype(dt, copy=False) if per else np.zeros(0, dtype=dt)  # noqa: E731
+      draws = (cat(0, np.int64), cat(1, np.float64), cat(2, np.int8), off)
+    else:
+      for sd in seeds:
+        if not (0 <= sd <= SEED_MAX):
+          raise ValueError('Seed value {} is out of range 0 - {}'.format(sd, SEED_MAX))
+    nt, nb, ub, ut = engine.generate_batch(batch, unit_seg, seeds, ncand, list(units), sample_name, seg_chrom, seg_cpy, read_model['p'],
+                                           MODE_DET if mode == 'deterministic' else MODE_PHILOX, draws=draws, corrupt=corrupt,
+                                           corrupt_seed=corrupt_seed, sink=sink, producer=producer)
+  finally:
+    engine.free_batch(batch)
+  return nt, nb, ub, ut, dropped
+
+
+def _runs(my_units, schedule, ok, vcf_df):
+  """my_units (ascending) cut into runs that keep the order: ('batch', [units]) for stretches of batchable
+  units (bounded in reference bases and units), ('unit', k) for the others."""
+  cur, bases, seen = [], 0, set()
+  for k in my_units:
+    wd = schedule[k]
+    key = (wd['region_idx'], wd['region_cpy'])
+    if key in ok:
+      if wd['region_idx'] not in seen:
+        region = vcf_df[wd['region_idx']]['region']
+        span = region[2] - region[1]
+        if cur and (bases + span > BATCH_MAX_BASES or len(cur) >= BATCH_MAX_UNITS):
+          yield 'batch', cur
+          cur, bases, seen = [], 0, set()
+        seen.add(wd['region_idx']); bases += span
+      cur.append(k)
+    else:
+      if cur:
+        yield 'batch', cur
+        cur, bases, seen = [], 0, set()
+      yield 'unit', k
+  if cur:
+    yield 'batch', cur
+
+
 last_run = {}              # statistics of the most recent process_multi_threaded call (the reference returns nothing)
 CHUNK_BYTES = 64 << 20     # sink slot per file: a unit travels to the writer threads in pieces of this size
 SLOTS_PER_GPU = 6          # page-locked slot pairs per GPU: the spill that lets GPUs run ahead of the files
 
 
 def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, corrupt_seed,
-               drop_end_deletions=False, stats=None, engine=None, my_units=None):
+               drop_end_deletions=False, stats=None, engine=None, my_units=None, batch_small=True):
   """One host thread (or process) per GPU worker.  With ``my_units`` (ascending schedule indices: all
   units of a region on one worker, so each region / copy is built once) the worker walks its list;
   without, units are PULLED from the sink's counter one at a time, in schedule order across all
@@ -206,14 +303,31 @@ def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module,
         key = (schedule[k]['region_idx'], schedule[k]['region_cpy'])
         expect[key] = expect.get(key, 0) + 1
     cache = RegionCache(engine, vcf_df, fetch_ref, expect, drop_end_deletions)
-    todo = iter(my_units) if my_units is not None else None
+    # stretches of small units (an exome-style BED) take the batch path: one launch sequence per stretch
+    ok = batchable(vcf_df, read_model, sample_name, len(schedule)) if (my_units is not None and batch_small) else set()
+    todo = _runs(my_units, schedule, ok, vcf_df) if my_units is not None else None
+    n_batches = 0
     while True:
-      k = next(todo, -1) if todo is not None else sink.next_unit()
-      if k < 0:
+      kind, k = next(todo, ('end', -1)) if todo is not None else ('unit', sink.next_unit())
+      if kind == 'end' or (kind == 'unit' and k < 0):
         break
+      if kind == 'batch' and len(k) == 1:
+        kind, k = 'unit', k[0]
+      ta = time.perf_counter()
+      if kind == 'batch':
+        cnt, _, _, _, n_drop = generate_batch(engine, read_module, read_model, k, schedule, vcf_df, fetch_ref, sample_name, mode=mode,
+                                              corrupt=corrupt, corrupt_seed=corrupt_seed, drop_end_deletions=drop_end_deletions,
+                                              sink=sink, producer=producer)
+        for u in k:
+          cache.done(schedule[u]['region_idx'], schedule[u]['region_cpy'], built=False)
+        cache.dropped += n_drop
+        total += cnt
+        n_batches += 1
+        t_gen += time.perf_counter() - ta
+        logger.debug('Batch of {} units: {} templates'.format(len(k), cnt))
+        continue
       wd = schedule[k]
       r_idx, cpy = wd['region_idx'], wd['region_cpy']
-      ta = time.perf_counter()
       cp = cache.copy(r_idx, cpy)
       tb = time.perf_counter()
       _, _, cnt, _, nb = generate_unit(engine, read_module, read_model, cp, vcf_df[r_idx]['region'][0], cpy, int(wd['rng_seed']),
@@ -227,7 +341,7 @@ def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module,
     engine.drain_wait()
     logger.info('GPU {}: {} templates; region/copy builds {:0.2f}s, unit kernels {:0.2f}s'.format(device, total, t_build, t_gen))
     if stats is not None:
-      stats.update(build_s=t_build, gen_s=t_gen, dropped=cache.dropped)
+      stats.update(build_s=t_build, gen_s=t_gen, dropped=cache.dropped, batches=n_batches)
     return total
   except BaseException as e:
     sink.abort('{}: {}'.format(type(e).__name__, e))   # wakes every producer and writer
@@ -249,7 +363,7 @@ def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module,
 def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_module, model, coverage,
                            fastq1_fname, fastq2_fname, threads=2, seed=7, mode='philox', corrupt=False,
                            corrupt_seed=None, devices=None, drop_end_deletions=False, gzip_level=None, sink_threads=None,
-                           workers_per_gpu=None):
+                           workers_per_gpu=None, batch_small=True):
   """Same signature as the reference (readgenerate.py:76-78) plus keyword-only extras.
 
   ``threads`` = number of GPUs to use (capped by the GPUs present; ``devices`` overrides).  One host
@@ -260,6 +374,8 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   index = schedule index), whatever the GPU count.
 
   workers_per_gpu: host threads (each with its own context and stream) per GPU (default 1).
+  batch_small: stretches of small work units (regions of a few kb: an exome-style BED) are generated in ONE
+  launch sequence each (``generate_batch``); the bytes are the same either way.
   gzip_level: 1-9 writes multi-member gzip (what the reference's ``>(gzip > r1.fq.gz)`` produces,
   Readme.md:170, without the external process); None = by file name ('.gz'), 0 = plain.
   Page-locked memory: SLOTS_PER_GPU x CHUNK_BYTES per file and GPU (768 MB per GPU for a pair).
@@ -300,17 +416,22 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   span = max([r['region'][2] - r['region'][1] for r in vcf_df] + [1])
   rlen = int(read_model['rlen'])
   est = int(span * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150)) + (1 << 16)      # bytes per file of the largest unit
+  small = batchable(vcf_df, read_model, sample_name, len(schedule)) if batch_small else set()
+  if small:                              # stretches of small units leave the device as one stream
+    tot = sum(weights[k] for k, wd in enumerate(schedule) if (wd['region_idx'], wd['region_cpy']) in small)
+    est = max(est, int(tot / len(devices) * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150)) + (1 << 16))
   chunk = max(256, min(CHUNK_BYTES, est))
   n_writers = sink_threads or max(2, min(16, 2 * len(devices) if not gzip_level else (os.cpu_count() or 4)))
   sink = Sink(fastq1_fname, fastq2_fname, len(schedule), n_producers=len(devices), slots=SLOTS_PER_GPU, chunk_bytes=chunk,
               gzip_level=gzip_level, threads=n_writers)
   t0 = time.time()
   totals, errors = [0] * len(devices), []
+  wstats = [{} for _ in devices]
 
   def run(i, dev):
     try:
       totals[i] = gpu_worker(dev, i, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, cs,
-                             drop_end_deletions, my_units=assign[i])
+                             drop_end_deletions, stats=wstats[i], my_units=assign[i], batch_small=batch_small)
     except BaseException as e:  # noqa: B902 -- re-raised below, in the caller's thread
       errors.append(e)
 
@@ -333,7 +454,8 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   t1 = time.time()
   total = sum(totals)
   logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s); inputs {:0.2f}s'.format(total, t1 - t0, total / max(t1 - t0, 1e-9), t0 - t_in))
-  last_run.update(templates=total, seconds=t1 - t0, input_seconds=t0 - t_in, gpus=len(devices), writers=n_writers, gzip_level=gzip_level)
+  last_run.update(templates=total, seconds=t1 - t0, input_seconds=t0 - t_in, gpus=len(devices), writers=n_writers, gzip_level=gzip_level,
+                  batches=sum(w.get('batches', 0) for w in wstats), dropped=sum(w.get('dropped', 0) for w in wstats))
   return None
 
 

@@ -52,7 +52,7 @@ static int64_t emul_unit_t(const uint32_t *hap, uint32_t hap_len, const MgNode *
     MgSeqSrc<MAXW, const uint32_t *> S;
     S.load(hap, first.x, L, first.strand);
     if (corrupt) {
-      mg_emit_frame_qname<MgGenericSpace>(dst, Q, (uint32_t)cnt, nodes, first, second, L);
+      mg_emit_frame_qname<MgGenericSpace>(dst, Q, Q, (uint32_t)cnt, nodes, first, second, L);
       mg_emit_frame_seps<MgGenericSpace>(dst, qlen, L);
       if (code9) mg_emit_seq_corrupt<MgGenericSpace, true>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, exc, ne_first, cor, (uint32_t)(cnt - 1), 0u, 0u);
       else mg_emit_seq_corrupt<MgGenericSpace, false>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, exc, ne_first, cor, (uint32_t)(cnt - 1), 0u, 0u);
@@ -63,7 +63,7 @@ static int64_t emul_unit_t(const uint32_t *hap, uint32_t hap_len, const MgNode *
       memcpy(out2 + off, dst, rec);
     } else {
       MgStream<MgGenericSpace> ws;
-      mg_emit_record<MgGenericSpace>(ws, dst, Q, (uint32_t)cnt, nodes, first, second, S);
+      mg_emit_record<MgGenericSpace>(ws, dst, Q, Q, (uint32_t)cnt, nodes, first, second, S);
       ws.end();
       if (ne_first) mg_patch_exc<MgGenericSpace>(dst + (qlen + 1), exc, ne_first, S.hap, S.x, L, S.strand);
       memcpy(out1 + off, dst, rec);

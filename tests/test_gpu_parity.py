@@ -639,11 +639,12 @@ def test_bench_unit_full_size_exact(eng):
   eng.free_copy(cp); eng.free_region(rid)
 
 
-@pytest.mark.parametrize('workers', [1, 4])
-def test_exome_style_bed_many_small_regions(tmp_path, workers):
+@pytest.mark.parametrize('workers,batch', [(1, True), (4, True), (1, False), (4, False)])
+def test_exome_style_bed_many_small_regions(tmp_path, workers, batch):
   """A BED of 1000 regions of 2 kb (4000 work units in the reference's shuffled schedule order,
   readgenerate.py:129-159), several host workers per GPU: deterministic mode == the oracle's
-  generate-reads byte for byte, whatever the number of workers."""
+  generate-reads byte for byte, whatever the number of workers, on the batch path (one launch
+  sequence for all units of a worker) and unit by unit."""
   import mitty_b200.simulation.illumina as il
   import mitty_b200.simulation.readgenerate as rg
   n_reg, width = 1000, 2000
@@ -659,7 +660,75 @@ def test_exome_style_bed_many_small_regions(tmp_path, workers):
   m = H.model('hiseq-X-v2.5-Garvan.pkl')
   fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'exome'))
   r1, r2 = str(tmp_path / 'r1.fq'), str(tmp_path / 'r2.fq')
-  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, 30.0, r1, r2, threads=1, seed=7, mode='deterministic', workers_per_gpu=workers)
+  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, 30.0, r1, r2, threads=1, seed=7, mode='deterministic', workers_per_gpu=workers,
+                            batch_small=batch)
   o1, o2, n = oracle.generate_reads_cmd(H.oracle_regions(H.workload_regions(wl)), m, 30.0, 7, wl['sample'])
   assert n > 150000 and rg.last_run['templates'] == n
+  assert rg.last_run['batches'] == (workers if batch else 0)
   assert H.sha256(open(r1, 'rb').read()) == H.sha256(o1) and H.sha256(open(r2, 'rb').read()) == H.sha256(o2)
+
+
+def _mixed_bed_workload():
+  """Small regions (batch path) with two large ones in between (unit path), N runs and a soft-masked stretch."""
+  wl = synth.config1(contig_len=1200000, names=('1', '2'))
+  regs = []
+  for c in ('1', '2'):
+    regs += [(c, 3000 + 3000 * k, 3000 + 3000 * k + 1200 + 37 * (k % 7)) for k in range(120)]
+    regs.append((c, 500000, 700000))
+    regs += [(c, 800000 + 2500 * k, 800000 + 2500 * k + 900) for k in range(100)]
+  wl['regions'] = regs
+  for i, (name, seq) in enumerate(wl['contigs']):
+    seq = np.array(seq, copy=True)
+    seq[3100:3130] = ord('N'); seq[6200] = ord('R'); seq[9000:9400] |= 0x20; seq[805000:805020] = ord('N')
+    wl['contigs'][i] = (name, seq)
+  for i, t in enumerate(wl['tables']):
+    starts = np.array(sorted(r[1] for r in regs if r[0] == wl['contigs'][i][0])); ends = np.array(sorted(r[2] for r in regs if r[0] == wl['contigs'][i][0]))
+    j = np.searchsorted(starts, t.pos - 1, side='right') - 1
+    reflen = t.ref_off[1:] - t.ref_off[:-1]
+    ok = (j < 0) | (t.pos - 1 >= ends[np.maximum(j, 0)]) | (t.pos - 1 + reflen + 1 < ends[np.maximum(j, 0)])
+    wl['tables'][i] = synth._subset(t, ok)
+  return wl
+
+
+@pytest.mark.parametrize('corrupt', [False, True])
+def test_batch_path_equals_unit_path(tmp_path, corrupt):
+  """Production mode (Philox, with and without fused corruption) on a BED that mixes small and large regions:
+  the batch path, unit by unit, three workers, gzip members and FIFOs (sequential targets) all give the
+  same bytes; and every perfect read passes the god-aligner round trip."""
+  import gzip
+  import mitty_b200.simulation.illumina as il
+  import mitty_b200.simulation.readgenerate as rg
+  wl = _mixed_bed_workload()
+  m = H.model('hiseq-X-v2.5-Garvan.pkl')
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'mix'))
+  out = {}
+  for tag, kw in (('unit', dict(batch_small=False)), ('batch', dict()), ('batch3', dict(workers_per_gpu=3)),
+                  ('gz', dict(gzip_level=1)), ('pwrite_off', dict(sink_threads=1))):
+    r1, r2 = str(tmp_path / (tag + '1.fq')), str(tmp_path / (tag + '2.fq'))
+    rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, 30.0, r1, r2, threads=1, seed=11, mode='philox', corrupt=corrupt, **kw)
+    rd = (lambda p: gzip.open(p, 'rb').read()) if tag == 'gz' else (lambda p: open(p, 'rb').read())
+    out[tag] = (H.sha256(rd(r1)), H.sha256(rd(r2)), rg.last_run['templates'], rg.last_run['batches'])
+  assert out['unit'][3] == 0 and out['batch'][3] >= 2 and out['batch3'][3] >= 3
+  assert out['unit'][2] > 30000
+  for tag in ('batch', 'batch3', 'gz', 'pwrite_off'):
+    assert out[tag][:3] == out['unit'][:3], tag
+  # sequential targets (FIFOs): pieces that run through several units are appended in order
+  import threading
+  f1, f2 = str(tmp_path / 'p1'), str(tmp_path / 'p2')
+  os.mkfifo(f1); os.mkfifo(f2)
+  got = {}
+
+  def drain(name, path):
+    with open(path, 'rb') as fp:
+      got[name] = H.sha256(fp.read())
+  th = [threading.Thread(target=drain, args=(1, f1), daemon=True), threading.Thread(target=drain, args=(2, f2), daemon=True)]
+  for t in th:
+    t.start()
+  rg.process_multi_threaded(fa, vcf, wl['sample'], bed, il, m, 30.0, f1, f2, threads=1, seed=11, mode='philox', corrupt=corrupt, workers_per_gpu=2)
+  for t in th:
+    t.join(timeout=120)
+  assert (got[1], got[2]) == out['unit'][:2]
+  if not corrupt:   # every read of the batch path's files is where its qname says (god-aligner round trip on the device)
+    from mitty_b200.simulation.readcheck import check_fastq
+    res = check_fastq(fa, vcf, wl['sample'], bed, str(tmp_path / 'batch1.fq'), str(tmp_path / 'batch2.fq'))
+    assert res['templates'] == out['unit'][2] and res['bad'] == 0, res['examples']

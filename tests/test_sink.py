@@ -174,3 +174,62 @@ def test_processes_share_one_pair_of_files(tmp_path):
   units = _units(n_units, np.random.RandomState(seed), chunk)
   assert open(p1, 'rb').read() == b''.join(u[0].tobytes() for u in units)
   assert open(p2, 'rb').read() == b''.join(u[1].tobytes() for u in units)
+
+
+@pytest.mark.parametrize('target', ['file', 'gzip', 'fifo'])
+@pytest.mark.timeout(120)
+def test_streams_of_many_small_units(tmp_path, target):
+  """A batch of small units leaves the device as ONE byte stream: slot-sized pieces that run through unit
+  boundaries (mg_sink_commit_multi), from two producers whose units interleave in the schedule, mixed
+  with ordinary single-unit pieces.  Empty units included."""
+  chunk, rs = 1000, np.random.RandomState(3)
+  n = 300
+  units = []
+  for k in range(n):
+    size = 0 if k % 11 == 5 else int(rs.randint(1, 400)) if k % 50 else int(rs.randint(1500, 4000))
+    units.append((rs.randint(32, 127, size=size).astype(np.uint8), rs.randint(32, 127, size=size).astype(np.uint8)))
+  p1, p2 = str(tmp_path / 'a'), str(tmp_path / 'b')
+  got = {}
+  readers = []
+  if target == 'fifo':
+    os.mkfifo(p1); os.mkfifo(p2)
+
+    def drain(name, path):
+      with open(path, 'rb') as fp:
+        got[name] = fp.read()
+    readers = [threading.Thread(target=drain, args=(nm, p)) for nm, p in (('a', p1), ('b', p2))]
+    for t in readers:
+      t.start()
+  sink = Sink(p1, p2, n, n_producers=2, slots=2, chunk_bytes=chunk, gzip_level=1 if target == 'gzip' else 0, threads=3)
+  errs = []
+
+  def produce(producer, mine):
+    try:
+      # stretches of units as streams; every 4th stretch unit by unit
+      for j in range(0, len(mine), 37):
+        part = mine[j:j + 37]
+        if (j // 37) % 4 == 3:
+          _produce(sink, producer, part, units, chunk, errs)
+        else:
+          sink.put_stream(producer, part, [units[k][0].size for k in part], np.concatenate([units[k][0] for k in part]),
+                          np.concatenate([units[k][1] for k in part]))
+    except BaseException as e:  # noqa: B902
+      errs.append(e)
+  # producer 0: runs of consecutive units (these merge into one piece); producer 1: the units in between
+  mine0 = [k for k in range(n) if (k // 10) % 2 == 0]
+  mine1 = [k for k in range(n) if (k // 10) % 2 == 1]
+  ts = [threading.Thread(target=produce, args=(1, mine1)), threading.Thread(target=produce, args=(0, mine0))]
+  for t in ts:
+    t.start()
+  for t in ts:
+    t.join()
+  assert not errs, errs
+  sink.close()
+  for t in readers:
+    t.join(timeout=60)
+  want1, want2 = b''.join(u[0].tobytes() for u in units), b''.join(u[1].tobytes() for u in units)
+  if target == 'fifo':
+    assert got['a'] == want1 and got['b'] == want2
+  else:
+    rd = (lambda p: gzip.open(p, 'rb').read()) if target == 'gzip' else (lambda p: open(p, 'rb').read())
+    assert rd(p1) == want1 and rd(p2) == want2

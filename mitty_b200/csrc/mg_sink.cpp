@@ -416,7 +416,8 @@ int mg_sink_commit_multi(mg_sink *s, void *slot, int32_t n, const int64_t *unit,
       // the run so far ends where its last unit ends, unit[i] is the next unit of the schedule (empty ones in between do not count)
       int64_t k = r.unit, end = r.off + r.bytes;           // walk the run to its last unit
       while (k < s->n_units && s->size[k] >= 0 && end >= s->size[k] && k < unit[i]) { end -= s->size[k]; k++; }
-      if (k == unit[i] && end == 0 && unit_off[i] == 0 && slot_off[i] == r.soff + r.bytes) { r.bytes += bytes[i]; continue; }
+      // (bounded, so that the writer threads share the work of one slot)
+      if (k == unit[i] && end == 0 && unit_off[i] == 0 && slot_off[i] == r.soff + r.bytes && r.bytes + bytes[i] <= (4ll << 20)) { r.bytes += bytes[i]; continue; }
     }
     runs.push_back({unit[i], unit_off[i], slot_off[i], bytes[i]});
   }

@@ -235,12 +235,15 @@ class Engine(object):
     np.cumsum([len(v) for v in seg_variants], out=var_off[1:])
     cat = lambda name, dt: np.ascontiguousarray(np.concatenate([getattr(v, name) for v in seg_variants]) if n_seg else np.zeros(0), dtype=dt)  # noqa: E731
     pos, op, oplen = cat('pos', np.int64), cat('op', np.uint8), cat('oplen', np.int64)
-    alt_pool = np.concatenate([v.alt_pool for v in seg_variants] + [np.zeros(1, dtype=np.uint8)]).astype(np.uint8)
+    alt_pool = np.concatenate([v.alt_pool[int(v.alt_off[0]):int(v.alt_off[len(v)])] for v in seg_variants if len(v)] +
+                              [np.zeros(1, dtype=np.uint8)]).astype(np.uint8)
     alt_off = np.zeros(int(var_off[-1]) + 1, dtype=np.int64)
     base = 0
     for s, v in enumerate(seg_variants):                 # alt offsets into the concatenated pool
-      alt_off[var_off[s]:var_off[s + 1] + 1] = v.alt_off[:len(v) + 1] + base
-      base += int(v.alt_off[len(v)])
+      if len(v):
+        alt_off[var_off[s]:var_off[s + 1] + 1] = v.alt_off[:len(v) + 1] + (base - int(v.alt_off[0]))
+        base += int(v.alt_off[len(v)] - v.alt_off[0])
+    alt_off[-1] = base
     bid = C.c_int64(0)
     p_min, p_max = np.zeros(n_seg, dtype=np.int64), np.zeros(n_seg, dtype=np.int64)
     self._check(self._L.mg_batch_build(self._h, n_reg, _ptr(ref), _ptr(ref_off), _ptr(bed), n_seg, _ptr(sreg), _ptr(var_off), _ptr(pos),

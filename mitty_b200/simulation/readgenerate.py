@@ -72,6 +72,8 @@ def _without_end_crossing_deletions(vl, region, drop):
   reads at the region end come out short).  That output cannot be reproduced, so by default such a
   region is an error (the message of mg_copy_build); with ``drop`` (``--drop-end-deletions``) the
   offending deletions are left out -- a documented deviation from the reference -- and counted."""
+  if len(vl) == 0:
+    return vl, 0
   cross = (vl.op == ord('D')) & (vl.pos + vl.oplen > region[2])
   if not cross.any():
     return vl, 0
@@ -206,6 +208,7 @@ def generate_batch(engine, read_module, read_model, units, schedule, vcf_df, fet
   (mg_batch_build), one planning CTA per unit and one emit launch (mg_batch_generate).  The bytes of
   every unit equal those of ``generate_unit``.
   -> (templates, bytes per file, per-unit bytes, per-unit templates, deletions dropped)."""
+  t0 = time.perf_counter()
   reg_of, seg_of = {}, {}
   refs, bed_starts, seg_region, seg_variants, seg_chrom, seg_cpy = [], [], [], [], [], []
   unit_seg, dropped = [], 0
@@ -223,7 +226,9 @@ def generate_batch(engine, read_module, read_model, units, schedule, vcf_df, fet
       dropped += n_drop
       seg_region.append(reg_of[r_idx]); seg_variants.append(vl); seg_chrom.append(region[0]); seg_cpy.append(cpy)
     unit_seg.append(seg_of[(r_idx, cpy)])
+  t1 = time.perf_counter()
   batch = engine.build_batch(refs, bed_starts, seg_region, seg_variants)
+  t2 = time.perf_counter()
   try:
     seeds = [int(schedule[k]['rng_seed']) for k in units]
     ncand = [int((batch.p_max[sg] - batch.p_min[sg]) * read_model['p'] * 1.2) for sg in unit_seg]          # illumina.py:69
@@ -238,9 +243,12 @@ def generate_batch(engine, read_module, read_model, units, schedule, vcf_df, fet
       for sd in seeds:
         if not (0 <= sd <= SEED_MAX):
           raise ValueError('Seed value {} is out of range 0 - {}'.format(sd, SEED_MAX))
+    t3 = time.perf_counter()
     nt, nb, ub, ut = engine.generate_batch(batch, unit_seg, seeds, ncand, list(units), sample_name, seg_chrom, seg_cpy, read_model['p'],
                                            MODE_DET if mode == 'deterministic' else MODE_PHILOX, draws=draws, corrupt=corrupt,
                                            corrupt_seed=corrupt_seed, sink=sink, producer=producer)
+    logger.info('Batch of {} units over {} segments: inputs {:0.3f}s, build {:0.3f}s, draws {:0.3f}s, kernels {:0.3f}s'.format(
+      len(units), len(seg_region), t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3))
   finally:
     engine.free_batch(batch)
   return nt, nb, ub, ut, dropped
@@ -277,7 +285,7 @@ SLOTS_PER_GPU = 6          # page-locked slot pairs per GPU: the spill that lets
 
 
 def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, corrupt_seed,
-               drop_end_deletions=False, stats=None, engine=None, my_units=None, batch_small=True):
+               drop_end_deletions=False, stats=None, engine=None, my_units=None, batch_small=True, batch_ok=None):
   """One host thread (or process) per GPU worker.  With ``my_units`` (ascending schedule indices: all
   units of a region on one worker, so each region / copy is built once) the worker walks its list;
   without, units are PULLED from the sink's counter one at a time, in schedule order across all
@@ -304,7 +312,9 @@ def gpu_worker(device, producer, sink, schedule, vcf_df, fetch_ref, read_module,
         expect[key] = expect.get(key, 0) + 1
     cache = RegionCache(engine, vcf_df, fetch_ref, expect, drop_end_deletions)
     # stretches of small units (an exome-style BED) take the batch path: one launch sequence per stretch
-    ok = batchable(vcf_df, read_model, sample_name, len(schedule)) if (my_units is not None and batch_small) else set()
+    ok = set()
+    if my_units is not None and batch_small:
+      ok = batch_ok if batch_ok is not None else batchable(vcf_df, read_model, sample_name, len(schedule))
     todo = _runs(my_units, schedule, ok, vcf_df) if my_units is not None else None
     n_batches = 0
     while True:
@@ -421,7 +431,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
     tot = sum(weights[k] for k, wd in enumerate(schedule) if (wd['region_idx'], wd['region_cpy']) in small)
     est = max(est, int(tot / len(devices) * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150)) + (1 << 16))
   chunk = max(256, min(CHUNK_BYTES, est))
-  n_writers = sink_threads or max(2, min(16, 2 * len(devices) if not gzip_level else (os.cpu_count() or 4)))
+  n_writers = sink_threads or max(4, min(16, 2 * len(devices) if not gzip_level else (os.cpu_count() or 4)))
   sink = Sink(fastq1_fname, fastq2_fname, len(schedule), n_producers=len(devices), slots=SLOTS_PER_GPU, chunk_bytes=chunk,
               gzip_level=gzip_level, threads=n_writers)
   t0 = time.time()
@@ -431,7 +441,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   def run(i, dev):
     try:
       totals[i] = gpu_worker(dev, i, sink, schedule, vcf_df, fetch_ref, read_module, read_model, sample_name, mode, corrupt, cs,
-                             drop_end_deletions, stats=wstats[i], my_units=assign[i], batch_small=batch_small)
+                             drop_end_deletions, stats=wstats[i], my_units=assign[i], batch_small=batch_small, batch_ok=small)
     except BaseException as e:  # noqa: B902 -- re-raised below, in the caller's thread
       errors.append(e)
 

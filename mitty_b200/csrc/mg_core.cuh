@@ -769,18 +769,92 @@ MG_HD uint8_t mg_exc_byte(const MgExc &e, HP hap, uint64_t i) {
   return (uint8_t)("acgt"[(hap[i >> 4] >> (2 * (i & 15))) & 3u]);
 }
 
+// the 2-bit codes of consecutive haplotype positions: one load per 16 bases
+template <class HP>
+struct MgCodeCursor {
+  HP hap; uint64_t wi; uint32_t wv;
+  MG_HD explicit MgCodeCursor(HP h) : hap(h), wi(~0ull), wv(0u) {}
+  MG_HD uint32_t at(uint64_t i) {
+    if ((i >> 4) != wi) { wi = i >> 4; wv = hap[wi]; }
+    return (wv >> (2u * ((uint32_t)i & 15u))) & 3u;
+  }
+};
+
+// ---- soft-masked stretches, four bases per step ------------------------------------------------------
+// The case runs a read touches as a bit mask in OUTPUT order, 192 bits in six registers: bit a + n is set
+// when output base n (n = L - 1 - idx on strand 1) is lower case, a = the byte phase of the sequence line in
+// its first aligned word.  The patch loops below then walk the line's aligned words, four mask bits at a
+// time (the whole mask shifts down by four per word).  The words at both ends also hold the '\n' before /
+// after the line -- bytes of the same record, written by the same thread -- so the read-modify-write of
+// whole words touches nobody else's bytes.
+#define MG_CASE_WORDS 6
+struct MgCaseMask {
+  uint32_t m[MG_CASE_WORDS];
+  MG_HD void clear() { MG_UNROLL for (int w = 0; w < MG_CASE_WORDS; w++) m[w] = 0u; }
+  MG_HD void set(uint32_t lo, uint32_t hi) {            // bits [lo, hi), hi <= 32 * MG_CASE_WORDS
+    MG_UNROLL
+    for (int w = 0; w < MG_CASE_WORDS; w++) {
+      const uint32_t l = lo > 32u * w ? lo - 32u * w : 0u, h = hi < 32u * w + 32u ? (hi > 32u * w ? hi - 32u * w : 0u) : 32u;
+      if (l < h) m[w] |= (h - l == 32u ? 0xFFFFFFFFu : ((1u << (h - l)) - 1u) << l);
+    }
+  }
+  MG_HD uint32_t next4() {                              // the low four bits; the mask moves down by four
+    const uint32_t b = m[0] & 15u;
+    MG_UNROLL
+    for (int w = 0; w + 1 < MG_CASE_WORDS; w++) m[w] = mg_funnel_r(m[w], m[w + 1], 4u);
+    m[MG_CASE_WORDS - 1] >>= 4;
+    return b;
+  }
+  MG_HD bool any() const { uint32_t o = 0; MG_UNROLL for (int w = 0; w < MG_CASE_WORDS; w++) o |= m[w]; return o != 0u; }
+};
+
+MG_HD uint32_t mg_bits4_to_bytes(uint32_t b) { return ((b * 0x00204081u) & 0x01010101u) * 0xFFu; }   // bit j -> byte j = 0xFF
+// four upper-case letters A/C/G/T -> their complements (A ^ T = 0x15, C ^ G = 0x04; bit 1 tells the pairs apart)
+MG_HD uint32_t mg_complement4(uint32_t w) { return w ^ (0x15151515u ^ (((w >> 1) & 0x01010101u) * 0x11u)); }
+
+// perfect reads: the line holds upper-case letters, complemented on strand 1.  A lower-case base is copied
+// as it is on either strand (the reference's translate table only maps ATCGN, readgenerate.py:56).
+template <class SP>
+MG_HD void mg_patch_case_words(typename SP::ptr seq, MgCaseMask &M, int L, int strand) {
+  const uint32_t a = SP::low2(seq);
+  typename SP::ptr wp = seq - a;
+  const int nw = (int)((a + (uint32_t)L + 3u) >> 2);
+  MG_NOUNROLL
+  for (int k = 0; k < nw; k++, wp += 4) {
+    const uint32_t bits = M.next4();
+    if (!bits) continue;
+    const uint32_t bm = mg_bits4_to_bytes(bits);
+    uint32_t w = SP::ld32(wp);
+    const uint32_t u = strand ? mg_complement4(w) : w;
+    w = (w & ~bm) | ((u | 0x20202020u) & bm);
+    SP::st32(wp, w);
+  }
+}
+
 template <class SP, class EP, class HP>
 MG_NI void mg_patch_exc(typename SP::ptr seq, EP exc, int n_exc, HP hap, uint32_t x, int L, int strand) {
+  MgCodeCursor<HP> cur(hap);
+  const uint32_t ph = SP::low2(seq);
+  const bool words = ph + (uint32_t)L <= 32u * MG_CASE_WORDS;      // the mask registers cover the line
+  MgCaseMask M; M.clear();
   for (int k = mg_exc_first(exc, n_exc, x); k < n_exc; k++) {
     MgExc e = exc[k];
     if ((uint64_t)e.start >= (uint64_t)x + L) break;
     uint64_t a = e.start > x ? e.start : x;
     uint64_t b = (uint64_t)e.start + e.len < (uint64_t)x + L ? (uint64_t)e.start + e.len : (uint64_t)x + L;
+    const bool soft = e.byte == MG_EXC_CASE;
+    if (soft && words) {
+      const uint32_t i0 = (uint32_t)(a - x), i1 = (uint32_t)(b - x);
+      if (strand) M.set(ph + (uint32_t)L - i1, ph + (uint32_t)L - i0); else M.set(ph + i0, ph + i1);
+      continue;
+    }
     for (uint64_t i = a; i < b; i++) {
       int idx = (int)(i - x);
-      SP::st8(seq + (uint32_t)(strand ? (L - 1 - idx) : idx), mg_exc_byte(e, hap, i));
+      const uint32_t out = soft ? (0x74676361u /* "acgt" */ >> (8u * cur.at(i))) & 0xFFu : (uint32_t)e.byte;
+      SP::st8(seq + (uint32_t)(strand ? (L - 1 - idx) : idx), (uint8_t)out);
     }
   }
+  if (M.any()) mg_patch_case_words<SP>(seq, M, L, strand);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1086,19 +1160,58 @@ MG_HD void mg_emit_seq_corrupt(typename SP::ptr seq_dst, typename SP::ptr qual_d
   }
   ws.end(); wq.end();
   if (n_exc) {
-    // bases in exception runs: a non-ACGT byte becomes 'N' on a miscall (base_rot.get(base, 'NNN'),
-    // illumina.py:160) and is copied otherwise; the quality line is already right
+    // bases in exception runs: a non-ACGT byte (lower case included) becomes 'N' on a miscall
+    // (base_rot.get(base, 'NNN'), illumina.py:160) and is copied otherwise; the quality line is already
+    // right.  Whether the call was a miscall is read off the letter the main loop wrote: it differs from
+    // the letter of the packed code exactly when the substitution s was not 0 (code ^ s != code).
+    MgCodeCursor<HP> cur(mine.hap);
+    const uint32_t ph = SP::low2(seq_dst);
+    const bool words = ph + (uint32_t)L <= 32u * MG_CASE_WORDS;
+    MgCaseMask M; M.clear();
     for (int k = mg_exc_first(exc, n_exc, mine.x); k < n_exc; k++) {
       const MgExc e = exc[k];
       if ((uint64_t)e.start >= (uint64_t)mine.x + L) break;
       uint64_t a = e.start > mine.x ? e.start : mine.x;
       uint64_t b = (uint64_t)e.start + e.len < (uint64_t)mine.x + L ? (uint64_t)e.start + e.len : (uint64_t)mine.x + L;
+      const bool soft = e.byte == MG_EXC_CASE;
+      if (soft && words) {
+        const uint32_t i0 = (uint32_t)(a - mine.x), i1 = (uint32_t)(b - mine.x);
+        if (mine.strand) M.set(ph + (uint32_t)L - i1, ph + (uint32_t)L - i0); else M.set(ph + i0, ph + i1);
+        continue;
+      }
       for (uint64_t i = a; i < b; i++) {
         const int idx = (int)(i - mine.x), n = mine.strand ? (L - 1 - idx) : idx;
-        const MgPhilox r = mg_philox_corrupt(t_lo, t_hi2f, (uint32_t)(n >> 2), C.k0, C.k1);
-        uint32_t base = mg_exc_byte(e, mine.hap, i), qual;
-        mg_corrupt_one(C, f, n, r.v[n & 3], base, qual);
-        SP::st8(seq_dst + (uint32_t)n, (uint8_t)base);
+        const uint32_t code = cur.at(i);
+        const uint32_t clean = (0x54474341u /* "ACGT" */ >> (8u * (mine.strand ? code ^ 3u : code))) & 0xFFu;   // what the loop writes when s == 0
+        const uint32_t keep = soft ? (0x74676361u /* "acgt" */ >> (8u * code)) & 0xFFu : (uint32_t)e.byte;
+        const uint32_t got = SP::ld8(seq_dst + (uint32_t)n);
+        SP::st8(seq_dst + (uint32_t)n, (uint8_t)(got != clean ? (uint32_t)'N' : keep));
+      }
+    }
+    if (M.any()) {
+      // soft-masked stretches, one aligned word of the line (four cycles) per step: the clean letters are
+      // rebuilt from the haplotype, a case base that was miscalled becomes 'N', the others their lower-case
+      // (on strand 1: uncomplemented) letter
+      typename SP::ptr wp = seq_dst - ph;
+      const int nw = (int)((ph + (uint32_t)L + 3u) >> 2);
+      MG_NOUNROLL
+      for (int k = 0; k < nw; k++, wp += 4) {
+        const uint32_t bits = M.next4();
+        if (!bits) continue;
+        const uint32_t bm = mg_bits4_to_bytes(bits);
+        const int n0 = 4 * k - (int)ph;                                  // output position of the word's byte 0
+        // haplotype position of the lowest base the word covers, relative to the read
+        const int rel = mine.strand ? L - 4 - n0 : n0;
+        const int64_t p = (int64_t)mine.x + rel;
+        uint32_t c8;                                                     // the four codes at p .. p + 3 (zeros where p < 0)
+        if (p >= 0) c8 = mg_codes16(mine.hap, p) & 0xFFu; else c8 = (mg_codes16(mine.hap, 0) << (2u * (uint32_t)(-p))) & 0xFFu;
+        if (mine.strand) c8 = (((c8 & 3u) << 6) | ((c8 & 0xCu) << 2) | ((c8 >> 2) & 0xCu) | (c8 >> 6)) ^ 0xFFu;
+        const uint32_t clean = mg_chars4(c8);
+        const uint32_t got = SP::ld32(wp);
+        const uint32_t mis = ((((got ^ clean) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) >> 7 & 0x01010101u) * 0xFFu;   // bytes that differ
+        const uint32_t low = (mine.strand ? mg_complement4(got) : got) | 0x20202020u;
+        const uint32_t out = (mis & 0x4E4E4E4Eu /* 'N' */) | (~mis & low);
+        SP::st32(wp, (got & ~bm) | (out & bm));
       }
     }
   }

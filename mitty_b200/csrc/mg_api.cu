@@ -723,7 +723,7 @@ static int fill_unit_params(mg_ctx *ctx, const mg_unit_desc *d, MgUnitParams &P,
     const MgUnitKeys K = mg_unit_keys(d->unit_seed, (uint32_t)n);
     P.key_tlen0 = K.tlen0; P.key_tlen1 = K.tlen1;
     P.key_perm0 = K.perm0; P.key_perm1 = K.perm1;
-    P.half_bits = K.half_bits;
+    P.perm_bits = K.perm_bits;
   } else if (d->mode == MG_MODE_DET || d->mode == MG_MODE_EXPLICIT) {
     if (n && (!d->ts || (!d->fo && !sample_only) || (d->mode == MG_MODE_DET ? !d->u_tlen : !d->tl))) return fail(ctx, MG_EINVAL, "deterministic mode needs ts, fo and u_tlen/tl arrays");
     if (n) {

@@ -187,23 +187,33 @@ MG_HD double mg_u53(uint32_t a, uint32_t b) {
 #define MG_STREAM_TLEN 0x746c656eu
 #define MG_STREAM_CORRUPT 0x636f7272u
 
-// Keyed pseudo-random permutation of [0, n): balanced Feistel network on the next even power of
-// two with cycle walking.  Replaces RandomState.shuffle (illumina.py:71) in production mode.
+// Keyed pseudo-random permutation of [0, n): a Feistel network over exactly bits = ceil(log2 n) bits (the low
+// bits / 2 and the high bits - bits / 2 bits take turns being the half that is XORed: with unequal halves it
+// is still a bijection of [0, 2^bits)) with cycle walking -- n > 2^(bits - 1), so at least half of the domain is
+// accepted and the lanes of a warp rarely walk more than twice.  Replaces RandomState.shuffle (illumina.py:71)
+// in production mode.
 MG_HD uint32_t mg_feistel_round(uint32_t r, uint32_t k) {
   uint32_t x = r * 0x9E3779B1u + k;
   x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
   return x;
 }
 
-MG_HD uint32_t mg_permute(uint32_t i, uint32_t n, uint32_t half_bits, uint32_t k0, uint32_t k1) {
-  const uint32_t hm = (1u << half_bits) - 1u;
+MG_HD uint32_t mg_perm_bits(uint32_t n) {       // ceil(log2 n), at least 2
+  uint32_t bits = 2;
+  while (bits < 32 && (1ull << bits) < (unsigned long long)n) bits++;
+  return bits;
+}
+
+MG_HD uint32_t mg_permute(uint32_t i, uint32_t n, uint32_t bits, uint32_t k0, uint32_t k1) {
+  const uint32_t wa = bits >> 1, ma = (1u << wa) - 1u, mb = (bits - wa >= 32u) ? 0xFFFFFFFFu : (1u << (bits - wa)) - 1u;
   do {
-    uint32_t l = i >> half_bits, r = i & hm;
-    for (int t = 0; t < 6; t++) {
-      uint32_t f = mg_feistel_round(r, (t & 1) ? k1 + (uint32_t)t : k0 + (uint32_t)t) & hm;
-      uint32_t nl = r; r = l ^ f; l = nl;
+    uint32_t a = i & ma, b = (i >> wa) & mb;
+    MG_UNROLL
+    for (int t = 0; t < 6; t += 2) {
+      a ^= mg_feistel_round(b, k0 + (uint32_t)t) & ma;
+      b ^= mg_feistel_round(a, k1 + (uint32_t)t + 1u) & mb;
     }
-    i = (l << half_bits) | r;
+    i = (b << wa) | a;
   } while (i >= n);
   return i;
 }
@@ -219,15 +229,24 @@ MG_HD uint32_t mg_pow10(int d) {   // 10^d for d in 0..9
   }
 }
 
-MG_NI int mg_ndigits32(uint32_t v) {   // no division: bit length -> digit estimate -> one correction
-#if defined(__CUDA_ARCH__)
-  const int bits = 32 - __clz((int)(v | 1u));
-#else
-  const int bits = 32 - __builtin_clz(v | 1u);
-#endif
-  const int g = (bits * 1233) >> 12;          // floor(bits * log10(2)), g in 0..9
-  return g + ((v >= mg_pow10(g)) || v == 0u ? 1 : 0);
+// decimal digits of v, and (ones) the number 11..1 with as many ones: no branch, no table (a switch or a table
+// indexed per lane serialises the lanes of a warp that hold numbers of different lengths)
+MG_HD int mg_ndigits_ones(uint32_t v, uint32_t &ones) {
+  int d = 1; uint32_t o = 1u;
+  if (v >= 10u) { d++; o += 10u; }
+  if (v >= 100u) { d++; o += 100u; }
+  if (v >= 1000u) { d++; o += 1000u; }
+  if (v >= 10000u) { d++; o += 10000u; }
+  if (v >= 100000u) { d++; o += 100000u; }
+  if (v >= 1000000u) { d++; o += 1000000u; }
+  if (v >= 10000000u) { d++; o += 10000000u; }
+  if (v >= 100000000u) { d++; o += 100000000u; }
+  if (v >= 1000000000u) { d++; o += 1000000000u; }
+  ones = o;
+  return d;
 }
+
+MG_HD int mg_ndigits32(uint32_t v) { uint32_t o; return mg_ndigits_ones(v, o); }
 
 MG_HD int mg_ndigits(uint64_t v) {
   if (v <= 0xFFFFFFFFull) return mg_ndigits32((uint32_t)v);
@@ -239,12 +258,12 @@ MG_HD int mg_ndigits(uint64_t v) {
 
 // sum of the decimal lengths of 1..m  (closed form; used to place records whose qname carries a
 // serial number that is only known after the block/grid scan):  d*(m+1) - 11..1 (d ones)
-MG_NI uint64_t mg_digit_sum(uint64_t m) {
+MG_HD uint64_t mg_digit_sum(uint64_t m) {
   if (m == 0) return 0;
   if (m <= 0xFFFFFFFFull) {
-    const int d = mg_ndigits32((uint32_t)m);
-    const uint64_t ones = d < 10 ? (uint64_t)((mg_pow10(d) - 1u) / 9u) : 1111111111ull;
-    return (uint64_t)d * (m + 1) - ones;
+    uint32_t ones;
+    const int d = mg_ndigits_ones((uint32_t)m, ones);
+    return (uint64_t)d * (m + 1) - (uint64_t)ones;
   }
   const int d = mg_ndigits(m);
   uint64_t ones = 0, p = 1;

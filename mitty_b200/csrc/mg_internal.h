@@ -52,7 +52,7 @@ struct MgUnitParams {
   const int64_t *tl_in;      // EXPLICIT: template lengths
   const int8_t *fo_in;       // DET / EXPLICIT: file-order bits, consumed in te<p_max survivor order
   const uint32_t *ts_sorted; // PHILOX: cumulative geometric gaps (+1), relative to p_min
-  uint32_t key_tlen0, key_tlen1, key_perm0, key_perm1, half_bits;
+  uint32_t key_tlen0, key_tlen1, key_perm0, key_perm1, perm_bits;
   // qname constants as tokens: "@sample:worker:ps:", "|chrom|cpy", "|<L>|<L>=|" (built on the host, read from
   // the kernel's parameter space)
   MgQnConst qn;
@@ -77,16 +77,13 @@ struct MgUnitParams {
 
 // the keys of a unit's Philox streams, all derived from its rng_seed: the one-unit path (mg_api.cu) and the
 // batch kernels must agree, so that a unit's bytes do not depend on the path it took
-struct MgUnitKeys { uint32_t gap0, gap1, tlen0, tlen1, perm0, perm1, half_bits; };
+struct MgUnitKeys { uint32_t gap0, gap1, tlen0, tlen1, perm0, perm1, perm_bits; };
 __host__ __device__ inline MgUnitKeys mg_unit_keys(uint32_t seed, uint32_t n_cand) {
   MgUnitKeys k;
   k.gap0 = seed; k.gap1 = 0x67617031u;
   k.tlen0 = seed; k.tlen1 = 0x746c6531u;
   k.perm0 = seed ^ 0x7368756bu; k.perm1 = seed * 0x9E3779B1u + 0x66656973u;
-  uint32_t bits = 2;
-  while (bits < 32 && (1ull << bits) < (unsigned long long)(n_cand > 2 ? n_cand : 2)) bits++;
-  if (bits & 1) bits++;
-  k.half_bits = bits / 2;
+  k.perm_bits = mg_perm_bits(n_cand);
   return k;
 }
 

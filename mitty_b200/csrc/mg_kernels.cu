@@ -557,7 +557,7 @@ __device__ __forceinline__ Cand sample_candidate(const MgUnitParams &P, const ui
   int64_t tl;
   c.fo = 0;
   if (P.mode == MG_MODE_PHILOX) {
-    uint32_t i = mg_permute(j, P.n_cand, P.half_bits, P.key_perm0, P.key_perm1);
+    uint32_t i = mg_permute(j, P.n_cand, P.perm_bits, P.key_perm0, P.key_perm1);
     c.ts_rel = (int64_t)P.ts_sorted[i];
     MgPhilox r = mg_philox(j, 0u, 0u, MG_STREAM_TLEN, P.key_tlen0, P.key_tlen1);
     if (P.tlen_alias) {                                                        // illumina.py:72 by the alias method
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_batch_plan(const __grid_consta
     if (j < n) {
       int64_t ts_rel, tl;
       if (P.mode == MG_MODE_PHILOX) {
-        const uint32_t i = mg_permute(j, n, K.half_bits, K.perm0, K.perm1);
+        const uint32_t i = mg_permute(j, n, K.perm_bits, K.perm0, K.perm1);
         ts_rel = (int64_t)s_ts[i];
         const MgPhilox r = mg_philox(j, 0u, 0u, MG_STREAM_TLEN, K.tlen0, K.tlen1);
         if (P.tlen_alias) { const uint32_t idx = r.v[0] >> 22, e = s_tlen[idx]; tl = (r.v[0] & 0x3FFFFFu) < (e >> 10) ? idx : (e & 1023u); }

@@ -92,8 +92,8 @@ int64_t emul_unit(const uint32_t *hap, uint32_t hap_len, const MgNode *nodes, in
   return -9;
 }
 
-void emul_permute(uint32_t n, uint32_t half_bits, uint32_t k0, uint32_t k1, uint32_t *out) {
-  for (uint32_t i = 0; i < n; i++) out[i] = mg_permute(i, n, half_bits, k0, k1);
+void emul_permute(uint32_t n, uint32_t k0, uint32_t k1, uint32_t *out) {
+  for (uint32_t i = 0; i < n; i++) out[i] = mg_permute(i, n, mg_perm_bits(n), k0, k1);
 }
 
 void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {

@@ -95,13 +95,9 @@ def test_digit_sum_and_permutation(emul):
     acc += len(str(m + 1))
   for m in (99999, 100000, 123456789, 10 ** 9):
     assert emul.emul_digit_sum(m) == sum((min(m, 10 ** d - 1) - 10 ** (d - 1) + 1) * d for d in range(1, len(str(m)) + 1))
-  for n in (1, 2, 3, 17, 1000, 4097, 70001):
-    bits = 2
-    while (1 << bits) < max(n, 2):
-      bits += 1
-    bits += bits & 1
+  for n in (1, 2, 3, 4, 5, 17, 1000, 2048, 2049, 4097, 70001, 131072):      # odd and even bit counts, exact powers of two
     out = np.zeros(n, dtype=np.uint32)
-    emul.emul_permute(C.c_uint32(n), C.c_uint32(bits // 2), C.c_uint32(12345), C.c_uint32(678), C.c_void_p(out.ctypes.data))
+    emul.emul_permute(C.c_uint32(n), C.c_uint32(12345), C.c_uint32(678), C.c_void_p(out.ctypes.data))
     assert np.array_equal(np.sort(out), np.arange(n, dtype=np.uint32))
     if n > 1000:
       assert np.corrcoef(out.astype(float), np.arange(n))[0, 1] < 0.05

@@ -391,6 +391,16 @@ def main():
   contigs = dict(wl['contigs'])
   vcf_df = [vcfio.from_variant_table(tables[region[0]], region) for region in wl['regions']]
   refs = {region: np.ascontiguousarray(contigs[region[0]][region[1]:region[2]]) for region in wl['regions']}
+  # the step's host inputs (the reference bytes of every region) live in page-locked host memory, as the timing contract
+  # asks: the H2D copy inside the timed region then runs at the link's speed instead of through the driver's staging buffer
+  pinned_keep = []
+  if sum(a.nbytes for a in refs.values()) <= (4 << 30):
+    for region, a in list(refs.items()):
+      t = torch.empty(max(1, a.size), dtype=torch.uint8).pin_memory()
+      v = t.numpy()[:a.size]
+      v[:] = a
+      refs[region] = v
+      pinned_keep.append(t)
   fetch_ref = lambda region: refs[region]  # noqa: E731
   if args.workload == 'wgs':
     mine = multigpu.assign_units([r[2] - r[1] for r in wl['regions']], world)[rank]       # value leg: contigs by LPT
@@ -564,7 +574,7 @@ def main():
                      'writer_threads_per_rank': e2e['writers'], 'gbs_written': e2e['bytes'] / e2e['wall'] / 1e9,
                      'd2h_ceiling_gbs': e2e['d2h_ceiling_gbs'], 'frac_of_d2h_ceiling': (e2e['bytes'] / e2e['wall'] / 1e9) / max(1e-9, e2e['d2h_ceiling_gbs']),
                      'file_sink': e2e['file'],
-                     'path': 'readgenerate.gpu_worker (units pulled in schedule order) -> drain thread (D2H) -> native sink'}
+                     'host_inputs': 'page-locked' if pinned_keep else 'pageable', 'path': 'readgenerate.gpu_worker (units pulled in schedule order) -> drain thread (D2H) -> native sink'}
     if not args.no_cpu_baseline and world == 1:
       cwl = wl if args.workload == 'chr1' else {'contigs': [wl['contigs'][0]], 'tables': [wl['tables'][0]], 'sample': wl['sample']}
       n, wall, sl = port_baseline(cwl, 1)

@@ -602,9 +602,10 @@ static int build_segments(mg_ctx *ctx, const uint32_t *d_ref, const MgExc *d_rex
   if (n_exc) mg_launch_exc_write(C.d_nodes, W.node_alt, W.sum, (int)max_nodes, sb + o_alt, d_rexc, n_rexc, e_off, C.d_exc, ctx->stream);
   CU(cudaMemsetAsync(C.d_hap, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
   CU(cudaMemsetAsync(C.d_hap + MG_HAP_PAD + C.hap_words, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
-  if (hap_len > 0)
-    mg_launch_hap_build(d_ref, sb + o_alt, C.d_nodes, W.node_alt, (int)nn, (uint32_t)hap_len, C.d_hap + MG_HAP_PAD, C.hap_words, ctx->stream);
   mg_launch_blk_table(C.d_nodes, (int)nn, C.d_blk, C.n_blk, BLK_SHIFT, ctx->stream);
+  if (hap_len > 0)
+    mg_launch_hap_build(d_ref, sb + o_alt, C.d_nodes, W.node_alt, (int)nn, C.d_blk, BLK_SHIFT, C.n_blk, (uint32_t)hap_len, C.d_hap + MG_HAP_PAD,
+                        C.hap_words, ctx->stream);
   ctx->total_launches += 2 + (n_exc ? 1 : 0);
   CU(cudaGetLastError());
   tm.lap("enqueue build");                            // stream-ordered: units launched next wait for these kernels

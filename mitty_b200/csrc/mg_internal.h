@@ -149,7 +149,8 @@ void mg_launch_exc_count(const MgNode *nodes, const uint32_t *node_alt, const Mg
 void mg_launch_exc_write(const MgNode *nodes, const uint32_t *node_alt, const MgWalkSummary *sum, int max_nodes,
                          const uint8_t *alt_pool, const MgExc *rexc, int n_rexc, int64_t *off, MgExc *out, cudaStream_t st);
 void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const MgNode *nodes, const uint32_t *node_alt,
-                         int n_nodes, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st);
+                         int n_nodes, const uint32_t *blk, int blk_shift, int n_blk, uint32_t hap_len, uint32_t *hap, int64_t hap_words,
+                         cudaStream_t st);   // after mg_launch_blk_table
 void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st);
 void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
                         cudaStream_t st);

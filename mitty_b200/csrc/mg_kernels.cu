@@ -372,18 +372,15 @@ __device__ __forceinline__ uint64_t hap_node_src(const MgNode &nd, uint32_t alt)
 
 __global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ ref, const uint8_t *__restrict__ alt_pool,
                                                    const MgNode *__restrict__ nodes, const uint32_t *__restrict__ node_alt,
-                                                   int n_seg, uint32_t hap_len, uint32_t *__restrict__ hap, int64_t hap_words) {
+                                                   int n_seg, const uint32_t *__restrict__ blk, int blk_shift, int n_blk,
+                                                   uint32_t hap_len, uint32_t *__restrict__ hap, int64_t hap_words) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= hap_words) return;
   uint64_t s0 = (uint64_t)w * 16;
   if (s0 >= hap_len) { hap[w] = 0; return; }
-  // last node with key <= s0 (of equal keys the later one: never the empty 'D')
-  int lo = 0, hi = n_seg - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if ((uint64_t)nodes[mid].key <= s0) lo = mid; else hi = mid - 1;
-  }
-  int k = lo;
+  // last node with key <= s0 (of equal keys the later one: never the empty 'D'): the block table (built just
+  // before) leaves a search over the few nodes of one 256-base block
+  int k = mg_find_node(nodes, blk, blk_shift, n_blk, n_seg, (uint32_t)s0);
   MgNode nd = nodes[k];
   uint64_t seg_end = (k + 1 < n_seg) ? nodes[k + 1].key : hap_len;
   uint64_t src = hap_node_src(nd, node_alt[k]);
@@ -416,9 +413,10 @@ __global__ void __launch_bounds__(256) k_hap_build(const uint32_t *__restrict__ 
 }
 
 void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const MgNode *nodes, const uint32_t *node_alt,
-                         int n_nodes, uint32_t hap_len, uint32_t *hap, int64_t hap_words, cudaStream_t st) {
+                         int n_nodes, const uint32_t *blk, int blk_shift, int n_blk, uint32_t hap_len, uint32_t *hap, int64_t hap_words,
+                         cudaStream_t st) {
   if (hap_words == 0) return;
-  k_hap_build<<<(unsigned)((hap_words + 255) / 256), 256, 0, st>>>(ref, alt_pool, nodes, node_alt, n_nodes, hap_len, hap, hap_words);
+  k_hap_build<<<(unsigned)((hap_words + 255) / 256), 256, 0, st>>>(ref, alt_pool, nodes, node_alt, n_nodes, blk, blk_shift, n_blk, hap_len, hap, hap_words);
 }
 
 __global__ void __launch_bounds__(256) k_blk_table(const MgNode *__restrict__ nodes, int n_nodes, uint32_t *__restrict__ blk,

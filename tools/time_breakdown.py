@@ -12,7 +12,9 @@ from mitty_b200.readmodels import load_model
 class A: pass
 args = A(); args.contig_len = int(sys.argv[1]) if len(sys.argv) > 1 else 249250621; args.seed = 7
 model = load_model(bench.MODEL); rm = il.read_model_params(model, 30.0)
-t0 = time.perf_counter(); wl, region, r = bench.make_workload(args, 0); print('make_workload %.2fs' % (time.perf_counter() - t0))
+t0 = time.perf_counter(); wl = bench.make_chr1(args, 0); print('make_chr1 %.2fs' % (time.perf_counter() - t0))
+from mitty_b200.lib import vcfio
+r = vcfio.from_variant_table(wl['tables'][0], wl['regions'][0])
 eng = Engine(0); eng.load_model(rm)
 ref = np.ascontiguousarray(wl['contigs'][0][1])
 def T(label, fn):

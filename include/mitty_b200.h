@@ -199,6 +199,19 @@ int mg_batch_generate(mg_ctx *ctx, int64_t batch_id, int64_t n_units, const int3
                       const int8_t *fo, const int64_t *cand_off, int32_t corrupt, uint32_t corrupt_seed, mg_sink *sink,
                       int32_t producer, int64_t *n_templates, int64_t *n_bytes, int64_t *unit_bytes, int64_t *unit_templates);
 
+/* ---- FASTA front end: pysam.FastaFile(fname).fetch(reference=, start=, end=) as the reference uses it
+ * (mitty/simulation/readgenerate.py:181, 186), native and free of the GIL, so that the worker threads of
+ * several GPUs fetch their regions at the same time.  Plain (not gzip) files; contigs with lines of one
+ * width are addressed arithmetically in the mapped file, ragged ones are stripped once.  Bytes come back
+ * as they are in the file.  mg_fasta_fetch -> bases written (start / end clamped to the contig, as a numpy
+ * slice), MG_EINDEX for an unknown contig.                                                            */
+typedef struct mg_fasta mg_fasta;
+int mg_fasta_open(const char *path, mg_fasta **out);
+void mg_fasta_close(mg_fasta *f);
+int64_t mg_fasta_n_contigs(mg_fasta *f);
+int mg_fasta_contig(mg_fasta *f, int64_t i, const char **name, int64_t *length, int32_t *uniform);
+int64_t mg_fasta_fetch(mg_fasta *f, const char *name, int64_t start, int64_t end, uint8_t *out, int32_t threads);
+
 /* ---- corrupt-reads: replaces readcorrupt.multi_process / illumina.corrupt_template
  * (mitty/simulation/readcorrupt.py:18-118, illumina.py:113-162) over whole FASTQ buffers.
  * in2/out2 may be NULL (single-end).  DET mode consumes the reference's draws: for read k (file-1

@@ -11,8 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libmitty_b200.so')
-SOURCES = ['mg_api.cu', 'mg_kernels.cu', 'mg_check.cu', 'mg_sink.cpp']
-HEADERS = ['mg_core.cuh', 'mg_internal.h', 'mg_sink.cpp', 'mg_check.cu', os.path.join('..', '..', 'include', 'mitty_b200.h')]
+SOURCES = ['mg_api.cu', 'mg_kernels.cu', 'mg_check.cu', 'mg_sink.cpp', 'mg_fasta.cpp']
+HEADERS = ['mg_core.cuh', 'mg_internal.h', 'mg_sink.cpp', 'mg_check.cu', 'mg_fasta.cpp', os.path.join('..', '..', 'include', 'mitty_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared', '-lz']
 
@@ -26,6 +26,7 @@ SYMBOLS = ['mg_device_count', 'mg_ctx_create', 'mg_ctx_destroy', 'mg_last_error'
            'mg_prof_reset', 'mg_prof_get', 'mg_sink_create', 'mg_sink_create_shared', 'mg_sink_next_unit', 'mg_sink_unit_size', 'mg_sink_acquire', 'mg_sink_commit', 'mg_sink_abort',
            'mg_sink_commit_multi', 'mg_sink_error', 'mg_sink_chunk_bytes', 'mg_sink_close', 'mg_unit_drain_async', 'mg_drain_wait',
            'mg_batch_build', 'mg_batch_free', 'mg_batch_generate',
+           'mg_fasta_open', 'mg_fasta_close', 'mg_fasta_n_contigs', 'mg_fasta_contig', 'mg_fasta_fetch',
            'mg_check_open', 'mg_check_close', 'mg_check_add_copy', 'mg_check_fastq']
 
 
@@ -116,6 +117,14 @@ def lib():
     L.mg_sink_close.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mg_unit_drain_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]
     L.mg_drain_wait.argtypes = [C.c_void_p]
+    L.mg_fasta_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.mg_fasta_close.argtypes = [C.c_void_p]
+    L.mg_fasta_close.restype = None
+    L.mg_fasta_n_contigs.argtypes = [C.c_void_p]
+    L.mg_fasta_n_contigs.restype = C.c_int64
+    L.mg_fasta_contig.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    L.mg_fasta_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32]
+    L.mg_fasta_fetch.restype = C.c_int64
     L.mg_check_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.mg_check_close.argtypes = [C.c_void_p]
     L.mg_check_close.restype = None

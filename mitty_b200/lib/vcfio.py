@@ -15,6 +15,8 @@ test_vcfio.py:9-18 pins it: deletion at 11 is returned for [8,14), insertion at 
 The per-copy result is a ``VariantList``: flat numpy arrays ready for the C-ABI
 (``mg_copy_build``), which also behaves like the reference's ``list`` of ``Variant`` objects.
 """
+import ctypes as C
+import os
 import gzip
 import re
 import time
@@ -131,6 +133,9 @@ def _gt_tuple(fmt, s):
   return tuple(None if g == '.' else int(g) for g in s.replace('/', '|').split('|'))
 
 
+VCF_PIECE_BYTES = 4 << 20      # a VCF body larger than two of these is parsed in pieces by threads (1.19 -> 0.23 s for 1.2 M records on 8 cores)
+
+
 class VcfTable(object):
   """All records of one sample, grouped by contig, parsed with numpy over the raw bytes (a 4 M-record
   WGS call set in seconds; the reference walks pysam records one by one, vcfio.py:59-62).
@@ -163,24 +168,53 @@ class VcfTable(object):
     # names an indexed fetch accepts; pysam raises ValueError for any other (vcfio.py:62)
     self.header_contigs = set(m.decode() for m in re.findall(rb'^##contig=<(?:[^>\n]*,)?ID=([^,>\n]+)', data[:h], flags=re.M))
     body = min(he + 1, len(data))
-    nl = np.flatnonzero(buf[body:] == 10) + body
+    # large files: the body is cut at line starts into pieces parsed by threads (numpy releases the GIL in the
+    # scans, searches and gathers that make up the parser); a contig met again in a later piece is merged
+    n_pieces = 1
+    if len(data) - body > 2 * VCF_PIECE_BYTES:
+      n_pieces = max(1, min(os.cpu_count() or 1, 16, (len(data) - body) // VCF_PIECE_BYTES))
+    cuts = [body]
+    for k in range(1, n_pieces):
+      at = data.find(b'\n', body + (len(data) - body) * k // n_pieces)
+      if at < 0:
+        break
+      if at + 1 > cuts[-1]:
+        cuts.append(at + 1)
+    cuts.append(len(data))
+    ranges = [(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+    if len(ranges) > 1:
+      from concurrent.futures import ThreadPoolExecutor
+      with ThreadPoolExecutor(len(ranges)) as ex:
+        parts = list(ex.map(lambda r: self._parse_range(r[0], r[1], col, fname), ranges))
+    else:
+      parts = [self._parse_range(lo, hi, col, fname) for lo, hi in ranges]
+    for part in parts:
+      for name, c in part:
+        self.contigs[name] = self.contigs[name].merged(c) if name in self.contigs else c
+
+  def _parse_range(self, body, stop, col, fname):
+    """The records of data[body:stop] (whole lines) -> [(contig name, _Contig)] in file order.  Byte
+    positions in the _Contig arrays are absolute (into self.buf)."""
+    data, buf = self.data, self.buf
+    out = []
+    nl = np.flatnonzero(buf[body:stop] == 10) + body
     starts = np.concatenate([np.array([body], dtype=np.int64), nl + 1])
-    ends = np.concatenate([nl, np.array([len(data)], dtype=np.int64)])
+    ends = np.concatenate([nl, np.array([stop], dtype=np.int64)])
     keep = ends > starts
     starts, ends = starts[keep], ends[keep]
     if starts.size:
       keep = buf[starts] != 35                                           # stray '#' lines
       starts, ends = starts[keep], ends[keep]
       ends = ends - (buf[ends - 1] == 13)                                # CRLF
-    tabs = np.flatnonzero(buf[body:] == 9) + body
+    tabs = np.flatnonzero(buf[body:stop] == 9) + body
     t0 = np.searchsorted(tabs, starts)
     ntab = np.searchsorted(tabs, ends) - t0
     keep = ntab >= col                                                   # short lines are skipped
     starts, ends, t0, ntab = starts[keep], ends[keep], t0[keep], ntab[keep]
     n = starts.size
     if n == 0:
-      return
-    tabs_p = np.concatenate([tabs, np.array([len(data)], dtype=np.int64)])
+      return out
+    tabs_p = np.concatenate([tabs, np.array([stop], dtype=np.int64)])
 
     def fs(k):
       return starts if k == 0 else tabs[t0 + k - 1] + 1
@@ -209,16 +243,16 @@ class VcfTable(object):
       pos[m] = pos[m] * 10 + d
     rs, re_, as_, ae = fs(3), fe(3), fs(4), fe(4)
     # which records need the per-line path
-    commas = np.flatnonzero(buf[body:] == 44) + body
+    commas = np.flatnonzero(buf[body:stop] == 44) + body
     exotic = (np.searchsorted(commas, ae) - np.searchsorted(commas, as_)) > 0
     f8s, f8e = fs(8), fe(8)
     flen = f8e - f8s
     ok_fmt = (flen >= 2) & (buf[f8s] == 71) & (buf[np.minimum(f8s + 1, len(data) - 1)] == 84)
     ok_fmt &= (flen == 2) | (buf[np.minimum(f8s + 2, len(data) - 1)] == 58)
     ss, se = fs(col), fe(col)
-    colons = np.flatnonzero(buf[body:] == 58) + body
+    colons = np.flatnonzero(buf[body:stop] == 58) + body
     ci = np.searchsorted(colons, ss)
-    cpos = np.concatenate([colons, np.array([len(data)], dtype=np.int64)])[np.minimum(ci, colons.size)]
+    cpos = np.concatenate([colons, np.array([stop], dtype=np.int64)])[np.minimum(ci, colons.size)]
     ge = np.minimum(cpos, se)
     glen = ge - ss
     gmat = gather(ss, np.minimum(glen, 15))
@@ -255,7 +289,8 @@ class VcfTable(object):
       slow = {i - a: v for i, v in slow_all.items() if a <= i < b} if slow_all else {}
       c = _Contig(pos[a:b], rs[a:b], re_[a:b], as_[a:b], ae[a:b], gt[a:b], ploidy[a:b], exotic[a:b], slow,
                   (starts[a:b], ends[a:b], f8e[a:b], ss[a:b], se[a:b]))
-      self.contigs[name] = self.contigs[name].merged(c) if name in self.contigs else c
+      out.append((name, c))
+    return out
 
   def fetch(self, contig, start, stop):
     """Indices of records overlapping 0-based [start, stop) -- htslib semantics (vcfio.py:62)."""
@@ -440,9 +475,29 @@ def from_variant_table(vt, region):
 
 class FastaFile(object):
   """FASTA reader with pysam.FastaFile's fetch(reference=, start=, end=) (readgenerate.py:181,186).
-  Sequences come back as uint8 arrays of the file's bytes (case and IUPAC codes preserved)."""
+  Sequences come back as uint8 arrays of the file's bytes (case and IUPAC codes preserved).
 
-  def __init__(self, fname):
+  Plain files go through the library's native reader (mg_fasta_*: the file is mapped, a fetch is one
+  memcpy per line and holds no GIL, so the worker threads of several GPUs fetch at once); gzip'd files
+  (and a missing library) through the bytes-level reader below."""
+
+  def __init__(self, fname, native=True):
+    self._h = None
+    self._lengths = {}
+    if native:
+      try:
+        from mitty_b200 import _lib
+        L = _lib.lib()
+        h = C.c_void_p()
+        if L.mg_fasta_open(str(fname).encode(), C.byref(h)) == 0:
+          self._L, self._h = L, h
+          name, ln = C.c_char_p(), C.c_int64(0)
+          for i in range(L.mg_fasta_n_contigs(h)):
+            L.mg_fasta_contig(h, i, C.byref(name), C.byref(ln), None)
+            self._lengths.setdefault(name.value.decode(), ln.value)
+          return
+      except (RuntimeError, OSError, AttributeError):
+        self._h = None
     data = _open_bytes(fname)
     self._seqs = {}
     # headers are '>' at a line start; bytes.find runs at memchr speed (a 3 GB genome in a second)
@@ -457,10 +512,26 @@ class FastaFile(object):
       if eol < 0:
         eol = len(data)
       name = data[h + 1:eol].split()[0].decode() if eol > h + 1 else ''
-      self._seqs[name] = (min(eol + 1, len(data)), bounds[k + 1])
+      self._seqs.setdefault(name, (min(eol + 1, len(data)), bounds[k + 1]))
     self._data = data
     self._cache = {}
     self._lock = threading.Lock()
+
+  @property
+  def references(self):
+    return list(self._lengths) if self._h is not None else list(self._seqs)
+
+  def close(self):
+    if self._h is not None:
+      self._L.mg_fasta_close(self._h)
+      self._h = None
+      self._lengths = {}
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
 
   def _contig(self, name):
     with self._lock:   # one worker thread per GPU may fetch concurrently
@@ -470,4 +541,13 @@ class FastaFile(object):
       return self._cache[name]
 
   def fetch(self, reference=None, start=None, end=None):
-    return self._contig(reference)[start:end]
+    if self._h is None:
+      return self._contig(reference)[start:end]
+    n = self._lengths[reference]                       # KeyError for an unknown contig, as the dict above
+    a, b, _ = slice(start, end).indices(n)
+    out = np.empty(max(0, b - a), dtype=np.uint8)
+    if out.size:
+      got = self._L.mg_fasta_fetch(self._h, str(reference).encode(), a, b, C.c_void_p(out.ctypes.data), 4)
+      if got != out.size:
+        raise IOError('FASTA fetch of {}:{}-{} returned {} of {} bases'.format(reference, a, b, got, out.size))
+    return out

@@ -5,6 +5,7 @@ import gzip
 import numpy as np
 import pytest
 
+from mitty_b200 import synth
 from mitty_b200.lib import vcfio
 
 HDR = '##fileformat=VCFv4.2\n##contig=<ID=1>\n##contig=<ID=3>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS0\tS1\n'
@@ -169,3 +170,102 @@ def test_unknown_contig_is_an_error(tmp_path):
   open(bed, 'w').write('chr1\t0\t100\n')
   with pytest.raises(ValueError, match='invalid contig'):
     vcfio.load_variant_file(vin, 'S0', bed)
+
+
+def _fasta_cases(tmp_path):
+  rs = np.random.RandomState(11)
+  def seq(n):
+    s = rs.choice(np.frombuffer(b'ACGTacgtNnRY', dtype=np.uint8), size=n)
+    return s.tobytes()
+  def wrap(s, w, eol=b'\n', last_eol=True):
+    lines = [s[i:i + w] for i in range(0, len(s), w)]
+    return eol.join(lines) + (eol if last_eol and lines else b'')
+  contigs = [('chr1 some description', seq(100003), 60, b'\n', True),     # the usual layout
+             ('2', seq(5000), 70, b'\r\n', True),                        # CRLF
+             ('empty', b'', 60, b'\n', True),
+             ('one_line', seq(777), 100000, b'\n', True),
+             ('exact', seq(600), 60, b'\n', True),                        # the last line is full
+             ('last', seq(12345), 50, b'\n', False)]                      # no line end at the end of the file
+  ragged = seq(900)
+  body = b''
+  want = {}
+  for name, s, w, eol, le in contigs[:-1]:
+    body += b'>' + name.encode() + eol + wrap(s, w, eol, le)
+    want[name.split()[0]] = s
+  # a contig whose lines differ in width, and one with two short lines adding up to a full one (61 bytes)
+  body += b'>ragged\n' + ragged[:60] + b'\n' + ragged[60:100] + b'\n' + ragged[100:400] + b'\n\n' + ragged[400:] + b'\n'
+  want['ragged'] = ragged
+  tricky = seq(240)
+  body += b'>tricky\n' + tricky[:60] + b'\n' + tricky[60:90] + b'\n' + tricky[90:119] + b'\n' + tricky[119:179] + b'\n' + tricky[179:239] + b'\n' + tricky[239:] + b'\n'
+  want['tricky'] = tricky
+  name, s, w, eol, le = contigs[-1]
+  body += b'>' + name.encode() + eol + wrap(s, w, eol, le)
+  want[name] = s
+  path = str(tmp_path / 'ref.fa')
+  with open(path, 'wb') as fp:
+    fp.write(body)
+  return path, want
+
+
+def test_native_fasta_reader_equals_the_bytes_level_one(tmp_path):
+  """mg_fasta_* (mapped file, arithmetic addressing of uniform contigs) against the plain-Python reader and
+  the known sequences: line widths, CRLF, empty / one-line contigs, ragged lines, no final line end, and
+  numpy-slice semantics of start / end (pysam clamps the same way)."""
+  path, want = _fasta_cases(tmp_path)
+  nat, ref = vcfio.FastaFile(path), vcfio.FastaFile(path, native=False)
+  assert nat._h is not None and ref._h is None
+  assert set(nat.references) == set(want) == set(ref.references)
+  rs = np.random.RandomState(3)
+  for name, s in want.items():
+    n = len(s)
+    assert nat.fetch(reference=name).tobytes() == s == ref.fetch(reference=name).tobytes()
+    spans = [(0, n), (0, 0), (n, n + 5), (n - 1, n), (5, 3), (None, 10), (10, None), (59, 61), (60, 120), (n - 7, n + 100)]
+    spans += [tuple(sorted(rs.randint(0, n + 1, size=2))) for _ in range(30)] if n else []
+    for a, b in spans:
+      got = nat.fetch(reference=name, start=a, end=b).tobytes()
+      assert got == s[slice(a, b)] == ref.fetch(reference=name, start=a, end=b).tobytes(), (name, a, b)
+  with pytest.raises(KeyError):
+    nat.fetch(reference='nope', start=0, end=1)
+  nat.close()
+
+
+def test_native_fasta_reader_large_region_in_threads(tmp_path):
+  """A fetch of more than 8 MB is split over threads: the pieces must join without a seam."""
+  rs = np.random.RandomState(5)
+  s = rs.choice(np.frombuffer(b'ACGT', dtype=np.uint8), size=20000003)
+  path = str(tmp_path / 'big.fa')
+  with open(path, 'wb') as fp:
+    fp.write(b'>big\n')
+    lines = np.full((s.size + 59) // 60 * 61, 10, dtype=np.uint8).reshape(-1, 61)
+    pad = np.concatenate([s, np.zeros(lines.shape[0] * 60 - s.size, dtype=np.uint8)])
+    lines[:, :60] = pad.reshape(-1, 60)
+    flat = lines.reshape(-1)
+    fp.write(flat[:s.size + s.size // 60].tobytes())          # ends with the last base (no final line end)
+  fa = vcfio.FastaFile(path)
+  assert fa._h is not None
+  assert np.array_equal(fa.fetch(reference='big'), s)
+  assert np.array_equal(fa.fetch(reference='big', start=1234567, end=19999999), s[1234567:19999999])
+
+
+def test_vcf_parsed_in_pieces_equals_one_pass(tmp_path, monkeypatch):
+  """Large call sets are cut at line starts and parsed by threads: same table as the single pass, also when a
+  contig continues in the next piece and when exotic records (multi-allelic, FORMAT beyond GT) fall anywhere."""
+  wl = synth.config1(contig_len=400000, names=('1', '2', '3'))
+  fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'w'))
+  one = vcfio.VcfTable(vcf, wl['sample'])
+  monkeypatch.setattr(vcfio, 'VCF_PIECE_BYTES', 1500)
+  monkeypatch.setattr(vcfio.os, 'cpu_count', lambda: 7)
+  many = vcfio.VcfTable(vcf, wl['sample'])
+  assert list(one.contigs) == list(many.contigs) and len(one.contigs) == 3
+  for name in one.contigs:
+    a, b = one.contigs[name], many.contigs[name]
+    for f in ('pos', 'reflen', 'rs', 're', 'as_', 'ae', 'gt', 'ploidy', 'exotic', 'ls', 'le', 'f9e', 'ss', 'se'):
+      assert np.array_equal(getattr(a, f), getattr(b, f)), (name, f)
+    assert a.slow == b.slow
+  r1 = vcfio.load_variant_file(vcf, wl['sample'], bed)
+  monkeypatch.undo()
+  r0 = vcfio.load_variant_file(vcf, wl['sample'], bed)
+  for x, y in zip(r0, r1):
+    assert x['region'] == y['region'] and len(x['v']) == len(y['v'])
+    for vx, vy in zip(x['v'], y['v']):
+      assert np.array_equal(vx.pos, vy.pos) and np.array_equal(vx.op, vy.op) and np.array_equal(vx.alt_pool, vy.alt_pool)

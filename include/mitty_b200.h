@@ -160,6 +160,9 @@ int mg_sink_commit(mg_sink *s, void *slot, int64_t unit, int64_t offset, int64_t
  * [slot_off[i], slot_off[i] + bytes[i]) of the slot = bytes [unit_off[i], ...) of unit[i]            */
 int mg_sink_commit_multi(mg_sink *s, void *slot, int32_t n, const int64_t *unit, const int64_t *unit_off, const int64_t *slot_off,
                          const int64_t *bytes);
+/* page-locks n buffers of chunk_bytes ahead of mg_sink_create (which takes them from the library's cache): the slow
+ * part of creating a sink, overlapped by the caller with its input parsing.  -> buffers locked                  */
+int32_t mg_sink_prealloc(int64_t chunk_bytes, int32_t n, int32_t n_threads);
 void mg_sink_abort(mg_sink *s, const char *why);   /* wakes every blocked producer with an error       */
 const char *mg_sink_error(mg_sink *s);
 int64_t mg_sink_chunk_bytes(mg_sink *s);          /* bytes per slot, as given at creation             */

@@ -24,7 +24,7 @@ SYMBOLS = ['mg_device_count', 'mg_ctx_create', 'mg_ctx_destroy', 'mg_last_error'
            'mg_region_load', 'mg_region_free', 'mg_copy_build', 'mg_copy_free', 'mg_copy_nodes',
            'mg_copy_haplotype', 'mg_sample_templates', 'mg_unit_generate', 'mg_unit_generate_async', 'mg_wait_copies', 'mg_unit_read_async', 'mg_corrupt_fastq',
            'mg_prof_reset', 'mg_prof_get', 'mg_sink_create', 'mg_sink_create_shared', 'mg_sink_next_unit', 'mg_sink_unit_size', 'mg_sink_acquire', 'mg_sink_commit', 'mg_sink_abort',
-           'mg_sink_commit_multi', 'mg_sink_error', 'mg_sink_chunk_bytes', 'mg_sink_close', 'mg_unit_drain_async', 'mg_drain_wait',
+           'mg_sink_commit_multi', 'mg_sink_prealloc', 'mg_sink_error', 'mg_sink_chunk_bytes', 'mg_sink_close', 'mg_unit_drain_async', 'mg_drain_wait',
            'mg_batch_build', 'mg_batch_free', 'mg_batch_generate',
            'mg_fasta_open', 'mg_fasta_close', 'mg_fasta_n_contigs', 'mg_fasta_contig', 'mg_fasta_fetch',
            'mg_check_open', 'mg_check_close', 'mg_check_add_copy', 'mg_check_fastq']
@@ -108,6 +108,8 @@ def lib():
     L.mg_batch_generate.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_uint32, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+    L.mg_sink_prealloc.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    L.mg_sink_prealloc.restype = C.c_int32
     L.mg_sink_abort.argtypes = [C.c_void_p, C.c_char_p]
     L.mg_sink_abort.restype = None
     L.mg_sink_error.argtypes = [C.c_void_p]

@@ -401,6 +401,26 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
     raise ValueError('fused corruption draws from Philox; for the deterministic mode run generate-reads --deterministic '
                      'and then corrupt-reads --deterministic, as the reference does')
   read_model = read_module.read_model_params(model, coverage)
+  if workers_per_gpu is None:
+    workers_per_gpu = 1      # (measured: several contexts on one GPU do not overlap the per-unit latencies -- the driver serialises them)
+  # Start-up work that needs no parsed input runs beside the parsing: CUDA initialisation and, when the regions are large
+  # enough for full-size slots, the page-locking of the sink's slots (seconds for the 6 GB of an 8-GPU run)
+  warm = {}
+
+  def warm_up():
+    try:
+      from mitty_b200 import _lib
+      warm['n_dev'] = device_count()
+      bed_span = max([r[2] - r[1] for r in vio.read_bed(bed_fname)] + [1])
+      est0 = int(bed_span * 1.05 * read_model['p'] * 1.2 * (2 * int(read_model['rlen']) + 150)) + (1 << 16)
+      if est0 >= CHUNK_BYTES and warm['n_dev'] > 0:
+        n_workers = len(devices) if devices is not None else max(1, min(int(threads), warm['n_dev']))
+        n_bufs = n_workers * max(1, int(workers_per_gpu)) * SLOTS_PER_GPU * (2 if fastq2_fname is not None else 1)
+        warm['locked'] = _lib.lib().mg_sink_prealloc(CHUNK_BYTES, n_bufs, 4)
+    except Exception as e:  # noqa: B902 -- best effort: the sink allocates what is missing
+      warm['error'] = e
+  warm_thread = threading.Thread(target=warm_up, daemon=True)
+  warm_thread.start()
   vcf_df = vio.load_variant_file(vcf_fname, sample_name, bed_fname)
   for r in vcf_df:                       # inputs the engine rejects: found before the outputs are opened
     for vl in r['v']:
@@ -408,14 +428,13 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   fasta = vio.FastaFile(fasta_fname)
   fetch_ref = lambda region: fasta.fetch(reference=region[0], start=region[1], end=region[2])  # noqa: E731
   schedule = list(get_data_for_workers(read_model, vcf_df, seed))
+  t_parsed = time.time()
+  warm_thread.join()
   if devices is None:
-    n_dev = device_count()
+    n_dev = warm.get('n_dev', device_count())
     if n_dev < 1:
       raise RuntimeError('mitty_b200: no CUDA device; the engine has no CPU fallback')
     devices = list(range(max(1, min(int(threads), n_dev))))
-  span_max = max([r['region'][2] - r['region'][1] for r in vcf_df] + [1])
-  if workers_per_gpu is None:
-    workers_per_gpu = 1      # (measured: several contexts on one GPU do not overlap the per-unit latencies -- the driver serialises them)
   devices = [d for d in devices for _ in range(max(1, int(workers_per_gpu)))]
   from mitty_b200 import multigpu
   weights = [vcf_df[wd['region_idx']]['region'][2] - vcf_df[wd['region_idx']]['region'][1] for wd in schedule]
@@ -431,7 +450,10 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
     tot = sum(weights[k] for k, wd in enumerate(schedule) if (wd['region_idx'], wd['region_cpy']) in small)
     est = max(est, int(tot / len(devices) * 1.05 * read_model['p'] * 1.2 * (2 * rlen + 150)) + (1 << 16))
   chunk = max(256, min(CHUNK_BYTES, est))
-  n_writers = sink_threads or max(4, min(16, 2 * len(devices) if not gzip_level else (os.cpu_count() or 4)))
+  # writer threads: the cores the box has beyond one drain thread per worker (they spin on their copy events); tmpfs
+  # writes keep scaling up to there (8 / 16 writers: 11.9 / 14.6 GB/s on a 16-core box), deflate needs every core
+  cores = os.cpu_count() or 4
+  n_writers = sink_threads or max(4, min(24, cores - len(devices) - 2) if not gzip_level else cores)
   sink = Sink(fastq1_fname, fastq2_fname, len(schedule), n_producers=len(devices), slots=SLOTS_PER_GPU, chunk_bytes=chunk,
               gzip_level=gzip_level, threads=n_writers)
   t0 = time.time()
@@ -464,7 +486,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
   t1 = time.time()
   total = sum(totals)
   logger.debug('Finished: {} templates in {:0.2f}s ({:0.2f} t/s); inputs {:0.2f}s'.format(total, t1 - t0, total / max(t1 - t0, 1e-9), t0 - t_in))
-  last_run.update(templates=total, seconds=t1 - t0, input_seconds=t0 - t_in, gpus=len(devices), writers=n_writers, gzip_level=gzip_level,
+  last_run.update(templates=total, seconds=t1 - t0, input_seconds=t0 - t_in, parse_seconds=t_parsed - t_in, gpus=len(devices), writers=n_writers, gzip_level=gzip_level,
                   batches=sum(w.get('batches', 0) for w in wstats), dropped=sum(w.get('dropped', 0) for w in wstats))
   return None
 

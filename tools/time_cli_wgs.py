@@ -38,7 +38,7 @@ try:
   st = rg.last_run
   out = {'run': 'generate-reads --corrupt --threads {} (configs[3] at scale {:.3f}) -> {}'.format(threads, scale, target + ('  gzip level %d' % gz if gz else '')),
          'pairs': st['templates'], 'bytes_file1': os.path.getsize(r1), 'bytes_file2': os.path.getsize(r2),
-         'seconds_units_to_files': st['seconds'], 'seconds_inputs_parsed': st['input_seconds'], 'seconds_total': t2 - t1,
+         'seconds_units_to_files': st['seconds'], 'seconds_inputs_parsed': st.get('parse_seconds'), 'seconds_before_first_unit': st['input_seconds'], 'seconds_total': t2 - t1,
          'pairs_per_s': st['templates'] / st['seconds'], 'pairs_per_min': 60.0 * st['templates'] / st['seconds'],
          'pairs_per_min_incl_input_parsing': 60.0 * st['templates'] / (t2 - t1),
          'gbs_written': (os.path.getsize(r1) + os.path.getsize(r2)) / st['seconds'] / 1e9,

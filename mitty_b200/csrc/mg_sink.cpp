@@ -26,6 +26,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <condition_variable>
@@ -97,6 +98,8 @@ struct mg_sink {
   std::mutex mu;
   std::condition_variable cv_work, cv_slot, cv_idle, cv_poll;
   std::vector<std::thread> threads;
+  std::thread grower;                      // page-locks the slots beyond the first two per producer
+  std::atomic<bool> stop_grow{false}, no_pin{false};
   int64_t in_flight = 0;                   // committed pieces not yet written
   bool closing = false, failed = false;
   std::string err;
@@ -177,6 +180,31 @@ void poller(mg_sink *s) {
     if (!s->waiting.empty()) refresh_known(s);
     s->cv_poll.wait_for(lk, std::chrono::microseconds(200));
   }
+}
+
+// one slot (a buffer per file) for producer p: from the cache of closed sinks, else page-locked, else ordinary memory
+// (no CUDA driver -- the host logic is being exercised on a GPU-less box -- or no more lockable memory: ordinary
+// memory carries the bytes just as well, the device-to-host copies are merely slower)
+Slot *alloc_slot(mg_sink *s, int p) {
+  Slot *sl = new Slot();
+  sl->producer = p; sl->refs = 0; sl->buf[0] = sl->buf[1] = nullptr; sl->pinned = true;
+  for (int f = 0; f < s->n_files; f++) {
+    if ((sl->buf[f] = cache_get(s->chunk)) != nullptr) continue;
+    if (!s->no_pin.load() && cudaHostAlloc((void **)&sl->buf[f], (size_t)s->chunk, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      s->no_pin.store(true); sl->buf[f] = nullptr;
+    }
+    if (!sl->buf[f]) {
+      sl->pinned = false;
+      if (posix_memalign((void **)&sl->buf[f], 4096, (size_t)s->chunk) != 0) {
+        fprintf(stderr, "mitty_b200: cannot allocate %lld bytes for the output sink\n", (long long)s->chunk);
+        for (int g = 0; g < f; g++) cache_put(s->chunk, sl->buf[g]);
+        delete sl;
+        return nullptr;
+      }
+    }
+  }
+  return sl;
 }
 
 void deflate_piece(Piece *p, int level) {
@@ -311,29 +339,29 @@ int mg_sink_create_shared(const char *path1, const char *path2, int64_t n_units,
     }
   }
   s->pool.resize((size_t)n_producers);
-  bool pinned = true;
-  for (int p = 0; p < n_producers; p++)
-    for (int k = 0; k < slots_per_producer; k++) {
-      Slot *sl = new Slot();
-      sl->producer = p; sl->refs = 0; sl->buf[0] = sl->buf[1] = nullptr; sl->pinned = pinned;
-      for (int f = 0; f < s->n_files; f++) {
-        if ((sl->buf[f] = cache_get(chunk_bytes)) != nullptr) continue;
-        if (pinned && cudaHostAlloc((void **)&sl->buf[f], (size_t)chunk_bytes, cudaHostAllocPortable) != cudaSuccess) {
-          // no CUDA driver (the host logic is being exercised on a GPU-less box) or no more lockable memory:
-          // ordinary memory carries the bytes just as well, the device-to-host copies are merely slower
-          cudaGetLastError();
-          pinned = false; sl->pinned = f > 0;
-        }
-        if (!pinned && !sl->buf[f] && posix_memalign((void **)&sl->buf[f], 4096, (size_t)chunk_bytes) != 0) {
-          fprintf(stderr, "mitty_b200: cannot allocate %lld bytes for the output sink\n", (long long)chunk_bytes);
-          s->all_slots.push_back(sl);
-          mg_sink_close(s, nullptr, nullptr);
-          return MG_ECUDA;
-        }
-      }
+  // two slots per producer now; the others are page-locked by a side thread while the first units are already
+  // travelling (locking runs at about a GB/s: the 6 GB of an 8-GPU run would otherwise hold the start back for seconds)
+  const int first = slots_per_producer < 2 ? slots_per_producer : 2;
+  for (int k = 0; k < first; k++)
+    for (int p = 0; p < n_producers; p++) {
+      Slot *sl = alloc_slot(s, p);
+      if (!sl) { mg_sink_close(s, nullptr, nullptr); return MG_ECUDA; }
       s->all_slots.push_back(sl);
       s->pool[(size_t)p].push_back(sl);
     }
+  if (slots_per_producer > first)
+    s->grower = std::thread([s, first, slots_per_producer, n_producers]() {
+      for (int k = first; k < slots_per_producer; k++)
+        for (int p = 0; p < n_producers; p++) {
+          if (s->stop_grow.load()) return;
+          Slot *sl = alloc_slot(s, p);
+          if (!sl) return;                                   // the producers go on with the slots they have
+          std::lock_guard<std::mutex> lk(s->mu);
+          s->all_slots.push_back(sl);
+          s->pool[(size_t)p].push_back(sl);
+          s->cv_slot.notify_all();
+        }
+    });
   if (n_threads < 1) n_threads = 1;
   for (int t = 0; t < n_threads; t++) s->threads.emplace_back(worker, s);
   if (s->shared) s->threads.emplace_back(poller, s);
@@ -480,6 +508,8 @@ int mg_sink_close(mg_sink *s, int64_t *written1, int64_t *written2) {
     s->closing = true;
     s->cv_work.notify_all(); s->cv_poll.notify_all();
   }
+  s->stop_grow.store(true);
+  if (s->grower.joinable()) s->grower.join();
   for (auto &t : s->threads) t.join();
   const bool failed = s->failed;
   if (written1) *written1 = s->written[0];

@@ -415,7 +415,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
       est0 = int(bed_span * 1.05 * read_model['p'] * 1.2 * (2 * int(read_model['rlen']) + 150)) + (1 << 16)
       if est0 >= CHUNK_BYTES and warm['n_dev'] > 0:
         n_workers = len(devices) if devices is not None else max(1, min(int(threads), warm['n_dev']))
-        n_bufs = n_workers * max(1, int(workers_per_gpu)) * SLOTS_PER_GPU * (2 if fastq2_fname is not None else 1)
+        n_bufs = n_workers * max(1, int(workers_per_gpu)) * 2 * (2 if fastq2_fname is not None else 1)   # the sink locks the rest while units already travel
         warm['locked'] = _lib.lib().mg_sink_prealloc(CHUNK_BYTES, n_bufs, 4)
     except Exception as e:  # noqa: B902 -- best effort: the sink allocates what is missing
       warm['error'] = e

@@ -348,6 +348,9 @@ def pick_sink(args, bytes_per_step):
 
 
 def main():
+  if os.environ.get('MG_BENCH_LOG'):
+    import logging
+    logging.basicConfig(level=getattr(logging, os.environ['MG_BENCH_LOG'].upper(), logging.INFO))
   args = parse()
   _guard_stdout()
   if args.impl == 'reference':

@@ -84,6 +84,7 @@ struct mg_ctx {
   // standalone corrupt kernel's (every cycle of the model); kshift / code9 are chosen per table
   std::vector<uint32_t> h_alias[2]; int a_kshift[2] = {0, 0}, a_code9[2] = {0, 0}, a_rows[2] = {0, 0};
   std::vector<std::pair<void *, size_t>> pool;   // device blocks of freed copies, reused by the next build
+  size_t pool_bytes = 0;
   std::map<void *, size_t> block_size;
   // handles
   std::map<int64_t, std::unique_ptr<Region>> regions;
@@ -114,6 +115,7 @@ struct mg_ctx {
   bool dstop = false, dfailed = false;
   std::string derr;
   cudaEvent_t ev_drain[2] = {nullptr, nullptr};
+  double d_wait_slot_ms = 0, d_wait_copy_ms = 0, d_idle_ms = 0; int64_t d_bytes = 0;   // MG_TIMING: where the drain thread's time went
 };
 
 namespace {
@@ -232,15 +234,26 @@ struct DeviceGuard {
 
 namespace {
 
-// Device blocks of freed chromosome copies are kept and handed to the next build: cudaMalloc /
-// cudaFree synchronise the device and cost milliseconds for haplotype-sized blocks.
+// Device blocks of freed regions / chromosome copies are kept and handed to the next build: cudaMalloc and
+// cudaFree wait for the device -- with device-to-host copies of finished units always in flight that is
+// milliseconds per call, and a worker that builds many copies per step (units pulled dynamically by several
+// processes: every rank meets most chromosomes) then starves its own drain thread.  Best fit among the blocks
+// that waste at most 4x / 16 MB; the blocks of a genome's chromosomes differ by 5x in size, so after the first
+// pass over the genome nearly every request is served from here.
 cudaError_t pool_get(mg_ctx *ctx, void **p, size_t bytes) {
   int best = -1;
+  const size_t limit = std::max(4 * bytes, bytes + ((size_t)16 << 20));
   for (size_t i = 0; i < ctx->pool.size(); i++)
-    if (ctx->pool[i].second >= bytes && ctx->pool[i].second <= 2 * bytes + (1u << 20) &&
+    if (ctx->pool[i].second >= bytes && ctx->pool[i].second <= limit &&
         (best < 0 || ctx->pool[i].second < ctx->pool[best].second)) best = (int)i;
-  if (best >= 0) { *p = ctx->pool[best].first; ctx->pool.erase(ctx->pool.begin() + best); return cudaSuccess; }
+  if (best >= 0) { *p = ctx->pool[best].first; ctx->pool_bytes -= ctx->pool[best].second; ctx->pool.erase(ctx->pool.begin() + best); return cudaSuccess; }
   cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess && !ctx->pool.empty()) {          // out of memory with blocks in reserve: give them back and try again
+    cudaGetLastError();
+    for (auto &b : ctx->pool) { ctx->block_size.erase(b.first); cudaFree(b.first); }
+    ctx->pool.clear(); ctx->pool_bytes = 0;
+    e = cudaMalloc(p, bytes);
+  }
   if (e == cudaSuccess) ctx->block_size[*p] = bytes;
   return e;
 }
@@ -249,7 +262,10 @@ void pool_free(mg_ctx *ctx, void *p) {
   if (!p) return;
   if (ctx) {
     auto it = ctx->block_size.find(p);
-    if (it != ctx->block_size.end() && ctx->pool.size() < 64) { ctx->pool.push_back({p, it->second}); return; }
+    if (it != ctx->block_size.end() && ctx->pool.size() < 4096 && ctx->pool_bytes + it->second <= ((size_t)48 << 30)) {
+      ctx->pool.push_back({p, it->second}); ctx->pool_bytes += it->second;
+      return;
+    }
     if (it != ctx->block_size.end()) ctx->block_size.erase(it);
   }
   cudaFree(p);
@@ -1040,7 +1056,7 @@ static void drain_loop(mg_ctx *ctx) {
   cudaSetDevice(ctx->device);
   std::unique_lock<std::mutex> lk(ctx->dmu);
   while (true) {
-    while (ctx->djobs.empty() && !ctx->dstop) ctx->dcv.wait(lk);
+    { const double ti = Timer::now(); while (ctx->djobs.empty() && !ctx->dstop) ctx->dcv.wait(lk); ctx->d_idle_ms += Timer::now() - ti; }
     if (ctx->djobs.empty()) return;
     const mg_ctx::DrainJob job = ctx->djobs.front(); ctx->djobs.pop_front();
     lk.unlock();
@@ -1052,7 +1068,7 @@ static void drain_loop(mg_ctx *ctx) {
     std::vector<int64_t> m_unit, m_uoff, m_soff, m_bytes;
     auto finish = [&](int i) {
       if (!slot[i]) return;
-      if (cudaEventSynchronize(ctx->ev_drain[i]) != cudaSuccess && err.empty()) err = "device-to-host copy failed";
+      { const double tc = Timer::now(); if (cudaEventSynchronize(ctx->ev_drain[i]) != cudaSuccess && err.empty()) err = "device-to-host copy failed"; ctx->d_wait_copy_ms += Timer::now() - tc; }
       int rc;
       if (job.units) {                                      // bytes [s_off, s_off + s_n) of the batch's stream: the units they belong to
         const std::vector<int64_t> &ui = *job.units, &b = *job.base;
@@ -1075,8 +1091,11 @@ static void drain_loop(mg_ctx *ctx) {
     for (int64_t off = 0; off < job.bytes && err.empty(); off += chunk, k ^= 1) {
       finish(k);                                            // the piece that used this event two steps ago
       void *b1 = nullptr, *b2 = nullptr;
+      const double ta = Timer::now();
       if (mg_sink_acquire(job.sink, job.producer, &b1, &b2, &slot[k]) != MG_OK) { err = mg_sink_error(job.sink); slot[k] = nullptr; break; }
+      ctx->d_wait_slot_ms += Timer::now() - ta;
       const int64_t n = std::min(chunk, job.bytes - off);
+      ctx->d_bytes += 2 * n;
       s_off[k] = off; s_n[k] = n;
       cudaError_t e = cudaMemcpyAsync(b1, ctx->s_out[job.ob][0].as<uint8_t>() + off, (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream);
       if (e == cudaSuccess && b2) e = cudaMemcpyAsync(b2, ctx->s_out[job.ob][1].as<uint8_t>() + off, (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream);
@@ -1114,6 +1133,11 @@ int mg_drain_wait(mg_ctx *ctx) {
   std::unique_lock<std::mutex> lk(ctx->dmu);
   while ((ctx->dbusy[0] > 0 || ctx->dbusy[1] > 0) && !ctx->dfailed) ctx->dcv.wait(lk);
   if (ctx->dfailed) return fail(ctx, MG_EVALUE, "output sink: %s", ctx->derr.c_str());
+  if (getenv("MG_TIMING")) {
+    fprintf(stderr, "[mg] drain thread of device %d: %.1f GB copied; waiting for copies %.0f ms, for slots %.0f ms, for units %.0f ms\n", ctx->device,
+            ctx->d_bytes / 1e9, ctx->d_wait_copy_ms, ctx->d_wait_slot_ms, ctx->d_idle_ms);
+    ctx->d_bytes = 0; ctx->d_wait_copy_ms = ctx->d_wait_slot_ms = ctx->d_idle_ms = 0;
+  }
   return MG_OK;
 }
 

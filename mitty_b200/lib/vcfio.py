@@ -540,14 +540,23 @@ class FastaFile(object):
         self._cache[name] = np.frombuffer(self._data[s:e].translate(None, b'\r\n'), dtype=np.uint8)
       return self._cache[name]
 
-  def fetch(self, reference=None, start=None, end=None):
+  def fetch(self, reference=None, start=None, end=None, out=None):
+    """out: optional uint8 array (e.g. page-locked) to receive the bases; a view of it is returned."""
     if self._h is None:
-      return self._contig(reference)[start:end]
+      seq = self._contig(reference)[start:end]
+      if out is None:
+        return seq
+      out[:seq.size] = seq
+      return out[:seq.size]
     n = self._lengths[reference]                       # KeyError for an unknown contig, as the dict above
     a, b, _ = slice(start, end).indices(n)
-    out = np.empty(max(0, b - a), dtype=np.uint8)
-    if out.size:
+    m = max(0, b - a)
+    if out is None:
+      out = np.empty(m, dtype=np.uint8)
+    elif out.size < m or out.dtype != np.uint8 or not out.flags['C_CONTIGUOUS']:
+      raise ValueError('FastaFile.fetch: out must be a contiguous uint8 array of at least {} bytes'.format(m))
+    if m:
       got = self._L.mg_fasta_fetch(self._h, str(reference).encode(), a, b, C.c_void_p(out.ctypes.data), 4)
-      if got != out.size:
-        raise IOError('FASTA fetch of {}:{}-{} returned {} of {} bases'.format(reference, a, b, got, out.size))
-    return out
+      if got != m:
+        raise IOError('FASTA fetch of {}:{}-{} returned {} of {} bases'.format(reference, a, b, got, m))
+    return out[:m]

@@ -94,6 +94,9 @@ def _without_end_crossing_deletions(vl, region, drop):
   return vio.VariantList(vl.pos[keep], vl.op[keep], vl.oplen[keep], ap, ao, rp, ro), int(cross.sum())
 
 
+PIN_REGION_BYTES = 4 << 20   # regions from this size on are fetched into page-locked memory
+
+
 class RegionCache(object):
   """Regions and chromosome copies resident in HBM, built on first use.  With ``expect``
   ({(region idx, copy): number of units that will ask for it}) each is released after its last
@@ -109,6 +112,19 @@ class RegionCache(object):
     for (r_idx, _cpy) in (expect or {}):
       self.left_copies[r_idx] = self.left_copies.get(r_idx, 0) + 1
     self.budget, self.resident, self.clock, self.used = budget, 0, 0, {}
+    self._pin = None          # page-locked landing area for the reference bytes of large regions (see _fetch)
+
+  def _fetch(self, region):
+    """The region's reference bytes.  A fetcher with ``into`` (FastaFetcher) fills a page-locked buffer of this
+    cache: the copy to the device is then one DMA instead of the driver's staged pieces, which queue behind the
+    device-to-host pieces of the units being drained.  (load_region returns after the copy: the buffer is free again.)"""
+    into = getattr(self.fetch_ref, 'into', None)
+    n = region[2] - region[1]
+    if into is None or n < PIN_REGION_BYTES:
+      return self.fetch_ref(region)
+    if self._pin is None or self._pin.size < n:
+      self._pin = self.engine.pinned(max([n] + [r['region'][2] - r['region'][1] for r in self.vcf_df]))
+    return into(region, self._pin)
 
   def _cost(self, r_idx):
     region = self.vcf_df[r_idx]['region']
@@ -134,7 +150,7 @@ class RegionCache(object):
     if key not in self.copies:
       region = self.vcf_df[r_idx]['region']
       if r_idx not in self.regions:
-        self.regions[r_idx] = self.engine.load_region(self.fetch_ref(region), region[1])
+        self.regions[r_idx] = self.engine.load_region(self._fetch(region), region[1])
         self.resident += self._cost(r_idx)
       vl, n_drop = _without_end_crossing_deletions(self.vcf_df[r_idx]['v'][cpy], region, self.drop_end_deletions)
       self.dropped += n_drop
@@ -158,6 +174,20 @@ class RegionCache(object):
       self.left_copies[r_idx] -= 1
       if self.left_copies[r_idx] == 0 and r_idx in self.regions:
         self.engine.free_region(self.regions.pop(r_idx))
+
+
+class FastaFetcher(object):
+  """fetch_ref of generate-reads over a FastaFile: ``f(region)`` -> the region's bytes (fasta.fetch(...),
+  readgenerate.py:186); ``f.into(region, out)`` -> the same, written into ``out``."""
+
+  def __init__(self, fasta):
+    self.fasta = fasta
+
+  def __call__(self, region):
+    return self.fasta.fetch(reference=region[0], start=region[1], end=region[2])
+
+  def into(self, region, out):
+    return self.fasta.fetch(reference=region[0], start=region[1], end=region[2], out=out)
 
 
 def generate_unit(engine, read_module, read_model, cp, chrom, cpy, rng_seed, sample_name, worker_id, ps,
@@ -426,7 +456,7 @@ def process_multi_threaded(fasta_fname, vcf_fname, sample_name, bed_fname, read_
     for vl in r['v']:
       _without_end_crossing_deletions(vl, r['region'], drop_end_deletions)
   fasta = vio.FastaFile(fasta_fname)
-  fetch_ref = lambda region: fasta.fetch(reference=region[0], start=region[1], end=region[2])  # noqa: E731
+  fetch_ref = FastaFetcher(fasta)
   schedule = list(get_data_for_workers(read_model, vcf_df, seed))
   t_parsed = time.time()
   warm_thread.join()

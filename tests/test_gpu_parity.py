@@ -291,13 +291,16 @@ def test_units_streamed_through_small_ring(tmp_path, monkeypatch, chunk):
 
 
 @pytest.mark.parametrize('devices', [[0, 0], [0, 0, 0], 'all'])
-def test_sharded_workers_identical_output(tmp_path, devices):
+def test_sharded_workers_identical_output(tmp_path, devices, monkeypatch):
   """Units dealt to several GPU workers (LPT), appended in schedule order: the bytes must not
   depend on the worker count.  [0, 0]: two workers with their own contexts on one GPU (the host
-  logic of the multi-GPU path on a 1-GPU box); 'all': one worker per GPU present."""
+  logic of the multi-GPU path on a 1-GPU box); 'all': one worker per GPU present.  With three workers the
+  regions also take the large-region route (reference bytes fetched into a worker's page-locked buffer)."""
   import mitty_b200.simulation.illumina as il
   import mitty_b200.simulation.readgenerate as rg
   from mitty_b200.engine import device_count
+  if devices == [0, 0, 0]:
+    monkeypatch.setattr(rg, 'PIN_REGION_BYTES', 1)
   info = H.golden()['fastq']['edge']
   wl = synth.edge_workload()
   fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'))

@@ -226,6 +226,14 @@ def test_native_fasta_reader_equals_the_bytes_level_one(tmp_path):
       assert got == s[slice(a, b)] == ref.fetch(reference=name, start=a, end=b).tobytes(), (name, a, b)
   with pytest.raises(KeyError):
     nat.fetch(reference='nope', start=0, end=1)
+  # into a caller's buffer (the workers' page-locked landing area)
+  buf = np.zeros(200000, dtype=np.uint8)
+  for fa_ in (nat, ref):
+    got = fa_.fetch(reference='chr1', start=17, end=90017, out=buf)
+    assert got.base is buf or got.ctypes.data == buf.ctypes.data
+    assert got.tobytes() == want['chr1'][17:90017]
+  with pytest.raises(ValueError):
+    nat.fetch(reference='chr1', start=0, end=1000, out=np.zeros(10, dtype=np.uint8))
   nat.close()
 
 

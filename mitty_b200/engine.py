@@ -175,7 +175,8 @@ class Engine(object):
 
   def generate_unit(self, cp, n, p, mode, seed, prefix, mid, ts=None, u_tlen=None, tl=None, fo=None,
                     corrupt=False, corrupt_seed=0, out=None, fetch=True, wait=True):
-    """One work unit -> (fastq1, fastq2, n_templates, n_te_kept).
+    """One work unit -> (fastq1, fastq2, n_templates, n_te_kept, bytes per file); the two arrays are None with
+    fetch=False (the unit stays on the device for ``drain_async`` / ``unit_read``).
 
     out: optional pair of preallocated uint8 arrays (e.g. pinned) to receive the bytes; the
     returned arrays are views of them.  fetch=False leaves the result on the device.

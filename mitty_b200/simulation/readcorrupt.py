@@ -91,7 +91,10 @@ def multi_process(read_module, read_model, fastq1_in, fastq1_out, fastq2_in=None
 
   The files are streamed in chunks through pinned buffers: the device indexes the records of each
   chunk, corrupts the complete templates and reports how many input bytes they occupied; the rest
-  is carried into the next chunk.  The output does not depend on the chunk size."""
+  is carried into the next chunk.  The output does not depend on the chunk size.
+
+  Page-locked host memory: one input buffer of ``chunk_bytes`` and two output buffers of twice that per file,
+  i.e. 10 x chunk_bytes for a pair (2.5 GB at the default 256 MB; ``chunk_bytes`` scales it down)."""
   t0 = time.time()
   engine = Engine(device)
   cnt = 0

@@ -1334,21 +1334,33 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_const
     const bool active = r < P.n_rec;
     const int64_t rr = active ? r : P.n_rec - 1;
     const int64_t gr = P.first + rr;                           // template index in the whole file: the Philox counter
-    int64_t nh0, nh1, s0, s1;
+    // everything this tile needs from the index arrays is asked for at once (one memory latency instead of one per
+    // file), and so are the line bounds of the tile this warp takes NEXT: they are used at the end of this one to
+    // prefetch that tile's name / sequence lines into L2 (the kernel is bound by the latency of its cold input
+    // loads: 7.8 stall cycles per issue on the long scoreboard before this, `profiles/r02_corrupt_staged_full.txt`)
+    int64_t nh0, nh1, s0, s1, s0b = 0, s1b = 0;
     fq_lines(P.nl[0], rr, nh0, nh1, s0, s1);
+    const bool two = P.n_files > 1;
+    if (two) { s0b = P.nl[1][4 * rr] + 1; s1b = P.nl[1][4 * rr + 1]; }
+    const int64_t off_a = P.out_off[0][rr], end_a = P.out_off[0][rr + 1];
+    const int64_t off_b = two ? P.out_off[1][rr] : 0, end_b = two ? P.out_off[1][rr + 1] : 0;
+    const int64_t rn = r + (int64_t)gridDim.x * MG_CTA;       // this lane's record of the warp's next tile
+    const bool has_next = rn < P.n_rec;
+    int64_t pn0 = 0, pn1 = 0, pb0 = 0, pb1 = 0;
+    if (has_next) {
+      pn0 = P.nl[0][4 * rn - 1] + 1; pn1 = P.nl[0][4 * rn + 1];
+      if (two) { pb0 = P.nl[1][4 * rn] + 1; pb1 = P.nl[1][4 * rn + 1]; }
+    }
+    if (two) for (int64_t a = s0b & ~31ll; a < s1b; a += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.in[1] + a));   // the other file's sequence line
     const int n_act = (int)(P.n_rec - wt * 32 < 32 ? P.n_rec - wt * 32 : 32);
     for (int f = 0; f < P.n_files; f++) {
-      if (f) { int64_t h0, h1; fq_lines(P.nl[f], rr, h0, h1, s0, s1); }
-      const int64_t off = P.out_off[f][rr];
-      const uint32_t rec = (uint32_t)(P.out_off[f][rr + 1] - off);
+      if (f) { s0 = s0b; s1 = s1b; }
+      const int64_t off = f ? off_b : off_a;
+      const uint32_t rec = (uint32_t)((f ? end_b : end_a) - off);
       const int L = (int)(s1 - s0);
       const int name_len = (int)rec - 2 * L - 6;
       const unsigned long long my_end = active ? (unsigned long long)(off + rec) : 0ull;
       const uint8_t *src = P.in[f] + s0;
-      if (f + 1 < P.n_files) {                                  // the other file's sequence line, on its way while this one is processed
-        const int64_t q0 = P.nl[f + 1][4 * rr] + 1, q1 = P.nl[f + 1][4 * rr + 1];
-        for (int64_t a = q0 & ~31ll; a < q1; a += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.in[f + 1] + a));
-      }
       const uint32_t rowf = (uint32_t)f * (uint32_t)C.n_cycles, t_lo = (uint32_t)gr, t_hi2f = (uint32_t)((unsigned long long)gr >> 32) * 2u + (uint32_t)f;
       int lo = 0;
       while (lo < n_act) {
@@ -1374,13 +1386,22 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_const
           const uint32_t *wp = reinterpret_cast<const uint32_t *>(np_ - ((uintptr_t)np_ & 3));
           uint32_t carry = wp[0];
           wn.append(mg_tok('@', 0, 1));
-          for (int i = 0; i < name_len; i += 8) {
-            const uint32_t w1 = wp[(i >> 2) + 1], w2 = wp[(i >> 2) + 2];
-            uint32_t lo4 = __funnelshift_r(carry, w1, sh), hi4 = __funnelshift_r(w1, w2, sh);
-            carry = w2;
-            const int m = name_len - i < 8 ? name_len - i : 8;
-            if (m < 8) { if (m <= 4) { hi4 = 0; lo4 = m == 4 ? lo4 : lo4 & ((1u << (8 * m)) - 1u); } else hi4 &= (1u << (8 * (m - 4))) - 1u; }
-            wn.append(mg_tok(lo4, hi4, (uint32_t)m));
+#pragma unroll 1
+          for (int i0 = 0; i0 < name_len; i0 += 32) {              // eight words (four tokens) per trip: their loads are in flight together
+            uint32_t v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = (i0 + 4 * q < name_len) ? wp[(i0 >> 2) + q + 1] : 0u;
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+              const int i = i0 + 4 * q;
+              if (i < name_len) {
+                uint32_t lo4 = __funnelshift_r(carry, v[q], sh), hi4 = __funnelshift_r(v[q], v[q + 1], sh);
+                const int m = name_len - i < 8 ? name_len - i : 8;
+                if (m < 8) { if (m <= 4) { hi4 = 0; lo4 = m == 4 ? lo4 : lo4 & ((1u << (8 * m)) - 1u); } else hi4 &= (1u << (8 * (m - 4))) - 1u; }
+                wn.append(mg_tok(lo4, hi4, (uint32_t)m));
+              }
+              carry = v[q + 1];
+            }
           }
           wn.append(mg_tok('\n', 0, 1));
           wn.flush_own();
@@ -1480,6 +1501,10 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_const
         }
         lo = hi;
       }
+    }
+    if (has_next) {                                              // the next tile's name and sequence lines, on their way into L2
+      for (int64_t a = pn0 & ~31ll; a < pn1; a += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.in[0] + a));
+      if (two) for (int64_t a = pb0 & ~31ll; a < pb1; a += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.in[1] + a));
     }
   }
   if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

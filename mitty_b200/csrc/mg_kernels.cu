@@ -1411,8 +1411,9 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_const
           const uint32_t seq_dst = dst + (uint32_t)name_len + 2u, qual_dst = seq_dst + (uint32_t)L + 3u;
           MgSharedSpace::st8(qual_dst + L, '\n');
           const int NG = L >> 2, rem = L & 3;
-          {   // 1. the letters as they are, parked in the record's own sequence line: eight independent loads in flight
-              //    at a time (the per-group loads of the main loop would each wait for DRAM on their own)
+          {   // 1. the letters as they are, parked in the record's own sequence line: PARK independent loads in flight
+              //    at a time (the per-group loads of the main loop would each wait for memory on their own)
+            constexpr int PARK = 16;
             MgStream<MgSharedSpace> wl;
             wl.begin_rmw(seq_dst);
             const uint32_t ish = 8u * (uint32_t)((uintptr_t)src & 3);
@@ -1420,12 +1421,12 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_corrupt_staged(const __grid_const
             const int NW = (L + 3) >> 2;
             uint32_t carry = iw[0];
 #pragma unroll 1
-            for (int w0 = 0; w0 < NW; w0 += 8) {
-              uint32_t v[8];
+            for (int w0 = 0; w0 < NW; w0 += PARK) {
+              uint32_t v[PARK];
 #pragma unroll
-              for (int i = 0; i < 8; i++) v[i] = (w0 + i < NW) ? iw[w0 + i + 1] : 0u;
+              for (int i = 0; i < PARK; i++) v[i] = (w0 + i < NW) ? iw[w0 + i + 1] : 0u;
 #pragma unroll
-              for (int i = 0; i < 8; i++) {
+              for (int i = 0; i < PARK; i++) {
                 if (w0 + i < NG) wl.put_word(__funnelshift_r(carry, v[i], ish));
                 else if (w0 + i == NG && rem) { const uint32_t ch = __funnelshift_r(carry, v[i], ish); for (int j = 0; j < rem; j++) wl.put((uint8_t)(ch >> (8 * j))); }
                 carry = v[i];

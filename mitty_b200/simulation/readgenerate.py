@@ -94,7 +94,8 @@ def _without_end_crossing_deletions(vl, region, drop):
   return vio.VariantList(vl.pos[keep], vl.op[keep], vl.oplen[keep], ap, ao, rp, ro), int(cross.sum())
 
 
-PIN_REGION_BYTES = 4 << 20   # regions from this size on are fetched into page-locked memory
+PIN_REGION_BYTES = 4 << 20   # regions from this size on may be fetched into page-locked memory ...
+PIN_MIN_REGIONS = 4           # ... by a worker that loads at least this many of them
 
 
 class RegionCache(object):
@@ -113,14 +114,26 @@ class RegionCache(object):
       self.left_copies[r_idx] = self.left_copies.get(r_idx, 0) + 1
     self.budget, self.resident, self.clock, self.used = budget, 0, 0, {}
     self._pin = None          # page-locked landing area for the reference bytes of large regions (see _fetch)
+    self._large_loads = 0
+    self._large_expected = len(set(r for (r, _c) in (expect or {}) if self._span(r) >= PIN_REGION_BYTES)) if expect else None
+
+  def _span(self, r_idx):
+    region = self.vcf_df[r_idx]['region']
+    return region[2] - region[1]
 
   def _fetch(self, region):
-    """The region's reference bytes.  A fetcher with ``into`` (FastaFetcher) fills a page-locked buffer of this
+    """The region's reference bytes.  A fetcher with ``into`` (FastaFetcher) can fill a page-locked buffer of this
     cache: the copy to the device is then one DMA instead of the driver's staged pieces, which queue behind the
-    device-to-host pieces of the units being drained.  (load_region returns after the copy: the buffer is free again.)"""
+    device-to-host pieces of the units being drained.  Locking the buffer costs about as much as three staged copies
+    of a chromosome, so it is only done for a worker that loads many large regions (known from its unit list, or
+    after the third such load).  (load_region returns after the copy: the buffer is free again.)"""
     into = getattr(self.fetch_ref, 'into', None)
     n = region[2] - region[1]
     if into is None or n < PIN_REGION_BYTES:
+      return self.fetch_ref(region)
+    self._large_loads += 1
+    many = self._large_expected >= PIN_MIN_REGIONS if self._large_expected is not None else self._large_loads >= PIN_MIN_REGIONS
+    if not many and self._pin is None:
       return self.fetch_ref(region)
     if self._pin is None or self._pin.size < n:
       self._pin = self.engine.pinned(max([n] + [r['region'][2] - r['region'][1] for r in self.vcf_df]))

@@ -301,6 +301,7 @@ def test_sharded_workers_identical_output(tmp_path, devices, monkeypatch):
   from mitty_b200.engine import device_count
   if devices == [0, 0, 0]:
     monkeypatch.setattr(rg, 'PIN_REGION_BYTES', 1)
+    monkeypatch.setattr(rg, 'PIN_MIN_REGIONS', 1)
   info = H.golden()['fastq']['edge']
   wl = synth.edge_workload()
   fa, vcf, bed = synth.write_workload(wl, str(tmp_path / 'edge'))

@@ -562,7 +562,8 @@ def main():
             'value': value, 'unit': 'pairs/s', 'pairs_per_min': 60.0 * value, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'strong' if args.workload == 'wgs' else 'weak', 'vs_baseline': None,
             'dtype': 'u8', 'data': 'synthetic',
-            'config': dict(config_dict(args), host_binding=('rank 0 on cores {}..{} (GPU-local, NVML)'.format(numa_cores[0], numa_cores[-1]) if numa_cores else 'none')),
+            'config': config_dict(args),          # the same dict on both arms (--impl reference prints it too)
+            'host_binding': 'rank 0 on cores {}..{} (GPU-local, NVML)'.format(numa_cores[0], numa_cores[-1]) if numa_cores else 'none',
             'clocks': clk, 'gpu_launches': prof['total_launches'],
             'roofline': {'bound': 'hbm', 'kernel': 'k_unit_emit', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                          'traffic': traffic, 'peak_source': peak_src, 'launches': prof['emit_launches'],

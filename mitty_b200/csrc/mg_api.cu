@@ -68,6 +68,7 @@ struct Copy {
   int64_t n_nodes = 0;
   int64_t n_exc = 0;
   MgNode *d_nodes = nullptr; uint32_t *d_hap = nullptr; uint32_t *d_blk = nullptr; MgExc *d_exc = nullptr;
+  uint32_t *d_eblk = nullptr;        // block table over d_exc (n_blk + 1 entries), when there are exception runs
   int n_blk = 0; int64_t hap_words = 0, hap_len = 0;
   std::vector<MgSegOut> segs;      // a batch of small regions: one entry per (region, copy)
   std::vector<int64_t> seg_start1;
@@ -287,7 +288,7 @@ void pool_free(mg_ctx *ctx, void *p) {
 }
 
 Region::~Region() { pool_free(owner, d_ref); pool_free(owner, d_exc); }
-Copy::~Copy() { pool_free(owner, d_nodes); pool_free(owner, d_hap); pool_free(owner, d_blk); pool_free(owner, d_exc); }
+Copy::~Copy() { pool_free(owner, d_nodes); pool_free(owner, d_hap); pool_free(owner, d_blk); pool_free(owner, d_exc); pool_free(owner, d_eblk); }
 
 }  // namespace
 
@@ -637,7 +638,12 @@ static int build_segments(mg_ctx *ctx, const uint32_t *d_ref, const MgExc *d_rex
   CU(pool_get(ctx, (void **)&C.d_hap, sizeof(uint32_t) * (C.hap_words + 2 * MG_HAP_PAD)));
   CU(pool_get(ctx, (void **)&C.d_blk, sizeof(uint32_t) * C.n_blk));
   CU(pool_get(ctx, (void **)&C.d_exc, sizeof(MgExc) * std::max<size_t>(1, (size_t)n_exc)));
-  if (n_exc) mg_launch_exc_write(C.d_nodes, W.node_alt, W.sum, (int)max_nodes, sb + o_alt, d_rexc, n_rexc, e_off, C.d_exc, ctx->stream);
+  if (n_exc) {
+    mg_launch_exc_write(C.d_nodes, W.node_alt, W.sum, (int)max_nodes, sb + o_alt, d_rexc, n_rexc, e_off, C.d_exc, ctx->stream);
+    CU(pool_get(ctx, (void **)&C.d_eblk, sizeof(uint32_t) * ((size_t)C.n_blk + 1)));
+    mg_launch_eblk_table(C.d_exc, (int)n_exc, C.d_eblk, C.n_blk + 1, BLK_SHIFT, ctx->stream);
+    ctx->total_launches++;
+  }
   CU(cudaMemsetAsync(C.d_hap, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
   CU(cudaMemsetAsync(C.d_hap + MG_HAP_PAD + C.hap_words, 0, sizeof(uint32_t) * MG_HAP_PAD, ctx->stream));
   mg_launch_blk_table(C.d_nodes, (int)nn, C.d_blk, C.n_blk, BLK_SHIFT, ctx->stream);
@@ -742,7 +748,7 @@ static int fill_unit_params(mg_ctx *ctx, const mg_unit_desc *d, MgUnitParams &P,
     P.hap = C.d_hap + MG_HAP_PAD; P.hap_len = (uint32_t)(C.p_max - C.p_min); P.p_min = C.p_min;
     P.nodes = C.d_nodes; P.n_nodes = (int)C.n_nodes;
     P.blk = C.d_blk; P.blk_shift = BLK_SHIFT; P.n_blk = C.n_blk;
-    P.exc = C.d_exc; P.n_exc = (int)C.n_exc;
+    P.exc = C.d_exc; P.n_exc = (int)C.n_exc; P.eblk = C.d_eblk;
   }
   P.cum_tlen = ctx->m_tlen.as<double>(); P.n_tlen = ctx->n_tlen; P.rlen = ctx->rlen;
   P.tlen_alias = ctx->has_tlen_alias ? ctx->m_tlen_alias.as<uint32_t>() : nullptr;
@@ -1283,7 +1289,7 @@ int mg_batch_generate(mg_ctx *ctx, int64_t batch_id, int64_t n_units, const int3
   P.hap = C.d_hap + MG_HAP_PAD; P.hap_len = (uint32_t)C.hap_len; P.p_min = 0;
   P.nodes = C.d_nodes; P.n_nodes = (int)C.n_nodes;
   P.blk = C.d_blk; P.blk_shift = BLK_SHIFT; P.n_blk = C.n_blk;
-  P.exc = C.d_exc; P.n_exc = (int)C.n_exc;
+  P.exc = C.d_exc; P.n_exc = (int)C.n_exc; P.eblk = C.d_eblk;
   P.cum_tlen = ctx->m_tlen.as<double>(); P.n_tlen = ctx->n_tlen; P.rlen = L;
   P.tlen_alias = ctx->has_tlen_alias ? ctx->m_tlen_alias.as<uint32_t>() : nullptr;
   P.mode = mode;

@@ -758,6 +758,32 @@ MG_HD int mg_exc_first(EP exc, int n_exc, uint32_t x) {
   return lo;
 }
 
+// Exception runs with a block table over them: eblk[b] = the first run that ends beyond haplotype position
+// b << shift (n_blk + 1 entries).  The first run that can touch a read starting at x then lies in
+// [eblk[x >> shift], eblk[(x >> shift) + 1]] -- two adjacent table entries instead of a binary search over every
+// run of the chromosome (39 N runs on chr1: six dependent loads per read, a tenth of k_unit_plan's instructions;
+// ~10^6 case runs on a soft-masked one: twenty).  blk == nullptr: plain binary search.
+struct MgExcView {
+  const MgExc *p; const uint32_t *blk; int shift, n_blk;
+  MG_HD const MgExc &operator[](int k) const { return p[k]; }
+};
+
+MG_HD int mg_exc_first(MgExcView exc, int n_exc, uint32_t x) {
+  int lo = 0, hi = n_exc;
+  if (exc.blk) {
+    uint32_t b = x >> exc.shift;
+    if ((int)b > exc.n_blk - 1) b = (uint32_t)(exc.n_blk - 1);
+    lo = (int)exc.blk[b]; hi = (int)exc.blk[b + 1];
+    if (hi > n_exc) hi = n_exc;
+    if (lo > hi) lo = hi;
+  }
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((uint64_t)exc.p[mid].start + exc.p[mid].len <= (uint64_t)x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // number of 'N' in the read (seq.count('N'), readgenerate.py:204); touch = the read overlaps an
 // exception run of any kind (its bases need patching after the word-stream emission)
 template <class EP>

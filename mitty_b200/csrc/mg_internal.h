@@ -42,6 +42,7 @@ struct MgUnitParams {
   const MgNode *nodes; int n_nodes;
   const uint32_t *blk; int blk_shift; int n_blk;
   const MgExc *exc; int n_exc;
+  const uint32_t *eblk;      // block table over the exception runs (MgExcView), or null
   // read model
   const double *cum_tlen; int n_tlen; int rlen;
   const uint32_t *tlen_alias; // PHILOX: MG_TLEN_K-entry alias table (prob22 << 10 | alias) or null
@@ -152,6 +153,7 @@ void mg_launch_hap_build(const uint32_t *ref, const uint8_t *alt_pool, const MgN
                          int n_nodes, const uint32_t *blk, int blk_shift, int n_blk, uint32_t hap_len, uint32_t *hap, int64_t hap_words,
                          cudaStream_t st);   // after mg_launch_blk_table
 void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st);
+void mg_launch_eblk_table(const MgExc *exc, int n_exc, uint32_t *eblk, int n_entries, int blk_shift, cudaStream_t st);   // n_entries = n_blk + 1
 void mg_launch_gap_scan(uint32_t n, double p, uint32_t k0, uint32_t k1, uint32_t *ts_sorted, unsigned long long *partial,
                         cudaStream_t st);
 int mg_unit_grid(int L, int corrupt, int stage_cap, int *smem_bytes);

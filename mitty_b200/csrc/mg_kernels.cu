@@ -432,6 +432,23 @@ __global__ void __launch_bounds__(256) k_blk_table(const MgNode *__restrict__ no
   blk[b] = (uint32_t)lo;
 }
 
+// block table over the exception runs (MgExcView): eblk[b] = first run that ends beyond b << shift
+__global__ void __launch_bounds__(256) k_eblk_table(const MgExc *__restrict__ exc, int n_exc, uint32_t *__restrict__ eblk, int n_entries, int blk_shift) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_entries) return;
+  const uint64_t x = (uint64_t)b << blk_shift;
+  int lo = 0, hi = n_exc;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((uint64_t)exc[mid].start + exc[mid].len <= x) lo = mid + 1; else hi = mid;
+  }
+  eblk[b] = (uint32_t)lo;
+}
+
+void mg_launch_eblk_table(const MgExc *exc, int n_exc, uint32_t *eblk, int n_entries, int blk_shift, cudaStream_t st) {
+  k_eblk_table<<<(n_entries + 255) / 256, 256, 0, st>>>(exc, n_exc, eblk, n_entries, blk_shift);
+}
+
 void mg_launch_blk_table(const MgNode *nodes, int n_nodes, uint32_t *blk, int n_blk, int blk_shift, cudaStream_t st) {
   k_blk_table<<<(n_blk + 255) / 256, 256, 0, st>>>(nodes, n_nodes, blk, n_blk, blk_shift);
 }
@@ -668,7 +685,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_unit_plan(const __grid_constan
         xa = (uint32_t)c.ts_rel; xb = (uint32_t)(c.te_rel - L);                 // illumina.py:95-96
         k2 = true;
         if (P.n_exc) {                                                           // readgenerate.py:204
-          const int na = mg_count_N(P.exc, P.n_exc, xa, L, ta), nb = mg_count_N(P.exc, P.n_exc, xb, L, tb);
+          const MgExcView ev = {P.exc, P.eblk, P.blk_shift, P.n_blk};
+          const int na = mg_count_N(ev, P.n_exc, xa, L, ta), nb = mg_count_N(ev, P.n_exc, xb, L, tb);
           k2 = na <= 2 && nb <= 2;
         }
         if (k2) {
@@ -797,7 +815,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_batch_plan(const __grid_consta
         xa = U.x0 + (uint32_t)ts_rel; xb = U.x0 + (uint32_t)(te_rel - L);       // illumina.py:95-96, in the concatenated haplotype
         k2 = true;
         if (P.n_exc) {                                                           // readgenerate.py:204
-          const int na = mg_count_N(P.exc, P.n_exc, xa, L, ta), nb = mg_count_N(P.exc, P.n_exc, xb, L, tb);
+          const MgExcView ev = {P.exc, P.eblk, P.blk_shift, P.n_blk};
+          const int na = mg_count_N(ev, P.n_exc, xa, L, ta), nb = mg_count_N(ev, P.n_exc, xb, L, tb);
           k2 = na <= 2 && nb <= 2;
         }
         if (k2) {
@@ -865,12 +884,12 @@ __device__ __noinline__ void emit_oversize(uint8_t *dst, uint32_t qlen, const Mg
   if constexpr (CORRUPT) {
     mg_emit_frame_qname<MgGenericSpace>(dst, P.qn, str, (uint32_t)cnt, P.nodes, first, second, L);
     mg_emit_frame_seps<MgGenericSpace>(dst, qlen, L);
-    mg_emit_seq_corrupt<MgGenericSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, P.n_exc, cor, (uint32_t)(cnt - 1), (uint32_t)f, (uint32_t)f);
+    mg_emit_seq_corrupt<MgGenericSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, MgExcView{P.exc, P.eblk, P.blk_shift, P.n_blk}, P.n_exc, cor, (uint32_t)(cnt - 1), (uint32_t)f, (uint32_t)f);
   } else {
     MgStream<MgGenericSpace> ws;
     mg_emit_record<MgGenericSpace>(ws, dst, P.qn, str, (uint32_t)cnt, P.nodes, first, second, S);
     ws.end();
-    if (P.n_exc) mg_patch_exc<MgGenericSpace>(dst + (qlen + 1), P.exc, P.n_exc, S.hap, S.x, L, S.strand);
+    if (P.n_exc) mg_patch_exc<MgGenericSpace>(dst + (qlen + 1), MgExcView{P.exc, P.eblk, P.blk_shift, P.n_blk}, P.n_exc, S.hap, S.x, L, S.strand);
   }
 }
 
@@ -893,6 +912,7 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
   uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   asm volatile("" : "+r"(stage_s));
   const int L = P.rlen;
+  const MgExcView ev = {P.exc, P.eblk, P.blk_shift, P.n_blk};
   const unsigned long long n_kept = BATCH ? (unsigned long long)P.kept_base[P.n_bunits] : P.totals[1];
   const unsigned long long n_bytes = BATCH ? (unsigned long long)P.byte_base[P.n_bunits] : P.totals[2];
   if (n_bytes > P.cap) { if (t == 0 && blockIdx.x == 0) P.totals[3] = 1ull; return; }   // host regrows and relaunches
@@ -978,9 +998,9 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
               if constexpr (BATCH) {
                 MgCorruptCtx cor = P.cor;
                 cor.k1 = U->seed ^ 0x636f7231u;              // the unit's corruption key, as mg_unit_generate derives it
-                mg_emit_seq_corrupt<MgSharedSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, ne_f, cor, (uint32_t)rank, (uint32_t)f, (uint32_t)f);
+                mg_emit_seq_corrupt<MgSharedSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, ev, ne_f, cor, (uint32_t)rank, (uint32_t)f, (uint32_t)f);
               } else {
-                mg_emit_seq_corrupt<MgSharedSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, P.exc, ne_f, P.cor, (uint32_t)rank, (uint32_t)f, (uint32_t)f);
+                mg_emit_seq_corrupt<MgSharedSpace, CORRUPT == 2>(dst + qlen + 1, dst + qlen + 1 + L + 3, S, ev, ne_f, P.cor, (uint32_t)rank, (uint32_t)f, (uint32_t)f);
               }
             }
           } else {
@@ -993,10 +1013,10 @@ __global__ void __launch_bounds__(MG_CTA, 4) k_unit_emit(const __grid_constant__
               __syncwarp();
               if (mine) {
                 ws.end();
-                if (ne_f) mg_patch_exc<MgSharedSpace>(dst + (qlen + 1), P.exc, ne_f, S.hap, S.x, L, S.strand);
+                if (ne_f) mg_patch_exc<MgSharedSpace>(dst + (qlen + 1), ev, ne_f, S.hap, S.x, L, S.strand);
               }
             } else if (mine) {
-              mg_rewrite_seq<MgSharedSpace>(dst + qlen + 1, S, P.exc, ne_f);
+              mg_rewrite_seq<MgSharedSpace>(dst + qlen + 1, S, ev, ne_f);
             }
           }
         } else if (f >= 0 && mine) {

@@ -105,7 +105,7 @@ def _open_bytes(fname):
 
 class _Contig(object):
   """Records of one contig as arrays over the file's bytes (no per-record Python objects)."""
-  __slots__ = ('pos', 'reflen', 'rs', 're', 'as_', 'ae', 'gt', 'ploidy', 'exotic', 'slow', 'ls', 'le', 'f9e', 'ss', 'se')
+  __slots__ = ('pos', 'reflen', 'rs', 're', 'as_', 'ae', 'gt', 'ploidy', 'exotic', 'slow', 'ls', 'le', 'f9e', 'ss', 'se', 'p0', 'is_sorted', 'max_reflen')
 
   def __init__(self, pos, rs, re_, as_, ae, gt, ploidy, exotic, slow, lines=None):
     self.pos, self.rs, self.re, self.as_, self.ae = pos, rs, re_, as_, ae
@@ -113,6 +113,14 @@ class _Contig(object):
     self.ls, self.le, self.f9e, self.ss, self.se = lines if lines is not None else (None,) * 5
     self.reflen = re_ - rs
     self.gt, self.ploidy, self.exotic, self.slow = gt, ploidy, exotic, slow
+    self.p0 = None                                    # the fetch index (0-based starts, sortedness, longest REF), made on first use
+
+  def fetch_index(self):
+    if self.p0 is None:
+      self.p0 = self.pos - 1
+      self.is_sorted = bool(self.p0.size < 2 or (self.p0[1:] >= self.p0[:-1]).all())
+      self.max_reflen = int(self.reflen.max()) if self.reflen.size else 1
+    return self.p0
 
   def merged(self, o):
     n = self.pos.size
@@ -302,7 +310,15 @@ class VcfTable(object):
           contig, ', '.join(sorted(set(self.contigs) | self.header_contigs)[:8]) or 'no contigs at all'))
       return contig, np.zeros(0, dtype=np.int64)
     c = self.contigs[contig]
-    p0 = c.pos - 1
+    p0 = c.fetch_index()
+    if c.is_sorted:
+      # records sorted by POS (every indexed VCF): the overlapping ones lie in a window found by two binary searches
+      # -- an exome BED of 200 000 targets over a 4 M-record call set would otherwise scan 10^12 elements
+      lo = int(np.searchsorted(p0, start - c.max_reflen + 1, side='left'))
+      hi = int(np.searchsorted(p0, stop, side='left'))
+      if hi <= lo:
+        return contig, np.zeros(0, dtype=np.int64)
+      return contig, lo + np.flatnonzero(p0[lo:hi] + c.reflen[lo:hi] > start)
     return contig, np.flatnonzero((p0 < stop) & (p0 + c.reflen > start))
 
   def gt_of(self, contig, i):

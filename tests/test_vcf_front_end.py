@@ -277,3 +277,30 @@ def test_vcf_parsed_in_pieces_equals_one_pass(tmp_path, monkeypatch):
     assert x['region'] == y['region'] and len(x['v']) == len(y['v'])
     for vx, vy in zip(x['v'], y['v']):
       assert np.array_equal(vx.pos, vy.pos) and np.array_equal(vx.op, vy.op) and np.array_equal(vx.alt_pool, vy.alt_pool)
+
+
+def test_windowed_fetch_equals_the_full_scan(tmp_path):
+  """VcfTable.fetch finds the records overlapping a region (htslib rule: a long REF that starts before the region
+  still overlaps it) with two binary searches when the contig is sorted; same indices as the plain scan, also for
+  an unsorted contig (which takes the scan)."""
+  rs = np.random.RandomState(8)
+  for sorted_ in (True, False):
+    pos = rs.randint(1, 50000, size=3000)
+    if sorted_:
+      pos = np.sort(pos)
+    reflen = np.where(rs.rand(pos.size) < 0.1, rs.randint(2, 400, size=pos.size), 1)
+    lines = ['##fileformat=VCFv4.2', '#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS']
+    for p, n in zip(pos.tolist(), reflen.tolist()):
+      lines.append('c\t{}\t.\t{}\t{}\t.\tPASS\t.\tGT\t0|1'.format(p, 'A' * n, 'A' if n > 1 else 'C'))
+    path = str(tmp_path / ('s%d.vcf' % sorted_))
+    with open(path, 'w') as fp:
+      fp.write('\n'.join(lines) + '\n')
+    tb = vcfio.VcfTable(path, 'S')
+    c = tb.contigs['c']
+    assert np.array_equal(c.pos, pos)
+    for _ in range(300):
+      a = int(rs.randint(0, 51000)); b = a + int(rs.randint(0, 3000))
+      _, idx = tb.fetch('c', a, b)
+      want = np.flatnonzero((pos - 1 < b) & (pos - 1 + reflen > a))
+      assert np.array_equal(idx, want), (sorted_, a, b)
+    assert c.is_sorted == sorted_

@@ -372,11 +372,15 @@ def _parse_copy_records(table, contig, idx, cpy):
                      np.frombuffer(b''.join(refs), dtype=np.uint8), ref_off)
 
 
+_EMPTY_VL = VariantList([], np.zeros(0, np.uint8), [], np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.uint8), np.zeros(1, np.int64))
+for _a in (_EMPTY_VL.pos, _EMPTY_VL.op, _EMPTY_VL.oplen, _EMPTY_VL.alt_pool, _EMPTY_VL.alt_off, _EMPTY_VL.ref_pool, _EMPTY_VL.ref_off):
+  _a.setflags(write=False)
+
+
 def parse_copy(table, contig, idx, cpy):
   """vcfio.parse over the records ``idx`` for copy ``cpy`` -> VariantList (vcfio.py:105-126)."""
   if idx.size == 0:
-    return VariantList([], np.zeros(0, np.uint8), [], np.zeros(0, np.uint8), np.zeros(1, np.int64),
-                       np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    return _EMPTY_VL                                       # shared: VariantLists are read-only everywhere
   c = table.contigs[contig]
   if c.exotic[idx].any():
     return _parse_copy_records(table, contig, idx, cpy)
